@@ -1,0 +1,249 @@
+/*
+ * b200gym.h -- C ABI of libb200gym.so: the B200-native replacement for the part of the
+ * reference that lives in the closed Isaac Gym binary (gymapi + PhysX) on the hot path
+ * `VecTask.step` (reference: isaacgymenvs/tasks/base/vec_task.py:360-408).
+ *
+ * Every entry point cites the Isaac Gym call (and the reference call site) it replaces.
+ * Conventions:
+ *   - plain C types only: pointers, sizes, PODs. No torch / C++ types cross this boundary.
+ *   - every call returns int: 0 = OK, <0 = error code; b2g_last_error() gives the message.
+ *   - the sim owns all device memory; pointers returned by b2g_sim_tensor() stay valid until
+ *     b2g_sim_destroy(). Python wraps them as non-owning torch tensors through DLPack.
+ *   - all device work is enqueued on the caller-supplied cudaStream_t (passed as void*); the
+ *     library never synchronises except in the *_host convenience calls, which say so.
+ *   - one thread drives one sim (same as the reference's process-global singleton,
+ *     vec_task.py:55-64). Not thread-safe.
+ *   - there is NO CPU fallback: if no CUDA device is usable b2g_sim_create fails with
+ *     B2G_ERR_CUDA.
+ */
+#ifndef B200GYM_H
+#define B200GYM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2G_ABI_VERSION 1
+
+#define B2G_MAX_DOF 24
+#define B2G_MAX_LINKS (B2G_MAX_DOF + 1)
+#define B2G_MAX_BODIES 32
+#define B2G_MAX_CHAINS 8
+#define B2G_MAX_CHAIN_LEN 6
+#define B2G_MAX_CPTS 128
+#define B2G_MAX_CONTACTS_PER_CHAIN 4
+
+enum b2g_status {
+    B2G_OK = 0,
+    B2G_ERR_ARG = -1,      /* bad argument / bad handle              */
+    B2G_ERR_CUDA = -2,     /* CUDA runtime error (message has detail) */
+    B2G_ERR_STATE = -3,    /* call out of order (e.g. step before prepare) */
+    B2G_ERR_UNSUPPORTED = -4
+};
+
+/* Isaac Gym gymapi.DOF_MODE_* (reference: tasks/anymal.py:201, tasks/cartpole.py:110-111) */
+enum b2g_drive_mode { B2G_DOF_MODE_NONE = 0, B2G_DOF_MODE_POS = 1, B2G_DOF_MODE_VEL = 2, B2G_DOF_MODE_EFFORT = 4 };
+
+enum b2g_joint_type { B2G_JOINT_REVOLUTE = 0, B2G_JOINT_PRISMATIC = 1 };
+
+/*
+ * Compiled articulation ("asset"): one root link + n_chains serial chains (star topology).
+ * Replaces the result of gym.load_asset (reference: tasks/anymal.py:183). Produced by the Python
+ * model compiler (isaacgymenv_b200/model/urdf.py). Link 0 is the root; link 1+d is the child link of
+ * DOF d. DOFs are numbered chain after chain, which is Isaac Gym's depth-first order.
+ * Inertia is about the link's centre of mass in link axes: xx, yy, zz, xy, xz, yz.
+ */
+typedef struct b2g_model {
+    int32_t fixed_base;
+    int32_t n_dof;
+    int32_t n_bodies;
+    int32_t n_chains;
+    int32_t n_cpts;
+    int32_t chain_start[B2G_MAX_CHAINS];
+    int32_t chain_len[B2G_MAX_CHAINS];
+    float link_mass[B2G_MAX_LINKS];
+    float link_com[B2G_MAX_LINKS][3];
+    float link_inertia[B2G_MAX_LINKS][6];
+    int32_t joint_type[B2G_MAX_DOF];
+    float joint_pos[B2G_MAX_DOF][3];   /* joint frame origin in the parent link frame          */
+    float joint_quat[B2G_MAX_DOF][4];  /* joint frame rotation in the parent frame, xyzw, q = 0 */
+    float joint_axis[B2G_MAX_DOF][3];  /* unit axis in the child (= joint) frame               */
+    float lower[B2G_MAX_DOF];          /* -inf / +inf when the joint has no limits              */
+    float upper[B2G_MAX_DOF];
+    float effort[B2G_MAX_DOF];
+    float vel_limit[B2G_MAX_DOF];
+    float armature[B2G_MAX_DOF];
+    /* API bodies = rows of the rigid-body-state and net-contact-force tensors */
+    int32_t body_link[B2G_MAX_BODIES];
+    float body_pos[B2G_MAX_BODIES][3];
+    float body_quat[B2G_MAX_BODIES][4];
+    /* contact spheres; cp_chain = the chain (lane) that owns the candidate in the solver */
+    int32_t cp_link[B2G_MAX_CPTS];
+    int32_t cp_body[B2G_MAX_CPTS];
+    int32_t cp_chain[B2G_MAX_CPTS];
+    float cp_pos[B2G_MAX_CPTS][3];
+    float cp_radius[B2G_MAX_CPTS];
+} b2g_model;
+
+/* gymapi.SimParams + PlaneParams subset (reference: vec_task.py:514-562, cfg/task/Anymal.yaml:81-100,
+ * tasks/anymal.py:159-164). */
+typedef struct b2g_sim_params {
+    float dt;
+    int32_t substeps;
+    float gravity[3];
+    int32_t num_position_iterations;
+    int32_t num_velocity_iterations;
+    float contact_offset;
+    float rest_offset;
+    float bounce_threshold_velocity;
+    float max_depenetration_velocity;
+    float plane_static_friction;
+    float plane_dynamic_friction;
+    float plane_restitution;
+    int32_t has_ground;               /* add_ground was called */
+} b2g_sim_params;
+
+/* per-DOF drive properties, identical for every env (reference: tasks/anymal.py:199-203,214) */
+typedef struct b2g_dof_props {
+    int32_t drive_mode[B2G_MAX_DOF];
+    float stiffness[B2G_MAX_DOF];
+    float damping[B2G_MAX_DOF];
+    float effort[B2G_MAX_DOF];
+    float lower[B2G_MAX_DOF];
+    float upper[B2G_MAX_DOF];
+    float velocity[B2G_MAX_DOF];
+} b2g_dof_props;
+
+/* heightfield terrain: int16 samples, row index along +x, column along +y
+ * (reference: tasks/anymal_terrain.py:196-209,515-538,549-576). height = raw * vertical_scale;
+ * world x of row i = origin_x + i * horizontal_scale. */
+typedef struct b2g_heightfield {
+    int32_t rows, cols;
+    float horizontal_scale, vertical_scale;
+    float origin_x, origin_y;
+    float friction, restitution;
+} b2g_heightfield;
+
+/* tensors the sim owns; kind selects one (gym.acquire_*_tensor, reference: tasks/anymal.py:110-113,
+ * tasks/useful_hound.py:440-455) */
+enum b2g_tensor_kind {
+    B2G_T_ROOT_STATE = 0,       /* (N,13) f32  pos3 quat4(xyzw) linvel3 angvel3, world      */
+    B2G_T_DOF_STATE = 1,        /* (N*nd,2) f32 pos, vel                                     */
+    B2G_T_NET_CONTACT = 2,      /* (N*nb,3) f32 world                                        */
+    B2G_T_DOF_FORCE = 3,        /* (N*nd) f32                                                */
+    B2G_T_RIGID_BODY_STATE = 4, /* (N*nb,13) f32                                             */
+    B2G_T_DOF_TARGET = 5,       /* (N*nd) f32 position/velocity targets                      */
+    B2G_T_DOF_ACTUATION = 6,    /* (N*nd) f32 efforts                                        */
+    B2G_T_JACOBIAN = 7,         /* (N,nb,6,nd+6 or nd) f32                                   */
+    B2G_T_MASS_MATRIX = 8,      /* (N,nd,nd) f32 (joint block, Isaac Gym convention)         */
+    B2G_T_FRICTION = 9,         /* (N) f32 per-env shape friction coefficient                */
+    B2G_T_ENV_ORIGIN = 10,      /* (N,3) f32 env origin offsets (create_env grid)            */
+    B2G_T_COUNT
+};
+
+typedef struct b2g_tensor_desc {
+    void* data;          /* device pointer */
+    int32_t dtype;       /* 0 = f32, 1 = i32, 2 = i64, 3 = u8, 4 = i16 */
+    int32_t ndim;
+    int64_t shape[4];
+    int32_t device_id;
+} b2g_tensor_desc;
+
+typedef struct b2g_sim b2g_sim;
+
+/* ---- lifecycle: gymapi.acquire_gym / gym.create_sim / prepare_sim (vec_task.py:247,63,262) ---- */
+int b2g_abi_version(void);
+const char* b2g_last_error(void);
+int b2g_sim_create(int device_id, const b2g_sim_params* params, b2g_sim** out);
+int b2g_sim_destroy(b2g_sim* sim);
+int b2g_sim_set_params(b2g_sim* sim, const b2g_sim_params* params);       /* gym.set_sim_params */
+int b2g_sim_get_params(const b2g_sim* sim, b2g_sim_params* out);          /* gym.get_sim_params */
+/* gym.add_ground (tasks/anymal.py:159-164): sets has_ground + friction in the params */
+int b2g_sim_add_ground(b2g_sim* sim, float static_friction, float dynamic_friction, float restitution);
+/* gym.add_triangle_mesh for a gridded terrain (tasks/anymal_terrain.py:196-209): host int16 samples */
+int b2g_sim_add_heightfield(b2g_sim* sim, const b2g_heightfield* hf, const int16_t* samples_host);
+/* gym.load_asset + N x (create_env, create_actor, set_actor_dof_properties) (tasks/anymal.py:205-216).
+ * root_pose7 = start pose (pos3, quat xyzw) given to create_actor; env_spacing/num_per_row = create_env grid. */
+int b2g_sim_add_articulation(b2g_sim* sim, const b2g_model* model, const b2g_dof_props* props, int n_envs,
+                             const float* root_pose7, float env_spacing, int num_per_row);
+int b2g_sim_prepare(b2g_sim* sim);                                         /* gym.prepare_sim */
+int b2g_sim_set_dof_props(b2g_sim* sim, const b2g_dof_props* props);       /* gym.set_actor_dof_properties */
+
+/* ---- tensors: gym.acquire_* (tasks/anymal.py:110-113) ---- */
+int b2g_sim_tensor(b2g_sim* sim, int kind, b2g_tensor_desc* out);
+
+/* ---- stepping: gym.simulate (vec_task.py:382) = `substeps` sub-steps of dt/substeps ---- */
+int b2g_sim_simulate(b2g_sim* sim, void* stream);
+/* gym.refresh_rigid_body_state_tensor / refresh_jacobian_tensors / refresh_mass_matrix_tensors
+ * (tasks/useful_hound.py:729-732). Root/DOF/contact/DOF-force tensors alias live sim state, so
+ * their refresh is a no-op kept for API compatibility. */
+int b2g_sim_refresh(b2g_sim* sim, int kind, void* stream);
+/* gym.set_*_tensor_indexed (tasks/anymal.py:291-297): copy rows idx[0..n) of `src` (full-size device
+ * tensor, same layout as kind) into the sim tensor. src == the sim's own tensor is a no-op. */
+int b2g_sim_set_indexed(b2g_sim* sim, int kind, const void* src_dev, const int32_t* idx_dev, int n, void* stream);
+/* gym.set_dof_position_target_tensor / set_dof_actuation_force_tensor / set_actor_root_state_tensor /
+ * set_dof_state_tensor (tasks/anymal.py:229, tasks/anymal_terrain.py:446,439): full copy */
+int b2g_sim_set_tensor(b2g_sim* sim, int kind, const void* src_dev, void* stream);
+
+/* forward dynamics probe used by the parity tests: qdd (N,nd) and root spatial acceleration (N,6:
+ * angular3, linear3 of the root origin, world) for the current state and DOF_ACTUATION efforts, no
+ * contact, no drives. */
+int b2g_sim_forward_dynamics(b2g_sim* sim, float* qdd_dev, float* root_acc_dev, void* stream);
+
+/* ---- fused task steps: pre_physics_step + simulate x k + post_physics_step in one launch ---- */
+
+/* Anymal / Hound flat task (reference: tasks/anymal.py:226-304,311-386; tasks/hound.py same lines) */
+typedef struct b2g_anymal_cfg {
+    float lin_vel_scale, ang_vel_scale, dof_pos_scale, dof_vel_scale, action_scale;
+    float rew_lin_vel_xy, rew_ang_vel_z, rew_torque;   /* already multiplied by dt (anymal.py:99-100) */
+    float clip_obs, clip_actions;
+    float cmd_x[2], cmd_y[2], cmd_yaw[2];
+    float default_dof_pos[B2G_MAX_DOF];
+    float init_root[13];
+    int32_t base_body;
+    int32_t n_knee;
+    int32_t knee_bodies[8];
+    int64_t max_episode_length;
+    uint64_t seed;
+} b2g_anymal_cfg;
+
+typedef struct b2g_task_buffers {
+    float* obs;          /* (N,num_obs) unclamped, the task's obs_buf                       */
+    float* obs_clamped;  /* (N,num_obs) clamp(obs, +-clip_obs): what step() returns          */
+    float* rew;          /* (N)                                                              */
+    int64_t* reset;      /* (N) int64 (flat tasks) -- vec_task.py:316                        */
+    int64_t* progress;   /* (N) int64                                                        */
+    int64_t* timeout;    /* (N) int64 0/1                                                    */
+    float* commands;     /* (N,3|4)                                                          */
+    float* actions;      /* (N,na) last clamped actions (task's self.actions)                */
+    const float* rand_override; /* optional (N,n_rand) uniforms in [0,1) replacing Philox (tests) */
+} b2g_task_buffers;
+
+int b2g_task_anymal_create(b2g_sim* sim, const b2g_anymal_cfg* cfg);
+/* allocate-and-describe the task buffers the sim owns (obs_buf, rew_buf, reset_buf, ...) */
+enum b2g_task_tensor_kind {
+    B2G_TT_OBS = 0, B2G_TT_OBS_CLAMPED = 1, B2G_TT_REW = 2, B2G_TT_RESET = 3, B2G_TT_PROGRESS = 4,
+    B2G_TT_TIMEOUT = 5, B2G_TT_COMMANDS = 6, B2G_TT_ACTIONS = 7, B2G_TT_RAND_OVERRIDE = 8, B2G_TT_COUNT
+};
+int b2g_task_tensor(b2g_sim* sim, int kind, b2g_tensor_desc* out);
+/* reset_idx(all envs) as in the task constructor (tasks/anymal.py:146) + first observations */
+int b2g_task_anymal_reset_all(b2g_sim* sim, void* stream);
+/* VecTask.step for the flat task: one kernel launch. actions_dev: (N,12) f32 */
+int b2g_task_anymal_step(b2g_sim* sim, const float* actions_dev, void* stream);
+/* use_rand_override != 0: reset draws come from the RAND_OVERRIDE tensor instead of Philox */
+int b2g_task_set_rand_override(b2g_sim* sim, int use_rand_override);
+
+/* host-buffer convenience used by the end-to-end benchmark and non-torch callers: copies actions
+ * H2D, steps, copies obs/rew/reset/timeout D2H, synchronises the stream. */
+int b2g_task_anymal_step_host(b2g_sim* sim, const float* actions_host, float* obs_host, float* rew_host,
+                              int64_t* reset_host, int64_t* timeout_host, void* stream);
+
+/* number of kernels this library has launched since creation (bench.py's gpu_launches) */
+int64_t b2g_sim_launch_count(const b2g_sim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GYM_H */

@@ -1,0 +1,699 @@
+/*
+ * ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked, imported or executed by the product path
+ * (isaacgymenv_b200/ + libb200gym.so).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may use it, as the checker or the timed CPU baseline.
+ *
+ * CPU restatement (scalar C, float64 and float32 instantiations) of the physics that the reference
+ * delegates to Isaac Gym / PhysX behind `gym.simulate` (reference call sites:
+ * isaacgymenvs/tasks/base/vec_task.py:379-382, tasks/anymal_terrain.py:443-451; solver settings
+ * cfg/task/Anymal.yaml:81-100; drives tasks/anymal.py:199-203).
+ *
+ * PARITY UNPINNED for dynamics: Isaac Gym Preview 4 (closed binary, un-vendored, un-pinned in
+ * setup.py:15-25) is absent, and the reference holds no test or golden vector that touches the
+ * simulator.  This file restates the *published* algorithms instead:
+ *   - Featherstone articulated-body algorithm (forward dynamics), composite-rigid-body algorithm
+ *     (mass matrix) and recursive Newton-Euler (bias forces), floating or fixed base
+ *     [R. Featherstone, Rigid Body Dynamics Algorithms, 2008, ch. 5-7, 9];
+ *   - implicit PD position drives folded into the joint-space inertia (h*Kd + h^2*Kp on the diagonal),
+ *     which is how an implicit spring/damper drive enters a velocity-level articulation solver;
+ *   - hard contact at the velocity level: projected Gauss-Seidel over contact points with Coulomb
+ *     friction (cone projection), impulses propagated through the articulated inertias, position
+ *     iterations with penetration bias followed by velocity iterations without it (PGS/TGS-style
+ *     split named by `num_position_iterations` / `num_velocity_iterations`);
+ *   - semi-implicit Euler integration per sub-step.
+ * It is self-validated by invariants in tests/ (ABA == CRBA/RNEA solve, kinetic energy against an
+ * independent finite-difference FK, momentum and energy conservation), not by PhysX output.
+ *
+ * This header is a template: include it with ORC_REAL and ORC_SUF defined.
+ */
+
+#define ORC_CAT2(a, b) a##b
+#define ORC_CAT(a, b) ORC_CAT2(a, b)
+#define FN(name) ORC_CAT(name, ORC_SUF)
+#define R ORC_REAL
+
+typedef struct FN(orc_kin) {
+    R rot[B2G_MAX_LINKS][9];      /* link rotation, world axes                     */
+    R pos[B2G_MAX_LINKS][3];      /* link origin relative to the root origin       */
+    R S[B2G_MAX_DOF][6];          /* joint motion subspace (angular, linear at O)  */
+    R vel[B2G_MAX_LINKS][6];      /* link spatial velocity                          */
+    R cb[B2G_MAX_DOF][6];         /* velocity-product acceleration v x (S qd)       */
+    R I[B2G_MAX_LINKS][36];       /* link spatial inertia about O                   */
+    R IA[B2G_MAX_LINKS][36];      /* articulated inertia                            */
+    R pA[B2G_MAX_LINKS][6];       /* articulated bias force                         */
+    R U[B2G_MAX_DOF][6];
+    R D[B2G_MAX_DOF];
+    R u[B2G_MAX_DOF];
+    R IA0inv[36];
+} FN(orc_kin);
+
+static void FN(cross3)(const R* a, const R* b, R* o) {
+    R x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static void FN(matvec3)(const R* m, const R* v, R* o) {
+    R x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+    R y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+    R z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static void FN(matmul3)(const R* a, const R* b, R* o) {
+    R t[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) t[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+    for (int i = 0; i < 9; i++) o[i] = t[i];
+}
+static void FN(quat2mat)(const R* q, R* m) {
+    R x = q[0], y = q[1], z = q[2], w = q[3];
+    m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - z * w); m[2] = 2 * (x * z + y * w);
+    m[3] = 2 * (x * y + z * w); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - x * w);
+    m[6] = 2 * (x * z - y * w); m[7] = 2 * (y * z + x * w); m[8] = 1 - 2 * (x * x + y * y);
+}
+static void FN(axisangle2mat)(const R* a, R ang, R* m) {
+    R c = (R)cos((double)ang), s = (R)sin((double)ang), t = 1 - c;
+    m[0] = t * a[0] * a[0] + c; m[1] = t * a[0] * a[1] - s * a[2]; m[2] = t * a[0] * a[2] + s * a[1];
+    m[3] = t * a[0] * a[1] + s * a[2]; m[4] = t * a[1] * a[1] + c; m[5] = t * a[1] * a[2] - s * a[0];
+    m[6] = t * a[0] * a[2] - s * a[1]; m[7] = t * a[1] * a[2] + s * a[0]; m[8] = t * a[2] * a[2] + c;
+}
+/* motion cross product v x m */
+static void FN(crm)(const R* v, const R* m, R* o) {
+    R a[3], b[3], c[3];
+    FN(cross3)(v, m, a); FN(cross3)(v, m + 3, b); FN(cross3)(v + 3, m, c);
+    o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = b[0] + c[0]; o[4] = b[1] + c[1]; o[5] = b[2] + c[2];
+}
+/* force cross product v x* f */
+static void FN(crf)(const R* v, const R* f, R* o) {
+    R a[3], b[3], c[3];
+    FN(cross3)(v, f, a); FN(cross3)(v + 3, f + 3, b); FN(cross3)(v, f + 3, c);
+    o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2]; o[3] = c[0]; o[4] = c[1]; o[5] = c[2];
+}
+static void FN(mv6)(const R* m, const R* v, R* o) {
+    R t[6];
+    for (int i = 0; i < 6; i++) { R s = 0; for (int j = 0; j < 6; j++) s += m[i * 6 + j] * v[j]; t[i] = s; }
+    for (int i = 0; i < 6; i++) o[i] = t[i];
+}
+static R FN(dot6)(const R* a, const R* b) { R s = 0; for (int i = 0; i < 6; i++) s += a[i] * b[i]; return s; }
+
+/* spatial inertia about O from mass, com position c (rel. O) and rotational inertia about the com (world axes) */
+static void FN(spatial_inertia)(R m, const R* c, const R* Ic, R* I) {
+    R cx[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0};
+    R cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            I[i * 6 + j] = Ic[i * 3 + j] + m * ((i == j ? cc : 0) - c[i] * c[j]);
+            I[i * 6 + 3 + j] = m * cx[i * 3 + j];
+            I[(3 + i) * 6 + j] = m * cx[j * 3 + i];
+            I[(3 + i) * 6 + 3 + j] = (i == j) ? m : 0;
+        }
+}
+
+/* inverse of a symmetric positive definite 6x6 via Cholesky; returns 0 on success */
+static int FN(spd_inverse6)(const R* a, R* inv) {
+    R L[36];
+    for (int i = 0; i < 36; i++) L[i] = 0;
+    for (int j = 0; j < 6; j++) {
+        R d = a[j * 6 + j];
+        for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k];
+        if (!(d > 0)) return -1;
+        R s = (R)sqrt((double)d);
+        L[j * 6 + j] = s;
+        for (int i = j + 1; i < 6; i++) {
+            R t = a[i * 6 + j];
+            for (int k = 0; k < j; k++) t -= L[i * 6 + k] * L[j * 6 + k];
+            L[i * 6 + j] = t / s;
+        }
+    }
+    for (int c = 0; c < 6; c++) {
+        R y[6], x[6];
+        for (int i = 0; i < 6; i++) {
+            R t = (i == c) ? 1 : 0;
+            for (int k = 0; k < i; k++) t -= L[i * 6 + k] * y[k];
+            y[i] = t / L[i * 6 + i];
+        }
+        for (int i = 5; i >= 0; i--) {
+            R t = y[i];
+            for (int k = i + 1; k < 6; k++) t -= L[k * 6 + i] * x[k];
+            x[i] = t / L[i * 6 + i];
+        }
+        for (int i = 0; i < 6; i++) inv[i * 6 + c] = x[i];
+    }
+    return 0;
+}
+
+/* ---- kinematics + velocity-dependent terms, common frame = world axes at the root origin ---- */
+static void FN(orc_kinematics)(const b2g_model* m, const R* root13, const R* q, const R* qd, FN(orc_kin)* k) {
+    int nd = m->n_dof;
+    FN(quat2mat)(root13 + 3, k->rot[0]);
+    k->pos[0][0] = k->pos[0][1] = k->pos[0][2] = 0;
+    if (m->fixed_base) {
+        for (int i = 0; i < 6; i++) k->vel[0][i] = 0;
+    } else {
+        for (int i = 0; i < 3; i++) { k->vel[0][i] = root13[10 + i]; k->vel[0][3 + i] = root13[7 + i]; }
+    }
+    for (int c = 0; c < m->n_chains; c++) {
+        for (int j = 0; j < m->chain_len[c]; j++) {
+            int d = m->chain_start[c] + j;
+            int l = d + 1, p = (j == 0) ? 0 : l - 1;
+            R jq[4] = {m->joint_quat[d][0], m->joint_quat[d][1], m->joint_quat[d][2], m->joint_quat[d][3]};
+            R jp[3] = {m->joint_pos[d][0], m->joint_pos[d][1], m->joint_pos[d][2]};
+            R ax[3] = {m->joint_axis[d][0], m->joint_axis[d][1], m->joint_axis[d][2]};
+            R rj[9], rjw[9], off[3], axw[3];
+            FN(quat2mat)(jq, rj);
+            FN(matmul3)(k->rot[p], rj, rjw);
+            FN(matvec3)(k->rot[p], jp, off);
+            FN(matvec3)(rjw, ax, axw);
+            R pj[3] = {k->pos[p][0] + off[0], k->pos[p][1] + off[1], k->pos[p][2] + off[2]};
+            if (m->joint_type[d] == B2G_JOINT_REVOLUTE) {
+                R rq[9];
+                FN(axisangle2mat)(ax, q[d], rq);
+                FN(matmul3)(rjw, rq, k->rot[l]);
+                for (int i = 0; i < 3; i++) k->pos[l][i] = pj[i];
+                R lin[3];
+                FN(cross3)(pj, axw, lin);
+                for (int i = 0; i < 3; i++) { k->S[d][i] = axw[i]; k->S[d][3 + i] = lin[i]; }
+            } else {
+                for (int i = 0; i < 9; i++) k->rot[l][i] = rjw[i];
+                for (int i = 0; i < 3; i++) { k->pos[l][i] = pj[i] + axw[i] * q[d]; k->S[d][i] = 0; k->S[d][3 + i] = axw[i]; }
+            }
+            R vj[6];
+            for (int i = 0; i < 6; i++) { vj[i] = k->S[d][i] * qd[d]; k->vel[l][i] = k->vel[p][i] + vj[i]; }
+            FN(crm)(k->vel[l], vj, k->cb[d]);
+        }
+    }
+    for (int l = 0; l <= nd; l++) {
+        R com[3] = {m->link_com[l][0], m->link_com[l][1], m->link_com[l][2]};
+        R il[9] = {m->link_inertia[l][0], m->link_inertia[l][3], m->link_inertia[l][4],
+                   m->link_inertia[l][3], m->link_inertia[l][1], m->link_inertia[l][5],
+                   m->link_inertia[l][4], m->link_inertia[l][5], m->link_inertia[l][2]};
+        R cw[3], t[9], rt[9], iw[9];
+        FN(matvec3)(k->rot[l], com, cw);
+        for (int i = 0; i < 3; i++) cw[i] += k->pos[l][i];
+        FN(matmul3)(k->rot[l], il, t);
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rt[i * 3 + j] = k->rot[l][j * 3 + i];
+        FN(matmul3)(t, rt, iw);
+        FN(spatial_inertia)((R)m->link_mass[l], cw, iw, k->I[l]);
+    }
+}
+
+/* ABA passes 1-2: articulated inertias and bias forces. tau = applied joint efforts, dext = extra
+ * joint-space diagonal (armature + implicit drive terms). */
+static int FN(orc_aba_backward)(const b2g_model* m, FN(orc_kin)* k, const R* tau, const R* dext) {
+    int nd = m->n_dof;
+    for (int l = 0; l <= nd; l++) {
+        R iv[6];
+        for (int i = 0; i < 36; i++) k->IA[l][i] = k->I[l][i];
+        FN(mv6)(k->I[l], k->vel[l], iv);
+        FN(crf)(k->vel[l], iv, k->pA[l]);
+    }
+    for (int c = 0; c < m->n_chains; c++) {
+        for (int j = m->chain_len[c] - 1; j >= 0; j--) {
+            int d = m->chain_start[c] + j;
+            int l = d + 1, p = (j == 0) ? 0 : l - 1;
+            FN(mv6)(k->IA[l], k->S[d], k->U[d]);
+            k->D[d] = FN(dot6)(k->S[d], k->U[d]) + dext[d];
+            k->u[d] = tau[d] - FN(dot6)(k->S[d], k->pA[l]);
+            R Ia[36], pa[6], t[6];
+            R dinv = 1 / k->D[d];
+            for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) Ia[a * 6 + b] = k->IA[l][a * 6 + b] - k->U[d][a] * k->U[d][b] * dinv;
+            FN(mv6)(Ia, k->cb[d], t);
+            for (int a = 0; a < 6; a++) pa[a] = k->pA[l][a] + t[a] + k->U[d][a] * (k->u[d] * dinv);
+            if (p != 0 || !m->fixed_base) {
+                for (int a = 0; a < 36; a++) k->IA[p][a] += Ia[a];
+                for (int a = 0; a < 6; a++) k->pA[p][a] += pa[a];
+            }
+        }
+    }
+    if (!m->fixed_base) return FN(spd_inverse6)(k->IA[0], k->IA0inv);
+    for (int i = 0; i < 36; i++) k->IA0inv[i] = 0;
+    return 0;
+}
+
+/* ABA pass 3. grav = gravity vector. Outputs qdd (nd) and the root's spatial acceleration (6). */
+static void FN(orc_aba_forward)(const b2g_model* m, const FN(orc_kin)* k, const R* grav, R* qdd, R* a0) {
+    R acc[B2G_MAX_LINKS][6];
+    if (m->fixed_base) {
+        for (int i = 0; i < 3; i++) { acc[0][i] = 0; acc[0][3 + i] = -grav[i]; }
+    } else {
+        /* gravity is a uniform field: solve for a' = a - a_g (pA holds no gravity term), add a_g back below */
+        FN(mv6)(k->IA0inv, k->pA[0], acc[0]);
+        for (int i = 0; i < 6; i++) acc[0][i] = -acc[0][i];
+    }
+    for (int c = 0; c < m->n_chains; c++) {
+        for (int j = 0; j < m->chain_len[c]; j++) {
+            int d = m->chain_start[c] + j;
+            int l = d + 1, p = (j == 0) ? 0 : l - 1;
+            R ap[6];
+            for (int i = 0; i < 6; i++) ap[i] = acc[p][i] + k->cb[d][i];
+            qdd[d] = (k->u[d] - FN(dot6)(k->U[d], ap)) / k->D[d];
+            for (int i = 0; i < 6; i++) acc[l][i] = ap[i] + k->S[d][i] * qdd[d];
+        }
+    }
+    /* true root acceleration = relative acceleration + gravity field (zero for a fixed base) */
+    for (int i = 0; i < 3; i++) { a0[i] = acc[0][i]; a0[3 + i] = acc[0][3 + i] + grav[i]; }
+}
+
+/* velocity change caused by a spatial impulse F applied to link `link` (0 = root) plus optional joint
+ * impulse tj on DOF dj (dj < 0: none). Accumulates into dv0 (6) and dqd (nd). Uses IA/U/D from the
+ * last orc_aba_backward. */
+static void FN(orc_apply_impulse)(const b2g_model* m, const FN(orc_kin)* k, int link, const R* F, int dj, R tj, R* v0, R* qd) {
+    R ud[B2G_MAX_DOF];
+    R P[6] = {0, 0, 0, 0, 0, 0};
+    for (int d = 0; d < m->n_dof; d++) ud[d] = 0;
+    int cpath = -1;
+    if (link > 0 || dj >= 0) {
+        int dd = (link > 0) ? link - 1 : dj;
+        for (int c = 0; c < m->n_chains; c++)
+            if (dd >= m->chain_start[c] && dd < m->chain_start[c] + m->chain_len[c]) cpath = c;
+    }
+    if (link == 0 && F) for (int i = 0; i < 6; i++) P[i] = -F[i];
+    if (cpath >= 0) {
+        int c = cpath;
+        int have = 0;
+        for (int j = m->chain_len[c] - 1; j >= 0; j--) {
+            int d = m->chain_start[c] + j;
+            int l = d + 1;
+            if (F && l == link) { for (int i = 0; i < 6; i++) P[i] -= F[i]; have = 1; }
+            if (d == dj) have = 1;
+            if (!have) continue;
+            ud[d] = ((d == dj) ? tj : 0) - FN(dot6)(k->S[d], P);
+            R s = ud[d] / k->D[d];
+            for (int i = 0; i < 6; i++) P[i] += k->U[d][i] * s;
+        }
+    }
+    R dv[B2G_MAX_LINKS][6];
+    if (m->fixed_base) {
+        for (int i = 0; i < 6; i++) dv[0][i] = 0;
+    } else {
+        FN(mv6)(k->IA0inv, P, dv[0]);
+        for (int i = 0; i < 6; i++) { dv[0][i] = -dv[0][i]; v0[i] += dv[0][i]; }
+    }
+    for (int c = 0; c < m->n_chains; c++) {
+        for (int j = 0; j < m->chain_len[c]; j++) {
+            int d = m->chain_start[c] + j;
+            int l = d + 1, p = (j == 0) ? 0 : l - 1;
+            R dq = (ud[d] - FN(dot6)(k->U[d], dv[p])) / k->D[d];
+            for (int i = 0; i < 6; i++) dv[l][i] = dv[p][i] + k->S[d][i] * dq;
+            qd[d] += dq;
+        }
+    }
+}
+
+/* spatial velocity of a link from (v0, qd) */
+static void FN(orc_link_velocity)(const b2g_model* m, const FN(orc_kin)* k, int link, const R* v0, const R* qd, R* v) {
+    for (int i = 0; i < 6; i++) v[i] = m->fixed_base ? 0 : v0[i];
+    if (link == 0) return;
+    int dd = link - 1;
+    for (int c = 0; c < m->n_chains; c++) {
+        if (dd < m->chain_start[c] || dd >= m->chain_start[c] + m->chain_len[c]) continue;
+        for (int d = m->chain_start[c]; d <= dd; d++)
+            for (int i = 0; i < 6; i++) v[i] += k->S[d][i] * qd[d];
+    }
+}
+
+/* terrain height and unit normal under world point (x, y); plane z = 0 when there is no heightfield */
+static void FN(orc_ground)(const b2g_heightfield* hf, const int16_t* s, R x, R y, R* h, R* n) {
+    n[0] = 0; n[1] = 0; n[2] = 1; *h = 0;
+    if (!hf || !s) return;
+    R gx = (x - (R)hf->origin_x) / (R)hf->horizontal_scale, gy = (y - (R)hf->origin_y) / (R)hf->horizontal_scale;
+    if (gx < 0) gx = 0; if (gy < 0) gy = 0;
+    if (gx > (R)(hf->rows - 1)) gx = (R)(hf->rows - 1);
+    if (gy > (R)(hf->cols - 1)) gy = (R)(hf->cols - 1);
+    int i = (int)gx, j = (int)gy;
+    if (i > hf->rows - 2) i = hf->rows - 2;
+    if (j > hf->cols - 2) j = hf->cols - 2;
+    R fx = gx - (R)i, fy = gy - (R)j;
+    R vs = (R)hf->vertical_scale, hs = (R)hf->horizontal_scale;
+    R h00 = vs * (R)s[i * hf->cols + j], h10 = vs * (R)s[(i + 1) * hf->cols + j];
+    R h01 = vs * (R)s[i * hf->cols + j + 1], h11 = vs * (R)s[(i + 1) * hf->cols + j + 1];
+    R dzdx, dzdy;
+    if (fx >= fy) { dzdx = (h10 - h00); dzdy = (h11 - h10); *h = h00 + dzdx * fx + dzdy * fy; }
+    else { dzdx = (h11 - h01); dzdy = (h01 - h00); *h = h00 + dzdx * fx + dzdy * fy; }
+    R nx = -dzdx / hs, ny = -dzdy / hs, nz = 1;
+    R inv = 1 / (R)sqrt((double)(nx * nx + ny * ny + nz * nz));
+    n[0] = nx * inv; n[1] = ny * inv; n[2] = nz * inv;
+}
+
+typedef struct FN(orc_contact) {
+    int link, body;
+    R r[3];          /* contact point relative to O */
+    R n[3], t1[3], t2[3];
+    R gap;
+    R A[9];          /* local Delassus block in (n, t1, t2) */
+    R lam[3];        /* accumulated impulse (n, t1, t2) */
+} FN(orc_contact);
+
+typedef struct FN(orc_limit) {
+    int dof; R sign; R gap; R A; R lam;
+} FN(orc_limit);
+
+static void FN(orc_contact_wrench)(const FN(orc_contact)* c, const R* dir, R* F) {
+    R mom[3];
+    FN(cross3)(c->r, dir, mom);
+    for (int i = 0; i < 3; i++) { F[i] = mom[i]; F[3 + i] = dir[i]; }
+}
+
+static void FN(orc_point_velocity)(const FN(orc_contact)* c, const R* v, R* out) {
+    R wxr[3];
+    FN(cross3)(v, c->r, wxr);
+    for (int i = 0; i < 3; i++) out[i] = v[3 + i] + wxr[i];
+}
+
+/*
+ * One sub-step of length h for one environment.
+ *  root13: pos3 quat4 linvel3 angvel3 (in/out)   dof: nd x (pos, vel) (in/out)
+ *  target: position (POS) / velocity (VEL) targets; actuation: efforts (EFFORT mode)
+ *  dof_force (nd) and contact (nb x 3, world) are outputs.
+ */
+static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp,
+                           const b2g_heightfield* hf, const int16_t* hfs, R mu_shape, R h,
+                           R* root13, R* dof, const R* target, const R* actuation, R* dof_force, R* contact) {
+    int nd = m->n_dof;
+    FN(orc_kin)* k = (FN(orc_kin)*)malloc(sizeof(FN(orc_kin)));
+    if (!k) return -1;
+    R q[B2G_MAX_DOF], qd[B2G_MAX_DOF], tau[B2G_MAX_DOF], dext[B2G_MAX_DOF], qdd[B2G_MAX_DOF], a0[6];
+    R grav[3] = {(R)sp->gravity[0], (R)sp->gravity[1], (R)sp->gravity[2]};
+    for (int d = 0; d < nd; d++) { q[d] = dof[2 * d]; qd[d] = dof[2 * d + 1]; }
+    for (int d = 0; d < nd; d++) {
+        R kp = (R)dp->stiffness[d], kd = (R)dp->damping[d];
+        dext[d] = (R)m->armature[d];
+        tau[d] = 0;
+        if (dp->drive_mode[d] == B2G_DOF_MODE_POS) {
+            tau[d] = kp * (target[d] - q[d]) - (kd + h * kp) * qd[d];
+            dext[d] += h * kd + h * h * kp;
+        } else if (dp->drive_mode[d] == B2G_DOF_MODE_VEL) {
+            tau[d] = kd * (target[d] - qd[d]);
+            dext[d] += h * kd;
+        } else if (dp->drive_mode[d] == B2G_DOF_MODE_EFFORT) {
+            R e = actuation[d], lim = (R)dp->effort[d];
+            if (lim > 0) { if (e > lim) e = lim; if (e < -lim) e = -lim; }
+            tau[d] = e;
+        }
+    }
+    FN(orc_kinematics)(m, root13, q, qd, k);
+    if (FN(orc_aba_backward)(m, k, tau, dext) != 0) { free(k); return -2; }
+    FN(orc_aba_forward)(m, k, grav, qdd, a0);
+
+    /* free velocity */
+    R v0[6] = {0, 0, 0, 0, 0, 0};
+    if (!m->fixed_base) {
+        R w[3] = {k->vel[0][0], k->vel[0][1], k->vel[0][2]}, vl[3] = {k->vel[0][3], k->vel[0][4], k->vel[0][5]}, wxv[3];
+        FN(cross3)(w, vl, wxv);
+        /* root origin is a body-fixed point: classical acceleration = spatial + w x v */
+        for (int i = 0; i < 3; i++) { v0[i] = w[i] + h * a0[i]; v0[3 + i] = vl[i] + h * (a0[3 + i] + wxv[i]); }
+    }
+    for (int d = 0; d < nd; d++) qd[d] += h * qdd[d];
+
+    /* ---- collect contacts: per chain, candidates in model order, first B2G_MAX_CONTACTS_PER_CHAIN ---- */
+    FN(orc_contact) con[B2G_MAX_CHAINS][B2G_MAX_CONTACTS_PER_CHAIN];
+    int ncon[B2G_MAX_CHAINS];
+    R mu_g = hf && hfs ? (R)hf->friction : (R)sp->plane_dynamic_friction;
+    R mu = (R)0.5 * (mu_g + mu_shape);   /* PhysX default combine mode: average */
+    int ground = (hf && hfs) || sp->has_ground;
+    for (int c = 0; c < m->n_chains; c++) ncon[c] = 0;
+    for (int i = 0; i < m->n_cpts && ground; i++) {
+        int c = m->cp_chain[i], l = m->cp_link[i];
+        if (m->fixed_base && l == 0) continue;
+        if (ncon[c] >= B2G_MAX_CONTACTS_PER_CHAIN) continue;
+        R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
+        FN(matvec3)(k->rot[l], lp, rc);
+        for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];
+        FN(orc_ground)(hf, hfs, root13[0] + rc[0], root13[1] + rc[1], &gh, n);
+        R gap = (root13[2] + rc[2] - gh) * n[2] - (R)m->cp_radius[i];
+        if (gap >= (R)sp->contact_offset) continue;
+        FN(orc_contact)* cc = &con[c][ncon[c]++];
+        cc->link = l; cc->body = m->cp_body[i]; cc->gap = gap;
+        for (int a = 0; a < 3; a++) { cc->n[a] = n[a]; cc->r[a] = rc[a] - (R)m->cp_radius[i] * n[a]; cc->lam[a] = 0; }
+        /* tangent basis: t1 = normalise(x_world - (x.n) n), t2 = n x t1 */
+        R ex[3] = {1, 0, 0};
+        R dn = n[0];
+        R t1[3] = {ex[0] - dn * n[0], ex[1] - dn * n[1], ex[2] - dn * n[2]};
+        R inv = 1 / (R)sqrt((double)(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]));
+        for (int a = 0; a < 3; a++) cc->t1[a] = t1[a] * inv;
+        FN(cross3)(cc->n, cc->t1, cc->t2);
+        /* local Delassus block */
+        const R* dirs[3] = {cc->n, cc->t1, cc->t2};
+        for (int b = 0; b < 3; b++) {
+            R F[6], dv0[6] = {0, 0, 0, 0, 0, 0}, dqd[B2G_MAX_DOF], lv[6], pv[3];
+            for (int d = 0; d < nd; d++) dqd[d] = 0;
+            FN(orc_contact_wrench)(cc, dirs[b], F);
+            FN(orc_apply_impulse)(m, k, l, F, -1, 0, dv0, dqd);
+            FN(orc_link_velocity)(m, k, l, dv0, dqd, lv);
+            FN(orc_point_velocity)(cc, lv, pv);
+            for (int a = 0; a < 3; a++) cc->A[a * 3 + b] = pv[0] * dirs[a][0] + pv[1] * dirs[a][1] + pv[2] * dirs[a][2];
+        }
+    }
+    /* ---- joint limits ---- */
+    FN(orc_limit) lim[B2G_MAX_DOF];
+    int nlim = 0;
+    for (int d = 0; d < nd; d++) {
+        R lo = (R)dp->lower[d], hi = (R)dp->upper[d];
+        int act = 0; R sign = 0, gap = 0;
+        if (lo > -1e30f && q[d] + h * qd[d] < lo) { act = 1; sign = 1; gap = q[d] - lo; }
+        else if (hi < 1e30f && q[d] + h * qd[d] > hi) { act = 1; sign = -1; gap = hi - q[d]; }
+        if (!act) continue;
+        R dv0[6] = {0, 0, 0, 0, 0, 0}, dqd[B2G_MAX_DOF];
+        for (int e = 0; e < nd; e++) dqd[e] = 0;
+        FN(orc_apply_impulse)(m, k, 0, 0, d, 1, dv0, dqd);
+        lim[nlim].dof = d; lim[nlim].sign = sign; lim[nlim].gap = gap; lim[nlim].A = dqd[d]; lim[nlim].lam = 0;
+        nlim++;
+    }
+
+    /* ---- projected Gauss-Seidel: position iterations (with bias), integrate, velocity iterations ---- */
+    int npos = sp->num_position_iterations, nvel = sp->num_velocity_iterations;
+    R maxdep = (R)sp->max_depenetration_velocity;
+    R vpos0[6], qdpos[B2G_MAX_DOF];
+    for (int it = 0; it <= npos + nvel; it++) {
+        if (it == npos) {   /* snapshot the velocity used to integrate positions */
+            for (int i = 0; i < 6; i++) vpos0[i] = v0[i];
+            for (int d = 0; d < nd; d++) qdpos[d] = qd[d];
+        }
+        if (it == npos + nvel) break;
+        int with_bias = it < npos;
+        for (int s = 0; s < B2G_MAX_CONTACTS_PER_CHAIN; s++) {
+            for (int c = 0; c < m->n_chains; c++) {
+                if (s >= ncon[c]) continue;
+                FN(orc_contact)* cc = &con[c][s];
+                R lv[6], pv[3];
+                FN(orc_link_velocity)(m, k, cc->link, v0, qd, lv);
+                FN(orc_point_velocity)(cc, lv, pv);
+                R vn = pv[0] * cc->n[0] + pv[1] * cc->n[1] + pv[2] * cc->n[2];
+                R vt1 = pv[0] * cc->t1[0] + pv[1] * cc->t1[1] + pv[2] * cc->t1[2];
+                R vt2 = pv[0] * cc->t2[0] + pv[1] * cc->t2[1] + pv[2] * cc->t2[2];
+                R tgt = -cc->gap / h;
+                if (tgt > maxdep) tgt = maxdep;
+                if (!with_bias && tgt > 0) tgt = 0;
+                R dl[3];
+                R ln = cc->lam[0] - (vn - tgt) / cc->A[0];
+                if (ln < 0) ln = 0;
+                dl[0] = ln - cc->lam[0];
+                vt1 += cc->A[3] * dl[0]; vt2 += cc->A[6] * dl[0];
+                R l1 = cc->lam[1] - vt1 / cc->A[4];
+                vt2 += cc->A[7] * (l1 - cc->lam[1]);
+                R l2 = cc->lam[2] - vt2 / cc->A[8];
+                R lim_t = mu * ln, mag = (R)sqrt((double)(l1 * l1 + l2 * l2));
+                if (mag > lim_t) { R sc = (mag > 0) ? lim_t / mag : 0; l1 *= sc; l2 *= sc; }
+                dl[1] = l1 - cc->lam[1]; dl[2] = l2 - cc->lam[2];
+                cc->lam[0] = ln; cc->lam[1] = l1; cc->lam[2] = l2;
+                R dir[3], F[6];
+                for (int a = 0; a < 3; a++) dir[a] = cc->n[a] * dl[0] + cc->t1[a] * dl[1] + cc->t2[a] * dl[2];
+                FN(orc_contact_wrench)(cc, dir, F);
+                FN(orc_apply_impulse)(m, k, cc->link, F, -1, 0, v0, qd);
+            }
+        }
+        for (int i = 0; i < nlim; i++) {
+            FN(orc_limit)* L = &lim[i];
+            R vrel = L->sign * qd[L->dof];
+            R tgt = -L->gap / h;
+            if (!with_bias && tgt > 0) tgt = 0;
+            R ln = L->lam - (vrel - tgt) / L->A;
+            if (ln < 0) ln = 0;
+            R dl = ln - L->lam;
+            L->lam = ln;
+            FN(orc_apply_impulse)(m, k, 0, 0, L->dof, L->sign * dl, v0, qd);
+        }
+    }
+    if (npos + nvel == 0) {
+        for (int i = 0; i < 6; i++) vpos0[i] = v0[i];
+        for (int d = 0; d < nd; d++) qdpos[d] = qd[d];
+    }
+
+    /* ---- integrate positions with the post-position-iteration velocity ---- */
+    for (int d = 0; d < nd; d++) {
+        R vl = (R)dp->velocity[d];
+        if (vl > 0) { if (qd[d] > vl) qd[d] = vl; if (qd[d] < -vl) qd[d] = -vl; if (qdpos[d] > vl) qdpos[d] = vl; if (qdpos[d] < -vl) qdpos[d] = -vl; }
+        q[d] += h * qdpos[d];
+        dof[2 * d] = q[d]; dof[2 * d + 1] = qd[d];
+    }
+    if (!m->fixed_base) {
+        for (int i = 0; i < 3; i++) root13[i] += h * vpos0[3 + i];
+        R w[3] = {vpos0[0], vpos0[1], vpos0[2]};
+        R ang = (R)sqrt((double)(w[0] * w[0] + w[1] * w[1] + w[2] * w[2])) * h;
+        R dq[4] = {0, 0, 0, 1};
+        if (ang > (R)1e-12) {
+            R s = (R)sin((double)(ang / 2)) / (ang / h);
+            dq[0] = w[0] * s; dq[1] = w[1] * s; dq[2] = w[2] * s; dq[3] = (R)cos((double)(ang / 2));
+        }
+        R* qo = root13 + 3;
+        R x1 = dq[0], y1 = dq[1], z1 = dq[2], w1 = dq[3], x2 = qo[0], y2 = qo[1], z2 = qo[2], w2 = qo[3];
+        R nq[4] = {w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                   w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2};
+        R nn = 1 / (R)sqrt((double)(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]));
+        for (int i = 0; i < 4; i++) qo[i] = nq[i] * nn;
+        for (int i = 0; i < 3; i++) { root13[7 + i] = v0[3 + i]; root13[10 + i] = v0[i]; }
+    }
+    /* ---- outputs ---- */
+    for (int d = 0; d < nd; d++) {
+        R f = 0, lim_e = (R)dp->effort[d];
+        if (dp->drive_mode[d] == B2G_DOF_MODE_POS) f = (R)dp->stiffness[d] * (target[d] - q[d]) - (R)dp->damping[d] * qd[d];
+        else if (dp->drive_mode[d] == B2G_DOF_MODE_VEL) f = (R)dp->damping[d] * (target[d] - qd[d]);
+        else if (dp->drive_mode[d] == B2G_DOF_MODE_EFFORT) f = actuation[d];
+        if (lim_e > 0) { if (f > lim_e) f = lim_e; if (f < -lim_e) f = -lim_e; }
+        dof_force[d] = f;
+    }
+    for (int b = 0; b < m->n_bodies * 3; b++) contact[b] = 0;
+    for (int c = 0; c < m->n_chains; c++)
+        for (int s = 0; s < ncon[c]; s++) {
+            FN(orc_contact)* cc = &con[c][s];
+            for (int a = 0; a < 3; a++)
+                contact[cc->body * 3 + a] += (cc->n[a] * cc->lam[0] + cc->t1[a] * cc->lam[1] + cc->t2[a] * cc->lam[2]) / h;
+        }
+    free(k);
+    return 0;
+}
+
+/* gym.simulate for n_envs environments: sp->substeps sub-steps of dt/substeps each. */
+int FN(orc_simulate)(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp,
+                     const b2g_heightfield* hf, const int16_t* hfs, const float* friction, int n_envs,
+                     R* root, R* dof, const R* target, const R* actuation, R* dof_force, R* contact) {
+    int nd = m->n_dof, nb = m->n_bodies;
+    R h = (R)sp->dt / (R)(sp->substeps > 0 ? sp->substeps : 1);
+    int rc = 0;
+    for (int e = 0; e < n_envs; e++) {
+        R dummy_root[13] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0};
+        R* r = root ? root + (size_t)e * 13 : dummy_root;
+        for (int s = 0; s < (sp->substeps > 0 ? sp->substeps : 1); s++) {
+            int st = FN(orc_substep)(m, sp, dp, hf, hfs, friction ? (R)friction[e] : (R)1, h, r, dof + (size_t)e * nd * 2,
+                                     target + (size_t)e * nd, actuation + (size_t)e * nd, dof_force + (size_t)e * nd,
+                                     contact + (size_t)e * nb * 3);
+            if (st != 0) rc = st;
+        }
+    }
+    return rc;
+}
+
+/* forward dynamics probe: joint accelerations + root spatial acceleration (contact-free, no drives) */
+int FN(orc_forward_dynamics)(const b2g_model* m, const b2g_sim_params* sp, int n_envs, const R* root, const R* dof,
+                             const R* tau, R* qdd, R* root_acc) {
+    int nd = m->n_dof;
+    FN(orc_kin)* k = (FN(orc_kin)*)malloc(sizeof(FN(orc_kin)));
+    if (!k) return -1;
+    R grav[3] = {(R)sp->gravity[0], (R)sp->gravity[1], (R)sp->gravity[2]};
+    R dext[B2G_MAX_DOF];
+    for (int d = 0; d < nd; d++) dext[d] = (R)m->armature[d];
+    int rc = 0;
+    for (int e = 0; e < n_envs; e++) {
+        R q[B2G_MAX_DOF], qd[B2G_MAX_DOF];
+        R dummy_root[13] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0};
+        const R* r = root ? root + (size_t)e * 13 : dummy_root;
+        for (int d = 0; d < nd; d++) { q[d] = dof[((size_t)e * nd + d) * 2]; qd[d] = dof[((size_t)e * nd + d) * 2 + 1]; }
+        FN(orc_kinematics)(m, r, q, qd, k);
+        if (FN(orc_aba_backward)(m, k, tau + (size_t)e * nd, dext) != 0) rc = -2;
+        FN(orc_aba_forward)(m, k, grav, qdd + (size_t)e * nd, root_acc + (size_t)e * 6);
+    }
+    free(k);
+    return rc;
+}
+
+/* CRBA mass matrix H ((6+nd)^2 floating: root block first (angular, linear), or nd^2 fixed) and RNEA bias
+ * C (same ordering) with gravity, so that H [a0; qdd] + C = [0; tau]. Independent of the ABA code path. */
+int FN(orc_crba_rnea)(const b2g_model* m, const b2g_sim_params* sp, const R* root13, const R* dofs, R* H, R* C) {
+    int nd = m->n_dof, nb = m->fixed_base ? 0 : 6, n = nd + nb;
+    FN(orc_kin)* k = (FN(orc_kin)*)malloc(sizeof(FN(orc_kin)));
+    if (!k) return -1;
+    R q[B2G_MAX_DOF], qd[B2G_MAX_DOF];
+    R dummy_root[13] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0};
+    if (!root13) root13 = dummy_root;
+    for (int d = 0; d < nd; d++) { q[d] = dofs[2 * d]; qd[d] = dofs[2 * d + 1]; }
+    FN(orc_kinematics)(m, root13, q, qd, k);
+    /* composite inertias */
+    R Ic[B2G_MAX_LINKS][36];
+    for (int l = 0; l <= nd; l++) for (int i = 0; i < 36; i++) Ic[l][i] = k->I[l][i];
+    for (int c = 0; c < m->n_chains; c++)
+        for (int j = m->chain_len[c] - 1; j >= 0; j--) {
+            int l = m->chain_start[c] + j + 1, p = (j == 0) ? 0 : l - 1;
+            for (int i = 0; i < 36; i++) Ic[p][i] += Ic[l][i];
+        }
+    for (int i = 0; i < n * n; i++) H[i] = 0;
+    if (nb) for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) H[a * n + b] = Ic[0][a * 6 + b];
+    for (int c = 0; c < m->n_chains; c++)
+        for (int j = 0; j < m->chain_len[c]; j++) {
+            int d = m->chain_start[c] + j;
+            R F[6];
+            FN(mv6)(Ic[d + 1], k->S[d], F);
+            H[(nb + d) * n + nb + d] = FN(dot6)(k->S[d], F) + (R)m->armature[d];
+            for (int jj = 0; jj < j; jj++) {
+                int e = m->chain_start[c] + jj;
+                R v = FN(dot6)(k->S[e], F);
+                H[(nb + d) * n + nb + e] = v; H[(nb + e) * n + nb + d] = v;
+            }
+            if (nb) for (int a = 0; a < 6; a++) { H[a * n + nb + d] = F[a]; H[(nb + d) * n + a] = F[a]; }
+        }
+    /* RNEA with zero accelerations (relative to gravity field) */
+    R grav[3] = {(R)sp->gravity[0], (R)sp->gravity[1], (R)sp->gravity[2]};
+    R acc[B2G_MAX_LINKS][6], f[B2G_MAX_LINKS][6];
+    for (int i = 0; i < 3; i++) { acc[0][i] = 0; acc[0][3 + i] = -grav[i]; }
+    for (int c = 0; c < m->n_chains; c++)
+        for (int j = 0; j < m->chain_len[c]; j++) {
+            int d = m->chain_start[c] + j, l = d + 1, p = (j == 0) ? 0 : l - 1;
+            for (int i = 0; i < 6; i++) acc[l][i] = acc[p][i] + k->cb[d][i];
+        }
+    for (int l = 0; l <= nd; l++) {
+        R ia[6], iv[6], t[6];
+        FN(mv6)(k->I[l], acc[l], ia);
+        FN(mv6)(k->I[l], k->vel[l], iv);
+        FN(crf)(k->vel[l], iv, t);
+        for (int i = 0; i < 6; i++) f[l][i] = ia[i] + t[i];
+    }
+    for (int c = 0; c < m->n_chains; c++)
+        for (int j = m->chain_len[c] - 1; j >= 0; j--) {
+            int d = m->chain_start[c] + j, l = d + 1, p = (j == 0) ? 0 : l - 1;
+            C[nb + d] = FN(dot6)(k->S[d], f[l]);
+            for (int i = 0; i < 6; i++) f[p][i] += f[l][i];
+        }
+    if (nb) for (int i = 0; i < 6; i++) C[i] = f[0][i];
+    free(k);
+    return 0;
+}
+
+/* total kinetic energy, potential energy, and spatial momentum about the WORLD origin (6) */
+int FN(orc_energy_momentum)(const b2g_model* m, const b2g_sim_params* sp, const R* root13, const R* dofs, R* ke, R* pe, R* mom) {
+    int nd = m->n_dof;
+    FN(orc_kin)* k = (FN(orc_kin)*)malloc(sizeof(FN(orc_kin)));
+    if (!k) return -1;
+    R q[B2G_MAX_DOF], qd[B2G_MAX_DOF];
+    R dummy_root[13] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0};
+    if (!root13) root13 = dummy_root;
+    for (int d = 0; d < nd; d++) { q[d] = dofs[2 * d]; qd[d] = dofs[2 * d + 1]; }
+    FN(orc_kinematics)(m, root13, q, qd, k);
+    R T = 0, V = 0, hO[6] = {0, 0, 0, 0, 0, 0};
+    for (int l = 0; l <= nd; l++) {
+        R iv[6], cw[3], com[3] = {m->link_com[l][0], m->link_com[l][1], m->link_com[l][2]};
+        FN(mv6)(k->I[l], k->vel[l], iv);
+        T += (R)0.5 * FN(dot6)(k->vel[l], iv);
+        for (int i = 0; i < 6; i++) hO[i] += iv[i];
+        FN(matvec3)(k->rot[l], com, cw);
+        for (int i = 0; i < 3; i++) V -= (R)m->link_mass[l] * (R)sp->gravity[i] * (root13[i] + k->pos[l][i] + cw[i]);
+    }
+    /* shift the moment from O (root origin) to the world origin: n_w = n_O + p0 x f */
+    R sh[3];
+    FN(cross3)(root13, hO + 3, sh);
+    for (int i = 0; i < 3; i++) { mom[i] = hO[i] + sh[i]; mom[3 + i] = hO[3 + i]; }
+    *ke = T; *pe = V;
+    free(k);
+    return 0;
+}
+
+#undef R
+#undef FN
+#undef ORC_CAT
+#undef ORC_CAT2
