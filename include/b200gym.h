@@ -139,7 +139,6 @@ enum b2g_tensor_kind {
     B2G_T_JACOBIAN = 7,         /* (N,nb,6,nd+6 or nd) f32                                   */
     B2G_T_MASS_MATRIX = 8,      /* (N,nd,nd) f32 (joint block, Isaac Gym convention)         */
     B2G_T_FRICTION = 9,         /* (N) f32 per-env shape friction coefficient                */
-    B2G_T_ENV_ORIGIN = 10,      /* (N,3) f32 env origin offsets (create_env grid)            */
     B2G_T_COUNT
 };
 
@@ -232,6 +231,9 @@ int b2g_task_tensor(b2g_sim* sim, int kind, b2g_tensor_desc* out);
 int b2g_task_anymal_reset_all(b2g_sim* sim, void* stream);
 /* VecTask.step for the flat task: one kernel launch. actions_dev: (N,12) f32 */
 int b2g_task_anymal_step(b2g_sim* sim, const float* actions_dev, void* stream);
+/* parity-test entry: post_physics_step only (tasks/anymal.py:231-239) on the sim tensors as they are --
+ * root/DOF state, DOF forces, net contact forces, commands, progress, reset -- no physics */
+int b2g_task_anymal_post_only(b2g_sim* sim, const float* actions_dev, void* stream);
 /* use_rand_override != 0: reset draws come from the RAND_OVERRIDE tensor instead of Philox */
 int b2g_task_set_rand_override(b2g_sim* sim, int use_rand_override);
 
@@ -242,6 +244,16 @@ int b2g_task_anymal_step_host(b2g_sim* sim, const float* actions_host, float* ob
 
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 int64_t b2g_sim_launch_count(const b2g_sim* sim);
+
+/* sizeof() of the public PODs (0 model, 1 sim_params, 2 dof_props, 3 heightfield, 4 tensor_desc,
+ * 5 anymal_cfg) so a foreign-language mirror of this header can verify its layout */
+int b2g_sizeof(int which);
+
+/* gymtorch.wrap_tensor (tasks/anymal.py:121-126): wrap a tensor description as a DLPack
+ * DLManagedTensor* (v0.8 ABI, kDLCUDA, non-owning; its deleter frees only the descriptor). The
+ * consumer (torch.from_dlpack on a "dltensor" capsule) gets a view that stays valid until
+ * b2g_sim_destroy. */
+int b2g_dlpack_from_desc(const b2g_tensor_desc* desc, void** out_managed);
 
 #ifdef __cplusplus
 }

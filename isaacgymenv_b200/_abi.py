@@ -125,11 +125,16 @@ def pack_model(art) -> Model:
     _fill(m.body_pos, art.body_pos.astype(np.float32))
     _fill(m.body_quat, art.body_quat.astype(np.float32))
     if ncp:
-        _fill(m.cp_link, art.cp_link)
-        _fill(m.cp_body, art.cp_body)
-        _fill(m.cp_chain, contact_owner_chains(art))
-        _fill(m.cp_pos, art.cp_pos.astype(np.float32))
-        _fill(m.cp_radius, art.cp_radius.astype(np.float32))
+        owner = contact_owner_chains(art)
+        # kernels need candidates grouped: per link (chains in order, distal link first), then root-link
+        # candidates grouped by owner lane
+        order = sorted(range(ncp), key=lambda i: (art.cp_link[i] == 0, owner[i], -int(art.cp_link[i]), i))
+        order = np.array(order, dtype=np.int64)
+        _fill(m.cp_link, art.cp_link[order])
+        _fill(m.cp_body, art.cp_body[order])
+        _fill(m.cp_chain, owner[order])
+        _fill(m.cp_pos, art.cp_pos[order].astype(np.float32))
+        _fill(m.cp_radius, art.cp_radius[order].astype(np.float32))
     return m
 
 

@@ -1,0 +1,714 @@
+// libb200gym.so -- kernels + C ABI (include/b200gym.h).
+//
+// One CUDA thread per (environment, chain); LANES consecutive threads of a warp form one environment.
+// Kernels: simulate (gym.simulate), fused Anymal/Hound step (pre_physics + simulate + post_physics),
+// reset_all, forward-dynamics probe, rigid-body-state refresh, indexed row copies.
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build()).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200gym.h"
+#include "b2g_host_pack.h"
+#include "b2g_threads.cuh"
+
+using namespace b2g;
+
+namespace {
+
+constexpr int kBlock = 64;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) return fail(B2G_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct Variant {
+    int lanes, nl;
+    bool fixed;
+};
+
+Variant pick_variant(const b2g_model& m) {
+    int maxlen = 0;
+    for (int c = 0; c < m.n_chains; c++) maxlen = m.chain_len[c] > maxlen ? m.chain_len[c] : maxlen;
+    if (m.fixed_base && m.n_chains <= 1 && maxlen <= 2) return {1, 2, true};
+    if (!m.fixed_base && m.n_chains <= 4 && maxlen <= 3) return {4, 3, false};
+    return {8, 6, m.fixed_base != 0};
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+template <int LANES>
+__device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int& env, int& lane, bool& valid, ScratchStrided& sc, float*& bf) {
+    const int tid = threadIdx.x;
+    constexpr int EPB = kBlock / LANES;
+    const int eib = tid / LANES;
+    lane = tid % LANES;
+    const int e = blockIdx.x * EPB + eib;
+    valid = e < n_envs;
+    env = valid ? e : n_envs - 1;
+    sc.base = smem + tid;
+    sc.stride = kBlock;
+    bf = smem + kBlock * MAXC * CF_COUNT + eib * nb * 3;
+}
+
+template <int LANES, int NL, bool FIXED, bool HF>
+__global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
+    extern __shared__ float smem[];
+    int env, lane; bool valid; ScratchStrided sc; float* bf;
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, valid, sc, bf);
+}
+
+template <int LANES, int NL, bool HF>
+__global__ void __launch_bounds__(kBlock) k_anymal_step(SimArgs A, TaskArgs T) {
+    extern __shared__ float smem[];
+    int env, lane; bool valid; ScratchStrided sc; float* bf;
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
+}
+
+template <int LANES, int NL>
+__global__ void __launch_bounds__(kBlock) k_anymal_reset_all(SimArgs A, TaskArgs T) {
+    extern __shared__ float smem[];
+    int env, lane; bool valid; ScratchStrided sc; float* bf;
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    anymal_reset_all_thread<LANES, NL>(A, T, env, lane, valid);
+}
+
+template <int LANES, int NL, bool FIXED>
+__global__ void __launch_bounds__(kBlock) k_probe(SimArgs A, float* qdd, float* a0) {
+    extern __shared__ float smem[];
+    int env, lane; bool valid; ScratchStrided sc; float* bf;
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    const DevModel* M = A.M;
+    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
+    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    LaneState<NL> st;
+    load_state<NL>(A, env, len, d0, st);
+#pragma unroll
+    for (int j = 0; j < NL; j++)
+        if (j < len) st.act[j] = A.actuation[(size_t)env * M->n_dof + d0 + j];
+    substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, 1.0f, false, sc, bf);
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < NL; j++)
+            if (j < len) qdd[(size_t)env * M->n_dof + d0 + j] = st.frc[j];
+        if (lane == 0) {
+            float* o = a0 + (size_t)env * 6;
+            o[0] = st.rw.x; o[1] = st.rw.y; o[2] = st.rw.z; o[3] = st.rv.x; o[4] = st.rv.y; o[5] = st.rv.z;
+        }
+    }
+}
+
+__global__ void k_body_state(const DevModel* M, const float* root, const float* dof, float* out, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    body_state_env(M, root + (size_t)e * 13, dof + (size_t)e * M->n_dof * 2, out + (size_t)e * M->n_bodies * 13);
+}
+
+// rows idx[0..n) of src -> dst, row = `row` floats (gym.set_*_tensor_indexed)
+__global__ void k_copy_rows(float* dst, const float* src, const int* idx, int n, int row) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * row) return;
+    const int r = idx[t / row], c = t % row;
+    dst[(size_t)r * row + c] = src[(size_t)r * row + c];
+}
+
+__global__ void k_fill_rows(float* dst, const float* row_vals, int n, int row) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * row) return;
+    dst[t] = row_vals[t % row];
+}
+
+__global__ void k_fill_i64(long long* dst, long long v, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = v;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// the sim object
+// ------------------------------------------------------------------------------------------------
+struct b2g_sim {
+    int device = 0;
+    b2g_sim_params params{};
+    b2g_model model{};
+    b2g_dof_props props{};
+    bool has_model = false, prepared = false;
+    b2g_heightfield hf{};
+    int16_t* d_hf = nullptr;
+    bool has_hf = false;
+    int n_envs = 0;
+    float root_pose[7] = {0, 0, 0, 0, 0, 0, 1};
+    Variant v{4, 3, false};
+    DevModel* d_model = nullptr;
+    float* t[B2G_T_COUNT] = {nullptr};
+    // task
+    bool has_task = false;
+    int num_obs = 0;
+    b2g_anymal_cfg acfg{};
+    float *obs = nullptr, *obs_clamped = nullptr, *rew = nullptr, *commands = nullptr, *actions = nullptr, *rand_override = nullptr;
+    long long *reset = nullptr, *progress = nullptr, *timeout = nullptr;
+    int* reset_count = nullptr;
+    float* actions_in = nullptr;   // staging for step_host
+    int use_rand_override = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+
+size_t smem_bytes(const b2g_sim* s) {
+    const int epb = kBlock / s->v.lanes;
+    return sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)epb * s->model.n_bodies * 3);
+}
+
+int grid_size(const b2g_sim* s) {
+    const int epb = kBlock / s->v.lanes;
+    return (s->n_envs + epb - 1) / epb;
+}
+
+SimArgs make_args(const b2g_sim* s) {
+    SimArgs A;
+    A.M = s->d_model;
+    pack_dev_params(s->params, s->has_hf ? &s->hf : nullptr, s->d_hf, A.P);
+    A.n_envs = s->n_envs;
+    A.root = s->t[B2G_T_ROOT_STATE];
+    A.dof = s->t[B2G_T_DOF_STATE];
+    A.target = s->t[B2G_T_DOF_TARGET];
+    A.actuation = s->t[B2G_T_DOF_ACTUATION];
+    A.dof_force = s->t[B2G_T_DOF_FORCE];
+    A.contact = s->t[B2G_T_NET_CONTACT];
+    A.friction = s->t[B2G_T_FRICTION];
+    return A;
+}
+
+TaskArgs make_task_args(const b2g_sim* s, const float* actions_in, int post_only = 0) {
+    TaskArgs T;
+    T.post_only = post_only;
+    T.cfg = s->acfg;
+    T.actions_in = actions_in;
+    T.obs = s->obs; T.obs_clamped = s->obs_clamped; T.rew = s->rew; T.reset = s->reset; T.progress = s->progress;
+    T.timeout = s->timeout; T.commands = s->commands; T.actions = s->actions; T.reset_count = s->reset_count;
+    T.rand_override = s->use_rand_override ? s->rand_override : nullptr;
+    return T;
+}
+
+int upload_model(b2g_sim* s) {
+    DevModel* h = (DevModel*)malloc(sizeof(DevModel));
+    if (!h) return fail(B2G_ERR_ARG, "out of host memory");
+    const char* why = "";
+    if (pack_dev_model(s->model, s->props, *h, &why) != 0) {
+        free(h);
+        return fail(B2G_ERR_ARG, "bad model: %s", why);
+    }
+    cudaError_t e = cudaSuccess;
+    if (!s->d_model) e = cudaMalloc(&s->d_model, sizeof(DevModel));
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_model, h, sizeof(DevModel), cudaMemcpyHostToDevice);
+    free(h);
+    if (e != cudaSuccess) return fail(B2G_ERR_CUDA, "model upload: %s", cudaGetErrorString(e));
+    return B2G_OK;
+}
+
+size_t tensor_floats(const b2g_sim* s, int kind) {
+    const size_t n = s->n_envs, nd = s->model.n_dof, nb = s->model.n_bodies;
+    const size_t jcols = nd + (s->model.fixed_base ? 0 : 6);
+    switch (kind) {
+        case B2G_T_ROOT_STATE: return n * 13;
+        case B2G_T_DOF_STATE: return n * nd * 2;
+        case B2G_T_NET_CONTACT: return n * nb * 3;
+        case B2G_T_DOF_FORCE: return n * nd;
+        case B2G_T_RIGID_BODY_STATE: return n * nb * 13;
+        case B2G_T_DOF_TARGET: return n * nd;
+        case B2G_T_DOF_ACTUATION: return n * nd;
+        case B2G_T_JACOBIAN: return n * nb * 6 * jcols;
+        case B2G_T_MASS_MATRIX: return n * nd * nd;
+        case B2G_T_FRICTION: return n;
+        default: return 0;
+    }
+}
+
+void describe(const b2g_sim* s, int kind, b2g_tensor_desc* d) {
+    const int64_t n = s->n_envs, nd = s->model.n_dof, nb = s->model.n_bodies;
+    const int64_t jcols = nd + (s->model.fixed_base ? 0 : 6);
+    d->dtype = 0;
+    d->device_id = s->device;
+    d->shape[0] = d->shape[1] = d->shape[2] = d->shape[3] = 1;
+    switch (kind) {
+        case B2G_T_ROOT_STATE: d->ndim = 2; d->shape[0] = n; d->shape[1] = 13; break;
+        case B2G_T_DOF_STATE: d->ndim = 2; d->shape[0] = n * nd; d->shape[1] = 2; break;
+        case B2G_T_NET_CONTACT: d->ndim = 2; d->shape[0] = n * nb; d->shape[1] = 3; break;
+        case B2G_T_DOF_FORCE: d->ndim = 1; d->shape[0] = n * nd; break;
+        case B2G_T_RIGID_BODY_STATE: d->ndim = 2; d->shape[0] = n * nb; d->shape[1] = 13; break;
+        case B2G_T_DOF_TARGET: d->ndim = 1; d->shape[0] = n * nd; break;
+        case B2G_T_DOF_ACTUATION: d->ndim = 1; d->shape[0] = n * nd; break;
+        case B2G_T_JACOBIAN: d->ndim = 4; d->shape[0] = n; d->shape[1] = nb; d->shape[2] = 6; d->shape[3] = jcols; break;
+        case B2G_T_MASS_MATRIX: d->ndim = 3; d->shape[0] = n; d->shape[1] = nd; d->shape[2] = nd; break;
+        case B2G_T_FRICTION: d->ndim = 1; d->shape[0] = n; break;
+        default: d->ndim = 0;
+    }
+}
+
+template <class F>
+int with_device(b2g_sim* s, F&& f) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != s->device) cudaSetDevice(s->device);
+    const int rc = f();
+    if (prev != s->device) cudaSetDevice(prev);
+    return rc;
+}
+
+int launch_simulate(b2g_sim* s, cudaStream_t st) {
+    const SimArgs A = make_args(s);
+    const int grid = grid_size(s);
+    const size_t sm = smem_bytes(s);
+    const bool hf = s->has_hf;
+    if (s->v.lanes == 1) k_simulate<1, 2, true, false><<<grid, kBlock, sm, st>>>(A);
+    else if (s->v.lanes == 4) { if (hf) k_simulate<4, 3, false, true><<<grid, kBlock, sm, st>>>(A); else k_simulate<4, 3, false, false><<<grid, kBlock, sm, st>>>(A); }
+    else if (s->v.fixed) k_simulate<8, 6, true, false><<<grid, kBlock, sm, st>>>(A);
+    else { if (hf) k_simulate<8, 6, false, true><<<grid, kBlock, sm, st>>>(A); else k_simulate<8, 6, false, false><<<grid, kBlock, sm, st>>>(A); }
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2G_OK;
+}
+
+int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, int post_only = 0) {
+    const SimArgs A = make_args(s);
+    const TaskArgs T = make_task_args(s, actions_dev, post_only);
+    const int grid = grid_size(s);
+    const size_t sm = smem_bytes(s);
+    if (s->v.lanes == 4) { if (s->has_hf) k_anymal_step<4, 3, true><<<grid, kBlock, sm, st>>>(A, T); else k_anymal_step<4, 3, false><<<grid, kBlock, sm, st>>>(A, T); }
+    else { if (s->has_hf) k_anymal_step<8, 6, true><<<grid, kBlock, sm, st>>>(A, T); else k_anymal_step<8, 6, false><<<grid, kBlock, sm, st>>>(A, T); }
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2G_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b2g_abi_version(void) { return B2G_ABI_VERSION; }
+const char* b2g_last_error(void) { return g_err; }
+
+// sizeof() of the public PODs, so the Python mirror can verify its layout
+int b2g_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(b2g_model);
+        case 1: return (int)sizeof(b2g_sim_params);
+        case 2: return (int)sizeof(b2g_dof_props);
+        case 3: return (int)sizeof(b2g_heightfield);
+        case 4: return (int)sizeof(b2g_tensor_desc);
+        case 5: return (int)sizeof(b2g_anymal_cfg);
+        default: return -1;
+    }
+}
+
+int b2g_sim_create(int device_id, const b2g_sim_params* params, b2g_sim** out) {
+    if (!params || !out) return fail(B2G_ERR_ARG, "null argument");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(B2G_ERR_CUDA, "no usable CUDA device (%s); libb200gym has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= count) return fail(B2G_ERR_ARG, "device %d out of range (%d devices)", device_id, count);
+    b2g_sim* s = new b2g_sim();
+    s->device = device_id;
+    s->params = *params;
+    if (s->params.substeps <= 0) s->params.substeps = 1;
+    *out = s;
+    return B2G_OK;
+}
+
+int b2g_sim_destroy(b2g_sim* s) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    with_device(s, [&]() {
+        for (int k = 0; k < B2G_T_COUNT; k++) if (s->t[k]) cudaFree(s->t[k]);
+        void* ptrs[] = {s->d_model, s->d_hf, s->obs, s->obs_clamped, s->rew, s->commands, s->actions, s->rand_override,
+                        s->reset, s->progress, s->timeout, s->reset_count, s->actions_in};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        return 0;
+    });
+    delete s;
+    return B2G_OK;
+}
+
+int b2g_sim_set_params(b2g_sim* s, const b2g_sim_params* p) {
+    if (!s || !p) return fail(B2G_ERR_ARG, "null argument");
+    const int ground = s->params.has_ground;
+    s->params = *p;
+    if (s->params.substeps <= 0) s->params.substeps = 1;
+    s->params.has_ground = ground || p->has_ground;
+    return B2G_OK;
+}
+
+int b2g_sim_get_params(const b2g_sim* s, b2g_sim_params* out) {
+    if (!s || !out) return fail(B2G_ERR_ARG, "null argument");
+    *out = s->params;
+    return B2G_OK;
+}
+
+int b2g_sim_add_ground(b2g_sim* s, float sf, float df, float rest) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    s->params.has_ground = 1;
+    s->params.plane_static_friction = sf;
+    s->params.plane_dynamic_friction = df;
+    s->params.plane_restitution = rest;
+    return B2G_OK;
+}
+
+int b2g_sim_add_heightfield(b2g_sim* s, const b2g_heightfield* hf, const int16_t* samples) {
+    if (!s || !hf || !samples) return fail(B2G_ERR_ARG, "null argument");
+    if (hf->rows < 2 || hf->cols < 2 || hf->horizontal_scale <= 0) return fail(B2G_ERR_ARG, "bad heightfield dimensions");
+    return with_device(s, [&]() {
+        if (s->d_hf) { cudaFree(s->d_hf); s->d_hf = nullptr; }
+        const size_t bytes = sizeof(int16_t) * (size_t)hf->rows * hf->cols;
+        CUDA_TRY(cudaMalloc(&s->d_hf, bytes));
+        CUDA_TRY(cudaMemcpy(s->d_hf, samples, bytes, cudaMemcpyHostToDevice));
+        s->hf = *hf;
+        s->has_hf = true;
+        return (int)B2G_OK;
+    });
+}
+
+int b2g_sim_add_articulation(b2g_sim* s, const b2g_model* model, const b2g_dof_props* props, int n_envs, const float* root_pose7,
+                             float env_spacing, int num_per_row) {
+    (void)env_spacing; (void)num_per_row;   // state tensors are env-local (Isaac Gym convention); the grid only matters for rendering
+    if (!s || !model || !props) return fail(B2G_ERR_ARG, "null argument");
+    if (s->has_model) return fail(B2G_ERR_UNSUPPORTED, "one articulation type per sim");
+    if (n_envs <= 0) return fail(B2G_ERR_ARG, "n_envs must be positive");
+    s->model = *model;
+    s->props = *props;
+    s->n_envs = n_envs;
+    if (root_pose7) memcpy(s->root_pose, root_pose7, sizeof(float) * 7);
+    s->v = pick_variant(*model);
+    const int rc = with_device(s, [&]() { return upload_model(s); });
+    if (rc != B2G_OK) return rc;
+    s->has_model = true;
+    return B2G_OK;
+}
+
+int b2g_sim_set_dof_props(b2g_sim* s, const b2g_dof_props* props) {
+    if (!s || !props) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->has_model) return fail(B2G_ERR_STATE, "no articulation yet");
+    s->props = *props;
+    return with_device(s, [&]() { return upload_model(s); });
+}
+
+int b2g_sim_prepare(b2g_sim* s) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    if (!s->has_model) return fail(B2G_ERR_STATE, "prepare_sim before any actor was created");
+    if (s->prepared) return B2G_OK;
+    return with_device(s, [&]() {
+        for (int k = 0; k < B2G_T_COUNT; k++) {
+            if (k == B2G_T_JACOBIAN || k == B2G_T_MASS_MATRIX) continue;   // allocated on first acquire
+            const size_t nf = tensor_floats(s, k);
+            CUDA_TRY(cudaMalloc(&s->t[k], sizeof(float) * (nf ? nf : 1)));
+            CUDA_TRY(cudaMemset(s->t[k], 0, sizeof(float) * (nf ? nf : 1)));
+        }
+        // initial root state = the create_actor pose, zero velocity; friction 1
+        float row[13] = {0};
+        memcpy(row, s->root_pose, sizeof(float) * 7);
+        float* d_row = nullptr;
+        CUDA_TRY(cudaMalloc(&d_row, sizeof(row)));
+        CUDA_TRY(cudaMemcpy(d_row, row, sizeof(row), cudaMemcpyHostToDevice));
+        k_fill_rows<<<(s->n_envs * 13 + 255) / 256, 256>>>(s->t[B2G_T_ROOT_STATE], d_row, s->n_envs, 13);
+        const float one = 1.0f;
+        CUDA_TRY(cudaMemcpy(d_row, &one, sizeof(float), cudaMemcpyHostToDevice));
+        k_fill_rows<<<(s->n_envs + 255) / 256, 256>>>(s->t[B2G_T_FRICTION], d_row, s->n_envs, 1);
+        s->launches += 2;
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(d_row);
+        // opt in to the dynamic shared memory the kernels need
+        const int sm = (int)smem_bytes(s);
+        cudaFuncSetAttribute(k_simulate<1, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_simulate<4, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_simulate<4, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_simulate<8, 6, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_simulate<8, 6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_simulate<8, 6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_anymal_step<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_anymal_step<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_anymal_step<8, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_anymal_step<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_probe<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_probe<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_probe<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_probe<8, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        s->prepared = true;
+        return (int)B2G_OK;
+    });
+}
+
+int b2g_sim_tensor(b2g_sim* s, int kind, b2g_tensor_desc* out) {
+    if (!s || !out) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "acquire_*_tensor before prepare_sim");
+    if (kind < 0 || kind >= B2G_T_COUNT) return fail(B2G_ERR_ARG, "unknown tensor kind %d", kind);
+    if (!s->t[kind]) {
+        const int rc = with_device(s, [&]() {
+            const size_t nf = tensor_floats(s, kind);
+            CUDA_TRY(cudaMalloc(&s->t[kind], sizeof(float) * (nf ? nf : 1)));
+            CUDA_TRY(cudaMemset(s->t[kind], 0, sizeof(float) * (nf ? nf : 1)));
+            return (int)B2G_OK;
+        });
+        if (rc != B2G_OK) return rc;
+    }
+    describe(s, kind, out);
+    out->data = s->t[kind];
+    return B2G_OK;
+}
+
+int b2g_sim_simulate(b2g_sim* s, void* stream) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "simulate before prepare_sim");
+    return with_device(s, [&]() { return launch_simulate(s, (cudaStream_t)stream); });
+}
+
+int b2g_sim_refresh(b2g_sim* s, int kind, void* stream) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "refresh before prepare_sim");
+    if (kind == B2G_T_RIGID_BODY_STATE) {
+        return with_device(s, [&]() {
+            k_body_state<<<(s->n_envs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s->d_model, s->t[B2G_T_ROOT_STATE], s->t[B2G_T_DOF_STATE],
+                                                                                s->t[B2G_T_RIGID_BODY_STATE], s->n_envs);
+            s->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return (int)B2G_OK;
+        });
+    }
+    if (kind == B2G_T_JACOBIAN || kind == B2G_T_MASS_MATRIX) return fail(B2G_ERR_UNSUPPORTED, "jacobian / mass-matrix tensors are not implemented yet");
+    return B2G_OK;   // live state: nothing to do
+}
+
+int b2g_sim_set_indexed(b2g_sim* s, int kind, const void* src, const int32_t* idx, int n, void* stream) {
+    if (!s || !src || (!idx && n > 0)) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "set_*_indexed before prepare_sim");
+    if (kind < 0 || kind >= B2G_T_COUNT || !s->t[kind]) return fail(B2G_ERR_ARG, "unknown tensor kind %d", kind);
+    if (n <= 0 || src == s->t[kind]) return B2G_OK;   // the task edited the live tensor in place
+    int row = 0;
+    const int nd = s->model.n_dof;
+    switch (kind) {
+        case B2G_T_ROOT_STATE: row = 13; break;
+        case B2G_T_DOF_STATE: row = nd * 2; break;
+        case B2G_T_DOF_TARGET: case B2G_T_DOF_ACTUATION: row = nd; break;
+        default: return fail(B2G_ERR_UNSUPPORTED, "indexed set not supported for tensor kind %d", kind);
+    }
+    return with_device(s, [&]() {
+        k_copy_rows<<<(n * row + 255) / 256, 256, 0, (cudaStream_t)stream>>>(s->t[kind], (const float*)src, idx, n, row);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return (int)B2G_OK;
+    });
+}
+
+int b2g_sim_set_tensor(b2g_sim* s, int kind, const void* src, void* stream) {
+    if (!s || !src) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "set_*_tensor before prepare_sim");
+    if (kind < 0 || kind >= B2G_T_COUNT || !s->t[kind]) return fail(B2G_ERR_ARG, "unknown tensor kind %d", kind);
+    if (src == s->t[kind]) return B2G_OK;
+    return with_device(s, [&]() {
+        CUDA_TRY(cudaMemcpyAsync(s->t[kind], src, sizeof(float) * tensor_floats(s, kind), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return (int)B2G_OK;
+    });
+}
+
+int b2g_sim_forward_dynamics(b2g_sim* s, float* qdd, float* a0, void* stream) {
+    if (!s || !qdd || !a0) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "forward_dynamics before prepare_sim");
+    return with_device(s, [&]() {
+        const SimArgs A = make_args(s);
+        const int grid = grid_size(s);
+        const size_t sm = smem_bytes(s);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (s->v.lanes == 1) k_probe<1, 2, true><<<grid, kBlock, sm, st>>>(A, qdd, a0);
+        else if (s->v.lanes == 4) k_probe<4, 3, false><<<grid, kBlock, sm, st>>>(A, qdd, a0);
+        else if (s->v.fixed) k_probe<8, 6, true><<<grid, kBlock, sm, st>>>(A, qdd, a0);
+        else k_probe<8, 6, false><<<grid, kBlock, sm, st>>>(A, qdd, a0);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return (int)B2G_OK;
+    });
+}
+
+// ---- fused flat task ----
+int b2g_task_anymal_create(b2g_sim* s, const b2g_anymal_cfg* cfg) {
+    if (!s || !cfg) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "task created before prepare_sim");
+    if (s->model.fixed_base) return fail(B2G_ERR_UNSUPPORTED, "the flat locomotion task needs a floating base");
+    if (cfg->base_body < 0 || cfg->base_body >= s->model.n_bodies || cfg->n_knee < 0 || cfg->n_knee > 8)
+        return fail(B2G_ERR_ARG, "bad base/knee body indices");
+    for (int k = 0; k < cfg->n_knee; k++)
+        if (cfg->knee_bodies[k] < 0 || cfg->knee_bodies[k] >= s->model.n_bodies) return fail(B2G_ERR_ARG, "bad knee body index");
+    s->acfg = *cfg;
+    if (s->has_task) return B2G_OK;
+    return with_device(s, [&]() {
+        const size_t n = s->n_envs, nd = s->model.n_dof;
+        s->num_obs = 12 + 3 * (int)nd;
+        CUDA_TRY(cudaMalloc(&s->obs, sizeof(float) * n * s->num_obs));
+        CUDA_TRY(cudaMalloc(&s->obs_clamped, sizeof(float) * n * s->num_obs));
+        CUDA_TRY(cudaMalloc(&s->rew, sizeof(float) * n));
+        CUDA_TRY(cudaMalloc(&s->commands, sizeof(float) * n * 3));
+        CUDA_TRY(cudaMalloc(&s->actions, sizeof(float) * n * nd));
+        CUDA_TRY(cudaMalloc(&s->actions_in, sizeof(float) * n * nd));
+        CUDA_TRY(cudaMalloc(&s->rand_override, sizeof(float) * n * (2 * nd + 3)));
+        CUDA_TRY(cudaMalloc(&s->reset, sizeof(long long) * n));
+        CUDA_TRY(cudaMalloc(&s->progress, sizeof(long long) * n));
+        CUDA_TRY(cudaMalloc(&s->timeout, sizeof(long long) * n));
+        CUDA_TRY(cudaMalloc(&s->reset_count, sizeof(int) * n));
+        CUDA_TRY(cudaMemset(s->obs, 0, sizeof(float) * n * s->num_obs));
+        CUDA_TRY(cudaMemset(s->obs_clamped, 0, sizeof(float) * n * s->num_obs));
+        CUDA_TRY(cudaMemset(s->rew, 0, sizeof(float) * n));
+        CUDA_TRY(cudaMemset(s->commands, 0, sizeof(float) * n * 3));
+        CUDA_TRY(cudaMemset(s->actions, 0, sizeof(float) * n * nd));
+        CUDA_TRY(cudaMemset(s->rand_override, 0, sizeof(float) * n * (2 * nd + 3)));
+        CUDA_TRY(cudaMemset(s->progress, 0, sizeof(long long) * n));
+        CUDA_TRY(cudaMemset(s->timeout, 0, sizeof(long long) * n));
+        CUDA_TRY(cudaMemset(s->reset_count, 0, sizeof(int) * n));
+        k_fill_i64<<<((int)n + 255) / 256, 256>>>(s->reset, 1, (int)n);   // reset_buf starts at ones (vec_task.py:316)
+        s->launches++;
+        CUDA_TRY(cudaDeviceSynchronize());
+        s->has_task = true;
+        return (int)B2G_OK;
+    });
+}
+
+int b2g_task_tensor(b2g_sim* s, int kind, b2g_tensor_desc* d) {
+    if (!s || !d) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
+    const int64_t n = s->n_envs, nd = s->model.n_dof;
+    d->device_id = s->device;
+    d->dtype = 0;
+    d->shape[0] = n; d->shape[1] = d->shape[2] = d->shape[3] = 1;
+    d->ndim = 1;
+    switch (kind) {
+        case B2G_TT_OBS: d->data = s->obs; d->ndim = 2; d->shape[1] = s->num_obs; break;
+        case B2G_TT_OBS_CLAMPED: d->data = s->obs_clamped; d->ndim = 2; d->shape[1] = s->num_obs; break;
+        case B2G_TT_REW: d->data = s->rew; break;
+        case B2G_TT_RESET: d->data = s->reset; d->dtype = 2; break;
+        case B2G_TT_PROGRESS: d->data = s->progress; d->dtype = 2; break;
+        case B2G_TT_TIMEOUT: d->data = s->timeout; d->dtype = 2; break;
+        case B2G_TT_COMMANDS: d->data = s->commands; d->ndim = 2; d->shape[1] = 3; break;
+        case B2G_TT_ACTIONS: d->data = s->actions; d->ndim = 2; d->shape[1] = nd; break;
+        case B2G_TT_RAND_OVERRIDE: d->data = s->rand_override; d->ndim = 2; d->shape[1] = 2 * nd + 3; break;
+        default: return fail(B2G_ERR_ARG, "unknown task tensor kind %d", kind);
+    }
+    return B2G_OK;
+}
+
+int b2g_task_set_rand_override(b2g_sim* s, int use) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    s->use_rand_override = use;
+    return B2G_OK;
+}
+
+int b2g_task_anymal_reset_all(b2g_sim* s, void* stream) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
+    return with_device(s, [&]() {
+        const SimArgs A = make_args(s);
+        const TaskArgs T = make_task_args(s, nullptr);
+        const int grid = grid_size(s);
+        if (s->v.lanes == 4) k_anymal_reset_all<4, 3><<<grid, kBlock, 0, (cudaStream_t)stream>>>(A, T);
+        else k_anymal_reset_all<8, 6><<<grid, kBlock, 0, (cudaStream_t)stream>>>(A, T);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return (int)B2G_OK;
+    });
+}
+
+int b2g_task_anymal_step(b2g_sim* s, const float* actions_dev, void* stream) {
+    if (!s || !actions_dev) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
+    return with_device(s, [&]() { return launch_anymal_step(s, actions_dev, (cudaStream_t)stream); });
+}
+
+int b2g_task_anymal_post_only(b2g_sim* s, const float* actions_dev, void* stream) {
+    if (!s || !actions_dev) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
+    return with_device(s, [&]() { return launch_anymal_step(s, actions_dev, (cudaStream_t)stream, 1); });
+}
+
+int b2g_task_anymal_step_host(b2g_sim* s, const float* actions_host, float* obs_host, float* rew_host, int64_t* reset_host,
+                              int64_t* timeout_host, void* stream) {
+    if (!s || !actions_host) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
+    return with_device(s, [&]() {
+        cudaStream_t st = (cudaStream_t)stream;
+        const size_t n = s->n_envs, nd = s->model.n_dof;
+        CUDA_TRY(cudaMemcpyAsync(s->actions_in, actions_host, sizeof(float) * n * nd, cudaMemcpyHostToDevice, st));
+        const int rc = launch_anymal_step(s, s->actions_in, st);
+        if (rc != B2G_OK) return rc;
+        if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, s->obs_clamped, sizeof(float) * n * s->num_obs, cudaMemcpyDeviceToHost, st));
+        if (rew_host) CUDA_TRY(cudaMemcpyAsync(rew_host, s->rew, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        if (reset_host) CUDA_TRY(cudaMemcpyAsync(reset_host, s->reset, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        if (timeout_host) CUDA_TRY(cudaMemcpyAsync(timeout_host, s->timeout, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return (int)B2G_OK;
+    });
+}
+
+int64_t b2g_sim_launch_count(const b2g_sim* s) { return s ? s->launches : 0; }
+
+// ---- DLPack export (dlpack v0.8 ABI, declared locally: plain C structs) ----
+typedef struct { int32_t device_type; int32_t device_id; } B2gDLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } B2gDLDataType;
+typedef struct {
+    void* data; B2gDLDevice device; int32_t ndim; B2gDLDataType dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset;
+} B2gDLTensor;
+typedef struct B2gDLManagedTensor {
+    B2gDLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct B2gDLManagedTensor*);
+} B2gDLManagedTensor;
+
+static void b2g_dl_deleter(B2gDLManagedTensor* m) {
+    if (!m) return;
+    free(m->dl_tensor.shape);   // the data stays owned by the sim
+    free(m);
+}
+
+// Wrap a tensor description as a DLManagedTensor (non-owning view; valid until b2g_sim_destroy).
+int b2g_dlpack_from_desc(const b2g_tensor_desc* d, void** out_managed) {
+    if (!d || !out_managed || !d->data) return fail(B2G_ERR_ARG, "null argument");
+    B2gDLManagedTensor* m = (B2gDLManagedTensor*)calloc(1, sizeof(B2gDLManagedTensor));
+    int64_t* shape = (int64_t*)calloc(4, sizeof(int64_t));
+    if (!m || !shape) { free(m); free(shape); return fail(B2G_ERR_ARG, "out of host memory"); }
+    for (int i = 0; i < d->ndim; i++) shape[i] = d->shape[i];
+    m->dl_tensor.data = d->data;
+    m->dl_tensor.device.device_type = 2;   // kDLCUDA
+    m->dl_tensor.device.device_id = d->device_id;
+    m->dl_tensor.ndim = d->ndim;
+    switch (d->dtype) {
+        case 0: m->dl_tensor.dtype = B2gDLDataType{2, 32, 1}; break;   // float32
+        case 1: m->dl_tensor.dtype = B2gDLDataType{0, 32, 1}; break;   // int32
+        case 2: m->dl_tensor.dtype = B2gDLDataType{0, 64, 1}; break;   // int64
+        case 3: m->dl_tensor.dtype = B2gDLDataType{1, 8, 1}; break;    // uint8
+        case 4: m->dl_tensor.dtype = B2gDLDataType{0, 16, 1}; break;   // int16
+        default: free(m); free(shape); return fail(B2G_ERR_ARG, "bad dtype");
+    }
+    m->dl_tensor.shape = shape;
+    m->dl_tensor.strides = nullptr;
+    m->dl_tensor.byte_offset = 0;
+    m->manager_ctx = nullptr;
+    m->deleter = b2g_dl_deleter;
+    *out_managed = m;
+    return B2G_OK;
+}
+
+}  // extern "C"

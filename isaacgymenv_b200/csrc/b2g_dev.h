@@ -1,0 +1,59 @@
+// Device-side (kernel-facing) model / parameter structures, built by the host API from the public
+// b2g_model / b2g_dof_props / b2g_sim_params PODs of include/b200gym.h.
+#pragma once
+
+#include <stdint.h>
+
+#include "b200gym.h"
+
+namespace b2g {
+
+struct DevDof {
+    float jpos[3];      // joint frame origin in the parent link frame
+    int type;           // b2g_joint_type
+    float jrot[9];      // joint frame rotation in the parent frame (row-major)
+    float axis[3];      // unit axis in the child frame
+    float mass;
+    float com[3];
+    float armature;
+    float inertia[6];   // xx, xy, xz, yy, yz, zz about the com, link axes
+    int cp_start, cp_count;   // contact candidates riding on this link
+    float kp, kd, effort, vel_limit;
+    float lower, upper;
+    int drive_mode;
+    int pad;
+};
+
+struct DevModel {
+    int fixed_base, n_dof, n_bodies, n_chains;
+    int chain_start[B2G_MAX_CHAINS];
+    int chain_len[B2G_MAX_CHAINS];
+    int root_cp_start[B2G_MAX_CHAINS];   // root-link candidates owned by each lane
+    int root_cp_count[B2G_MAX_CHAINS];
+    float root_mass;
+    float root_com[3];
+    float root_inertia[6];
+    DevDof dof[B2G_MAX_DOF];
+    float cp[B2G_MAX_CPTS][4];   // link-frame position, radius
+    int cp_body[B2G_MAX_CPTS];
+    int body_link[B2G_MAX_BODIES];
+    float body_pos[B2G_MAX_BODIES][3];
+    float body_quat[B2G_MAX_BODIES][4];
+};
+
+struct DevParams {
+    float h;             // sub-step length
+    int substeps;
+    float g[3];
+    int npos, nvel;
+    float contact_offset;
+    float max_depen;
+    float mu_ground;
+    int has_ground;
+    // heightfield (null -> plane z = 0)
+    const int16_t* hf;
+    int hf_rows, hf_cols;
+    float hf_hs, hf_vs, hf_ox, hf_oy;
+};
+
+}  // namespace b2g

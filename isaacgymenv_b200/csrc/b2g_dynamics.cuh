@@ -1,0 +1,611 @@
+// One physics sub-step for one environment, executed by a group of LANES cooperating threads (one
+// thread per serial chain hanging off the root: a leg, the arm).  This is what replaces PhysX behind
+// `gym.simulate` (reference: isaacgymenvs/tasks/base/vec_task.py:379-382, solver settings
+// cfg/task/Anymal.yaml:81-100, drives tasks/anymal.py:199-203).
+//
+// Algorithm (DESIGN.md "dynamics"): Featherstone articulated-body algorithm in one common frame (world
+// axes at the root origin, so no spatial transforms inside the recursion); implicit PD drives folded
+// into the joint-space diagonal; hard contact solved at the velocity level by projected Gauss-Seidel
+// with impulses propagated through the articulated inertias; position iterations with penetration
+// bias, positions integrated, then velocity iterations without bias; semi-implicit Euler.
+//
+// Parallel mapping: each lane owns one chain (kinematics, ABA recursion, its contact candidates); the
+// root's 6x6 articulated inertia and bias are summed across the lanes with warp shuffles, the root
+// solve is replicated, and every Gauss-Seidel impulse is broadcast from its owner lane as a 6-vector.
+#pragma once
+
+#include "b2g_dev.h"
+#include "b2g_math.cuh"
+
+namespace b2g {
+
+constexpr int MAXC = B2G_MAX_CONTACTS_PER_CHAIN;
+
+// per-thread scratch for the (dynamically indexed) contact slots
+enum ContactField {
+    CF_RX, CF_RY, CF_RZ, CF_NX, CF_NY, CF_NZ, CF_T1X, CF_T1Y, CF_T1Z, CF_T2X, CF_T2Y, CF_T2Z,
+    CF_GAP, CF_JC, CF_BODY, CF_ANN, CF_ANT1, CF_ANT2, CF_AT1T1, CF_AT1T2, CF_AT2T2, CF_LN, CF_L1, CF_L2, CF_COUNT
+};
+
+#if defined(B2G_HOST_EMU)
+// ---- host lane emulator (tests only): LANES host threads in lock-step through a spin barrier ----
+struct EmuGroup {
+    int lanes;
+    volatile int count;
+    volatile int sense;
+    float fslot[8];
+    int islot[8];
+};
+struct EmuCtx {
+    EmuGroup* g;
+    int lane;
+    int local_sense;
+};
+extern thread_local EmuCtx emu_ctx;
+inline void emu_barrier() {
+    EmuGroup* g = emu_ctx.g;
+    if (g->lanes == 1) return;
+    int s = emu_ctx.local_sense ^= 1;
+    if (__atomic_add_fetch(&g->count, 1, __ATOMIC_ACQ_REL) == g->lanes) {
+        g->count = 0;
+        __atomic_store_n(&g->sense, s, __ATOMIC_RELEASE);
+    } else {
+        while (__atomic_load_n(&g->sense, __ATOMIC_ACQUIRE) != s) {
+        }
+    }
+}
+template <int LANES>
+struct Grp {
+    static float bcast(float x, int src) {
+        if (LANES == 1) return x;
+        emu_ctx.g->fslot[emu_ctx.lane] = x;
+        emu_barrier();
+        float r = emu_ctx.g->fslot[src];
+        emu_barrier();
+        return r;
+    }
+    static float sum(float x) {
+        if (LANES == 1) return x;
+        // same butterfly order as the device xor-shuffle reduction
+        for (int o = LANES / 2; o > 0; o >>= 1) {
+            emu_ctx.g->fslot[emu_ctx.lane] = x;
+            emu_barrier();
+            float other = emu_ctx.g->fslot[emu_ctx.lane ^ o];
+            emu_barrier();
+            x += other;
+        }
+        return x;
+    }
+    static int warp_max(int x) {
+        if (LANES == 1) return x;
+        emu_ctx.g->islot[emu_ctx.lane] = x;
+        emu_barrier();
+        int r = x;
+        for (int i = 0; i < LANES; i++) r = emu_ctx.g->islot[i] > r ? emu_ctx.g->islot[i] : r;
+        emu_barrier();
+        return r;
+    }
+    static bool warp_any(bool p) { return warp_max(p ? 1 : 0) != 0; }
+    static void sync() { emu_barrier(); }
+};
+#else
+template <int LANES>
+struct Grp {
+    static __device__ __forceinline__ float bcast(float x, int src) {
+        if (LANES == 1) return x;
+        return __shfl_sync(0xffffffffu, x, src, LANES);
+    }
+    static __device__ __forceinline__ float sum(float x) {
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        return x;
+    }
+    static __device__ __forceinline__ int warp_max(int x) { return __reduce_max_sync(0xffffffffu, x); }
+    static __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+#endif
+
+template <int LANES>
+B2G_HD B2G_INL SV grp_bcast(SV s, int src) {
+    return SV{V3{Grp<LANES>::bcast(s.w.x, src), Grp<LANES>::bcast(s.w.y, src), Grp<LANES>::bcast(s.w.z, src)},
+              V3{Grp<LANES>::bcast(s.v.x, src), Grp<LANES>::bcast(s.v.y, src), Grp<LANES>::bcast(s.v.z, src)}};
+}
+template <int LANES>
+B2G_HD B2G_INL SV grp_sum(SV s) {
+    return SV{V3{Grp<LANES>::sum(s.w.x), Grp<LANES>::sum(s.w.y), Grp<LANES>::sum(s.w.z)},
+              V3{Grp<LANES>::sum(s.v.x), Grp<LANES>::sum(s.v.y), Grp<LANES>::sum(s.v.z)}};
+}
+template <int LANES>
+B2G_HD B2G_INL SI grp_sum(const SI& s) {
+    SI o;
+    o.A.xx = Grp<LANES>::sum(s.A.xx); o.A.xy = Grp<LANES>::sum(s.A.xy); o.A.xz = Grp<LANES>::sum(s.A.xz);
+    o.A.yy = Grp<LANES>::sum(s.A.yy); o.A.yz = Grp<LANES>::sum(s.A.yz); o.A.zz = Grp<LANES>::sum(s.A.zz);
+    o.C.xx = Grp<LANES>::sum(s.C.xx); o.C.xy = Grp<LANES>::sum(s.C.xy); o.C.xz = Grp<LANES>::sum(s.C.xz);
+    o.C.yy = Grp<LANES>::sum(s.C.yy); o.C.yz = Grp<LANES>::sum(s.C.yz); o.C.zz = Grp<LANES>::sum(s.C.zz);
+#pragma unroll
+    for (int k = 0; k < 9; k++) o.B.m[k] = Grp<LANES>::sum(s.B.m[k]);
+    return o;
+}
+
+// state one lane keeps in registers across the sub-steps of a simulate() call
+template <int NL>
+struct LaneState {
+    V3 rp;                  // root position (world)
+    float qx, qy, qz, qw;   // root orientation
+    V3 rv, rw;              // root linear / angular velocity (world)
+    float q[NL], qd[NL];    // this lane's chain
+    float tgt[NL], act[NL]; // drive targets / efforts
+    float frc[NL];          // DOF force output
+};
+
+// per-thread contact scratch: field f of slot s
+struct ScratchStrided {
+    float* base;   // points at this thread's column
+    int stride;    // number of threads sharing the buffer
+    B2G_HD B2G_INL float& at(int slot, int f) { return base[(slot * CF_COUNT + f) * stride]; }
+};
+
+B2G_HD B2G_INL void ground_sample(const DevParams& P, float x, float y, float& hgt, V3& n) {
+    float gx = (x - P.hf_ox) / P.hf_hs, gy = (y - P.hf_oy) / P.hf_hs;
+    gx = fminf(fmaxf(gx, 0.0f), (float)(P.hf_rows - 1));
+    gy = fminf(fmaxf(gy, 0.0f), (float)(P.hf_cols - 1));
+    int i = (int)gx, j = (int)gy;
+    i = i > P.hf_rows - 2 ? P.hf_rows - 2 : i;
+    j = j > P.hf_cols - 2 ? P.hf_cols - 2 : j;
+    float fx = gx - (float)i, fy = gy - (float)j;
+    const int16_t* s = P.hf + (size_t)i * P.hf_cols + j;
+    float h00 = P.hf_vs * (float)s[0], h01 = P.hf_vs * (float)s[1];
+    float h10 = P.hf_vs * (float)s[P.hf_cols], h11 = P.hf_vs * (float)s[P.hf_cols + 1];
+    float dzdx, dzdy;
+    if (fx >= fy) { dzdx = h10 - h00; dzdy = h11 - h10; }
+    else { dzdx = h11 - h01; dzdy = h01 - h00; }
+    hgt = h00 + dzdx * fx + dzdy * fy;
+    float nx = -dzdx / P.hf_hs, ny = -dzdy / P.hf_hs;
+    float inv = 1.0f / sqrtf(nx * nx + ny * ny + 1.0f);
+    n = V3{nx * inv, ny * inv, inv};
+}
+
+// One sub-step.  `len` = links in this lane's chain (0 for an idle lane), `d0` = first DOF of the chain.
+// `bf` = this environment's body-force accumulator (n_bodies*3 floats, shared by the group), written on
+// the last sub-step only.
+// PROBE = true turns the call into the forward-dynamics probe of the parity tests: efforts st.act are
+// applied raw (no drives), the function returns after the ABA with joint accelerations in st.frc and the
+// root's spatial acceleration (angular, linear) in st.rw / st.rv.
+template <int LANES, int NL, bool FIXED, bool HF, bool PROBE = false>
+B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, int lane, int len, int d0,
+                            LaneState<NL>& st, float mu_shape, bool last, ScratchStrided sc, float* bf) {
+    const float h = P.h;
+    const V3 grav = V3{P.g[0], P.g[1], P.g[2]};
+
+    // ---------------- kinematics down the chain ----------------
+    const M3 R0 = quat_to_m3(st.qx, st.qy, st.qz, st.qw);
+    const SV v0 = FIXED ? sv0() : SV{st.rw, st.rv};
+    M3 Rl[NL];
+    V3 pl[NL];
+    SV S[NL], cb[NL], vl[NL];
+    float tau[NL], dext[NL];
+    {
+        M3 Rp = R0;
+        V3 pp = V3{0, 0, 0};
+        SV vp = v0;
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            if (j < len) {
+                const DevDof& D = M->dof[d0 + j];
+                M3 jr;
+#pragma unroll
+                for (int k = 0; k < 9; k++) jr.m[k] = D.jrot[k];
+                const V3 ax = V3{D.axis[0], D.axis[1], D.axis[2]};
+                const M3 RJ = mul(Rp, jr);
+                const V3 pj = pp + mul(Rp, V3{D.jpos[0], D.jpos[1], D.jpos[2]});
+                const V3 axw = mul(RJ, ax);
+                if (D.type == B2G_JOINT_REVOLUTE) {
+                    Rl[j] = mul(RJ, axis_angle_m3(ax, st.q[j]));
+                    pl[j] = pj;
+                    S[j] = SV{axw, cross(pj, axw)};
+                } else {
+                    Rl[j] = RJ;
+                    pl[j] = pj + axw * st.q[j];
+                    S[j] = SV{V3{0, 0, 0}, axw};
+                }
+                const SV vj = S[j] * st.qd[j];
+                vl[j] = vp + vj;
+                cb[j] = crm(vl[j], vj);
+                // drive
+                const float kp = D.kp, kd = D.kd;
+                float t = 0.0f, de = D.armature;
+                if (PROBE) {
+                    t = st.act[j];
+                } else if (D.drive_mode == B2G_DOF_MODE_POS) {
+                    t = kp * (st.tgt[j] - st.q[j]) - (kd + h * kp) * st.qd[j];
+                    de += h * kd + h * h * kp;
+                } else if (D.drive_mode == B2G_DOF_MODE_VEL) {
+                    t = kd * (st.tgt[j] - st.qd[j]);
+                    de += h * kd;
+                } else if (D.drive_mode == B2G_DOF_MODE_EFFORT) {
+                    t = st.act[j];
+                    if (D.effort > 0.0f) t = fminf(fmaxf(t, -D.effort), D.effort);
+                }
+                tau[j] = t;
+                dext[j] = de;
+                Rp = Rl[j]; pp = pl[j]; vp = vl[j];
+            } else {
+                Rl[j] = R0; pl[j] = V3{0, 0, 0}; S[j] = sv0(); cb[j] = sv0(); vl[j] = sv0(); tau[j] = 0; dext[j] = 1.0f;
+            }
+        }
+    }
+
+    // ---------------- ABA backward: articulated inertias and bias forces ----------------
+    SV U[NL];
+    float Dinv[NL], u[NL];
+    SI IAc;
+    SV pAc = sv0();
+    {
+        IAc.A = S3{0, 0, 0, 0, 0, 0}; IAc.C = S3{0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 9; k++) IAc.B.m[k] = 0;
+#pragma unroll
+        for (int j = NL - 1; j >= 0; j--) {
+            if (j < len) {
+                const DevDof& D = M->dof[d0 + j];
+                const V3 cw = pl[j] + mul(Rl[j], V3{D.com[0], D.com[1], D.com[2]});
+                const S3 iw = rotate_sym(Rl[j], S3{D.inertia[0], D.inertia[1], D.inertia[2], D.inertia[3], D.inertia[4], D.inertia[5]});
+                SI I = rigid_inertia(D.mass, cw, iw);
+                SV pA = crf(vl[j], mul(I, vl[j]));
+                if (j + 1 < len) { I += IAc; pA += pAc; }
+                U[j] = mul(I, S[j]);
+                const float Dj = dot(S[j], U[j]) + dext[j];
+                Dinv[j] = 1.0f / Dj;
+                u[j] = tau[j] - dot(S[j], pA);
+                IAc = rank1_sub(I, U[j], Dinv[j]);
+                pAc = pA + mul(IAc, cb[j]) + U[j] * (u[j] * Dinv[j]);
+            } else {
+                U[j] = sv0(); Dinv[j] = 0.0f; u[j] = 0.0f;
+            }
+        }
+    }
+
+    // ---------------- root: sum the chains, solve ----------------
+    P6 inv;
+    SV a0 = sv0();   // relative root acceleration a' = a - a_g
+    if (!FIXED) {
+        SI IA0 = grp_sum<LANES>(IAc);
+        SV pA0 = grp_sum<LANES>(pAc);
+        const V3 cw = mul(R0, V3{M->root_com[0], M->root_com[1], M->root_com[2]});
+        const S3 iw = rotate_sym(R0, S3{M->root_inertia[0], M->root_inertia[1], M->root_inertia[2], M->root_inertia[3], M->root_inertia[4], M->root_inertia[5]});
+        SI I0 = rigid_inertia(M->root_mass, cw, iw);
+        pA0 += crf(v0, mul(I0, v0));
+        IA0 += I0;
+        bool ok;
+        inv = spd_inverse6(pack6(IA0), ok);
+        a0 = -mul(inv, pA0);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 21; k++) inv.a[k] = 0.0f;
+    }
+
+    // ---------------- ABA forward: accelerations, free velocities ----------------
+    float qdn[NL];
+    SV v0n = sv0();
+    {
+        SV a = FIXED ? SV{V3{0, 0, 0}, -grav} : a0;
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            if (j < len) {
+                const SV ap = a + cb[j];
+                const float qdd = (u[j] - dot(U[j], ap)) * Dinv[j];
+                a = ap + S[j] * qdd;
+                qdn[j] = st.qd[j] + h * qdd;
+                if (PROBE) st.frc[j] = qdd;
+            } else {
+                qdn[j] = 0.0f;
+            }
+        }
+        if (!FIXED) {
+            // root origin is a body-fixed point: classical acceleration = spatial + w x v
+            v0n.w = st.rw + a0.w * h;
+            v0n.v = st.rv + (a0.v + grav + cross(st.rw, st.rv)) * h;
+        }
+    }
+
+    if (PROBE) {
+        st.rw = a0.w;
+        st.rv = FIXED ? V3{0, 0, 0} : a0.v + grav;
+        return;
+    }
+
+    // impulse helpers -----------------------------------------------------------------
+    // backward half: impulse F on link `jc` of this chain (-1 = root, -2 = none) and joint impulse tj on
+    // joint `jd` (-1 = none); returns the root-level bias Pb and per-joint ud[]
+    auto push_up = [&](int jc, SV F, int jd, float tj, float* ud) -> SV {
+        SV Pb = (jc >= -1) ? -F : sv0();
+        const int top = jc > jd ? jc : jd;
+#pragma unroll
+        for (int i = NL - 1; i >= 0; i--) {
+            if (i <= top) {
+                ud[i] = ((i == jd) ? tj : 0.0f) - dot(S[i], Pb);
+                Pb += U[i] * (ud[i] * Dinv[i]);
+            } else {
+                ud[i] = 0.0f;
+            }
+        }
+        return Pb;
+    };
+
+    // ---------------- contact candidates ----------------
+    int ncon = 0;
+    const bool ground = HF || (P.has_ground != 0);
+    auto test_candidate = [&](int i, const M3& R, V3 p, int jc) {
+        const float cx = M->cp[i][0], cy = M->cp[i][1], cz = M->cp[i][2], cr = M->cp[i][3];
+        const V3 rc = p + mul(R, V3{cx, cy, cz});
+        float gh = 0.0f;
+        V3 n = V3{0, 0, 1};
+        if (HF) ground_sample(P, st.rp.x + rc.x, st.rp.y + rc.y, gh, n);
+        const float gap = (st.rp.z + rc.z - gh) * n.z - cr;
+        if (gap < P.contact_offset && ncon < MAXC) {
+            const V3 r = rc - n * cr;
+            V3 t1 = V3{1.0f - n.x * n.x, -n.x * n.y, -n.x * n.z};
+            t1 = t1 * (1.0f / sqrtf(dot(t1, t1)));
+            const V3 t2 = cross(n, t1);
+            const int s = ncon++;
+            sc.at(s, CF_RX) = r.x; sc.at(s, CF_RY) = r.y; sc.at(s, CF_RZ) = r.z;
+            sc.at(s, CF_NX) = n.x; sc.at(s, CF_NY) = n.y; sc.at(s, CF_NZ) = n.z;
+            sc.at(s, CF_T1X) = t1.x; sc.at(s, CF_T1Y) = t1.y; sc.at(s, CF_T1Z) = t1.z;
+            sc.at(s, CF_T2X) = t2.x; sc.at(s, CF_T2Y) = t2.y; sc.at(s, CF_T2Z) = t2.z;
+            sc.at(s, CF_GAP) = gap;
+            sc.at(s, CF_JC) = (float)jc;
+            sc.at(s, CF_BODY) = (float)M->cp_body[i];
+            sc.at(s, CF_LN) = 0.0f; sc.at(s, CF_L1) = 0.0f; sc.at(s, CF_L2) = 0.0f;
+            // local Delassus block: response of this contact point to unit impulses along n, t1, t2
+            const V3 dirs[3] = {n, t1, t2};
+            float A[9];
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                float ud[NL];
+                const SV F = SV{cross(r, dirs[b]), dirs[b]};
+                const SV Pb = push_up(jc, F, -1, 0.0f, ud);
+                SV a = FIXED ? sv0() : -mul(inv, Pb);
+#pragma unroll
+                for (int k = 0; k < NL; k++) {
+                    if (k <= jc) {
+                        const float dq = (ud[k] - dot(U[k], a)) * Dinv[k];
+                        a += S[k] * dq;
+                    }
+                }
+                const V3 pv = a.v + cross(a.w, r);
+#pragma unroll
+                for (int c = 0; c < 3; c++) A[c * 3 + b] = dot(pv, dirs[c]);
+            }
+            sc.at(s, CF_ANN) = A[0]; sc.at(s, CF_ANT1) = A[3]; sc.at(s, CF_ANT2) = A[6];
+            sc.at(s, CF_AT1T1) = A[4]; sc.at(s, CF_AT1T2) = A[7]; sc.at(s, CF_AT2T2) = A[8];
+        }
+    };
+    if (ground) {
+#pragma unroll
+        for (int j = NL - 1; j >= 0; j--) {
+            if (j < len) {
+                const int c0 = M->dof[d0 + j].cp_start, cn = M->dof[d0 + j].cp_count;
+                for (int i = c0; i < c0 + cn; i++) test_candidate(i, Rl[j], pl[j], j);
+            }
+        }
+        if (!FIXED) {
+            const int c0 = M->root_cp_start[lane], cn = M->root_cp_count[lane];
+            for (int i = c0; i < c0 + cn; i++) test_candidate(i, R0, V3{0, 0, 0}, -1);
+        }
+    }
+
+    // ---------------- joint limits ----------------
+    bool lim_on[NL];
+    float lim_sign[NL], lim_gap[NL], lim_A[NL], lim_lam[NL];
+    bool any_lim = false;
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        lim_on[j] = false; lim_sign[j] = 0; lim_gap[j] = 0; lim_A[j] = 1.0f; lim_lam[j] = 0;
+        if (j < len) {
+            const float lo = M->dof[d0 + j].lower, hi = M->dof[d0 + j].upper;
+            const float qp = st.q[j] + h * qdn[j];
+            if (lo > -1e30f && qp < lo) { lim_on[j] = true; lim_sign[j] = 1.0f; lim_gap[j] = st.q[j] - lo; }
+            else if (hi < 1e30f && qp > hi) { lim_on[j] = true; lim_sign[j] = -1.0f; lim_gap[j] = hi - st.q[j]; }
+            any_lim = any_lim || lim_on[j];
+        }
+    }
+    const bool warp_lim = Grp<LANES>::warp_any(any_lim);
+    if (warp_lim) {
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            if (lim_on[j]) {
+                float ud[NL];
+                const SV Pb = push_up(-2, sv0(), j, 1.0f, ud);
+                SV a = FIXED ? sv0() : -mul(inv, Pb);
+                float dqj = 0.0f;
+#pragma unroll
+                for (int k = 0; k < NL; k++) {
+                    if (k <= j) {
+                        const float dq = (ud[k] - dot(U[k], a)) * Dinv[k];
+                        a += S[k] * dq;
+                        if (k == j) dqj = dq;
+                    }
+                }
+                lim_A[j] = dqj;
+            }
+        }
+    }
+
+    // ---------------- projected Gauss-Seidel ----------------
+    const int maxs = Grp<LANES>::warp_max(ncon);
+    SV v0pos = v0n;
+    float qdpos[NL];
+#pragma unroll
+    for (int j = 0; j < NL; j++) qdpos[j] = qdn[j];
+    const int nit = P.npos + P.nvel;
+    const float mu = 0.5f * (P.mu_ground + mu_shape);   // PhysX default combine mode: average
+
+    // apply the owner's root-level bias + joint terms to the whole articulation
+    auto spread = [&](SV Pb, const float* ud, int owner) {
+        SV Pw = (lane == owner) ? Pb : sv0();
+        if (LANES > 1) Pw = grp_bcast<LANES>(Pw, owner);
+        SV a = sv0();
+        if (!FIXED) {
+            a = -mul(inv, Pw);
+            v0n += a;
+        }
+#pragma unroll
+        for (int k = 0; k < NL; k++) {
+            if (k < len) {
+                const float udk = (lane == owner) ? ud[k] : 0.0f;
+                const float dq = (udk - dot(U[k], a)) * Dinv[k];
+                a += S[k] * dq;
+                qdn[k] += dq;
+            }
+        }
+    };
+
+    for (int it = 0; it < nit; it++) {
+        if (it == P.npos) {
+            v0pos = v0n;
+#pragma unroll
+            for (int j = 0; j < NL; j++) qdpos[j] = qdn[j];
+        }
+        const bool with_bias = it < P.npos;
+        for (int s = 0; s < maxs; s++) {
+            for (int owner = 0; owner < LANES; owner++) {
+                const bool mine = (lane == owner) && (s < ncon);
+                if (!Grp<LANES>::warp_any(mine)) continue;
+                SV Pb = sv0();
+                float ud[NL];
+#pragma unroll
+                for (int k = 0; k < NL; k++) ud[k] = 0.0f;
+                if (mine) {
+                    const V3 r = V3{sc.at(s, CF_RX), sc.at(s, CF_RY), sc.at(s, CF_RZ)};
+                    const V3 n = V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)};
+                    const V3 t1 = V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)};
+                    const V3 t2 = V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)};
+                    const int jc = (int)sc.at(s, CF_JC);
+                    SV lv = v0n;
+#pragma unroll
+                    for (int k = 0; k < NL; k++)
+                        if (k <= jc) lv += S[k] * qdn[k];
+                    const V3 pv = lv.v + cross(lv.w, r);
+                    float vn = dot(pv, n), vt1 = dot(pv, t1), vt2 = dot(pv, t2);
+                    float tgt = -sc.at(s, CF_GAP) / h;
+                    tgt = fminf(tgt, P.max_depen);
+                    if (!with_bias) tgt = fminf(tgt, 0.0f);
+                    const float l0 = sc.at(s, CF_LN), l1o = sc.at(s, CF_L1), l2o = sc.at(s, CF_L2);
+                    float ln = fmaxf(l0 - (vn - tgt) / sc.at(s, CF_ANN), 0.0f);
+                    const float dn = ln - l0;
+                    vt1 += sc.at(s, CF_ANT1) * dn;
+                    vt2 += sc.at(s, CF_ANT2) * dn;
+                    float l1 = l1o - vt1 / sc.at(s, CF_AT1T1);
+                    vt2 += sc.at(s, CF_AT1T2) * (l1 - l1o);
+                    float l2 = l2o - vt2 / sc.at(s, CF_AT2T2);
+                    const float lim_t = mu * ln, mag = sqrtf(l1 * l1 + l2 * l2);
+                    if (mag > lim_t) {
+                        const float scl = (mag > 0.0f) ? lim_t / mag : 0.0f;
+                        l1 *= scl; l2 *= scl;
+                    }
+                    sc.at(s, CF_LN) = ln; sc.at(s, CF_L1) = l1; sc.at(s, CF_L2) = l2;
+                    const V3 dir = n * dn + t1 * (l1 - l1o) + t2 * (l2 - l2o);
+                    Pb = push_up(jc, SV{cross(r, dir), dir}, -1, 0.0f, ud);
+                }
+                spread(Pb, ud, owner);
+            }
+        }
+        if (warp_lim) {
+            for (int owner = 0; owner < LANES; owner++) {
+#pragma unroll
+                for (int j = 0; j < NL; j++) {
+                    const bool mine = (lane == owner) && lim_on[j];
+                    if (!Grp<LANES>::warp_any(mine)) continue;
+                    SV Pb = sv0();
+                    float ud[NL];
+#pragma unroll
+                    for (int k = 0; k < NL; k++) ud[k] = 0.0f;
+                    if (mine) {
+                        const float vrel = lim_sign[j] * qdn[j];
+                        float tgt = -lim_gap[j] / h;
+                        if (!with_bias) tgt = fminf(tgt, 0.0f);
+                        const float ln = fmaxf(lim_lam[j] - (vrel - tgt) / lim_A[j], 0.0f);
+                        const float dl = ln - lim_lam[j];
+                        lim_lam[j] = ln;
+                        Pb = push_up(-2, sv0(), j, lim_sign[j] * dl, ud);
+                    }
+                    spread(Pb, ud, owner);
+                }
+            }
+        }
+    }
+    if (P.npos >= nit) {   // no velocity iterations: positions integrate with the final velocity
+        v0pos = v0n;
+#pragma unroll
+        for (int j = 0; j < NL; j++) qdpos[j] = qdn[j];
+    }
+
+    // ---------------- integrate ----------------
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        if (j < len) {
+            const DevDof& D = M->dof[d0 + j];
+            float qv = qdn[j], qp = qdpos[j];
+            if (D.vel_limit > 0.0f) {
+                qv = fminf(fmaxf(qv, -D.vel_limit), D.vel_limit);
+                qp = fminf(fmaxf(qp, -D.vel_limit), D.vel_limit);
+            }
+            st.q[j] += h * qp;
+            st.qd[j] = qv;
+            float f = 0.0f;
+            if (D.drive_mode == B2G_DOF_MODE_POS) f = D.kp * (st.tgt[j] - st.q[j]) - D.kd * qv;
+            else if (D.drive_mode == B2G_DOF_MODE_VEL) f = D.kd * (st.tgt[j] - qv);
+            else if (D.drive_mode == B2G_DOF_MODE_EFFORT) f = st.act[j];
+            if (D.effort > 0.0f) f = fminf(fmaxf(f, -D.effort), D.effort);
+            st.frc[j] = f;
+        }
+    }
+    if (!FIXED) {
+        st.rp += v0pos.v * h;
+        const V3 w = v0pos.w;
+        const float wn = sqrtf(dot(w, w)), ang = wn * h;
+        float dx = 0, dy = 0, dz = 0, dw = 1.0f;
+        if (ang > 1e-12f) {
+            float sh, ch;
+#if defined(B2G_HOST_EMU)
+            sh = sinf(0.5f * ang); ch = cosf(0.5f * ang);
+#else
+            sincosf(0.5f * ang, &sh, &ch);
+#endif
+            const float k = sh / wn;
+            dx = w.x * k; dy = w.y * k; dz = w.z * k; dw = ch;
+        }
+        const float x2 = st.qx, y2 = st.qy, z2 = st.qz, w2 = st.qw;
+        float nx = dw * x2 + dx * w2 + dy * z2 - dz * y2;
+        float ny = dw * y2 - dx * z2 + dy * w2 + dz * x2;
+        float nz = dw * z2 + dx * y2 - dy * x2 + dz * w2;
+        float nw = dw * w2 - dx * x2 - dy * y2 - dz * z2;
+        const float nn = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+        st.qx = nx * nn; st.qy = ny * nn; st.qz = nz * nn; st.qw = nw * nn;
+        st.rv = v0n.v;
+        st.rw = v0n.w;
+    }
+
+    // ---------------- net contact force per API body (last sub-step only) ----------------
+    if (last) {
+        const int nb3 = M->n_bodies * 3;
+        for (int i = lane; i < nb3; i += LANES) bf[i] = 0.0f;
+        Grp<LANES>::sync();
+        const float ih = 1.0f / h;
+        for (int owner = 0; owner < LANES; owner++) {
+            if (lane == owner) {
+                for (int s = 0; s < ncon; s++) {
+                    const float ln = sc.at(s, CF_LN) * ih, l1 = sc.at(s, CF_L1) * ih, l2 = sc.at(s, CF_L2) * ih;
+                    const int b = (int)sc.at(s, CF_BODY);
+                    bf[b * 3 + 0] += sc.at(s, CF_NX) * ln + sc.at(s, CF_T1X) * l1 + sc.at(s, CF_T2X) * l2;
+                    bf[b * 3 + 1] += sc.at(s, CF_NY) * ln + sc.at(s, CF_T1Y) * l1 + sc.at(s, CF_T2Y) * l2;
+                    bf[b * 3 + 2] += sc.at(s, CF_NZ) * ln + sc.at(s, CF_T1Z) * l1 + sc.at(s, CF_T2Z) * l2;
+                }
+            }
+            Grp<LANES>::sync();
+        }
+    }
+}
+
+}  // namespace b2g

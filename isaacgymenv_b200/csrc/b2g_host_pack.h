@@ -1,0 +1,101 @@
+// Host-side translation of the public PODs (include/b200gym.h) into the kernel-facing structures.
+#pragma once
+
+#include <math.h>
+#include <string.h>
+
+#include "b2g_dev.h"
+
+namespace b2g {
+
+inline void quat_to_rot9(const float* q, float* m) {
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - z * w); m[2] = 2 * (x * z + y * w);
+    m[3] = 2 * (x * y + z * w); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - x * w);
+    m[6] = 2 * (x * z - y * w); m[7] = 2 * (y * z + x * w); m[8] = 1 - 2 * (x * x + y * y);
+}
+
+// Returns 0 on success, <0 when the model violates an assumption of the kernels (message in *why).
+inline int pack_dev_model(const b2g_model& m, const b2g_dof_props& p, DevModel& d, const char** why) {
+    memset(&d, 0, sizeof(d));
+    *why = "";
+    if (m.n_dof < 0 || m.n_dof > B2G_MAX_DOF || m.n_bodies < 1 || m.n_bodies > B2G_MAX_BODIES || m.n_chains < 0 ||
+        m.n_chains > B2G_MAX_CHAINS || m.n_cpts < 0 || m.n_cpts > B2G_MAX_CPTS) {
+        *why = "model dimensions out of range";
+        return -1;
+    }
+    d.fixed_base = m.fixed_base; d.n_dof = m.n_dof; d.n_bodies = m.n_bodies; d.n_chains = m.n_chains;
+    int expect = 0;
+    for (int c = 0; c < m.n_chains; c++) {
+        if (m.chain_start[c] != expect || m.chain_len[c] < 1 || m.chain_len[c] > B2G_MAX_CHAIN_LEN) {
+            *why = "chains must be contiguous, non-empty and at most B2G_MAX_CHAIN_LEN long";
+            return -1;
+        }
+        d.chain_start[c] = m.chain_start[c]; d.chain_len[c] = m.chain_len[c];
+        expect += m.chain_len[c];
+    }
+    if (expect != m.n_dof) { *why = "chain lengths do not add up to n_dof"; return -1; }
+    d.root_mass = m.link_mass[0];
+    for (int i = 0; i < 3; i++) d.root_com[i] = m.link_com[0][i];
+    // public order xx,yy,zz,xy,xz,yz -> kernel order xx,xy,xz,yy,yz,zz
+    auto inertia6 = [](const float* s, float* o) { o[0] = s[0]; o[1] = s[3]; o[2] = s[4]; o[3] = s[1]; o[4] = s[5]; o[5] = s[2]; };
+    inertia6(m.link_inertia[0], d.root_inertia);
+    for (int k = 0; k < m.n_dof; k++) {
+        DevDof& D = d.dof[k];
+        for (int i = 0; i < 3; i++) { D.jpos[i] = m.joint_pos[k][i]; D.axis[i] = m.joint_axis[k][i]; D.com[i] = m.link_com[k + 1][i]; }
+        D.type = m.joint_type[k];
+        quat_to_rot9(m.joint_quat[k], D.jrot);
+        D.mass = m.link_mass[k + 1];
+        D.armature = m.armature[k];
+        inertia6(m.link_inertia[k + 1], D.inertia);
+        D.kp = p.stiffness[k]; D.kd = p.damping[k]; D.effort = p.effort[k]; D.vel_limit = p.velocity[k];
+        D.lower = p.lower[k]; D.upper = p.upper[k]; D.drive_mode = p.drive_mode[k];
+        D.cp_start = 0; D.cp_count = 0;
+    }
+    // contact candidates must be grouped: non-root candidates by link (any link order), then root candidates
+    // grouped by owner chain.  Ranges are derived here.
+    for (int c = 0; c < B2G_MAX_CHAINS; c++) { d.root_cp_start[c] = 0; d.root_cp_count[c] = 0; }
+    for (int i = 0; i < m.n_cpts; i++) {
+        for (int a = 0; a < 3; a++) d.cp[i][a] = m.cp_pos[i][a];
+        d.cp[i][3] = m.cp_radius[i];
+        d.cp_body[i] = m.cp_body[i];
+        const int l = m.cp_link[i];
+        if (l < 0 || l > m.n_dof || m.cp_body[i] < 0 || m.cp_body[i] >= m.n_bodies) { *why = "contact candidate refers to a bad link/body"; return -1; }
+        if (l > 0) {
+            DevDof& D = d.dof[l - 1];
+            if (D.cp_count == 0) D.cp_start = i;
+            else if (D.cp_start + D.cp_count != i) { *why = "contact candidates of a link must be contiguous"; return -1; }
+            D.cp_count++;
+        } else {
+            const int c = m.cp_chain[i];
+            if (c < 0 || c >= (m.n_chains > 0 ? m.n_chains : 1)) { *why = "root contact candidate has a bad owner chain"; return -1; }
+            if (d.root_cp_count[c] == 0) d.root_cp_start[c] = i;
+            else if (d.root_cp_start[c] + d.root_cp_count[c] != i) { *why = "root contact candidates of a chain must be contiguous"; return -1; }
+            d.root_cp_count[c]++;
+        }
+    }
+    for (int b = 0; b < m.n_bodies; b++) {
+        d.body_link[b] = m.body_link[b];
+        for (int a = 0; a < 3; a++) d.body_pos[b][a] = m.body_pos[b][a];
+        for (int a = 0; a < 4; a++) d.body_quat[b][a] = m.body_quat[b][a];
+    }
+    return 0;
+}
+
+inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, const int16_t* hf_dev, DevParams& d) {
+    memset(&d, 0, sizeof(d));
+    const int sub = s.substeps > 0 ? s.substeps : 1;
+    d.h = s.dt / (float)sub;
+    d.substeps = sub;
+    for (int i = 0; i < 3; i++) d.g[i] = s.gravity[i];
+    d.npos = s.num_position_iterations; d.nvel = s.num_velocity_iterations;
+    d.contact_offset = s.contact_offset; d.max_depen = s.max_depenetration_velocity;
+    d.mu_ground = (hf && hf_dev) ? hf->friction : s.plane_dynamic_friction;
+    d.has_ground = s.has_ground;
+    if (hf && hf_dev) {
+        d.hf = hf_dev; d.hf_rows = hf->rows; d.hf_cols = hf->cols; d.hf_hs = hf->horizontal_scale; d.hf_vs = hf->vertical_scale;
+        d.hf_ox = hf->origin_x; d.hf_oy = hf->origin_y;
+    }
+}
+
+}  // namespace b2g

@@ -1,0 +1,351 @@
+// Per-thread bodies of the kernels (one thread = one lane = one chain of one environment).
+// Kept in a header so the very same code is compiled into the CUDA kernels (b200gym.cu) and into the
+// host lane emulator used by the CPU tests (tests/emu/emu.cpp, B2G_HOST_EMU).
+#pragma once
+
+#include "b2g_dynamics.cuh"
+
+namespace b2g {
+
+struct SimArgs {
+    const DevModel* M;
+    DevParams P;
+    int n_envs;
+    float* root;             // (N,13)
+    float* dof;              // (N,nd,2)
+    const float* target;     // (N,nd)
+    const float* actuation;  // (N,nd)
+    float* dof_force;        // (N,nd)
+    float* contact;          // (N,nb,3)
+    const float* friction;   // (N) per-env shape friction
+};
+
+struct TaskArgs {
+    b2g_anymal_cfg cfg;
+    const float* actions_in;   // (N,na)
+    float* obs;                // (N,12+3*nd)
+    float* obs_clamped;
+    float* rew;                // (N)
+    long long* reset;          // (N) int64
+    long long* progress;       // (N)
+    long long* timeout;        // (N)
+    float* commands;           // (N,3)
+    float* actions;            // (N,na)
+    int* reset_count;          // (N)
+    const float* rand_override; // (N, 2*nd+3) or null
+    int post_only;              // 1: skip the physics, run post_physics_step on the tensors as they are (parity tests)
+};
+
+template <int NL>
+B2G_HD B2G_INL void load_state(const SimArgs& A, int env, int len, int d0, LaneState<NL>& st) {
+    const float* r = A.root + (size_t)env * 13;
+    st.rp = V3{r[0], r[1], r[2]};
+    st.qx = r[3]; st.qy = r[4]; st.qz = r[5]; st.qw = r[6];
+    st.rv = V3{r[7], r[8], r[9]};
+    st.rw = V3{r[10], r[11], r[12]};
+    const int nd = A.M->n_dof;
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        st.q[j] = 0; st.qd[j] = 0; st.tgt[j] = 0; st.act[j] = 0; st.frc[j] = 0;
+        if (j < len) {
+            const size_t k = (size_t)env * nd + d0 + j;
+            st.q[j] = A.dof[2 * k];
+            st.qd[j] = A.dof[2 * k + 1];
+        }
+    }
+}
+
+template <int NL>
+B2G_HD B2G_INL void store_state(const SimArgs& A, int env, int lane, int len, int d0, const LaneState<NL>& st, bool fixed) {
+    const int nd = A.M->n_dof;
+    if (lane == 0 && !fixed) {
+        float* r = A.root + (size_t)env * 13;
+        r[0] = st.rp.x; r[1] = st.rp.y; r[2] = st.rp.z;
+        r[3] = st.qx; r[4] = st.qy; r[5] = st.qz; r[6] = st.qw;
+        r[7] = st.rv.x; r[8] = st.rv.y; r[9] = st.rv.z;
+        r[10] = st.rw.x; r[11] = st.rw.y; r[12] = st.rw.z;
+    }
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        if (j < len) {
+            const size_t k = (size_t)env * nd + d0 + j;
+            A.dof[2 * k] = st.q[j];
+            A.dof[2 * k + 1] = st.qd[j];
+            A.dof_force[k] = st.frc[j];
+        }
+    }
+}
+
+// gym.simulate: `substeps` sub-steps for one lane.
+template <int LANES, int NL, bool FIXED, bool HF>
+B2G_HD B2G_INL void simulate_thread(const SimArgs& A, int env, int lane, bool valid, ScratchStrided sc, float* bf) {
+    const DevModel* M = A.M;
+    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
+    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    LaneState<NL> st;
+    load_state<NL>(A, env, len, d0, st);
+    const int nd = M->n_dof;
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        if (j < len) {
+            const size_t k = (size_t)env * nd + d0 + j;
+            st.tgt[j] = A.target[k];
+            st.act[j] = A.actuation[k];
+        }
+    }
+    const float mu_shape = A.friction ? A.friction[env] : 1.0f;
+    for (int s = 0; s < A.P.substeps; s++)
+        substep<LANES, NL, FIXED, HF>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
+    if (valid) {
+        store_state<NL>(A, env, lane, len, d0, st, FIXED);
+        const int nb3 = M->n_bodies * 3;
+        for (int i = lane; i < nb3; i += LANES) A.contact[(size_t)env * nb3 + i] = bf[i];
+    }
+}
+
+// Philox4x32-10 (Salmon et al., SC'11); checked against the Random123 known-answer vectors in the tests.
+B2G_HD B2G_INL void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = (unsigned long long)c0 * 0xD2511F53ull;
+        const unsigned long long p1 = (unsigned long long)c2 * 0xCD9E8D57ull;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0;
+        const unsigned n1 = (unsigned)p1;
+        const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+        const unsigned n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// i-th uniform in [0,1) of env `env` at its `rc`-th reset
+B2G_HD B2G_INL float reset_uniform(const TaskArgs& T, int env, int rc, int i, int n_draws) {
+    if (T.rand_override) return T.rand_override[(size_t)env * n_draws + i];
+    unsigned o[4];
+    philox4x32((unsigned)env, (unsigned)rc, (unsigned)(i >> 2), 0u, (unsigned)(T.cfg.seed & 0xffffffffull), (unsigned)(T.cfg.seed >> 32), o);
+    return (float)(o[i & 3] >> 8) * (1.0f / 16777216.0f);
+}
+
+// utils/torch_jit_utils.py:93-103 (same arithmetic form as the reference)
+B2G_HD B2G_INL V3 quat_rotate_inverse(float qx, float qy, float qz, float qw, V3 v) {
+    const V3 qv = V3{qx, qy, qz};
+    const V3 a = v * (2.0f * qw * qw - 1.0f);
+    const V3 b = cross(qv, v) * qw * 2.0f;
+    const V3 c = qv * dot(qv, v) * 2.0f;
+    return a - b + c;
+}
+// utils/torch_jit_utils.py:80-90
+B2G_HD B2G_INL V3 quat_rotate(float qx, float qy, float qz, float qw, V3 v) {
+    const V3 qv = V3{qx, qy, qz};
+    const V3 a = v * (2.0f * qw * qw - 1.0f);
+    const V3 b = cross(qv, v) * qw * 2.0f;
+    const V3 c = qv * dot(qv, v) * 2.0f;
+    return a + b + c;
+}
+
+// reset_idx of the flat task for one lane (tasks/anymal.py:278-304): state <- init root, dof draws, commands
+template <int NL>
+B2G_HD B2G_INL void anymal_reset_lane(const TaskArgs& T, int env, int lane, int len, int d0, int nd, int rc, LaneState<NL>& st, float* cmd) {
+    const int n_draws = 2 * nd + 3;
+    const float* ir = T.cfg.init_root;
+    st.rp = V3{ir[0], ir[1], ir[2]};
+    st.qx = ir[3]; st.qy = ir[4]; st.qz = ir[5]; st.qw = ir[6];
+    st.rv = V3{ir[7], ir[8], ir[9]};
+    st.rw = V3{ir[10], ir[11], ir[12]};
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        if (j < len) {
+            const int d = d0 + j;
+            const float up = reset_uniform(T, env, rc, d, n_draws), uv = reset_uniform(T, env, rc, nd + d, n_draws);
+            st.q[j] = T.cfg.default_dof_pos[d] * ((1.5f - 0.5f) * up + 0.5f);
+            st.qd[j] = (0.1f - (-0.1f)) * uv + (-0.1f);
+        }
+    }
+    cmd[0] = (T.cfg.cmd_x[1] - T.cfg.cmd_x[0]) * reset_uniform(T, env, rc, 2 * nd + 0, n_draws) + T.cfg.cmd_x[0];
+    cmd[1] = (T.cfg.cmd_y[1] - T.cfg.cmd_y[0]) * reset_uniform(T, env, rc, 2 * nd + 1, n_draws) + T.cfg.cmd_y[0];
+    cmd[2] = (T.cfg.cmd_yaw[1] - T.cfg.cmd_yaw[0]) * reset_uniform(T, env, rc, 2 * nd + 2, n_draws) + T.cfg.cmd_yaw[0];
+}
+
+// The reset_idx(all) the task constructor performs (tasks/anymal.py:146).
+template <int LANES, int NL>
+B2G_HD B2G_INL void anymal_reset_all_thread(const SimArgs& A, const TaskArgs& T, int env, int lane, bool valid) {
+    const DevModel* M = A.M;
+    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
+    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    LaneState<NL> st;
+    load_state<NL>(A, env, len, d0, st);
+    float cmd[3];
+    const int rc = T.reset_count[env];
+    anymal_reset_lane<NL>(T, env, lane, len, d0, M->n_dof, rc, st, cmd);
+    Grp<LANES>::sync();
+    if (valid) {
+        store_state<NL>(A, env, lane, len, d0, st, false);
+        if (lane == 0) {
+            T.commands[(size_t)env * 3 + 0] = cmd[0]; T.commands[(size_t)env * 3 + 1] = cmd[1]; T.commands[(size_t)env * 3 + 2] = cmd[2];
+            T.progress[env] = 0;
+            T.reset[env] = 1;
+            T.reset_count[env] = rc + 1;
+        }
+    }
+}
+
+// VecTask.step for the flat Anymal / Hound task, fused:
+//   clamp actions, position targets   (vec_task.py:374, tasks/anymal.py:226-229)
+//   gym.simulate                       (vec_task.py:379-382)
+//   post_physics_step                  (tasks/anymal.py:231-239: progress, reset_idx, observations, reward)
+//   timeout_buf, clamp obs             (vec_task.py:394,402)
+template <int LANES, int NL, bool HF>
+B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int env, int lane, bool valid, ScratchStrided sc, float* bf) {
+    const DevModel* M = A.M;
+    const int nd = M->n_dof;
+    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
+    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    const b2g_anymal_cfg& C = T.cfg;
+    LaneState<NL> st;
+    load_state<NL>(A, env, len, d0, st);
+    float act[NL];
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        act[j] = 0.0f;
+        if (j < len) {
+            const int d = d0 + j;
+            float a = T.actions_in[(size_t)env * nd + d];
+            a = fminf(fmaxf(a, -C.clip_actions), C.clip_actions);
+            act[j] = a;
+            st.tgt[j] = C.action_scale * a + C.default_dof_pos[d];
+        }
+    }
+    if (!T.post_only) {
+        const float mu_shape = A.friction ? A.friction[env] : 1.0f;
+        for (int s = 0; s < A.P.substeps; s++)
+            substep<LANES, NL, false, HF>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
+    } else {
+        // torques and contact forces come from the sim tensors instead of a physics step
+#pragma unroll
+        for (int j = 0; j < NL; j++)
+            if (j < len) st.frc[j] = A.dof_force[(size_t)env * nd + d0 + j];
+        const int nb3p = M->n_bodies * 3;
+        for (int i = lane; i < nb3p; i += LANES) bf[i] = A.contact[(size_t)env * nb3p + i];
+        Grp<LANES>::sync();
+    }
+
+    // ---- post_physics_step ----
+    long long progress = T.progress[env] + 1;
+    float cmd[3] = {T.commands[(size_t)env * 3], T.commands[(size_t)env * 3 + 1], T.commands[(size_t)env * 3 + 2]};
+    const bool do_reset = T.reset[env] != 0;
+    int rc = 0;
+    if (do_reset) {
+        rc = T.reset_count[env];
+        anymal_reset_lane<NL>(T, env, lane, len, d0, nd, rc, st, cmd);
+        progress = 0;
+    }
+    // observations (tasks/anymal.py:354-386)
+    const V3 lin = quat_rotate_inverse(st.qx, st.qy, st.qz, st.qw, st.rv);
+    const V3 ang = quat_rotate_inverse(st.qx, st.qy, st.qz, st.qw, st.rw);
+    const V3 pg = quat_rotate(st.qx, st.qy, st.qz, st.qw, V3{0.0f, 0.0f, -1.0f});
+    // reward (tasks/anymal.py:311-351)
+    float tq2 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NL; j++)
+        if (j < len) tq2 += st.frc[j] * st.frc[j];
+    tq2 = Grp<LANES>::sum(tq2);
+    const float ex = cmd[0] - lin.x, ey = cmd[1] - lin.y, ez = cmd[2] - ang.z;
+    const float lin_err = ex * ex + ey * ey, ang_err = ez * ez;
+    float rew = expf(-lin_err / 0.25f) * C.rew_lin_vel_xy + expf(-ang_err / 0.25f) * C.rew_ang_vel_z + tq2 * C.rew_torque;
+    rew = fmaxf(rew, 0.0f);
+    // termination: base or knee contact force above 1 N, or time-out
+    bool term = false;
+    {
+        const float* f = bf + C.base_body * 3;
+        term = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
+        for (int k = 0; k < C.n_knee; k++) {
+            const float* g = bf + C.knee_bodies[k] * 3;
+            term = term || (sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) > 1.0f);
+        }
+    }
+    const bool time_out = progress >= C.max_episode_length - 1;
+    const bool reset = term || time_out;
+    if (valid) {
+        store_state<NL>(A, env, lane, len, d0, st, false);
+        const int nb3 = M->n_bodies * 3;
+        for (int i = lane; i < nb3; i += LANES) A.contact[(size_t)env * nb3 + i] = bf[i];
+        const int no = 12 + 3 * nd;
+        float* o = T.obs + (size_t)env * no;
+        float* oc = T.obs_clamped + (size_t)env * no;
+        const float clip = C.clip_obs;
+#define B2G_PUT(idx, val) { const float vv = (val); o[idx] = vv; oc[idx] = fminf(fmaxf(vv, -clip), clip); }
+        if (lane == 0) {
+            B2G_PUT(0, lin.x * C.lin_vel_scale) B2G_PUT(1, lin.y * C.lin_vel_scale) B2G_PUT(2, lin.z * C.lin_vel_scale)
+            B2G_PUT(3, ang.x * C.ang_vel_scale) B2G_PUT(4, ang.y * C.ang_vel_scale) B2G_PUT(5, ang.z * C.ang_vel_scale)
+            B2G_PUT(6, pg.x) B2G_PUT(7, pg.y) B2G_PUT(8, pg.z)
+            B2G_PUT(9, cmd[0] * C.lin_vel_scale) B2G_PUT(10, cmd[1] * C.lin_vel_scale) B2G_PUT(11, cmd[2] * C.ang_vel_scale)
+            T.rew[env] = rew;
+            T.reset[env] = reset ? 1 : 0;
+            T.progress[env] = progress;
+            T.timeout[env] = (time_out && reset) ? 1 : 0;
+            T.commands[(size_t)env * 3 + 0] = cmd[0]; T.commands[(size_t)env * 3 + 1] = cmd[1]; T.commands[(size_t)env * 3 + 2] = cmd[2];
+            if (do_reset) T.reset_count[env] = rc + 1;
+        }
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            if (j < len) {
+                const int d = d0 + j;
+                B2G_PUT(12 + d, (st.q[j] - C.default_dof_pos[d]) * C.dof_pos_scale)
+                B2G_PUT(12 + nd + d, st.qd[j] * C.dof_vel_scale)
+                B2G_PUT(12 + 2 * nd + d, act[j])
+                T.actions[(size_t)env * nd + d] = act[j];
+            }
+        }
+#undef B2G_PUT
+    }
+}
+
+// refresh_rigid_body_state_tensor: world pose + velocity of every API body (N,nb,13). One thread per env.
+B2G_HD B2G_INL void body_state_env(const DevModel* M, const float* root, const float* dof, float* out) {
+    const int nd = M->n_dof;
+    M3 Rl[B2G_MAX_LINKS];
+    V3 pl[B2G_MAX_LINKS];
+    SV vl[B2G_MAX_LINKS];
+    Rl[0] = quat_to_m3(root[3], root[4], root[5], root[6]);
+    pl[0] = V3{0, 0, 0};
+    vl[0] = M->fixed_base ? sv0() : SV{V3{root[10], root[11], root[12]}, V3{root[7], root[8], root[9]}};
+    for (int c = 0; c < M->n_chains; c++) {
+        for (int j = 0; j < M->chain_len[c]; j++) {
+            const int d = M->chain_start[c] + j, l = d + 1, p = (j == 0) ? 0 : l - 1;
+            const DevDof& D = M->dof[d];
+            M3 jr;
+            for (int k = 0; k < 9; k++) jr.m[k] = D.jrot[k];
+            const V3 ax = V3{D.axis[0], D.axis[1], D.axis[2]};
+            const M3 RJ = mul(Rl[p], jr);
+            const V3 pj = pl[p] + mul(Rl[p], V3{D.jpos[0], D.jpos[1], D.jpos[2]});
+            const V3 axw = mul(RJ, ax);
+            SV S;
+            if (D.type == B2G_JOINT_REVOLUTE) { Rl[l] = mul(RJ, axis_angle_m3(ax, dof[2 * d])); pl[l] = pj; S = SV{axw, cross(pj, axw)}; }
+            else { Rl[l] = RJ; pl[l] = pj + axw * dof[2 * d]; S = SV{V3{0, 0, 0}, axw}; }
+            vl[l] = vl[p] + S * dof[2 * d + 1];
+        }
+    }
+    (void)nd;
+    for (int b = 0; b < M->n_bodies; b++) {
+        const int l = M->body_link[b];
+        const V3 off = mul(Rl[l], V3{M->body_pos[b][0], M->body_pos[b][1], M->body_pos[b][2]});
+        const V3 p = pl[l] + off;
+        const M3 R = mul(Rl[l], quat_to_m3(M->body_quat[b][0], M->body_quat[b][1], M->body_quat[b][2], M->body_quat[b][3]));
+        // rotation matrix -> quaternion (xyzw)
+        float qx, qy, qz, qw;
+        const float tr = R.m[0] + R.m[4] + R.m[8];
+        if (tr > 0.0f) { float s = sqrtf(tr + 1.0f) * 2.0f; qw = 0.25f * s; qx = (R.m[7] - R.m[5]) / s; qy = (R.m[2] - R.m[6]) / s; qz = (R.m[3] - R.m[1]) / s; }
+        else if (R.m[0] > R.m[4] && R.m[0] > R.m[8]) { float s = sqrtf(1.0f + R.m[0] - R.m[4] - R.m[8]) * 2.0f; qw = (R.m[7] - R.m[5]) / s; qx = 0.25f * s; qy = (R.m[1] + R.m[3]) / s; qz = (R.m[2] + R.m[6]) / s; }
+        else if (R.m[4] > R.m[8]) { float s = sqrtf(1.0f + R.m[4] - R.m[0] - R.m[8]) * 2.0f; qw = (R.m[2] - R.m[6]) / s; qx = (R.m[1] + R.m[3]) / s; qy = 0.25f * s; qz = (R.m[5] + R.m[7]) / s; }
+        else { float s = sqrtf(1.0f + R.m[8] - R.m[0] - R.m[4]) * 2.0f; qw = (R.m[3] - R.m[1]) / s; qx = (R.m[2] + R.m[6]) / s; qy = (R.m[5] + R.m[7]) / s; qz = 0.25f * s; }
+        const V3 v = vl[l].v + cross(vl[l].w, p);   // velocity of the body-frame origin
+        float* o = out + (size_t)b * 13;
+        o[0] = root[0] + p.x; o[1] = root[1] + p.y; o[2] = root[2] + p.z;
+        o[3] = qx; o[4] = qy; o[5] = qz; o[6] = qw;
+        o[7] = v.x; o[8] = v.y; o[9] = v.z;
+        o[10] = vl[l].w.x; o[11] = vl[l].w.y; o[12] = vl[l].w.z;
+    }
+}
+
+}  // namespace b2g

@@ -1,0 +1,205 @@
+"""Two ways to run the kernel code under test with numpy in / numpy out:
+
+* ``CudaBackend``: the product -- ``libb200gym.so`` through its C ABI on ``cuda:0`` (``-m gpu`` tests);
+* ``EmuBackend``: the same per-thread kernel bodies compiled for the host by ``tests/emu`` (CPU tests).
+
+Both expose the same small interface so one test body checks both against the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from isaacgymenv_b200 import _abi
+
+TASK_KEYS = ("obs", "obs_clamped", "rew", "reset", "progress", "timeout", "commands", "actions")
+
+
+class EmuBackend:
+    name = "emu"
+
+    def __init__(self, art, params, props, n):
+        from tests.emu import emu
+
+        self.emu = emu
+        self.art, self.params, self.props, self.n = art, params, props, n
+        self.model = _abi.pack_model(art)
+        nd, nb = art.num_dofs, art.num_bodies
+        self.root = np.zeros((n, 13), np.float32)
+        self.root[:, 6] = 1
+        self.dof = np.zeros((n, nd, 2), np.float32)
+        self.dof_force = np.zeros((n, nd), np.float32)
+        self.contact = np.zeros((n, nb, 3), np.float32)
+        self.task = None
+
+    def set_state(self, root, dof):
+        self.root[:] = root
+        self.dof[:] = dof
+
+    def get_state(self):
+        return self.root.copy(), self.dof.copy()
+
+    def simulate(self, target, actuation):
+        f, c = self.emu.simulate(self.model, self.params, self.props, self.root, self.dof, target, actuation)
+        self.dof_force[:], self.contact[:] = f, c
+        return f, c
+
+    def forward_dynamics(self, tau):
+        return self.emu.forward_dynamics(self.model, self.params, self.props, self.root.copy(), self.dof.copy(), tau)
+
+    # ---- fused flat task ----
+    def anymal_create(self, cfg):
+        n, nd = self.n, self.art.num_dofs
+        no = 12 + 3 * nd
+        self.cfg = cfg
+        self.task = dict(obs=np.zeros((n, no), np.float32), obs_clamped=np.zeros((n, no), np.float32), rew=np.zeros(n, np.float32),
+                         reset=np.ones(n, np.int64), progress=np.zeros(n, np.int64), timeout=np.zeros(n, np.int64),
+                         commands=np.zeros((n, 3), np.float32), actions=np.zeros((n, nd), np.float32), reset_count=np.zeros(n, np.int32))
+
+    def _bufs(self):
+        b = dict(self.task)
+        b.update(root=self.root, dof=self.dof, dof_force=self.dof_force, contact=self.contact)
+        return b
+
+    def anymal_reset_all(self, draws=None):
+        self.emu.anymal(self.model, self.params, self.props, self.cfg, 0, self._bufs(), None, draws)
+
+    def anymal_step(self, actions, draws=None):
+        self.emu.anymal(self.model, self.params, self.props, self.cfg, 1, self._bufs(), actions, draws)
+
+    def anymal_post_only(self, actions, draws=None):
+        self.emu.anymal(self.model, self.params, self.props, self.cfg, 2, self._bufs(), actions, draws)
+
+    def get_task(self):
+        out = {k: self.task[k].copy() for k in TASK_KEYS}
+        out["dof_force"], out["contact"] = self.dof_force.copy(), self.contact.copy()
+        return out
+
+    def set_task(self, **kw):
+        for k, v in kw.items():
+            if k == "dof_force":
+                self.dof_force[:] = v
+            elif k == "contact":
+                self.contact[:] = v
+            else:
+                self.task[k][:] = v
+
+    def close(self):
+        pass
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, art, params, props, n):
+        import torch
+
+        from isaacgymenv_b200 import _lib
+
+        self.torch, self._lib = torch, _lib
+        self.lib = _lib.load()
+        self.art, self.n = art, n
+        self.model = _abi.pack_model(art)
+        self.sim = C.c_void_p()
+        p = _abi.SimParams.from_buffer_copy(params)
+        ground = (p.has_ground, p.plane_static_friction, p.plane_dynamic_friction, p.plane_restitution)
+        _lib.check(self.lib.b2g_sim_create(0, C.byref(p), C.byref(self.sim)), "create")
+        if ground[0]:
+            _lib.check(self.lib.b2g_sim_add_ground(self.sim, ground[1], ground[2], ground[3]))
+        pose = (C.c_float * 7)(0, 0, 0, 0, 0, 0, 1)
+        _lib.check(self.lib.b2g_sim_add_articulation(self.sim, C.byref(self.model), C.byref(props), n, pose, 1.0, 1), "add")
+        _lib.check(self.lib.b2g_sim_prepare(self.sim), "prepare")
+        self.t = {k: self._tensor(k) for k in (_abi.T_ROOT_STATE, _abi.T_DOF_STATE, _abi.T_NET_CONTACT, _abi.T_DOF_FORCE,
+                                                _abi.T_DOF_TARGET, _abi.T_DOF_ACTUATION)}
+        self.task = None
+        self.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _tensor(self, kind, task=False):
+        d = _abi.TensorDesc()
+        fn = self.lib.b2g_task_tensor if task else self.lib.b2g_sim_tensor
+        self._lib.check(fn(self.sim, kind, C.byref(d)), "tensor")
+        return self._lib.desc_to_torch(d)
+
+    def _put(self, t, a):
+        t.copy_(self.torch.from_numpy(np.ascontiguousarray(a)).to(t.device).reshape(t.shape))
+
+    def set_state(self, root, dof):
+        self._put(self.t[_abi.T_ROOT_STATE], np.asarray(root, np.float32))
+        self._put(self.t[_abi.T_DOF_STATE], np.asarray(dof, np.float32))
+
+    def get_state(self):
+        nd = self.art.num_dofs
+        return self.t[_abi.T_ROOT_STATE].cpu().numpy().copy(), self.t[_abi.T_DOF_STATE].cpu().numpy().reshape(self.n, nd, 2).copy()
+
+    def simulate(self, target, actuation):
+        self._put(self.t[_abi.T_DOF_TARGET], np.asarray(target, np.float32))
+        self._put(self.t[_abi.T_DOF_ACTUATION], np.asarray(actuation, np.float32))
+        self._lib.check(self.lib.b2g_sim_simulate(self.sim, self.stream), "simulate")
+        self.torch.cuda.synchronize()
+        nd, nb = self.art.num_dofs, self.art.num_bodies
+        return (self.t[_abi.T_DOF_FORCE].cpu().numpy().reshape(self.n, nd).copy(),
+                self.t[_abi.T_NET_CONTACT].cpu().numpy().reshape(self.n, nb, 3).copy())
+
+    def forward_dynamics(self, tau):
+        torch = self.torch
+        self._put(self.t[_abi.T_DOF_ACTUATION], np.asarray(tau, np.float32))
+        qdd = torch.zeros(self.n, self.art.num_dofs, device="cuda:0")
+        a0 = torch.zeros(self.n, 6, device="cuda:0")
+        self._lib.check(self.lib.b2g_sim_forward_dynamics(self.sim, C.c_void_p(qdd.data_ptr()), C.c_void_p(a0.data_ptr()), self.stream), "fd")
+        torch.cuda.synchronize()
+        return qdd.cpu().numpy(), a0.cpu().numpy()
+
+    def anymal_create(self, cfg):
+        self._lib.check(self.lib.b2g_task_anymal_create(self.sim, C.byref(cfg)), "task create")
+        kinds = dict(obs=_abi.TT_OBS, obs_clamped=_abi.TT_OBS_CLAMPED, rew=_abi.TT_REW, reset=_abi.TT_RESET, progress=_abi.TT_PROGRESS,
+                     timeout=_abi.TT_TIMEOUT, commands=_abi.TT_COMMANDS, actions=_abi.TT_ACTIONS, rand=_abi.TT_RAND_OVERRIDE)
+        self.task = {k: self._tensor(v, task=True) for k, v in kinds.items()}
+
+    def _draws(self, draws):
+        if draws is None:
+            self._lib.check(self.lib.b2g_task_set_rand_override(self.sim, 0))
+        else:
+            self._put(self.task["rand"], np.asarray(draws, np.float32))
+            self._lib.check(self.lib.b2g_task_set_rand_override(self.sim, 1))
+
+    def anymal_reset_all(self, draws=None):
+        self._draws(draws)
+        self._lib.check(self.lib.b2g_task_anymal_reset_all(self.sim, self.stream), "reset_all")
+        self.torch.cuda.synchronize()
+
+    def _actions(self, actions):
+        self._a = self.torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32)).to("cuda:0")
+        return C.c_void_p(self._a.data_ptr())
+
+    def anymal_step(self, actions, draws=None):
+        self._draws(draws)
+        self._lib.check(self.lib.b2g_task_anymal_step(self.sim, self._actions(actions), self.stream), "step")
+        self.torch.cuda.synchronize()
+
+    def anymal_post_only(self, actions, draws=None):
+        self._draws(draws)
+        self._lib.check(self.lib.b2g_task_anymal_post_only(self.sim, self._actions(actions), self.stream), "post_only")
+        self.torch.cuda.synchronize()
+
+    def get_task(self):
+        nd, nb = self.art.num_dofs, self.art.num_bodies
+        out = {k: self.task[k].cpu().numpy().copy() for k in TASK_KEYS}
+        out["dof_force"] = self.t[_abi.T_DOF_FORCE].cpu().numpy().reshape(self.n, nd).copy()
+        out["contact"] = self.t[_abi.T_NET_CONTACT].cpu().numpy().reshape(self.n, nb, 3).copy()
+        return out
+
+    def set_task(self, **kw):
+        for k, v in kw.items():
+            if k == "dof_force":
+                self._put(self.t[_abi.T_DOF_FORCE], np.asarray(v, np.float32))
+            elif k == "contact":
+                self._put(self.t[_abi.T_NET_CONTACT], np.asarray(v, np.float32))
+            else:
+                self._put(self.task[k], np.asarray(v, self.task[k].cpu().numpy().dtype))
+
+    def close(self):
+        if self.sim:
+            self.t, self.task = {}, None
+            self.lib.b2g_sim_destroy(self.sim)
+            self.sim = C.c_void_p()

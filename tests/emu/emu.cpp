@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE: host lane emulator.  Compiles the *same* per-thread kernel bodies as the CUDA
+// library (isaacgymenv_b200/csrc/b2g_threads.cuh) for the CPU, running the LANES cooperating lanes of an
+// environment as lock-stepped host threads.  It lets the CPU test-suite (-m "not gpu") exercise the
+// kernel logic against the oracle without a GPU.  It is NOT part of the product and is never loaded by
+// isaacgymenv_b200; the product has no CPU path.
+#define B2G_HOST_EMU 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+#include "b2g_host_pack.h"
+#include "b2g_threads.cuh"
+
+namespace b2g {
+thread_local EmuCtx emu_ctx;
+}
+using namespace b2g;
+
+namespace {
+
+struct Variant { int lanes, nl; bool fixed; };
+
+Variant pick(const b2g_model& m) {
+    int maxlen = 0;
+    for (int c = 0; c < m.n_chains; c++) maxlen = m.chain_len[c] > maxlen ? m.chain_len[c] : maxlen;
+    if (m.fixed_base && m.n_chains <= 1 && maxlen <= 2) return {1, 2, true};
+    if (!m.fixed_base && m.n_chains <= 4 && maxlen <= 3) return {4, 3, false};
+    return {8, 6, m.fixed_base != 0};
+}
+
+template <class F>
+void run_group(int lanes, F&& body) {
+    EmuGroup g;
+    g.lanes = lanes; g.count = 0; g.sense = 0;
+    std::vector<std::thread> th;
+    for (int l = 0; l < lanes; l++)
+        th.emplace_back([&, l]() {
+            emu_ctx.g = &g; emu_ctx.lane = l; emu_ctx.local_sense = 0;
+            body(l);
+        });
+    for (auto& t : th) t.join();
+}
+
+template <int LANES, int NL, bool FIXED, bool HF>
+void sim_env(const SimArgs& A, int env) {
+    std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
+    run_group(LANES, [&](int lane) {
+        ScratchStrided sc{scratch.data() + lane, LANES};
+        simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, true, sc, bf.data());
+    });
+}
+
+template <int LANES, int NL, bool FIXED>
+void probe_env(const SimArgs& A, int env, float* qdd, float* a0) {
+    std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
+    run_group(LANES, [&](int lane) {
+        const DevModel* M = A.M;
+        const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
+        const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+        LaneState<NL> st;
+        load_state<NL>(A, env, len, d0, st);
+        for (int j = 0; j < NL; j++) if (j < len) st.act[j] = A.actuation[(size_t)env * M->n_dof + d0 + j];
+        ScratchStrided sc{scratch.data() + lane, LANES};
+        substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, 1.0f, false, sc, bf.data());
+        for (int j = 0; j < NL; j++) if (j < len) qdd[(size_t)env * M->n_dof + d0 + j] = st.frc[j];
+        if (lane == 0) {
+            float* o = a0 + (size_t)env * 6;
+            o[0] = st.rw.x; o[1] = st.rw.y; o[2] = st.rw.z; o[3] = st.rv.x; o[4] = st.rv.y; o[5] = st.rv.z;
+        }
+    });
+}
+
+template <int LANES, int NL, bool HF>
+void anymal_env(const SimArgs& A, const TaskArgs& T, int env, int mode) {
+    std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
+    run_group(LANES, [&](int lane) {
+        ScratchStrided sc{scratch.data() + lane, LANES};
+        if (mode == 0) anymal_reset_all_thread<LANES, NL>(A, T, env, lane, true);
+        else anymal_step_thread<LANES, NL, HF>(A, T, env, lane, true, sc, bf.data());
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, const b2g_heightfield* hf,
+                 const int16_t* hfs, const float* friction, int n_envs, float* root, float* dof, const float* target,
+                 const float* actuation, float* dof_force, float* contact) {
+    DevModel* dm = new DevModel;
+    const char* why;
+    if (pack_dev_model(*m, *dp, *dm, &why) != 0) { delete dm; return -1; }
+    SimArgs A;
+    A.M = dm;
+    pack_dev_params(*sp, hf, hfs, A.P);
+    A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = target; A.actuation = actuation;
+    A.dof_force = dof_force; A.contact = contact; A.friction = friction;
+    const Variant v = pick(*m);
+    const bool HFm = hf && hfs;
+    for (int e = 0; e < n_envs; e++) {
+        if (v.lanes == 1) sim_env<1, 2, true, false>(A, e);
+        else if (v.lanes == 4) { if (HFm) sim_env<4, 3, false, true>(A, e); else sim_env<4, 3, false, false>(A, e); }
+        else if (v.fixed) sim_env<8, 6, true, false>(A, e);
+        else { if (HFm) sim_env<8, 6, false, true>(A, e); else sim_env<8, 6, false, false>(A, e); }
+    }
+    delete dm;
+    return 0;
+}
+
+int emu_forward_dynamics(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, int n_envs, float* root,
+                         float* dof, const float* tau, float* qdd, float* a0) {
+    DevModel* dm = new DevModel;
+    const char* why;
+    if (pack_dev_model(*m, *dp, *dm, &why) != 0) { delete dm; return -1; }
+    SimArgs A;
+    A.M = dm;
+    pack_dev_params(*sp, nullptr, nullptr, A.P);
+    A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = tau; A.actuation = tau; A.dof_force = nullptr; A.contact = nullptr; A.friction = nullptr;
+    const Variant v = pick(*m);
+    for (int e = 0; e < n_envs; e++) {
+        if (v.lanes == 1) probe_env<1, 2, true>(A, e, qdd, a0);
+        else if (v.lanes == 4) probe_env<4, 3, false>(A, e, qdd, a0);
+        else if (v.fixed) probe_env<8, 6, true>(A, e, qdd, a0);
+        else probe_env<8, 6, false>(A, e, qdd, a0);
+    }
+    delete dm;
+    return 0;
+}
+
+// mode 0: reset_all, mode 1: step, mode 2: post_physics_step only
+int emu_anymal(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, const b2g_anymal_cfg* cfg, int mode,
+               int n_envs, float* root, float* dof, float* dof_force, float* contact, const float* actions_in, float* obs,
+               float* obs_clamped, float* rew, long long* reset, long long* progress, long long* timeout, float* commands,
+               float* actions, int* reset_count, const float* rand_override) {
+    DevModel* dm = new DevModel;
+    const char* why;
+    if (pack_dev_model(*m, *dp, *dm, &why) != 0) { delete dm; return -1; }
+    SimArgs A;
+    A.M = dm;
+    pack_dev_params(*sp, nullptr, nullptr, A.P);
+    A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = dof_force;
+    A.contact = contact; A.friction = nullptr;
+    TaskArgs T;
+    T.cfg = *cfg; T.actions_in = actions_in; T.obs = obs; T.obs_clamped = obs_clamped; T.rew = rew; T.reset = reset;
+    T.progress = progress; T.timeout = timeout; T.commands = commands; T.actions = actions; T.reset_count = reset_count;
+    T.rand_override = rand_override;
+    T.post_only = (mode == 2);
+    const Variant v = pick(*m);
+    if (v.fixed) { delete dm; return -2; }
+    for (int e = 0; e < n_envs; e++) {
+        if (v.lanes == 4) anymal_env<4, 3, false>(A, T, e, mode);
+        else anymal_env<8, 6, false>(A, T, e, mode);
+    }
+    delete dm;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+"""TEST INFRASTRUCTURE: ctypes front-end of the host lane emulator (tests/emu/emu.cpp), which runs the
+CUDA kernels' per-thread code on the CPU so the kernel logic can be checked against the oracle
+without a GPU.  Never imported by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))
+_LIB = os.path.join(_HERE, "libb2g_emu.so")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, "emu.cpp")] + [os.path.join(_ROOT, "isaacgymenv_b200", "csrc", f) for f in
+            ("b2g_threads.cuh", "b2g_dynamics.cuh", "b2g_math.cuh", "b2g_dev.h", "b2g_host_pack.h")] + [os.path.join(_ROOT, "include", "b200gym.h")]
+    stale = not os.path.isfile(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + os.path.join(_ROOT, "include"),
+                               "-I" + os.path.join(_ROOT, "isaacgymenv_b200", "csrc"), "-x", "c++", os.path.join(_HERE, "emu.cpp"),
+                               "-o", _LIB, "-lpthread"])
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _p(a, ct=C.c_float):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+def simulate(model, params, props, root, dof, target, actuation, heightfield=None, hf_samples=None, friction=None):
+    n = root.shape[0]
+    assert root.dtype == np.float32 and dof.dtype == np.float32
+    dof_force = np.zeros((n, model.n_dof), dtype=np.float32)
+    contact = np.zeros((n, model.n_bodies, 3), dtype=np.float32)
+    hs = None if hf_samples is None else np.ascontiguousarray(hf_samples, dtype=np.int16)
+    fr = None if friction is None else np.ascontiguousarray(friction, dtype=np.float32)
+    rc = lib().emu_simulate(C.byref(model), C.byref(params), C.byref(props), C.byref(heightfield) if heightfield is not None else None,
+                            _p(hs, C.c_int16), _p(fr), C.c_int(n), _p(root), _p(dof),
+                            _p(np.ascontiguousarray(target, dtype=np.float32)), _p(np.ascontiguousarray(actuation, dtype=np.float32)),
+                            _p(dof_force), _p(contact))
+    assert rc == 0, rc
+    return dof_force, contact
+
+
+def forward_dynamics(model, params, props, root, dof, tau):
+    n = root.shape[0]
+    qdd = np.zeros((n, model.n_dof), dtype=np.float32)
+    a0 = np.zeros((n, 6), dtype=np.float32)
+    rc = lib().emu_forward_dynamics(C.byref(model), C.byref(params), C.byref(props), C.c_int(n), _p(root), _p(dof),
+                                    _p(np.ascontiguousarray(tau, dtype=np.float32)), _p(qdd), _p(a0))
+    assert rc == 0, rc
+    return qdd, a0
+
+
+def anymal(model, params, props, cfg, mode, bufs, actions=None, rand_override=None):
+    """mode 0 = reset_all, 1 = step.  bufs: dict of numpy arrays (root, dof, dof_force, contact, obs, obs_clamped,
+    rew, reset, progress, timeout, commands, actions, reset_count) updated in place."""
+    n = bufs["root"].shape[0]
+    ai = None if actions is None else np.ascontiguousarray(actions, dtype=np.float32)
+    ro = None if rand_override is None else np.ascontiguousarray(rand_override, dtype=np.float32)
+    rc = lib().emu_anymal(C.byref(model), C.byref(params), C.byref(props), C.byref(cfg), C.c_int(mode), C.c_int(n),
+                          _p(bufs["root"]), _p(bufs["dof"]), _p(bufs["dof_force"]), _p(bufs["contact"]), _p(ai), _p(bufs["obs"]),
+                          _p(bufs["obs_clamped"]), _p(bufs["rew"]), _p(bufs["reset"], C.c_longlong), _p(bufs["progress"], C.c_longlong),
+                          _p(bufs["timeout"], C.c_longlong), _p(bufs["commands"]), _p(bufs["actions"]), _p(bufs["reset_count"], C.c_int), _p(ro))
+    assert rc == 0, rc

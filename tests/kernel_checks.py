@@ -1,0 +1,310 @@
+"""Parity checks shared by the CPU (host lane emulator) and GPU (libb200gym.so through its C ABI) test
+modules.  Every check compares the kernel code against the oracle (oracle/) or the committed golden vectors
+(tests/golden/, outputs of the reference's own @torch.jit.script functions).
+
+Tolerances (north_star): reward/obs math 1e-5 relative on identical state tensors, integer/boolean masks
+bit-exact; contact-free joint accelerations 1e-3 relative; contact states within 1e-2 over a 10-step horizon.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from isaacgymenv_b200 import _abi
+from isaacgymenv_b200.model.store import COMPILED_DIR, load_articulation
+from oracle import dyn_oracle as O
+from oracle import task_math as tm
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+ANYMAL_DEFAULT = {"LF_HAA": .03, "LH_HAA": .03, "RF_HAA": -.03, "RH_HAA": -.03, "LF_HFE": .4, "LH_HFE": -.4, "RF_HFE": .4, "RH_HFE": -.4,
+                  "LF_KFE": -.8, "LH_KFE": .8, "RF_KFE": -.8, "RH_KFE": .8}
+HOUND_DEFAULT = {"roll": 0.0, "hip": 0.7854, "knee": -1.5708}
+
+
+def load_robot(name):
+    files = {"anymal": "urdf__anymal_c__urdf__anymal.c1k1f0.json", "anymal_minimal": "urdf__anymal_c__urdf__anymal_minimal.c1k1f0.json",
+             "hound": "urdf__Hound_new__Hound.c0k0f0.json", "useful_hound": "urdf__UsefulHound__urdf__Hound.c0k0f0.json",
+             "cartpole": "urdf__cartpole.c0k0f1.json"}
+    return load_articulation(os.path.join(COMPILED_DIR, files[name]))
+
+
+def default_pose(art):
+    if art.dof_names[0] in ANYMAL_DEFAULT:
+        return np.array([ANYMAL_DEFAULT[n] for n in art.dof_names])
+    out = []
+    for n in art.dof_names:
+        out.append(next((v for k, v in HOUND_DEFAULT.items() if k in n), 0.0))
+    return np.array(out)
+
+
+def flat_params(dt=0.02, substeps=2, npos=4, nvel=1, ground=True):
+    sp = _abi.SimParams(dt=dt, substeps=substeps, num_position_iterations=npos, num_velocity_iterations=nvel, contact_offset=0.02,
+                        rest_offset=0.0, bounce_threshold_velocity=0.2, max_depenetration_velocity=100.0, plane_static_friction=1.0,
+                        plane_dynamic_friction=1.0, plane_restitution=0.0, has_ground=1 if ground else 0)
+    sp.gravity[2] = -9.81
+    return sp
+
+
+def random_flying_state(art, n, rng, scale_qd=2.0):
+    nd = art.num_dofs
+    root = np.zeros((n, 13), np.float32)
+    root[:, 2] = 5.0
+    q = rng.normal(size=(n, 4))
+    root[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    root[:, 7:13] = rng.normal(size=(n, 6))
+    dof = np.zeros((n, nd, 2), np.float32)
+    dof[:, :, 0] = default_pose(art) + rng.uniform(-.3, .3, (n, nd))
+    dof[:, :, 1] = rng.normal(size=(n, nd)) * scale_qd
+    return root, dof
+
+
+def standing_state(art, n, rng, z0=0.55):
+    nd = art.num_dofs
+    root = np.zeros((n, 13), np.float32)
+    root[:, 2] = z0 + rng.uniform(0, .1, n)
+    root[:, 3:6] = rng.normal(size=(n, 3)) * 0.05
+    root[:, 6] = 1
+    root[:, 3:7] /= np.linalg.norm(root[:, 3:7], axis=1, keepdims=True)
+    dof = np.zeros((n, nd, 2), np.float32)
+    dof[:, :, 0] = default_pose(art) * rng.uniform(.5, 1.5, (n, nd))
+    dof[:, :, 1] = rng.uniform(-.1, .1, (n, nd))
+    return root, dof
+
+
+# ------------------------------------------------------------------------------------------------
+def check_forward_dynamics(make_backend, robot="anymal", n=16, seed=0):
+    """Contact-free joint and root accelerations vs the float64 oracle: <= 1e-3 relative (north_star)."""
+    art = load_robot(robot)
+    rng = np.random.default_rng(seed)
+    sp = flat_params(ground=False)
+    props = _abi.default_dof_props(art)
+    root, dof = random_flying_state(art, n, rng)
+    tau = (rng.normal(size=(n, art.num_dofs)) * 20).astype(np.float32)
+    be = make_backend(art, sp, props, n)
+    try:
+        be.set_state(root, dof)
+        qdd, a0 = be.forward_dynamics(tau)
+    finally:
+        be.close()
+    m = _abi.pack_model(art)
+    qo, ao = O.forward_dynamics(m, sp, root.astype(np.float64), dof.astype(np.float64), tau.astype(np.float64))
+    if art.fixed_base:
+        ao = np.zeros_like(ao)
+    err_q = np.abs(qdd - qo).max(axis=1) / np.abs(qo).max(axis=1)
+    assert err_q.max() < 1e-3, f"joint acceleration relative error {err_q.max():.2e}"
+    if not art.fixed_base:
+        err_a = np.abs(a0 - ao).max(axis=1) / np.abs(ao).max(axis=1)
+        assert err_a.max() < 1e-3, f"root acceleration relative error {err_a.max():.2e}"
+    return float(err_q.max())
+
+
+def check_simulate_horizon(make_backend, robot="anymal", n=16, steps=10, seed=1, drive="pos", tol=1e-2):
+    """gym.simulate with ground contact for `steps` steps vs the float64 oracle: states within 1e-2."""
+    art = load_robot(robot)
+    rng = np.random.default_rng(seed)
+    nd = art.num_dofs
+    if drive == "pos":
+        sp = flat_params()
+        props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 85.0, 2.0)
+    else:
+        sp = flat_params(dt=0.005, substeps=1)
+        props = _abi.default_dof_props(art, _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    z0 = 0.55 if "anymal" in robot else 0.5
+    root, dof = standing_state(art, n, rng, z0)
+    be = make_backend(art, sp, props, n)
+    m = _abi.pack_model(art)
+    r64, d64 = root.astype(np.float64), dof.astype(np.float64)
+    q0 = default_pose(art)
+    worst = 0.0
+    saw_contact = False
+    try:
+        be.set_state(root, dof)
+        for _ in range(steps):
+            if drive == "pos":
+                tgt = q0 + 0.5 * rng.uniform(-1, 1, (n, nd))
+                act = np.zeros((n, nd))
+            else:
+                rb, db = be.get_state()
+                tgt = np.zeros((n, nd))
+                act = np.clip(80.0 * (q0 + 0.5 * rng.uniform(-1, 1, (n, nd)) - db[:, :, 0]) - 2.0 * db[:, :, 1], -80, 80)
+            f, c = be.simulate(tgt, act)
+            f64, c64 = O.simulate(m, sp, props, r64, d64, tgt.astype(np.float64), act.astype(np.float64))
+            rb, db = be.get_state()
+            worst = max(worst, float(np.abs(rb - r64).max()), float(np.abs(db[:, :, 0] - d64[:, :, 0]).max()))
+            saw_contact = saw_contact or bool((np.abs(c64) > 1.0).any())
+            cn = np.abs(c - c64).max() / max(1.0, np.abs(c64).max())
+            assert cn < 5e-2, f"contact force relative deviation {cn:.2e}"
+            assert np.abs(db[:, :, 1] - d64[:, :, 1]).max() < 10 * tol * max(1.0, np.abs(d64[:, :, 1]).max())
+    finally:
+        be.close()
+    assert saw_contact, "test never reached ground contact"
+    assert worst < tol, f"state deviation {worst:.2e} over {steps} steps"
+    return worst
+
+
+# ------------------------------------------------------------------------------------------------
+def anymal_cfg(art, seed=42, robot="anymal"):
+    c = _abi.AnymalCfg()
+    c.lin_vel_scale, c.ang_vel_scale, c.dof_pos_scale, c.dof_vel_scale, c.action_scale = 2.0, 0.25, 1.0, 0.05, 0.5
+    c.rew_lin_vel_xy, c.rew_ang_vel_z, c.rew_torque = 1.0 * 0.02, 0.5 * 0.02, -0.000025 * 0.02
+    c.clip_obs, c.clip_actions = 5.0, 1.0
+    c.cmd_x[0], c.cmd_x[1], c.cmd_y[0], c.cmd_y[1], c.cmd_yaw[0], c.cmd_yaw[1] = -2, 2, -1, 1, -1, 1
+    for i, v in enumerate(default_pose(art)):
+        c.default_dof_pos[i] = v
+    for i, v in enumerate([0, 0, 0.62, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0]):
+        c.init_root[i] = v
+    key = "THIGH" if robot == "anymal" else "thigh"
+    knees = [i for i, n in enumerate(art.body_names) if key in n]
+    c.base_body, c.n_knee = 0, len(knees)
+    for i, k in enumerate(knees):
+        c.knee_bodies[i] = k
+    c.max_episode_length = 2500
+    c.seed = seed
+    return c
+
+
+def cfg_dict(c, nd):
+    return dict(default_dof_pos=np.array(list(c.default_dof_pos)[:nd], np.float32), init_root=np.array(list(c.init_root), np.float32),
+                cmd_x=list(c.cmd_x), cmd_y=list(c.cmd_y), cmd_yaw=list(c.cmd_yaw), lin_vel_scale=c.lin_vel_scale,
+                ang_vel_scale=c.ang_vel_scale, dof_pos_scale=c.dof_pos_scale, dof_vel_scale=c.dof_vel_scale,
+                rew_scales={"lin_vel_xy": c.rew_lin_vel_xy, "ang_vel_z": c.rew_ang_vel_z, "torque": c.rew_torque},
+                knee_bodies=np.array(list(c.knee_bodies)[:c.n_knee]), base_body=c.base_body, max_episode_length=int(c.max_episode_length),
+                clip_obs=c.clip_obs)
+
+
+def check_post_physics_golden(make_backend, robot="anymal"):
+    """The kernel's post_physics_step (obs + reward + reset mask) on the golden inputs vs the reference's own
+    outputs: 1e-5 relative, masks bit-exact."""
+    g = np.load(os.path.join(GOLDEN, "anymal_flat.npz" if robot == "anymal" else "hound_flat.npz"))
+    art = load_robot(robot)
+    n, nd = g["root"].shape[0], art.num_dofs
+    sp = flat_params()
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 85.0, 2.0)
+    c = anymal_cfg(art, robot=robot)
+    c.clip_obs = 3.0e38
+    for i, v in enumerate(g["default"][0]):
+        c.default_dof_pos[i] = float(v)
+    c.base_body = int(g["base"])
+    for i, k in enumerate(g["knee"]):
+        c.knee_bodies[i] = int(k)
+    c.n_knee = len(g["knee"])
+    c.rew_lin_vel_xy, c.rew_ang_vel_z, c.rew_torque = float(g["scale_lin"]), float(g["scale_ang"]), float(g["scale_torque"])
+    c.max_episode_length = int(g["max_len"])
+    be = make_backend(art, sp, props, n)
+    try:
+        be.anymal_create(c)
+        dof = np.stack([g["dof_pos"], g["dof_vel"]], axis=2)
+        be.set_state(g["root"], dof)
+        # progress is incremented before use (tasks/anymal.py:232); reset_buf = 0 so no env is reset first
+        be.set_task(commands=g["commands"], progress=g["progress"] - 1, reset=np.zeros(n, np.int64), dof_force=g["torques"], contact=g["contact"])
+        be.anymal_post_only(g["actions"])
+        out = be.get_task()
+    finally:
+        be.close()
+    np.testing.assert_allclose(out["obs"], g["obs"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["rew"], g["rew"], rtol=1e-5, atol=1e-8)
+    assert np.array_equal(out["reset"], g["reset"].astype(np.int64)), "reset mask differs from the reference"
+    want_timeout = ((g["progress"] >= int(g["max_len"]) - 1) & g["reset"]).astype(np.int64)
+    assert np.array_equal(out["timeout"], want_timeout)
+    assert np.array_equal(out["progress"], g["progress"])
+
+
+def check_reset_draws(make_backend, robot="anymal", n=32, seed=1234):
+    """reset_idx(all) with the in-kernel Philox stream == the numpy restatement of the stream, bit for bit."""
+    art = load_robot(robot)
+    nd = art.num_dofs
+    sp = flat_params()
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 85.0, 2.0)
+    c = anymal_cfg(art, seed=seed, robot=robot)
+    be = make_backend(art, sp, props, n)
+    try:
+        be.anymal_create(c)
+        be.anymal_reset_all()
+        root, dof = be.get_state()
+        t = be.get_task()
+    finally:
+        be.close()
+    u = tm.philox_uniform(seed, np.arange(n), np.zeros(n), 2 * nd + 3)
+    d0 = np.array(list(c.default_dof_pos)[:nd], np.float32)
+    assert np.array_equal(dof[:, :, 0], d0[None] * tm.torch_rand_float(np.float32(0.5), np.float32(1.5), u[:, :nd]))
+    assert np.array_equal(dof[:, :, 1], tm.torch_rand_float(np.float32(-0.1), np.float32(0.1), u[:, nd:2 * nd]))
+    assert np.array_equal(t["commands"][:, 0], tm.torch_rand_float(np.float32(-2), np.float32(2), u[:, 2 * nd]))
+    assert np.array_equal(t["commands"][:, 2], tm.torch_rand_float(np.float32(-1), np.float32(1), u[:, 2 * nd + 2]))
+    assert np.array_equal(root, np.tile(np.array(list(c.init_root), np.float32), (n, 1)))
+    assert (t["reset"] == 1).all() and (t["progress"] == 0).all()
+
+
+def check_fused_step(make_backend, robot="anymal", n=16, steps=25, seed=3):
+    """VecTask.step fused in one kernel vs the oracle composition (float32 dynamics oracle + numpy task math in the
+    reference's order, same injected reset draws).  Physics drift is bounded loosely; the task math is then
+    re-checked at 1e-5 on the kernel's own state tensors, masks bit-exact."""
+    art = load_robot(robot)
+    nd, nb = art.num_dofs, art.num_bodies
+    rng = np.random.default_rng(seed)
+    sp = flat_params()
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 85.0, 2.0)
+    c = anymal_cfg(art, robot=robot)
+    c.max_episode_length = 12      # make time-outs happen inside the test
+    cd = cfg_dict(c, nd)
+    m = _abi.pack_model(art)
+    be = make_backend(art, sp, props, n)
+    n_draws = 2 * nd + 3
+    resets_seen = timeouts_seen = 0
+    try:
+        be.anymal_create(c)
+        draws = rng.uniform(0, 1, (n, n_draws)).astype(np.float32)
+        be.anymal_reset_all(draws)
+        root, dof = be.get_state()
+        t0 = be.get_task()
+        st = dict(root=root.copy(), dof_pos=dof[:, :, 0].copy(), dof_vel=dof[:, :, 1].copy(), torques=np.zeros((n, nd), np.float32),
+                  contact=np.zeros((n, nb, 3), np.float32), commands=t0["commands"].copy(), progress=t0["progress"].copy(), reset=t0["reset"].copy())
+        for k in range(steps):
+            actions = rng.uniform(-1.3, 1.3, (n, nd)).astype(np.float32)
+            draws = rng.uniform(0, 1, (n, n_draws)).astype(np.float32)
+            be.anymal_step(actions, draws)
+            # oracle: pre_physics + simulate + post_physics
+            a = np.clip(actions, -1.0, 1.0)
+            tgt = (np.float32(0.5) * a + cd["default_dof_pos"][None]).astype(np.float32)
+            dof_o = np.stack([st["dof_pos"], st["dof_vel"]], axis=2).astype(np.float32)
+            f, cf = O.simulate(m, sp, props, st["root"], dof_o, tgt, np.zeros((n, nd), np.float32))
+            st["dof_pos"], st["dof_vel"], st["torques"], st["contact"] = dof_o[:, :, 0].copy(), dof_o[:, :, 1].copy(), f, cf
+            was_reset = st["reset"].copy()
+            obs_o, obsc_o, rew_o, to_o = tm.anymal_post_physics(st, cd, a, draws)
+            root_k, dof_k = be.get_state()
+            tk = be.get_task()
+            # (1) end-to-end agreement, physics tolerance
+            assert np.abs(root_k - st["root"]).max() < 2e-3, f"step {k}: root deviates {np.abs(root_k - st['root']).max():.2e}"
+            assert np.abs(dof_k[:, :, 0] - st["dof_pos"]).max() < 5e-3
+            np.testing.assert_allclose(tk["obs"], obs_o, rtol=0, atol=2e-2)
+            assert np.array_equal(tk["progress"], st["progress"])
+            assert np.array_equal(tk["actions"], a)
+            # envs that were reset this step carry exactly the injected draws
+            ids = np.nonzero(was_reset)[0]
+            if len(ids):
+                assert np.array_equal(dof_k[ids, :, 0], st["dof_pos"][ids])
+                assert np.array_equal(tk["commands"][ids], st["commands"][ids])
+            # (2) task math at 1e-5 on the kernel's own state tensors
+            grav = np.tile(np.array([[0, 0, -1]], np.float32), (n, 1))
+            obs_s = tm.compute_anymal_observations(root_k, tk["commands"], dof_k[:, :, 0], np.tile(cd["default_dof_pos"], (n, 1)), dof_k[:, :, 1],
+                                                   grav, a, 2.0, 0.25, 1.0, 0.05)
+            rew_s, reset_s = tm.compute_anymal_reward(root_k, tk["commands"], tk["dof_force"], tk["contact"], cd["knee_bodies"], tk["progress"],
+                                                      cd["rew_scales"], cd["base_body"], cd["max_episode_length"])
+            np.testing.assert_allclose(tk["obs"], obs_s, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(tk["obs_clamped"], np.clip(obs_s, -5, 5), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(tk["rew"], rew_s, rtol=1e-5, atol=1e-8)
+            # contact-force norms within 1e-4 N of the 1 N threshold are legitimately ambiguous in float32
+            fn = np.concatenate([np.linalg.norm(tk["contact"][:, [cd["base_body"]], :], axis=2), np.linalg.norm(tk["contact"][:, cd["knee_bodies"], :], axis=2)], axis=1)
+            sure = (np.abs(fn - 1.0) > 1e-4).all(axis=1)
+            assert np.array_equal(tk["reset"][sure], reset_s.astype(np.int64)[sure])
+            to_s = ((tk["progress"] >= cd["max_episode_length"] - 1) & (tk["reset"] != 0)).astype(np.int64)
+            assert np.array_equal(tk["timeout"], to_s)
+            # keep the oracle in lock-step with the kernel's discrete decisions
+            assert np.array_equal(tk["reset"][sure], st["reset"][sure]), f"step {k}: reset decisions diverged"
+            st["reset"][:] = tk["reset"]
+            resets_seen += int(tk["reset"].sum())
+            timeouts_seen += int(tk["timeout"].sum())
+    finally:
+        be.close()
+    assert resets_seen > 0 and timeouts_seen > 0, "test must exercise resets and time-outs"

@@ -1,0 +1,38 @@
+"""GPU parity tests: libb200gym.so through its C ABI on cuda:0 against the oracle and the reference's
+golden vectors (same checks as the CPU emulator tests, larger batches)."""
+import pytest
+
+from tests import kernel_checks as kc
+
+pytestmark = pytest.mark.gpu
+
+
+def make(art, params, props, n):
+    from tests.backends import CudaBackend
+
+    return CudaBackend(art, params, props, n)
+
+
+@pytest.mark.parametrize("robot", ["anymal", "hound", "useful_hound", "cartpole"])
+def test_forward_dynamics(robot):
+    kc.check_forward_dynamics(make, robot, n=256)
+
+
+@pytest.mark.parametrize("robot,drive", [("anymal", "pos"), ("hound", "pos"), ("anymal_minimal", "effort"), ("useful_hound", "effort")])
+def test_simulate_horizon(robot, drive):
+    kc.check_simulate_horizon(make, robot, n=128, steps=10, drive=drive)
+
+
+@pytest.mark.parametrize("robot", ["anymal", "hound"])
+def test_post_physics_golden(robot):
+    kc.check_post_physics_golden(make, robot)
+
+
+@pytest.mark.parametrize("robot", ["anymal", "hound"])
+def test_reset_draws(robot):
+    kc.check_reset_draws(make, robot, n=1000)
+
+
+@pytest.mark.parametrize("robot", ["anymal", "hound"])
+def test_fused_step(robot):
+    kc.check_fused_step(make, robot, n=64, steps=40)
