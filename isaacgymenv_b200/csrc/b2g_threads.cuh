@@ -144,6 +144,17 @@ B2G_HD B2G_INL V3 quat_rotate(float qx, float qy, float qz, float qw, V3 v) {
     return a + b + c;
 }
 
+// (upper - lower) * u + lower exactly as torch evaluates it (utils/torch_jit_utils.py:215-218): a rounded multiply
+// followed by a rounded add -- no FMA contraction, so reset draws are bit-identical to the reference formula
+B2G_HD B2G_INL float rand_range(float lower, float upper, float u) {
+#if defined(B2G_HOST_EMU)
+    volatile float p = (upper - lower) * u;
+    return p + lower;
+#else
+    return __fadd_rn(__fmul_rn(upper - lower, u), lower);
+#endif
+}
+
 // reset_idx of the flat task for one lane (tasks/anymal.py:278-304): state <- init root, dof draws, commands
 template <int NL>
 B2G_HD B2G_INL void anymal_reset_lane(const TaskArgs& T, int env, int lane, int len, int d0, int nd, int rc, LaneState<NL>& st, float* cmd) {
@@ -158,13 +169,13 @@ B2G_HD B2G_INL void anymal_reset_lane(const TaskArgs& T, int env, int lane, int 
         if (j < len) {
             const int d = d0 + j;
             const float up = reset_uniform(T, env, rc, d, n_draws), uv = reset_uniform(T, env, rc, nd + d, n_draws);
-            st.q[j] = T.cfg.default_dof_pos[d] * ((1.5f - 0.5f) * up + 0.5f);
-            st.qd[j] = (0.1f - (-0.1f)) * uv + (-0.1f);
+            st.q[j] = T.cfg.default_dof_pos[d] * rand_range(0.5f, 1.5f, up);
+            st.qd[j] = rand_range(-0.1f, 0.1f, uv);
         }
     }
-    cmd[0] = (T.cfg.cmd_x[1] - T.cfg.cmd_x[0]) * reset_uniform(T, env, rc, 2 * nd + 0, n_draws) + T.cfg.cmd_x[0];
-    cmd[1] = (T.cfg.cmd_y[1] - T.cfg.cmd_y[0]) * reset_uniform(T, env, rc, 2 * nd + 1, n_draws) + T.cfg.cmd_y[0];
-    cmd[2] = (T.cfg.cmd_yaw[1] - T.cfg.cmd_yaw[0]) * reset_uniform(T, env, rc, 2 * nd + 2, n_draws) + T.cfg.cmd_yaw[0];
+    cmd[0] = rand_range(T.cfg.cmd_x[0], T.cfg.cmd_x[1], reset_uniform(T, env, rc, 2 * nd + 0, n_draws));
+    cmd[1] = rand_range(T.cfg.cmd_y[0], T.cfg.cmd_y[1], reset_uniform(T, env, rc, 2 * nd + 1, n_draws));
+    cmd[2] = rand_range(T.cfg.cmd_yaw[0], T.cfg.cmd_yaw[1], reset_uniform(T, env, rc, 2 * nd + 2, n_draws));
 }
 
 // The reset_idx(all) the task constructor performs (tasks/anymal.py:146).
