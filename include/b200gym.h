@@ -221,6 +221,22 @@ typedef struct b2g_task_buffers {
 } b2g_task_buffers;
 
 int b2g_task_anymal_create(b2g_sim* sim, const b2g_anymal_cfg* cfg);
+
+/* Cartpole task (reference: tasks/cartpole.py:36-196): effort = action * max_push_effort on DOF 0 (:159-163), obs =
+ * [x, xdot, theta, thetadot] (:131-142), reward/reset (:180-196), reset draws (:144-158). */
+typedef struct b2g_cartpole_cfg {
+    float reset_dist, max_push_effort;
+    float clip_obs, clip_actions;
+    int64_t max_episode_length;
+    uint64_t seed;
+} b2g_cartpole_cfg;
+int b2g_task_cartpole_create(b2g_sim* sim, const b2g_cartpole_cfg* cfg);
+
+/* task-generic entry points (dispatch on the task created on this sim) */
+int b2g_task_step(b2g_sim* sim, const float* actions_dev, void* stream);          /* VecTask.step, one launch   */
+int b2g_task_post_only(b2g_sim* sim, const float* actions_dev, void* stream);     /* post_physics_step only     */
+int b2g_task_step_host(b2g_sim* sim, const float* actions_host, float* obs_host, float* rew_host, int64_t* reset_host,
+                       int64_t* timeout_host, void* stream);                      /* host buffers, synchronises */
 /* allocate-and-describe the task buffers the sim owns (obs_buf, rew_buf, reset_buf, ...) */
 enum b2g_task_tensor_kind {
     B2G_TT_OBS = 0, B2G_TT_OBS_CLAMPED = 1, B2G_TT_REW = 2, B2G_TT_RESET = 3, B2G_TT_PROGRESS = 4,
@@ -246,7 +262,7 @@ int b2g_task_anymal_step_host(b2g_sim* sim, const float* actions_host, float* ob
 int64_t b2g_sim_launch_count(const b2g_sim* sim);
 
 /* sizeof() of the public PODs (0 model, 1 sim_params, 2 dof_props, 3 heightfield, 4 tensor_desc,
- * 5 anymal_cfg) so a foreign-language mirror of this header can verify its layout */
+ * 5 anymal_cfg, 6 cartpole_cfg) so a foreign-language mirror of this header can verify its layout */
 int b2g_sizeof(int which);
 
 /* gymtorch.wrap_tensor (tasks/anymal.py:121-126): wrap a tensor description as a DLPack

@@ -85,6 +85,11 @@ class AnymalCfg(C.Structure):
     ]
 
 
+class CartpoleCfg(C.Structure):
+    _fields_ = [("reset_dist", f32), ("max_push_effort", f32), ("clip_obs", f32), ("clip_actions", f32),
+                ("max_episode_length", C.c_int64), ("seed", C.c_uint64)]
+
+
 def _fill(dst, src):
     a = np.asarray(src)
     if a.ndim == 1:

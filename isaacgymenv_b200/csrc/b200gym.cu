@@ -82,6 +82,13 @@ __global__ void __launch_bounds__(kBlock) k_anymal_step(SimArgs A, TaskArgs T) {
     anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
 }
 
+__global__ void __launch_bounds__(kBlock) k_cartpole_step(SimArgs A, TaskArgs T) {
+    extern __shared__ float smem[];
+    int env, lane; bool valid; ScratchStrided sc; float* bf;
+    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    cartpole_step_thread(A, T, env, valid, sc, bf);
+}
+
 template <int LANES, int NL>
 __global__ void __launch_bounds__(kBlock) k_anymal_reset_all(SimArgs A, TaskArgs T) {
     extern __shared__ float smem[];
@@ -161,8 +168,11 @@ struct b2g_sim {
     float* t[B2G_T_COUNT] = {nullptr};
     // task
     bool has_task = false;
-    int num_obs = 0;
+    int task_kind = 0;             // 1 = flat locomotion (Anymal/Hound), 2 = Cartpole
+    int num_obs = 0, num_act = 0, n_draws = 0, n_cmd = 3;
+    unsigned long long seed = 0;
     b2g_anymal_cfg acfg{};
+    b2g_cartpole_cfg ccfg{};
     float *obs = nullptr, *obs_clamped = nullptr, *rew = nullptr, *commands = nullptr, *actions = nullptr, *rand_override = nullptr;
     long long *reset = nullptr, *progress = nullptr, *timeout = nullptr;
     int* reset_count = nullptr;
@@ -202,6 +212,8 @@ TaskArgs make_task_args(const b2g_sim* s, const float* actions_in, int post_only
     TaskArgs T;
     T.post_only = post_only;
     T.cfg = s->acfg;
+    T.ccfg = s->ccfg;
+    T.seed = s->seed;
     T.actions_in = actions_in;
     T.obs = s->obs; T.obs_clamped = s->obs_clamped; T.rew = s->rew; T.reset = s->reset; T.progress = s->progress;
     T.timeout = s->timeout; T.commands = s->commands; T.actions = s->actions; T.reset_count = s->reset_count;
@@ -293,6 +305,12 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
     const TaskArgs T = make_task_args(s, actions_dev, post_only);
     const int grid = grid_size(s);
     const size_t sm = smem_bytes(s);
+    if (s->task_kind == 2) {
+        k_cartpole_step<<<grid, kBlock, sm, st>>>(A, T);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return B2G_OK;
+    }
     if (s->v.lanes == 4) { if (s->has_hf) k_anymal_step<4, 3, true><<<grid, kBlock, sm, st>>>(A, T); else k_anymal_step<4, 3, false><<<grid, kBlock, sm, st>>>(A, T); }
     else { if (s->has_hf) k_anymal_step<8, 6, true><<<grid, kBlock, sm, st>>>(A, T); else k_anymal_step<8, 6, false><<<grid, kBlock, sm, st>>>(A, T); }
     s->launches++;
@@ -319,6 +337,7 @@ int b2g_sizeof(int which) {
         case 3: return (int)sizeof(b2g_heightfield);
         case 4: return (int)sizeof(b2g_tensor_desc);
         case 5: return (int)sizeof(b2g_anymal_cfg);
+        case 6: return (int)sizeof(b2g_cartpole_cfg);
         default: return -1;
     }
 }
@@ -549,36 +568,27 @@ int b2g_sim_forward_dynamics(b2g_sim* s, float* qdd, float* a0, void* stream) {
 }
 
 // ---- fused flat task ----
-int b2g_task_anymal_create(b2g_sim* s, const b2g_anymal_cfg* cfg) {
-    if (!s || !cfg) return fail(B2G_ERR_ARG, "null argument");
-    if (!s->prepared) return fail(B2G_ERR_STATE, "task created before prepare_sim");
-    if (s->model.fixed_base) return fail(B2G_ERR_UNSUPPORTED, "the flat locomotion task needs a floating base");
-    if (cfg->base_body < 0 || cfg->base_body >= s->model.n_bodies || cfg->n_knee < 0 || cfg->n_knee > 8)
-        return fail(B2G_ERR_ARG, "bad base/knee body indices");
-    for (int k = 0; k < cfg->n_knee; k++)
-        if (cfg->knee_bodies[k] < 0 || cfg->knee_bodies[k] >= s->model.n_bodies) return fail(B2G_ERR_ARG, "bad knee body index");
-    s->acfg = *cfg;
-    if (s->has_task) return B2G_OK;
+static int alloc_task_buffers(b2g_sim* s, int num_obs, int num_act, int n_draws) {
     return with_device(s, [&]() {
-        const size_t n = s->n_envs, nd = s->model.n_dof;
-        s->num_obs = 12 + 3 * (int)nd;
-        CUDA_TRY(cudaMalloc(&s->obs, sizeof(float) * n * s->num_obs));
-        CUDA_TRY(cudaMalloc(&s->obs_clamped, sizeof(float) * n * s->num_obs));
+        const size_t n = s->n_envs;
+        s->num_obs = num_obs; s->num_act = num_act; s->n_draws = n_draws;
+        CUDA_TRY(cudaMalloc(&s->obs, sizeof(float) * n * num_obs));
+        CUDA_TRY(cudaMalloc(&s->obs_clamped, sizeof(float) * n * num_obs));
         CUDA_TRY(cudaMalloc(&s->rew, sizeof(float) * n));
-        CUDA_TRY(cudaMalloc(&s->commands, sizeof(float) * n * 3));
-        CUDA_TRY(cudaMalloc(&s->actions, sizeof(float) * n * nd));
-        CUDA_TRY(cudaMalloc(&s->actions_in, sizeof(float) * n * nd));
-        CUDA_TRY(cudaMalloc(&s->rand_override, sizeof(float) * n * (2 * nd + 3)));
+        CUDA_TRY(cudaMalloc(&s->commands, sizeof(float) * n * 4));
+        CUDA_TRY(cudaMalloc(&s->actions, sizeof(float) * n * num_act));
+        CUDA_TRY(cudaMalloc(&s->actions_in, sizeof(float) * n * num_act));
+        CUDA_TRY(cudaMalloc(&s->rand_override, sizeof(float) * n * n_draws));
         CUDA_TRY(cudaMalloc(&s->reset, sizeof(long long) * n));
         CUDA_TRY(cudaMalloc(&s->progress, sizeof(long long) * n));
         CUDA_TRY(cudaMalloc(&s->timeout, sizeof(long long) * n));
         CUDA_TRY(cudaMalloc(&s->reset_count, sizeof(int) * n));
-        CUDA_TRY(cudaMemset(s->obs, 0, sizeof(float) * n * s->num_obs));
-        CUDA_TRY(cudaMemset(s->obs_clamped, 0, sizeof(float) * n * s->num_obs));
+        CUDA_TRY(cudaMemset(s->obs, 0, sizeof(float) * n * num_obs));
+        CUDA_TRY(cudaMemset(s->obs_clamped, 0, sizeof(float) * n * num_obs));
         CUDA_TRY(cudaMemset(s->rew, 0, sizeof(float) * n));
-        CUDA_TRY(cudaMemset(s->commands, 0, sizeof(float) * n * 3));
-        CUDA_TRY(cudaMemset(s->actions, 0, sizeof(float) * n * nd));
-        CUDA_TRY(cudaMemset(s->rand_override, 0, sizeof(float) * n * (2 * nd + 3)));
+        CUDA_TRY(cudaMemset(s->commands, 0, sizeof(float) * n * 4));
+        CUDA_TRY(cudaMemset(s->actions, 0, sizeof(float) * n * num_act));
+        CUDA_TRY(cudaMemset(s->rand_override, 0, sizeof(float) * n * n_draws));
         CUDA_TRY(cudaMemset(s->progress, 0, sizeof(long long) * n));
         CUDA_TRY(cudaMemset(s->timeout, 0, sizeof(long long) * n));
         CUDA_TRY(cudaMemset(s->reset_count, 0, sizeof(int) * n));
@@ -590,10 +600,40 @@ int b2g_task_anymal_create(b2g_sim* s, const b2g_anymal_cfg* cfg) {
     });
 }
 
+int b2g_task_anymal_create(b2g_sim* s, const b2g_anymal_cfg* cfg) {
+    if (!s || !cfg) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "task created before prepare_sim");
+    if (s->model.fixed_base) return fail(B2G_ERR_UNSUPPORTED, "the flat locomotion task needs a floating base");
+    if (cfg->base_body < 0 || cfg->base_body >= s->model.n_bodies || cfg->n_knee < 0 || cfg->n_knee > 8)
+        return fail(B2G_ERR_ARG, "bad base/knee body indices");
+    for (int k = 0; k < cfg->n_knee; k++)
+        if (cfg->knee_bodies[k] < 0 || cfg->knee_bodies[k] >= s->model.n_bodies) return fail(B2G_ERR_ARG, "bad knee body index");
+    if (s->has_task && s->task_kind != 1) return fail(B2G_ERR_STATE, "another task already lives on this sim");
+    s->acfg = *cfg;
+    s->seed = cfg->seed;
+    s->task_kind = 1;
+    s->n_cmd = 3;
+    if (s->has_task) return B2G_OK;
+    const int nd = s->model.n_dof;
+    return alloc_task_buffers(s, 12 + 3 * nd, nd, 2 * nd + 3);
+}
+
+int b2g_task_cartpole_create(b2g_sim* s, const b2g_cartpole_cfg* cfg) {
+    if (!s || !cfg) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "task created before prepare_sim");
+    if (!s->model.fixed_base || s->model.n_dof != 2 || s->v.lanes != 1) return fail(B2G_ERR_UNSUPPORTED, "Cartpole needs the fixed-base 2-DOF cart-pole model");
+    if (s->has_task && s->task_kind != 2) return fail(B2G_ERR_STATE, "another task already lives on this sim");
+    s->ccfg = *cfg;
+    s->seed = cfg->seed;
+    s->task_kind = 2;
+    if (s->has_task) return B2G_OK;
+    return alloc_task_buffers(s, 4, 1, 4);
+}
+
 int b2g_task_tensor(b2g_sim* s, int kind, b2g_tensor_desc* d) {
     if (!s || !d) return fail(B2G_ERR_ARG, "null argument");
     if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
-    const int64_t n = s->n_envs, nd = s->model.n_dof;
+    const int64_t n = s->n_envs;
     d->device_id = s->device;
     d->dtype = 0;
     d->shape[0] = n; d->shape[1] = d->shape[2] = d->shape[3] = 1;
@@ -605,9 +645,9 @@ int b2g_task_tensor(b2g_sim* s, int kind, b2g_tensor_desc* d) {
         case B2G_TT_RESET: d->data = s->reset; d->dtype = 2; break;
         case B2G_TT_PROGRESS: d->data = s->progress; d->dtype = 2; break;
         case B2G_TT_TIMEOUT: d->data = s->timeout; d->dtype = 2; break;
-        case B2G_TT_COMMANDS: d->data = s->commands; d->ndim = 2; d->shape[1] = 3; break;
-        case B2G_TT_ACTIONS: d->data = s->actions; d->ndim = 2; d->shape[1] = nd; break;
-        case B2G_TT_RAND_OVERRIDE: d->data = s->rand_override; d->ndim = 2; d->shape[1] = 2 * nd + 3; break;
+        case B2G_TT_COMMANDS: d->data = s->commands; d->ndim = 2; d->shape[1] = s->n_cmd; break;
+        case B2G_TT_ACTIONS: d->data = s->actions; d->ndim = 2; d->shape[1] = s->num_act; break;
+        case B2G_TT_RAND_OVERRIDE: d->data = s->rand_override; d->ndim = 2; d->shape[1] = s->n_draws; break;
         default: return fail(B2G_ERR_ARG, "unknown task tensor kind %d", kind);
     }
     return B2G_OK;
@@ -621,7 +661,7 @@ int b2g_task_set_rand_override(b2g_sim* s, int use) {
 
 int b2g_task_anymal_reset_all(b2g_sim* s, void* stream) {
     if (!s) return fail(B2G_ERR_ARG, "null sim");
-    if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
+    if (!s->has_task || s->task_kind != 1) return fail(B2G_ERR_STATE, "no flat locomotion task created");
     return with_device(s, [&]() {
         const SimArgs A = make_args(s);
         const TaskArgs T = make_task_args(s, nullptr);
@@ -652,7 +692,7 @@ int b2g_task_anymal_step_host(b2g_sim* s, const float* actions_host, float* obs_
     if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
     return with_device(s, [&]() {
         cudaStream_t st = (cudaStream_t)stream;
-        const size_t n = s->n_envs, nd = s->model.n_dof;
+        const size_t n = s->n_envs, nd = s->num_act;
         CUDA_TRY(cudaMemcpyAsync(s->actions_in, actions_host, sizeof(float) * n * nd, cudaMemcpyHostToDevice, st));
         const int rc = launch_anymal_step(s, s->actions_in, st);
         if (rc != B2G_OK) return rc;
@@ -663,6 +703,12 @@ int b2g_task_anymal_step_host(b2g_sim* s, const float* actions_host, float* obs_
         CUDA_TRY(cudaStreamSynchronize(st));
         return (int)B2G_OK;
     });
+}
+
+int b2g_task_step(b2g_sim* s, const float* actions_dev, void* stream) { return b2g_task_anymal_step(s, actions_dev, stream); }
+int b2g_task_post_only(b2g_sim* s, const float* actions_dev, void* stream) { return b2g_task_anymal_post_only(s, actions_dev, stream); }
+int b2g_task_step_host(b2g_sim* s, const float* a, float* o, float* r, int64_t* rs, int64_t* to, void* stream) {
+    return b2g_task_anymal_step_host(s, a, o, r, rs, to, stream);
 }
 
 int64_t b2g_sim_launch_count(const b2g_sim* s) { return s ? s->launches : 0; }

@@ -22,6 +22,8 @@ struct SimArgs {
 
 struct TaskArgs {
     b2g_anymal_cfg cfg;
+    b2g_cartpole_cfg ccfg;
+    unsigned long long seed;
     const float* actions_in;   // (N,na)
     float* obs;                // (N,12+3*nd)
     float* obs_clamped;
@@ -123,7 +125,7 @@ B2G_HD B2G_INL void philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c
 B2G_HD B2G_INL float reset_uniform(const TaskArgs& T, int env, int rc, int i, int n_draws) {
     if (T.rand_override) return T.rand_override[(size_t)env * n_draws + i];
     unsigned o[4];
-    philox4x32((unsigned)env, (unsigned)rc, (unsigned)(i >> 2), 0u, (unsigned)(T.cfg.seed & 0xffffffffull), (unsigned)(T.cfg.seed >> 32), o);
+    philox4x32((unsigned)env, (unsigned)rc, (unsigned)(i >> 2), 0u, (unsigned)(T.seed & 0xffffffffull), (unsigned)(T.seed >> 32), o);
     return (float)(o[i & 3] >> 8) * (1.0f / 16777216.0f);
 }
 
@@ -309,6 +311,57 @@ B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int 
             }
         }
 #undef B2G_PUT
+    }
+}
+
+// VecTask.step for Cartpole, fused (tasks/cartpole.py:159-163 effort, :166-175 post_physics_step, :144-158 reset_idx,
+// :131-142 observations, :180-196 reward/reset; vec_task.py:394,402 tail).  One thread per environment.
+B2G_HD B2G_INL void cartpole_step_thread(const SimArgs& A, const TaskArgs& T, int env, bool valid, ScratchStrided sc, float* bf) {
+    const DevModel* M = A.M;
+    const b2g_cartpole_cfg& C = T.ccfg;
+    LaneState<2> st;
+    load_state<2>(A, env, 2, 0, st);
+    float a = T.actions_in[env];
+    a = fminf(fmaxf(a, -C.clip_actions), C.clip_actions);
+    st.act[0] = a * C.max_push_effort;
+    st.act[1] = 0.0f;
+    if (!T.post_only) {
+        for (int s = 0; s < A.P.substeps; s++)
+            substep<1, 2, true, false>(M, A.P, 0, 2, 0, st, 1.0f, s == A.P.substeps - 1, sc, bf);
+    }
+    long long progress = T.progress[env] + 1;
+    long long reset_prev = T.reset[env];
+    int rc = 0;
+    const bool do_reset = reset_prev != 0;
+    if (do_reset) {
+        rc = T.reset_count[env];
+        // positions = 0.2 * (rand - 0.5), velocities = 0.5 * (rand - 0.5); draw order: pos[0], pos[1], vel[0], vel[1]
+        st.q[0] = 0.2f * (reset_uniform(T, env, rc, 0, 4) - 0.5f);
+        st.q[1] = 0.2f * (reset_uniform(T, env, rc, 1, 4) - 0.5f);
+        st.qd[0] = 0.5f * (reset_uniform(T, env, rc, 2, 4) - 0.5f);
+        st.qd[1] = 0.5f * (reset_uniform(T, env, rc, 3, 4) - 0.5f);
+        reset_prev = 0;
+        progress = 0;
+    }
+    const float cart_pos = st.q[0], cart_vel = st.qd[0], pole_angle = st.q[1], pole_vel = st.qd[1];
+    float rew = 1.0f - pole_angle * pole_angle - 0.01f * fabsf(cart_vel) - 0.005f * fabsf(pole_vel);
+    const bool out_x = fabsf(cart_pos) > C.reset_dist, out_a = fabsf(pole_angle) > 1.57079632679489661923f;
+    if (out_x) rew = -2.0f;
+    if (out_a) rew = -2.0f;
+    const bool time_out = progress >= C.max_episode_length - 1;
+    const long long reset = (out_x || out_a || time_out) ? 1 : reset_prev;
+    if (valid) {
+        store_state<2>(A, env, 0, 2, 0, st, true);
+        float* o = T.obs + (size_t)env * 4;
+        float* oc = T.obs_clamped + (size_t)env * 4;
+        const float v[4] = {cart_pos, cart_vel, pole_angle, pole_vel};
+        for (int k = 0; k < 4; k++) { o[k] = v[k]; oc[k] = fminf(fmaxf(v[k], -C.clip_obs), C.clip_obs); }
+        T.rew[env] = rew;
+        T.reset[env] = reset;
+        T.progress[env] = progress;
+        T.timeout[env] = (time_out && reset != 0) ? 1 : 0;
+        T.actions[env] = a;
+        if (do_reset) T.reset_count[env] = rc + 1;
     }
 }
 

@@ -49,6 +49,22 @@ class EmuBackend:
         return self.emu.forward_dynamics(self.model, self.params, self.props, self.root.copy(), self.dof.copy(), tau)
 
     # ---- fused flat task ----
+    def cartpole_create(self, cfg):
+        n = self.n
+        self.cfg = cfg
+        self.kind = "cartpole"
+        self.task = dict(obs=np.zeros((n, 4), np.float32), obs_clamped=np.zeros((n, 4), np.float32), rew=np.zeros(n, np.float32),
+                         reset=np.ones(n, np.int64), progress=np.zeros(n, np.int64), timeout=np.zeros(n, np.int64),
+                         commands=np.zeros((n, 3), np.float32), actions=np.zeros((n, 1), np.float32), reset_count=np.zeros(n, np.int32))
+
+    def task_step(self, actions, draws=None, post_only=False):
+        if getattr(self, "kind", "anymal") == "cartpole":
+            self.emu.cartpole(self.model, self.params, self.props, self.cfg, 2 if post_only else 1, self._bufs(), actions, draws)
+        elif post_only:
+            self.anymal_post_only(actions, draws)
+        else:
+            self.anymal_step(actions, draws)
+
     def anymal_create(self, cfg):
         n, nd = self.n, self.art.num_dofs
         no = 12 + 3 * nd
@@ -155,6 +171,18 @@ class CudaBackend:
         kinds = dict(obs=_abi.TT_OBS, obs_clamped=_abi.TT_OBS_CLAMPED, rew=_abi.TT_REW, reset=_abi.TT_RESET, progress=_abi.TT_PROGRESS,
                      timeout=_abi.TT_TIMEOUT, commands=_abi.TT_COMMANDS, actions=_abi.TT_ACTIONS, rand=_abi.TT_RAND_OVERRIDE)
         self.task = {k: self._tensor(v, task=True) for k, v in kinds.items()}
+
+    def cartpole_create(self, cfg):
+        self._lib.check(self.lib.b2g_task_cartpole_create(self.sim, C.byref(cfg)), "task create")
+        kinds = dict(obs=_abi.TT_OBS, obs_clamped=_abi.TT_OBS_CLAMPED, rew=_abi.TT_REW, reset=_abi.TT_RESET, progress=_abi.TT_PROGRESS,
+                     timeout=_abi.TT_TIMEOUT, commands=_abi.TT_COMMANDS, actions=_abi.TT_ACTIONS, rand=_abi.TT_RAND_OVERRIDE)
+        self.task = {k: self._tensor(v, task=True) for k, v in kinds.items()}
+
+    def task_step(self, actions, draws=None, post_only=False):
+        self._draws(draws)
+        fn = self.lib.b2g_task_post_only if post_only else self.lib.b2g_task_step
+        self._lib.check(fn(self.sim, self._actions(actions), self.stream), "task step")
+        self.torch.cuda.synchronize()
 
     def _draws(self, draws):
         if draws is None:

@@ -308,3 +308,97 @@ def check_fused_step(make_backend, robot="anymal", n=16, steps=25, seed=3):
     finally:
         be.close()
     assert resets_seen > 0 and timeouts_seen > 0, "test must exercise resets and time-outs"
+
+
+# ------------------------------------------------------------------------------------------------
+def cartpole_params():
+    sp = _abi.SimParams(dt=0.0166, substeps=2, num_position_iterations=4, num_velocity_iterations=0, contact_offset=0.02, rest_offset=0.001,
+                        bounce_threshold_velocity=0.2, max_depenetration_velocity=100.0, plane_static_friction=1.0, plane_dynamic_friction=1.0,
+                        plane_restitution=0.0, has_ground=1)
+    sp.gravity[2] = -9.81
+    return sp
+
+
+def cartpole_cfg(seed=42):
+    return _abi.CartpoleCfg(reset_dist=3.0, max_push_effort=400.0, clip_obs=5.0, clip_actions=1.0, max_episode_length=500, seed=seed)
+
+
+def cartpole_props(art):
+    p = _abi.default_dof_props(art, _abi.DOF_MODE_NONE, 0.0, 0.0)
+    p.drive_mode[0] = _abi.DOF_MODE_EFFORT
+    return p
+
+
+def check_cartpole_golden(make_backend):
+    """Cartpole reward / reset (tasks/cartpole.py:180-196) through the kernel vs the reference's own outputs."""
+    g = np.load(os.path.join(GOLDEN, "cartpole.npz"))
+    art = load_robot("cartpole")
+    n = g["pole_angle"].shape[0]
+    be = make_backend(art, cartpole_params(), cartpole_props(art), n)
+    try:
+        c = cartpole_cfg()
+        c.clip_obs = 3.0e38
+        be.cartpole_create(c)
+        root = np.zeros((n, 13), np.float32)
+        root[:, 2], root[:, 6] = 2.0, 1.0
+        dof = np.zeros((n, 2, 2), np.float32)
+        dof[:, 0, 0], dof[:, 0, 1], dof[:, 1, 0], dof[:, 1, 1] = g["cart_pos"], g["cart_vel"], g["pole_angle"], g["pole_vel"]
+        be.set_state(root, dof)
+        be.set_task(progress=g["progress"] - 1, reset=np.zeros(n, np.int64))
+        be.task_step(np.zeros((n, 1), np.float32), post_only=True)
+        out = be.get_task()
+    finally:
+        be.close()
+    keep = g["reset_buf"] == 0        # envs whose incoming reset_buf was 1 would be re-initialised first by post_physics_step
+    np.testing.assert_allclose(out["rew"], g["rew"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(out["reset"][keep], g["reset"][keep])
+    np.testing.assert_allclose(out["obs"][:, 0], g["cart_pos"], rtol=0, atol=0)
+    np.testing.assert_allclose(out["obs"][:, 2], g["pole_angle"], rtol=0, atol=0)
+
+
+def check_cartpole_step(make_backend, n=32, steps=60, seed=5):
+    """Fused Cartpole step vs oracle composition (float32 dynamics oracle + numpy reward in the reference's order)."""
+    art = load_robot("cartpole")
+    sp, props, c = cartpole_params(), cartpole_props(art), cartpole_cfg()
+    c.max_episode_length = 25
+    m = _abi.pack_model(art)
+    rng = np.random.default_rng(seed)
+    be = make_backend(art, sp, props, n)
+    resets = 0
+    try:
+        be.cartpole_create(c)
+        root = np.zeros((n, 13), np.float32)
+        root[:, 2], root[:, 6] = 2.0, 1.0
+        dof = np.zeros((n, 2, 2), np.float32)
+        be.set_state(root, dof)
+        progress, reset = np.zeros(n, np.int64), np.ones(n, np.int64)
+        for k in range(steps):
+            actions = rng.uniform(-1.2, 1.2, (n, 1)).astype(np.float32)
+            draws = rng.uniform(0, 1, (n, 4)).astype(np.float32)
+            be.task_step(actions, draws)
+            a = np.clip(actions, -1, 1)
+            act = np.zeros((n, 2), np.float32)
+            act[:, 0] = a[:, 0] * np.float32(400.0)
+            O.simulate(m, sp, props, root, dof, np.zeros((n, 2), np.float32), act)
+            progress += 1
+            ids = np.nonzero(reset)[0]
+            dof[ids, :, 0] = np.float32(0.2) * (draws[ids, 0:2] - np.float32(0.5))
+            dof[ids, :, 1] = np.float32(0.5) * (draws[ids, 2:4] - np.float32(0.5))
+            reset[ids], progress[ids] = 0, 0
+            rew, reset = tm.compute_cartpole_reward(dof[:, 1, 0], dof[:, 1, 1], dof[:, 0, 1], dof[:, 0, 0], 3.0, reset, progress, 25.0)
+            rk, dk = be.get_state()
+            t = be.get_task()
+            assert np.abs(dk - dof).max() < 2e-3, f"step {k}: dof state deviates {np.abs(dk - dof).max():.2e}"
+            assert np.array_equal(dk[ids], dof[ids])          # reset draws applied exactly
+            obs = np.stack([dk[:, 0, 0], dk[:, 0, 1], dk[:, 1, 0], dk[:, 1, 1]], axis=1)
+            np.testing.assert_array_equal(t["obs"], obs)
+            np.testing.assert_array_equal(t["obs_clamped"], np.clip(obs, -5, 5))
+            rew_s, reset_s = tm.compute_cartpole_reward(dk[:, 1, 0], dk[:, 1, 1], dk[:, 0, 1], dk[:, 0, 0], 3.0, np.zeros(n, np.int64), t["progress"], 25.0)
+            np.testing.assert_allclose(t["rew"], rew_s, rtol=1e-5, atol=1e-6)
+            assert np.array_equal(t["reset"], reset_s) and np.array_equal(t["progress"], progress)
+            assert np.array_equal(t["timeout"], ((progress >= 24) & (t["reset"] != 0)).astype(np.int64))
+            reset = t["reset"].copy()
+            resets += int(reset.sum())
+    finally:
+        be.close()
+    assert resets > 0

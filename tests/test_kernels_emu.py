@@ -32,3 +32,11 @@ def test_reset_draws():
 
 def test_fused_step():
     kc.check_fused_step(make, "anymal", n=6, steps=25)
+
+
+def test_cartpole_golden():
+    kc.check_cartpole_golden(make)
+
+
+def test_cartpole_step():
+    kc.check_cartpole_step(make)

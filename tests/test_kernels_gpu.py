@@ -36,3 +36,11 @@ def test_reset_draws(robot):
 @pytest.mark.parametrize("robot", ["anymal", "hound"])
 def test_fused_step(robot):
     kc.check_fused_step(make, robot, n=64, steps=40)
+
+
+def test_cartpole_golden():
+    kc.check_cartpole_golden(make)
+
+
+def test_cartpole_step():
+    kc.check_cartpole_step(make)
