@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2G_ABI_VERSION 1
+#define B2G_ABI_VERSION 2
 
 #define B2G_MAX_DOF 24
 #define B2G_MAX_LINKS (B2G_MAX_DOF + 1)
@@ -103,6 +103,8 @@ typedef struct b2g_sim_params {
     float plane_dynamic_friction;
     float plane_restitution;
     int32_t has_ground;               /* add_ground was called */
+    float joint_limit_stiffness;      /* joint limits are one-sided implicit spring-dampers [N m/rad, N m s/rad]  */
+    float joint_limit_damping;
 } b2g_sim_params;
 
 /* per-DOF drive properties, identical for every env (reference: tasks/anymal.py:199-203,214) */

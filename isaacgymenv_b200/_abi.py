@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-B2G_ABI_VERSION = 1
+B2G_ABI_VERSION = 2
 MAX_DOF = 24
 MAX_LINKS = MAX_DOF + 1
 MAX_BODIES = 32
@@ -50,7 +50,7 @@ class SimParams(C.Structure):
         ("contact_offset", f32), ("rest_offset", f32), ("bounce_threshold_velocity", f32),
         ("max_depenetration_velocity", f32),
         ("plane_static_friction", f32), ("plane_dynamic_friction", f32), ("plane_restitution", f32),
-        ("has_ground", i32),
+        ("has_ground", i32), ("joint_limit_stiffness", f32), ("joint_limit_damping", f32),
     ]
 
 
@@ -144,15 +144,13 @@ def pack_model(art) -> Model:
 
 
 def contact_owner_chains(art) -> np.ndarray:
-    """Chain (solver lane) that owns each contact candidate: the chain of its link; root-link
-    candidates are dealt round-robin so every lane scans about the same number."""
-    nc = max(len(art.chain_start), 1)
+    """Chain (solver lane) that owns each contact candidate: the chain of its link; root-link candidates all go to
+    lane 0 (the solver is Gauss-Seidel inside a lane and Jacobi across lanes, which is only safe for weakly coupled
+    contacts, i.e. contacts on different chains)."""
     owner = np.zeros(len(art.cp_link), dtype=np.int32)
-    rr = 0
     for i, l in enumerate(art.cp_link):
         if l == 0:
-            owner[i] = rr % nc
-            rr += 1
+            owner[i] = 0     # all root-link candidates belong to lane 0: contacts on one body must not be Jacobi-split
         else:
             d = l - 1
             for c, (s, n) in enumerate(zip(art.chain_start, art.chain_len)):

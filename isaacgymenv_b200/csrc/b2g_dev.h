@@ -50,6 +50,7 @@ struct DevParams {
     float max_depen;
     float mu_ground;
     int has_ground;
+    float limit_kp, limit_kd;   // joint-limit spring / damper
     // heightfield (null -> plane z = 0)
     const int16_t* hf;
     int hf_rows, hf_cols;

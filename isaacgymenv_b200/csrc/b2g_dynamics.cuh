@@ -5,13 +5,14 @@
 //
 // Algorithm (DESIGN.md "dynamics"): Featherstone articulated-body algorithm in one common frame (world
 // axes at the root origin, so no spatial transforms inside the recursion); implicit PD drives folded
-// into the joint-space diagonal; hard contact solved at the velocity level by projected Gauss-Seidel
-// with impulses propagated through the articulated inertias; position iterations with penetration
-// bias, positions integrated, then velocity iterations without bias; semi-implicit Euler.
+// (and one-sided joint-limit springs) folded into the joint-space diagonal; hard contact solved at the velocity
+// level by projected relaxation (Gauss-Seidel along a chain, Jacobi across chains) with impulses propagated through
+// the articulated inertias; position iterations with penetration bias, positions integrated, then velocity
+// iterations without bias; semi-implicit Euler.
 //
 // Parallel mapping: each lane owns one chain (kinematics, ABA recursion, its contact candidates); the
 // root's 6x6 articulated inertia and bias are summed across the lanes with warp shuffles, the root
-// solve is replicated, and every Gauss-Seidel impulse is broadcast from its owner lane as a 6-vector.
+// solve is replicated, and in every contact sweep the lanes' root-level impulse biases are summed the same way.
 #pragma once
 
 #include "b2g_dev.h"
@@ -169,12 +170,14 @@ B2G_HD B2G_INL void ground_sample(const DevParams& P, float x, float y, float& h
 // One sub-step.  `len` = links in this lane's chain (0 for an idle lane), `d0` = first DOF of the chain.
 // `bf` = this environment's body-force accumulator (n_bodies*3 floats, shared by the group), written on
 // the last sub-step only.
-// PROBE = true turns the call into the forward-dynamics probe of the parity tests: efforts st.act are
+// FULL = true promises len == NL on every lane.  PROBE = true turns the call into the forward-dynamics probe of the parity tests: efforts st.act are
 // applied raw (no drives), the function returns after the ABA with joint accelerations in st.frc and the
 // root's spatial acceleration (angular, linear) in st.rw / st.rv.
-template <int LANES, int NL, bool FIXED, bool HF, bool PROBE = false>
-B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, int lane, int len, int d0,
+template <int LANES, int NL, bool FIXED, bool HF, bool PROBE = false, bool FULL = false>
+B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, int lane, int len_in, int d0,
                             LaneState<NL>& st, float mu_shape, bool last, ScratchStrided sc, float* bf) {
+    // FULL: every lane's chain has exactly NL links (the quadrupeds) -> the `j < len` predicates fold away
+    const int len = FULL ? NL : len_in;
     const float h = P.h;
     const V3 grav = V3{P.g[0], P.g[1], P.g[2]};
 
@@ -226,6 +229,18 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
                 } else if (D.drive_mode == B2G_DOF_MODE_EFFORT) {
                     t = st.act[j];
                     if (D.effort > 0.0f) t = fminf(fmaxf(t, -D.effort), D.effort);
+                }
+                // joint limit: one-sided implicit spring-damper, folded in exactly like the implicit drive
+                {
+                    const float lo = D.lower, hi = D.upper, qp = st.q[j] + h * st.qd[j];
+                    float ref = 0.0f;
+                    bool on = false;
+                    if (lo > -1e30f && (st.q[j] < lo || qp < lo)) { ref = lo; on = true; }
+                    else if (hi < 1e30f && (st.q[j] > hi || qp > hi)) { ref = hi; on = true; }
+                    if (on && !PROBE) {
+                        t += P.limit_kp * (ref - st.q[j]) - (P.limit_kd + h * P.limit_kp) * st.qd[j];
+                        de += h * P.limit_kd + h * h * P.limit_kp;
+                    }
                 }
                 tau[j] = t;
                 dext[j] = de;
@@ -316,15 +331,14 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
     }
 
     // impulse helpers -----------------------------------------------------------------
-    // backward half: impulse F on link `jc` of this chain (-1 = root, -2 = none) and joint impulse tj on
-    // joint `jd` (-1 = none); returns the root-level bias Pb and per-joint ud[]
-    auto push_up = [&](int jc, SV F, int jd, float tj, float* ud) -> SV {
-        SV Pb = (jc >= -1) ? -F : sv0();
-        const int top = jc > jd ? jc : jd;
+    // backward half: impulse F on link `jc` of this chain (-1 = root): returns the root-level bias Pb and the per-joint
+    // terms ud[] the forward half needs
+    auto push_up = [&](int jc, SV F, float* ud) -> SV {
+        SV Pb = -F;
 #pragma unroll
         for (int i = NL - 1; i >= 0; i--) {
-            if (i <= top) {
-                ud[i] = ((i == jd) ? tj : 0.0f) - dot(S[i], Pb);
+            if (i <= jc) {
+                ud[i] = -dot(S[i], Pb);
                 Pb += U[i] * (ud[i] * Dinv[i]);
             } else {
                 ud[i] = 0.0f;
@@ -357,28 +371,6 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
             sc.at(s, CF_JC) = (float)jc;
             sc.at(s, CF_BODY) = (float)M->cp_body[i];
             sc.at(s, CF_LN) = 0.0f; sc.at(s, CF_L1) = 0.0f; sc.at(s, CF_L2) = 0.0f;
-            // local Delassus block: response of this contact point to unit impulses along n, t1, t2
-            const V3 dirs[3] = {n, t1, t2};
-            float A[9];
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
-                float ud[NL];
-                const SV F = SV{cross(r, dirs[b]), dirs[b]};
-                const SV Pb = push_up(jc, F, -1, 0.0f, ud);
-                SV a = FIXED ? sv0() : -mul(inv, Pb);
-#pragma unroll
-                for (int k = 0; k < NL; k++) {
-                    if (k <= jc) {
-                        const float dq = (ud[k] - dot(U[k], a)) * Dinv[k];
-                        a += S[k] * dq;
-                    }
-                }
-                const V3 pv = a.v + cross(a.w, r);
-#pragma unroll
-                for (int c = 0; c < 3; c++) A[c * 3 + b] = dot(pv, dirs[c]);
-            }
-            sc.at(s, CF_ANN) = A[0]; sc.at(s, CF_ANT1) = A[3]; sc.at(s, CF_ANT2) = A[6];
-            sc.at(s, CF_AT1T1) = A[4]; sc.at(s, CF_AT1T2) = A[7]; sc.at(s, CF_AT2T2) = A[8];
         }
     };
     if (ground) {
@@ -395,71 +387,48 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
         }
     }
 
-    // ---------------- joint limits ----------------
-    bool lim_on[NL];
-    float lim_sign[NL], lim_gap[NL], lim_A[NL], lim_lam[NL];
-    bool any_lim = false;
+    const int maxs = Grp<LANES>::warp_max(ncon);
+
+    // local Delassus block of every active contact: response of the contact point to unit impulses along n, t1, t2
+    // (one code instance for all links: the contact's link index is a run-time value, the chain loops are predicated)
+    for (int s = 0; s < maxs; s++) {
+        if (s < ncon) {
+            const V3 r = V3{sc.at(s, CF_RX), sc.at(s, CF_RY), sc.at(s, CF_RZ)};
+            const V3 dirs[3] = {V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)}, V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)},
+                                V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)}};
+            const int jc = (int)sc.at(s, CF_JC);
+            float A[9];
 #pragma unroll
-    for (int j = 0; j < NL; j++) {
-        lim_on[j] = false; lim_sign[j] = 0; lim_gap[j] = 0; lim_A[j] = 1.0f; lim_lam[j] = 0;
-        if (j < len) {
-            const float lo = M->dof[d0 + j].lower, hi = M->dof[d0 + j].upper;
-            const float qp = st.q[j] + h * qdn[j];
-            if (lo > -1e30f && qp < lo) { lim_on[j] = true; lim_sign[j] = 1.0f; lim_gap[j] = st.q[j] - lo; }
-            else if (hi < 1e30f && qp > hi) { lim_on[j] = true; lim_sign[j] = -1.0f; lim_gap[j] = hi - st.q[j]; }
-            any_lim = any_lim || lim_on[j];
-        }
-    }
-    const bool warp_lim = Grp<LANES>::warp_any(any_lim);
-    if (warp_lim) {
-#pragma unroll
-        for (int j = 0; j < NL; j++) {
-            if (lim_on[j]) {
+            for (int b = 0; b < 3; b++) {
                 float ud[NL];
-                const SV Pb = push_up(-2, sv0(), j, 1.0f, ud);
+                const SV F = SV{cross(r, dirs[b]), dirs[b]};
+                const SV Pb = push_up(jc, F, ud);
                 SV a = FIXED ? sv0() : -mul(inv, Pb);
-                float dqj = 0.0f;
 #pragma unroll
                 for (int k = 0; k < NL; k++) {
-                    if (k <= j) {
+                    if (k <= jc) {
                         const float dq = (ud[k] - dot(U[k], a)) * Dinv[k];
                         a += S[k] * dq;
-                        if (k == j) dqj = dq;
                     }
                 }
-                lim_A[j] = dqj;
+                const V3 pv = a.v + cross(a.w, r);
+#pragma unroll
+                for (int c = 0; c < 3; c++) A[c * 3 + b] = dot(pv, dirs[c]);
             }
+            sc.at(s, CF_ANN) = A[0]; sc.at(s, CF_ANT1) = A[3]; sc.at(s, CF_ANT2) = A[6];
+            sc.at(s, CF_AT1T1) = A[4]; sc.at(s, CF_AT1T2) = A[7]; sc.at(s, CF_AT2T2) = A[8];
         }
     }
 
-    // ---------------- projected Gauss-Seidel ----------------
-    const int maxs = Grp<LANES>::warp_max(ncon);
+    // ---------------- projected relaxation: Gauss-Seidel along a lane, Jacobi across lanes ----------------
+    // Contacts of different chains couple only through the (heavy) root, so slot s of every lane is updated from the
+    // same velocities; the root-level biases are summed with one shuffle butterfly and applied once.
     SV v0pos = v0n;
     float qdpos[NL];
 #pragma unroll
     for (int j = 0; j < NL; j++) qdpos[j] = qdn[j];
     const int nit = P.npos + P.nvel;
     const float mu = 0.5f * (P.mu_ground + mu_shape);   // PhysX default combine mode: average
-
-    // apply the owner's root-level bias + joint terms to the whole articulation
-    auto spread = [&](SV Pb, const float* ud, int owner) {
-        SV Pw = (lane == owner) ? Pb : sv0();
-        if (LANES > 1) Pw = grp_bcast<LANES>(Pw, owner);
-        SV a = sv0();
-        if (!FIXED) {
-            a = -mul(inv, Pw);
-            v0n += a;
-        }
-#pragma unroll
-        for (int k = 0; k < NL; k++) {
-            if (k < len) {
-                const float udk = (lane == owner) ? ud[k] : 0.0f;
-                const float dq = (udk - dot(U[k], a)) * Dinv[k];
-                a += S[k] * dq;
-                qdn[k] += dq;
-            }
-        }
-    };
 
     for (int it = 0; it < nit; it++) {
         if (it == P.npos) {
@@ -469,68 +438,55 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
         }
         const bool with_bias = it < P.npos;
         for (int s = 0; s < maxs; s++) {
-            for (int owner = 0; owner < LANES; owner++) {
-                const bool mine = (lane == owner) && (s < ncon);
-                if (!Grp<LANES>::warp_any(mine)) continue;
-                SV Pb = sv0();
-                float ud[NL];
+            SV Pb = sv0();
+            float ud[NL];
 #pragma unroll
-                for (int k = 0; k < NL; k++) ud[k] = 0.0f;
-                if (mine) {
-                    const V3 r = V3{sc.at(s, CF_RX), sc.at(s, CF_RY), sc.at(s, CF_RZ)};
-                    const V3 n = V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)};
-                    const V3 t1 = V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)};
-                    const V3 t2 = V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)};
-                    const int jc = (int)sc.at(s, CF_JC);
-                    SV lv = v0n;
+            for (int k = 0; k < NL; k++) ud[k] = 0.0f;
+            if (s < ncon) {
+                const V3 r = V3{sc.at(s, CF_RX), sc.at(s, CF_RY), sc.at(s, CF_RZ)};
+                const V3 n = V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)};
+                const V3 t1 = V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)};
+                const V3 t2 = V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)};
+                const int jc = (int)sc.at(s, CF_JC);
+                SV lv = v0n;
 #pragma unroll
-                    for (int k = 0; k < NL; k++)
-                        if (k <= jc) lv += S[k] * qdn[k];
-                    const V3 pv = lv.v + cross(lv.w, r);
-                    float vn = dot(pv, n), vt1 = dot(pv, t1), vt2 = dot(pv, t2);
-                    float tgt = -sc.at(s, CF_GAP) / h;
-                    tgt = fminf(tgt, P.max_depen);
-                    if (!with_bias) tgt = fminf(tgt, 0.0f);
-                    const float l0 = sc.at(s, CF_LN), l1o = sc.at(s, CF_L1), l2o = sc.at(s, CF_L2);
-                    float ln = fmaxf(l0 - (vn - tgt) / sc.at(s, CF_ANN), 0.0f);
-                    const float dn = ln - l0;
-                    vt1 += sc.at(s, CF_ANT1) * dn;
-                    vt2 += sc.at(s, CF_ANT2) * dn;
-                    float l1 = l1o - vt1 / sc.at(s, CF_AT1T1);
-                    vt2 += sc.at(s, CF_AT1T2) * (l1 - l1o);
-                    float l2 = l2o - vt2 / sc.at(s, CF_AT2T2);
-                    const float lim_t = mu * ln, mag = sqrtf(l1 * l1 + l2 * l2);
-                    if (mag > lim_t) {
-                        const float scl = (mag > 0.0f) ? lim_t / mag : 0.0f;
-                        l1 *= scl; l2 *= scl;
-                    }
-                    sc.at(s, CF_LN) = ln; sc.at(s, CF_L1) = l1; sc.at(s, CF_L2) = l2;
-                    const V3 dir = n * dn + t1 * (l1 - l1o) + t2 * (l2 - l2o);
-                    Pb = push_up(jc, SV{cross(r, dir), dir}, -1, 0.0f, ud);
+                for (int k = 0; k < NL; k++)
+                    if (k <= jc) lv += S[k] * qdn[k];
+                const V3 pv = lv.v + cross(lv.w, r);
+                float vn = dot(pv, n), vt1 = dot(pv, t1), vt2 = dot(pv, t2);
+                float tgt = -sc.at(s, CF_GAP) / h;
+                tgt = fminf(tgt, P.max_depen);
+                if (!with_bias) tgt = fminf(tgt, 0.0f);
+                const float l0 = sc.at(s, CF_LN), l1o = sc.at(s, CF_L1), l2o = sc.at(s, CF_L2);
+                float ln = fmaxf(l0 - (vn - tgt) / sc.at(s, CF_ANN), 0.0f);
+                const float dn = ln - l0;
+                vt1 += sc.at(s, CF_ANT1) * dn;
+                vt2 += sc.at(s, CF_ANT2) * dn;
+                float l1 = l1o - vt1 / sc.at(s, CF_AT1T1);
+                vt2 += sc.at(s, CF_AT1T2) * (l1 - l1o);
+                float l2 = l2o - vt2 / sc.at(s, CF_AT2T2);
+                const float lim_t = mu * ln, mag = sqrtf(l1 * l1 + l2 * l2);
+                if (mag > lim_t) {
+                    const float scl = (mag > 0.0f) ? lim_t / mag : 0.0f;
+                    l1 *= scl; l2 *= scl;
                 }
-                spread(Pb, ud, owner);
+                sc.at(s, CF_LN) = ln; sc.at(s, CF_L1) = l1; sc.at(s, CF_L2) = l2;
+                const V3 dir = n * dn + t1 * (l1 - l1o) + t2 * (l2 - l2o);
+                Pb = push_up(jc, SV{cross(r, dir), dir}, ud);
             }
-        }
-        if (warp_lim) {
-            for (int owner = 0; owner < LANES; owner++) {
+            // all lanes' impulses reach the root together, then run down every chain
+            SV a = sv0();
+            if (!FIXED) {
+                const SV Psum = (LANES > 1) ? grp_sum<LANES>(Pb) : Pb;
+                a = -mul(inv, Psum);
+                v0n += a;
+            }
 #pragma unroll
-                for (int j = 0; j < NL; j++) {
-                    const bool mine = (lane == owner) && lim_on[j];
-                    if (!Grp<LANES>::warp_any(mine)) continue;
-                    SV Pb = sv0();
-                    float ud[NL];
-#pragma unroll
-                    for (int k = 0; k < NL; k++) ud[k] = 0.0f;
-                    if (mine) {
-                        const float vrel = lim_sign[j] * qdn[j];
-                        float tgt = -lim_gap[j] / h;
-                        if (!with_bias) tgt = fminf(tgt, 0.0f);
-                        const float ln = fmaxf(lim_lam[j] - (vrel - tgt) / lim_A[j], 0.0f);
-                        const float dl = ln - lim_lam[j];
-                        lim_lam[j] = ln;
-                        Pb = push_up(-2, sv0(), j, lim_sign[j] * dl, ud);
-                    }
-                    spread(Pb, ud, owner);
+            for (int k = 0; k < NL; k++) {
+                if (k < len) {
+                    const float dq = (ud[k] - dot(U[k], a)) * Dinv[k];
+                    a += S[k] * dq;
+                    qdn[k] += dq;
                 }
             }
         }

@@ -92,6 +92,7 @@ inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, 
     d.contact_offset = s.contact_offset; d.max_depen = s.max_depenetration_velocity;
     d.mu_ground = (hf && hf_dev) ? hf->friction : s.plane_dynamic_friction;
     d.has_ground = s.has_ground;
+    d.limit_kp = s.joint_limit_stiffness; d.limit_kd = s.joint_limit_damping;
     if (hf && hf_dev) {
         d.hf = hf_dev; d.hf_rows = hf->rows; d.hf_cols = hf->cols; d.hf_hs = hf->horizontal_scale; d.hf_vs = hf->vertical_scale;
         d.hf_ox = hf->origin_x; d.hf_oy = hf->origin_y;

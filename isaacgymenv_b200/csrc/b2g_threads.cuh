@@ -97,7 +97,7 @@ B2G_HD B2G_INL void simulate_thread(const SimArgs& A, int env, int lane, bool va
     }
     const float mu_shape = A.friction ? A.friction[env] : 1.0f;
     for (int s = 0; s < A.P.substeps; s++)
-        substep<LANES, NL, FIXED, HF>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
+        substep<LANES, NL, FIXED, HF, false, (LANES == 4 && NL == 3) || (LANES == 1 && NL == 2)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
     if (valid) {
         store_state<NL>(A, env, lane, len, d0, st, FIXED);
         const int nb3 = M->n_bodies * 3;
@@ -232,7 +232,7 @@ B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int 
     if (!T.post_only) {
         const float mu_shape = A.friction ? A.friction[env] : 1.0f;
         for (int s = 0; s < A.P.substeps; s++)
-            substep<LANES, NL, false, HF>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
+            substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
     } else {
         // torques and contact forces come from the sim tensors instead of a physics step
 #pragma unroll
@@ -327,7 +327,7 @@ B2G_HD B2G_INL void cartpole_step_thread(const SimArgs& A, const TaskArgs& T, in
     st.act[1] = 0.0f;
     if (!T.post_only) {
         for (int s = 0; s < A.P.substeps; s++)
-            substep<1, 2, true, false>(M, A.P, 0, 2, 0, st, 1.0f, s == A.P.substeps - 1, sc, bf);
+            substep<1, 2, true, false, false, true>(M, A.P, 0, 2, 0, st, 1.0f, s == A.P.substeps - 1, sc, bf);
     }
     long long progress = T.progress[env] + 1;
     long long reset_prev = T.reset[env];

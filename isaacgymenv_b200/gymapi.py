@@ -131,6 +131,9 @@ class _PhysXParams:
         self.friction_offset_threshold = 0.04
         self.friction_correlation_distance = 0.025
         self.always_use_articulations = False
+        # not Isaac Gym parameters: joint limits are one-sided implicit spring-dampers in this engine
+        self.joint_limit_stiffness = 2000.0
+        self.joint_limit_damping = 20.0
 
 
 class _FlexParams:
@@ -239,7 +242,9 @@ class Sim:
                            num_velocity_iterations=int(px.num_velocity_iterations), contact_offset=px.contact_offset,
                            rest_offset=px.rest_offset, bounce_threshold_velocity=px.bounce_threshold_velocity,
                            max_depenetration_velocity=px.max_depenetration_velocity, plane_static_friction=1.0,
-                           plane_dynamic_friction=1.0, plane_restitution=0.0, has_ground=0)
+                           plane_dynamic_friction=1.0, plane_restitution=0.0, has_ground=0,
+                           joint_limit_stiffness=float(getattr(px, "joint_limit_stiffness", 2000.0)),
+                           joint_limit_damping=float(getattr(px, "joint_limit_damping", 20.0)))
         c.gravity[0], c.gravity[1], c.gravity[2] = g.x, g.y, g.z
         return c
 

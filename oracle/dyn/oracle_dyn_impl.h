@@ -16,8 +16,9 @@
  *     [R. Featherstone, Rigid Body Dynamics Algorithms, 2008, ch. 5-7, 9];
  *   - implicit PD position drives folded into the joint-space inertia (h*Kd + h^2*Kp on the diagonal),
  *     which is how an implicit spring/damper drive enters a velocity-level articulation solver;
- *   - hard contact at the velocity level: projected Gauss-Seidel over contact points with Coulomb
- *     friction (cone projection), impulses propagated through the articulated inertias, position
+ *   - hard contact at the velocity level: projected relaxation over contact points with Coulomb friction (cone
+ *     projection) -- Gauss-Seidel along a chain, Jacobi across chains (they couple only through the root) --
+ *     impulses propagated through the articulated inertias, position
  *     iterations with penetration bias followed by velocity iterations without it (PGS/TGS-style
  *     split named by `num_position_iterations` / `num_velocity_iterations`);
  *   - semi-implicit Euler integration per sub-step.
@@ -342,10 +343,6 @@ typedef struct FN(orc_contact) {
     R lam[3];        /* accumulated impulse (n, t1, t2) */
 } FN(orc_contact);
 
-typedef struct FN(orc_limit) {
-    int dof; R sign; R gap; R A; R lam;
-} FN(orc_limit);
-
 static void FN(orc_contact_wrench)(const FN(orc_contact)* c, const R* dir, R* F) {
     R mom[3];
     FN(cross3)(c->r, dir, mom);
@@ -387,6 +384,19 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
             R e = actuation[d], lim = (R)dp->effort[d];
             if (lim > 0) { if (e > lim) e = lim; if (e < -lim) e = -lim; }
             tau[d] = e;
+        }
+        /* joint limits: one-sided implicit spring-damper (same implicit folding as the drive), active when the joint
+         * is beyond a limit or would cross it within this sub-step at its current velocity */
+        {
+            R lo = (R)dp->lower[d], hi = (R)dp->upper[d], kl = (R)sp->joint_limit_stiffness, dl = (R)sp->joint_limit_damping;
+            R qp = q[d] + h * qd[d];
+            R ref = 0; int on = 0;
+            if (lo > -1e30f && (q[d] < lo || qp < lo)) { ref = lo; on = 1; }
+            else if (hi < 1e30f && (q[d] > hi || qp > hi)) { ref = hi; on = 1; }
+            if (on) {
+                tau[d] += kl * (ref - q[d]) - (dl + h * kl) * qd[d];
+                dext[d] += h * dl + h * h * kl;
+            }
         }
     }
     FN(orc_kinematics)(m, root13, q, qd, k);
@@ -442,22 +452,6 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
             for (int a = 0; a < 3; a++) cc->A[a * 3 + b] = pv[0] * dirs[a][0] + pv[1] * dirs[a][1] + pv[2] * dirs[a][2];
         }
     }
-    /* ---- joint limits ---- */
-    FN(orc_limit) lim[B2G_MAX_DOF];
-    int nlim = 0;
-    for (int d = 0; d < nd; d++) {
-        R lo = (R)dp->lower[d], hi = (R)dp->upper[d];
-        int act = 0; R sign = 0, gap = 0;
-        if (lo > -1e30f && q[d] + h * qd[d] < lo) { act = 1; sign = 1; gap = q[d] - lo; }
-        else if (hi < 1e30f && q[d] + h * qd[d] > hi) { act = 1; sign = -1; gap = hi - q[d]; }
-        if (!act) continue;
-        R dv0[6] = {0, 0, 0, 0, 0, 0}, dqd[B2G_MAX_DOF];
-        for (int e = 0; e < nd; e++) dqd[e] = 0;
-        FN(orc_apply_impulse)(m, k, 0, 0, d, 1, dv0, dqd);
-        lim[nlim].dof = d; lim[nlim].sign = sign; lim[nlim].gap = gap; lim[nlim].A = dqd[d]; lim[nlim].lam = 0;
-        nlim++;
-    }
-
     /* ---- projected Gauss-Seidel: position iterations (with bias), integrate, velocity iterations ---- */
     int npos = sp->num_position_iterations, nvel = sp->num_velocity_iterations;
     R maxdep = (R)sp->max_depenetration_velocity;
@@ -469,8 +463,12 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
         }
         if (it == npos + nvel) break;
         int with_bias = it < npos;
+        /* slot s of every chain is updated from the SAME velocities (Jacobi across chains: they couple only through
+         * the root), then all impulses are applied; slots of one chain follow each other (Gauss-Seidel within a chain) */
         for (int s = 0; s < B2G_MAX_CONTACTS_PER_CHAIN; s++) {
+            R Fall[B2G_MAX_CHAINS][6];
             for (int c = 0; c < m->n_chains; c++) {
+                for (int a = 0; a < 6; a++) Fall[c][a] = 0;
                 if (s >= ncon[c]) continue;
                 FN(orc_contact)* cc = &con[c][s];
                 R lv[6], pv[3];
@@ -494,22 +492,14 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
                 if (mag > lim_t) { R sc = (mag > 0) ? lim_t / mag : 0; l1 *= sc; l2 *= sc; }
                 dl[1] = l1 - cc->lam[1]; dl[2] = l2 - cc->lam[2];
                 cc->lam[0] = ln; cc->lam[1] = l1; cc->lam[2] = l2;
-                R dir[3], F[6];
+                R dir[3];
                 for (int a = 0; a < 3; a++) dir[a] = cc->n[a] * dl[0] + cc->t1[a] * dl[1] + cc->t2[a] * dl[2];
-                FN(orc_contact_wrench)(cc, dir, F);
-                FN(orc_apply_impulse)(m, k, cc->link, F, -1, 0, v0, qd);
+                FN(orc_contact_wrench)(cc, dir, Fall[c]);
             }
-        }
-        for (int i = 0; i < nlim; i++) {
-            FN(orc_limit)* L = &lim[i];
-            R vrel = L->sign * qd[L->dof];
-            R tgt = -L->gap / h;
-            if (!with_bias && tgt > 0) tgt = 0;
-            R ln = L->lam - (vrel - tgt) / L->A;
-            if (ln < 0) ln = 0;
-            R dl = ln - L->lam;
-            L->lam = ln;
-            FN(orc_apply_impulse)(m, k, 0, 0, L->dof, L->sign * dl, v0, qd);
+            for (int c = 0; c < m->n_chains; c++) {
+                if (s >= ncon[c]) continue;
+                FN(orc_apply_impulse)(m, k, con[c][s].link, Fall[c], -1, 0, v0, qd);
+            }
         }
     }
     if (npos + nvel == 0) {

@@ -26,8 +26,11 @@ struct Variant { int lanes, nl; bool fixed; };
 Variant pick(const b2g_model& m) {
     int maxlen = 0;
     for (int c = 0; c < m.n_chains; c++) maxlen = m.chain_len[c] > maxlen ? m.chain_len[c] : maxlen;
-    if (m.fixed_base && m.n_chains <= 1 && maxlen <= 2) return {1, 2, true};
-    if (!m.fixed_base && m.n_chains <= 4 && maxlen <= 3) return {4, 3, false};
+    int minlen = 1 << 20;
+    for (int c = 0; c < m.n_chains; c++) minlen = m.chain_len[c] < minlen ? m.chain_len[c] : minlen;
+    // the specialised variants assume FULL chains (every lane has exactly NL links)
+    if (m.fixed_base && m.n_chains == 1 && maxlen == 2) return {1, 2, true};
+    if (!m.fixed_base && m.n_chains == 4 && maxlen == 3 && minlen == 3) return {4, 3, false};
     return {8, 6, m.fixed_base != 0};
 }
 

@@ -42,7 +42,8 @@ def default_pose(art):
 def flat_params(dt=0.02, substeps=2, npos=4, nvel=1, ground=True):
     sp = _abi.SimParams(dt=dt, substeps=substeps, num_position_iterations=npos, num_velocity_iterations=nvel, contact_offset=0.02,
                         rest_offset=0.0, bounce_threshold_velocity=0.2, max_depenetration_velocity=100.0, plane_static_friction=1.0,
-                        plane_dynamic_friction=1.0, plane_restitution=0.0, has_ground=1 if ground else 0)
+                        plane_dynamic_friction=1.0, plane_restitution=0.0, has_ground=1 if ground else 0, joint_limit_stiffness=2000.0,
+                        joint_limit_damping=20.0)
     sp.gravity[2] = -9.81
     return sp
 
@@ -314,7 +315,7 @@ def check_fused_step(make_backend, robot="anymal", n=16, steps=25, seed=3):
 def cartpole_params():
     sp = _abi.SimParams(dt=0.0166, substeps=2, num_position_iterations=4, num_velocity_iterations=0, contact_offset=0.02, rest_offset=0.001,
                         bounce_threshold_velocity=0.2, max_depenetration_velocity=100.0, plane_static_friction=1.0, plane_dynamic_friction=1.0,
-                        plane_restitution=0.0, has_ground=1)
+                        plane_restitution=0.0, has_ground=1, joint_limit_stiffness=2000.0, joint_limit_damping=20.0)
     sp.gravity[2] = -9.81
     return sp
 

@@ -77,7 +77,7 @@ def test_kinetic_energy_against_finite_difference_kinematics(robot):
 def test_free_flight_conservation():
     art = load_robot("anymal")
     m = _abi.pack_model(art)
-    sp = _abi.SimParams(dt=0.0005, substeps=1, num_position_iterations=0, num_velocity_iterations=0)
+    sp = _abi.SimParams(dt=0.0005, substeps=1, num_position_iterations=0, num_velocity_iterations=0, joint_limit_stiffness=2000.0, joint_limit_damping=20.0)
     sp.gravity[2] = -9.81
     props = _abi.default_dof_props(art)
     for d in range(art.num_dofs):
