@@ -18,6 +18,7 @@ struct DevDof {
     float armature;
     float inertia[6];   // xx, xy, xz, yy, yz, zz about the com, link axes
     int cp_start, cp_count;   // contact candidates riding on this link
+    float cp_c[3], cp_h[3];   // bounding box (centre, half extents incl. radii) of those candidates, link frame
     float kp, kd, effort, vel_limit;
     float lower, upper;
     int drive_mode;
@@ -33,6 +34,7 @@ struct DevModel {
     float root_mass;
     float root_com[3];
     float root_inertia[6];
+    float root_cp_c[3], root_cp_h[3];    // bounding box of the root-link contact candidates
     DevDof dof[B2G_MAX_DOF];
     float cp[B2G_MAX_CPTS][4];   // link-frame position, radius
     int cp_body[B2G_MAX_CPTS];

@@ -373,17 +373,27 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
             sc.at(s, CF_LN) = 0.0f; sc.at(s, CF_L1) = 0.0f; sc.at(s, CF_L2) = 0.0f;
         }
     };
+    // plane ground: a link whose candidate bounding box clears the contact offset cannot touch (skips most loops)
+    auto may_touch = [&](const M3& R, V3 p, const float* c, const float* hx) -> bool {
+        if (HF) return true;
+        const float zc = st.rp.z + p.z + R.m[6] * c[0] + R.m[7] * c[1] + R.m[8] * c[2];
+        const float ext = fabsf(R.m[6]) * hx[0] + fabsf(R.m[7]) * hx[1] + fabsf(R.m[8]) * hx[2];
+        return zc - ext < P.contact_offset;
+    };
     if (ground) {
 #pragma unroll
         for (int j = NL - 1; j >= 0; j--) {
             if (j < len) {
-                const int c0 = M->dof[d0 + j].cp_start, cn = M->dof[d0 + j].cp_count;
-                for (int i = c0; i < c0 + cn; i++) test_candidate(i, Rl[j], pl[j], j);
+                const DevDof& D = M->dof[d0 + j];
+                const int c0 = D.cp_start, cn = D.cp_count;
+                if (cn > 0 && may_touch(Rl[j], pl[j], D.cp_c, D.cp_h))
+                    for (int i = c0; i < c0 + cn; i++) test_candidate(i, Rl[j], pl[j], j);
             }
         }
         if (!FIXED) {
             const int c0 = M->root_cp_start[lane], cn = M->root_cp_count[lane];
-            for (int i = c0; i < c0 + cn; i++) test_candidate(i, R0, V3{0, 0, 0}, -1);
+            if (cn > 0 && may_touch(R0, V3{0, 0, 0}, M->root_cp_c, M->root_cp_h))
+                for (int i = c0; i < c0 + cn; i++) test_candidate(i, R0, V3{0, 0, 0}, -1);
         }
     }
 

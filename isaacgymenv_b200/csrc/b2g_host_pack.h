@@ -74,6 +74,22 @@ inline int pack_dev_model(const b2g_model& m, const b2g_dof_props& p, DevModel& 
             d.root_cp_count[c]++;
         }
     }
+    // bounding boxes of each link's candidates (conservative early-out in the kernels)
+    for (int l = 0; l <= m.n_dof; l++) {
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        int cnt = 0;
+        for (int i = 0; i < m.n_cpts; i++) {
+            if (m.cp_link[i] != l) continue;
+            cnt++;
+            for (int a = 0; a < 3; a++) {
+                lo[a] = fminf(lo[a], m.cp_pos[i][a] - m.cp_radius[i]);
+                hi[a] = fmaxf(hi[a], m.cp_pos[i][a] + m.cp_radius[i]);
+            }
+        }
+        float* c = l == 0 ? d.root_cp_c : d.dof[l - 1].cp_c;
+        float* h = l == 0 ? d.root_cp_h : d.dof[l - 1].cp_h;
+        for (int a = 0; a < 3; a++) { c[a] = cnt ? 0.5f * (lo[a] + hi[a]) : 0.0f; h[a] = cnt ? 0.5f * (hi[a] - lo[a]) : 0.0f; }
+    }
     for (int b = 0; b < m.n_bodies; b++) {
         d.body_link[b] = m.body_link[b];
         for (int a = 0; a < 3; a++) d.body_pos[b][a] = m.body_pos[b][a];

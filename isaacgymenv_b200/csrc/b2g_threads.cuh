@@ -217,6 +217,11 @@ B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int 
     const b2g_anymal_cfg& C = T.cfg;
     LaneState<NL> st;
     load_state<NL>(A, env, len, d0, st);
+    // post-physics inputs are fetched now so their (possibly DRAM) latency hides behind the physics
+    const long long progress_in = T.progress[env];
+    const long long reset_in = T.reset[env];
+    const float cmd_in[3] = {T.commands[(size_t)env * 3], T.commands[(size_t)env * 3 + 1], T.commands[(size_t)env * 3 + 2]};
+    const int rc_in = T.reset_count[env];
     float act[NL];
 #pragma unroll
     for (int j = 0; j < NL; j++) {
@@ -244,12 +249,12 @@ B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int 
     }
 
     // ---- post_physics_step ----
-    long long progress = T.progress[env] + 1;
-    float cmd[3] = {T.commands[(size_t)env * 3], T.commands[(size_t)env * 3 + 1], T.commands[(size_t)env * 3 + 2]};
-    const bool do_reset = T.reset[env] != 0;
+    long long progress = progress_in + 1;
+    float cmd[3] = {cmd_in[0], cmd_in[1], cmd_in[2]};
+    const bool do_reset = reset_in != 0;
     int rc = 0;
     if (do_reset) {
-        rc = T.reset_count[env];
+        rc = rc_in;
         anymal_reset_lane<NL>(T, env, lane, len, d0, nd, rc, st, cmd);
         progress = 0;
     }
