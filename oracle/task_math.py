@@ -220,3 +220,163 @@ def anymal_post_physics(state, cfg, actions, draws):
     timeout = ((state["progress"] >= cfg["max_episode_length"] - 1) & (state["reset"] != 0)).astype(np.int64)
     obs_clamped = np.clip(obs, -dt.type(cfg["clip_obs"]), dt.type(cfg["clip_obs"]))
     return obs, obs_clamped, rew, timeout
+
+
+# ----------------------------------------------------------------------------------------------
+# tasks/anymal_terrain.py / tasks/Hound_terrain.py: post_physics_step of the rough-terrain tasks
+# ----------------------------------------------------------------------------------------------
+EPISODE_KEYS = ("lin_vel_xy", "lin_vel_z", "ang_vel_z", "ang_vel_xy", "orient", "torques", "joint_acc", "base_height", "air_time", "collision",
+                "stumble", "action_rate", "hip")
+REW_ORDER = ("termination", "lin_vel_xy", "lin_vel_z", "ang_vel_z", "ang_vel_xy", "orient", "torque", "joint_acc", "base_height", "air_time",
+             "collision", "stumble", "action_rate", "hip")
+HEIGHT_X = 0.1 * np.array([-8, -7, -6, -5, -4, -3, -2, 2, 3, 4, 5, 6, 7, 8], dtype=np.float32)
+HEIGHT_Y = 0.1 * np.array([-5, -4, -3, -2, -1, 1, 2, 3, 4, 5], dtype=np.float32)
+
+
+def height_points(n):
+    """tasks/anymal_terrain.py:503-513: 14 x 10 grid, x-major (index = ix * 10 + iy)."""
+    gx, gy = np.meshgrid(HEIGHT_X, HEIGHT_Y, indexing="ij")
+    pts = np.zeros((n, gx.size, 3), dtype=np.float32)
+    pts[:, :, 0] = gx.reshape(-1)
+    pts[:, :, 1] = gy.reshape(-1)
+    return pts
+
+
+def get_heights(root, height_samples, border_size, hscale, vscale):
+    """tasks/anymal_terrain.py:515-538 (trimesh branch); ``height_samples`` None = plane -> zeros."""
+    n = root.shape[0]
+    pts = height_points(n)
+    if height_samples is None:
+        return np.zeros((n, pts.shape[1]), dtype=np.float32)
+    quat = np.repeat(root[:, 3:7], pts.shape[1], axis=0)
+    p = quat_apply_yaw(quat, pts.reshape(-1, 3)).reshape(n, -1, 3) + root[:, None, :3]
+    p = p + np.float32(border_size)
+    p = (p / np.float32(hscale)).astype(np.int64)       # .long(): truncation toward zero
+    px = np.clip(p[:, :, 0].reshape(-1), 0, height_samples.shape[0] - 2)
+    py = np.clip(p[:, :, 1].reshape(-1), 0, height_samples.shape[1] - 2)
+    h = np.minimum(height_samples[px, py], height_samples[px + 1, py + 1])
+    return (h.reshape(n, -1) * np.float32(vscale)).astype(np.float32)
+
+
+def terrain_post_physics(st, cfg, draws):
+    """post_physics_step of AnymalTerrain (tasks/anymal_terrain.py:453-485) and HoundTerrain (Hound_terrain.py, same
+    structure; termination :304-311, base-height target :347), followed by the VecTask.step tail (vec_task.py:394).
+
+    ``st`` (updated in place): root (N,13), dof_pos, dof_vel, contact (N,nb,3), torques, commands (N,4), actions, last_actions,
+    last_dof_vel, feet_air_time (N,4), progress int64, timeout_prev bool, episode_sums (13,N), and for custom origins
+    terrain_levels, terrain_types (int64), env_origins (N,3).
+    ``cfg``: rew_scales (14, REW_ORDER, already x dt), scales, knee/feet/base indices, allow_knee, hound (bool), base_height_target,
+    noise_scale_vec (188) or None, dt, max_len, push (bool: this step pushes), default_dof_pos, init_root, cmd ranges, custom_origins,
+    curriculum, terrain (height_samples, border_size, hscale, vscale, env_length, env_rows, terrain_origins), max_episode_length_s.
+    ``draws``: reset (N,29), noise (N,188), push (N,2) uniforms in [0,1).
+    Returns obs (N,188), rew, reset int64, timeout int64, measured heights, extras (14: 13 episode means + terrain level) or None.
+    """
+    f = np.float32
+    n = st["root"].shape[0]
+    rs = dict(zip(REW_ORDER, cfg["rew_scales"].astype(f)))
+    st["progress"] += 1
+    if cfg["push"]:      # :437-439  root lin vel x/y <- U(-1, 1) for all envs
+        st["root"][:, 7:9] = torch_rand_float(f(-1.0), f(1.0), draws["push"].astype(f))
+    root = st["root"]
+    quat = root[:, 3:7].copy()
+    base_lin = quat_rotate_inverse(quat, root[:, 7:10])
+    base_ang = quat_rotate_inverse(quat, root[:, 10:13])
+    grav = np.tile(np.array([[0, 0, -1]], f), (n, 1))
+    pg = quat_rotate_inverse(quat, grav)
+    fwd = quat_apply(quat, np.tile(np.array([[1, 0, 0]], f), (n, 1)))
+    heading = np.arctan2(fwd[:, 1], fwd[:, 0]).astype(f)
+    st["commands"][:, 2] = np.clip(f(0.5) * wrap_to_pi(st["commands"][:, 3] - heading), -1.0, 1.0)      # :469-471
+    cf = st["contact"]
+    # check_termination
+    if cfg.get("hound", False):       # Hound_terrain.py:304-311
+        reset = np.linalg.norm(cf[:, cfg["base_body"], :], axis=1) > 1.0
+        reset = reset | np.any(np.linalg.norm(cf[:, cfg["knee"], :], axis=2) > 1.0, axis=1)
+        reset = reset | np.any(np.linalg.norm(cf[:, cfg["base_indices"], :], axis=2) > 1.0, axis=1)
+        reset = reset | (st["progress"] >= cfg["max_len"] - 1)
+    else:                             # anymal_terrain.py:294-300
+        reset = np.linalg.norm(cf[:, cfg["base_body"], :], axis=1) > 1.0
+        if not cfg["allow_knee"]:
+            reset = reset | np.any(np.linalg.norm(cf[:, cfg["knee"], :], axis=2) > 1.0, axis=1)
+        reset = np.where(st["progress"] >= cfg["max_len"] - 1, True, reset)
+    # compute_reward :315-382
+    cmd = st["commands"]
+    lin_err = np.sum(np.square(cmd[:, :2] - base_lin[:, :2]), axis=1)
+    ang_err = np.square(cmd[:, 2] - base_ang[:, 2])
+    r_lin_xy = np.exp(-lin_err / f(0.25)) * rs["lin_vel_xy"]
+    r_ang_z = np.exp(-ang_err / f(0.25)) * rs["ang_vel_z"]
+    r_lin_z = np.square(base_lin[:, 2]) * rs["lin_vel_z"]
+    r_ang_xy = np.sum(np.square(base_ang[:, :2]), axis=1) * rs["ang_vel_xy"]
+    r_orient = np.sum(np.square(pg[:, :2]), axis=1) * rs["orient"]
+    r_height = np.square(root[:, 2] - f(cfg["base_height_target"])) * rs["base_height"]
+    r_torque = np.sum(np.square(st["torques"]), axis=1) * rs["torque"]
+    r_jacc = np.sum(np.square(st["last_dof_vel"] - st["dof_vel"]), axis=1) * rs["joint_acc"]
+    knee_contact = np.linalg.norm(cf[:, cfg["knee"], :], axis=2) > 1.0
+    r_coll = np.sum(knee_contact, axis=1).astype(f) * rs["collision"]
+    stumble = (np.linalg.norm(cf[:, cfg["feet"], :2], axis=2) > 5.0) & (np.abs(cf[:, cfg["feet"], 2]) < 1.0)
+    r_stumble = np.sum(stumble, axis=1).astype(f) * rs["stumble"]
+    r_arate = np.sum(np.square(st["last_actions"] - st["actions"]), axis=1) * rs["action_rate"]
+    contact = cf[:, cfg["feet"], 2] > 1.0
+    first = (st["feet_air_time"] > 0.0) & contact
+    st["feet_air_time"] += f(cfg["dt"])
+    r_air = np.sum((st["feet_air_time"] - f(0.5)) * first, axis=1).astype(f) * rs["air_time"]
+    r_air = r_air * (np.linalg.norm(cmd[:, :2], axis=1) > 0.1)
+    st["feet_air_time"] *= ~contact
+    hips = [0, 3, 6, 9]
+    r_hip = np.sum(np.abs(st["dof_pos"][:, hips] - cfg["default_dof_pos"][hips][None]), axis=1) * rs["hip"]
+    rew = r_lin_xy + r_ang_z + r_lin_z + r_ang_xy + r_orient + r_height + r_torque + r_jacc + r_coll + r_arate + r_air + r_hip + r_stumble
+    rew = np.clip(rew, 0.0, None).astype(f)
+    rew = rew + rs["termination"] * reset * ~st["timeout_prev"]
+    terms = dict(lin_vel_xy=r_lin_xy, ang_vel_z=r_ang_z, lin_vel_z=r_lin_z, ang_vel_xy=r_ang_xy, orient=r_orient, torques=r_torque,
+                 joint_acc=r_jacc, collision=r_coll, stumble=r_stumble, action_rate=r_arate, air_time=r_air, base_height=r_height, hip=r_hip)
+    for i, k in enumerate(EPISODE_KEYS):
+        st["episode_sums"][i] += terms[k].astype(f)
+    # reset_idx :384-425
+    ids = np.nonzero(reset)[0]
+    extras = None
+    if len(ids) > 0:
+        u = draws["reset"][ids].astype(f)
+        d0 = cfg["default_dof_pos"].astype(f)
+        st["dof_pos"][ids] = d0[None] * torch_rand_float(f(0.5), f(1.5), u[:, 0:12])
+        st["dof_vel"][ids] = torch_rand_float(f(-0.1), f(0.1), u[:, 12:24])
+        col = 24
+        if cfg["custom_origins"]:
+            t = cfg["terrain"]
+            if cfg["curriculum"]:            # update_terrain_level :427-435 (norm WITHOUT dim: one scalar for all resetting envs, quirk Q10)
+                dist = np.linalg.norm(st["root"][ids, :2] - st["env_origins"][ids, :2], axis=1)
+                thr = f(np.sqrt(np.sum(np.square(st["commands"][ids, :2]).astype(f)))) * f(cfg["max_episode_length_s"]) * f(0.25)
+                st["terrain_levels"][ids] -= 1 * (dist < thr)
+                st["terrain_levels"][ids] += 1 * (dist > t["env_length"] / 2)
+                st["terrain_levels"][ids] = np.clip(st["terrain_levels"][ids], 0, None) % t["env_rows"]
+                st["env_origins"][ids] = t["terrain_origins"][st["terrain_levels"][ids], st["terrain_types"][ids]]
+            st["root"][ids] = cfg["init_root"].astype(f)[None]
+            st["root"][ids, :3] += st["env_origins"][ids]
+            st["root"][ids, :2] += torch_rand_float(f(-0.5), f(0.5), u[:, 24:26])
+            col = 26
+        else:
+            st["root"][ids] = cfg["init_root"].astype(f)[None]
+        st["commands"][ids, 0] = torch_rand_float(f(cfg["cmd_x"][0]), f(cfg["cmd_x"][1]), u[:, col])
+        st["commands"][ids, 1] = torch_rand_float(f(cfg["cmd_y"][0]), f(cfg["cmd_y"][1]), u[:, col + 1])
+        st["commands"][ids, 3] = torch_rand_float(f(cfg["cmd_yaw"][0]), f(cfg["cmd_yaw"][1]), u[:, col + 2])
+        st["commands"][ids] *= (np.linalg.norm(st["commands"][ids, :2], axis=1) > 0.25)[:, None]
+        st["last_actions"][ids] = 0.0
+        st["last_dof_vel"][ids] = 0.0
+        st["feet_air_time"][ids] = 0.0
+        st["progress"][ids] = 0
+        extras = np.zeros(14, f)
+        for i in range(13):
+            extras[i] = np.mean(st["episode_sums"][i][ids]) / f(cfg["max_episode_length_s"])
+            st["episode_sums"][i][ids] = 0.0
+        extras[13] = np.mean(st["terrain_levels"].astype(f)) if "terrain_levels" in st else 0.0
+    # compute_observations :302-313 (base velocities / projected gravity are the pre-reset values; heights, DOFs, commands post-reset)
+    t = cfg.get("terrain")
+    measured = get_heights(st["root"], t["height_samples"] if t else None, t["border_size"] if t else 0, t["hscale"] if t else 1, t["vscale"] if t else 1)
+    heights = np.clip(st["root"][:, 2:3] - f(0.5) - measured, -1, 1.0) * f(cfg["height_meas_scale"])
+    obs = np.concatenate([base_lin * f(cfg["lin_vel_scale"]), base_ang * f(cfg["ang_vel_scale"]), pg,
+                          st["commands"][:, :3] * np.array([cfg["lin_vel_scale"], cfg["lin_vel_scale"], cfg["ang_vel_scale"]], f),
+                          st["dof_pos"] * f(cfg["dof_pos_scale"]), st["dof_vel"] * f(cfg["dof_vel_scale"]), heights, st["actions"]], axis=-1).astype(f)
+    if cfg.get("noise_scale_vec") is not None:
+        obs = obs + (f(2) * draws["noise"].astype(f) - f(1)) * cfg["noise_scale_vec"].astype(f)[None]
+    st["last_actions"][:] = st["actions"]
+    st["last_dof_vel"][:] = st["dof_vel"]
+    timeout = ((st["progress"] >= cfg["max_len"] - 1) & reset).astype(np.int64)
+    return obs.astype(f), rew.astype(f), reset.astype(np.int64), timeout, measured, extras

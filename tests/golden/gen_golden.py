@@ -103,3 +103,193 @@ if __name__ == "__main__":
     gen_anymal(ref_loader.load("tasks.hound"), "hound", 17, [2, 6, 10, 14], 0, os.path.join(HERE, "hound_flat.npz"))
     gen_cartpole(os.path.join(HERE, "cartpole.npz"))
     gen_utils(os.path.join(HERE, "jit_utils.npz"))
+    if "--no-terrain" not in sys.argv:
+        globals()["_run_terrain_after"] = True
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# terrain tasks: the reference keeps this math in eager methods of the task class (tasks/anymal_terrain.py:294-485,
+# Hound_terrain.py same lines).  They are executed here unmodified, bound to an attribute bag that stands in for the
+# task object; torch's RNG entry points are replaced by tables so that the fixtures are RNG-free and the kernels can
+# be fed the very same draws.
+# ------------------------------------------------------------------------------------------------------------------
+import types  # noqa: E402
+
+
+class _NullGym:
+    def __getattr__(self, name):
+        return lambda *a, **k: True
+
+
+def _terrain_bag(mod, cls_name, n, nb, terrain_kind, seed_phase, knee, feet, base_indices=None):
+    ref_cls = getattr(mod, cls_name)
+
+    class Bag:
+        def __getattr__(self, name):
+            f = getattr(ref_cls, name)
+            return types.MethodType(f, self)
+
+        def reset_idx(self, env_ids):
+            self._cur_ids = env_ids
+            self._draw_col = 0
+            ref_cls.reset_idx(self, env_ids)
+
+        def push_robots(self):
+            self._cur_ids = torch.arange(self.num_envs)
+            self._draw_col = None
+            ref_cls.push_robots(self)
+
+    b = Bag()
+    dt = 4 * 0.005
+    b.num_envs, b.num_dof, b.num_actions, b.num_bodies, b.device = n, 12, 12, nb, "cpu"
+    b.gym, b.sim, b.viewer, b.enable_viewer_sync, b.debug_viz = _NullGym(), None, None, False, False
+    b.dt, b.max_episode_length_s = dt, 20
+    b.max_episode_length = int(20 / dt + 0.5)
+    b.push_interval = int(15 / dt + 0.5)
+    b.allow_knee_contacts = False if cls_name == "AnymalTerrain" else True
+    b.lin_vel_scale, b.ang_vel_scale, b.dof_pos_scale, b.dof_vel_scale, b.height_meas_scale, b.action_scale = 2.0, 0.25, 1.0, 0.05, 5.0, 0.5
+    raw = dict(termination=-1.0, lin_vel_xy=1.0, lin_vel_z=-4.0, ang_vel_z=0.5, ang_vel_xy=-0.05, orient=-0.2, torque=-0.00002, joint_acc=-0.0005,
+               base_height=-0.5, air_time=1.0, collision=-0.25, stumble=-0.1, action_rate=-0.01, hip=-0.05)
+    b.rew_scales = {k: v * dt for k, v in raw.items()}
+    b.command_x_range, b.command_y_range, b.command_yaw_range = [-1.0, 1.0], [-1.0, 1.0], [-3.14, 3.14]
+    b.base_init_state = torch.tensor([0, 0, 0.62, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0], dtype=torch.float32)
+    b.cfg = {"env": {"terrain": {"terrainType": terrain_kind}}}
+    b.custom_origins = terrain_kind == "trimesh"
+    b.curriculum, b.init_done = True, True
+    b.add_noise = True
+    b.knee_indices, b.feet_indices, b.base_index = torch.tensor(knee), torch.tensor(feet), 0
+    if base_indices is not None:
+        b.base_indices = torch.tensor(base_indices)
+    b.extras = {}
+    b.terrain_levels = torch.zeros(n, dtype=torch.int64)     # created for every terrain type (anymal_terrain.py:258)
+    b.terrain_types = torch.zeros(n, dtype=torch.int64)
+    b.env_origins = torch.zeros(n, 3)
+    ph = seed_phase
+    b.root_states = make_root(n, 0.37 + ph, 0.1, z0=0.55)
+    b.root_states[:, 7:13] *= 0.3
+    b.dof_state = torch.zeros(n * 12, 2)
+    b.dof_pos = sinfill((n, 12), 0.29, 0.3 + ph, 0.8)
+    b.dof_vel = sinfill((n, 12), 0.53, 0.9 + ph, 2.0)
+    contact = sinfill((n, nb, 3), 0.67, 0.7 + ph)
+    # most envs: small forces on base/knees (below the 1 N thresholds); every 8th env exceeds them
+    mag = torch.tensor([0.1, 0.2, 0.3, 0.55, 0.4, 3.0, 0.45, 0.05])[torch.arange(n) % 8]
+    b.contact_forces = contact * mag[:, None, None]
+    # feet: realistic loads so that the air-time / stumble logic sees contacts, lift-offs and side hits
+    ft = torch.tensor(feet)
+    b.contact_forces[:, ft, 2] = sinfill((n, len(feet)), 0.77, 0.2 + ph, 60.0).clamp(min=0.0)
+    b.contact_forces[:, ft, :2] = sinfill((n, len(feet), 2), 0.41, 0.5 + ph, 7.0)
+    b.torques = sinfill((n, 12), 0.43, 0.6 + ph, 12.0)
+    b.commands = sinfill((n, 4), 0.91, 0.2 + ph) * torch.tensor([1.0, 1.0, 1.0, 3.0])
+    b.commands[::5, :2] *= 0.05
+    b.commands_scale = torch.tensor([2.0, 2.0, 0.25])
+    b.actions = sinfill((n, 12), 0.77, 1.1 + ph)
+    b.last_actions = b.actions + sinfill((n, 12), 0.71, 0.4 + ph, 0.3)
+    b.last_dof_vel = b.dof_vel + sinfill((n, 12), 0.59, 0.8 + ph, 0.8)
+    b.feet_air_time = (sinfill((n, 4), 0.83, 0.3 + ph) * 0.4).clamp(min=0.0)
+    b.default_dof_pos = sinfill((1, 12), 1.3, 0.5, 0.6).repeat(n, 1)
+    b.gravity_vec = torch.tensor([[0.0, 0.0, -1.0]]).repeat(n, 1)
+    b.forward_vec = torch.tensor([[1.0, 0.0, 0.0]]).repeat(n, 1)
+    b.progress_buf = torch.roll(torch.tensor([0, 10, 997, 998, 999, 1000, 1, 300], dtype=torch.int64)[torch.arange(n) % 8], 3)
+    b.randomize_buf = torch.zeros(n, dtype=torch.int64)
+    b.timeout_buf = (torch.arange(n) % 3 == 0)
+    b.reset_buf = torch.zeros(n, dtype=torch.int64)
+    b.obs_buf = torch.zeros(n, 188)
+    b.rew_buf = torch.zeros(n)
+    keys = ["lin_vel_xy", "lin_vel_z", "ang_vel_z", "ang_vel_xy", "orient", "torques", "joint_acc", "base_height", "air_time", "collision",
+            "stumble", "action_rate", "hip"]
+    b.episode_sums = {k: sinfill((n,), 0.31 + 0.01 * i, 0.2 + ph) for i, k in enumerate(keys)}
+    b.height_points = ref_cls.init_height_points(b)
+    b.measured_heights = None
+    b.noise_scale_vec = torch.zeros(188)
+    nl = 1.0
+    b.noise_scale_vec[:3] = 0.1 * nl * 2.0
+    b.noise_scale_vec[3:6] = 0.2 * nl * 0.25
+    b.noise_scale_vec[6:9] = 0.05 * nl
+    b.noise_scale_vec[12:24] = 0.01 * nl * 1.0
+    b.noise_scale_vec[24:36] = 1.5 * nl * 0.05
+    b.noise_scale_vec[36:176] = 0.06 * nl * 5.0
+    return b, keys
+
+
+def gen_terrain(cls_name, modname, out, nb, knee, feet, terrain_kind, push, base_indices=None):
+    mod = ref_loader.load(modname)
+    n = 64
+    b, keys = _terrain_bag(mod, cls_name, n, nb, terrain_kind, 0.0 if terrain_kind == "plane" else 0.37, knee, feet, base_indices)
+    if terrain_kind == "trimesh":
+        sys.path.insert(0, os.path.join(HERE, "..", ".."))
+        from isaacgymenv_b200.terrain import Terrain
+        tcfg = dict(terrainType="trimesh", curriculum=True, mapLength=8.0, mapWidth=8.0, numLevels=3, numTerrains=5,
+                    terrainProportions=[0.1, 0.1, 0.35, 0.25, 0.2], slopeTreshold=0.5)
+        t = Terrain(tcfg, n, seed=7)
+        b.terrain = types.SimpleNamespace(border_size=t.border_size, horizontal_scale=t.horizontal_scale, vertical_scale=t.vertical_scale,
+                                          env_length=t.env_length, env_rows=t.env_rows)
+        b.height_samples = torch.tensor(t.heightsamples).view(t.tot_rows, t.tot_cols)
+        b.terrain_origins = torch.from_numpy(t.env_origins).to(torch.float)
+        b.terrain_levels = torch.arange(n) % 3
+        b.terrain_types = (torch.arange(n) * 7) % 5
+        b.env_origins = b.terrain_origins[b.terrain_levels, b.terrain_types].clone()
+        b.root_states[:, :2] = b.env_origins[:, :2] + sinfill((n, 2), 0.47, 0.6, 5.0)
+        b.root_states[:, 2] += b.env_origins[:, 2]
+    b.common_step_counter = (b.push_interval - 1) if push else 5
+    csc_before = b.common_step_counter
+    # RNG tables
+    reset_draws = sinfill((n, 29), 0.173, 0.05).abs() * 0.999
+    noise_draws = sinfill((n, 188), 0.0917, 0.33).abs() * 0.999
+    push_draws = sinfill((n, 2), 0.61, 0.21).abs() * 0.999
+
+    def fake_rand_float(lower, upper, shape, device):
+        ids = b._cur_ids
+        if b._draw_col is None:
+            u = push_draws[ids]
+        else:
+            c0 = b._draw_col
+            u = reset_draws[ids][:, c0:c0 + shape[1]]
+            b._draw_col += shape[1]
+        assert tuple(u.shape) == tuple(shape), (u.shape, shape)
+        return (upper - lower) * u + lower
+
+    mod.torch_rand_float = fake_rand_float
+    real_rand_like = torch.rand_like
+    torch.rand_like = lambda t: noise_draws.clone()
+    inputs = dict(root=b.root_states.clone(), dof_pos=b.dof_pos.clone(), dof_vel=b.dof_vel.clone(), contact=b.contact_forces.clone(),
+                  torques=b.torques.clone(), commands=b.commands.clone(), actions=b.actions.clone(), last_actions=b.last_actions.clone(),
+                  last_dof_vel=b.last_dof_vel.clone(), feet_air_time=b.feet_air_time.clone(), progress=b.progress_buf.clone(),
+                  timeout_prev=b.timeout_buf.clone(), default=b.default_dof_pos.clone(),
+                  episode_sums=torch.stack([b.episode_sums[k] for k in keys]).clone())
+    if terrain_kind == "trimesh":
+        inputs.update(height_samples=b.height_samples.clone(), terrain_origins=b.terrain_origins.clone(), terrain_levels=b.terrain_levels.clone(),
+                      terrain_types=b.terrain_types.clone(), env_origins=b.env_origins.clone())
+    try:
+        getattr(mod, cls_name).post_physics_step(b)
+    finally:
+        torch.rand_like = real_rand_like
+    # VecTask.step tail (vec_task.py:394)
+    timeout = (b.progress_buf >= b.max_episode_length - 1) & (b.reset_buf != 0)
+    outs = dict(o_root=b.root_states, o_dof_pos=b.dof_pos, o_dof_vel=b.dof_vel, o_commands=b.commands, o_obs=b.obs_buf, o_rew=b.rew_buf,
+                o_reset=b.reset_buf.to(torch.int64), o_progress=b.progress_buf, o_timeout=timeout.to(torch.int64), o_last_actions=b.last_actions,
+                o_last_dof_vel=b.last_dof_vel, o_feet_air_time=b.feet_air_time, o_episode_sums=torch.stack([b.episode_sums[k] for k in keys]),
+                o_measured_heights=b.measured_heights,
+                o_extras=torch.tensor([float(b.extras["episode"]["rew_" + k]) for k in keys] + [float(b.extras["episode"]["terrain_level"])])
+                if "episode" in b.extras else torch.zeros(14))
+    if terrain_kind == "trimesh":
+        outs.update(o_terrain_levels=b.terrain_levels, o_env_origins=b.env_origins)
+    meta = dict(knee=np.array(knee), feet=np.array(feet), base_indices=np.array(base_indices if base_indices is not None else []),
+                rew_scales=np.array([b.rew_scales[k] for k in ["termination", "lin_vel_xy", "lin_vel_z", "ang_vel_z", "ang_vel_xy", "orient", "torque",
+                                                                 "joint_acc", "base_height", "air_time", "collision", "stumble", "action_rate", "hip"]], dtype=np.float32),
+                noise_scale_vec=b.noise_scale_vec.numpy(), reset_draws=reset_draws.numpy(), noise_draws=noise_draws.numpy(), push_draws=push_draws.numpy(),
+                common_step_counter=np.array(csc_before), push_interval=np.array(b.push_interval), max_len=np.array(b.max_episode_length),
+                allow_knee=np.array(b.allow_knee_contacts), dt=np.float32(b.dt), custom_origins=np.array(b.custom_origins),
+                border_size=np.float32(20.0), hscale=np.float32(0.1), vscale=np.float32(0.005), env_length=np.float32(8.0), env_rows=np.array(3))
+    np.savez_compressed(out, **{k: v.numpy() for k, v in inputs.items()}, **{k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in outs.items()}, **meta)
+    print(out, "resets", int(b.reset_buf.sum()), "rew range", float(b.rew_buf.min()), float(b.rew_buf.max()))
+
+
+def gen_all_terrain():
+    gen_terrain("AnymalTerrain", "tasks.anymal_terrain", os.path.join(HERE, "anymal_terrain_plane.npz"), 13, [2, 5, 8, 11], [3, 6, 9, 12], "plane", push=True)
+    gen_terrain("AnymalTerrain", "tasks.anymal_terrain", os.path.join(HERE, "anymal_terrain_trimesh.npz"), 13, [2, 5, 8, 11], [3, 6, 9, 12], "trimesh", push=False)
+    gen_terrain("HoundTerrain", "tasks.Hound_terrain", os.path.join(HERE, "hound_terrain_plane.npz"), 17, [2, 6, 10, 14], [4, 8, 12, 16], "plane", push=False,
+                base_indices=[1, 5, 9, 13])
+
+
+if __name__ == "__main__" and ("--terrain" in sys.argv or globals().get("_run_terrain_after")):
+    gen_all_terrain()
