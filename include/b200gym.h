@@ -234,6 +234,52 @@ typedef struct b2g_cartpole_cfg {
 } b2g_cartpole_cfg;
 int b2g_task_cartpole_create(b2g_sim* sim, const b2g_cartpole_cfg* cfg);
 
+/* Rough-terrain locomotion task: AnymalTerrain / HoundTerrain (reference: tasks/anymal_terrain.py:45-538,
+ * tasks/Hound_terrain.py same lines).  One step() = `decimation` sim steps with fresh explicit PD torques
+ * (:441-451) + `extra_sim_steps` with the last torques (the generic VecTask loop, vec_task.py:379-382), then
+ * post_physics_step (:453-485): push, heading command, termination (:294-300 / Hound_terrain.py:304-311), 13-term reward
+ * (:315-382), reset_idx with terrain curriculum (:384-435), 188 observations with the 14x10 height scan (:302-313,
+ * :503-538) and uniform observation noise (:481-482).  Two launches per step (physics+reward, then reset+obs). */
+#define B2G_REW_TERMS 14
+typedef struct b2g_terrain_cfg {
+    float lin_vel_scale, ang_vel_scale, dof_pos_scale, dof_vel_scale, height_meas_scale, action_scale;
+    float kp, kd, torque_limit;
+    int32_t decimation, extra_sim_steps;
+    float dt;                        /* decimation * sim dt (anymal_terrain.py:94-95)                           */
+    float rew[B2G_REW_TERMS];        /* x dt; order: termination, lin_vel_xy, lin_vel_z, ang_vel_z, ang_vel_xy, orient,
+                                        torque, joint_acc, base_height, air_time, collision, stumble, action_rate, hip */
+    float base_height_target;        /* 0.52 (anymal_terrain.py:330) / 0.48 (Hound_terrain.py:347)              */
+    float clip_obs, clip_actions;
+    float cmd_x[2], cmd_y[2], cmd_yaw[2];
+    float default_dof_pos[B2G_MAX_DOF];
+    float init_root[13];
+    int32_t add_noise;
+    float noise_lin_vel, noise_ang_vel, noise_gravity, noise_dof_pos, noise_dof_vel, noise_height;   /* x level x obs scale */
+    int32_t base_body;
+    int32_t n_knee, knee_bodies[8];
+    int32_t n_feet, feet_bodies[8];
+    int32_t hound_termination;       /* 1: Hound_terrain.py:304-311 (knee + extra bodies always terminate)        */
+    int32_t n_term_extra, term_extra_bodies[8];
+    int32_t allow_knee_contacts;
+    int32_t hip_dofs[4];
+    int64_t max_episode_length;
+    int32_t push_interval;
+    float max_episode_length_s;
+    int32_t custom_origins, curriculum;
+    int32_t n_hx, n_hy;              /* height-scan grid (x-major): 14 x 10                                       */
+    float hx[16], hy[16];
+    int32_t hs_rows, hs_cols;        /* height_samples grid incl. border                                          */
+    float border_size, hscale, vscale, env_length;
+    int32_t env_rows, env_cols;      /* terrain levels x terrain types                                            */
+    uint64_t seed;
+} b2g_terrain_cfg;
+/* height_samples (hs_rows*hs_cols int16) and terrain_origins (env_rows*env_cols*3 f32) are host arrays (NULL for a plane) */
+int b2g_task_terrain_create(b2g_sim* sim, const b2g_terrain_cfg* cfg, const int16_t* height_samples_host, const float* terrain_origins_host);
+/* the caller's step counter (common_step_counter AFTER its increment for this step, anymal_terrain.py:460) */
+int b2g_task_terrain_set_step(b2g_sim* sim, int64_t common_step_counter);
+/* init_done / curriculum switch of update_terrain_level (anymal_terrain.py:428) */
+int b2g_task_terrain_set_init_done(b2g_sim* sim, int init_done);
+
 /* task-generic entry points (dispatch on the task created on this sim) */
 int b2g_task_step(b2g_sim* sim, const float* actions_dev, void* stream);          /* VecTask.step, one launch   */
 int b2g_task_post_only(b2g_sim* sim, const float* actions_dev, void* stream);     /* post_physics_step only     */
@@ -242,7 +288,11 @@ int b2g_task_step_host(b2g_sim* sim, const float* actions_host, float* obs_host,
 /* allocate-and-describe the task buffers the sim owns (obs_buf, rew_buf, reset_buf, ...) */
 enum b2g_task_tensor_kind {
     B2G_TT_OBS = 0, B2G_TT_OBS_CLAMPED = 1, B2G_TT_REW = 2, B2G_TT_RESET = 3, B2G_TT_PROGRESS = 4,
-    B2G_TT_TIMEOUT = 5, B2G_TT_COMMANDS = 6, B2G_TT_ACTIONS = 7, B2G_TT_RAND_OVERRIDE = 8, B2G_TT_COUNT
+    B2G_TT_TIMEOUT = 5, B2G_TT_COMMANDS = 6, B2G_TT_ACTIONS = 7, B2G_TT_RAND_OVERRIDE = 8,
+    /* rough-terrain tasks */
+    B2G_TT_TORQUES = 9, B2G_TT_LAST_ACTIONS = 10, B2G_TT_LAST_DOF_VEL = 11, B2G_TT_FEET_AIR_TIME = 12, B2G_TT_EPISODE_SUMS = 13,
+    B2G_TT_ENV_ORIGINS = 14, B2G_TT_TERRAIN_LEVELS = 15, B2G_TT_TERRAIN_TYPES = 16, B2G_TT_NOISE_OVERRIDE = 17, B2G_TT_PUSH_OVERRIDE = 18,
+    B2G_TT_EXTRAS = 19, B2G_TT_MEASURED_HEIGHTS = 20, B2G_TT_COUNT
 };
 int b2g_task_tensor(b2g_sim* sim, int kind, b2g_tensor_desc* out);
 /* reset_idx(all envs) as in the task constructor (tasks/anymal.py:146) + first observations */
@@ -264,7 +314,7 @@ int b2g_task_anymal_step_host(b2g_sim* sim, const float* actions_host, float* ob
 int64_t b2g_sim_launch_count(const b2g_sim* sim);
 
 /* sizeof() of the public PODs (0 model, 1 sim_params, 2 dof_props, 3 heightfield, 4 tensor_desc,
- * 5 anymal_cfg, 6 cartpole_cfg) so a foreign-language mirror of this header can verify its layout */
+ * 5 anymal_cfg, 6 cartpole_cfg, 7 terrain_cfg) so a foreign-language mirror of this header can verify its layout */
 int b2g_sizeof(int which);
 
 /* gymtorch.wrap_tensor (tasks/anymal.py:121-126): wrap a tensor description as a DLPack

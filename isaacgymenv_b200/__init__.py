@@ -28,8 +28,10 @@ def task_map():
         pass
     try:
         from .tasks.anymal_terrain import AnymalTerrain
+        from .tasks.hound_terrain import HoundTerrain
 
         m["AnymalTerrain"] = AnymalTerrain
+        m["HoundTerrain"] = HoundTerrain
     except ImportError:
         pass
     return m

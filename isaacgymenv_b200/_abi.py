@@ -23,7 +23,10 @@ DOF_MODE_NONE, DOF_MODE_POS, DOF_MODE_VEL, DOF_MODE_EFFORT = 0, 1, 2, 4
 (T_ROOT_STATE, T_DOF_STATE, T_NET_CONTACT, T_DOF_FORCE, T_RIGID_BODY_STATE, T_DOF_TARGET, T_DOF_ACTUATION,
  T_JACOBIAN, T_MASS_MATRIX, T_FRICTION) = range(10)
 
-(TT_OBS, TT_OBS_CLAMPED, TT_REW, TT_RESET, TT_PROGRESS, TT_TIMEOUT, TT_COMMANDS, TT_ACTIONS, TT_RAND_OVERRIDE) = range(9)
+(TT_OBS, TT_OBS_CLAMPED, TT_REW, TT_RESET, TT_PROGRESS, TT_TIMEOUT, TT_COMMANDS, TT_ACTIONS, TT_RAND_OVERRIDE, TT_TORQUES, TT_LAST_ACTIONS,
+ TT_LAST_DOF_VEL, TT_FEET_AIR_TIME, TT_EPISODE_SUMS, TT_ENV_ORIGINS, TT_TERRAIN_LEVELS, TT_TERRAIN_TYPES, TT_NOISE_OVERRIDE, TT_PUSH_OVERRIDE,
+ TT_EXTRAS, TT_MEASURED_HEIGHTS) = range(21)
+REW_TERMS = 14
 
 f32, i32 = C.c_float, C.c_int32
 
@@ -88,6 +91,24 @@ class AnymalCfg(C.Structure):
 class CartpoleCfg(C.Structure):
     _fields_ = [("reset_dist", f32), ("max_push_effort", f32), ("clip_obs", f32), ("clip_actions", f32),
                 ("max_episode_length", C.c_int64), ("seed", C.c_uint64)]
+
+
+class TerrainCfg(C.Structure):
+    _fields_ = [
+        ("lin_vel_scale", f32), ("ang_vel_scale", f32), ("dof_pos_scale", f32), ("dof_vel_scale", f32), ("height_meas_scale", f32),
+        ("action_scale", f32), ("kp", f32), ("kd", f32), ("torque_limit", f32),
+        ("decimation", i32), ("extra_sim_steps", i32), ("dt", f32), ("rew", f32 * REW_TERMS), ("base_height_target", f32),
+        ("clip_obs", f32), ("clip_actions", f32), ("cmd_x", f32 * 2), ("cmd_y", f32 * 2), ("cmd_yaw", f32 * 2),
+        ("default_dof_pos", f32 * MAX_DOF), ("init_root", f32 * 13),
+        ("add_noise", i32), ("noise_lin_vel", f32), ("noise_ang_vel", f32), ("noise_gravity", f32), ("noise_dof_pos", f32),
+        ("noise_dof_vel", f32), ("noise_height", f32),
+        ("base_body", i32), ("n_knee", i32), ("knee_bodies", i32 * 8), ("n_feet", i32), ("feet_bodies", i32 * 8),
+        ("hound_termination", i32), ("n_term_extra", i32), ("term_extra_bodies", i32 * 8), ("allow_knee_contacts", i32),
+        ("hip_dofs", i32 * 4), ("max_episode_length", C.c_int64), ("push_interval", i32), ("max_episode_length_s", f32),
+        ("custom_origins", i32), ("curriculum", i32), ("n_hx", i32), ("n_hy", i32), ("hx", f32 * 16), ("hy", f32 * 16),
+        ("hs_rows", i32), ("hs_cols", i32), ("border_size", f32), ("hscale", f32), ("vscale", f32), ("env_length", f32),
+        ("env_rows", i32), ("env_cols", i32), ("seed", C.c_uint64),
+    ]
 
 
 def _fill(dst, src):

@@ -92,6 +92,67 @@ __global__ void __launch_bounds__(kBlock) k_cartpole_step(SimArgs A, TaskArgs T)
     cartpole_step_thread(A, T, env, valid, sc, bf);
 }
 
+template <int LANES, int NL, bool HF>
+__global__ void __launch_bounds__(kBlock) k_terrain_phys(SimArgs A, TerrainArgs T) {
+    extern __shared__ float smem[];
+    int env, lane; bool valid; ScratchStrided sc; float* bf;
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    terrain_phys_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
+}
+
+template <int LANES, int NL>
+__global__ void __launch_bounds__(kBlock) k_terrain_post(SimArgs A, TerrainArgs T) {
+    __shared__ float red[kBlock];
+    float cnorm = 0.0f;
+    if (T.cfg.custom_origins && T.cfg.curriculum && T.init_done) {
+        // one scalar for ALL resetting envs (reference quirk: torch.norm without dim, anymal_terrain.py:432); every block
+        // sums the same N values in the same order -> identical, deterministic result everywhere
+        float acc = 0.0f;
+        for (int i = threadIdx.x; i < A.n_envs; i += kBlock) acc += T.resetw[i];
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = kBlock / 2; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        cnorm = sqrtf(red[0]);
+    }
+    const int tid = threadIdx.x;
+    constexpr int EPB = kBlock / LANES;
+    const int lane = tid % LANES;
+    const int e = blockIdx.x * EPB + tid / LANES;
+    const bool valid = e < A.n_envs;
+    terrain_post_thread<LANES, NL>(A, T, valid ? e : A.n_envs - 1, lane, valid, cnorm);
+}
+
+// extras["episode"] (anymal_terrain.py:420-425): means over the envs that reset this step; one block, fixed order
+__global__ void k_terrain_extras(const float* report, const long long* reset, const long long* levels, float* extras, int n, float inv_len_s) {
+    __shared__ float red[256];
+    float vals[15];
+    for (int k = 0; k < 15; k++) vals[k] = 0.0f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        for (int k = 0; k < 13; k++) vals[k] += report[(size_t)k * n + i];
+        vals[13] += reset[i] != 0 ? 1.0f : 0.0f;
+        vals[14] += (float)levels[i];
+    }
+    float tot[15];
+    for (int k = 0; k < 15; k++) {
+        red[threadIdx.x] = vals[k];
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        tot[k] = red[0];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && tot[13] > 0.0f) {
+        for (int k = 0; k < 13; k++) extras[k] = tot[k] / tot[13] * inv_len_s;
+        extras[13] = tot[14] / (float)n;
+        extras[14] = tot[13];
+    }
+}
+
 template <int LANES, int NL>
 __global__ void __launch_bounds__(kBlock) k_anymal_reset_all(SimArgs A, TaskArgs T) {
     extern __shared__ float smem[];
@@ -176,6 +237,14 @@ struct b2g_sim {
     unsigned long long seed = 0;
     b2g_anymal_cfg acfg{};
     b2g_cartpole_cfg ccfg{};
+    b2g_terrain_cfg tcfg{};
+    float *torques = nullptr, *last_actions = nullptr, *last_dof_vel = nullptr, *feet_air_time = nullptr, *episode_sums = nullptr;
+    float *env_origins = nullptr, *terrain_origins = nullptr, *scratch9 = nullptr, *resetw = nullptr, *report = nullptr, *measured = nullptr;
+    float *noise_override = nullptr, *push_override = nullptr, *extras = nullptr;
+    long long *terrain_levels = nullptr, *terrain_types = nullptr;
+    int16_t* height_samples = nullptr;
+    long long common_step = 0;
+    int init_done = 0;
     float *obs = nullptr, *obs_clamped = nullptr, *rew = nullptr, *commands = nullptr, *actions = nullptr, *rand_override = nullptr;
     long long *reset = nullptr, *progress = nullptr, *timeout = nullptr;
     int* reset_count = nullptr;
@@ -308,6 +377,30 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
     const TaskArgs T = make_task_args(s, actions_dev, post_only);
     const int grid = grid_size(s);
     const size_t sm = smem_bytes(s);
+    if (s->task_kind == 3) {
+        TerrainArgs R;
+        R.cfg = s->tcfg; R.actions_in = actions_dev; R.obs = s->obs; R.obs_clamped = s->obs_clamped; R.rew = s->rew; R.reset = s->reset;
+        R.progress = s->progress; R.timeout = s->timeout; R.commands = s->commands; R.actions = s->actions; R.torques = s->torques;
+        R.last_actions = s->last_actions; R.last_dof_vel = s->last_dof_vel; R.feet_air_time = s->feet_air_time; R.episode_sums = s->episode_sums;
+        R.env_origins = s->env_origins; R.terrain_levels = s->terrain_levels; R.terrain_types = s->terrain_types; R.terrain_origins = s->terrain_origins;
+        R.height_samples = s->height_samples; R.scratch = s->scratch9; R.resetw = s->resetw; R.report = s->report; R.measured = s->measured;
+        R.reset_count = s->reset_count;
+        R.reset_override = s->use_rand_override ? s->rand_override : nullptr;
+        R.noise_override = s->use_rand_override ? s->noise_override : nullptr;
+        R.push_override = s->use_rand_override ? s->push_override : nullptr;
+        R.common_step = s->common_step; R.init_done = s->init_done; R.post_only = post_only; R.seed = s->seed;
+        if (s->v.lanes == 4) {
+            if (s->has_hf) k_terrain_phys<4, 3, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<4, 3, false><<<grid, kBlock, sm, st>>>(A, R);
+            k_terrain_post<4, 3><<<grid, kBlock, 0, st>>>(A, R);
+        } else {
+            if (s->has_hf) k_terrain_phys<8, 6, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<8, 6, false><<<grid, kBlock, sm, st>>>(A, R);
+            k_terrain_post<8, 6><<<grid, kBlock, 0, st>>>(A, R);
+        }
+        k_terrain_extras<<<1, 256, 0, st>>>(s->report, s->reset, s->terrain_levels, s->extras, s->n_envs, 1.0f / s->tcfg.max_episode_length_s);
+        s->launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        return B2G_OK;
+    }
     if (s->task_kind == 2) {
         k_cartpole_step<<<grid, kBlock, sm, st>>>(A, T);
         s->launches++;
@@ -341,6 +434,7 @@ int b2g_sizeof(int which) {
         case 4: return (int)sizeof(b2g_tensor_desc);
         case 5: return (int)sizeof(b2g_anymal_cfg);
         case 6: return (int)sizeof(b2g_cartpole_cfg);
+        case 7: return (int)sizeof(b2g_terrain_cfg);
         default: return -1;
     }
 }
@@ -365,7 +459,9 @@ int b2g_sim_destroy(b2g_sim* s) {
     with_device(s, [&]() {
         for (int k = 0; k < B2G_T_COUNT; k++) if (s->t[k]) cudaFree(s->t[k]);
         void* ptrs[] = {s->d_model, s->d_hf, s->obs, s->obs_clamped, s->rew, s->commands, s->actions, s->rand_override,
-                        s->reset, s->progress, s->timeout, s->reset_count, s->actions_in};
+                        s->reset, s->progress, s->timeout, s->reset_count, s->actions_in, s->torques, s->last_actions, s->last_dof_vel,
+                        s->feet_air_time, s->episode_sums, s->env_origins, s->terrain_origins, s->scratch9, s->resetw, s->report, s->measured,
+                        s->noise_override, s->push_override, s->extras, s->terrain_levels, s->terrain_types, s->height_samples};
         for (void* p : ptrs) if (p) cudaFree(p);
         return 0;
     });
@@ -633,6 +729,76 @@ int b2g_task_cartpole_create(b2g_sim* s, const b2g_cartpole_cfg* cfg) {
     return alloc_task_buffers(s, 4, 1, 4);
 }
 
+int b2g_task_terrain_create(b2g_sim* s, const b2g_terrain_cfg* cfg, const int16_t* hs_host, const float* origins_host) {
+    if (!s || !cfg) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "task created before prepare_sim");
+    if (s->model.fixed_base) return fail(B2G_ERR_UNSUPPORTED, "the terrain task needs a floating base");
+    if (s->has_task) return fail(B2G_ERR_STATE, "a task already lives on this sim");
+    const int nb = s->model.n_bodies, nd = s->model.n_dof;
+    if (cfg->base_body < 0 || cfg->base_body >= nb || cfg->n_knee < 0 || cfg->n_knee > 8 || cfg->n_feet < 0 || cfg->n_feet > 4 ||
+        cfg->n_term_extra < 0 || cfg->n_term_extra > 8 || cfg->n_hx < 1 || cfg->n_hx > 16 || cfg->n_hy < 1 || cfg->n_hy > 16)
+        return fail(B2G_ERR_ARG, "bad body index counts / height grid");
+    for (int k = 0; k < cfg->n_knee; k++) if (cfg->knee_bodies[k] < 0 || cfg->knee_bodies[k] >= nb) return fail(B2G_ERR_ARG, "bad knee body");
+    for (int k = 0; k < cfg->n_feet; k++) if (cfg->feet_bodies[k] < 0 || cfg->feet_bodies[k] >= nb) return fail(B2G_ERR_ARG, "bad foot body");
+    for (int k = 0; k < cfg->n_term_extra; k++) if (cfg->term_extra_bodies[k] < 0 || cfg->term_extra_bodies[k] >= nb) return fail(B2G_ERR_ARG, "bad termination body");
+    if (cfg->custom_origins && (!hs_host || !origins_host || cfg->hs_rows < 2 || cfg->hs_cols < 2 || cfg->env_rows < 1 || cfg->env_cols < 1))
+        return fail(B2G_ERR_ARG, "custom origins need height samples and terrain origins");
+    s->tcfg = *cfg;
+    s->seed = cfg->seed;
+    s->task_kind = 3;
+    s->n_cmd = 4;
+    const int nhp = cfg->n_hx * cfg->n_hy;
+    const int no = 12 + 2 * nd + nhp + nd;
+    int rc = alloc_task_buffers(s, no, nd, 2 * nd + 5);
+    if (rc != B2G_OK) return rc;
+    return with_device(s, [&]() {
+        const size_t n = s->n_envs;
+        auto zalloc = [&](void** p, size_t bytes) -> cudaError_t {
+            cudaError_t e = cudaMalloc(p, bytes ? bytes : 4);
+            if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes ? bytes : 4);
+            return e;
+        };
+        CUDA_TRY(zalloc((void**)&s->torques, sizeof(float) * n * nd));
+        CUDA_TRY(zalloc((void**)&s->last_actions, sizeof(float) * n * nd));
+        CUDA_TRY(zalloc((void**)&s->last_dof_vel, sizeof(float) * n * nd));
+        CUDA_TRY(zalloc((void**)&s->feet_air_time, sizeof(float) * n * 4));
+        CUDA_TRY(zalloc((void**)&s->episode_sums, sizeof(float) * n * 13));
+        CUDA_TRY(zalloc((void**)&s->env_origins, sizeof(float) * n * 3));
+        CUDA_TRY(zalloc((void**)&s->scratch9, sizeof(float) * n * 9));
+        CUDA_TRY(zalloc((void**)&s->resetw, sizeof(float) * n));
+        CUDA_TRY(zalloc((void**)&s->report, sizeof(float) * n * 13));
+        CUDA_TRY(zalloc((void**)&s->measured, sizeof(float) * n * nhp));
+        CUDA_TRY(zalloc((void**)&s->noise_override, sizeof(float) * n * no));
+        CUDA_TRY(zalloc((void**)&s->push_override, sizeof(float) * n * 2));
+        CUDA_TRY(zalloc((void**)&s->extras, sizeof(float) * 16));
+        CUDA_TRY(zalloc((void**)&s->terrain_levels, sizeof(long long) * n));
+        CUDA_TRY(zalloc((void**)&s->terrain_types, sizeof(long long) * n));
+        if (hs_host && cfg->hs_rows > 0) {
+            const size_t b = sizeof(int16_t) * (size_t)cfg->hs_rows * cfg->hs_cols;
+            CUDA_TRY(cudaMalloc(&s->height_samples, b));
+            CUDA_TRY(cudaMemcpy(s->height_samples, hs_host, b, cudaMemcpyHostToDevice));
+        }
+        if (origins_host && cfg->env_rows > 0) {
+            const size_t b = sizeof(float) * (size_t)cfg->env_rows * cfg->env_cols * 3;
+            CUDA_TRY(cudaMalloc(&s->terrain_origins, b));
+            CUDA_TRY(cudaMemcpy(s->terrain_origins, origins_host, b, cudaMemcpyHostToDevice));
+        }
+        return (int)B2G_OK;
+    });
+}
+
+int b2g_task_terrain_set_step(b2g_sim* s, int64_t step) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    s->common_step = step;
+    return B2G_OK;
+}
+
+int b2g_task_terrain_set_init_done(b2g_sim* s, int v) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    s->init_done = v;
+    return B2G_OK;
+}
+
 int b2g_task_tensor(b2g_sim* s, int kind, b2g_tensor_desc* d) {
     if (!s || !d) return fail(B2G_ERR_ARG, "null argument");
     if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
@@ -641,6 +807,7 @@ int b2g_task_tensor(b2g_sim* s, int kind, b2g_tensor_desc* d) {
     d->dtype = 0;
     d->shape[0] = n; d->shape[1] = d->shape[2] = d->shape[3] = 1;
     d->ndim = 1;
+    if (kind >= B2G_TT_TORQUES && s->task_kind != 3) return fail(B2G_ERR_ARG, "tensor kind %d belongs to the terrain task", kind);
     switch (kind) {
         case B2G_TT_OBS: d->data = s->obs; d->ndim = 2; d->shape[1] = s->num_obs; break;
         case B2G_TT_OBS_CLAMPED: d->data = s->obs_clamped; d->ndim = 2; d->shape[1] = s->num_obs; break;
@@ -651,6 +818,18 @@ int b2g_task_tensor(b2g_sim* s, int kind, b2g_tensor_desc* d) {
         case B2G_TT_COMMANDS: d->data = s->commands; d->ndim = 2; d->shape[1] = s->n_cmd; break;
         case B2G_TT_ACTIONS: d->data = s->actions; d->ndim = 2; d->shape[1] = s->num_act; break;
         case B2G_TT_RAND_OVERRIDE: d->data = s->rand_override; d->ndim = 2; d->shape[1] = s->n_draws; break;
+        case B2G_TT_TORQUES: d->data = s->torques; d->ndim = 2; d->shape[1] = s->num_act; break;
+        case B2G_TT_LAST_ACTIONS: d->data = s->last_actions; d->ndim = 2; d->shape[1] = s->num_act; break;
+        case B2G_TT_LAST_DOF_VEL: d->data = s->last_dof_vel; d->ndim = 2; d->shape[1] = s->num_act; break;
+        case B2G_TT_FEET_AIR_TIME: d->data = s->feet_air_time; d->ndim = 2; d->shape[1] = 4; break;
+        case B2G_TT_EPISODE_SUMS: d->data = s->episode_sums; d->ndim = 2; d->shape[0] = 13; d->shape[1] = n; break;
+        case B2G_TT_ENV_ORIGINS: d->data = s->env_origins; d->ndim = 2; d->shape[1] = 3; break;
+        case B2G_TT_TERRAIN_LEVELS: d->data = s->terrain_levels; d->dtype = 2; break;
+        case B2G_TT_TERRAIN_TYPES: d->data = s->terrain_types; d->dtype = 2; break;
+        case B2G_TT_NOISE_OVERRIDE: d->data = s->noise_override; d->ndim = 2; d->shape[1] = s->num_obs; break;
+        case B2G_TT_PUSH_OVERRIDE: d->data = s->push_override; d->ndim = 2; d->shape[1] = 2; break;
+        case B2G_TT_EXTRAS: d->data = s->extras; d->shape[0] = 16; break;
+        case B2G_TT_MEASURED_HEIGHTS: d->data = s->measured; d->ndim = 2; d->shape[1] = s->tcfg.n_hx * s->tcfg.n_hy; break;
         default: return fail(B2G_ERR_ARG, "unknown task tensor kind %d", kind);
     }
     return B2G_OK;

@@ -370,6 +370,350 @@ B2G_HD B2G_INL void cartpole_step_thread(const SimArgs& A, const TaskArgs& T, in
     }
 }
 
+
+// ================================================================================================
+// Rough-terrain locomotion task (AnymalTerrain / HoundTerrain), two kernels per step
+// ================================================================================================
+struct TerrainArgs {
+    b2g_terrain_cfg cfg;
+    const float* actions_in;     // (N,na)
+    float* obs;                  // (N,no)
+    float* obs_clamped;
+    float* rew;
+    long long* reset;            // (N) 0/1
+    long long* progress;
+    long long* timeout;          // (N) previous step's value is an input of the reward (anymal_terrain.py:367)
+    float* commands;             // (N,4) x, y, yaw rate (heading-derived), heading
+    float* actions;              // (N,na)
+    float* torques;              // (N,nd)
+    float* last_actions;
+    float* last_dof_vel;
+    float* feet_air_time;        // (N,4)
+    float* episode_sums;         // (13,N)
+    float* env_origins;          // (N,3)
+    long long* terrain_levels;   // (N)
+    long long* terrain_types;    // (N)
+    const float* terrain_origins;   // (rows,cols,3) or null
+    const short* height_samples;    // (hs_rows,hs_cols) or null
+    float* scratch;              // (N,9) base lin vel, base ang vel, projected gravity of this step (pre-reset)
+    float* resetw;               // (N) reset ? |cmd_xy|^2 : 0      (curriculum scalar, quirk Q10)
+    float* report;               // (13,N) episode sums of the envs that reset this step (else 0)
+    float* measured;             // (N,n_height_points)
+    int* reset_count;
+    const float* reset_override; // (N,29)
+    const float* noise_override; // (N,no)
+    const float* push_override;  // (N,2)
+    long long common_step;       // counter AFTER this step's increment
+    int init_done;
+    int post_only;
+    unsigned long long seed;
+};
+
+B2G_HD B2G_INL float terrain_uniform(const TerrainArgs& T, const float* ovr, int ncol, int env, unsigned c1, unsigned stream, int i) {
+    if (ovr) return ovr[(size_t)env * ncol + i];
+    unsigned o[4];
+    philox4x32((unsigned)env, c1, (unsigned)(i >> 2), stream, (unsigned)(T.seed & 0xffffffffull), (unsigned)(T.seed >> 32), o);
+    return (float)(o[i & 3] >> 8) * (1.0f / 16777216.0f);
+}
+
+// utils/torch_jit_utils.py:70-77
+B2G_HD B2G_INL V3 quat_apply_v(float qx, float qy, float qz, float qw, V3 b) {
+    const V3 xyz = V3{qx, qy, qz};
+    const V3 t = cross(xyz, b) * 2.0f;
+    return b + t * qw + cross(xyz, t);
+}
+// tasks/anymal_terrain.py:683-687 as TorchScript runs it (C fmod)
+B2G_HD B2G_INL float wrap_to_pi_f(float a) {
+    a = fmodf(a, 6.283185307179586f);
+    if (a > 3.141592653589793f) a -= 6.283185307179586f;
+    return a;
+}
+B2G_HD B2G_INL float norm3(const float* f) { return sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]); }
+
+// kernel 1: pre_physics_step (decimation loop) + extra sim step + post_physics_step up to and including the reward
+template <int LANES, int NL, bool HF>
+B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, int env, int lane, bool valid, ScratchStrided sc, float* bf) {
+    const DevModel* M = A.M;
+    const b2g_terrain_cfg& C = T.cfg;
+    const int nd = M->n_dof;
+    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
+    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    LaneState<NL> st;
+    load_state<NL>(A, env, len, d0, st);
+    const long long progress = T.progress[env] + 1;
+    const bool timeout_prev = T.timeout[env] != 0;
+    float cmd[4] = {T.commands[(size_t)env * 4], T.commands[(size_t)env * 4 + 1], T.commands[(size_t)env * 4 + 2], T.commands[(size_t)env * 4 + 3]};
+    float act[NL], tq[NL], lact[NL], lqd[NL];
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        act[j] = 0; tq[j] = 0; lact[j] = 0; lqd[j] = 0;
+        if (j < len) {
+            const size_t k = (size_t)env * nd + d0 + j;
+            float a = T.actions_in[k];
+            a = fminf(fmaxf(a, -C.clip_actions), C.clip_actions);
+            act[j] = a;
+            lact[j] = T.last_actions[k];
+            lqd[j] = T.last_dof_vel[k];
+        }
+    }
+    if (!T.post_only) {
+        const float mu_shape = A.friction ? A.friction[env] : 1.0f;
+        const int total = C.decimation + C.extra_sim_steps;
+        for (int it = 0; it < total; it++) {
+            if (it < C.decimation) {      // tasks/anymal_terrain.py:444-445: fresh explicit PD torque, clipped
+#pragma unroll
+                for (int j = 0; j < NL; j++) {
+                    if (j < len) {
+                        const float t = C.kp * (C.action_scale * act[j] + C.default_dof_pos[d0 + j] - st.q[j]) - C.kd * st.qd[j];
+                        tq[j] = fminf(fmaxf(t, -C.torque_limit), C.torque_limit);
+                        st.act[j] = tq[j];
+                    }
+                }
+            }
+            for (int s = 0; s < A.P.substeps; s++)
+                substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape,
+                                                                             it == total - 1 && s == A.P.substeps - 1, sc, bf);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NL; j++)
+            if (j < len) { tq[j] = T.torques[(size_t)env * nd + d0 + j]; st.frc[j] = A.dof_force[(size_t)env * nd + d0 + j]; }
+        const int nb3p = M->n_bodies * 3;
+        for (int i = lane; i < nb3p; i += LANES) bf[i] = A.contact[(size_t)env * nb3p + i];
+        Grp<LANES>::sync();
+    }
+    // ---- post_physics_step (tasks/anymal_terrain.py:453-471) ----
+    if (C.push_interval > 0 && (T.common_step % C.push_interval) == 0) {      // push_robots :437-439
+        st.rv.x = rand_range(-1.0f, 1.0f, terrain_uniform(T, T.push_override, 2, env, (unsigned)T.common_step, 3u, 0));
+        st.rv.y = rand_range(-1.0f, 1.0f, terrain_uniform(T, T.push_override, 2, env, (unsigned)T.common_step, 3u, 1));
+    }
+    const V3 lin = quat_rotate_inverse(st.qx, st.qy, st.qz, st.qw, st.rv);
+    const V3 ang = quat_rotate_inverse(st.qx, st.qy, st.qz, st.qw, st.rw);
+    const V3 pg = quat_rotate_inverse(st.qx, st.qy, st.qz, st.qw, V3{0.0f, 0.0f, -1.0f});
+    const V3 fwd = quat_apply_v(st.qx, st.qy, st.qz, st.qw, V3{1.0f, 0.0f, 0.0f});
+    const float heading = atan2f(fwd.y, fwd.x);
+    cmd[2] = fminf(fmaxf(0.5f * wrap_to_pi_f(cmd[3] - heading), -1.0f), 1.0f);
+    // check_termination
+    bool term = norm3(bf + C.base_body * 3) > 1.0f;
+    if (C.hound_termination || !C.allow_knee_contacts)
+        for (int k = 0; k < C.n_knee; k++) term = term || (norm3(bf + C.knee_bodies[k] * 3) > 1.0f);
+    if (C.hound_termination)
+        for (int k = 0; k < C.n_term_extra; k++) term = term || (norm3(bf + C.term_extra_bodies[k] * 3) > 1.0f);
+    const bool reset = term || (progress >= C.max_episode_length - 1);
+    // compute_reward :315-382 -- per-lane partial sums, then one shuffle reduction each
+    float s_tq = 0, s_jacc = 0, s_arate = 0, s_hip = 0, s_coll = 0, s_stumble = 0, s_air = 0;
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        if (j < len) {
+            s_tq += tq[j] * tq[j];
+            const float dv = lqd[j] - st.qd[j], da = lact[j] - act[j];
+            s_jacc += dv * dv;
+            s_arate += da * da;
+            const int d = d0 + j;
+            if (d == C.hip_dofs[0] || d == C.hip_dofs[1] || d == C.hip_dofs[2] || d == C.hip_dofs[3]) s_hip += fabsf(st.q[j] - C.default_dof_pos[d]);
+        }
+    }
+    for (int k = lane; k < C.n_knee; k += LANES) s_coll += (norm3(bf + C.knee_bodies[k] * 3) > 1.0f) ? 1.0f : 0.0f;
+    for (int k = lane; k < C.n_feet; k += LANES) {
+        const float* f = bf + C.feet_bodies[k] * 3;
+        s_stumble += ((sqrtf(f[0] * f[0] + f[1] * f[1]) > 5.0f) && (fabsf(f[2]) < 1.0f)) ? 1.0f : 0.0f;
+        const bool contact = f[2] > 1.0f;
+        float air = T.feet_air_time[(size_t)env * 4 + k];
+        const bool first = (air > 0.0f) && contact;
+        air += C.dt;
+        if (first) s_air += air - 0.5f;
+        if (contact) air = 0.0f;
+        if (valid) T.feet_air_time[(size_t)env * 4 + k] = air;
+    }
+    s_tq = Grp<LANES>::sum(s_tq); s_jacc = Grp<LANES>::sum(s_jacc); s_arate = Grp<LANES>::sum(s_arate); s_hip = Grp<LANES>::sum(s_hip);
+    s_coll = Grp<LANES>::sum(s_coll); s_stumble = Grp<LANES>::sum(s_stumble); s_air = Grp<LANES>::sum(s_air);
+    const float ex = cmd[0] - lin.x, ey = cmd[1] - lin.y, ez = cmd[2] - ang.z;
+    const float r_lin_xy = expf(-(ex * ex + ey * ey) / 0.25f) * C.rew[1];
+    const float r_ang_z = expf(-(ez * ez) / 0.25f) * C.rew[3];
+    const float r_lin_z = lin.z * lin.z * C.rew[2];
+    const float r_ang_xy = (ang.x * ang.x + ang.y * ang.y) * C.rew[4];
+    const float r_orient = (pg.x * pg.x + pg.y * pg.y) * C.rew[5];
+    const float dz = st.rp.z - C.base_height_target;
+    const float r_height = dz * dz * C.rew[8];
+    const float r_torque = s_tq * C.rew[6];
+    const float r_jacc = s_jacc * C.rew[7];
+    const float r_coll = s_coll * C.rew[10];
+    const float r_stumble = s_stumble * C.rew[11];
+    const float r_arate = s_arate * C.rew[12];
+    float r_air = s_air * C.rew[9];
+    if (!(sqrtf(cmd[0] * cmd[0] + cmd[1] * cmd[1]) > 0.1f)) r_air = 0.0f;
+    const float r_hip = s_hip * C.rew[13];
+    float rew = r_lin_xy + r_ang_z + r_lin_z + r_ang_xy + r_orient + r_height + r_torque + r_jacc + r_coll + r_arate + r_air + r_hip + r_stumble;
+    rew = fmaxf(rew, 0.0f);
+    if (reset && !timeout_prev) rew += C.rew[0];
+    if (valid) {
+        store_state<NL>(A, env, lane, len, d0, st, false);
+        const int nb3 = M->n_bodies * 3;
+        for (int i = lane; i < nb3; i += LANES) A.contact[(size_t)env * nb3 + i] = bf[i];
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            if (j < len) {
+                const size_t k = (size_t)env * nd + d0 + j;
+                T.actions[k] = act[j];
+                T.torques[k] = tq[j];
+            }
+        }
+        if (lane == 0) {
+            T.rew[env] = rew;
+            T.reset[env] = reset ? 1 : 0;
+            T.progress[env] = progress;
+            T.commands[(size_t)env * 4 + 2] = cmd[2];
+            T.resetw[env] = reset ? (cmd[0] * cmd[0] + cmd[1] * cmd[1]) : 0.0f;
+            float* sc9 = T.scratch + (size_t)env * 9;
+            sc9[0] = lin.x; sc9[1] = lin.y; sc9[2] = lin.z; sc9[3] = ang.x; sc9[4] = ang.y; sc9[5] = ang.z; sc9[6] = pg.x; sc9[7] = pg.y; sc9[8] = pg.z;
+            // episode sums, key order of the reference dict (anymal_terrain.py:156-158)
+            const float terms[13] = {r_lin_xy, r_lin_z, r_ang_z, r_ang_xy, r_orient, r_torque, r_jacc, r_height, r_air, r_coll, r_stumble, r_arate, r_hip};
+            for (int k = 0; k < 13; k++) T.episode_sums[(size_t)k * A.n_envs + env] += terms[k];
+        }
+    }
+}
+
+// kernel 2: reset_idx (+ terrain curriculum), observations (+ height scan, noise), history, time-outs
+template <int LANES, int NL>
+B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, int env, int lane, bool valid, float curriculum_norm) {
+    const DevModel* M = A.M;
+    const b2g_terrain_cfg& C = T.cfg;
+    const int nd = M->n_dof, N = A.n_envs;
+    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
+    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    const bool reset = T.reset[env] != 0;
+    float root[13];
+    for (int k = 0; k < 13; k++) root[k] = A.root[(size_t)env * 13 + k];
+    float cmd[4] = {T.commands[(size_t)env * 4], T.commands[(size_t)env * 4 + 1], T.commands[(size_t)env * 4 + 2], T.commands[(size_t)env * 4 + 3]};
+    long long progress = T.progress[env];
+    const int rc = T.reset_count[env];
+    float q[NL], qd[NL];
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        q[j] = 0; qd[j] = 0;
+        if (j < len) { q[j] = A.dof[2 * ((size_t)env * nd + d0 + j)]; qd[j] = A.dof[2 * ((size_t)env * nd + d0 + j) + 1]; }
+    }
+    float origin[3] = {T.env_origins[(size_t)env * 3], T.env_origins[(size_t)env * 3 + 1], T.env_origins[(size_t)env * 3 + 2]};
+    long long level = T.terrain_levels[env];
+    const long long type = T.terrain_types[env];
+    // every lane has read the per-env inputs it replicates; only now may lane 0 overwrite them
+    Grp<LANES>::sync();
+    if (reset) {        // reset_idx, tasks/anymal_terrain.py:384-425; draw order of the torch_rand_float calls
+        const int ndraw = 2 * nd + 5;
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            if (j < len) {
+                const int d = d0 + j;
+                q[j] = C.default_dof_pos[d] * rand_range(0.5f, 1.5f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, d));
+                qd[j] = rand_range(-0.1f, 0.1f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, nd + d));
+            }
+        }
+        int col = 2 * nd;
+        if (C.custom_origins) {
+            if (T.init_done && C.curriculum) {      // update_terrain_level :427-435
+                const float dx = root[0] - origin[0], dy = root[1] - origin[1];
+                const float dist = sqrtf(dx * dx + dy * dy);
+                if (dist < curriculum_norm * C.max_episode_length_s * 0.25f) level -= 1;
+                if (dist > C.env_length / 2) level += 1;
+                if (level < 0) level = 0;
+                level = level % C.env_rows;
+                const float* o = T.terrain_origins + ((size_t)level * C.env_cols + (size_t)type) * 3;
+                origin[0] = o[0]; origin[1] = o[1]; origin[2] = o[2];
+                if (valid && lane == 0) {
+                    T.terrain_levels[env] = level;
+                    T.env_origins[(size_t)env * 3] = origin[0]; T.env_origins[(size_t)env * 3 + 1] = origin[1]; T.env_origins[(size_t)env * 3 + 2] = origin[2];
+                }
+            }
+            for (int k = 0; k < 13; k++) root[k] = C.init_root[k];
+            root[0] += origin[0]; root[1] += origin[1]; root[2] += origin[2];
+            root[0] += rand_range(-0.5f, 0.5f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, col));
+            root[1] += rand_range(-0.5f, 0.5f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, col + 1));
+            col += 2;
+        } else {
+            for (int k = 0; k < 13; k++) root[k] = C.init_root[k];
+        }
+        cmd[0] = rand_range(C.cmd_x[0], C.cmd_x[1], terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, col));
+        cmd[1] = rand_range(C.cmd_y[0], C.cmd_y[1], terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, col + 1));
+        cmd[3] = rand_range(C.cmd_yaw[0], C.cmd_yaw[1], terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, col + 2));
+        if (!(sqrtf(cmd[0] * cmd[0] + cmd[1] * cmd[1]) > 0.25f)) { cmd[0] = 0; cmd[1] = 0; cmd[2] = 0; cmd[3] = 0; }   // :412 (all four columns)
+        progress = 0;
+    }
+    // ---- observations (tasks/anymal_terrain.py:302-313) ----
+    const int nhp = C.n_hx * C.n_hy;
+    const int no = 12 + 2 * nd + nhp + nd;
+    float* o = T.obs + (size_t)env * no;
+    float* oc = T.obs_clamped + (size_t)env * no;
+    const unsigned step = (unsigned)T.common_step;
+    auto put = [&](int idx, float val, float nscale) {
+        if (C.add_noise && nscale != 0.0f) val += (2.0f * terrain_uniform(T, T.noise_override, no, env, step, 2u, idx) - 1.0f) * nscale;
+        if (valid) { o[idx] = val; oc[idx] = fminf(fmaxf(val, -C.clip_obs), C.clip_obs); }
+    };
+    if (lane == 0) {
+        const float* s9 = T.scratch + (size_t)env * 9;
+        for (int k = 0; k < 3; k++) put(k, s9[k] * C.lin_vel_scale, C.noise_lin_vel);
+        for (int k = 0; k < 3; k++) put(3 + k, s9[3 + k] * C.ang_vel_scale, C.noise_ang_vel);
+        for (int k = 0; k < 3; k++) put(6 + k, s9[6 + k], C.noise_gravity);
+        put(9, cmd[0] * C.lin_vel_scale, 0.0f);
+        put(10, cmd[1] * C.lin_vel_scale, 0.0f);
+        put(11, cmd[2] * C.ang_vel_scale, 0.0f);
+    }
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        if (j < len) {
+            const int d = d0 + j;
+            const size_t k = (size_t)env * nd + d;
+            const float a = T.actions[k];
+            put(12 + d, q[j] * C.dof_pos_scale, C.noise_dof_pos);
+            put(12 + nd + d, qd[j] * C.dof_vel_scale, C.noise_dof_vel);
+            put(12 + 2 * nd + nhp + d, a, 0.0f);
+            if (valid) {
+                T.last_actions[k] = a;          // :484-485 (post-reset values for envs that reset)
+                T.last_dof_vel[k] = qd[j];
+                if (reset) { A.dof[2 * k] = q[j]; A.dof[2 * k + 1] = qd[j]; }
+            }
+        }
+    }
+    // height scan: yaw-only rotation of the grid, truncating index, min of two diagonal samples (:515-538)
+    {
+        float yz = root[5], yw = root[6];
+        const float yn = fmaxf(sqrtf(yz * yz + yw * yw), 1e-9f);
+        yz /= yn; yw /= yn;
+        for (int p = lane; p < nhp; p += LANES) {
+            float h = 0.0f;
+            if (T.height_samples) {
+                const V3 pt = quat_apply_v(0.0f, 0.0f, yz, yw, V3{C.hx[p / C.n_hy], C.hy[p % C.n_hy], 0.0f});
+                long long px = (long long)((pt.x + root[0] + C.border_size) / C.hscale);
+                long long py = (long long)((pt.y + root[1] + C.border_size) / C.hscale);
+                px = px < 0 ? 0 : (px > C.hs_rows - 2 ? C.hs_rows - 2 : px);
+                py = py < 0 ? 0 : (py > C.hs_cols - 2 ? C.hs_cols - 2 : py);
+                const short h1 = T.height_samples[px * C.hs_cols + py], h2 = T.height_samples[(px + 1) * C.hs_cols + py + 1];
+                h = (float)(h1 < h2 ? h1 : h2) * C.vscale;
+            }
+            if (valid) T.measured[(size_t)env * nhp + p] = h;
+            const float v = fminf(fmaxf(root[2] - 0.5f - h, -1.0f), 1.0f) * C.height_meas_scale;
+            put(12 + 2 * nd + p, v, C.noise_height);
+        }
+    }
+    if (valid) {
+        for (int k = lane; k < C.n_feet; k += LANES)
+            if (reset) T.feet_air_time[(size_t)env * 4 + k] = 0.0f;
+        for (int k = lane; k < 13; k += LANES) {
+            float* es = T.episode_sums + (size_t)k * N + env;
+            T.report[(size_t)k * N + env] = reset ? *es : 0.0f;
+            if (reset) *es = 0.0f;
+        }
+        if (lane == 0) {
+            if (reset) {
+                for (int k = 0; k < 13; k++) A.root[(size_t)env * 13 + k] = root[k];
+                for (int k = 0; k < 4; k++) T.commands[(size_t)env * 4 + k] = cmd[k];
+                T.reset_count[env] = rc + 1;
+            }
+            T.progress[env] = progress;
+            T.timeout[env] = (progress >= C.max_episode_length - 1 && reset) ? 1 : 0;
+        }
+    }
+}
+
 // refresh_rigid_body_state_tensor: world pose + velocity of every API body (N,nb,13). One thread per env.
 B2G_HD B2G_INL void body_state_env(const DevModel* M, const float* root, const float* dof, float* out) {
     const int nd = M->n_dof;

@@ -227,6 +227,7 @@ class Sim:
         self.actor_pose = None
         self.dof_props = None           # numpy structured array
         self.env_friction: List[float] = []
+        self.actor_poses: List[tuple] = []
         self.env_spacing = 0.0
         self.num_per_row = 1
         self.prepared = False
@@ -311,8 +312,12 @@ class Gym:
                                                 float(sim.env_spacing), int(sim.num_per_row)), "create_actor")
         _lib.check(lib.b2g_sim_prepare(sim.handle), "prepare_sim")
         sim.prepared = True
+        import torch
+
+        if len(set(sim.actor_poses)) > 1:       # per-env start poses (terrain tasks place robots on their tiles)
+            root = self._tensor(sim, _abi.T_ROOT_STATE)
+            root[:, :7] = torch.tensor(sim.actor_poses, dtype=torch.float32, device=root.device)
         if any(abs(f - 1.0) > 0 for f in sim.env_friction):
-            import torch
 
             fr = self._tensor(sim, _abi.T_FRICTION)
             fr.copy_(torch.tensor(sim.env_friction, dtype=torch.float32, device=fr.device))
@@ -480,6 +485,7 @@ class Gym:
             raise _lib.B2GError("one actor per env is supported")
         env.actors.append(name)
         sim.env_friction.append(float(asset.shape_friction))
+        sim.actor_poses.append((pose.p.x, pose.p.y, pose.p.z, pose.r.x, pose.r.y, pose.r.z, pose.r.w))
         return 0
 
     def get_actor_dof_properties(self, env: Env, actor: int):

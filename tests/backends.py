@@ -14,6 +14,7 @@ import numpy as np
 from isaacgymenv_b200 import _abi
 
 TASK_KEYS = ("obs", "obs_clamped", "rew", "reset", "progress", "timeout", "commands", "actions")
+TERRAIN_KEYS = ("torques", "last_actions", "last_dof_vel", "feet_air_time", "episode_sums", "env_origins", "terrain_levels", "terrain_types", "measured")
 
 
 class EmuBackend:
@@ -58,12 +59,41 @@ class EmuBackend:
                          commands=np.zeros((n, 3), np.float32), actions=np.zeros((n, 1), np.float32), reset_count=np.zeros(n, np.int32))
 
     def task_step(self, actions, draws=None, post_only=False):
-        if getattr(self, "kind", "anymal") == "cartpole":
+        if getattr(self, "kind", "anymal") == "terrain":
+            self._terrain_step(actions, draws, post_only)
+        elif getattr(self, "kind", "anymal") == "cartpole":
             self.emu.cartpole(self.model, self.params, self.props, self.cfg, 2 if post_only else 1, self._bufs(), actions, draws)
         elif post_only:
             self.anymal_post_only(actions, draws)
         else:
             self.anymal_step(actions, draws)
+
+    def terrain_create(self, cfg, height_samples=None, terrain_origins=None, heightfield=None):
+        n, nd = self.n, self.art.num_dofs
+        nhp = cfg.n_hx * cfg.n_hy
+        no = 12 + 2 * nd + nhp + nd
+        self.cfg, self.kind = cfg, "terrain"
+        self.hs = None if height_samples is None else np.ascontiguousarray(height_samples, np.int16)
+        self.origins = None if terrain_origins is None else np.ascontiguousarray(terrain_origins, np.float32)
+        self.heightfield = heightfield
+        self.init_done, self.common_step = 1, 0
+        z = lambda *sh, dt=np.float32: np.zeros(sh, dt)
+        self.task = dict(obs=z(n, no), obs_clamped=z(n, no), rew=z(n), reset=np.ones(n, np.int64), progress=z(n, dt=np.int64), timeout=z(n, dt=np.int64),
+                         commands=z(n, 4), actions=z(n, nd), reset_count=z(n, dt=np.int32), torques=z(n, nd), last_actions=z(n, nd), last_dof_vel=z(n, nd),
+                         feet_air_time=z(n, 4), episode_sums=z(13, n), env_origins=z(n, 3), terrain_levels=z(n, dt=np.int64), terrain_types=z(n, dt=np.int64),
+                         scratch=z(n, 9), resetw=z(n), report=z(13, n), measured=z(n, nhp))
+
+    def _terrain_step(self, actions, draws, post_only):
+        b = self._bufs()
+        b["actions_in"] = np.ascontiguousarray(actions, np.float32)
+        b["terrain_origins"], b["height_samples"] = self.origins, self.hs
+        d = draws or {}
+        b["reset_override"] = None if d.get("reset") is None else np.ascontiguousarray(d["reset"], np.float32)
+        b["noise_override"] = None if d.get("noise") is None else np.ascontiguousarray(d["noise"], np.float32)
+        b["push_override"] = None if d.get("push") is None else np.ascontiguousarray(d["push"], np.float32)
+        hf = self.heightfield
+        self.emu.terrain(self.model, self.params, self.props, self.cfg, 2 if post_only else 1, b, self.common_step, self.init_done,
+                         hf[0] if hf else None, hf[1] if hf else None)
 
     def anymal_create(self, cfg):
         n, nd = self.n, self.art.num_dofs
@@ -89,8 +119,14 @@ class EmuBackend:
 
     def get_task(self):
         out = {k: self.task[k].copy() for k in TASK_KEYS}
+        if getattr(self, "kind", "") == "terrain":
+            out.update({k: self.task[k].copy() for k in TERRAIN_KEYS})
+            out["report"] = self.task["report"].copy()
         out["dof_force"], out["contact"] = self.dof_force.copy(), self.contact.copy()
         return out
+
+    def set_step(self, common_step, init_done=1):
+        self.common_step, self.init_done = int(common_step), int(init_done)
 
     def set_task(self, **kw):
         for k, v in kw.items():
@@ -178,8 +214,37 @@ class CudaBackend:
                      timeout=_abi.TT_TIMEOUT, commands=_abi.TT_COMMANDS, actions=_abi.TT_ACTIONS, rand=_abi.TT_RAND_OVERRIDE)
         self.task = {k: self._tensor(v, task=True) for k, v in kinds.items()}
 
+    def terrain_create(self, cfg, height_samples=None, terrain_origins=None, heightfield=None):
+        hs = None if height_samples is None else np.ascontiguousarray(height_samples, np.int16)
+        og = None if terrain_origins is None else np.ascontiguousarray(terrain_origins, np.float32)
+        if heightfield is not None:
+            self._lib.check(self.lib.b2g_sim_add_heightfield(self.sim, C.byref(heightfield[0]),
+                                                             np.ascontiguousarray(heightfield[1], np.int16).ctypes.data_as(C.c_void_p)), "add_heightfield")
+        self._lib.check(self.lib.b2g_task_terrain_create(self.sim, C.byref(cfg), None if hs is None else hs.ctypes.data_as(C.c_void_p),
+                                                         None if og is None else og.ctypes.data_as(C.c_void_p)), "terrain create")
+        self.kind = "terrain"
+        kinds = dict(obs=_abi.TT_OBS, obs_clamped=_abi.TT_OBS_CLAMPED, rew=_abi.TT_REW, reset=_abi.TT_RESET, progress=_abi.TT_PROGRESS,
+                     timeout=_abi.TT_TIMEOUT, commands=_abi.TT_COMMANDS, actions=_abi.TT_ACTIONS, rand=_abi.TT_RAND_OVERRIDE, torques=_abi.TT_TORQUES,
+                     last_actions=_abi.TT_LAST_ACTIONS, last_dof_vel=_abi.TT_LAST_DOF_VEL, feet_air_time=_abi.TT_FEET_AIR_TIME,
+                     episode_sums=_abi.TT_EPISODE_SUMS, env_origins=_abi.TT_ENV_ORIGINS, terrain_levels=_abi.TT_TERRAIN_LEVELS,
+                     terrain_types=_abi.TT_TERRAIN_TYPES, noise=_abi.TT_NOISE_OVERRIDE, push=_abi.TT_PUSH_OVERRIDE, extras=_abi.TT_EXTRAS,
+                     measured=_abi.TT_MEASURED_HEIGHTS)
+        self.task = {k: self._tensor(v, task=True) for k, v in kinds.items()}
+        self.set_step(0, 1)
+
+    def set_step(self, common_step, init_done=1):
+        self._lib.check(self.lib.b2g_task_terrain_set_step(self.sim, int(common_step)))
+        self._lib.check(self.lib.b2g_task_terrain_set_init_done(self.sim, int(init_done)))
+
     def task_step(self, actions, draws=None, post_only=False):
-        self._draws(draws)
+        if getattr(self, "kind", "") == "terrain" and draws is not None:
+            self._put(self.task["rand"], np.asarray(draws["reset"], np.float32))
+            self._put(self.task["noise"], np.asarray(draws["noise"], np.float32))
+            self._put(self.task["push"], np.asarray(draws["push"], np.float32))
+            self._lib.check(self.lib.b2g_task_set_rand_override(self.sim, 1))
+            draws = "keep"
+        if draws != "keep":
+            self._draws(draws)
         fn = self.lib.b2g_task_post_only if post_only else self.lib.b2g_task_step
         self._lib.check(fn(self.sim, self._actions(actions), self.stream), "task step")
         self.torch.cuda.synchronize()
@@ -213,6 +278,9 @@ class CudaBackend:
     def get_task(self):
         nd, nb = self.art.num_dofs, self.art.num_bodies
         out = {k: self.task[k].cpu().numpy().copy() for k in TASK_KEYS}
+        if getattr(self, "kind", "") == "terrain":
+            out.update({k: self.task[k].cpu().numpy().copy() for k in TERRAIN_KEYS})
+            out["extras"] = self.task["extras"].cpu().numpy().copy()
         out["dof_force"] = self.t[_abi.T_DOF_FORCE].cpu().numpy().reshape(self.n, nd).copy()
         out["contact"] = self.t[_abi.T_NET_CONTACT].cpu().numpy().reshape(self.n, nb, 3).copy()
         return out

@@ -161,6 +161,69 @@ int emu_anymal(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props
     return 0;
 }
 
+// rough-terrain task: mode 1 = step, mode 2 = post_physics_step only.  ptrs: see TerrainArgs.
+struct EmuTerrainBufs {
+    float *root, *dof, *dof_force, *contact;
+    const float* actions_in;
+    float *obs, *obs_clamped, *rew;
+    long long *reset, *progress, *timeout;
+    float *commands, *actions, *torques, *last_actions, *last_dof_vel, *feet_air_time, *episode_sums, *env_origins;
+    long long *terrain_levels, *terrain_types;
+    const float* terrain_origins;
+    const short* height_samples;
+    float *scratch, *resetw, *report, *measured;
+    int* reset_count;
+    const float *reset_override, *noise_override, *push_override;
+    const float* friction;
+};
+
+int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, const b2g_heightfield* hf, const int16_t* hfs,
+                const b2g_terrain_cfg* cfg, int mode, int n_envs, long long common_step, int init_done, const EmuTerrainBufs* B) {
+    DevModel* dm = new DevModel;
+    const char* why;
+    if (pack_dev_model(*m, *dp, *dm, &why) != 0) { delete dm; return -1; }
+    SimArgs A;
+    A.M = dm;
+    pack_dev_params(*sp, hf, hfs, A.P);
+    A.n_envs = n_envs; A.root = B->root; A.dof = B->dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = B->dof_force;
+    A.contact = B->contact; A.friction = B->friction;
+    TerrainArgs T;
+    T.cfg = *cfg; T.actions_in = B->actions_in; T.obs = B->obs; T.obs_clamped = B->obs_clamped; T.rew = B->rew; T.reset = B->reset;
+    T.progress = B->progress; T.timeout = B->timeout; T.commands = B->commands; T.actions = B->actions; T.torques = B->torques;
+    T.last_actions = B->last_actions; T.last_dof_vel = B->last_dof_vel; T.feet_air_time = B->feet_air_time; T.episode_sums = B->episode_sums;
+    T.env_origins = B->env_origins; T.terrain_levels = B->terrain_levels; T.terrain_types = B->terrain_types; T.terrain_origins = B->terrain_origins;
+    T.height_samples = B->height_samples; T.scratch = B->scratch; T.resetw = B->resetw; T.report = B->report; T.measured = B->measured;
+    T.reset_count = B->reset_count; T.reset_override = B->reset_override; T.noise_override = B->noise_override; T.push_override = B->push_override;
+    T.common_step = common_step; T.init_done = init_done; T.post_only = (mode == 2); T.seed = cfg->seed;
+    const Variant v = pick(*m);
+    if (v.fixed) { delete dm; return -2; }
+    const bool HFm = hf && hfs;
+    for (int e = 0; e < n_envs; e++) {
+        std::vector<float> scratch((size_t)v.lanes * MAXC * CF_COUNT), bf((size_t)m->n_bodies * 3);
+        run_group(v.lanes, [&](int lane) {
+            ScratchStrided sc{scratch.data() + lane, v.lanes};
+            if (v.lanes == 4) { if (HFm) terrain_phys_thread<4, 3, true>(A, T, e, lane, true, sc, bf.data()); else terrain_phys_thread<4, 3, false>(A, T, e, lane, true, sc, bf.data()); }
+            else { if (HFm) terrain_phys_thread<8, 6, true>(A, T, e, lane, true, sc, bf.data()); else terrain_phys_thread<8, 6, false>(A, T, e, lane, true, sc, bf.data()); }
+        });
+    }
+    float cnorm = 0.0f;
+    if (cfg->custom_origins && cfg->curriculum && init_done) {
+        // same summation order as the kernel: 64 strided partial sums, then a pairwise tree
+        float red[64];
+        for (int t = 0; t < 64; t++) { float acc = 0; for (int i = t; i < n_envs; i += 64) acc += B->resetw[i]; red[t] = acc; }
+        for (int o = 32; o > 0; o >>= 1) for (int t = 0; t < o; t++) red[t] += red[t + o];
+        cnorm = sqrtf(red[0]);
+    }
+    for (int e = 0; e < n_envs; e++) {
+        run_group(v.lanes, [&](int lane) {
+            if (v.lanes == 4) terrain_post_thread<4, 3>(A, T, e, lane, true, cnorm);
+            else terrain_post_thread<8, 6>(A, T, e, lane, true, cnorm);
+        });
+    }
+    delete dm;
+    return 0;
+}
+
 // Cartpole: mode 1 = step, mode 2 = post_physics_step only
 int emu_cartpole(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, const b2g_cartpole_cfg* cfg, int mode,
                  int n_envs, float* root, float* dof, float* dof_force, float* contact, const float* actions_in, float* obs,

@@ -84,3 +84,30 @@ def cartpole(model, params, props, cfg, mode, bufs, actions, rand_override=None)
                             _p(bufs["obs_clamped"]), _p(bufs["rew"]), _p(bufs["reset"], C.c_longlong), _p(bufs["progress"], C.c_longlong),
                             _p(bufs["timeout"], C.c_longlong), _p(bufs["actions"]), _p(bufs["reset_count"], C.c_int), _p(ro))
     assert rc == 0, rc
+
+
+class _TerrainBufs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("root", "dof", "dof_force", "contact", "actions_in", "obs", "obs_clamped", "rew", "reset", "progress",
+                                          "timeout", "commands", "actions", "torques", "last_actions", "last_dof_vel", "feet_air_time",
+                                          "episode_sums", "env_origins", "terrain_levels", "terrain_types", "terrain_origins", "height_samples",
+                                          "scratch", "resetw", "report", "measured", "reset_count", "reset_override", "noise_override",
+                                          "push_override", "friction")]
+
+
+def terrain(model, params, props, cfg, mode, bufs, common_step, init_done, heightfield=None, hf_samples=None):
+    """mode 1 = step, 2 = post_physics_step only.  bufs: dict name -> numpy array (or None) for every _TerrainBufs field."""
+    tb = _TerrainBufs()
+    keep = []
+    for k, _ in _TerrainBufs._fields_:
+        a = bufs.get(k)
+        if a is None:
+            setattr(tb, k, None)
+        else:
+            assert a.flags["C_CONTIGUOUS"], k
+            keep.append(a)
+            setattr(tb, k, a.ctypes.data)
+    n = bufs["root"].shape[0]
+    hs = None if hf_samples is None else np.ascontiguousarray(hf_samples, dtype=np.int16)
+    rc = lib().emu_terrain(C.byref(model), C.byref(params), C.byref(props), C.byref(heightfield) if heightfield is not None else None,
+                           _p(hs, C.c_int16), C.byref(cfg), C.c_int(mode), C.c_int(n), C.c_longlong(common_step), C.c_int(init_done), C.byref(tb))
+    assert rc == 0, rc

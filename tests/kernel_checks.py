@@ -403,3 +403,200 @@ def check_cartpole_step(make_backend, n=32, steps=60, seed=5):
     finally:
         be.close()
     assert resets > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# rough-terrain tasks
+# ------------------------------------------------------------------------------------------------
+def terrain_params():
+    sp = flat_params(dt=0.005, substeps=1)
+    return sp
+
+
+def terrain_cfg_struct(cfg, nd=12, seed=42):
+    """oracle cfg dict (tests/test_oracle_terrain.terrain_case) -> C b2g_terrain_cfg."""
+    c = _abi.TerrainCfg()
+    c.lin_vel_scale, c.ang_vel_scale, c.dof_pos_scale, c.dof_vel_scale = cfg["lin_vel_scale"], cfg["ang_vel_scale"], cfg["dof_pos_scale"], cfg["dof_vel_scale"]
+    c.height_meas_scale, c.action_scale = cfg["height_meas_scale"], 0.5
+    c.kp, c.kd, c.torque_limit = 80.0, 2.0, 80.0
+    c.decimation, c.extra_sim_steps, c.dt = 4, 1, cfg["dt"]
+    for i, v in enumerate(cfg["rew_scales"]):
+        c.rew[i] = float(v)
+    c.base_height_target = cfg["base_height_target"]
+    c.clip_obs, c.clip_actions = 3.0e38, 3.0e38
+    for i in range(2):
+        c.cmd_x[i], c.cmd_y[i], c.cmd_yaw[i] = cfg["cmd_x"][i], cfg["cmd_y"][i], cfg["cmd_yaw"][i]
+    for i, v in enumerate(cfg["default_dof_pos"]):
+        c.default_dof_pos[i] = float(v)
+    for i, v in enumerate(cfg["init_root"]):
+        c.init_root[i] = float(v)
+    nv = cfg.get("noise_scale_vec")
+    c.add_noise = 0 if nv is None else 1
+    if nv is not None:
+        c.noise_lin_vel, c.noise_ang_vel, c.noise_gravity = float(nv[0]), float(nv[3]), float(nv[6])
+        c.noise_dof_pos, c.noise_dof_vel, c.noise_height = float(nv[12]), float(nv[24]), float(nv[36])
+    c.base_body = int(cfg["base_body"])
+    c.n_knee, c.n_feet = len(cfg["knee"]), len(cfg["feet"])
+    for i, k in enumerate(cfg["knee"]):
+        c.knee_bodies[i] = int(k)
+    for i, k in enumerate(cfg["feet"]):
+        c.feet_bodies[i] = int(k)
+    c.hound_termination = 1 if cfg.get("hound") else 0
+    extra = list(cfg.get("base_indices", []))
+    c.n_term_extra = len(extra)
+    for i, k in enumerate(extra):
+        c.term_extra_bodies[i] = int(k)
+    c.allow_knee_contacts = 1 if cfg["allow_knee"] else 0
+    for i, d in enumerate([0, 3, 6, 9]):
+        c.hip_dofs[i] = d
+    c.max_episode_length = int(cfg["max_len"])
+    c.push_interval = int(cfg.get("push_interval", 750))
+    c.max_episode_length_s = float(cfg["max_episode_length_s"])
+    c.custom_origins, c.curriculum = int(cfg["custom_origins"]), int(cfg["curriculum"])
+    c.n_hx, c.n_hy = len(tm.HEIGHT_X), len(tm.HEIGHT_Y)
+    for i, v in enumerate(tm.HEIGHT_X):
+        c.hx[i] = float(v)
+    for i, v in enumerate(tm.HEIGHT_Y):
+        c.hy[i] = float(v)
+    t = cfg.get("terrain")
+    if t:
+        c.hs_rows, c.hs_cols = t["height_samples"].shape
+        c.border_size, c.hscale, c.vscale, c.env_length = t["border_size"], t["hscale"], t["vscale"], t["env_length"]
+        c.env_rows, c.env_cols = t["terrain_origins"].shape[0], t["terrain_origins"].shape[1]
+    c.seed = seed
+    return c
+
+
+def check_terrain_golden(make_backend, name):
+    """post_physics_step of the terrain tasks through the two kernels vs the reference's own outputs (golden vectors made by
+    executing the reference's eager methods): 1e-5 relative, masks / counters / curriculum levels bit-exact."""
+    from tests.test_oracle_terrain import check_terrain_outputs, terrain_case
+
+    g, st, cfg, draws = terrain_case(name)
+    robot = "hound" if "hound" in name else "anymal_minimal"
+    art = load_robot(robot)
+    n = st["root"].shape[0]
+    cfg["push_interval"] = int(g["push_interval"])
+    c = terrain_cfg_struct(cfg)
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    be = make_backend(art, terrain_params(), props, n)
+    try:
+        t = cfg.get("terrain")
+        be.terrain_create(c, t["height_samples"] if t else None, t["terrain_origins"] if t else None)
+        be.set_step(int(g["common_step_counter"]) + 1, 1)
+        be.set_state(st["root"], np.stack([st["dof_pos"], st["dof_vel"]], axis=2))
+        kw = dict(commands=st["commands"], progress=st["progress"], timeout=st["timeout_prev"].astype(np.int64), torques=st["torques"],
+                  last_actions=st["last_actions"], last_dof_vel=st["last_dof_vel"], feet_air_time=st["feet_air_time"], episode_sums=st["episode_sums"],
+                  contact=st["contact"], reset=np.zeros(n, np.int64))
+        if cfg["custom_origins"]:
+            kw.update(env_origins=st["env_origins"], terrain_levels=st["terrain_levels"], terrain_types=st["terrain_types"])
+        be.set_task(**kw)
+        be.task_step(st["actions"], draws, post_only=True)
+        out = be.get_task()
+        root, dof = be.get_state()
+    finally:
+        be.close()
+    res = dict(root=root, dof_pos=dof[:, :, 0], dof_vel=dof[:, :, 1], commands=out["commands"], last_actions=out["last_actions"],
+               last_dof_vel=out["last_dof_vel"], feet_air_time=out["feet_air_time"], episode_sums=out["episode_sums"], progress=out["progress"])
+    if cfg["custom_origins"]:
+        res.update(terrain_levels=out["terrain_levels"], env_origins=out["env_origins"])
+    extras = out["extras"][:14] if "extras" in out else None
+    if extras is not None and not cfg["custom_origins"]:
+        extras[13] = g["o_extras"][13]
+    check_terrain_outputs(g, res, out["obs"], out["rew"], out["reset"], out["timeout"], out["measured"], extras)
+
+
+def check_terrain_step(make_backend, robot="anymal_minimal", n=8, steps=12, seed=11, heightfield=True):
+    """Whole step of the terrain task (4 PD sim steps + 1 stale, post_physics_step) vs the oracle composition: float32 dynamics
+    oracle + numpy task math in the reference's order, same injected draws, on a generated heightfield with curriculum."""
+    from isaacgymenv_b200.terrain import Terrain
+
+    art = load_robot(robot)
+    nd, nb = art.num_dofs, art.num_bodies
+    rng = np.random.default_rng(seed)
+    sp = terrain_params()
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    m = _abi.pack_model(art)
+    hound = robot == "hound"
+    knee = [i for i, b in enumerate(art.body_names) if ("thigh" if hound else "THIGH") in b]
+    feet = [i for i, b in enumerate(art.body_names) if ("foot" if hound else "SHANK") in b]
+    terrain = hf = hf_t = None
+    if heightfield:
+        tcfg = dict(terrainType="trimesh", curriculum=True, mapLength=8.0, mapWidth=8.0, numLevels=3, numTerrains=4,
+                    terrainProportions=[0.1, 0.1, 0.35, 0.25, 0.2], slopeTreshold=0.5)
+        tr = Terrain(tcfg, n, seed=3)
+        terrain = dict(height_samples=tr.heightsamples, border_size=float(tr.border_size), hscale=tr.horizontal_scale, vscale=tr.vertical_scale,
+                       env_length=tr.env_length, env_rows=tr.env_rows, terrain_origins=tr.env_origins.astype(np.float32))
+        hf_t = _abi.Heightfield(rows=tr.tot_rows, cols=tr.tot_cols, horizontal_scale=tr.horizontal_scale, vertical_scale=tr.vertical_scale,
+                                origin_x=-tr.border_size, origin_y=-tr.border_size, friction=1.0, restitution=0.0)
+        hf = (hf_t, tr.heightsamples)
+    dt = 0.02
+    raw = np.array([-1.0, 1.0, -4.0, 0.5, -0.05, -0.2, -0.00002, -0.0005, -0.5, 1.0, -0.25, -0.1, -0.01, -0.05], np.float32) * np.float32(dt)
+    nv = np.zeros(12 + 2 * nd + 140 + nd, np.float32)
+    nv[:3], nv[3:6], nv[6:9], nv[12:24], nv[24:36], nv[36:176] = 0.2, 0.05, 0.05, 0.01, 0.075, 0.3
+    cfg = dict(rew_scales=raw, knee=np.array(knee), feet=np.array(feet), base_indices=np.array([i for i, b in enumerate(art.body_names) if "shoulder" in b]),
+               base_body=0, allow_knee=not hound and False, hound=hound, base_height_target=0.48 if hound else 0.52, noise_scale_vec=nv, dt=dt, max_len=9,
+               push=False, default_dof_pos=default_pose(art).astype(np.float32), init_root=np.array([0, 0, 0.62, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0], np.float32),
+               cmd_x=[-1, 1], cmd_y=[-1, 1], cmd_yaw=[-3.14, 3.14], custom_origins=heightfield, curriculum=True, terrain=terrain,
+               max_episode_length_s=20.0, lin_vel_scale=2.0, ang_vel_scale=0.25, dof_pos_scale=1.0, dof_vel_scale=0.05, height_meas_scale=5.0,
+               push_interval=5)
+    c = terrain_cfg_struct(cfg)
+    be = make_backend(art, sp, props, n)
+    resets = 0
+    try:
+        be.terrain_create(c, terrain["height_samples"] if terrain else None, terrain["terrain_origins"] if terrain else None, heightfield=hf)
+        # start on the terrain origins, standing
+        root, dof = standing_state(art, n, rng, 0.6)
+        st = dict(root=root, dof_pos=dof[:, :, 0].copy(), dof_vel=dof[:, :, 1].copy(), contact=np.zeros((n, nb, 3), np.float32), torques=np.zeros((n, nd), np.float32),
+                  commands=np.zeros((n, 4), np.float32), actions=np.zeros((n, nd), np.float32), last_actions=np.zeros((n, nd), np.float32),
+                  last_dof_vel=np.zeros((n, nd), np.float32), feet_air_time=np.zeros((n, 4), np.float32), progress=np.zeros(n, np.int64),
+                  timeout_prev=np.zeros(n, bool), episode_sums=np.zeros((13, n), np.float32), terrain_levels=(np.arange(n) % 3).astype(np.int64),
+                  terrain_types=(np.arange(n) % 4).astype(np.int64))
+        st["commands"][:, 0], st["commands"][:, 3] = 0.7, 0.5
+        if heightfield:
+            st["env_origins"] = terrain["terrain_origins"][st["terrain_levels"], st["terrain_types"]].copy()
+            st["root"][:, :3] += st["env_origins"]
+            be.set_task(env_origins=st["env_origins"], terrain_levels=st["terrain_levels"], terrain_types=st["terrain_types"])
+        else:
+            st["env_origins"] = np.zeros((n, 3), np.float32)
+            st["terrain_levels"][:] = 0
+            st["terrain_types"][:] = 0
+        be.set_state(st["root"], np.stack([st["dof_pos"], st["dof_vel"]], axis=2))
+        be.set_task(commands=st["commands"], reset=np.zeros(n, np.int64))
+        for k in range(steps):
+            step = k + 1
+            actions = rng.uniform(-1, 1, (n, nd)).astype(np.float32)
+            draws = dict(reset=rng.uniform(0, 1, (n, 2 * nd + 5)).astype(np.float32), noise=rng.uniform(0, 1, (n, len(nv))).astype(np.float32),
+                         push=rng.uniform(0, 1, (n, 2)).astype(np.float32))
+            be.set_step(step, 1)
+            be.task_step(actions, draws)
+            # oracle: decimation loop + extra sim step
+            st["actions"] = actions.copy()
+            dofs = np.stack([st["dof_pos"], st["dof_vel"]], axis=2).astype(np.float32)
+            for it in range(5):
+                if it < 4:
+                    tq = np.clip(np.float32(80.0) * (np.float32(0.5) * actions + cfg["default_dof_pos"][None] - dofs[:, :, 0]) - np.float32(2.0) * dofs[:, :, 1], -80, 80).astype(np.float32)
+                f, cf = O.simulate(m, sp, props, st["root"], dofs, np.zeros((n, nd), np.float32), tq, heightfield=hf_t, hf_samples=hf[1] if hf else None)
+            st["dof_pos"], st["dof_vel"], st["torques"], st["contact"] = dofs[:, :, 0].copy(), dofs[:, :, 1].copy(), tq, cf
+            cfg["push"] = step % cfg["push_interval"] == 0
+            obs, rew, reset, timeout, measured, extras = tm.terrain_post_physics(st, cfg, draws)
+            st["timeout_prev"] = timeout.astype(bool)
+            rk, dk = be.get_state()
+            t = be.get_task()
+            assert np.array_equal(t["reset"], reset), f"step {k}: reset decisions differ"
+            assert np.array_equal(t["progress"], st["progress"]) and np.array_equal(t["timeout"], timeout)
+            assert np.abs(rk - st["root"]).max() < 3e-3, f"step {k}: root deviates {np.abs(rk - st['root']).max():.2e}"
+            assert np.abs(dk[:, :, 0] - st["dof_pos"]).max() < 5e-3
+            np.testing.assert_allclose(t["obs"], obs, rtol=0, atol=3e-2)
+            np.testing.assert_allclose(t["rew"], rew, rtol=0, atol=2e-3)
+            np.testing.assert_allclose(t["measured"], measured, rtol=0, atol=0.051)     # a sample may fall in the neighbouring 0.1 m cell
+            assert np.array_equal(t["terrain_levels"], st["terrain_levels"])
+            np.testing.assert_allclose(t["commands"], st["commands"], rtol=0, atol=2e-3)
+            np.testing.assert_allclose(t["feet_air_time"], st["feet_air_time"], rtol=0, atol=1e-6)
+            # keep the oracle glued to the kernel state so that tolerances do not accumulate over steps
+            st["root"], st["dof_pos"], st["dof_vel"] = rk.copy(), dk[:, :, 0].copy(), dk[:, :, 1].copy()
+            st["commands"], st["last_dof_vel"], st["episode_sums"] = t["commands"].copy(), t["last_dof_vel"].copy(), t["episode_sums"].copy()
+            resets += int(reset.sum())
+    finally:
+        be.close()
+    assert resets > 0

@@ -44,3 +44,13 @@ def test_cartpole_golden():
 
 def test_cartpole_step():
     kc.check_cartpole_step(make)
+
+
+@pytest.mark.parametrize("name", ["anymal_terrain_plane.npz", "anymal_terrain_trimesh.npz", "hound_terrain_plane.npz"])
+def test_terrain_golden(name):
+    kc.check_terrain_golden(make, name)
+
+
+@pytest.mark.parametrize("robot,heightfield", [("anymal_minimal", True), ("hound", False)])
+def test_terrain_step(robot, heightfield):
+    kc.check_terrain_step(make, robot, n=64, heightfield=heightfield)

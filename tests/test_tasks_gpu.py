@@ -92,3 +92,35 @@ def test_gym_tensor_api_indexed_sets():
     torch.cuda.synchronize()
     np.testing.assert_allclose(rb[:, 0, :7].cpu().numpy(), env.root_states[:, :7].cpu().numpy(), atol=1e-6)
     assert float(rb[0, 3, 2]) < float(rb[0, 0, 2])          # shank body origin sits below the base
+
+
+@pytest.mark.parametrize("task,terrain", [("AnymalTerrain", "plane"), ("AnymalTerrain", "trimesh"), ("HoundTerrain", "plane")])
+def test_terrain_task_contract(task, terrain):
+    import torch
+
+    import isaacgymenv_b200 as b2g
+
+    n = 64
+    over = {"env": {"terrain": {"terrainType": terrain, "numLevels": 3, "numTerrains": 4}}}
+    env = b2g.make(seed=3, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=over)
+    assert env.num_obs == 188 and env.num_acts == 12 and env.max_episode_length == 1000 and env.push_interval == 750
+    assert env.commands.shape == (n, 4) and env.feet_air_time.shape == (n, 4) and env.torques.shape == (n, 12)
+    z0 = env.root_states[:, 2].clone()
+    if terrain == "trimesh":
+        assert env.height_samples.shape == (3 * 80 + 400, 4 * 80 + 400)
+        assert torch.allclose(env.root_states[:, 2], 0.62 + env.env_origins[:, 2])
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    rews = []
+    for k in range(60):
+        obs, rew, reset, extras = env.step(2 * torch.rand(n, 12, device="cuda:0", generator=g) - 1)
+        rews.append(rew.clone())
+    assert obs["obs"].shape == (n, 188) and torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all()
+    assert reset.dtype == torch.bool and extras["time_outs"].dtype == torch.bool          # terrain tasks hand out bool masks
+    assert set(extras["episode"]) >= {"rew_lin_vel_xy", "rew_air_time", "terrain_level"}
+    assert env.common_step_counter == 60 and int(env.progress_buf.max()) <= 60
+    assert float(torch.stack(rews).max()) > 0.0
+    # the robots came down onto their feet / the ground: somebody is in contact
+    assert float(env.contact_forces[:, env.feet_indices, 2].max()) > 50.0
+    assert bool((env.root_states[:, 2] < z0 + 0.05).all())
+    if terrain == "trimesh":
+        assert float(env.measured_heights.abs().max()) > 0.0
