@@ -242,8 +242,7 @@ class CudaBackend:
             self._put(self.task["noise"], np.asarray(draws["noise"], np.float32))
             self._put(self.task["push"], np.asarray(draws["push"], np.float32))
             self._lib.check(self.lib.b2g_task_set_rand_override(self.sim, 1))
-            draws = "keep"
-        if draws != "keep":
+        else:
             self._draws(draws)
         fn = self.lib.b2g_task_post_only if post_only else self.lib.b2g_task_step
         self._lib.check(fn(self.sim, self._actions(actions), self.stream), "task step")
