@@ -312,6 +312,9 @@ def terrain_post_physics(st, cfg, draws):
     r_jacc = np.sum(np.square(st["last_dof_vel"] - st["dof_vel"]), axis=1) * rs["joint_acc"]
     knee_contact = np.linalg.norm(cf[:, cfg["knee"], :], axis=2) > 1.0
     r_coll = np.sum(knee_contact, axis=1).astype(f) * rs["collision"]
+    if cfg.get("arm"):      # useful_hound.py:524-525: contacts on the `baseName` bodies are penalised as well
+        base_contact = np.linalg.norm(cf[:, cfg["base_indices"], :], axis=2) > 1.0
+        r_coll = r_coll + np.sum(base_contact, axis=1).astype(f) * rs["collision"]
     stumble = (np.linalg.norm(cf[:, cfg["feet"], :2], axis=2) > 5.0) & (np.abs(cf[:, cfg["feet"], 2]) < 1.0)
     r_stumble = np.sum(stumble, axis=1).astype(f) * rs["stumble"]
     r_arate = np.sum(np.square(st["last_actions"] - st["actions"]), axis=1) * rs["action_rate"]
@@ -354,6 +357,12 @@ def terrain_post_physics(st, cfg, draws):
             col = 26
         else:
             st["root"][ids] = cfg["init_root"].astype(f)[None]
+        if cfg.get("arm"):      # useful_hound.py:594-602: arm joints <- clamp(default + noise * 2 (u - 0.5)), zero velocity
+            a = cfg["arm"]
+            ua = u[:, col:col + 6]
+            st["arm_q"][ids] = np.clip(f(0.0) + f(a["dof_noise"]) * f(2.0) * (ua - f(0.5)), a["lower"].astype(f)[None], a["upper"].astype(f)[None])
+            st["arm_qd"][ids] = 0.0
+            col += 6
         st["commands"][ids, 0] = torch_rand_float(f(cfg["cmd_x"][0]), f(cfg["cmd_x"][1]), u[:, col])
         st["commands"][ids, 1] = torch_rand_float(f(cfg["cmd_y"][0]), f(cfg["cmd_y"][1]), u[:, col + 1])
         st["commands"][ids, 3] = torch_rand_float(f(cfg["cmd_yaw"][0]), f(cfg["cmd_yaw"][1]), u[:, col + 2])
@@ -374,9 +383,31 @@ def terrain_post_physics(st, cfg, draws):
     obs = np.concatenate([base_lin * f(cfg["lin_vel_scale"]), base_ang * f(cfg["ang_vel_scale"]), pg,
                           st["commands"][:, :3] * np.array([cfg["lin_vel_scale"], cfg["lin_vel_scale"], cfg["ang_vel_scale"]], f),
                           st["dof_pos"] * f(cfg["dof_pos_scale"]), st["dof_vel"] * f(cfg["dof_vel_scale"]), heights, st["actions"]], axis=-1).astype(f)
+    if cfg.get("arm"):      # useful_hound.py:482-497: + end-effector position, orientation (never-refreshed tensor, quirk Q12), arm command
+        obs = np.concatenate([obs, st["eef_state"][:, :3], st["eef_state"][:, 3:7], st["arm_commands"]], axis=-1).astype(f)
     if cfg.get("noise_scale_vec") is not None:
         obs = obs + (f(2) * draws["noise"].astype(f) - f(1)) * cfg["noise_scale_vec"].astype(f)[None]
     st["last_actions"][:] = st["actions"]
     st["last_dof_vel"][:] = st["dof_vel"]
     timeout = ((st["progress"] >= cfg["max_len"] - 1) & reset).astype(np.int64)
     return obs.astype(f), rew.astype(f), reset.astype(np.int64), timeout, measured, extras
+
+
+def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp=150.0, kp_null=10.0, effort=1000.0):
+    """tasks/useful_hound.py:660-691 (_compute_osc_torques): operational-space control of the 6-DOF arm.  ``mm`` (N,6,6) arm block of the
+    mass matrix, ``j_eef`` (N,6,6) the Jacobian slice the task takes, ``dpose`` (N,6), ``eef_vel`` (N,6), ``q``/``qd`` (N,6)."""
+    f = np.float32
+    kp_v = np.full(6, kp, f)
+    kd_v = (f(2) * np.sqrt(kp_v)).astype(f)
+    kpn = np.full(6, kp_null, f)
+    kdn = (f(2) * np.sqrt(kpn)).astype(f)
+    mm_inv = np.linalg.inv(mm.astype(np.float64)).astype(f)
+    jt = np.transpose(j_eef, (0, 2, 1))
+    m_eef_inv = j_eef @ mm_inv @ jt
+    m_eef = np.linalg.inv(m_eef_inv.astype(np.float64)).astype(f)
+    u = jt @ m_eef @ (kp_v * dpose - kd_v * eef_vel)[..., None]
+    j_eef_inv = m_eef @ j_eef @ mm_inv
+    u_null = kdn * -qd + kpn * (np.mod(f(0.0) - q + f(np.pi), f(2 * np.pi)) - f(np.pi))      # python-style remainder (eager torch %)
+    u_null = mm @ u_null[..., None]
+    u = u + (np.eye(6, dtype=f)[None] - jt @ j_eef_inv) @ u_null
+    return np.clip(u[..., 0], -effort, effort).astype(f)

@@ -293,3 +293,111 @@ def gen_all_terrain():
 
 if __name__ == "__main__" and ("--terrain" in sys.argv or globals().get("_run_terrain_after")):
     gen_all_terrain()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# UsefulHound (hound + arm): post_physics_step and the operational-space torque law, executed from the reference
+# (tasks/useful_hound.py:660-691, :727-760) on an attribute bag.
+# ------------------------------------------------------------------------------------------------------------------
+def gen_useful_hound(out):
+    mod = ref_loader.load("tasks.useful_hound")
+    n, nb = 64, 24
+    knee, feet, base_indices = [2, 6, 10, 14], [4, 8, 12, 16], [1, 5, 9, 13]
+    b, keys = _terrain_bag(mod, "UsefulHound", n, nb, "plane", 0.11, knee, feet, base_indices)
+    b.num_actions = 18
+    b.total_num_dof, b.hound_num_dof, b.arm_num_dof = 18, 12, 6
+    b.dof_state = torch.zeros(n, 18, 2)
+    b.dof_state[:, :12, 0] = b.dof_pos
+    b.dof_state[:, :12, 1] = b.dof_vel
+    b.dof_state[:, 12:, 0] = sinfill((n, 6), 0.33, 0.7, 1.2)
+    b.dof_state[:, 12:, 1] = sinfill((n, 6), 0.47, 0.2, 1.5)
+    b.hound_dof_pos, b.hound_dof_vel = b.dof_state[:, 0:12, 0], b.dof_state[:, 0:12, 1]
+    b._q, b._qd = b.dof_state[:, 12:, 0], b.dof_state[:, 12:, 1]
+    b.last_hound_dof_vel = b.last_dof_vel.clone()
+    b.hound_default_dof_pos = b.default_dof_pos.clone()
+    b.houndarm_default_dof_pos = torch.zeros(6)
+    b.houndarm_dof_noise = 0.25
+    b.houndarm_dof_lower_limits = torch.full((6,), -1.57)
+    b.houndarm_dof_upper_limits = torch.full((6,), 1.57)
+    b._houndarm_effort_limits = torch.full((6,), 1000.0)
+    b._pos_control = torch.zeros(n, 6)
+    b._effort_control = torch.zeros(n, 6)
+    b.arm_commands = torch.zeros(n, 3)
+    b.arm_kp = torch.full((6,), 150.0)
+    b.arm_kd = 2 * torch.sqrt(b.arm_kp)
+    b.arm_kp_null = torch.full((6,), 10.0)
+    b.arm_kd_null = 2 * torch.sqrt(b.arm_kp_null)
+    b.actions = sinfill((n, 18), 0.77, 1.1)
+    b.last_actions = b.actions + sinfill((n, 18), 0.71, 0.4, 0.3)
+    b.torques = sinfill((n, 18), 0.43, 0.6, 12.0)
+    b.obs_buf = torch.zeros(n, 204)
+    nv = torch.zeros(204)
+    nv[:188] = b.noise_scale_vec
+    b.noise_scale_vec = nv
+    b._eef_state = sinfill((n, 13), 0.21, 0.9)          # never-refreshed rigid-body rows (quirk Q12): arbitrary but fixed here
+    b.episode_sums = {k: sinfill((n,), 0.31 + 0.01 * i, 0.2) for i, k in enumerate(keys)}
+    # --- OSC torque law ---
+    mm = sinfill((n, 6, 6), 0.37, 0.3, 0.2)
+    b._mm = mm @ mm.transpose(1, 2) + 0.5 * torch.eye(6)
+    r = sinfill((n, 3), 0.59, 0.1, 0.4)
+    jj = torch.zeros(n, 6, 6)
+    jj[:, :3, :3] = torch.eye(3)
+    jj[:, 3:, 3:] = torch.eye(3)
+    jj[:, 0, 4], jj[:, 0, 5], jj[:, 1, 3], jj[:, 1, 5], jj[:, 2, 3], jj[:, 2, 4] = r[:, 2], -r[:, 1], -r[:, 2], r[:, 0], r[:, 1], -r[:, 0]
+    b._j_eef = jj
+    dpose = sinfill((n, 6), 0.83, 0.4) * torch.tensor([[0.1, 0.1, 0.1, 0.5, 0.5, 0.5]])
+    u = mod.UsefulHound._compute_osc_torques(b, dpose)
+    osc = dict(osc_mm=b._mm.numpy().copy(), osc_j=jj.numpy().copy(), osc_dpose=dpose.numpy().copy(), osc_eef_vel=b._eef_state[:, 7:].numpy().copy(),
+               osc_q=b._q.numpy().copy(), osc_qd=b._qd.numpy().copy(), osc_u=u.numpy().copy())
+    # --- post_physics_step ---
+    b.common_step_counter = 5
+    csc_before = 5
+    reset_draws = sinfill((n, 35), 0.173, 0.05).abs() * 0.999
+    noise_draws = sinfill((n, 204), 0.0917, 0.33).abs() * 0.999
+    push_draws = sinfill((n, 2), 0.61, 0.21).abs() * 0.999
+    state = {"col": 0}
+
+    def fake_rand_float(lower, upper, shape, device):
+        ids = b._cur_ids
+        if b._draw_col is None:
+            uu = push_draws[ids]
+        else:
+            c0 = b._draw_col
+            uu = reset_draws[ids][:, c0:c0 + shape[1]]
+            b._draw_col += shape[1]
+        return (upper - lower) * uu + lower
+
+    def fake_rand(shape, device=None):
+        c0 = b._draw_col
+        uu = reset_draws[b._cur_ids][:, c0:c0 + shape[1]]
+        b._draw_col += shape[1]
+        return uu.clone()
+
+    mod.torch_rand_float = fake_rand_float
+    real_rand_like, real_rand = torch.rand_like, torch.rand
+    torch.rand_like = lambda t: noise_draws.clone()
+    torch.rand = fake_rand
+    inputs = dict(root=b.root_states.clone(), dof_state=b.dof_state.clone(), contact=b.contact_forces.clone(), torques=b.torques.clone(),
+                  commands=b.commands.clone(), actions=b.actions.clone(), last_actions=b.last_actions.clone(), last_dof_vel=b.last_hound_dof_vel.clone(),
+                  feet_air_time=b.feet_air_time.clone(), progress=b.progress_buf.clone(), timeout_prev=b.timeout_buf.clone(), default=b.hound_default_dof_pos.clone(),
+                  episode_sums=torch.stack([b.episode_sums[k] for k in keys]).clone(), eef_state=b._eef_state.clone())
+    try:
+        mod.UsefulHound.post_physics_step(b)
+    finally:
+        torch.rand_like, torch.rand = real_rand_like, real_rand
+    timeout = (b.progress_buf >= b.max_episode_length - 1) & (b.reset_buf != 0)
+    outs = dict(o_root=b.root_states, o_dof_state=b.dof_state, o_commands=b.commands, o_obs=b.obs_buf, o_rew=b.rew_buf, o_reset=b.reset_buf.to(torch.int64),
+                o_progress=b.progress_buf, o_timeout=timeout.to(torch.int64), o_last_actions=b.last_actions, o_last_dof_vel=b.last_hound_dof_vel,
+                o_feet_air_time=b.feet_air_time, o_episode_sums=torch.stack([b.episode_sums[k] for k in keys]), o_measured_heights=b.measured_heights,
+                o_extras=torch.tensor([float(b.extras["episode"]["rew_" + k]) for k in keys] + [float(b.extras["episode"]["terrain_level"])]))
+    meta = dict(knee=np.array(knee), feet=np.array(feet), base_indices=np.array(base_indices),
+                rew_scales=np.array([b.rew_scales[k] for k in ["termination", "lin_vel_xy", "lin_vel_z", "ang_vel_z", "ang_vel_xy", "orient", "torque", "joint_acc",
+                                                                 "base_height", "air_time", "collision", "stumble", "action_rate", "hip"]], dtype=np.float32),
+                noise_scale_vec=b.noise_scale_vec.numpy(), reset_draws=reset_draws.numpy(), noise_draws=noise_draws.numpy(), push_draws=push_draws.numpy(),
+                common_step_counter=np.array(csc_before), push_interval=np.array(b.push_interval), max_len=np.array(b.max_episode_length), dt=np.float32(b.dt))
+    np.savez_compressed(out, **{k: v.numpy() for k, v in inputs.items()}, **{k: v.numpy() for k, v in outs.items()}, **meta, **osc)
+    print(out, "resets", int(b.reset_buf.sum()), "rew range", float(b.rew_buf.min()), float(b.rew_buf.max()), "osc |u| max", float(u.abs().max()))
+
+
+if __name__ == "__main__" and ("--useful" in sys.argv or globals().get("_run_terrain_after")):
+    gen_useful_hound(os.path.join(HERE, "useful_hound_plane.npz"))
