@@ -272,6 +272,16 @@ typedef struct b2g_terrain_cfg {
     float border_size, hscale, vscale, env_length;
     int32_t env_rows, env_cols;      /* terrain levels x terrain types                                            */
     uint64_t seed;
+    /* hound + manipulator arm (reference: tasks/useful_hound.py). n_ctrl_dof = PD-controlled leg DOFs (observed, :482-497);
+     * the DOFs of chain `arm_chain` are driven by the operational-space torque law (:660-691) from action columns
+     * [n_ctrl_dof, n_ctrl_dof+6). arm_chain < 0: no arm (AnymalTerrain / HoundTerrain). */
+    int32_t n_ctrl_dof;
+    int32_t arm_chain;
+    float arm_kp, arm_kp_null, arm_action_scale, arm_dof_noise;
+    float arm_cmd_limit[6];
+    int32_t eef_body;                /* body whose state fills obs[..+7] (:440-447)                               */
+    int32_t jac_body;                /* row of the Jacobian tensor the task slices (:448-451)                     */
+    int32_t refresh_eef;             /* 0: replicate the reference (end-effector state is never refreshed) */
 } b2g_terrain_cfg;
 /* height_samples (hs_rows*hs_cols int16) and terrain_origins (env_rows*env_cols*3 f32) are host arrays (NULL for a plane) */
 int b2g_task_terrain_create(b2g_sim* sim, const b2g_terrain_cfg* cfg, const int16_t* height_samples_host, const float* terrain_origins_host);
@@ -283,6 +293,9 @@ int b2g_task_terrain_set_init_done(b2g_sim* sim, int init_done);
 /* task-generic entry points (dispatch on the task created on this sim) */
 int b2g_task_step(b2g_sim* sim, const float* actions_dev, void* stream);          /* VecTask.step, one launch   */
 int b2g_task_post_only(b2g_sim* sim, const float* actions_dev, void* stream);     /* post_physics_step only     */
+/* parity-test entry of the hound+arm task: evaluate the operational-space torque law once on the ARM_MM / ARM_JAC / EEF_STATE
+ * tensors and the current arm DOF state; the 6 torques land in the arm columns of the TORQUES tensor */
+int b2g_task_osc_probe(b2g_sim* sim, const float* actions_dev, void* stream);
 int b2g_task_step_host(b2g_sim* sim, const float* actions_host, float* obs_host, float* rew_host, int64_t* reset_host,
                        int64_t* timeout_host, void* stream);                      /* host buffers, synchronises */
 /* allocate-and-describe the task buffers the sim owns (obs_buf, rew_buf, reset_buf, ...) */
@@ -292,7 +305,9 @@ enum b2g_task_tensor_kind {
     /* rough-terrain tasks */
     B2G_TT_TORQUES = 9, B2G_TT_LAST_ACTIONS = 10, B2G_TT_LAST_DOF_VEL = 11, B2G_TT_FEET_AIR_TIME = 12, B2G_TT_EPISODE_SUMS = 13,
     B2G_TT_ENV_ORIGINS = 14, B2G_TT_TERRAIN_LEVELS = 15, B2G_TT_TERRAIN_TYPES = 16, B2G_TT_NOISE_OVERRIDE = 17, B2G_TT_PUSH_OVERRIDE = 18,
-    B2G_TT_EXTRAS = 19, B2G_TT_MEASURED_HEIGHTS = 20, B2G_TT_COUNT
+    B2G_TT_EXTRAS = 19, B2G_TT_MEASURED_HEIGHTS = 20,
+    /* hound + arm */
+    B2G_TT_ARM_MM = 21, B2G_TT_ARM_JAC = 22, B2G_TT_EEF_STATE = 23, B2G_TT_ARM_COMMANDS = 24, B2G_TT_COUNT
 };
 int b2g_task_tensor(b2g_sim* sim, int kind, b2g_tensor_desc* out);
 /* reset_idx(all envs) as in the task constructor (tasks/anymal.py:146) + first observations */

@@ -32,6 +32,9 @@ def task_map():
 
         m["AnymalTerrain"] = AnymalTerrain
         m["HoundTerrain"] = HoundTerrain
+        from .tasks.useful_hound import UsefulHound
+
+        m["UsefulHound"] = UsefulHound
     except ImportError:
         pass
     return m

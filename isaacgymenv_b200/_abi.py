@@ -25,7 +25,7 @@ DOF_MODE_NONE, DOF_MODE_POS, DOF_MODE_VEL, DOF_MODE_EFFORT = 0, 1, 2, 4
 
 (TT_OBS, TT_OBS_CLAMPED, TT_REW, TT_RESET, TT_PROGRESS, TT_TIMEOUT, TT_COMMANDS, TT_ACTIONS, TT_RAND_OVERRIDE, TT_TORQUES, TT_LAST_ACTIONS,
  TT_LAST_DOF_VEL, TT_FEET_AIR_TIME, TT_EPISODE_SUMS, TT_ENV_ORIGINS, TT_TERRAIN_LEVELS, TT_TERRAIN_TYPES, TT_NOISE_OVERRIDE, TT_PUSH_OVERRIDE,
- TT_EXTRAS, TT_MEASURED_HEIGHTS) = range(21)
+ TT_EXTRAS, TT_MEASURED_HEIGHTS, TT_ARM_MM, TT_ARM_JAC, TT_EEF_STATE, TT_ARM_COMMANDS) = range(25)
 REW_TERMS = 14
 
 f32, i32 = C.c_float, C.c_int32
@@ -108,6 +108,8 @@ class TerrainCfg(C.Structure):
         ("custom_origins", i32), ("curriculum", i32), ("n_hx", i32), ("n_hy", i32), ("hx", f32 * 16), ("hy", f32 * 16),
         ("hs_rows", i32), ("hs_cols", i32), ("border_size", f32), ("hscale", f32), ("vscale", f32), ("env_length", f32),
         ("env_rows", i32), ("env_cols", i32), ("seed", C.c_uint64),
+        ("n_ctrl_dof", i32), ("arm_chain", i32), ("arm_kp", f32), ("arm_kp_null", f32), ("arm_action_scale", f32), ("arm_dof_noise", f32),
+        ("arm_cmd_limit", f32 * 6), ("eef_body", i32), ("jac_body", i32), ("refresh_eef", i32),
     ]
 
 

@@ -241,6 +241,7 @@ struct b2g_sim {
     float *torques = nullptr, *last_actions = nullptr, *last_dof_vel = nullptr, *feet_air_time = nullptr, *episode_sums = nullptr;
     float *env_origins = nullptr, *terrain_origins = nullptr, *scratch9 = nullptr, *resetw = nullptr, *report = nullptr, *measured = nullptr;
     float *noise_override = nullptr, *push_override = nullptr, *extras = nullptr;
+    float *arm_mm = nullptr, *arm_jac = nullptr, *eef_state = nullptr, *arm_commands = nullptr;
     long long *terrain_levels = nullptr, *terrain_types = nullptr;
     int16_t* height_samples = nullptr;
     long long common_step = 0;
@@ -385,16 +386,22 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         R.env_origins = s->env_origins; R.terrain_levels = s->terrain_levels; R.terrain_types = s->terrain_types; R.terrain_origins = s->terrain_origins;
         R.height_samples = s->height_samples; R.scratch = s->scratch9; R.resetw = s->resetw; R.report = s->report; R.measured = s->measured;
         R.reset_count = s->reset_count;
+        R.arm_mm = s->arm_mm; R.arm_jac = s->arm_jac; R.eef_state = s->eef_state; R.arm_commands = s->arm_commands;
         R.reset_override = s->use_rand_override ? s->rand_override : nullptr;
         R.noise_override = s->use_rand_override ? s->noise_override : nullptr;
         R.push_override = s->use_rand_override ? s->push_override : nullptr;
         R.common_step = s->common_step; R.init_done = s->init_done; R.post_only = post_only; R.seed = s->seed;
         if (s->v.lanes == 4) {
             if (s->has_hf) k_terrain_phys<4, 3, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<4, 3, false><<<grid, kBlock, sm, st>>>(A, R);
-            k_terrain_post<4, 3><<<grid, kBlock, 0, st>>>(A, R);
+            if (post_only != 2) k_terrain_post<4, 3><<<grid, kBlock, 0, st>>>(A, R);
         } else {
             if (s->has_hf) k_terrain_phys<8, 6, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<8, 6, false><<<grid, kBlock, sm, st>>>(A, R);
-            k_terrain_post<8, 6><<<grid, kBlock, 0, st>>>(A, R);
+            if (post_only != 2) k_terrain_post<8, 6><<<grid, kBlock, 0, st>>>(A, R);
+        }
+        if (post_only == 2) {
+            s->launches += 1;
+            CUDA_TRY(cudaGetLastError());
+            return B2G_OK;
         }
         k_terrain_extras<<<1, 256, 0, st>>>(s->report, s->reset, s->terrain_levels, s->extras, s->n_envs, 1.0f / s->tcfg.max_episode_length_s);
         s->launches += 3;
@@ -461,7 +468,8 @@ int b2g_sim_destroy(b2g_sim* s) {
         void* ptrs[] = {s->d_model, s->d_hf, s->obs, s->obs_clamped, s->rew, s->commands, s->actions, s->rand_override,
                         s->reset, s->progress, s->timeout, s->reset_count, s->actions_in, s->torques, s->last_actions, s->last_dof_vel,
                         s->feet_air_time, s->episode_sums, s->env_origins, s->terrain_origins, s->scratch9, s->resetw, s->report, s->measured,
-                        s->noise_override, s->push_override, s->extras, s->terrain_levels, s->terrain_types, s->height_samples};
+                        s->noise_override, s->push_override, s->extras, s->terrain_levels, s->terrain_types, s->height_samples,
+                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands};
         for (void* p : ptrs) if (p) cudaFree(p);
         return 0;
     });
@@ -747,9 +755,14 @@ int b2g_task_terrain_create(b2g_sim* s, const b2g_terrain_cfg* cfg, const int16_
     s->seed = cfg->seed;
     s->task_kind = 3;
     s->n_cmd = 4;
+    const bool arm = cfg->arm_chain >= 0;
+    if (arm && (cfg->arm_chain >= s->model.n_chains || s->model.chain_len[cfg->arm_chain] != 6 || cfg->eef_body < 0 || cfg->eef_body >= nb ||
+                cfg->jac_body < 0 || cfg->jac_body >= nb || cfg->n_ctrl_dof != s->model.chain_start[cfg->arm_chain]))
+        return fail(B2G_ERR_ARG, "bad arm description (the arm must be the last chain, 6 DOF)");
+    const int nctrl = cfg->n_ctrl_dof > 0 ? cfg->n_ctrl_dof : nd;
     const int nhp = cfg->n_hx * cfg->n_hy;
-    const int no = 12 + 2 * nd + nhp + nd;
-    int rc = alloc_task_buffers(s, no, nd, 2 * nd + 5);
+    const int no = 12 + 2 * nctrl + nhp + nd + (arm ? 10 : 0);
+    int rc = alloc_task_buffers(s, no, nd, 2 * nctrl + 5 + (arm ? 6 : 0));
     if (rc != B2G_OK) return rc;
     return with_device(s, [&]() {
         const size_t n = s->n_envs;
@@ -773,6 +786,10 @@ int b2g_task_terrain_create(b2g_sim* s, const b2g_terrain_cfg* cfg, const int16_
         CUDA_TRY(zalloc((void**)&s->extras, sizeof(float) * 16));
         CUDA_TRY(zalloc((void**)&s->terrain_levels, sizeof(long long) * n));
         CUDA_TRY(zalloc((void**)&s->terrain_types, sizeof(long long) * n));
+        CUDA_TRY(zalloc((void**)&s->arm_mm, sizeof(float) * n * 36));
+        CUDA_TRY(zalloc((void**)&s->arm_jac, sizeof(float) * n * 36));
+        CUDA_TRY(zalloc((void**)&s->eef_state, sizeof(float) * n * 13));
+        CUDA_TRY(zalloc((void**)&s->arm_commands, sizeof(float) * n * 3));
         if (hs_host && cfg->hs_rows > 0) {
             const size_t b = sizeof(int16_t) * (size_t)cfg->hs_rows * cfg->hs_cols;
             CUDA_TRY(cudaMalloc(&s->height_samples, b));
@@ -830,6 +847,10 @@ int b2g_task_tensor(b2g_sim* s, int kind, b2g_tensor_desc* d) {
         case B2G_TT_PUSH_OVERRIDE: d->data = s->push_override; d->ndim = 2; d->shape[1] = 2; break;
         case B2G_TT_EXTRAS: d->data = s->extras; d->shape[0] = 16; break;
         case B2G_TT_MEASURED_HEIGHTS: d->data = s->measured; d->ndim = 2; d->shape[1] = s->tcfg.n_hx * s->tcfg.n_hy; break;
+        case B2G_TT_ARM_MM: d->data = s->arm_mm; d->ndim = 3; d->shape[1] = 6; d->shape[2] = 6; break;
+        case B2G_TT_ARM_JAC: d->data = s->arm_jac; d->ndim = 3; d->shape[1] = 6; d->shape[2] = 6; break;
+        case B2G_TT_EEF_STATE: d->data = s->eef_state; d->ndim = 2; d->shape[1] = 13; break;
+        case B2G_TT_ARM_COMMANDS: d->data = s->arm_commands; d->ndim = 2; d->shape[1] = 3; break;
         default: return fail(B2G_ERR_ARG, "unknown task tensor kind %d", kind);
     }
     return B2G_OK;
@@ -889,6 +910,11 @@ int b2g_task_anymal_step_host(b2g_sim* s, const float* actions_host, float* obs_
 
 int b2g_task_step(b2g_sim* s, const float* actions_dev, void* stream) { return b2g_task_anymal_step(s, actions_dev, stream); }
 int b2g_task_post_only(b2g_sim* s, const float* actions_dev, void* stream) { return b2g_task_anymal_post_only(s, actions_dev, stream); }
+int b2g_task_osc_probe(b2g_sim* s, const float* actions_dev, void* stream) {
+    if (!s || !actions_dev) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->has_task || s->task_kind != 3 || s->tcfg.arm_chain < 0) return fail(B2G_ERR_STATE, "no hound+arm task created");
+    return with_device(s, [&]() { return launch_anymal_step(s, actions_dev, (cudaStream_t)stream, 2); });
+}
 int b2g_task_step_host(b2g_sim* s, const float* a, float* o, float* r, int64_t* rs, int64_t* to, void* stream) {
     return b2g_task_anymal_step_host(s, a, o, r, rs, to, stream);
 }

@@ -399,6 +399,10 @@ struct TerrainArgs {
     float* resetw;               // (N) reset ? |cmd_xy|^2 : 0      (curriculum scalar, quirk Q10)
     float* report;               // (13,N) episode sums of the envs that reset this step (else 0)
     float* measured;             // (N,n_height_points)
+    float* arm_mm;               // (N,36) arm block of the mass matrix as of the last post_physics refresh (pre-reset)
+    float* arm_jac;              // (N,36) Jacobian slice the task takes: base columns of body `jac_body`
+    float* eef_state;            // (N,13) end-effector rigid-body row (never refreshed unless cfg.refresh_eef)
+    float* arm_commands;         // (N,3)
     int* reset_count;
     const float* reset_override; // (N,29)
     const float* noise_override; // (N,no)
@@ -430,6 +434,147 @@ B2G_HD B2G_INL float wrap_to_pi_f(float a) {
 }
 B2G_HD B2G_INL float norm3(const float* f) { return sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]); }
 
+
+// ---- hound + arm helpers (tasks/useful_hound.py) ----
+// general 6x6 inverse, Gauss-Jordan with partial pivoting (what torch.inverse does for the OSC law, :668-670)
+B2G_HD inline void inv6(const float* a, float* inv) {
+    float m[6][12];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) { m[i][j] = a[i * 6 + j]; m[i][6 + j] = (i == j) ? 1.0f : 0.0f; }
+    for (int c = 0; c < 6; c++) {
+        int piv = c;
+        float best = fabsf(m[c][c]);
+        for (int r = c + 1; r < 6; r++) if (fabsf(m[r][c]) > best) { best = fabsf(m[r][c]); piv = r; }
+        if (piv != c) for (int j = 0; j < 12; j++) { const float t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
+        const float d = 1.0f / m[c][c];
+        for (int j = 0; j < 12; j++) m[c][j] *= d;
+        for (int r = 0; r < 6; r++) {
+            if (r == c) continue;
+            const float f = m[r][c];
+            for (int j = 0; j < 12; j++) m[r][j] -= f * m[c][j];
+        }
+    }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) inv[i * 6 + j] = m[i][6 + j];
+}
+B2G_HD inline void mm6(const float* a, const float* b, float* o, bool ta = false, bool tb = false) {
+    float t[36];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            float acc = 0.0f;
+            for (int k = 0; k < 6; k++) acc += (ta ? a[k * 6 + i] : a[i * 6 + k]) * (tb ? b[j * 6 + k] : b[k * 6 + j]);
+            t[i * 6 + j] = acc;
+        }
+    for (int i = 0; i < 36; i++) o[i] = t[i];
+}
+// _compute_osc_torques (tasks/useful_hound.py:660-691)
+B2G_HD inline void osc_torques(const float* mm, const float* j, const float* dpose, const float* eef_vel, const float* q, const float* qd, float kp,
+                               float kp_null, const float* effort, float* u) {
+    const float kd = 2.0f * sqrtf(kp), kdn = 2.0f * sqrtf(kp_null);
+    float mm_inv[36], t[36], m_eef_inv[36], m_eef[36], j_eef_inv[36];
+    inv6(mm, mm_inv);
+    mm6(j, mm_inv, t);
+    mm6(t, j, m_eef_inv, false, true);
+    inv6(m_eef_inv, m_eef);
+    float w[6], v[6];
+    for (int i = 0; i < 6; i++) w[i] = kp * dpose[i] - kd * eef_vel[i];
+    for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += m_eef[i * 6 + k] * w[k]; v[i] = acc; }
+    for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += j[k * 6 + i] * v[k]; u[i] = acc; }          // J^T (Lambda w)
+    mm6(m_eef, j, t);
+    mm6(t, mm_inv, j_eef_inv);
+    float un[6], mu_[6];
+    const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+    for (int i = 0; i < 6; i++) {
+        float a = 0.0f - q[i] + pi;
+        a = a - two_pi * floorf(a / two_pi);            // python-style remainder (eager torch %)
+        un[i] = kdn * -qd[i] + kp_null * (a - pi);
+    }
+    for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += mm[i * 6 + k] * un[k]; mu_[i] = acc; }
+    mm6(j, j_eef_inv, t, true, false);                  // J^T j_eef_inv
+    for (int i = 0; i < 6; i++) {
+        float acc = mu_[i];
+        for (int k = 0; k < 6; k++) acc -= t[i * 6 + k] * mu_[k];
+        u[i] += acc;
+        u[i] = fminf(fmaxf(u[i], -effort[i]), effort[i]);
+    }
+}
+// Kinematics + composite-rigid-body pass over one chain: joint-space mass-matrix block of the chain (n x n, row-major in
+// mm[36]), the position (relative to the root origin) of link `want_link` (chain-local index, -1 = root) and its world rotation.
+B2G_HD inline void chain_crba(const DevModel* M, int d0, int n, const float* rootq, const float* q, float* mm, int want_link, V3* want_pos, M3* want_rot,
+                              const float* qd, V3 root_w, V3 root_v, SV* want_vel) {
+    M3 R = quat_to_m3(rootq[0], rootq[1], rootq[2], rootq[3]);
+    V3 p = V3{0, 0, 0};
+    SV vel = SV{root_w, root_v};
+    SV S[B2G_MAX_CHAIN_LEN];
+    SI I[B2G_MAX_CHAIN_LEN];
+    if (want_link < 0) { *want_pos = p; *want_rot = R; *want_vel = vel; }
+    for (int j = 0; j < n; j++) {
+        const DevDof& D = M->dof[d0 + j];
+        M3 jr;
+        for (int k = 0; k < 9; k++) jr.m[k] = D.jrot[k];
+        const V3 ax = V3{D.axis[0], D.axis[1], D.axis[2]};
+        const M3 RJ = mul(R, jr);
+        const V3 pj = p + mul(R, V3{D.jpos[0], D.jpos[1], D.jpos[2]});
+        const V3 axw = mul(RJ, ax);
+        if (D.type == B2G_JOINT_REVOLUTE) { R = mul(RJ, axis_angle_m3(ax, q[j])); p = pj; S[j] = SV{axw, cross(pj, axw)}; }
+        else { R = RJ; p = pj + axw * q[j]; S[j] = SV{V3{0, 0, 0}, axw}; }
+        vel = vel + S[j] * qd[j];
+        const V3 cw = p + mul(R, V3{D.com[0], D.com[1], D.com[2]});
+        I[j] = rigid_inertia(D.mass, cw, rotate_sym(R, S3{D.inertia[0], D.inertia[1], D.inertia[2], D.inertia[3], D.inertia[4], D.inertia[5]}));
+        if (j == want_link) { *want_pos = p; *want_rot = R; *want_vel = vel; }
+    }
+    for (int j = n - 2; j >= 0; j--) I[j] += I[j + 1];
+    for (int i = 0; i < 36; i++) mm[i] = 0.0f;
+    for (int i = 0; i < n; i++) {
+        const SV F = mul(I[i], S[i]);
+        mm[i * 6 + i] = dot(S[i], F) + M->dof[d0 + i].armature;
+        for (int k = 0; k < i; k++) { const float v = dot(S[k], F); mm[i * 6 + k] = v; mm[k * 6 + i] = v; }
+    }
+}
+// what post_physics_step's refresh_jacobian / refresh_mass_matrix leave for the next step's OSC (pre-reset state), plus the
+// optional live end-effector row
+template <int NL>
+B2G_HD inline void arm_refresh(const SimArgs& A, const TerrainArgs& T, int env, int d0, int len, const LaneState<NL>& st) {
+    const DevModel* M = A.M;
+    const b2g_terrain_cfg& C = T.cfg;
+    const float rq[4] = {st.qx, st.qy, st.qz, st.qw};
+    float mm[36];
+    // Jacobian slice jacobian[:, jac_body, :, :6] of a floating-base actor = the base's six columns (linear rows first):
+    // [[I, -[r]x], [0, I]] with r = position of that body relative to the base origin
+    const int jl = M->body_link[C.jac_body];
+    const int jloc = (jl == 0) ? -1 : jl - 1 - d0;
+    V3 lp; M3 lr; SV lv;
+    chain_crba(M, d0, len, rq, st.q, mm, jloc, &lp, &lr, st.qd, st.rw, st.rv, &lv);
+    const V3 r = lp + mul(lr, V3{M->body_pos[C.jac_body][0], M->body_pos[C.jac_body][1], M->body_pos[C.jac_body][2]});
+    float* J = T.arm_jac + (size_t)env * 36;
+    for (int i = 0; i < 36; i++) J[i] = 0.0f;
+    for (int i = 0; i < 6; i++) J[i * 6 + i] = 1.0f;
+    J[0 * 6 + 4] = r.z; J[0 * 6 + 5] = -r.y; J[1 * 6 + 3] = -r.z; J[1 * 6 + 5] = r.x; J[2 * 6 + 3] = r.y; J[2 * 6 + 4] = -r.x;
+    float* MM = T.arm_mm + (size_t)env * 36;
+    for (int i = 0; i < 36; i++) MM[i] = mm[i];
+    if (C.refresh_eef) {
+        const int el = M->body_link[C.eef_body];
+        const int eloc = (el == 0) ? -1 : el - 1 - d0;
+        float dummy[36];
+        V3 ep; M3 er; SV ev;
+        chain_crba(M, d0, len, rq, st.q, dummy, eloc, &ep, &er, st.qd, st.rw, st.rv, &ev);
+        const V3 off = mul(er, V3{M->body_pos[C.eef_body][0], M->body_pos[C.eef_body][1], M->body_pos[C.eef_body][2]});
+        const V3 pos = ep + off;
+        const V3 lin = ev.v + cross(ev.w, pos);
+        float* e = T.eef_state + (size_t)env * 13;
+        e[0] = st.rp.x + pos.x; e[1] = st.rp.y + pos.y; e[2] = st.rp.z + pos.z;
+        // orientation: body rotation as a quaternion (xyzw)
+        const M3 Rb = mul(er, quat_to_m3(M->body_quat[C.eef_body][0], M->body_quat[C.eef_body][1], M->body_quat[C.eef_body][2], M->body_quat[C.eef_body][3]));
+        const float tr = Rb.m[0] + Rb.m[4] + Rb.m[8];
+        float qx, qy, qz, qw;
+        if (tr > 0.0f) { float s2 = sqrtf(tr + 1.0f) * 2.0f; qw = 0.25f * s2; qx = (Rb.m[7] - Rb.m[5]) / s2; qy = (Rb.m[2] - Rb.m[6]) / s2; qz = (Rb.m[3] - Rb.m[1]) / s2; }
+        else if (Rb.m[0] > Rb.m[4] && Rb.m[0] > Rb.m[8]) { float s2 = sqrtf(1.0f + Rb.m[0] - Rb.m[4] - Rb.m[8]) * 2.0f; qw = (Rb.m[7] - Rb.m[5]) / s2; qx = 0.25f * s2; qy = (Rb.m[1] + Rb.m[3]) / s2; qz = (Rb.m[2] + Rb.m[6]) / s2; }
+        else if (Rb.m[4] > Rb.m[8]) { float s2 = sqrtf(1.0f + Rb.m[4] - Rb.m[0] - Rb.m[8]) * 2.0f; qw = (Rb.m[2] - Rb.m[6]) / s2; qx = (Rb.m[1] + Rb.m[3]) / s2; qy = 0.25f * s2; qz = (Rb.m[5] + Rb.m[7]) / s2; }
+        else { float s2 = sqrtf(1.0f + Rb.m[8] - Rb.m[0] - Rb.m[4]) * 2.0f; qw = (Rb.m[3] - Rb.m[1]) / s2; qx = (Rb.m[2] + Rb.m[6]) / s2; qy = (Rb.m[5] + Rb.m[7]) / s2; qz = 0.25f * s2; }
+        e[3] = qx; e[4] = qy; e[5] = qz; e[6] = qw;
+        e[7] = lin.x; e[8] = lin.y; e[9] = lin.z; e[10] = ev.w.x; e[11] = ev.w.y; e[12] = ev.w.z;
+    }
+}
+
 // kernel 1: pre_physics_step (decimation loop) + extra sim step + post_physics_step up to and including the reward
 template <int LANES, int NL, bool HF>
 B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, int env, int lane, bool valid, ScratchStrided sc, float* bf) {
@@ -456,19 +601,52 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
             lqd[j] = T.last_dof_vel[k];
         }
     }
+    const bool is_arm = (C.arm_chain >= 0) && (lane == C.arm_chain);
+    // arm lane: OSC torque from the stored mass-matrix / Jacobian slices, the end-effector velocity row and the live arm DOFs
+    auto arm_osc = [&](float* out) {
+        float dpose[6], qa[6], qda[6], eff[6], u[6];
+        const float* ev = T.eef_state + (size_t)env * 13 + 7;
+        for (int j = 0; j < 6; j++) {
+            dpose[j] = 0; qa[j] = 0; qda[j] = 0; eff[j] = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            if (j < 6 && j < len) {
+                dpose[j] = act[j] * C.arm_cmd_limit[j] / C.arm_action_scale;
+                qa[j] = st.q[j]; qda[j] = st.qd[j]; eff[j] = M->dof[d0 + j].effort;
+            }
+        }
+        osc_torques(T.arm_mm + (size_t)env * 36, T.arm_jac + (size_t)env * 36, dpose, ev, qa, qda, C.arm_kp, C.arm_kp_null, eff, u);
+#pragma unroll
+        for (int j = 0; j < NL; j++)
+            if (j < 6 && j < len) out[j] = u[j];
+    };
+    if (T.post_only == 2) {        // OSC probe (parity tests): one evaluation of the torque law, nothing else
+        if (is_arm) {
+            arm_osc(tq);
+            if (valid)
+                for (int j = 0; j < len; j++) T.torques[(size_t)env * nd + d0 + j] = tq[j];
+        }
+        return;
+    }
     if (!T.post_only) {
         const float mu_shape = A.friction ? A.friction[env] : 1.0f;
         const int total = C.decimation + C.extra_sim_steps;
         for (int it = 0; it < total; it++) {
             if (it < C.decimation) {      // tasks/anymal_terrain.py:444-445: fresh explicit PD torque, clipped
+                if (is_arm) {             // tasks/useful_hound.py:704-716: operational-space torques for the arm, every decimation step
+                    arm_osc(tq);
+                } else {
 #pragma unroll
-                for (int j = 0; j < NL; j++) {
-                    if (j < len) {
-                        const float t = C.kp * (C.action_scale * act[j] + C.default_dof_pos[d0 + j] - st.q[j]) - C.kd * st.qd[j];
-                        tq[j] = fminf(fmaxf(t, -C.torque_limit), C.torque_limit);
-                        st.act[j] = tq[j];
+                    for (int j = 0; j < NL; j++) {
+                        if (j < len) {
+                            const float t = C.kp * (C.action_scale * act[j] + C.default_dof_pos[d0 + j] - st.q[j]) - C.kd * st.qd[j];
+                            tq[j] = fminf(fmaxf(t, -C.torque_limit), C.torque_limit);
+                        }
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < NL; j++) st.act[j] = tq[j];
             }
             for (int s = 0; s < A.P.substeps; s++)
                 substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape,
@@ -500,6 +678,7 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
     if (C.hound_termination)
         for (int k = 0; k < C.n_term_extra; k++) term = term || (norm3(bf + C.term_extra_bodies[k] * 3) > 1.0f);
     const bool reset = term || (progress >= C.max_episode_length - 1);
+    const int nctrl = C.n_ctrl_dof > 0 ? C.n_ctrl_dof : nd;
     // compute_reward :315-382 -- per-lane partial sums, then one shuffle reduction each
     float s_tq = 0, s_jacc = 0, s_arate = 0, s_hip = 0, s_coll = 0, s_stumble = 0, s_air = 0;
 #pragma unroll
@@ -507,13 +686,15 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
         if (j < len) {
             s_tq += tq[j] * tq[j];
             const float dv = lqd[j] - st.qd[j], da = lact[j] - act[j];
-            s_jacc += dv * dv;
+            if (d0 + j < nctrl) s_jacc += dv * dv;
             s_arate += da * da;
             const int d = d0 + j;
             if (d == C.hip_dofs[0] || d == C.hip_dofs[1] || d == C.hip_dofs[2] || d == C.hip_dofs[3]) s_hip += fabsf(st.q[j] - C.default_dof_pos[d]);
         }
     }
     for (int k = lane; k < C.n_knee; k += LANES) s_coll += (norm3(bf + C.knee_bodies[k] * 3) > 1.0f) ? 1.0f : 0.0f;
+    if (C.arm_chain >= 0)      // tasks/useful_hound.py:524-525
+        for (int k = lane; k < C.n_term_extra; k += LANES) s_coll += (norm3(bf + C.term_extra_bodies[k] * 3) > 1.0f) ? 1.0f : 0.0f;
     for (int k = lane; k < C.n_feet; k += LANES) {
         const float* f = bf + C.feet_bodies[k] * 3;
         s_stumble += ((sqrtf(f[0] * f[0] + f[1] * f[1]) > 5.0f) && (fabsf(f[2]) < 1.0f)) ? 1.0f : 0.0f;
@@ -558,6 +739,7 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
                 T.torques[k] = tq[j];
             }
         }
+        if (is_arm) arm_refresh<NL>(A, T, env, d0, len, st);      // refresh_jacobian / refresh_mass_matrix (useful_hound.py:731-732)
         if (lane == 0) {
             T.rew[env] = rew;
             T.reset[env] = reset ? 1 : 0;
@@ -598,17 +780,28 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
     const long long type = T.terrain_types[env];
     // every lane has read the per-env inputs it replicates; only now may lane 0 overwrite them
     Grp<LANES>::sync();
-    if (reset) {        // reset_idx, tasks/anymal_terrain.py:384-425; draw order of the torch_rand_float calls
-        const int ndraw = 2 * nd + 5;
+    const bool has_arm = C.arm_chain >= 0;
+    const bool is_arm = has_arm && lane == C.arm_chain;
+    const int nctrl = C.n_ctrl_dof > 0 ? C.n_ctrl_dof : nd;
+    if (reset) {        // reset_idx, tasks/anymal_terrain.py:384-425 (useful_hound.py:569-637); draw order of the random calls
+        const int ndraw = 2 * nctrl + 5 + (has_arm ? 6 : 0);
+        const int arm_col = 2 * nctrl + (C.custom_origins ? 2 : 0);
 #pragma unroll
         for (int j = 0; j < NL; j++) {
             if (j < len) {
                 const int d = d0 + j;
-                q[j] = C.default_dof_pos[d] * rand_range(0.5f, 1.5f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, d));
-                qd[j] = rand_range(-0.1f, 0.1f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, nd + d));
+                if (!is_arm) {
+                    q[j] = C.default_dof_pos[d] * rand_range(0.5f, 1.5f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, d));
+                    qd[j] = rand_range(-0.1f, 0.1f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, nctrl + d));
+                } else {      // arm joints <- clamp(0 + noise * 2 (u - 0.5), lower, upper), zero velocity (useful_hound.py:594-601)
+                    const float u = terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, arm_col + j);
+                    const float v = 0.0f + C.arm_dof_noise * 2.0f * (u - 0.5f);
+                    q[j] = fminf(fmaxf(v, M->dof[d].lower), M->dof[d].upper);
+                    qd[j] = 0.0f;
+                }
             }
         }
-        int col = 2 * nd;
+        int col = 2 * nctrl;
         if (C.custom_origins) {
             if (T.init_done && C.curriculum) {      // update_terrain_level :427-435
                 const float dx = root[0] - origin[0], dy = root[1] - origin[1];
@@ -632,6 +825,7 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
         } else {
             for (int k = 0; k < 13; k++) root[k] = C.init_root[k];
         }
+        if (has_arm) col += 6;
         cmd[0] = rand_range(C.cmd_x[0], C.cmd_x[1], terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, col));
         cmd[1] = rand_range(C.cmd_y[0], C.cmd_y[1], terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, col + 1));
         cmd[3] = rand_range(C.cmd_yaw[0], C.cmd_yaw[1], terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, col + 2));
@@ -640,7 +834,7 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
     }
     // ---- observations (tasks/anymal_terrain.py:302-313) ----
     const int nhp = C.n_hx * C.n_hy;
-    const int no = 12 + 2 * nd + nhp + nd;
+    const int no = 12 + 2 * nctrl + nhp + nd + (has_arm ? 10 : 0);
     float* o = T.obs + (size_t)env * no;
     float* oc = T.obs_clamped + (size_t)env * no;
     const unsigned step = (unsigned)T.common_step;
@@ -648,6 +842,12 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
         if (C.add_noise && nscale != 0.0f) val += (2.0f * terrain_uniform(T, T.noise_override, no, env, step, 2u, idx) - 1.0f) * nscale;
         if (valid) { o[idx] = val; oc[idx] = fminf(fmaxf(val, -C.clip_obs), C.clip_obs); }
     };
+    if (has_arm && lane == 0) {      // tasks/useful_hound.py:493-496: end-effector position, orientation, arm command
+        const float* e = T.eef_state + (size_t)env * 13;
+        const int b0 = 12 + 2 * nctrl + nhp + nd;
+        for (int k = 0; k < 7; k++) put(b0 + k, e[k], 0.0f);
+        for (int k = 0; k < 3; k++) put(b0 + 7 + k, T.arm_commands[(size_t)env * 3 + k], 0.0f);
+    }
     if (lane == 0) {
         const float* s9 = T.scratch + (size_t)env * 9;
         for (int k = 0; k < 3; k++) put(k, s9[k] * C.lin_vel_scale, C.noise_lin_vel);
@@ -663,9 +863,11 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
             const int d = d0 + j;
             const size_t k = (size_t)env * nd + d;
             const float a = T.actions[k];
-            put(12 + d, q[j] * C.dof_pos_scale, C.noise_dof_pos);
-            put(12 + nd + d, qd[j] * C.dof_vel_scale, C.noise_dof_vel);
-            put(12 + 2 * nd + nhp + d, a, 0.0f);
+            if (d < nctrl) {
+                put(12 + d, q[j] * C.dof_pos_scale, C.noise_dof_pos);
+                put(12 + nctrl + d, qd[j] * C.dof_vel_scale, C.noise_dof_vel);
+            }
+            put(12 + 2 * nctrl + nhp + d, a, 0.0f);
             if (valid) {
                 T.last_actions[k] = a;          // :484-485 (post-reset values for envs that reset)
                 T.last_dof_vel[k] = qd[j];
@@ -691,7 +893,7 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
             }
             if (valid) T.measured[(size_t)env * nhp + p] = h;
             const float v = fminf(fmaxf(root[2] - 0.5f - h, -1.0f), 1.0f) * C.height_meas_scale;
-            put(12 + 2 * nd + p, v, C.noise_height);
+            put(12 + 2 * nctrl + p, v, C.noise_height);
         }
     }
     if (valid) {

@@ -88,7 +88,7 @@ class AnymalTerrain(VecTask):
         self.forward_vec = to_torch([1.0, 0.0, 0.0], device=self.device).repeat((self.num_envs, 1))
         self.default_dof_pos = torch.zeros_like(self.dof_pos, dtype=torch.float, device=self.device, requires_grad=False)
         for i in range(self.num_dof):
-            self.default_dof_pos[:, i] = self.named_default_joint_angles[self.dof_names[i]]
+            self.default_dof_pos[:, i] = self.named_default_joint_angles.get(self.dof_names[i], 0.0)
         self.height_points = self.init_height_points()
         self._create_fused_task()
         self.reset_idx(torch.arange(self.num_envs, device=self.device))
@@ -259,6 +259,7 @@ class AnymalTerrain(VecTask):
             c.border_size, c.hscale, c.vscale, c.env_length = float(t.border_size), t.horizontal_scale, t.vertical_scale, float(t.env_length)
             c.env_rows, c.env_cols = t.env_rows, t.env_cols
         c.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        c.arm_chain = -1          # no manipulator (UsefulHound overrides)
         return c
 
     def _create_fused_task(self):
@@ -299,8 +300,9 @@ class AnymalTerrain(VecTask):
         """Reference :384-425.  Used for the constructor's reset of all envs (torch RNG, like the reference); during
         stepping resets happen inside the kernels."""
         n = len(env_ids)
-        self.dof_pos[env_ids] = self.default_dof_pos[env_ids] * torch_rand_float(0.5, 1.5, (n, self.num_dof), device=self.device)
-        self.dof_vel[env_ids] = torch_rand_float(-0.1, 0.1, (n, self.num_dof), device=self.device)
+        nleg = 12
+        self.dof_pos[env_ids, :nleg] = self.default_dof_pos[env_ids, :nleg] * torch_rand_float(0.5, 1.5, (n, nleg), device=self.device)
+        self.dof_vel[env_ids, :nleg] = torch_rand_float(-0.1, 0.1, (n, nleg), device=self.device)
         self.root_states[env_ids] = self.base_init_state
         if self.custom_origins:
             self.root_states[env_ids, :3] += self.env_origins[env_ids]

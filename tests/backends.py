@@ -14,7 +14,8 @@ import numpy as np
 from isaacgymenv_b200 import _abi
 
 TASK_KEYS = ("obs", "obs_clamped", "rew", "reset", "progress", "timeout", "commands", "actions")
-TERRAIN_KEYS = ("torques", "last_actions", "last_dof_vel", "feet_air_time", "episode_sums", "env_origins", "terrain_levels", "terrain_types", "measured")
+TERRAIN_KEYS = ("torques", "last_actions", "last_dof_vel", "feet_air_time", "episode_sums", "env_origins", "terrain_levels", "terrain_types", "measured",
+                "arm_mm", "arm_jac", "eef_state", "arm_commands")
 
 
 class EmuBackend:
@@ -71,7 +72,9 @@ class EmuBackend:
     def terrain_create(self, cfg, height_samples=None, terrain_origins=None, heightfield=None):
         n, nd = self.n, self.art.num_dofs
         nhp = cfg.n_hx * cfg.n_hy
-        no = 12 + 2 * nd + nhp + nd
+        arm = cfg.arm_chain >= 0
+        nctrl = cfg.n_ctrl_dof if cfg.n_ctrl_dof > 0 else nd
+        no = 12 + 2 * nctrl + nhp + nd + (10 if arm else 0)
         self.cfg, self.kind = cfg, "terrain"
         self.hs = None if height_samples is None else np.ascontiguousarray(height_samples, np.int16)
         self.origins = None if terrain_origins is None else np.ascontiguousarray(terrain_origins, np.float32)
@@ -81,7 +84,8 @@ class EmuBackend:
         self.task = dict(obs=z(n, no), obs_clamped=z(n, no), rew=z(n), reset=np.ones(n, np.int64), progress=z(n, dt=np.int64), timeout=z(n, dt=np.int64),
                          commands=z(n, 4), actions=z(n, nd), reset_count=z(n, dt=np.int32), torques=z(n, nd), last_actions=z(n, nd), last_dof_vel=z(n, nd),
                          feet_air_time=z(n, 4), episode_sums=z(13, n), env_origins=z(n, 3), terrain_levels=z(n, dt=np.int64), terrain_types=z(n, dt=np.int64),
-                         scratch=z(n, 9), resetw=z(n), report=z(13, n), measured=z(n, nhp))
+                         scratch=z(n, 9), resetw=z(n), report=z(13, n), measured=z(n, nhp), arm_mm=z(n, 6, 6), arm_jac=z(n, 6, 6),
+                         eef_state=z(n, 13), arm_commands=z(n, 3))
 
     def _terrain_step(self, actions, draws, post_only):
         b = self._bufs()
@@ -92,7 +96,8 @@ class EmuBackend:
         b["noise_override"] = None if d.get("noise") is None else np.ascontiguousarray(d["noise"], np.float32)
         b["push_override"] = None if d.get("push") is None else np.ascontiguousarray(d["push"], np.float32)
         hf = self.heightfield
-        self.emu.terrain(self.model, self.params, self.props, self.cfg, 2 if post_only else 1, b, self.common_step, self.init_done,
+        mode = 3 if post_only == 2 else (2 if post_only else 1)
+        self.emu.terrain(self.model, self.params, self.props, self.cfg, mode, b, self.common_step, self.init_done,
                          hf[0] if hf else None, hf[1] if hf else None)
 
     def anymal_create(self, cfg):
@@ -228,7 +233,8 @@ class CudaBackend:
                      last_actions=_abi.TT_LAST_ACTIONS, last_dof_vel=_abi.TT_LAST_DOF_VEL, feet_air_time=_abi.TT_FEET_AIR_TIME,
                      episode_sums=_abi.TT_EPISODE_SUMS, env_origins=_abi.TT_ENV_ORIGINS, terrain_levels=_abi.TT_TERRAIN_LEVELS,
                      terrain_types=_abi.TT_TERRAIN_TYPES, noise=_abi.TT_NOISE_OVERRIDE, push=_abi.TT_PUSH_OVERRIDE, extras=_abi.TT_EXTRAS,
-                     measured=_abi.TT_MEASURED_HEIGHTS)
+                     measured=_abi.TT_MEASURED_HEIGHTS, arm_mm=_abi.TT_ARM_MM, arm_jac=_abi.TT_ARM_JAC, eef_state=_abi.TT_EEF_STATE,
+                     arm_commands=_abi.TT_ARM_COMMANDS)
         self.task = {k: self._tensor(v, task=True) for k, v in kinds.items()}
         self.set_step(0, 1)
 
@@ -244,7 +250,7 @@ class CudaBackend:
             self._lib.check(self.lib.b2g_task_set_rand_override(self.sim, 1))
         else:
             self._draws(draws)
-        fn = self.lib.b2g_task_post_only if post_only else self.lib.b2g_task_step
+        fn = self.lib.b2g_task_osc_probe if post_only == 2 else (self.lib.b2g_task_post_only if post_only else self.lib.b2g_task_step)
         self._lib.check(fn(self.sim, self._actions(actions), self.stream), "task step")
         self.torch.cuda.synchronize()
 

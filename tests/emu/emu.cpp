@@ -172,6 +172,7 @@ struct EmuTerrainBufs {
     const float* terrain_origins;
     const short* height_samples;
     float *scratch, *resetw, *report, *measured;
+    float *arm_mm, *arm_jac, *eef_state, *arm_commands;
     int* reset_count;
     const float *reset_override, *noise_override, *push_override;
     const float* friction;
@@ -193,8 +194,9 @@ int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_prop
     T.last_actions = B->last_actions; T.last_dof_vel = B->last_dof_vel; T.feet_air_time = B->feet_air_time; T.episode_sums = B->episode_sums;
     T.env_origins = B->env_origins; T.terrain_levels = B->terrain_levels; T.terrain_types = B->terrain_types; T.terrain_origins = B->terrain_origins;
     T.height_samples = B->height_samples; T.scratch = B->scratch; T.resetw = B->resetw; T.report = B->report; T.measured = B->measured;
+    T.arm_mm = B->arm_mm; T.arm_jac = B->arm_jac; T.eef_state = B->eef_state; T.arm_commands = B->arm_commands;
     T.reset_count = B->reset_count; T.reset_override = B->reset_override; T.noise_override = B->noise_override; T.push_override = B->push_override;
-    T.common_step = common_step; T.init_done = init_done; T.post_only = (mode == 2); T.seed = cfg->seed;
+    T.common_step = common_step; T.init_done = init_done; T.post_only = (mode == 2) ? 1 : (mode == 3 ? 2 : 0); T.seed = cfg->seed;
     const Variant v = pick(*m);
     if (v.fixed) { delete dm; return -2; }
     const bool HFm = hf && hfs;
@@ -206,6 +208,7 @@ int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_prop
             else { if (HFm) terrain_phys_thread<8, 6, true>(A, T, e, lane, true, sc, bf.data()); else terrain_phys_thread<8, 6, false>(A, T, e, lane, true, sc, bf.data()); }
         });
     }
+    if (mode == 3) { delete dm; return 0; }      // OSC probe: first kernel only
     float cnorm = 0.0f;
     if (cfg->custom_origins && cfg->curriculum && init_done) {
         // same summation order as the kernel: 64 strided partial sums, then a pairwise tree

@@ -90,12 +90,12 @@ class _TerrainBufs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("root", "dof", "dof_force", "contact", "actions_in", "obs", "obs_clamped", "rew", "reset", "progress",
                                           "timeout", "commands", "actions", "torques", "last_actions", "last_dof_vel", "feet_air_time",
                                           "episode_sums", "env_origins", "terrain_levels", "terrain_types", "terrain_origins", "height_samples",
-                                          "scratch", "resetw", "report", "measured", "reset_count", "reset_override", "noise_override",
+                                          "scratch", "resetw", "report", "measured", "arm_mm", "arm_jac", "eef_state", "arm_commands", "reset_count", "reset_override", "noise_override",
                                           "push_override", "friction")]
 
 
 def terrain(model, params, props, cfg, mode, bufs, common_step, init_done, heightfield=None, hf_samples=None):
-    """mode 1 = step, 2 = post_physics_step only.  bufs: dict name -> numpy array (or None) for every _TerrainBufs field."""
+    """mode 1 = step, 2 = post_physics_step only, 3 = OSC probe.  bufs: dict name -> numpy array (or None) for every _TerrainBufs field."""
     tb = _TerrainBufs()
     keep = []
     for k, _ in _TerrainBufs._fields_:

@@ -464,6 +464,7 @@ def terrain_cfg_struct(cfg, nd=12, seed=42):
         c.border_size, c.hscale, c.vscale, c.env_length = t["border_size"], t["hscale"], t["vscale"], t["env_length"]
         c.env_rows, c.env_cols = t["terrain_origins"].shape[0], t["terrain_origins"].shape[1]
     c.seed = seed
+    c.arm_chain = -1
     return c
 
 
@@ -596,6 +597,165 @@ def check_terrain_step(make_backend, robot="anymal_minimal", n=8, steps=12, seed
             # keep the oracle glued to the kernel state so that tolerances do not accumulate over steps
             st["root"], st["dof_pos"], st["dof_vel"] = rk.copy(), dk[:, :, 0].copy(), dk[:, :, 1].copy()
             st["commands"], st["last_dof_vel"], st["episode_sums"] = t["commands"].copy(), t["last_dof_vel"].copy(), t["episode_sums"].copy()
+            resets += int(reset.sum())
+    finally:
+        be.close()
+    assert resets > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# hound + arm (UsefulHound)
+# ------------------------------------------------------------------------------------------------
+def useful_cfg_struct(cfg, art):
+    c = terrain_cfg_struct(cfg, nd=18)
+    c.n_ctrl_dof, c.arm_chain = 12, 4
+    c.arm_kp, c.arm_kp_null, c.arm_action_scale, c.arm_dof_noise = 150.0, 10.0, 1.0, 0.25
+    for i, v in enumerate([0.1, 0.1, 0.1, 0.5, 0.5, 0.5]):
+        c.arm_cmd_limit[i] = v
+    c.eef_body = art.body_names.index("end_link")
+    c.jac_body = art.joint_dict["joint6"]
+    c.refresh_eef = 0
+    c.hound_termination = 1
+    return c
+
+
+def check_useful_golden(make_backend):
+    """UsefulHound post_physics_step and OSC torque law through the kernels vs the reference's own outputs."""
+    from tests.test_oracle_terrain import useful_case
+
+    g, st, cfg, draws = useful_case()
+    art = load_robot("useful_hound")
+    n = st["root"].shape[0]
+    cfg["push_interval"] = int(g["push_interval"])
+    c = useful_cfg_struct(cfg, art)
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    be = make_backend(art, terrain_params(), props, n)
+    try:
+        be.terrain_create(c)
+        # (a) the OSC law on the golden inputs
+        dof = np.zeros((n, 18, 2), np.float32)
+        dof[:, 12:, 0], dof[:, 12:, 1] = g["osc_q"], g["osc_qd"]
+        be.set_state(st["root"], dof)
+        eef = np.zeros((n, 13), np.float32)
+        eef[:, 7:] = g["osc_eef_vel"]
+        be.set_task(arm_mm=g["osc_mm"], arm_jac=g["osc_j"], eef_state=eef)
+        acts = np.zeros((n, 18), np.float32)
+        acts[:, 12:] = g["osc_dpose"] / np.array([[0.1, 0.1, 0.1, 0.5, 0.5, 0.5]], np.float32)
+        be.task_step(acts, None, post_only=2)
+        u = be.get_task()["torques"][:, 12:]
+        np.testing.assert_allclose(u, g["osc_u"], rtol=3e-4, atol=3e-4)
+        # (b) post_physics_step
+        be.set_step(int(g["common_step_counter"]) + 1, 1)
+        be.set_state(st["root"], g["dof_state"])
+        be.set_task(commands=st["commands"], progress=st["progress"], timeout=st["timeout_prev"].astype(np.int64), torques=st["torques"],
+                    last_actions=st["last_actions"], last_dof_vel=np.concatenate([st["last_dof_vel"], np.zeros((n, 6), np.float32)], axis=1),
+                    feet_air_time=st["feet_air_time"], episode_sums=st["episode_sums"], contact=st["contact"], reset=np.zeros(n, np.int64),
+                    eef_state=st["eef_state"])
+        be.task_step(st["actions"], draws, post_only=True)
+        out = be.get_task()
+        root, dof = be.get_state()
+    finally:
+        be.close()
+    assert np.array_equal(out["reset"], g["o_reset"]) and np.array_equal(out["progress"], g["o_progress"]) and np.array_equal(out["timeout"], g["o_timeout"])
+    np.testing.assert_allclose(out["rew"], g["o_rew"], rtol=1e-5, atol=2e-7)
+    np.testing.assert_allclose(out["obs"], g["o_obs"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(dof, g["o_dof_state"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(root, g["o_root"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["commands"], g["o_commands"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["last_actions"], g["o_last_actions"], rtol=0, atol=0)
+    np.testing.assert_allclose(out["last_dof_vel"][:, :12], g["o_last_dof_vel"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(out["episode_sums"], g["o_episode_sums"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["feet_air_time"], g["o_feet_air_time"], rtol=1e-5, atol=1e-7)
+
+
+def check_useful_step(make_backend, n=6, steps=8, seed=21):
+    """Whole UsefulHound step (PD legs + OSC arm x 4 sim steps + 1 stale, post_physics_step) vs the oracle composition.  The oracle's arm
+    mass-matrix block comes from its own CRBA (float64), the Jacobian slice from the independent numpy kinematics."""
+    from isaacgymenv_b200.model import urdf
+
+    art = load_robot("useful_hound")
+    nd, nb = art.num_dofs, art.num_bodies
+    rng = np.random.default_rng(seed)
+    sp = terrain_params()
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    m = _abi.pack_model(art)
+    knee = [i for i, b in enumerate(art.body_names) if "thigh" in b]
+    feet = [i for i, b in enumerate(art.body_names) if "foot" in b]
+    shoulders = [i for i, b in enumerate(art.body_names) if "shoulder" in b]
+    dt = 0.02
+    raw = np.array([-1.0, 1.0, -4.0, 0.5, -0.05, -1.0, -0.00002, -0.0005, -4.0, 1.0, -0.25, -0.0, -0.01, -0.0], np.float32) * np.float32(dt)
+    q0 = default_pose(art).astype(np.float32)
+    cfg = dict(rew_scales=raw, knee=np.array(knee), feet=np.array(feet), base_indices=np.array(shoulders), base_body=0, allow_knee=True, hound=True,
+               base_height_target=0.52, noise_scale_vec=None, dt=dt, max_len=7, push=False, default_dof_pos=q0[:12],
+               init_root=np.array([0, 0, 0.62, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0], np.float32), cmd_x=[-2, 2], cmd_y=[-1, 1], cmd_yaw=[-1, 1],
+               custom_origins=False, curriculum=True, terrain=None, max_episode_length_s=20.0, lin_vel_scale=2.0, ang_vel_scale=0.25, dof_pos_scale=1.0,
+               dof_vel_scale=0.05, height_meas_scale=5.0, push_interval=1000,
+               arm=dict(dof_noise=0.25, lower=np.full(6, -1.57, np.float32), upper=np.full(6, 1.57, np.float32)))
+    c = useful_cfg_struct(cfg, art)
+    for i, v in enumerate(q0):
+        c.default_dof_pos[i] = float(v)
+    jac_body = int(c.jac_body)
+
+    def arm_mats(root, dofs):
+        mm = np.zeros((n, 6, 6), np.float32)
+        jj = np.zeros((n, 6, 6), np.float32)
+        for e in range(n):
+            H, _ = O.crba_rnea(m, sp, root[e].astype(np.float64), dofs[e].astype(np.float64))
+            mm[e] = H[18:24, 18:24]
+            bp, _ = urdf.body_poses(art, dofs[e, :, 0].astype(np.float64), root[e, :3], root[e, 3:7])
+            r = bp[jac_body] - root[e, :3]
+            jj[e] = np.eye(6)
+            jj[e, 0, 4], jj[e, 0, 5], jj[e, 1, 3], jj[e, 1, 5], jj[e, 2, 3], jj[e, 2, 4] = r[2], -r[1], -r[2], r[0], r[1], -r[0]
+        return mm, jj
+
+    be = make_backend(art, sp, props, n)
+    resets = 0
+    try:
+        be.terrain_create(c)
+        root, dof = standing_state(art, n, rng, 0.55)
+        dof[:, 12:, 0] = rng.uniform(-0.3, 0.3, (n, 6))
+        st = dict(root=root, dof_pos=dof[:, :12, 0].copy(), dof_vel=dof[:, :12, 1].copy(), arm_q=dof[:, 12:, 0].copy(), arm_qd=dof[:, 12:, 1].copy(),
+                  contact=np.zeros((n, nb, 3), np.float32), torques=np.zeros((n, nd), np.float32), commands=np.zeros((n, 4), np.float32),
+                  actions=np.zeros((n, nd), np.float32), last_actions=np.zeros((n, nd), np.float32), last_dof_vel=np.zeros((n, 12), np.float32),
+                  feet_air_time=np.zeros((n, 4), np.float32), progress=np.zeros(n, np.int64), timeout_prev=np.zeros(n, bool),
+                  episode_sums=np.zeros((13, n), np.float32), terrain_levels=np.zeros(n, np.int64), eef_state=np.zeros((n, 13), np.float32),
+                  arm_commands=np.zeros((n, 3), np.float32))
+        st["commands"][:, 0] = 0.5
+        mm, jj = arm_mats(root, dof)
+        be.set_state(root, dof)
+        be.set_task(commands=st["commands"], reset=np.zeros(n, np.int64), arm_mm=mm, arm_jac=jj)
+        for k in range(steps):
+            actions = rng.uniform(-1, 1, (n, nd)).astype(np.float32)
+            draws = dict(reset=rng.uniform(0, 1, (n, 35)).astype(np.float32), noise=np.zeros((n, 204), np.float32), push=np.zeros((n, 2), np.float32))
+            be.set_step(k + 1, 1)
+            be.task_step(actions, draws)
+            st["actions"] = actions.copy()
+            dofs = np.concatenate([np.stack([st["dof_pos"], st["dof_vel"]], axis=2), np.stack([st["arm_q"], st["arm_qd"]], axis=2)], axis=1).astype(np.float32)
+            dpose = actions[:, 12:] * np.array([[0.1, 0.1, 0.1, 0.5, 0.5, 0.5]], np.float32)
+            for it in range(5):
+                if it < 4:
+                    ua = tm.osc_torques(mm, jj, dpose, st["eef_state"][:, 7:], dofs[:, 12:, 0], dofs[:, 12:, 1])
+                    tl = np.clip(np.float32(80.0) * (np.float32(0.5) * actions[:, :12] + q0[None, :12] - dofs[:, :12, 0]) - np.float32(2.0) * dofs[:, :12, 1], -80, 80)
+                    tq = np.concatenate([tl, ua], axis=1).astype(np.float32)
+                f, cf = O.simulate(m, sp, props, st["root"], dofs, np.zeros((n, nd), np.float32), tq)
+            st["dof_pos"], st["dof_vel"], st["arm_q"], st["arm_qd"] = dofs[:, :12, 0].copy(), dofs[:, :12, 1].copy(), dofs[:, 12:, 0].copy(), dofs[:, 12:, 1].copy()
+            st["torques"], st["contact"] = tq, cf
+            mm, jj = arm_mats(st["root"], dofs)          # refresh_jacobian / refresh_mass_matrix happen before reset_idx
+            obs, rew, reset, timeout, measured, extras = tm.terrain_post_physics(st, cfg, draws)
+            st["timeout_prev"] = timeout.astype(bool)
+            rk, dk = be.get_state()
+            t = be.get_task()
+            assert np.array_equal(t["reset"], reset), f"step {k}: reset decisions differ"
+            assert np.abs(rk - st["root"]).max() < 3e-3, f"step {k}: root deviates {np.abs(rk - st['root']).max():.2e}"
+            assert np.abs(dk[:, :12, 0] - st["dof_pos"]).max() < 5e-3 and np.abs(dk[:, 12:, 0] - st["arm_q"]).max() < 5e-3
+            np.testing.assert_allclose(t["torques"], tq, rtol=0, atol=0.2)
+            np.testing.assert_allclose(t["arm_mm"], mm, rtol=2e-3, atol=2e-4)
+            np.testing.assert_allclose(t["arm_jac"], jj, rtol=0, atol=2e-3)
+            np.testing.assert_allclose(t["obs"], obs, rtol=0, atol=3e-2)
+            np.testing.assert_allclose(t["rew"], rew, rtol=0, atol=2e-3)
+            st["root"], st["dof_pos"], st["dof_vel"], st["arm_q"], st["arm_qd"] = rk.copy(), dk[:, :12, 0].copy(), dk[:, :12, 1].copy(), dk[:, 12:, 0].copy(), dk[:, 12:, 1].copy()
+            st["commands"], st["last_dof_vel"], st["episode_sums"] = t["commands"].copy(), t["last_dof_vel"][:, :12].copy(), t["episode_sums"].copy()
+            mm, jj = t["arm_mm"].copy(), t["arm_jac"].copy()
             resets += int(reset.sum())
     finally:
         be.close()

@@ -54,3 +54,11 @@ def test_terrain_golden(name):
 @pytest.mark.parametrize("robot,heightfield", [("anymal_minimal", True), ("hound", False)])
 def test_terrain_step(robot, heightfield):
     kc.check_terrain_step(make, robot, n=64, heightfield=heightfield)
+
+
+def test_useful_hound_golden():
+    kc.check_useful_golden(make)
+
+
+def test_useful_hound_step():
+    kc.check_useful_step(make, n=64)

@@ -124,3 +124,25 @@ def test_terrain_task_contract(task, terrain):
     assert bool((env.root_states[:, 2] < z0 + 0.05).all())
     if terrain == "trimesh":
         assert float(env.measured_heights.abs().max()) > 0.0
+
+
+def test_useful_hound_task_contract():
+    import torch
+
+    import isaacgymenv_b200 as b2g
+
+    n = 64
+    env = b2g.make(seed=5, task="UsefulHound", num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True)
+    assert env.num_obs == 204 and env.num_acts == 18 and env.num_dof == 18 and env.num_bodies == 24
+    assert env._mm.shape == (n, 6, 6) and env._j_eef.shape == (n, 6, 6) and env._eef_state.shape == (n, 13)
+    g = torch.Generator(device="cuda:0").manual_seed(0)
+    for k in range(40):
+        obs, rew, reset, extras = env.step(2 * torch.rand(n, 18, device="cuda:0", generator=g) - 1)
+    assert obs["obs"].shape == (n, 204) and torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all()
+    assert reset.dtype == torch.bool
+    # arm mass-matrix block is symmetric positive definite; Jacobian slice has the base-column structure
+    mm = env._mm
+    assert torch.allclose(mm, mm.transpose(1, 2), atol=1e-5) and bool((torch.linalg.eigvalsh(mm.double()) > 0).all())
+    assert torch.allclose(env._j_eef[:, :3, :3], torch.eye(3, device="cuda:0").expand(n, 3, 3))
+    assert float(env.torques[:, 12:].abs().max()) > 0.0            # the OSC law drives the arm
+    assert float(obs["obs"][:, 194:201].abs().max()) == 0.0        # end-effector slots stay at the never-refreshed value (quirk Q12)
