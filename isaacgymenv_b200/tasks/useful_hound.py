@@ -43,9 +43,9 @@ class UsefulHound(HoundTerrain):
         self.eef_index = self.gym.find_actor_rigid_body_handle(env, actor, self.cfg["env"]["urdfAsset"]["endpointName"])
         self.hand_joint_index = self.gym.get_actor_joint_dict(env, actor)["joint6"]
         props = self.gym.get_actor_dof_properties(env, actor)
-        self.houndarm_dof_lower_limits = torch.tensor(props["lower"][12:], device=self.device)
-        self.houndarm_dof_upper_limits = torch.tensor(props["upper"][12:], device=self.device)
-        self._houndarm_effort_limits = torch.tensor(props["effort"][12:], device=self.device)
+        self.houndarm_dof_lower_limits = torch.tensor(props["lower"][12:].astype("float32").copy(), device=self.device)
+        self.houndarm_dof_upper_limits = torch.tensor(props["upper"][12:].astype("float32").copy(), device=self.device)
+        self._houndarm_effort_limits = torch.tensor(props["effort"][12:].astype("float32").copy(), device=self.device)
 
     def _fused_cfg(self) -> _abi.TerrainCfg:
         c = super()._fused_cfg()
