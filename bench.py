@@ -30,6 +30,18 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 ALGO_BYTES_PER_ENV_STEP = 788      # boundary traffic of one Anymal env-step
 WORKLOAD = "Anymal flat-terrain, 4096 envs/GPU, implicit PD position drive (Kp 85, Kd 2), dt 0.02 s x 2 sub-steps, random actions"
+# other hot-path configs (--task): algorithmic bytes per env-step, env count, kernels per step, workload text
+TASKS = {
+    "Anymal": (788, 4096, "k_anymal_step", None, WORKLOAD),
+    "Hound": (836, 4096, "k_anymal_step", None, "Hound flat-terrain, 4096 envs/GPU, implicit PD position drive, dt 0.02 s x 2 sub-steps, random actions"),
+    "Cartpole": (88, 512, "k_cartpole_step", None, "Cartpole, 512 envs, effort control, dt 0.0166 s x 2 sub-steps, random actions"),
+    "AnymalTerrain": (2256, 4096, "k_terrain_phys", {"env": {"terrain": {"terrainType": "trimesh"}}},
+                      "AnymalTerrain rough heightfield (10 levels x 20 types, 1200x2000 int16) + 140-point height scan, 4096 envs/GPU, explicit PD "
+                      "decimation 4 (+1 sim step), dt 0.005 s, observation noise on, random actions"),
+    "HoundTerrain": (2256, 4096, "k_terrain_phys", None, "HoundTerrain (plane), 4096 envs/GPU, explicit PD decimation 4 (+1), dt 0.005 s, random actions"),
+    "UsefulHound": (2696, 4096, "k_terrain_phys", None, "UsefulHound hound + 6-DOF arm (OSC), 4096 envs/GPU, 18 actions, 204 obs, explicit PD decimation 4 (+1), "
+                    "dt 0.005 s, random actions"),
+}
 
 
 def measured_peak():
@@ -140,16 +152,24 @@ def run_ours(args):
     from isaacgymenv_b200 import _lib
 
     lib = _lib.load()
-    env = isaacgymenv_b200.make(seed=42 + rank, task="Anymal", num_envs=ENVS_PER_GPU, sim_device=dev, rl_device=dev, headless=True)
+    algo_bytes, envs_per_gpu, kernel_name, overrides, workload = TASKS[args.task]
+    env = isaacgymenv_b200.make(seed=42 + rank, task=args.task, num_envs=envs_per_gpu, sim_device=dev, rl_device=dev, headless=True, overrides=overrides)
     n, na = env.num_envs, env.num_actions
+    is_terrain = hasattr(env, "common_step_counter")
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     pool = [2.0 * torch.rand(n, na, device=dev, generator=g) - 1.0 for _ in range(16)]
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 192 MiB > 126 MB L2
 
+    def tick():
+        if is_terrain:      # the task's common_step_counter drives pushes and the noise stream
+            env.common_step_counter += 1
+            lib.b2g_task_terrain_set_step(env.sim.handle, int(env.common_step_counter))
+
     def step_dev(i):
-        _lib.check(lib.b2g_task_anymal_step(env.sim.handle, C.c_void_p(pool[i % 16].data_ptr()), sptr), "step")
+        tick()
+        _lib.check(lib.b2g_task_step(env.sim.handle, C.c_void_p(pool[i % 16].data_ptr()), sptr), "step")
 
     def barrier():
         if world > 1:
@@ -191,7 +211,8 @@ def run_ours(args):
     h_to = torch.empty(n, dtype=torch.int64).pin_memory()
 
     def step_host(i):
-        _lib.check(lib.b2g_task_anymal_step_host(env.sim.handle, C.c_void_p(h_act[i % 16].data_ptr()), C.c_void_p(h_obs.data_ptr()),
+        tick()
+        _lib.check(lib.b2g_task_step_host(env.sim.handle, C.c_void_p(h_act[i % 16].data_ptr()), C.c_void_p(h_obs.data_ptr()),
                                                  C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_reset.data_ptr()), C.c_void_p(h_to.data_ptr()), sptr), "step_host")
 
     for i in range(3):
@@ -216,16 +237,16 @@ def run_ours(args):
         value = total / (cold_ms * 1e-3)
         peak, peak_src = measured_peak()
         kernel_s = cold_ms * 1e-3 / args.steps
-        achieved = ALGO_BYTES_PER_ENV_STEP * n / kernel_s / 1e9
+        achieved = algo_bytes * n / kernel_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tp):
+        if os.path.isfile(tp) and args.task == "Anymal":
             try:
                 traffic = json.load(open(tp)).get("k_anymal_step_dram_bytes_per_launch")
             except Exception:
                 traffic = None
         cpu = None
-        if world == 1 or rank == 0:
+        if args.task == "Anymal":
             threads = os.cpu_count() or 1
             cpu_steps = 6
             cv, _ = time_cpu(1024, cpu_steps, 1, threads)
@@ -233,16 +254,16 @@ def run_ours(args):
                    "sample": f"1024 of 4096 envs x {cpu_steps} steps; CPU restatement of the step (oracle), NOT PhysX (Isaac Gym not installed)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": cold_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "envs_per_gpu": n, "l2": "flushed between timed steps (192 MiB fill, untimed)",
+                "config": {"workload": workload, "task": args.task, "envs_per_gpu": n, "l2": "flushed between timed steps (192 MiB fill, untimed)",
                            "timing": "per-step CUDA events on the launch stream, summed; max over ranks"},
                 "value_warm_l2": total / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / args.steps,
                 "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * na * 4,
                         "d2h_bytes_per_step": n * env.num_obs * 4 + n * 4 + n * 8 + n * 8, "ms_per_step": e2e_ms / args.steps,
-                        "path": "b2g_task_anymal_step_host (C ABI): pinned host actions -> obs/rew/reset/time_outs in pinned host memory, stream sync per step"},
+                        "path": "b2g_task_step_host (C ABI): pinned host actions -> obs/rew/reset/time_outs in pinned host memory, stream sync per step"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "k_anymal_step", "peak_source": peak_src,
-                             "note": "latency/issue-bound by construction: 3.2 MB algorithmic bytes per launch, working set L2-resident; see profiles/"},
+                             "kernel": kernel_name, "peak_source": peak_src,
+                             "note": "latency/issue-bound by construction: the per-launch working set (a few MB) is L2-resident; see profiles/ and DESIGN.md"},
                 "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -255,6 +276,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--task", default="Anymal", choices=sorted(TASKS), help="hot-path config to time (default: the headline Anymal config)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 50:
