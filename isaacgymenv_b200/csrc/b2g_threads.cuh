@@ -466,10 +466,16 @@ B2G_HD inline void mm6(const float* a, const float* b, float* o, bool ta = false
         }
     for (int i = 0; i < 36; i++) o[i] = t[i];
 }
-// _compute_osc_torques (tasks/useful_hound.py:660-691)
-B2G_HD inline void osc_torques(const float* mm, const float* j, const float* dpose, const float* eef_vel, const float* q, const float* qd, float kp,
-                               float kp_null, const float* effort, float* u) {
-    const float kd = 2.0f * sqrtf(kp), kdn = 2.0f * sqrtf(kp_null);
+// _compute_osc_torques (tasks/useful_hound.py:660-691), split in two because the mass-matrix block, the Jacobian slice, the
+// commanded pose change and the end-effector velocity row do not change inside one policy step:
+//   prepare (once per step):  u_task = J^T Lambda (kp dpose - kd eef_vel),  N = (I - J^T Lambda J M^-1) M
+//   apply   (every decimation step):  u = clamp(u_task + N (kd_null (-qd) + kp_null wrap(-q)), +-effort)
+struct OscPrepared {
+    float u_task[6];
+    float N[36];
+};
+B2G_HD inline void osc_prepare(const float* mm, const float* j, const float* dpose, const float* eef_vel, float kp, OscPrepared& P) {
+    const float kd = 2.0f * sqrtf(kp);
     float mm_inv[36], t[36], m_eef_inv[36], m_eef[36], j_eef_inv[36];
     inv6(mm, mm_inv);
     mm6(j, mm_inv, t);
@@ -478,23 +484,26 @@ B2G_HD inline void osc_torques(const float* mm, const float* j, const float* dpo
     float w[6], v[6];
     for (int i = 0; i < 6; i++) w[i] = kp * dpose[i] - kd * eef_vel[i];
     for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += m_eef[i * 6 + k] * w[k]; v[i] = acc; }
-    for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += j[k * 6 + i] * v[k]; u[i] = acc; }          // J^T (Lambda w)
+    for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += j[k * 6 + i] * v[k]; P.u_task[i] = acc; }   // J^T (Lambda w)
     mm6(m_eef, j, t);
     mm6(t, mm_inv, j_eef_inv);
-    float un[6], mu_[6];
+    mm6(j, j_eef_inv, t, true, false);                  // J^T j_eef_inv
+    for (int i = 0; i < 36; i++) t[i] = ((i / 6 == i % 6) ? 1.0f : 0.0f) - t[i];
+    mm6(t, mm, P.N);
+}
+B2G_HD inline void osc_apply(const OscPrepared& P, const float* q, const float* qd, float kp_null, const float* effort, float* u) {
+    const float kdn = 2.0f * sqrtf(kp_null);
     const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+    float un[6];
     for (int i = 0; i < 6; i++) {
         float a = 0.0f - q[i] + pi;
         a = a - two_pi * floorf(a / two_pi);            // python-style remainder (eager torch %)
         un[i] = kdn * -qd[i] + kp_null * (a - pi);
     }
-    for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += mm[i * 6 + k] * un[k]; mu_[i] = acc; }
-    mm6(j, j_eef_inv, t, true, false);                  // J^T j_eef_inv
     for (int i = 0; i < 6; i++) {
-        float acc = mu_[i];
-        for (int k = 0; k < 6; k++) acc -= t[i * 6 + k] * mu_[k];
-        u[i] += acc;
-        u[i] = fminf(fmaxf(u[i], -effort[i]), effort[i]);
+        float acc = P.u_task[i];
+        for (int k = 0; k < 6; k++) acc += P.N[i * 6 + k] * un[k];
+        u[i] = fminf(fmaxf(acc, -effort[i]), effort[i]);
     }
 }
 // Kinematics + composite-rigid-body pass over one chain: joint-space mass-matrix block of the chain (n x n, row-major in
@@ -603,20 +612,22 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
     }
     const bool is_arm = (C.arm_chain >= 0) && (lane == C.arm_chain);
     // arm lane: OSC torque from the stored mass-matrix / Jacobian slices, the end-effector velocity row and the live arm DOFs
-    auto arm_osc = [&](float* out) {
-        float dpose[6], qa[6], qda[6], eff[6], u[6];
-        const float* ev = T.eef_state + (size_t)env * 13 + 7;
-        for (int j = 0; j < 6; j++) {
-            dpose[j] = 0; qa[j] = 0; qda[j] = 0; eff[j] = 0;
-        }
+    OscPrepared osc;
+    if (is_arm) {
+        float dpose[6];
+        for (int j = 0; j < 6; j++) dpose[j] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < NL; j++) {
-            if (j < 6 && j < len) {
-                dpose[j] = act[j] * C.arm_cmd_limit[j] / C.arm_action_scale;
-                qa[j] = st.q[j]; qda[j] = st.qd[j]; eff[j] = M->dof[d0 + j].effort;
-            }
-        }
-        osc_torques(T.arm_mm + (size_t)env * 36, T.arm_jac + (size_t)env * 36, dpose, ev, qa, qda, C.arm_kp, C.arm_kp_null, eff, u);
+        for (int j = 0; j < NL; j++)
+            if (j < 6 && j < len) dpose[j] = act[j] * C.arm_cmd_limit[j] / C.arm_action_scale;
+        osc_prepare(T.arm_mm + (size_t)env * 36, T.arm_jac + (size_t)env * 36, dpose, T.eef_state + (size_t)env * 13 + 7, C.arm_kp, osc);
+    }
+    auto arm_osc = [&](float* out) {
+        float qa[6], qda[6], eff[6], u[6];
+        for (int j = 0; j < 6; j++) { qa[j] = 0; qda[j] = 0; eff[j] = 0; }
+#pragma unroll
+        for (int j = 0; j < NL; j++)
+            if (j < 6 && j < len) { qa[j] = st.q[j]; qda[j] = st.qd[j]; eff[j] = M->dof[d0 + j].effort; }
+        osc_apply(osc, qa, qda, C.arm_kp_null, eff, u);
 #pragma unroll
         for (int j = 0; j < NL; j++)
             if (j < 6 && j < len) out[j] = u[j];
