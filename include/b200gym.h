@@ -138,7 +138,7 @@ enum b2g_tensor_kind {
     B2G_T_RIGID_BODY_STATE = 4, /* (N*nb,13) f32                                             */
     B2G_T_DOF_TARGET = 5,       /* (N*nd) f32 position/velocity targets                      */
     B2G_T_DOF_ACTUATION = 6,    /* (N*nd) f32 efforts                                        */
-    B2G_T_JACOBIAN = 7,         /* (N,nb,6,nd+6 or nd) f32                                   */
+    B2G_T_JACOBIAN = 7,         /* floating base (N,nb,6,6+nd), fixed base (N,nb-1,6,nd) f32; rows lin3, ang3 */
     B2G_T_MASS_MATRIX = 8,      /* (N,nd,nd) f32 (joint block, Isaac Gym convention)         */
     B2G_T_FRICTION = 9,         /* (N) f32 per-env shape friction coefficient                */
     B2G_T_COUNT

@@ -192,6 +192,18 @@ __global__ void k_body_state(const DevModel* M, const float* root, const float* 
     body_state_env(M, root + (size_t)e * 13, dof + (size_t)e * M->n_dof * 2, out + (size_t)e * M->n_bodies * 13);
 }
 
+__global__ void k_mass_matrix(const DevModel* M, const float* root, const float* dof, float* out, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    mass_matrix_env(M, root + (size_t)e * 13, dof + (size_t)e * M->n_dof * 2, out + (size_t)e * M->n_dof * M->n_dof);
+}
+
+__global__ void k_jacobian(const DevModel* M, const float* root, const float* dof, float* out, int n, int per_env) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    jacobian_env(M, root + (size_t)e * 13, dof + (size_t)e * M->n_dof * 2, out + (size_t)e * per_env);
+}
+
 // rows idx[0..n) of src -> dst, row = `row` floats (gym.set_*_tensor_indexed)
 __global__ void k_copy_rows(float* dst, const float* src, const int* idx, int n, int row) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,7 +333,7 @@ size_t tensor_floats(const b2g_sim* s, int kind) {
         case B2G_T_RIGID_BODY_STATE: return n * nb * 13;
         case B2G_T_DOF_TARGET: return n * nd;
         case B2G_T_DOF_ACTUATION: return n * nd;
-        case B2G_T_JACOBIAN: return n * nb * 6 * jcols;
+        case B2G_T_JACOBIAN: return n * (nb - (s->model.fixed_base ? 1 : 0)) * 6 * jcols;
         case B2G_T_MASS_MATRIX: return n * nd * nd;
         case B2G_T_FRICTION: return n;
         default: return 0;
@@ -342,7 +354,7 @@ void describe(const b2g_sim* s, int kind, b2g_tensor_desc* d) {
         case B2G_T_RIGID_BODY_STATE: d->ndim = 2; d->shape[0] = n * nb; d->shape[1] = 13; break;
         case B2G_T_DOF_TARGET: d->ndim = 1; d->shape[0] = n * nd; break;
         case B2G_T_DOF_ACTUATION: d->ndim = 1; d->shape[0] = n * nd; break;
-        case B2G_T_JACOBIAN: d->ndim = 4; d->shape[0] = n; d->shape[1] = nb; d->shape[2] = 6; d->shape[3] = jcols; break;
+        case B2G_T_JACOBIAN: d->ndim = 4; d->shape[0] = n; d->shape[1] = nb - (s->model.fixed_base ? 1 : 0); d->shape[2] = 6; d->shape[3] = jcols; break;
         case B2G_T_MASS_MATRIX: d->ndim = 3; d->shape[0] = n; d->shape[1] = nd; d->shape[2] = nd; break;
         case B2G_T_FRICTION: d->ndim = 1; d->shape[0] = n; break;
         default: d->ndim = 0;
@@ -620,7 +632,20 @@ int b2g_sim_refresh(b2g_sim* s, int kind, void* stream) {
             return (int)B2G_OK;
         });
     }
-    if (kind == B2G_T_JACOBIAN || kind == B2G_T_MASS_MATRIX) return fail(B2G_ERR_UNSUPPORTED, "jacobian / mass-matrix tensors are not implemented yet");
+    if (kind == B2G_T_JACOBIAN || kind == B2G_T_MASS_MATRIX) {
+        if (!s->t[kind]) return B2G_OK;      // never acquired: nothing to refresh
+        return with_device(s, [&]() {
+            cudaStream_t st = (cudaStream_t)stream;
+            if (kind == B2G_T_MASS_MATRIX)
+                k_mass_matrix<<<(s->n_envs + 63) / 64, 64, 0, st>>>(s->d_model, s->t[B2G_T_ROOT_STATE], s->t[B2G_T_DOF_STATE], s->t[kind], s->n_envs);
+            else
+                k_jacobian<<<(s->n_envs + 63) / 64, 64, 0, st>>>(s->d_model, s->t[B2G_T_ROOT_STATE], s->t[B2G_T_DOF_STATE], s->t[kind], s->n_envs,
+                                                                 (int)(tensor_floats(s, kind) / s->n_envs));
+            s->launches++;
+            CUDA_TRY(cudaGetLastError());
+            return (int)B2G_OK;
+        });
+    }
     return B2G_OK;   // live state: nothing to do
 }
 

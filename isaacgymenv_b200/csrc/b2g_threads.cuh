@@ -927,6 +927,76 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
     }
 }
 
+
+// refresh_mass_matrix_tensors: joint-space block of the mass matrix, (nd x nd) per environment (Isaac Gym convention used by
+// tasks/useful_hound.py:452-455).  DOFs of different chains couple only through the root, which is not part of this block,
+// so the matrix is block diagonal over the chains.  One thread per environment.
+B2G_HD inline void mass_matrix_env(const DevModel* M, const float* root, const float* dof, float* out) {
+    const int nd = M->n_dof;
+    for (int i = 0; i < nd * nd; i++) out[i] = 0.0f;
+    for (int c = 0; c < M->n_chains; c++) {
+        const int d0 = M->chain_start[c], n = M->chain_len[c];
+        float q[B2G_MAX_CHAIN_LEN], qd[B2G_MAX_CHAIN_LEN], mm[36];
+        for (int j = 0; j < n; j++) { q[j] = dof[2 * (d0 + j)]; qd[j] = 0.0f; }
+        V3 p; M3 r; SV v;
+        chain_crba(M, d0, n, root + 3, q, mm, -1, &p, &r, qd, V3{0, 0, 0}, V3{0, 0, 0}, &v);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) out[(d0 + i) * nd + d0 + j] = mm[i * 6 + j];
+    }
+}
+
+// refresh_jacobian_tensors: geometric Jacobian of every API body, rows = (linear 3, angular 3) of the body-frame origin in the
+// world frame; columns = [6 base columns (linear, angular) for a floating base] + one per DOF.  Floating base: (nb, 6, 6+nd);
+// fixed base: (nb-1, 6, nd) with the root body left out (Isaac Gym convention).  One thread per environment.
+B2G_HD inline void jacobian_env(const DevModel* M, const float* root, const float* dof, float* out) {
+    const int nd = M->n_dof, nb = M->n_bodies;
+    const int ncol = nd + (M->fixed_base ? 0 : 6), row0 = M->fixed_base ? 1 : 0;
+    M3 Rl[B2G_MAX_LINKS];
+    V3 pl[B2G_MAX_LINKS], axw[B2G_MAX_DOF], pj[B2G_MAX_DOF];
+    Rl[0] = quat_to_m3(root[3], root[4], root[5], root[6]);
+    pl[0] = V3{0, 0, 0};
+    for (int c = 0; c < M->n_chains; c++)
+        for (int j = 0; j < M->chain_len[c]; j++) {
+            const int d = M->chain_start[c] + j, l = d + 1, p = (j == 0) ? 0 : l - 1;
+            const DevDof& D = M->dof[d];
+            M3 jr;
+            for (int k = 0; k < 9; k++) jr.m[k] = D.jrot[k];
+            const V3 ax = V3{D.axis[0], D.axis[1], D.axis[2]};
+            const M3 RJ = mul(Rl[p], jr);
+            pj[d] = pl[p] + mul(Rl[p], V3{D.jpos[0], D.jpos[1], D.jpos[2]});
+            axw[d] = mul(RJ, ax);
+            if (D.type == B2G_JOINT_REVOLUTE) { Rl[l] = mul(RJ, axis_angle_m3(ax, dof[2 * d])); pl[l] = pj[d]; }
+            else { Rl[l] = RJ; pl[l] = pj[d] + axw[d] * dof[2 * d]; }
+        }
+    for (int b = row0; b < nb; b++) {
+        float* J = out + (size_t)(b - row0) * 6 * ncol;
+        for (int i = 0; i < 6 * ncol; i++) J[i] = 0.0f;
+        const int l = M->body_link[b];
+        const V3 pb = pl[l] + mul(Rl[l], V3{M->body_pos[b][0], M->body_pos[b][1], M->body_pos[b][2]});
+        int c0 = 0;
+        if (!M->fixed_base) {
+            for (int i = 0; i < 6; i++) J[i * ncol + i] = 1.0f;
+            J[0 * ncol + 4] = pb.z; J[0 * ncol + 5] = -pb.y; J[1 * ncol + 3] = -pb.z; J[1 * ncol + 5] = pb.x; J[2 * ncol + 3] = pb.y; J[2 * ncol + 4] = -pb.x;
+            c0 = 6;
+        }
+        if (l > 0) {
+            // DOFs on the path root -> link l: those of its chain up to and including DOF l-1
+            int dfirst = 0;
+            for (int c = 0; c < M->n_chains; c++)
+                if (l - 1 >= M->chain_start[c] && l - 1 < M->chain_start[c] + M->chain_len[c]) dfirst = M->chain_start[c];
+            for (int d = dfirst; d <= l - 1; d++) {
+                if (M->dof[d].type == B2G_JOINT_REVOLUTE) {
+                    const V3 lin = cross(axw[d], pb - pj[d]);
+                    J[0 * ncol + c0 + d] = lin.x; J[1 * ncol + c0 + d] = lin.y; J[2 * ncol + c0 + d] = lin.z;
+                    J[3 * ncol + c0 + d] = axw[d].x; J[4 * ncol + c0 + d] = axw[d].y; J[5 * ncol + c0 + d] = axw[d].z;
+                } else {
+                    J[0 * ncol + c0 + d] = axw[d].x; J[1 * ncol + c0 + d] = axw[d].y; J[2 * ncol + c0 + d] = axw[d].z;
+                }
+            }
+        }
+    }
+}
+
 // refresh_rigid_body_state_tensor: world pose + velocity of every API body (N,nb,13). One thread per env.
 B2G_HD B2G_INL void body_state_env(const DevModel* M, const float* root, const float* dof, float* out) {
     const int nd = M->n_dof;

@@ -50,6 +50,9 @@ class EmuBackend:
     def forward_dynamics(self, tau):
         return self.emu.forward_dynamics(self.model, self.params, self.props, self.root.copy(), self.dof.copy(), tau)
 
+    def jacobian_mass_matrix(self):
+        return self.emu.jacobian_mass_matrix(self.model, self.props, self.root, self.dof)
+
     # ---- fused flat task ----
     def cartpole_create(self, cfg):
         n = self.n
@@ -206,6 +209,13 @@ class CudaBackend:
         self._lib.check(self.lib.b2g_sim_forward_dynamics(self.sim, C.c_void_p(qdd.data_ptr()), C.c_void_p(a0.data_ptr()), self.stream), "fd")
         torch.cuda.synchronize()
         return qdd.cpu().numpy(), a0.cpu().numpy()
+
+    def jacobian_mass_matrix(self):
+        j, m = self._tensor(_abi.T_JACOBIAN), self._tensor(_abi.T_MASS_MATRIX)
+        self._lib.check(self.lib.b2g_sim_refresh(self.sim, _abi.T_JACOBIAN, self.stream), "refresh jacobian")
+        self._lib.check(self.lib.b2g_sim_refresh(self.sim, _abi.T_MASS_MATRIX, self.stream), "refresh mass matrix")
+        self.torch.cuda.synchronize()
+        return j.cpu().numpy().copy(), m.cpu().numpy().copy()
 
     def anymal_create(self, cfg):
         self._lib.check(self.lib.b2g_task_anymal_create(self.sim, C.byref(cfg)), "task create")

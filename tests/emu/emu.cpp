@@ -227,6 +227,19 @@ int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_prop
     return 0;
 }
 
+// refresh_jacobian_tensors / refresh_mass_matrix_tensors for n_envs environments
+int emu_jac_mm(const b2g_model* m, const b2g_dof_props* dp, int n_envs, const float* root, const float* dof, float* jac, int jac_per_env, float* mm) {
+    DevModel* dm = new DevModel;
+    const char* why;
+    if (pack_dev_model(*m, *dp, *dm, &why) != 0) { delete dm; return -1; }
+    for (int e = 0; e < n_envs; e++) {
+        jacobian_env(dm, root + (size_t)e * 13, dof + (size_t)e * m->n_dof * 2, jac + (size_t)e * jac_per_env);
+        mass_matrix_env(dm, root + (size_t)e * 13, dof + (size_t)e * m->n_dof * 2, mm + (size_t)e * m->n_dof * m->n_dof);
+    }
+    delete dm;
+    return 0;
+}
+
 // Cartpole: mode 1 = step, mode 2 = post_physics_step only
 int emu_cartpole(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, const b2g_cartpole_cfg* cfg, int mode,
                  int n_envs, float* root, float* dof, float* dof_force, float* contact, const float* actions_in, float* obs,

@@ -111,3 +111,15 @@ def terrain(model, params, props, cfg, mode, bufs, common_step, init_done, heigh
     rc = lib().emu_terrain(C.byref(model), C.byref(params), C.byref(props), C.byref(heightfield) if heightfield is not None else None,
                            _p(hs, C.c_int16), C.byref(cfg), C.c_int(mode), C.c_int(n), C.c_longlong(common_step), C.c_int(init_done), C.byref(tb))
     assert rc == 0, rc
+
+
+def jacobian_mass_matrix(model, props, root, dof):
+    n, nd, nb = root.shape[0], model.n_dof, model.n_bodies
+    rows = nb - (1 if model.fixed_base else 0)
+    ncol = nd + (0 if model.fixed_base else 6)
+    jac = np.zeros((n, rows, 6, ncol), np.float32)
+    mm = np.zeros((n, nd, nd), np.float32)
+    rc = lib().emu_jac_mm(C.byref(model), C.byref(props), C.c_int(n), _p(np.ascontiguousarray(root, np.float32)), _p(np.ascontiguousarray(dof, np.float32)),
+                          _p(jac), C.c_int(rows * 6 * ncol), _p(mm))
+    assert rc == 0, rc
+    return jac, mm

@@ -760,3 +760,51 @@ def check_useful_step(make_backend, n=6, steps=8, seed=21):
     finally:
         be.close()
     assert resets > 0
+
+
+# ------------------------------------------------------------------------------------------------
+def check_jacobian_mass_matrix(make_backend, robot="useful_hound", n=4, seed=31):
+    """acquire/refresh_jacobian_tensor and _mass_matrix_tensor: the Jacobian against finite differences of the independent numpy
+    kinematics (body-frame origin velocity per unit generalized velocity), the mass matrix against the oracle's CRBA joint block."""
+    from isaacgymenv_b200.model import urdf
+
+    art = load_robot(robot)
+    nd, nb = art.num_dofs, art.num_bodies
+    rng = np.random.default_rng(seed)
+    sp = flat_params(ground=False)
+    props = _abi.default_dof_props(art)
+    root, dof = random_flying_state(art, n, rng)
+    if art.fixed_base:
+        root[:, :3], root[:, 3:7] = [0, 0, 2.0], [0, 0, 0, 1]
+    be = make_backend(art, sp, props, n)
+    try:
+        be.set_state(root, dof)
+        jac, mm = be.jacobian_mass_matrix()
+    finally:
+        be.close()
+    m = _abi.pack_model(art)
+    fb = 0 if art.fixed_base else 6
+    row0 = 1 if art.fixed_base else 0
+    assert jac.shape == (n, nb - row0, 6, nd + fb) and mm.shape == (n, nd, nd)
+    for e in range(n):
+        H, _ = O.crba_rnea(m, sp, root[e].astype(np.float64), dof[e].astype(np.float64))
+        np.testing.assert_allclose(mm[e], H[fb:, fb:], rtol=2e-4, atol=2e-5)
+        q = dof[e, :, 0].astype(np.float64)
+        p0, r0 = urdf.body_poses(art, q, root[e, :3], root[e, 3:7])
+        eps = 1e-6
+        for d in range(nd):
+            qq = q.copy()
+            qq[d] += eps
+            p1, r1 = urdf.body_poses(art, qq, root[e, :3], root[e, 3:7])
+            lin = (p1 - p0) / eps
+            for b in range(row0, nb):
+                W = ((r1[b] - r0[b]) / eps) @ r0[b].T
+                ang = np.array([W[2, 1], W[0, 2], W[1, 0]])
+                np.testing.assert_allclose(jac[e, b - row0, :3, fb + d], lin[b], rtol=0, atol=2e-4)
+                np.testing.assert_allclose(jac[e, b - row0, 3:, fb + d], ang, rtol=0, atol=2e-4)
+        if fb:
+            for b in range(nb):
+                r = p0[b] - root[e, :3]
+                want = np.eye(6)
+                want[:3, 3:] = -np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
+                np.testing.assert_allclose(jac[e, b, :, :6], want, rtol=0, atol=2e-5)

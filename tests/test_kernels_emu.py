@@ -58,3 +58,8 @@ def test_useful_hound_golden():
 
 def test_useful_hound_step():
     kc.check_useful_step(make, n=4)
+
+
+@pytest.mark.parametrize("robot", ["useful_hound", "anymal", "cartpole"])
+def test_jacobian_mass_matrix(robot):
+    kc.check_jacobian_mass_matrix(make, robot)

@@ -178,3 +178,28 @@ def test_deterministic_and_finite_long_run(task, nact):
     for a, b in zip(outs[0], outs[1]):
         for x, y in zip(a, b):
             assert torch.equal(x, y), "two runs with the same seed diverged"
+
+
+def test_generic_jacobian_and_mass_matrix_agree_with_the_fused_arm_slices():
+    """gym.acquire_jacobian_tensor / acquire_mass_matrix_tensor (tasks/useful_hound.py:448-455) sliced the way the reference slices
+    them == the slices the fused UsefulHound kernel keeps for its OSC law."""
+    import torch
+
+    import isaacgymenv_b200 as b2g
+    from isaacgymenv_b200 import gymtorch
+
+    n = 32
+    env = b2g.make(seed=9, task="UsefulHound", num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True)
+    jac = gymtorch.wrap_tensor(env.gym.acquire_jacobian_tensor(env.sim, "UsefulHound"))
+    mm = gymtorch.wrap_tensor(env.gym.acquire_mass_matrix_tensor(env.sim, "UsefulHound"))
+    assert jac.shape == (n, 24, 6, 24) and mm.shape == (n, 18, 18)
+    env.reset_buf[:] = 0
+    env._reset_i64[:] = 0
+    obs, rew, reset, _ = env.step(torch.zeros(n, 18, device="cuda:0"))
+    alive = ~reset            # the fused slices are refreshed before resets, the generic tensors see the post-reset state
+    env.gym.refresh_jacobian_tensors(env.sim)
+    env.gym.refresh_mass_matrix_tensors(env.sim)
+    torch.cuda.synchronize()
+    assert int(alive.sum()) > 0
+    torch.testing.assert_close(jac[alive][:, env.hand_joint_index, :, :6], env._j_eef[alive], rtol=0, atol=1e-5)
+    torch.testing.assert_close(mm[alive][:, -6:, -6:], env._mm[alive], rtol=1e-5, atol=1e-6)
