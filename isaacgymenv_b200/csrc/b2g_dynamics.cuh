@@ -425,8 +425,9 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
 #pragma unroll
                 for (int c = 0; c < 3; c++) A[c * 3 + b] = dot(pv, dirs[c]);
             }
-            sc.at(s, CF_ANN) = A[0]; sc.at(s, CF_ANT1) = A[3]; sc.at(s, CF_ANT2) = A[6];
-            sc.at(s, CF_AT1T1) = A[4]; sc.at(s, CF_AT1T2) = A[7]; sc.at(s, CF_AT2T2) = A[8];
+            // diagonal entries are kept as reciprocals: the sweeps multiply instead of dividing
+            sc.at(s, CF_ANN) = 1.0f / A[0]; sc.at(s, CF_ANT1) = A[3]; sc.at(s, CF_ANT2) = A[6];
+            sc.at(s, CF_AT1T1) = 1.0f / A[4]; sc.at(s, CF_AT1T2) = A[7]; sc.at(s, CF_AT2T2) = 1.0f / A[8];
         }
     }
 
@@ -439,6 +440,7 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
     for (int j = 0; j < NL; j++) qdpos[j] = qdn[j];
     const int nit = P.npos + P.nvel;
     const float mu = 0.5f * (P.mu_ground + mu_shape);   // PhysX default combine mode: average
+    const float inv_h = 1.0f / h;
 
     for (int it = 0; it < nit; it++) {
         if (it == P.npos) {
@@ -464,17 +466,17 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
                     if (k <= jc) lv += S[k] * qdn[k];
                 const V3 pv = lv.v + cross(lv.w, r);
                 float vn = dot(pv, n), vt1 = dot(pv, t1), vt2 = dot(pv, t2);
-                float tgt = -sc.at(s, CF_GAP) / h;
+                float tgt = -sc.at(s, CF_GAP) * inv_h;
                 tgt = fminf(tgt, P.max_depen);
                 if (!with_bias) tgt = fminf(tgt, 0.0f);
                 const float l0 = sc.at(s, CF_LN), l1o = sc.at(s, CF_L1), l2o = sc.at(s, CF_L2);
-                float ln = fmaxf(l0 - (vn - tgt) / sc.at(s, CF_ANN), 0.0f);
+                float ln = fmaxf(l0 - (vn - tgt) * sc.at(s, CF_ANN), 0.0f);
                 const float dn = ln - l0;
                 vt1 += sc.at(s, CF_ANT1) * dn;
                 vt2 += sc.at(s, CF_ANT2) * dn;
-                float l1 = l1o - vt1 / sc.at(s, CF_AT1T1);
+                float l1 = l1o - vt1 * sc.at(s, CF_AT1T1);
                 vt2 += sc.at(s, CF_AT1T2) * (l1 - l1o);
-                float l2 = l2o - vt2 / sc.at(s, CF_AT2T2);
+                float l2 = l2o - vt2 * sc.at(s, CF_AT2T2);
                 const float lim_t = mu * ln, mag = sqrtf(l1 * l1 + l2 * l2);
                 if (mag > lim_t) {
                     const float scl = (mag > 0.0f) ? lim_t / mag : 0.0f;

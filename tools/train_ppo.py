@@ -19,24 +19,41 @@ def main():
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import torch
+    import torch.distributed as dist
 
     import isaacgymenv_b200
+    from isaacgymenv_b200.distributed import rank_info
     from isaacgymenv_b200.learning.ppo import PPO, PPOConfig
 
-    env = isaacgymenv_b200.make(seed=args.seed, task=args.task, num_envs=args.num_envs, sim_device="cuda:0", rl_device="cuda:0", headless=True)
+    info = rank_info()
+    multi = info.world_size > 1
+    if multi:      # one process per GPU (torchrun); envs sharded by rank, gradients all-reduced over NCCL
+        torch.cuda.set_device(info.local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(info.device))
+    env = isaacgymenv_b200.make(seed=args.seed, task=args.task, num_envs=args.num_envs, sim_device=info.device, rl_device=info.device, headless=True,
+                                multi_gpu=multi)
     cfg = PPOConfig()
     if args.task != "Anymal" and args.task != "Hound":
         cfg = PPOConfig(units=(512, 256, 128), minibatch_size=16384, entropy_coef=0.001)
     if args.task == "Cartpole":
         cfg = PPOConfig(units=(32, 32), horizon_length=16, minibatch_size=8192, mini_epochs=8)
-    ppo = PPO(env, cfg, seed=args.seed)
-    log = ppo.train(max_epochs=args.epochs, log_every=10, verbose=True)
-    out = {"task": args.task, "num_envs": args.num_envs, "epochs": log.epochs, "env_steps": log.env_steps, "mean_episode_reward": log.mean_episode_reward,
-           "mean_episode_length": log.mean_episode_length, "wall_s": log.wall_s, "gpu": torch.cuda.get_device_name(0)}
+    ppo = PPO(env, cfg, multi_gpu=multi, seed=args.seed + info.rank)
+    log = ppo.train(max_epochs=args.epochs, log_every=10, verbose=info.rank == 0)
+    if multi:
+        dist.barrier()
+    if info.rank != 0:
+        if multi:
+            dist.destroy_process_group()
+        return
+    out = {"task": args.task, "num_envs_per_gpu": args.num_envs, "n_gpus": info.world_size, "env_steps_all_gpus": [s * info.world_size for s in log.env_steps], "epochs": log.epochs, "env_steps": log.env_steps, "mean_episode_reward": log.mean_episode_reward,
+           "mean_episode_length": log.mean_episode_length, "wall_s": log.wall_s, "gpu": torch.cuda.get_device_name(0),
+           "env_steps_per_sec_incl_learner": (log.env_steps[-1] * info.world_size / log.wall_s[-1]) if log.wall_s else None}
     if args.out:
         with open(args.out, "w") as fh:
             json.dump(out, fh)
     print(json.dumps({k: (v[-1] if isinstance(v, list) and v else v) for k, v in out.items()}))
+    if multi:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
