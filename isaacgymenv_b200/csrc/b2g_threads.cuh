@@ -236,6 +236,7 @@ B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int 
     }
     if (!T.post_only) {
         const float mu_shape = A.friction ? A.friction[env] : 1.0f;
+#pragma unroll 1
         for (int s = 0; s < A.P.substeps; s++)
             substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
     } else {
@@ -643,6 +644,7 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
     if (!T.post_only) {
         const float mu_shape = A.friction ? A.friction[env] : 1.0f;
         const int total = C.decimation + C.extra_sim_steps;
+#pragma unroll 1
         for (int it = 0; it < total; it++) {
             if (it < C.decimation) {      // tasks/anymal_terrain.py:444-445: fresh explicit PD torque, clipped
                 if (is_arm) {             // tasks/useful_hound.py:704-716: operational-space torques for the arm, every decimation step
@@ -659,6 +661,7 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
 #pragma unroll
                 for (int j = 0; j < NL; j++) st.act[j] = tq[j];
             }
+#pragma unroll 1
             for (int s = 0; s < A.P.substeps; s++)
                 substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape,
                                                                              it == total - 1 && s == A.P.substeps - 1, sc, bf);
