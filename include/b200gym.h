@@ -338,6 +338,29 @@ int b2g_sizeof(int which);
  * b2g_sim_destroy. */
 int b2g_dlpack_from_desc(const b2g_tensor_desc* desc, void** out_managed);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Rollout policy (next row 8(f)-1): the actor-critic MLP rl_games builds from cfg/train/AnymalPPO.yaml:10-33
+ * (shared trunk of three ELU layers, mu head, value head; input normalisation cfg/train/AnymalPPO.yaml:45),
+ * evaluated once per VecTask.step for every environment. One fused tcgen05 kernel: bf16 operands, fp32 accumulation
+ * in tensor memory, activations stay in shared memory between layers. Weights are given in nn.Linear layout
+ * (out x in, row-major fp32, device memory) and packed once per update.
+ * Limits (B2G_ERR_UNSUPPORTED otherwise): exactly three hidden layers, widths multiples of 16 in [16,256],
+ * n_actions <= 15, weights + one 128-row activation tile must fit in shared memory (units [256,128,64] do;
+ * the rough-terrain [512,256,128] network does not).
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct b2g_policy b2g_policy;
+enum b2g_policy_layer { B2G_POLICY_HIDDEN0 = 0, B2G_POLICY_HIDDEN1 = 1, B2G_POLICY_HIDDEN2 = 2, B2G_POLICY_MU = 3, B2G_POLICY_VALUE = 4 };
+int b2g_policy_create(int device, int n_obs, const int* units /*[3]*/, int n_actions, b2g_policy** out);
+void b2g_policy_destroy(b2g_policy* policy);
+/* W_dev: (out,in) f32, b_dev: (out) f32, both device pointers; the value head is (1,in) */
+int b2g_policy_set_layer(b2g_policy* policy, int layer, const float* W_dev, const float* b_dev, void* stream);
+/* running mean / variance of the observations (rl_games RunningMeanStd: (x-mean)/sqrt(var+eps), clamp to +-clip);
+ * null pointers = identity */
+int b2g_policy_set_obs_norm(b2g_policy* policy, const float* mean_dev, const float* var_dev, float eps, float clip, void* stream);
+/* obs_dev (n_rows,n_obs) f32 -> mu_dev (n_rows,n_actions) f32, value_dev (n_rows) f32; one launch */
+int b2g_policy_forward(b2g_policy* policy, const float* obs_dev, int n_rows, float* mu_dev, float* value_dev, void* stream);
+int64_t b2g_policy_launch_count(const b2g_policy* policy);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,15 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+}  // namespace
+
+namespace b2g {
+// shared with the other translation units of the library (b2g_policy.cu)
+int fail_msg(int code, const char* msg) { return fail(code, "%s", msg); }
+}  // namespace b2g
+
+namespace {
+
 #define CUDA_TRY(expr)                                                                                   \
     do {                                                                                                 \
         cudaError_t e_ = (expr);                                                                         \

@@ -1,0 +1,463 @@
+// b2g_policy.cu -- fused actor-critic MLP forward for the rollout ("next"): the network rl_games
+// builds from cfg/train/AnymalPPO.yaml:10-33 (shared trunk, units [256,128,64], ELU, mu head + value head, input
+// normalisation cfg/train/AnymalPPO.yaml:45) evaluated for every environment once per VecTask.step
+// (isaacgymenvs/utils/rlgames_utils.py:242-262 is the env side of that loop).
+//
+// sm_100a only.  One CTA = one tile of 128 observation rows:
+//   * all weights (bf16, UMMA canonical K-major no-swizzle layout, packed once by k_pack_layer) are brought into shared memory
+//     with four 1-D bulk async copies (cp.async.bulk, the TMA engine) completing on an mbarrier and stay resident for every
+//     tile the CTA processes;
+//   * each layer is a chain of tcgen05.mma (M=128, N=layer width, K=16 per instruction) issued by ONE thread, A and B from
+//     shared memory, fp32 accumulators in tensor memory (TMEM); completion is signalled by tcgen05.commit on an mbarrier;
+//   * the epilogue reads the accumulators with tcgen05.ld (one TMEM lane = one row = one thread), adds the bias, applies
+//     ELU, converts to bf16 and writes the row straight into the A-operand layout of the next layer in shared memory, so
+//     activations never leave the SM; the head writes mu (n_actions) and value to global memory.
+// Observation normalisation ((x-mean)/sqrt(var+eps), clamp) is fused into the first operand load.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <new>
+
+#include "b200gym.h"
+
+namespace b2g {
+int fail_msg(int code, const char* msg);   // b200gym.cu: sets b2g_last_error()
+}
+
+namespace {
+
+constexpr int kTileM = 128;       // rows per tile = UMMA M = TMEM lanes
+constexpr int kThreads = 128;     // 4 warps, warp w owns TMEM lanes 32w..32w+31
+constexpr int kHeadN = 16;        // mu (n_actions) + value, padded to the minimum UMMA N for M=128
+constexpr int kTmemCols = 512;
+
+struct PolicyDims {
+    int k0, k0p;          // observation width, padded to a multiple of 16
+    int n1, n2, n3;       // hidden widths (multiples of 16, <= 256)
+    int n_act;            // mu head width (n_act + 1 <= 16)
+    // byte offsets into dynamic shared memory
+    int off_w1, off_w2, off_w3, off_wh, off_a, off_bias, off_norm, off_bar, total;
+    int w_bytes[4];
+};
+
+#define CUDA_TRY_P(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            char b_[384];                                                                  \
+            snprintf(b_, sizeof(b_), "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return b2g::fail_msg(B2G_ERR_CUDA, b_);                                        \
+        }                                                                                  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a descriptor bug must surface as a trap (launch failure), never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: 8x(16 B) core matrices; LBO = byte distance between the two core
+// matrices of one K=16 slice, SBO = byte distance between consecutive 8-row groups; version 1 (Blackwell), base offset 0
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t instr_desc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : (__expf(x) - 1.f); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// one layer's MMAs: D[128 x n] (TMEM, column tcol) = A[128 x k] (smem a_addr) . W[n x k]^T (smem w_addr); single thread
+__device__ __forceinline__ void issue_layer(uint32_t tmem_base, int tcol, uint32_t a_addr, uint32_t w_addr, int n, int k, uint32_t bar) {
+    const uint32_t a_lbo = kTileM * 16, b_lbo = (uint32_t)n * 16, idesc = instr_desc(n);
+    for (int k16 = 0; k16 < k / 16; k16++) {
+        uint64_t ad = smem_desc(a_addr + (uint32_t)k16 * 2u * a_lbo, a_lbo, 128);
+        uint64_t bd = smem_desc(w_addr + (uint32_t)k16 * 2u * b_lbo, b_lbo, 128);
+        umma_bf16(tmem_base + (uint32_t)tcol, ad, bd, idesc, k16 > 0 ? 1u : 0u);
+    }
+    umma_commit(bar);
+}
+
+// hidden-layer epilogue: thread = row; acc -> +bias -> ELU -> bf16 -> next layer's A operand (k-slab s at s*2048 + row*16)
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, int tcol, int n, const float* bias, uint8_t* a_smem, int row) {
+    for (int c0 = 0; c0 < n; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_row + (uint32_t)(tcol + c0), v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = elu(v[i] + bias[c0 + i]);
+        uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        *reinterpret_cast<uint4*>(a_smem + (size_t)(c0 / 8) * (kTileM * 16) + row * 16) = lo;
+        *reinterpret_cast<uint4*>(a_smem + (size_t)(c0 / 8 + 1) * (kTileM * 16) + row * 16) = hi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+// fp32 row-major W[rows x cols] (nn.Linear layout: out x in) -> bf16 canonical K-major operand with np rows, at row row0
+__global__ void k_pack_layer(const float* __restrict__ W, const float* __restrict__ b, int rows, int cols, int row0, int np,
+                             __nv_bfloat16* __restrict__ Wp, float* __restrict__ bp) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < rows * cols) {
+        const int n = idx / cols, k = idx % cols;
+        Wp[(size_t)(k / 8) * ((size_t)np * 8) + (size_t)(row0 + n) * 8 + (k % 8)] = __float2bfloat16_rn(W[idx]);
+    }
+    if (idx < rows) bp[row0 + idx] = b[idx];
+}
+
+__global__ void k_pack_norm(const float* __restrict__ mean, const float* __restrict__ var, float eps, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out[i] = mean ? mean[i] : 0.f;
+        out[n + i] = var ? rsqrtf(var[i] + eps) : 1.f;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_policy_forward(PolicyDims d, const uint8_t* __restrict__ wpack, const float* __restrict__ bias_g, const float* __restrict__ norm_g,
+                 float clip, const float* __restrict__ obs, int n_rows, float* __restrict__ mu, float* __restrict__ value) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float* bias_s = reinterpret_cast<float*>(smem + d.off_bias);
+    float* norm_s = reinterpret_cast<float*>(smem + d.off_norm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + d.off_bar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    uint8_t* a_smem = smem + d.off_a;
+    const uint32_t a_addr = smem_u32(a_smem);
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+        // weights: global (already in operand layout) -> shared, one bulk copy per layer
+        mbar_expect_tx(bar_w, (uint32_t)(d.w_bytes[0] + d.w_bytes[1] + d.w_bytes[2] + d.w_bytes[3]));
+        const int offs[4] = {d.off_w1, d.off_w2, d.off_w3, d.off_wh};
+        size_t g = 0;
+        for (int l = 0; l < 4; l++) {
+            bulk_g2s(smem_u32(smem + offs[l]), wpack + g, (uint32_t)d.w_bytes[l], bar_w);
+            g += (size_t)d.w_bytes[l];
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const int n_bias = d.n1 + d.n2 + d.n3 + kHeadN;
+    for (int i = tid; i < n_bias; i += kThreads) bias_s[i] = bias_g[i];
+    for (int i = tid; i < 2 * d.k0; i += kThreads) norm_s[i] = norm_g[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int tc1 = 0, tc2 = d.n1, tc3 = d.n1 + d.n2, tch = d.n1 + d.n2 + d.n3;
+    const float* b1 = bias_s;
+    const float* b2 = b1 + d.n1;
+    const float* b3 = b2 + d.n2;
+    const float* bh = b3 + d.n3;
+    uint32_t phase = 0;
+    bool weights_ready = false;
+
+    const int n_tiles = (n_rows + kTileM - 1) / kTileM;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row_base = tile * kTileM;
+        // ---- observations -> normalise -> bf16 A operand (coalesced global reads) ----
+        for (int idx = tid; idx < kTileM * d.k0p; idx += kThreads) {
+            const int r = idx / d.k0p, k = idx - r * d.k0p;
+            float x = 0.f;
+            if (k < d.k0 && row_base + r < n_rows) {
+                x = (obs[(size_t)(row_base + r) * d.k0 + k] - norm_s[k]) * norm_s[d.k0 + k];
+                x = fminf(fmaxf(x, -clip), clip);
+            }
+            *reinterpret_cast<__nv_bfloat16*>(a_smem + (size_t)(k >> 3) * (kTileM * 16) + r * 16 + (k & 7) * 2) = __float2bfloat16_rn(x);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- layer 1 ----
+        if (tid == 0) {
+            if (!weights_ready) mbar_wait(bar_w, 0);
+            tc_fence_after();
+            issue_layer(tmem_base, tc1, a_addr, smem_u32(smem + d.off_w1), d.n1, d.k0p, bar_mma);
+        }
+        weights_ready = true;
+        mbar_wait(bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+        epilogue_hidden(tmem_row, tc1, d.n1, b1, a_smem, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- layer 2 ----
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, tc2, a_addr, smem_u32(smem + d.off_w2), d.n2, d.n1, bar_mma);
+        }
+        mbar_wait(bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+        epilogue_hidden(tmem_row, tc2, d.n2, b2, a_smem, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- layer 3 ----
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, tc3, a_addr, smem_u32(smem + d.off_w3), d.n3, d.n2, bar_mma);
+        }
+        mbar_wait(bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+        epilogue_hidden(tmem_row, tc3, d.n3, b3, a_smem, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- heads: mu (n_act columns) and value (column n_act) ----
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, tch, a_addr, smem_u32(smem + d.off_wh), kHeadN, d.n3, bar_mma);
+        }
+        mbar_wait(bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+        {
+            float v[16];
+            tmem_ld16(tmem_row + (uint32_t)tch, v);
+            const int row = row_base + tid;
+            if (row < n_rows) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float o = v[i] + bh[i];
+                    if (i < d.n_act) mu[(size_t)row * d.n_act + i] = o;
+                    else if (i == d.n_act) value[row] = o;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();    // the A buffer and the TMEM columns are free for the next tile
+    }
+    // a CTA that had no tile still has the weight copies in flight: they must land before the CTA exits
+    if (tid == 0 && !weights_ready) mbar_wait(bar_w, 0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct b2g_policy {
+    int device = 0;
+    PolicyDims d{};
+    uint8_t* wpack = nullptr;     // the four packed weight matrices, back to back
+    float* bias = nullptr;        // n1 + n2 + n3 + 16
+    float* norm = nullptr;        // mean[k0], rstd[k0]
+    float clip = 5.0f;
+    int n_sm = 148;
+    int64_t launches = 0;
+};
+
+extern "C" {
+
+int b2g_policy_create(int device, int n_obs, const int* units, int n_actions, b2g_policy** out) {
+    if (!out || !units) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_create: null argument");
+    *out = nullptr;
+    if (n_obs < 1 || n_actions < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_create: n_obs and n_actions must be positive");
+    for (int i = 0; i < 3; i++)
+        if (units[i] < 16 || units[i] > 256 || units[i] % 16)
+            return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: hidden widths must be multiples of 16 in [16,256] (three layers)");
+    if (n_actions + 1 > kHeadN) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: n_actions + 1 must be <= 16");
+    if (units[0] + units[1] + units[2] + kHeadN > kTmemCols)
+        return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: accumulators exceed the 512 tensor-memory columns");
+    CUDA_TRY_P(cudaSetDevice(device));
+    b2g_policy* p = new (std::nothrow) b2g_policy();
+    if (!p) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_create: out of memory");
+    p->device = device;
+    PolicyDims& d = p->d;
+    d.k0 = n_obs;
+    d.k0p = round_up(n_obs, 16);
+    d.n1 = units[0];
+    d.n2 = units[1];
+    d.n3 = units[2];
+    d.n_act = n_actions;
+    d.w_bytes[0] = d.n1 * d.k0p * 2;
+    d.w_bytes[1] = d.n2 * d.n1 * 2;
+    d.w_bytes[2] = d.n3 * d.n2 * 2;
+    d.w_bytes[3] = kHeadN * d.n3 * 2;
+    int off = 0;
+    d.off_w1 = off; off += round_up(d.w_bytes[0], 128);
+    d.off_w2 = off; off += round_up(d.w_bytes[1], 128);
+    d.off_w3 = off; off += round_up(d.w_bytes[2], 128);
+    d.off_wh = off; off += round_up(d.w_bytes[3], 128);
+    int kmax = d.k0p;
+    kmax = d.n1 > kmax ? d.n1 : kmax;
+    kmax = d.n2 > kmax ? d.n2 : kmax;
+    kmax = d.n3 > kmax ? d.n3 : kmax;
+    d.off_a = off; off += kTileM * kmax * 2;
+    d.off_bias = off; off += round_up((d.n1 + d.n2 + d.n3 + kHeadN) * 4, 16);
+    d.off_norm = off; off += round_up(2 * d.k0 * 4, 16);
+    d.off_bar = off; off += 32;
+    d.total = off;
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (d.total > max_smem) {
+        delete p;
+        return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: weights + one activation tile do not fit in shared memory");
+    }
+    const size_t wtot = (size_t)d.w_bytes[0] + d.w_bytes[1] + d.w_bytes[2] + d.w_bytes[3];
+    cudaError_t e = cudaMalloc(&p->wpack, wtot);
+    if (e == cudaSuccess) e = cudaMalloc(&p->bias, (size_t)(d.n1 + d.n2 + d.n3 + kHeadN) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->norm, (size_t)2 * d.k0 * 4);
+    if (e == cudaSuccess) e = cudaMemset(p->wpack, 0, wtot);
+    if (e == cudaSuccess) e = cudaMemset(p->bias, 0, (size_t)(d.n1 + d.n2 + d.n3 + kHeadN) * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_policy_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, d.total);
+    if (e == cudaSuccess) {
+        k_pack_norm<<<(d.k0 + 127) / 128, 128>>>(nullptr, nullptr, 0.f, d.k0, p->norm);   // identity normalisation
+        e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) {
+        cudaFree(p->wpack); cudaFree(p->bias); cudaFree(p->norm);
+        delete p;
+        char b[256];
+        snprintf(b, sizeof(b), "b2g_policy_create: %s", cudaGetErrorString(e));
+        return b2g::fail_msg(B2G_ERR_CUDA, b);
+    }
+    *out = p;
+    return B2G_OK;
+}
+
+void b2g_policy_destroy(b2g_policy* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->wpack);
+    cudaFree(p->bias);
+    cudaFree(p->norm);
+    delete p;
+}
+
+int b2g_policy_set_layer(b2g_policy* p, int layer, const float* W_dev, const float* b_dev, void* stream) {
+    if (!p || !W_dev || !b_dev) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_set_layer: null argument");
+    const PolicyDims& d = p->d;
+    int rows, cols, row0 = 0, np, slot;
+    size_t woff = 0, boff = 0;
+    switch (layer) {
+        case B2G_POLICY_HIDDEN0: rows = d.n1; cols = d.k0; np = d.n1; slot = 0; break;
+        case B2G_POLICY_HIDDEN1: rows = d.n2; cols = d.n1; np = d.n2; slot = 1; break;
+        case B2G_POLICY_HIDDEN2: rows = d.n3; cols = d.n2; np = d.n3; slot = 2; break;
+        case B2G_POLICY_MU: rows = d.n_act; cols = d.n3; np = kHeadN; slot = 3; break;
+        case B2G_POLICY_VALUE: rows = 1; cols = d.n3; np = kHeadN; slot = 3; row0 = d.n_act; break;
+        default: return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_set_layer: layer must be one of B2G_POLICY_*");
+    }
+    const int nb[4] = {d.n1, d.n2, d.n3, kHeadN};
+    for (int l = 0; l < slot; l++) {
+        woff += (size_t)d.w_bytes[l];
+        boff += (size_t)nb[l];
+    }
+    CUDA_TRY_P(cudaSetDevice(p->device));
+    k_pack_layer<<<(rows * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        W_dev, b_dev, rows, cols, row0, np, reinterpret_cast<__nv_bfloat16*>(p->wpack + woff), p->bias + boff);
+    CUDA_TRY_P(cudaGetLastError());
+    p->launches++;
+    return B2G_OK;
+}
+
+int b2g_policy_set_obs_norm(b2g_policy* p, const float* mean_dev, const float* var_dev, float eps, float clip, void* stream) {
+    if (!p) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_set_obs_norm: null policy");
+    if (!(clip > 0.f)) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_set_obs_norm: clip must be positive");
+    CUDA_TRY_P(cudaSetDevice(p->device));
+    k_pack_norm<<<(p->d.k0 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_dev, var_dev, eps, p->d.k0, p->norm);
+    CUDA_TRY_P(cudaGetLastError());
+    p->clip = clip;
+    p->launches++;
+    return B2G_OK;
+}
+
+int b2g_policy_forward(b2g_policy* p, const float* obs_dev, int n_rows, float* mu_dev, float* value_dev, void* stream) {
+    if (!p || !obs_dev || !mu_dev || !value_dev) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_forward: null argument");
+    if (n_rows < 0) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_forward: n_rows < 0");
+    if (n_rows == 0) return B2G_OK;
+    CUDA_TRY_P(cudaSetDevice(p->device));
+    const int n_tiles = (n_rows + kTileM - 1) / kTileM;
+    const int grid = n_tiles < p->n_sm ? n_tiles : p->n_sm;
+    k_policy_forward<<<grid, kThreads, p->d.total, (cudaStream_t)stream>>>(p->d, p->wpack, p->bias, p->norm, p->clip, obs_dev, n_rows,
+                                                                          mu_dev, value_dev);
+    CUDA_TRY_P(cudaGetLastError());
+    p->launches++;
+    return B2G_OK;
+}
+
+int64_t b2g_policy_launch_count(const b2g_policy* p) { return p ? p->launches : 0; }
+
+}  // extern "C"
