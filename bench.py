@@ -153,6 +153,9 @@ def run_ours(args):
 
     lib = _lib.load()
     algo_bytes, envs_per_gpu, kernel_name, overrides, workload = TASKS[args.task]
+    if args.num_envs > 0 and args.num_envs != envs_per_gpu:
+        envs_per_gpu = args.num_envs
+        workload += f" [scaling study: {envs_per_gpu} envs per GPU instead of the config's count]"
     env = isaacgymenv_b200.make(seed=42 + rank, task=args.task, num_envs=envs_per_gpu, sim_device=dev, rl_device=dev, headless=True, overrides=overrides)
     n, na = env.num_envs, env.num_actions
     is_terrain = hasattr(env, "common_step_counter")
@@ -276,6 +279,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--num-envs", type=int, default=0, help="environments per GPU (default: the config's own count, 4096 for Anymal); "
+                    "other values are a scaling study, not the headline config")
     ap.add_argument("--task", default="Anymal", choices=sorted(TASKS), help="hot-path config to time (default: the headline Anymal config)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -9,9 +9,10 @@
 //     tile the CTA processes;
 //   * each layer is a chain of tcgen05.mma (M=128, N=layer width, K=16 per instruction) issued by ONE thread, A and B from
 //     shared memory, fp32 accumulators in tensor memory (TMEM); completion is signalled by tcgen05.commit on an mbarrier;
-//   * the epilogue reads the accumulators with tcgen05.ld (one TMEM lane = one row = one thread), adds the bias, applies
-//     ELU, converts to bf16 and writes the row straight into the A-operand layout of the next layer in shared memory, so
-//     activations never leave the SM; the head writes mu (n_actions) and value to global memory.
+//   * the epilogue reads the accumulators with tcgen05.ld (one TMEM lane = one row; the row's columns are split between two
+//     threads, warps w and w+4), adds the bias, applies ELU, converts to bf16 and writes the row straight into the A-operand
+//     layout of the next layer in shared memory, so activations never leave the SM; the head writes mu (n_actions) and
+//     value to global memory.  The kernel is bound by this elementwise epilogue (K is tiny), not by the tensor cores.
 // Observation normalisation ((x-mean)/sqrt(var+eps), clamp) is fused into the first operand load.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -28,7 +29,7 @@ int fail_msg(int code, const char* msg);   // b200gym.cu: sets b2g_last_error()
 namespace {
 
 constexpr int kTileM = 128;       // rows per tile = UMMA M = TMEM lanes
-constexpr int kThreads = 128;     // 4 warps, warp w owns TMEM lanes 32w..32w+31
+constexpr int kThreads = 256;     // 8 warps: warp w reads TMEM lanes 32(w%4)..+31; warps w and w+4 split a row's columns
 constexpr int kHeadN = 16;        // mu (n_actions) + value, padded to the minimum UMMA N for M=128
 constexpr int kTmemCols = 512;
 
@@ -111,8 +112,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
+// 32 (16) accumulator columns of this thread's TMEM lane -> registers.  The load and its wait are ONE asm statement so that
+// neither the compiler nor the assembler can place a use of r[] between them.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
         "tcgen05.wait::ld.sync.aligned;"
@@ -120,11 +134,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : (__expf(x) - 1.f); }
+// ELU, branch-free: max(x, exp(min(x,0)) - 1)  (x > 0: max(x, 0) = x; x <= 0: e^x - 1 >= x).  ex2.approx.ftz is a single MUFU
+// (2^-22 relative); the non-ftz __expf expands to a denormal range check around it.
+__device__ __forceinline__ float elu(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.f) * 1.4426950408889634f));
+    return fmaxf(x, e - 1.f);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -142,17 +160,72 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_base, int tcol, uint32
     umma_commit(bar);
 }
 
-// hidden-layer epilogue: thread = row; acc -> +bias -> ELU -> bf16 -> next layer's A operand (k-slab s at s*2048 + row*16)
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, int tcol, int n, const float* bias, uint8_t* a_smem, int row) {
-    for (int c0 = 0; c0 < n; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_row + (uint32_t)(tcol + c0), v);
+// 16 accumulator columns -> +bias -> ELU -> bf16 -> two 16-byte k-slabs of the next layer's A operand
+__device__ __forceinline__ void store_slabs16(const uint32_t* r, const float* bias, uint8_t* a_row, int c0) {
+    float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = elu(v[i] + bias[c0 + i]);
-        uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-        uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-        *reinterpret_cast<uint4*>(a_smem + (size_t)(c0 / 8) * (kTileM * 16) + row * 16) = lo;
-        *reinterpret_cast<uint4*>(a_smem + (size_t)(c0 / 8 + 1) * (kTileM * 16) + row * 16) = hi;
+    for (int q = 0; q < 4; q++) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
+        v[4 * q + 0] = elu(__uint_as_float(r[4 * q + 0]) + b.x);
+        v[4 * q + 1] = elu(__uint_as_float(r[4 * q + 1]) + b.y);
+        v[4 * q + 2] = elu(__uint_as_float(r[4 * q + 2]) + b.z);
+        v[4 * q + 3] = elu(__uint_as_float(r[4 * q + 3]) + b.w);
+    }
+    *reinterpret_cast<uint4*>(a_row + (size_t)(c0 / 8) * (kTileM * 16)) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(a_row + (size_t)(c0 / 8 + 1) * (kTileM * 16)) =
+        make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+}
+
+// hidden-layer epilogue: thread = row; acc -> +bias -> ELU -> bf16 -> next layer's A operand (k-slab s at s*2048 + row*16),
+// 32 columns per tcgen05.ld, a 16-column tail if n % 32
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, int tcol, int n, const float* bias, uint8_t* a_smem, int row, int half) {
+    uint8_t* a_row = a_smem + row * 16;
+    const int n32 = n / 32;
+    uint32_t r[32];
+    for (int c = half; c < n32; c += 2) {        // the two threads of a row take alternate 32-column chunks
+        tmem_ld32(tmem_row + (uint32_t)(tcol + c * 32), r);
+        store_slabs16(r, bias, a_row, c * 32);
+        store_slabs16(r + 16, bias, a_row, c * 32 + 16);
+    }
+    if ((n % 32) && (n32 & 1) == half) {
+        tmem_ld16(tmem_row + (uint32_t)(tcol + n32 * 32), r);
+        store_slabs16(r, bias, a_row, n32 * 32);
+    }
+}
+
+// observation tile: 128 rows x k0 floats, contiguous in global memory.  Vector path (k0 % 4 == 0): thread t owns float4
+// number j*128+t, j < kObsVec -- coalesced, all loads issued before any use, so the next tile's rows can be fetched under the
+// current tile's epilogues.
+constexpr int kObsVec = 8;         // <= 8 float4 per thread (256 threads): k0 <= 64 on the vector path
+
+__device__ __forceinline__ void obs_fetch(const float* __restrict__ obs, int row_base, int n_rows, int k0, int tid, float4* pre) {
+    const int per_row = k0 >> 2, total = kTileM * per_row;
+    const float inv = 1.0f / (float)per_row;     // f < 2^13, per_row <= 16: (f + 0.5) * inv truncates to f / per_row exactly
+#pragma unroll
+    for (int j = 0; j < kObsVec; j++) {
+        const int f = j * kThreads + tid;
+        const int r = __float2int_rz(((float)f + 0.5f) * inv);
+        pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < total && row_base + r < n_rows) pre[j] = __ldg(reinterpret_cast<const float4*>(obs + (size_t)row_base * k0) + f);
+    }
+}
+
+__device__ __forceinline__ void obs_commit(const float4* pre, const float* norm_s, float clip, int k0, int tid, uint8_t* a_smem) {
+    const int per_row = k0 >> 2, total = kTileM * per_row;
+    const float inv = 1.0f / (float)per_row;
+#pragma unroll
+    for (int j = 0; j < kObsVec; j++) {
+        const int f = j * kThreads + tid;
+        if (f < total) {
+            const int r = __float2int_rz(((float)f + 0.5f) * inv), k = (f - r * per_row) * 4;
+            const float4 m = *reinterpret_cast<const float4*>(norm_s + k);
+            const float4 rs = *reinterpret_cast<const float4*>(norm_s + k0 + k);
+            const float x0 = fminf(fmaxf((pre[j].x - m.x) * rs.x, -clip), clip), x1 = fminf(fmaxf((pre[j].y - m.y) * rs.y, -clip), clip);
+            const float x2 = fminf(fmaxf((pre[j].z - m.z) * rs.z, -clip), clip), x3 = fminf(fmaxf((pre[j].w - m.w) * rs.w, -clip), clip);
+            *reinterpret_cast<uint2*>(a_smem + (size_t)(k >> 3) * (kTileM * 16) + r * 16 + (k & 7) * 2) =
+                make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+        }
     }
 }
 
@@ -180,28 +253,33 @@ __global__ void k_pack_norm(const float* __restrict__ mean, const float* __restr
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_policy_forward(PolicyDims d, const uint8_t* __restrict__ wpack, const float* __restrict__ bias_g, const float* __restrict__ norm_g,
-                 float clip, const float* __restrict__ obs, int n_rows, float* __restrict__ mu, float* __restrict__ value) {
+                 float clip, const float* __restrict__ obs, int n_rows, float* __restrict__ mu, float* __restrict__ value, int obs_aligned) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTileM - 1), half = tid >> 7;
     float* bias_s = reinterpret_cast<float*>(smem + d.off_bias);
     float* norm_s = reinterpret_cast<float*>(smem + d.off_norm);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + d.off_bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-    const uint32_t bar_w = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + d.off_bar);      // [0..3] weights of layer l landed, [4] MMA chain done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const uint32_t bar_mma = smem_u32(&bars[4]);
     uint8_t* a_smem = smem + d.off_a;
     const uint32_t a_addr = smem_u32(a_smem);
+    const int offs[4] = {d.off_w1, d.off_w2, d.off_w3, d.off_wh};
+    const bool vec = obs_aligned && (d.k0 & 3) == 0 && kTileM * (d.k0 >> 2) <= kObsVec * kThreads;
+    const int n_tiles = (n_rows + kTileM - 1) / kTileM;
+
+    // first tile's observations: in flight while the weights stream in
+    float4 pre[kObsVec];
+    if (vec && (int)blockIdx.x < n_tiles) obs_fetch(obs, blockIdx.x * kTileM, n_rows, d.k0, tid, pre);
 
     if (tid == 0) {
-        mbar_init(bar_w, 1);
-        mbar_init(bar_mma, 1);
+        for (int l = 0; l < 5; l++) mbar_init(smem_u32(&bars[l]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
-        // weights: global (already in operand layout) -> shared, one bulk copy per layer
-        mbar_expect_tx(bar_w, (uint32_t)(d.w_bytes[0] + d.w_bytes[1] + d.w_bytes[2] + d.w_bytes[3]));
-        const int offs[4] = {d.off_w1, d.off_w2, d.off_w3, d.off_wh};
+        // weights: global (already in operand layout) -> shared, one bulk copy and one barrier per layer, first layer first
         size_t g = 0;
         for (int l = 0; l < 4; l++) {
-            bulk_g2s(smem_u32(smem + offs[l]), wpack + g, (uint32_t)d.w_bytes[l], bar_w);
+            mbar_expect_tx(smem_u32(&bars[l]), (uint32_t)d.w_bytes[l]);
+            bulk_g2s(smem_u32(smem + offs[l]), wpack + g, (uint32_t)d.w_bytes[l], smem_u32(&bars[l]));
             g += (size_t)d.w_bytes[l];
         }
     }
@@ -216,95 +294,75 @@ k_policy_forward(PolicyDims d, const uint8_t* __restrict__ wpack, const float* _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int tc1 = 0, tc2 = d.n1, tc3 = d.n1 + d.n2, tch = d.n1 + d.n2 + d.n3;
-    const float* b1 = bias_s;
-    const float* b2 = b1 + d.n1;
-    const float* b3 = b2 + d.n2;
-    const float* bh = b3 + d.n3;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int tcol[4] = {0, d.n1, d.n1 + d.n2, d.n1 + d.n2 + d.n3};
+    const int width[4] = {d.n1, d.n2, d.n3, kHeadN};
+    const int depth[4] = {d.k0p, d.n1, d.n2, d.n3};
+    const float* bias_l[4] = {bias_s, bias_s + d.n1, bias_s + d.n1 + d.n2, bias_s + d.n1 + d.n2 + d.n3};
     uint32_t phase = 0;
-    bool weights_ready = false;
+    bool first = true;
 
-    const int n_tiles = (n_rows + kTileM - 1) / kTileM;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row_base = tile * kTileM;
-        // ---- observations -> normalise -> bf16 A operand (coalesced global reads) ----
-        for (int idx = tid; idx < kTileM * d.k0p; idx += kThreads) {
-            const int r = idx / d.k0p, k = idx - r * d.k0p;
-            float x = 0.f;
-            if (k < d.k0 && row_base + r < n_rows) {
-                x = (obs[(size_t)(row_base + r) * d.k0 + k] - norm_s[k]) * norm_s[d.k0 + k];
-                x = fminf(fmaxf(x, -clip), clip);
+        // ---- observations -> normalise -> bf16 A operand ----
+        if (vec) {
+            obs_commit(pre, norm_s, clip, d.k0, tid, a_smem);
+            if (d.k0p != d.k0)      // zero the K padding (the buffer holds the previous tile's activations)
+                for (int idx = tid; idx < kTileM * (d.k0p - d.k0); idx += kThreads) {
+                    const int r = idx / (d.k0p - d.k0), k = d.k0 + idx % (d.k0p - d.k0);
+                    *reinterpret_cast<__nv_bfloat16*>(a_smem + (size_t)(k >> 3) * (kTileM * 16) + r * 16 + (k & 7) * 2) = __float2bfloat16_rn(0.f);
+                }
+            // next tile's rows: fetched under this tile's four layers
+            if (tile + (int)gridDim.x < n_tiles) obs_fetch(obs, (tile + gridDim.x) * kTileM, n_rows, d.k0, tid, pre);
+        } else {
+            for (int idx = tid; idx < kTileM * d.k0p; idx += kThreads) {
+                const int r = idx / d.k0p, k = idx - r * d.k0p;
+                float x = 0.f;
+                if (k < d.k0 && row_base + r < n_rows) {
+                    x = (obs[(size_t)(row_base + r) * d.k0 + k] - norm_s[k]) * norm_s[d.k0 + k];
+                    x = fminf(fmaxf(x, -clip), clip);
+                }
+                *reinterpret_cast<__nv_bfloat16*>(a_smem + (size_t)(k >> 3) * (kTileM * 16) + r * 16 + (k & 7) * 2) = __float2bfloat16_rn(x);
             }
-            *reinterpret_cast<__nv_bfloat16*>(a_smem + (size_t)(k >> 3) * (kTileM * 16) + r * 16 + (k & 7) * 2) = __float2bfloat16_rn(x);
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        // ---- layer 1 ----
-        if (tid == 0) {
-            if (!weights_ready) mbar_wait(bar_w, 0);
-            tc_fence_after();
-            issue_layer(tmem_base, tc1, a_addr, smem_u32(smem + d.off_w1), d.n1, d.k0p, bar_mma);
-        }
-        weights_ready = true;
-        mbar_wait(bar_mma, phase);
-        phase ^= 1;
-        tc_fence_after();
-        epilogue_hidden(tmem_row, tc1, d.n1, b1, a_smem, tid);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        // ---- layer 2 ----
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer(tmem_base, tc2, a_addr, smem_u32(smem + d.off_w2), d.n2, d.n1, bar_mma);
-        }
-        mbar_wait(bar_mma, phase);
-        phase ^= 1;
-        tc_fence_after();
-        epilogue_hidden(tmem_row, tc2, d.n2, b2, a_smem, tid);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        // ---- layer 3 ----
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer(tmem_base, tc3, a_addr, smem_u32(smem + d.off_w3), d.n3, d.n2, bar_mma);
-        }
-        mbar_wait(bar_mma, phase);
-        phase ^= 1;
-        tc_fence_after();
-        epilogue_hidden(tmem_row, tc3, d.n3, b3, a_smem, tid);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        // ---- heads: mu (n_act columns) and value (column n_act) ----
-        if (tid == 0) {
-            tc_fence_after();
-            issue_layer(tmem_base, tch, a_addr, smem_u32(smem + d.off_wh), kHeadN, d.n3, bar_mma);
-        }
-        mbar_wait(bar_mma, phase);
-        phase ^= 1;
-        tc_fence_after();
-        {
-            float v[16];
-            tmem_ld16(tmem_row + (uint32_t)tch, v);
-            const int row = row_base + tid;
-            if (row < n_rows) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float o = v[i] + bh[i];
-                    if (i < d.n_act) mu[(size_t)row * d.n_act + i] = o;
-                    else if (i == d.n_act) value[row] = o;
+        for (int l = 0; l < 4; l++) {
+            // the A operand was written through the generic proxy: make it visible to the tensor core's async proxy
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                if (first) mbar_wait(smem_u32(&bars[l]), 0);
+                tc_fence_after();
+                issue_layer(tmem_base, tcol[l], a_addr, smem_u32(smem + offs[l]), width[l], depth[l], bar_mma);
+            }
+            mbar_wait(bar_mma, phase);
+            phase ^= 1;
+            tc_fence_after();
+            if (l < 3) {
+                epilogue_hidden(tmem_row, tcol[l], width[l], bias_l[l], a_smem, row, half);
+            } else if (half == 0) {
+                // heads: mu (n_act columns) and value (column n_act)
+                uint32_t r[16];
+                tmem_ld16(tmem_row + (uint32_t)tcol[3], r);
+                const int grow = row_base + row;
+                if (grow < n_rows) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float o = __uint_as_float(r[i]) + bias_l[3][i];
+                        if (i < d.n_act) mu[(size_t)grow * d.n_act + i] = o;
+                        else if (i == d.n_act) value[grow] = o;
+                    }
                 }
             }
         }
+        first = false;
         tc_fence_before();
         __syncthreads();    // the A buffer and the TMEM columns are free for the next tile
     }
-    // a CTA that had no tile still has the weight copies in flight: they must land before the CTA exits
-    if (tid == 0 && !weights_ready) mbar_wait(bar_w, 0);
+    // a CTA without a tile still has the weight copies in flight: they must land before the CTA exits
+    if (tid == 0 && first)
+        for (int l = 0; l < 4; l++) mbar_wait(smem_u32(&bars[l]), 0);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -367,7 +425,7 @@ int b2g_policy_create(int device, int n_obs, const int* units, int n_actions, b2
     d.off_a = off; off += kTileM * kmax * 2;
     d.off_bias = off; off += round_up((d.n1 + d.n2 + d.n3 + kHeadN) * 4, 16);
     d.off_norm = off; off += round_up(2 * d.k0 * 4, 16);
-    d.off_bar = off; off += 32;
+    d.off_bar = off; off += 64;
     d.total = off;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -452,7 +510,8 @@ int b2g_policy_forward(b2g_policy* p, const float* obs_dev, int n_rows, float* m
     const int n_tiles = (n_rows + kTileM - 1) / kTileM;
     const int grid = n_tiles < p->n_sm ? n_tiles : p->n_sm;
     k_policy_forward<<<grid, kThreads, p->d.total, (cudaStream_t)stream>>>(p->d, p->wpack, p->bias, p->norm, p->clip, obs_dev, n_rows,
-                                                                          mu_dev, value_dev);
+                                                                          mu_dev, value_dev,
+                                                                          (reinterpret_cast<uintptr_t>(obs_dev) & 15) == 0 ? 1 : 0);
     CUDA_TRY_P(cudaGetLastError());
     p->launches++;
     return B2G_OK;

@@ -92,25 +92,59 @@ class TrainLog:
 
 
 class PPO:
-    def __init__(self, env, cfg: PPOConfig = PPOConfig(), multi_gpu: bool = False, seed: int = 42):
+    def __init__(self, env, cfg: PPOConfig = PPOConfig(), multi_gpu: bool = False, seed: int = 42, fused_rollout: bool = False,
+                 cuda_graphs: bool = False):
+        """``fused_rollout``: evaluate the policy during the rollout with the library's fused tcgen05 kernel
+        (``learning/fused_policy.py``; bf16 operands, fp32 accumulation) instead of the torch modules. The update still
+        differentiates the fp32 torch network; the behaviour policy's (mu, neglogp, value) are the kernel's.
+
+        ``cuda_graphs``: capture the whole rollout (``horizon_length`` x [normalise, policy, sample, ``env.step``, bookkeeping] +
+        GAE) as ONE CUDA graph and each minibatch update (forward, backward, clip, Adam) as another, so that an epoch is a
+        handful of graph launches instead of ~2000 kernel launches from Python.  Needs a task whose ``step()`` is free of host
+        synchronisation and host-side per-step state (the fused flat tasks and Cartpole); the update graph is used on a
+        single GPU only (the multi-GPU path keeps its eager NCCL all-reduce)."""
         self.env, self.cfg, self.multi_gpu = env, cfg, multi_gpu
+        self.fused = None
+        self.cuda_graphs = bool(cuda_graphs)
         self.device = env.rl_device
         torch.manual_seed(seed)
         self.model = ActorCritic(env.num_obs, env.num_acts, cfg.units).to(self.device)
         self.obs_rms = RunningMeanStd((env.num_obs,)).to(self.device)
         self.val_rms = RunningMeanStd(()).to(self.device)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-8)
+        self.lr_t = torch.tensor(cfg.learning_rate, device=self.device, dtype=torch.float32)
+        graph_update = self.cuda_graphs and not multi_gpu
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t if graph_update else cfg.learning_rate, eps=1e-8,
+                                    capturable=graph_update)
         self.lr = cfg.learning_rate
         if multi_gpu:
             import torch.distributed as dist
 
             for p in self.model.parameters():
                 dist.broadcast(p.data, 0)
-        n = env.num_envs
-        self.ep_rew = torch.zeros(n, device=self.device)
-        self.ep_len = torch.zeros(n, device=self.device)
-        self.done_rew: List[float] = []
-        self.done_len: List[float] = []
+        if fused_rollout:
+            from .fused_policy import FusedPolicy
+
+            self.fused = FusedPolicy(env.num_obs, env.num_acts, cfg.units, self.device)
+        n, T, dev = env.num_envs, cfg.horizon_length, self.device
+        self.ep_rew = torch.zeros(n, device=dev)
+        self.ep_len = torch.zeros(n, device=dev)
+        # finished-episode accumulators (device side: no host sync inside the rollout)
+        self.fin = torch.zeros(3, device=dev, dtype=torch.float64)         # sum of rewards, sum of lengths, count
+        self._last_stats = (0.0, 0.0)
+        # rollout storage (static: the graphs replay into these)
+        self.obs = torch.zeros(n, env.num_obs, device=dev)
+        self.b_obs = torch.zeros(T, n, env.num_obs, device=dev)
+        self.b_act = torch.zeros(T, n, env.num_acts, device=dev)
+        self.b_mu = torch.zeros(T, n, env.num_acts, device=dev)
+        self.b_nlp, self.b_val, self.b_rew, self.b_done = (torch.zeros(T, n, device=dev) for _ in range(4))
+        self.f_ret = torch.zeros(T * n, device=dev)
+        self.f_val = torch.zeros(T * n, device=dev)
+        self.f_adv = torch.zeros(T * n, device=dev)
+        self.mb = min(cfg.minibatch_size, T * n)
+        self.idx = torch.zeros(self.mb, dtype=torch.long, device=dev)
+        self.kl_acc = torch.zeros((), device=dev)
+        self._g_rollout = None
+        self._g_update = None
 
     def _allreduce_grads(self):
         import torch.distributed as dist
@@ -125,100 +159,158 @@ class PPO:
                 p.grad.copy_(flat[off:off + k].view_as(p.grad))
                 off += k
 
+    # ------------------------------------------------------------------ rollout (static shapes, no host sync)
+    @torch.no_grad()
+    def _rollout(self):
+        cfg, env = self.cfg, self.env
+        T, N = cfg.horizon_length, env.num_envs
+        obs = self.obs
+        if self.fused is not None:
+            self.fused.sync(self.model)
+        log_std = self.model.log_std.expand(N, -1)
+        for t in range(T):
+            self.obs_rms.update(obs)
+            nobs = self.obs_rms.normalize(obs)
+            if self.fused is not None:
+                self.fused.set_obs_norm(self.obs_rms.mean, self.obs_rms.var, self.obs_rms.eps, 5.0)
+                mu, v = self.fused.forward(obs)
+            else:
+                mu, _, v = self.model(nobs)
+            act = mu + log_std.exp() * torch.randn_like(mu)
+            self.b_obs[t], self.b_act[t], self.b_mu[t], self.b_nlp[t] = nobs, act, mu, neglogp(act, mu, log_std)
+            self.b_val[t] = self.val_rms.denormalize(v)
+            o, rew, done, extras = env.step(torch.clamp(act, -1.0, 1.0))
+            obs.copy_(o["obs"])
+            # value bootstrap on time-outs (rl_games value_bootstrap, docs/release_notes.md:67)
+            rew = rew + cfg.gamma * self.b_val[t] * extras["time_outs"].float()
+            donef = (done != 0).float()
+            self.b_rew[t], self.b_done[t] = rew, donef
+            self.ep_rew += rew
+            self.ep_len += 1
+            self.fin[0] += (self.ep_rew * donef).sum()
+            self.fin[1] += (self.ep_len * donef).sum()
+            self.fin[2] += donef.sum()
+            self.ep_rew *= 1.0 - donef
+            self.ep_len *= 1.0 - donef
+        _, _, v_last = self.model(self.obs_rms.normalize(obs))
+        v_last = self.val_rms.denormalize(v_last)
+        adv = torch.zeros(T, N, device=self.device)
+        last = torch.zeros(N, device=self.device)
+        for t in reversed(range(T)):
+            nv = v_last if t == T - 1 else self.b_val[t + 1]
+            nonterm = 1.0 - self.b_done[t]
+            delta = self.b_rew[t] + cfg.gamma * nv * nonterm - self.b_val[t]
+            last = delta + cfg.gamma * cfg.tau * nonterm * last
+            adv[t] = last
+        ret = adv + self.b_val
+        self.val_rms.update(ret)
+        self.f_ret.copy_((ret.reshape(-1) - self.val_rms.mean.float()) / torch.sqrt(self.val_rms.var.float() + 1e-5))
+        self.f_val.copy_((self.b_val.reshape(-1) - self.val_rms.mean.float()) / torch.sqrt(self.val_rms.var.float() + 1e-5))
+        a = adv.reshape(-1)
+        self.f_adv.copy_((a - a.mean()) / (a.std() + 1e-8))
+
+    # ------------------------------------------------------------------ one minibatch update on self.idx
+    def _update(self):
+        cfg = self.cfg
+        T, N = cfg.horizon_length, self.env.num_envs
+        idx = self.idx
+        f_obs, f_act = self.b_obs.reshape(T * N, -1), self.b_act.reshape(T * N, -1)
+        f_nlp, f_mu = self.b_nlp.reshape(-1), self.b_mu.reshape(T * N, -1)
+        mu, log_std, v = self.model(f_obs[idx])
+        nlp = neglogp(f_act[idx], mu, log_std)
+        ratio = torch.exp(f_nlp[idx] - nlp)
+        a = self.f_adv[idx]
+        a_loss = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - cfg.e_clip, 1.0 + cfg.e_clip)).mean()
+        fv, fr = self.f_val[idx], self.f_ret[idx]
+        v_clip = fv + (v - fv).clamp(-cfg.e_clip, cfg.e_clip)
+        c_loss = torch.max((v - fr) ** 2, (v_clip - fr) ** 2).mean()
+        b_loss = (torch.clamp(mu - 1.1, min=0.0) ** 2 + torch.clamp(-1.1 - mu, min=0.0) ** 2).sum(-1).mean()
+        entropy = (log_std + 0.5 + 0.9189385332046727).sum(-1).mean()
+        loss = a_loss + 0.5 * cfg.critic_coef * c_loss - cfg.entropy_coef * entropy + cfg.bounds_loss_coef * b_loss
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.multi_gpu:
+            self._allreduce_grads()
+        nn.utils.clip_grad_norm_(self.model.parameters(), cfg.grad_norm)
+        self.opt.step()
+        with torch.no_grad():
+            # KL between the old and the new diagonal Gaussians (same fixed sigma family)
+            self.kl_acc += (((mu - f_mu[idx]) ** 2) / (2.0 * torch.exp(2.0 * log_std))).sum(-1).mean()
+
+    def _capture(self, fn, warmup=2):
+        """Warm ``fn`` up on a side stream (cuBLAS handles, lazy state), then capture it."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def _episode_stats(self):
+        s = self.fin.tolist()
+        if s[2] > 0:
+            self._last_stats = (s[0] / s[2], s[1] / s[2])
+        self.fin.zero_()
+        return self._last_stats
+
     def train(self, max_epochs=None, log_every=10, verbose=False) -> TrainLog:
         cfg, env = self.cfg, self.env
         T, N = cfg.horizon_length, env.num_envs
         log = TrainLog()
-        obs = env.reset()["obs"].clone()
+        self.obs.copy_(env.reset()["obs"])
+        graph_update = self.cuda_graphs and not self.multi_gpu
+        if self.cuda_graphs and self._g_rollout is None:
+            # the warm-up passes are real rollouts/updates on the live state (a few extra environment steps before epoch 0)
+            self._g_rollout = self._capture(self._rollout, warmup=1)
+            if graph_update:
+                self.idx.copy_(torch.randperm(T * N, device=self.device)[:self.mb])
+                self._g_update = self._capture(self._update, warmup=2)
+            self.fin.zero_()
         t0 = time.time()
         steps = 0
+        kl_lo, kl_hi = 0.5 * cfg.kl_threshold, 2.0 * cfg.kl_threshold
+        n_mb = max((T * N) // self.mb, 1)
         for epoch in range(max_epochs or cfg.max_epochs):
-            b_obs = torch.zeros(T, N, env.num_obs, device=self.device)
-            b_act = torch.zeros(T, N, env.num_acts, device=self.device)
-            b_nlp, b_val, b_rew, b_done = (torch.zeros(T, N, device=self.device) for _ in range(4))
-            b_mu = torch.zeros(T, N, env.num_acts, device=self.device)
-            with torch.no_grad():
-                for t in range(T):
-                    self.obs_rms.update(obs)
-                    nobs = self.obs_rms.normalize(obs)
-                    mu, log_std, v = self.model(nobs)
-                    act = mu + log_std.exp() * torch.randn_like(mu)
-                    b_obs[t], b_act[t], b_mu[t], b_nlp[t] = nobs, act, mu, neglogp(act, mu, log_std)
-                    b_val[t] = self.val_rms.denormalize(v)
-                    o, rew, done, extras = env.step(torch.clamp(act, -1.0, 1.0))
-                    obs = o["obs"].clone()
-                    rew = rew.clone()
-                    # value bootstrap on time-outs (rl_games value_bootstrap, docs/release_notes.md:67)
-                    rew += cfg.gamma * b_val[t] * extras["time_outs"].float()
-                    b_rew[t], b_done[t] = rew, done.float()
-                    self.ep_rew += rew
-                    self.ep_len += 1
-                    ids = done.nonzero(as_tuple=False).flatten()
-                    if len(ids) > 0:
-                        self.done_rew += self.ep_rew[ids].tolist()
-                        self.done_len += self.ep_len[ids].tolist()
-                        self.ep_rew[ids] = 0
-                        self.ep_len[ids] = 0
-                steps += T * N
-                _, _, v_last = self.model(self.obs_rms.normalize(obs))
-                v_last = self.val_rms.denormalize(v_last)
-                adv = torch.zeros(T, N, device=self.device)
-                last = torch.zeros(N, device=self.device)
-                for t in reversed(range(T)):
-                    nv = v_last if t == T - 1 else b_val[t + 1]
-                    nonterm = 1.0 - b_done[t]
-                    delta = b_rew[t] + cfg.gamma * nv * nonterm - b_val[t]
-                    last = delta + cfg.gamma * cfg.tau * nonterm * last
-                    adv[t] = last
-                ret = adv + b_val
-                self.val_rms.update(ret)
-                f_ret = (ret.reshape(-1) - self.val_rms.mean.float()) / torch.sqrt(self.val_rms.var.float() + 1e-5)
-                f_val = (b_val.reshape(-1) - self.val_rms.mean.float()) / torch.sqrt(self.val_rms.var.float() + 1e-5)
-                f_adv = adv.reshape(-1)
-                f_adv = (f_adv - f_adv.mean()) / (f_adv.std() + 1e-8)
-                f_obs, f_act, f_nlp, f_mu = b_obs.reshape(T * N, -1), b_act.reshape(T * N, -1), b_nlp.reshape(-1), b_mu.reshape(T * N, -1)
-            mb = min(cfg.minibatch_size, T * N)
+            if self._g_rollout is not None:
+                self._g_rollout.replay()
+            else:
+                self._rollout()
+            steps += T * N
             for _ in range(cfg.mini_epochs):
                 perm = torch.randperm(T * N, device=self.device)
-                kls = []
-                for s in range(0, T * N, mb):
-                    idx = perm[s:s + mb]
-                    mu, log_std, v = self.model(f_obs[idx])
-                    nlp = neglogp(f_act[idx], mu, log_std)
-                    ratio = torch.exp(f_nlp[idx] - nlp)
-                    a = f_adv[idx]
-                    a_loss = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - cfg.e_clip, 1.0 + cfg.e_clip)).mean()
-                    v_clip = f_val[idx] + (v - f_val[idx]).clamp(-cfg.e_clip, cfg.e_clip)
-                    c_loss = torch.max((v - f_ret[idx]) ** 2, (v_clip - f_ret[idx]) ** 2).mean()
-                    b_loss = (torch.clamp(mu - 1.1, min=0.0) ** 2 + torch.clamp(-1.1 - mu, min=0.0) ** 2).sum(-1).mean()
-                    entropy = (log_std + 0.5 + 0.9189385332046727).sum(-1).mean()
-                    loss = a_loss + 0.5 * cfg.critic_coef * c_loss - cfg.entropy_coef * entropy + cfg.bounds_loss_coef * b_loss
-                    self.opt.zero_grad(set_to_none=True)
-                    loss.backward()
-                    if self.multi_gpu:
-                        self._allreduce_grads()
-                    nn.utils.clip_grad_norm_(self.model.parameters(), cfg.grad_norm)
-                    self.opt.step()
-                    with torch.no_grad():
-                        # KL between the old and the new diagonal Gaussians (same fixed sigma family)
-                        kl = (((mu - f_mu[idx]) ** 2) / (2.0 * torch.exp(2.0 * log_std))).sum(-1).mean()
-                        kls.append(kl)
-                kl = torch.stack(kls).mean()
+                self.kl_acc.zero_()
+                for k in range(n_mb):
+                    self.idx.copy_(perm[k * self.mb:(k + 1) * self.mb])
+                    if self._g_update is not None:
+                        self._g_update.replay()
+                    else:
+                        self._update()
+                kl = self.kl_acc / n_mb
                 if self.multi_gpu:
                     import torch.distributed as dist
 
                     dist.all_reduce(kl)
                     kl /= dist.get_world_size()
-                kl = float(kl)
-                if kl > 2.0 * cfg.kl_threshold:
-                    self.lr = max(self.lr / 1.5, 1e-6)
-                elif kl < 0.5 * cfg.kl_threshold:
-                    self.lr = min(self.lr * 1.5, 1e-2)
-                for g in self.opt.param_groups:
-                    g["lr"] = self.lr
+                if graph_update:       # adaptive learning rate on the device (the Adam graph reads self.lr_t)
+                    lr = self.lr_t
+                    self.lr_t.copy_(torch.where(kl > kl_hi, torch.clamp(lr / 1.5, min=1e-6), torch.where(kl < kl_lo, torch.clamp(lr * 1.5, max=1e-2), lr)))
+                else:
+                    kl = float(kl)
+                    if kl > kl_hi:
+                        self.lr = max(self.lr / 1.5, 1e-6)
+                    elif kl < kl_lo:
+                        self.lr = min(self.lr * 1.5, 1e-2)
+                    for g in self.opt.param_groups:
+                        g["lr"] = self.lr
             if (epoch + 1) % log_every == 0 or epoch == 0:
-                r = sum(self.done_rew[-2000:]) / max(len(self.done_rew[-2000:]), 1)
-                l = sum(self.done_len[-2000:]) / max(len(self.done_len[-2000:]), 1)
+                if graph_update:
+                    self.lr = float(self.lr_t)
+                r, l = self._episode_stats()
                 log.epochs.append(epoch + 1)
                 log.env_steps.append(steps)
                 log.mean_episode_reward.append(r)
@@ -226,5 +318,4 @@ class PPO:
                 log.wall_s.append(time.time() - t0)
                 if verbose:
                     print(f"epoch {epoch + 1:5d} env_steps {steps:10d} ep_rew {r:8.3f} ep_len {l:7.1f} lr {self.lr:.2e} wall {time.time() - t0:6.1f}s", flush=True)
-                self.done_rew, self.done_len = self.done_rew[-4000:], self.done_len[-4000:]
         return log

@@ -92,6 +92,21 @@ def test_policy_identity_norm_and_sync():
     assert (mu - mu_e).abs().max().item() < 2e-3 and (v - v_e).abs().max().item() < 2e-3
 
 
+def test_policy_unaligned_observation_view():
+    """An observation view that is not 16-byte aligned takes the scalar load path and gives the same result."""
+    from isaacgymenv_b200.learning.fused_policy import FusedPolicy
+
+    model = _net(48, 12, (256, 128, 64), seed=11)
+    pol = FusedPolicy(48, 12, (256, 128, 64), "cuda:0")
+    pol.sync(model)
+    buf = torch.randn(700 * 48 + 1, device="cuda")
+    obs_u = buf[1:].view(700, 48)
+    assert obs_u.data_ptr() % 16 != 0 and obs_u.is_contiguous()
+    mu_u, v_u = pol.forward(obs_u)
+    mu_a, v_a = pol.forward(obs_u.clone())
+    assert torch.equal(mu_u, mu_a) and torch.equal(v_u, v_a)
+
+
 def test_policy_rejects_unsupported_shapes():
     from isaacgymenv_b200 import _lib
     from isaacgymenv_b200.learning.fused_policy import FusedPolicy

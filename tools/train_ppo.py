@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=300)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--out", default="")
+    ap.add_argument("--cuda-graphs", action="store_true", help="capture the rollout and the minibatch update as CUDA graphs")
+    ap.add_argument("--fused-rollout", action="store_true", help="evaluate the policy in the rollout with the fused tcgen05 kernel")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -37,7 +39,7 @@ def main():
         cfg = PPOConfig(units=(512, 256, 128), minibatch_size=16384, entropy_coef=0.001)
     if args.task == "Cartpole":
         cfg = PPOConfig(units=(32, 32), horizon_length=16, minibatch_size=8192, mini_epochs=8)
-    ppo = PPO(env, cfg, multi_gpu=multi, seed=args.seed + info.rank)
+    ppo = PPO(env, cfg, multi_gpu=multi, seed=args.seed + info.rank, fused_rollout=args.fused_rollout, cuda_graphs=args.cuda_graphs)
     log = ppo.train(max_epochs=args.epochs, log_every=10, verbose=info.rank == 0)
     if multi:
         dist.barrier()
@@ -45,7 +47,7 @@ def main():
         if multi:
             dist.destroy_process_group()
         return
-    out = {"task": args.task, "num_envs_per_gpu": args.num_envs, "n_gpus": info.world_size, "env_steps_all_gpus": [s * info.world_size for s in log.env_steps], "epochs": log.epochs, "env_steps": log.env_steps, "mean_episode_reward": log.mean_episode_reward,
+    out = {"task": args.task, "fused_rollout": bool(args.fused_rollout), "cuda_graphs": bool(args.cuda_graphs), "num_envs_per_gpu": args.num_envs, "n_gpus": info.world_size, "env_steps_all_gpus": [s * info.world_size for s in log.env_steps], "epochs": log.epochs, "env_steps": log.env_steps, "mean_episode_reward": log.mean_episode_reward,
            "mean_episode_length": log.mean_episode_length, "wall_s": log.wall_s, "gpu": torch.cuda.get_device_name(0),
            "env_steps_per_sec_incl_learner": (log.env_steps[-1] * info.world_size / log.wall_s[-1]) if log.wall_s else None}
     if args.out:
