@@ -289,6 +289,10 @@ int b2g_task_terrain_create(b2g_sim* sim, const b2g_terrain_cfg* cfg, const int1
 int b2g_task_terrain_set_step(b2g_sim* sim, int64_t common_step_counter);
 /* init_done / curriculum switch of update_terrain_level (anymal_terrain.py:428) */
 int b2g_task_terrain_set_init_done(b2g_sim* sim, int init_done);
+/* enable != 0: the library keeps common_step_counter in device memory and advances it at the end of every
+ * b2g_task_step, so consecutive steps need no host-side state and can be captured in a CUDA graph
+ * (b2g_task_terrain_set_step then sets the value the NEXT step uses). */
+int b2g_task_terrain_device_step(b2g_sim* sim, int enable);
 
 /* task-generic entry points (dispatch on the task created on this sim) */
 int b2g_task_step(b2g_sim* sim, const float* actions_dev, void* stream);          /* VecTask.step, one launch   */
@@ -324,6 +328,12 @@ int b2g_task_set_rand_override(b2g_sim* sim, int use_rand_override);
  * H2D, steps, copies obs/rew/reset/timeout D2H, synchronises the stream. */
 int b2g_task_anymal_step_host(b2g_sim* sim, const float* actions_host, float* obs_host, float* rew_host,
                               int64_t* reset_host, int64_t* timeout_host, void* stream);
+
+/* Host-buffer layout that makes b2g_task_step_host return everything with ONE device-to-host copy: byte offsets of
+ * obs, rew, reset and time-outs inside a single (page-locked) host allocation of total_bytes; pass obs_host = base +
+ * offsets[0], rew_host = base + offsets[1], ... Buffers laid out differently are served with one copy each. Page-locked
+ * action buffers are read by the kernel in place, pageable ones are staged. */
+int b2g_task_host_layout(const b2g_sim* sim, int64_t* offsets /*[4]*/, int64_t* total_bytes);
 
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 int64_t b2g_sim_launch_count(const b2g_sim* sim);

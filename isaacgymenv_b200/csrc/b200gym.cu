@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(kBlock) k_terrain_post(SimArgs A, TerrainArgs 
 }
 
 // extras["episode"] (anymal_terrain.py:420-425): means over the envs that reset this step; one block, fixed order
-__global__ void k_terrain_extras(const float* report, const long long* reset, const long long* levels, float* extras, int n, float inv_len_s) {
+__global__ void k_terrain_extras(const float* report, const long long* reset, const long long* levels, float* extras, int n, float inv_len_s,
+                                 long long* step_ctr) {
     __shared__ float red[256];
     float vals[15];
     for (int k = 0; k < 15; k++) vals[k] = 0.0f;
@@ -160,6 +161,7 @@ __global__ void k_terrain_extras(const float* report, const long long* reset, co
         extras[13] = tot[14] / (float)n;
         extras[14] = tot[13];
     }
+    if (threadIdx.x == 0 && step_ctr) *step_ctr += 1;     // last kernel of the step: the next step sees the next counter value
 }
 
 template <int LANES, int NL>
@@ -266,11 +268,17 @@ struct b2g_sim {
     long long *terrain_levels = nullptr, *terrain_types = nullptr;
     int16_t* height_samples = nullptr;
     long long common_step = 0;
+    long long* step_ctr = nullptr;   // device copy of the counter the NEXT step uses (b2g_task_terrain_device_step)
+    int auto_step = 0;
     int init_done = 0;
     float *obs = nullptr, *obs_clamped = nullptr, *rew = nullptr, *commands = nullptr, *actions = nullptr, *rand_override = nullptr;
     long long *reset = nullptr, *progress = nullptr, *timeout = nullptr;
     int* reset_count = nullptr;
     float* actions_in = nullptr;   // staging for step_host
+    // obs_clamped | rew | reset | timeout live back to back in ONE allocation so that step_host can return them with a
+    // single device-to-host copy when the caller's buffers follow the same layout (b2g_task_host_layout)
+    unsigned char* out_arena = nullptr;
+    size_t out_off[4] = {0, 0, 0, 0}, out_total = 0;
     int use_rand_override = 0;
     int64_t launches = 0;
 };
@@ -411,7 +419,7 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         R.reset_override = s->use_rand_override ? s->rand_override : nullptr;
         R.noise_override = s->use_rand_override ? s->noise_override : nullptr;
         R.push_override = s->use_rand_override ? s->push_override : nullptr;
-        R.common_step = s->common_step; R.init_done = s->init_done; R.post_only = post_only; R.seed = s->seed;
+        R.common_step = s->common_step; R.step_ctr = s->auto_step ? s->step_ctr : nullptr; R.init_done = s->init_done; R.post_only = post_only; R.seed = s->seed;
         if (s->v.lanes == 4) {
             if (s->has_hf) k_terrain_phys<4, 3, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<4, 3, false><<<grid, kBlock, sm, st>>>(A, R);
             if (post_only != 2) k_terrain_post<4, 3><<<grid, kBlock, 0, st>>>(A, R);
@@ -424,7 +432,10 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
             CUDA_TRY(cudaGetLastError());
             return B2G_OK;
         }
-        k_terrain_extras<<<1, 256, 0, st>>>(s->report, s->reset, s->terrain_levels, s->extras, s->n_envs, 1.0f / s->tcfg.max_episode_length_s);
+        const bool advance = s->auto_step && post_only == 0;
+        k_terrain_extras<<<1, 256, 0, st>>>(s->report, s->reset, s->terrain_levels, s->extras, s->n_envs, 1.0f / s->tcfg.max_episode_length_s,
+                                          advance ? s->step_ctr : nullptr);
+        if (advance) s->common_step++;
         s->launches += 3;
         CUDA_TRY(cudaGetLastError());
         return B2G_OK;
@@ -486,11 +497,11 @@ int b2g_sim_destroy(b2g_sim* s) {
     if (!s) return fail(B2G_ERR_ARG, "null sim");
     with_device(s, [&]() {
         for (int k = 0; k < B2G_T_COUNT; k++) if (s->t[k]) cudaFree(s->t[k]);
-        void* ptrs[] = {s->d_model, s->d_hf, s->obs, s->obs_clamped, s->rew, s->commands, s->actions, s->rand_override,
-                        s->reset, s->progress, s->timeout, s->reset_count, s->actions_in, s->torques, s->last_actions, s->last_dof_vel,
+        void* ptrs[] = {s->d_model, s->d_hf, s->obs, s->out_arena, s->commands, s->actions, s->rand_override,
+                        s->progress, s->reset_count, s->actions_in, s->torques, s->last_actions, s->last_dof_vel,
                         s->feet_air_time, s->episode_sums, s->env_origins, s->terrain_origins, s->scratch9, s->resetw, s->report, s->measured,
                         s->noise_override, s->push_override, s->extras, s->terrain_levels, s->terrain_types, s->height_samples,
-                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands};
+                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands, s->step_ctr};
         for (void* p : ptrs) if (p) cudaFree(p);
         return 0;
     });
@@ -714,15 +725,23 @@ static int alloc_task_buffers(b2g_sim* s, int num_obs, int num_act, int n_draws)
         const size_t n = s->n_envs;
         s->num_obs = num_obs; s->num_act = num_act; s->n_draws = n_draws;
         CUDA_TRY(cudaMalloc(&s->obs, sizeof(float) * n * num_obs));
-        CUDA_TRY(cudaMalloc(&s->obs_clamped, sizeof(float) * n * num_obs));
-        CUDA_TRY(cudaMalloc(&s->rew, sizeof(float) * n));
+        auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+        s->out_off[0] = 0;
+        s->out_off[1] = s->out_off[0] + up(sizeof(float) * n * num_obs);
+        s->out_off[2] = s->out_off[1] + up(sizeof(float) * n);
+        s->out_off[3] = s->out_off[2] + up(sizeof(long long) * n);
+        s->out_total = s->out_off[3] + up(sizeof(long long) * n);
+        CUDA_TRY(cudaMalloc(&s->out_arena, s->out_total));
+        CUDA_TRY(cudaMemset(s->out_arena, 0, s->out_total));
+        s->obs_clamped = reinterpret_cast<float*>(s->out_arena + s->out_off[0]);
+        s->rew = reinterpret_cast<float*>(s->out_arena + s->out_off[1]);
+        s->reset = reinterpret_cast<long long*>(s->out_arena + s->out_off[2]);
+        s->timeout = reinterpret_cast<long long*>(s->out_arena + s->out_off[3]);
         CUDA_TRY(cudaMalloc(&s->commands, sizeof(float) * n * 4));
         CUDA_TRY(cudaMalloc(&s->actions, sizeof(float) * n * num_act));
         CUDA_TRY(cudaMalloc(&s->actions_in, sizeof(float) * n * num_act));
         CUDA_TRY(cudaMalloc(&s->rand_override, sizeof(float) * n * n_draws));
-        CUDA_TRY(cudaMalloc(&s->reset, sizeof(long long) * n));
         CUDA_TRY(cudaMalloc(&s->progress, sizeof(long long) * n));
-        CUDA_TRY(cudaMalloc(&s->timeout, sizeof(long long) * n));
         CUDA_TRY(cudaMalloc(&s->reset_count, sizeof(int) * n));
         CUDA_TRY(cudaMemset(s->obs, 0, sizeof(float) * n * num_obs));
         CUDA_TRY(cudaMemset(s->obs_clamped, 0, sizeof(float) * n * num_obs));
@@ -841,7 +860,30 @@ int b2g_task_terrain_create(b2g_sim* s, const b2g_terrain_cfg* cfg, const int16_
 int b2g_task_terrain_set_step(b2g_sim* s, int64_t step) {
     if (!s) return fail(B2G_ERR_ARG, "null sim");
     s->common_step = step;
+    if (s->auto_step && s->step_ctr)
+        return with_device(s, [&]() {
+            const long long v = step;
+            CUDA_TRY(cudaMemcpy(s->step_ctr, &v, sizeof(v), cudaMemcpyHostToDevice));
+            return (int)B2G_OK;
+        });
     return B2G_OK;
+}
+
+int b2g_task_terrain_device_step(b2g_sim* s, int enable) {
+    if (!s) return fail(B2G_ERR_ARG, "null sim");
+    if (!s->has_task || s->task_kind != 3) return fail(B2G_ERR_STATE, "no rough-terrain task created");
+    return with_device(s, [&]() {
+        if (enable) {
+            if (!s->step_ctr) CUDA_TRY(cudaMalloc(&s->step_ctr, sizeof(long long)));
+            const long long v = s->common_step + 1;      // the value the next step uses
+            CUDA_TRY(cudaMemcpy(s->step_ctr, &v, sizeof(v), cudaMemcpyHostToDevice));
+            s->common_step = v;
+        } else if (s->auto_step) {
+            s->common_step -= 1;                         // back to "last value used"; the caller sets the next one itself
+        }
+        s->auto_step = enable ? 1 : 0;
+        return (int)B2G_OK;
+    });
 }
 
 int b2g_task_terrain_set_init_done(b2g_sim* s, int v) {
@@ -923,6 +965,14 @@ int b2g_task_anymal_post_only(b2g_sim* s, const float* actions_dev, void* stream
     return with_device(s, [&]() { return launch_anymal_step(s, actions_dev, (cudaStream_t)stream, 1); });
 }
 
+int b2g_task_host_layout(const b2g_sim* s, int64_t* offsets, int64_t* total_bytes) {
+    if (!s || !offsets || !total_bytes) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->has_task) return fail(B2G_ERR_STATE, "no task created");
+    for (int i = 0; i < 4; i++) offsets[i] = (int64_t)s->out_off[i];
+    *total_bytes = (int64_t)s->out_total;
+    return B2G_OK;
+}
+
 int b2g_task_anymal_step_host(b2g_sim* s, const float* actions_host, float* obs_host, float* rew_host, int64_t* reset_host,
                               int64_t* timeout_host, void* stream) {
     if (!s || !actions_host) return fail(B2G_ERR_ARG, "null argument");
@@ -930,13 +980,31 @@ int b2g_task_anymal_step_host(b2g_sim* s, const float* actions_host, float* obs_
     return with_device(s, [&]() {
         cudaStream_t st = (cudaStream_t)stream;
         const size_t n = s->n_envs, nd = s->num_act;
-        CUDA_TRY(cudaMemcpyAsync(s->actions_in, actions_host, sizeof(float) * n * nd, cudaMemcpyHostToDevice, st));
-        const int rc = launch_anymal_step(s, s->actions_in, st);
+        // page-locked actions are read by the kernel in place (each thread loads its own few values once, over PCIe / C2C);
+        // pageable ones are staged with a copy
+        const float* actions_dev = s->actions_in;
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, actions_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+            actions_dev = static_cast<const float*>(pa.devicePointer);
+        } else {
+            cudaGetLastError();
+            CUDA_TRY(cudaMemcpyAsync(s->actions_in, actions_host, sizeof(float) * n * nd, cudaMemcpyHostToDevice, st));
+        }
+        const int rc = launch_anymal_step(s, actions_dev, st);
         if (rc != B2G_OK) return rc;
-        if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, s->obs_clamped, sizeof(float) * n * s->num_obs, cudaMemcpyDeviceToHost, st));
-        if (rew_host) CUDA_TRY(cudaMemcpyAsync(rew_host, s->rew, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-        if (reset_host) CUDA_TRY(cudaMemcpyAsync(reset_host, s->reset, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
-        if (timeout_host) CUDA_TRY(cudaMemcpyAsync(timeout_host, s->timeout, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(obs_host);
+        const bool packed = obs_host && rew_host && reset_host && timeout_host &&
+                            reinterpret_cast<const unsigned char*>(rew_host) == base + s->out_off[1] &&
+                            reinterpret_cast<const unsigned char*>(reset_host) == base + s->out_off[2] &&
+                            reinterpret_cast<const unsigned char*>(timeout_host) == base + s->out_off[3];
+        if (packed) {   // the caller's buffers follow b2g_task_host_layout: one copy
+            CUDA_TRY(cudaMemcpyAsync(obs_host, s->out_arena, s->out_off[3] + sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, s->obs_clamped, sizeof(float) * n * s->num_obs, cudaMemcpyDeviceToHost, st));
+            if (rew_host) CUDA_TRY(cudaMemcpyAsync(rew_host, s->rew, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+            if (reset_host) CUDA_TRY(cudaMemcpyAsync(reset_host, s->reset, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+            if (timeout_host) CUDA_TRY(cudaMemcpyAsync(timeout_host, s->timeout, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        }
         CUDA_TRY(cudaStreamSynchronize(st));
         return (int)B2G_OK;
     });

@@ -409,6 +409,7 @@ struct TerrainArgs {
     const float* noise_override; // (N,no)
     const float* push_override;  // (N,2)
     long long common_step;       // counter AFTER this step's increment
+    const long long* step_ctr = nullptr;   // when set, the counter is read from device memory instead (CUDA-graph replay)
     int init_done;
     int post_only;
     unsigned long long seed;
@@ -675,9 +676,10 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
         Grp<LANES>::sync();
     }
     // ---- post_physics_step (tasks/anymal_terrain.py:453-471) ----
-    if (C.push_interval > 0 && (T.common_step % C.push_interval) == 0) {      // push_robots :437-439
-        st.rv.x = rand_range(-1.0f, 1.0f, terrain_uniform(T, T.push_override, 2, env, (unsigned)T.common_step, 3u, 0));
-        st.rv.y = rand_range(-1.0f, 1.0f, terrain_uniform(T, T.push_override, 2, env, (unsigned)T.common_step, 3u, 1));
+    const long long common_step = T.step_ctr ? *T.step_ctr : T.common_step;
+    if (C.push_interval > 0 && (common_step % C.push_interval) == 0) {      // push_robots :437-439
+        st.rv.x = rand_range(-1.0f, 1.0f, terrain_uniform(T, T.push_override, 2, env, (unsigned)common_step, 3u, 0));
+        st.rv.y = rand_range(-1.0f, 1.0f, terrain_uniform(T, T.push_override, 2, env, (unsigned)common_step, 3u, 1));
     }
     const V3 lin = quat_rotate_inverse(st.qx, st.qy, st.qz, st.qw, st.rv);
     const V3 ang = quat_rotate_inverse(st.qx, st.qy, st.qz, st.qw, st.rw);
@@ -851,7 +853,7 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
     const int no = 12 + 2 * nctrl + nhp + nd + (has_arm ? 10 : 0);
     float* o = T.obs + (size_t)env * no;
     float* oc = T.obs_clamped + (size_t)env * no;
-    const unsigned step = (unsigned)T.common_step;
+    const unsigned step = (unsigned)(T.step_ctr ? *T.step_ctr : T.common_step);
     auto put = [&](int idx, float val, float nscale) {
         if (C.add_noise && nscale != 0.0f) val += (2.0f * terrain_uniform(T, T.noise_override, no, env, step, 2u, idx) - 1.0f) * nscale;
         if (valid) { o[idx] = val; oc[idx] = fminf(fmaxf(val, -C.clip_obs), C.clip_obs); }

@@ -265,6 +265,8 @@ class PPO:
         self.obs.copy_(env.reset()["obs"])
         graph_update = self.cuda_graphs and not self.multi_gpu
         if self.cuda_graphs and self._g_rollout is None:
+            if hasattr(env, "enable_device_step_counter"):      # rough-terrain tasks: no per-step host state inside the graph
+                env.enable_device_step_counter(True)
             # the warm-up passes are real rollouts/updates on the live state (a few extra environment steps before epoch 0)
             self._g_rollout = self._capture(self._rollout, warmup=1)
             if graph_update:

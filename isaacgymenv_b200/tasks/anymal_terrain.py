@@ -81,6 +81,7 @@ class AnymalTerrain(VecTask):
         self.dof_vel = self.dof_state.view(self.num_envs, self.num_dof, 2)[..., 1]
         self.contact_forces = gymtorch.wrap_tensor(self.gym.acquire_net_contact_force_tensor(self.sim)).view(self.num_envs, -1, 3)
         self.common_step_counter = 0
+        self._device_step = False
         self.extras = {}
         self.noise_scale_vec = self._get_noise_scale_vec(cfg)
         self.commands_scale = torch.tensor([self.lin_vel_scale, self.lin_vel_scale, self.ang_vel_scale], device=self.device, requires_grad=False)
@@ -318,6 +319,12 @@ class AnymalTerrain(VecTask):
         self._reset_i64[env_ids] = 1
         self._episode_sums[:, env_ids] = 0.0
 
+    def enable_device_step_counter(self, enable: bool = True):
+        """Keep ``common_step_counter`` (push schedule, noise stream) on the device so that ``step()`` has no per-step host
+        state and a rollout can be captured in a CUDA graph; the Python attribute then counts eager calls only."""
+        _lib.check(self._lib.b2g_task_terrain_device_step(self.sim.handle, 1 if enable else 0), "device_step")
+        self._device_step = bool(enable)
+
     def pre_physics_step(self, actions):
         raise NotImplementedError("the terrain tasks run fused (step() launches the kernels directly)")
 
@@ -330,7 +337,8 @@ class AnymalTerrain(VecTask):
             a = a.contiguous()
         self._last_actions_in = a
         self.common_step_counter += 1
-        _lib.check(self._lib.b2g_task_terrain_set_step(self.sim.handle, int(self.common_step_counter)))
+        if not self._device_step:
+            _lib.check(self._lib.b2g_task_terrain_set_step(self.sim.handle, int(self.common_step_counter)))
         _lib.check(self._lib.b2g_task_step(self.sim.handle, C.c_void_p(a.data_ptr()), self.sim.stream()), "step")
         self.control_steps += 1
         # reference: reset_buf / timeout_buf are bool in the terrain tasks (anymal_terrain.py:295, vec_task.py:394)

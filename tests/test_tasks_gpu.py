@@ -203,3 +203,98 @@ def test_generic_jacobian_and_mass_matrix_agree_with_the_fused_arm_slices():
     assert int(alive.sum()) > 0
     torch.testing.assert_close(jac[alive][:, env.hand_joint_index, :, :6], env._j_eef[alive], rtol=0, atol=1e-5)
     torch.testing.assert_close(mm[alive][:, -6:, -6:], env._mm[alive], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("task,nact", [("Anymal", 12), ("Cartpole", 1), ("AnymalTerrain", 12)])
+def test_step_host_matches_device_step(task, nact):
+    """b2g_task_step_host (the host-buffer entry the end-to-end benchmark times) against the device-pointer step on a twin
+    sim: (a) page-locked buffers in the packed b2g_task_host_layout (zero-copy actions, one D2H copy), (b) pageable numpy
+    buffers laid out separately (staged actions, one copy per result) -- all three bit-identical."""
+    import ctypes as C
+
+    import torch
+
+    import isaacgymenv_b200
+    from isaacgymenv_b200 import _lib
+
+    lib = _lib.load()
+    n = 128
+    over = {"env": {"terrain": {"terrainType": "plane"}}} if task == "AnymalTerrain" else None
+    envs = []
+    for _ in range(3):
+        torch.manual_seed(77)       # the terrain tasks draw friction buckets / start offsets from torch at construction
+        envs.append(isaacgymenv_b200.make(seed=5, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=over))
+    nobs = envs[0].num_obs
+    offs, tot = (C.c_int64 * 4)(), C.c_int64()
+    _lib.check(lib.b2g_task_host_layout(envs[1].sim.handle, offs, C.byref(tot)))
+    assert list(offs) == sorted(offs) and offs[0] == 0 and tot.value >= offs[3] + 8 * n and all(o % 256 == 0 for o in offs)
+    arena = torch.zeros(tot.value, dtype=torch.uint8).pin_memory()
+    p_obs = arena[offs[0]:offs[0] + n * nobs * 4].view(torch.float32).view(n, nobs)
+    p_rew = arena[offs[1]:offs[1] + n * 4].view(torch.float32)
+    p_rs = arena[offs[2]:offs[2] + n * 8].view(torch.int64)
+    p_to = arena[offs[3]:offs[3] + n * 8].view(torch.int64)
+    q_obs, q_rew = np.zeros((n, nobs), np.float32), np.zeros(n, np.float32)
+    q_rs, q_to = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator().manual_seed(9)
+    for it in range(12):
+        act = (2 * torch.rand(n, nact, generator=g) - 1)
+        a_pin = act.clone().pin_memory()
+        a_np = act.numpy().copy()
+        if hasattr(envs[0], "common_step_counter"):
+            for e in envs[1:]:      # the python task advances this counter inside step(); the raw C entry does not
+                e.common_step_counter += 1
+                lib.b2g_task_terrain_set_step(e.sim.handle, int(e.common_step_counter))
+        o, r, d, ex = envs[0].step(act.cuda())
+        _lib.check(lib.b2g_task_step_host(envs[1].sim.handle, C.c_void_p(a_pin.data_ptr()), C.c_void_p(p_obs.data_ptr()), C.c_void_p(p_rew.data_ptr()),
+                                          C.c_void_p(p_rs.data_ptr()), C.c_void_p(p_to.data_ptr()), sp), "step_host packed")
+        _lib.check(lib.b2g_task_step_host(envs[2].sim.handle, a_np.ctypes.data_as(C.c_void_p), q_obs.ctypes.data_as(C.c_void_p),
+                                          q_rew.ctypes.data_as(C.c_void_p), q_rs.ctypes.data_as(C.c_void_p), q_to.ctypes.data_as(C.c_void_p), sp),
+                   "step_host pageable")
+        torch.cuda.synchronize()
+        assert torch.equal(o["obs"].cpu(), torch.from_numpy(q_obs)), ("pageable", it, (o["obs"].cpu() - torch.from_numpy(q_obs)).abs().max(0))
+        assert torch.equal(o["obs"].cpu(), p_obs), ("packed", it, (o["obs"].cpu() - p_obs).abs().max(0))
+        assert torch.equal(r.cpu(), p_rew) and torch.equal(r.cpu(), torch.from_numpy(q_rew))
+        assert torch.equal(d.cpu().long(), p_rs) and torch.equal(d.cpu().long(), torch.from_numpy(q_rs))
+        assert torch.equal(ex["time_outs"].cpu().long(), p_to) and torch.equal(ex["time_outs"].cpu().long(), torch.from_numpy(q_to))
+
+
+@pytest.mark.parametrize("task,nact", [("AnymalTerrain", 12), ("UsefulHound", 18)])
+def test_terrain_device_step_counter_matches_host_counter(task, nact):
+    """common_step_counter kept on the device (graph-capturable step) == the host-driven counter, bit for bit; then the same
+    steps replayed from a CUDA graph."""
+    import torch
+
+    import isaacgymenv_b200
+
+    n = 64
+    over = {"env": {"terrain": {"terrainType": "plane"}, "learn": {"pushInterval_s": 0.1}}}
+    twins = []
+    for _ in range(3):
+        torch.manual_seed(77)       # construction draws (friction buckets, start offsets) come from torch
+        twins.append(isaacgymenv_b200.make(seed=11, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=over))
+    a, b, c = twins
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = [2 * torch.rand(n, nact, device="cuda", generator=g) - 1 for _ in range(24)]
+    for i in range(4):          # a few host-counter steps first: enabling must pick the counter up where it is
+        for e in (a, b, c):
+            e.step(acts[i])
+    b.enable_device_step_counter(True)
+    c.enable_device_step_counter(True)
+    static_act = acts[4].clone()
+    out = {}
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    for i in range(4, 24):
+        oa, ra, da, _ = a.step(acts[i])
+        ob, rb, db, _ = b.step(acts[i])
+        assert torch.equal(oa["obs"], ob["obs"]) and torch.equal(ra, rb) and torch.equal(da, db), i
+        static_act.copy_(acts[i])
+        if i == 4:
+            with torch.cuda.graph(graph):
+                oc, rc, dc, _ = c.step(static_act)
+                out = {"obs": oc["obs"], "rew": rc, "done": dc}
+        graph.replay()          # capture does not execute: every step of `c`, the first included, is a replay
+        torch.cuda.synchronize()
+        assert torch.equal(oa["obs"], out["obs"]) and torch.equal(ra, out["rew"]) and torch.equal(da, out["done"]), i
