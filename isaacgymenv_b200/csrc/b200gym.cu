@@ -86,8 +86,11 @@ __global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
     simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, valid, sc, bf);
 }
 
-template <int LANES, int NL, bool HF>
-__global__ void __launch_bounds__(kBlock) k_anymal_step(SimArgs A, TaskArgs T) {
+// MINB = minimum resident blocks per SM the register allocation must allow: 1 = no cap (233 registers, 4 blocks/SM: lowest
+// latency per warp, the 4096-env headline), 6 = 168 registers with a few spills (3 warps per sub-partition) for grids that
+// exceed one wave of the uncapped variant
+template <int LANES, int NL, bool HF, int MINB = 1>
+__global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArgs T) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
@@ -241,6 +244,7 @@ __global__ void k_fill_i64(long long* dst, long long v, int n) {
 // ------------------------------------------------------------------------------------------------
 struct b2g_sim {
     int device = 0;
+    int n_sm = 148;
     b2g_sim_params params{};
     b2g_model model{};
     b2g_dof_props props{};
@@ -446,7 +450,11 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         CUDA_TRY(cudaGetLastError());
         return B2G_OK;
     }
-    if (s->v.lanes == 4) { if (s->has_hf) k_anymal_step<4, 3, true><<<grid, kBlock, sm, st>>>(A, T); else k_anymal_step<4, 3, false><<<grid, kBlock, sm, st>>>(A, T); }
+    if (s->v.lanes == 4) {
+        if (s->has_hf) k_anymal_step<4, 3, true><<<grid, kBlock, sm, st>>>(A, T);
+        else if (grid > 4 * s->n_sm) k_anymal_step<4, 3, false, 6><<<grid, kBlock, sm, st>>>(A, T);     // more than one wave: occupancy build
+        else k_anymal_step<4, 3, false><<<grid, kBlock, sm, st>>>(A, T);
+    }
     else { if (s->has_hf) k_anymal_step<8, 6, true><<<grid, kBlock, sm, st>>>(A, T); else k_anymal_step<8, 6, false><<<grid, kBlock, sm, st>>>(A, T); }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -487,6 +495,7 @@ int b2g_sim_create(int device_id, const b2g_sim_params* params, b2g_sim** out) {
     if (device_id < 0 || device_id >= count) return fail(B2G_ERR_ARG, "device %d out of range (%d devices)", device_id, count);
     b2g_sim* s = new b2g_sim();
     s->device = device_id;
+    cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     s->params = *params;
     if (s->params.substeps <= 0) s->params.substeps = 1;
     *out = s;
@@ -604,6 +613,7 @@ int b2g_sim_prepare(b2g_sim* s) {
         cudaFuncSetAttribute(k_simulate<8, 6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_simulate<8, 6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_anymal_step<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_anymal_step<4, 3, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_anymal_step<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_anymal_step<8, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_anymal_step<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);

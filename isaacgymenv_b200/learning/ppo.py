@@ -80,6 +80,8 @@ class PPOConfig:
     bounds_loss_coef: float = 0.001
     units: tuple = (256, 128, 64)
     max_epochs: int = 1000
+    tf32: bool = False          # TF32 tensor-core matmuls in the update (the reference trains with mixed_precision: True)
+    fused_adam: bool = False    # single-kernel Adam (torch fused implementation)
 
 
 @dataclass
@@ -113,8 +115,11 @@ class PPO:
         self.val_rms = RunningMeanStd(()).to(self.device)
         self.lr_t = torch.tensor(cfg.learning_rate, device=self.device, dtype=torch.float32)
         graph_update = self.cuda_graphs and not multi_gpu
+        if cfg.tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
         self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t if graph_update else cfg.learning_rate, eps=1e-8,
-                                    capturable=graph_update)
+                                    capturable=graph_update, fused=True if cfg.fused_adam else None)
         self.lr = cfg.learning_rate
         if multi_gpu:
             import torch.distributed as dist

@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=300)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--out", default="")
+    ap.add_argument("--tf32", action="store_true", help="TF32 matmuls in the update")
+    ap.add_argument("--fused-adam", action="store_true")
     ap.add_argument("--cuda-graphs", action="store_true", help="capture the rollout and the minibatch update as CUDA graphs")
     ap.add_argument("--fused-rollout", action="store_true", help="evaluate the policy in the rollout with the fused tcgen05 kernel")
     args = ap.parse_args()
@@ -39,6 +41,7 @@ def main():
         cfg = PPOConfig(units=(512, 256, 128), minibatch_size=16384, entropy_coef=0.001)
     if args.task == "Cartpole":
         cfg = PPOConfig(units=(32, 32), horizon_length=16, minibatch_size=8192, mini_epochs=8)
+    cfg.tf32, cfg.fused_adam = args.tf32, args.fused_adam
     ppo = PPO(env, cfg, multi_gpu=multi, seed=args.seed + info.rank, fused_rollout=args.fused_rollout, cuda_graphs=args.cuda_graphs)
     log = ppo.train(max_epochs=args.epochs, log_every=10, verbose=info.rank == 0)
     if multi:
