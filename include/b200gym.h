@@ -141,6 +141,8 @@ enum b2g_tensor_kind {
     B2G_T_JACOBIAN = 7,         /* floating base (N,nb,6,6+nd), fixed base (N,nb-1,6,nd) f32; rows lin3, ang3 */
     B2G_T_MASS_MATRIX = 8,      /* (N,nd,nd) f32 (joint block, Isaac Gym convention)         */
     B2G_T_FRICTION = 9,         /* (N) f32 per-env shape friction coefficient                */
+    B2G_T_ENV_SCALE = 10,       /* (N,4) f32 per-env scale of [link masses+inertias, drive stiffness, drive damping, spare]:
+                                   tensorised domain randomisation (vec_task.py:610-840); ones until acquired */
     B2G_T_COUNT
 };
 

@@ -21,6 +21,13 @@
 namespace b2g {
 
 constexpr int MAXC = B2G_MAX_CONTACTS_PER_CHAIN;
+// per-link loops of the recursions: fully unrolled (link state in registers).  -DB2G_ROLL_LINKS keeps them rolled (link state
+// in local memory, ~1/3 of the code) -- an experiment switch, see DESIGN.md "code size"
+#ifdef B2G_ROLL_LINKS
+#define B2G_LINK_UNROLL _Pragma("unroll 1")
+#else
+#define B2G_LINK_UNROLL _Pragma("unroll")
+#endif
 
 // per-thread scratch for the (dynamically indexed) contact slots
 enum ContactField {
@@ -140,6 +147,22 @@ struct LaneState {
     float frc[NL];          // DOF force output
 };
 
+// per-environment physical randomisation (tensorised domain randomisation, reference vec_task.py:610-840 /
+// cfg/task/Anymal.yaml:104-170): shape friction, and scale factors on every link mass (+ inertia), drive stiffness and damping
+struct EnvDr {
+    float mu = 1.0f, mass = 1.0f, kp = 1.0f, kd = 1.0f;
+};
+B2G_HD B2G_INL EnvDr load_env_dr(const float* friction, const float* env_scale, int env) {
+    EnvDr d;
+    if (friction) d.mu = friction[env];
+    if (env_scale) {
+        d.mass = env_scale[(size_t)env * 4 + 0];
+        d.kp = env_scale[(size_t)env * 4 + 1];
+        d.kd = env_scale[(size_t)env * 4 + 2];
+    }
+    return d;
+}
+
 // per-thread contact scratch: field f of slot s
 struct ScratchStrided {
     float* base;   // points at this thread's column
@@ -175,7 +198,7 @@ B2G_HD B2G_INL void ground_sample(const DevParams& P, float x, float y, float& h
 // root's spatial acceleration (angular, linear) in st.rw / st.rv.
 template <int LANES, int NL, bool FIXED, bool HF, bool PROBE = false, bool FULL = false>
 B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, int lane, int len_in, int d0,
-                            LaneState<NL>& st, float mu_shape, bool last, ScratchStrided sc, float* bf) {
+                            LaneState<NL>& st, const EnvDr dr, bool last, ScratchStrided sc, float* bf) {
     // FULL: every lane's chain has exactly NL links (the quadrupeds) -> the `j < len` predicates fold away
     const int len = FULL ? NL : len_in;
     const float h = P.h;
@@ -192,7 +215,7 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
         M3 Rp = R0;
         V3 pp = V3{0, 0, 0};
         SV vp = v0;
-#pragma unroll
+B2G_LINK_UNROLL
         for (int j = 0; j < NL; j++) {
             if (j < len) {
                 const DevDof& D = M->dof[d0 + j];
@@ -216,7 +239,7 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
                 vl[j] = vp + vj;
                 cb[j] = crm(vl[j], vj);
                 // drive
-                const float kp = D.kp, kd = D.kd;
+                const float kp = D.kp * dr.kp, kd = D.kd * dr.kd;
                 float t = 0.0f, de = D.armature;
                 if (PROBE) {
                     t = st.act[j];
@@ -260,13 +283,14 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
         IAc.A = S3{0, 0, 0, 0, 0, 0}; IAc.C = S3{0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 9; k++) IAc.B.m[k] = 0;
-#pragma unroll
+B2G_LINK_UNROLL
         for (int j = NL - 1; j >= 0; j--) {
             if (j < len) {
                 const DevDof& D = M->dof[d0 + j];
                 const V3 cw = pl[j] + mul(Rl[j], V3{D.com[0], D.com[1], D.com[2]});
-                const S3 iw = rotate_sym(Rl[j], S3{D.inertia[0], D.inertia[1], D.inertia[2], D.inertia[3], D.inertia[4], D.inertia[5]});
-                SI I = rigid_inertia(D.mass, cw, iw);
+                const S3 iw = rotate_sym(Rl[j], S3{D.inertia[0] * dr.mass, D.inertia[1] * dr.mass, D.inertia[2] * dr.mass, D.inertia[3] * dr.mass,
+                                                   D.inertia[4] * dr.mass, D.inertia[5] * dr.mass});
+                SI I = rigid_inertia(D.mass * dr.mass, cw, iw);
                 SV pA = crf(vl[j], mul(I, vl[j]));
                 if (j + 1 < len) { I += IAc; pA += pAc; }
                 U[j] = mul(I, S[j]);
@@ -288,8 +312,9 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
         SI IA0 = grp_sum<LANES>(IAc);
         SV pA0 = grp_sum<LANES>(pAc);
         const V3 cw = mul(R0, V3{M->root_com[0], M->root_com[1], M->root_com[2]});
-        const S3 iw = rotate_sym(R0, S3{M->root_inertia[0], M->root_inertia[1], M->root_inertia[2], M->root_inertia[3], M->root_inertia[4], M->root_inertia[5]});
-        SI I0 = rigid_inertia(M->root_mass, cw, iw);
+        const S3 iw = rotate_sym(R0, S3{M->root_inertia[0] * dr.mass, M->root_inertia[1] * dr.mass, M->root_inertia[2] * dr.mass,
+                                        M->root_inertia[3] * dr.mass, M->root_inertia[4] * dr.mass, M->root_inertia[5] * dr.mass});
+        SI I0 = rigid_inertia(M->root_mass * dr.mass, cw, iw);
         pA0 += crf(v0, mul(I0, v0));
         IA0 += I0;
         bool ok;
@@ -305,7 +330,7 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
     SV v0n = sv0();
     {
         SV a = FIXED ? SV{V3{0, 0, 0}, -grav} : a0;
-#pragma unroll
+B2G_LINK_UNROLL
         for (int j = 0; j < NL; j++) {
             if (j < len) {
                 const SV ap = a + cb[j];
@@ -381,7 +406,7 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
         return zc - ext < P.contact_offset;
     };
     if (ground) {
-#pragma unroll
+B2G_LINK_UNROLL
         for (int j = NL - 1; j >= 0; j--) {
             if (j < len) {
                 const DevDof& D = M->dof[d0 + j];
@@ -439,7 +464,7 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
 #pragma unroll
     for (int j = 0; j < NL; j++) qdpos[j] = qdn[j];
     const int nit = P.npos + P.nvel;
-    const float mu = 0.5f * (P.mu_ground + mu_shape);   // PhysX default combine mode: average
+    const float mu = 0.5f * (P.mu_ground + dr.mu);   // PhysX default combine mode: average
     const float inv_h = 1.0f / h;
 
     for (int it = 0; it < nit; it++) {

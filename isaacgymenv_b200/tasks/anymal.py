@@ -56,8 +56,6 @@ class Anymal(VecTask):
                            "torque": learn["torqueRewardScale"]}
         self.randomization_params = cfg["task"]["randomization_params"]
         self.randomize = cfg["task"]["randomize"]
-        if self.randomize:
-            raise NotImplementedError("task.randomize=True (domain randomisation) is outside the B200 hot path")
         rng = cfg["env"]["randomCommandVelocityRanges"]
         self.command_x_range, self.command_y_range, self.command_yaw_range = rng["linear_x"], rng["linear_y"], rng["yaw"]
         plane = cfg["env"]["plane"]
@@ -109,6 +107,9 @@ class Anymal(VecTask):
         self.commands_y = self.commands.view(self.num_envs, 3)[..., 1]
         self.commands_yaw = self.commands.view(self.num_envs, 3)[..., 2]
         self.extras = {}
+        # reference :154-156: randomise once before the first sim step
+        if self.randomize:
+            self.apply_randomizations(self.randomization_params)
         self.reset_idx(torch.arange(self.num_envs, device=self.device))
 
     # ------------------------------------------------------------------ sim construction
@@ -234,14 +235,29 @@ class Anymal(VecTask):
         if not self.fused:
             return super().step(actions)
         a = actions.to(self.device, torch.float32)
+        if self.randomize:      # vec_task.py:370-372 action noise; the envs flagged now are the ones the kernel resets this step
+            if self.dr_randomizations.get("actions", None):
+                a = self.dr_randomizations["actions"]["noise_lambda"](a)
+            resetting = self.reset_buf != 0
         if not a.is_contiguous():
             a = a.contiguous()
         # keep a reference until the stream has consumed it
         self._last_actions_in = a
         _lib.check(self._lib.b2g_task_anymal_step(self.sim.handle, C.c_void_p(a.data_ptr()), self.sim.stream()), "step")
         self.control_steps += 1
+        self.sim.frame_count += 1
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
-        self.obs_dict["obs"] = self.obs_clamped.to(self.rl_device)
+        if self.randomize:
+            # the reference re-randomises inside reset_idx (:280-281), i.e. for the environments reset in this step
+            if self._dr.count_steps:
+                self.randomize_buf += 1
+            self.apply_randomizations(self.randomization_params, reset_mask=resetting)
+            obs = self.obs_buf
+            if self.dr_randomizations.get("observations", None):      # vec_task.py:396-398, then the clamp of :402
+                obs = self.dr_randomizations["observations"]["noise_lambda"](obs)
+            self.obs_dict["obs"] = torch.clamp(obs, -self.clip_obs, self.clip_obs).to(self.rl_device)
+        else:
+            self.obs_dict["obs"] = self.obs_clamped.to(self.rl_device)
         return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
 
     def reset(self):
@@ -302,6 +318,8 @@ class Anymal(VecTask):
                 raise NotImplementedError("fused task: partial resets happen inside step(); use fusedStep=false for manual resets")
             _lib.check(self._lib.b2g_task_anymal_reset_all(self.sim.handle, self.sim.stream()), "reset_all")
             return
+        if self.randomize:      # reference :280-281
+            self.apply_randomizations(self.randomization_params)
         positions_offset = torch_rand_float(0.5, 1.5, (len(env_ids), self.num_dof), device=self.device)
         velocities = torch_rand_float(-0.1, 0.1, (len(env_ids), self.num_dof), device=self.device)
         self.dof_pos[env_ids] = self.default_dof_pos[env_ids] * positions_offset

@@ -6,7 +6,7 @@ What a learner (rl_games' ``RLGPUEnv``, ``utils/rlgames_utils.py:242-295``) reli
 ``step(actions) -> (obs_dict, rew, reset, extras)``, ``reset()``, ``reset_done()``, ``obs_buf / rew_buf /
 reset_buf / progress_buf / timeout_buf``, ``extras["time_outs"]``, the ``*_space`` properties and the
 constructor signature.  Rendering, the viewer and domain randomisation are outside the hot path and
-are not provided (``headless=True`` only; ``task.randomize`` must be False -- SURVEY.md 8(f)).
+are not provided (``headless=True`` only).  ``task.randomize`` is served by the tensorised ``utils/domain_rand.py``.
 """
 from __future__ import annotations
 
@@ -193,6 +193,8 @@ class VecTask(Env):
             self.gym.fetch_results(self.sim, True)
         self.post_physics_step()
         self.control_steps += 1
+        if getattr(self, "_dr", None) is not None and self._dr.count_steps:
+            self.randomize_buf += 1
         self.timeout_buf = (self.progress_buf >= self.max_episode_length - 1) & (self.reset_buf != 0)
         if self.dr_randomizations.get("observations", None):
             self.obs_buf = self.dr_randomizations["observations"]["noise_lambda"](self.obs_buf)
@@ -249,5 +251,12 @@ class VecTask(Env):
     # kept under the reference's (name-mangled) private name too
     _VecTask__parse_sim_params = _parse_sim_params
 
-    def apply_randomizations(self, dr_params):
-        raise NotImplementedError("domain randomisation is outside the B200 hot path (task.randomize must be False)")
+    def apply_randomizations(self, dr_params, reset_mask=None):
+        """Reference :610-840, tensorised (``utils/domain_rand.py``): per-environment mass / drive-gain / friction tensors
+        read by the step kernels, gravity, observation and action noise.  No per-environment Python loop, no host sync."""
+        if getattr(self, "_dr", None) is None:
+            from ...utils.domain_rand import DomainRandomizer
+
+            self._dr = DomainRandomizer(self, count_steps=bool(dr_params.get("count_steps", False)))
+        self._dr.apply(dr_params, reset_mask)
+        self.first_randomization = False

@@ -42,13 +42,25 @@ class EmuBackend:
     def get_state(self):
         return self.root.copy(), self.dof.copy()
 
+    def set_env_scale(self, scale, friction=None):
+        self._scale = np.ascontiguousarray(scale, np.float32)
+        self._fric = None if friction is None else np.ascontiguousarray(friction, np.float32)
+
     def simulate(self, target, actuation):
-        f, c = self.emu.simulate(self.model, self.params, self.props, self.root, self.dof, target, actuation)
+        self.emu.set_env_scale(getattr(self, "_scale", None))
+        try:
+            f, c = self.emu.simulate(self.model, self.params, self.props, self.root, self.dof, target, actuation, friction=getattr(self, "_fric", None))
+        finally:
+            self.emu.set_env_scale(None)
         self.dof_force[:], self.contact[:] = f, c
         return f, c
 
     def forward_dynamics(self, tau):
-        return self.emu.forward_dynamics(self.model, self.params, self.props, self.root.copy(), self.dof.copy(), tau)
+        self.emu.set_env_scale(getattr(self, "_scale", None))
+        try:
+            return self.emu.forward_dynamics(self.model, self.params, self.props, self.root.copy(), self.dof.copy(), tau)
+        finally:
+            self.emu.set_env_scale(None)
 
     def jacobian_mass_matrix(self):
         return self.emu.jacobian_mass_matrix(self.model, self.props, self.root, self.dof)
@@ -200,6 +212,12 @@ class CudaBackend:
         nd, nb = self.art.num_dofs, self.art.num_bodies
         return (self.t[_abi.T_DOF_FORCE].cpu().numpy().reshape(self.n, nd).copy(),
                 self.t[_abi.T_NET_CONTACT].cpu().numpy().reshape(self.n, nb, 3).copy())
+
+    def set_env_scale(self, scale, friction=None):
+        """(N,4) per-env [mass, stiffness, damping, spare] scales (+ optional (N) shape friction)."""
+        self._put(self._tensor(_abi.T_ENV_SCALE), np.asarray(scale, np.float32))
+        if friction is not None:
+            self._put(self._tensor(_abi.T_FRICTION), np.asarray(friction, np.float32))
 
     def forward_dynamics(self, tau):
         torch = self.torch

@@ -67,7 +67,7 @@ void probe_env(const SimArgs& A, int env, float* qdd, float* a0) {
         load_state<NL>(A, env, len, d0, st);
         for (int j = 0; j < NL; j++) if (j < len) st.act[j] = A.actuation[(size_t)env * M->n_dof + d0 + j];
         ScratchStrided sc{scratch.data() + lane, LANES};
-        substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, 1.0f, false, sc, bf.data());
+        substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, load_env_dr(nullptr, A.env_scale, env), false, sc, bf.data());
         for (int j = 0; j < NL; j++) if (j < len) qdd[(size_t)env * M->n_dof + d0 + j] = st.frc[j];
         if (lane == 0) {
             float* o = a0 + (size_t)env * 6;
@@ -88,7 +88,12 @@ void anymal_env(const SimArgs& A, const TaskArgs& T, int env, int mode) {
 
 }  // namespace
 
+// per-env domain-randomisation scales (N,4) used by the next emu_simulate / emu_forward_dynamics calls; null = ones
+static const float* g_env_scale = nullptr;
+
 extern "C" {
+
+void emu_set_env_scale(const float* p) { g_env_scale = p; }
 
 int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, const b2g_heightfield* hf,
                  const int16_t* hfs, const float* friction, int n_envs, float* root, float* dof, const float* target,
@@ -100,7 +105,7 @@ int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     A.M = dm;
     pack_dev_params(*sp, hf, hfs, A.P);
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = target; A.actuation = actuation;
-    A.dof_force = dof_force; A.contact = contact; A.friction = friction;
+    A.dof_force = dof_force; A.contact = contact; A.friction = friction; A.env_scale = g_env_scale;
     const Variant v = pick(*m);
     const bool HFm = hf && hfs;
     for (int e = 0; e < n_envs; e++) {
@@ -121,7 +126,7 @@ int emu_forward_dynamics(const b2g_model* m, const b2g_sim_params* sp, const b2g
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, nullptr, nullptr, A.P);
-    A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = tau; A.actuation = tau; A.dof_force = nullptr; A.contact = nullptr; A.friction = nullptr;
+    A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = tau; A.actuation = tau; A.dof_force = nullptr; A.contact = nullptr; A.friction = nullptr; A.env_scale = g_env_scale;
     const Variant v = pick(*m);
     for (int e = 0; e < n_envs; e++) {
         if (v.lanes == 1) probe_env<1, 2, true>(A, e, qdd, a0);

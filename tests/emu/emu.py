@@ -36,6 +36,17 @@ def _p(a, ct=C.c_float):
     return None if a is None else a.ctypes.data_as(C.POINTER(ct))
 
 
+_env_scale_keep = None
+
+
+def set_env_scale(scale):
+    """(N,4) per-env [mass, stiffness, damping, spare] scales for the following simulate / forward_dynamics calls; None = ones."""
+    global _env_scale_keep
+    _env_scale_keep = None if scale is None else np.ascontiguousarray(scale, dtype=np.float32)
+    lib().emu_set_env_scale.restype = None
+    lib().emu_set_env_scale(_p(_env_scale_keep))
+
+
 def simulate(model, params, props, root, dof, target, actuation, heightfield=None, hf_samples=None, friction=None):
     n = root.shape[0]
     assert root.dtype == np.float32 and dof.dtype == np.float32

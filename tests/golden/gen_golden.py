@@ -97,7 +97,7 @@ def gen_utils(out):
     print(out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--dr-only" not in sys.argv:
     torch.set_num_threads(1)
     gen_anymal(ref_loader.load("tasks.anymal"), "anymal", 13, [2, 5, 8, 11], 0, os.path.join(HERE, "anymal_flat.npz"))
     gen_anymal(ref_loader.load("tasks.hound"), "hound", 17, [2, 6, 10, 14], 0, os.path.join(HERE, "hound_flat.npz"))
@@ -399,5 +399,40 @@ def gen_useful_hound(out):
     print(out, "resets", int(b.reset_buf.sum()), "rew range", float(b.rew_buf.min()), float(b.rew_buf.max()), "osc |u| max", float(u.abs().max()))
 
 
-if __name__ == "__main__" and ("--useful" in sys.argv or globals().get("_run_terrain_after")):
+if __name__ == "__main__" and "--dr-only" not in sys.argv and ("--useful" in sys.argv or globals().get("_run_terrain_after")):
     gen_useful_hound(os.path.join(HERE, "useful_hound_plane.npz"))
+
+
+# ------------------------------------------------------------------------------------------------
+# domain-randomisation samplers (utils/dr_utils.py): bucketing is deterministic -> golden values; the samplers are random ->
+# their first two moments and range over 200k numpy draws, per parameter block and gym step count
+# ------------------------------------------------------------------------------------------------
+def gen_dr(out):
+    dr = ref_loader.load("utils.dr_utils")
+    blocks = {
+        "mass": {"range": [0.5, 1.5], "operation": "scaling", "distribution": "uniform", "schedule": "linear", "schedule_steps": 3000},
+        "friction": {"range": [0.7, 1.3], "operation": "scaling", "distribution": "uniform", "schedule": "linear", "schedule_steps": 3000, "num_buckets": 500},
+        "gravity": {"range": [0, 0.4], "operation": "additive", "distribution": "gaussian", "schedule": "linear", "schedule_steps": 3000},
+        "gauss_scaling": {"range": [1.2, 0.3], "operation": "scaling", "distribution": "gaussian", "schedule": "constant", "schedule_steps": 1000},
+        "loguniform": {"range": [0.3, 3.0], "operation": "scaling", "distribution": "loguniform"},
+        "gauss_buckets": {"range": [1.0, 0.04], "operation": "scaling", "distribution": "gaussian", "num_buckets": 250},
+    }
+    res = {}
+    np.random.seed(12345)
+    for name, p in blocks.items():
+        for step in (0, 500, 1500, 3000, 10000):
+            s = dr.generate_random_samples(dict(p), 200000, step)
+            res[f"stat_{name}_{step}"] = np.array([s.mean(), s.std(), s.min(), s.max()])
+    v = np.linspace(0.55, 1.45, 181)
+    for name in ("friction", "gauss_buckets"):
+        res[f"bucket_in_{name}"] = v
+        res[f"bucket_out_{name}"] = np.array([dr.get_bucketed_val(x, blocks[name]) for x in v])
+    import json
+
+    res["blocks_json"] = np.array(json.dumps(blocks))
+    np.savez_compressed(out, **res)
+    print(out, len(res), "arrays")
+
+
+if __name__ == "__main__" and ("--dr" in sys.argv or "--dr-only" in sys.argv):
+    gen_dr(os.path.join(HERE, "dr_utils.npz"))

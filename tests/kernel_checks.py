@@ -101,6 +101,78 @@ def check_forward_dynamics(make_backend, robot="anymal", n=16, seed=0):
     return float(err_q.max())
 
 
+def scaled_model_props(m, props, mass, kp, kd):
+    """Copies of the packed model / DOF properties with every link mass + inertia scaled by ``mass`` and the drive gains by
+    ``kp`` / ``kd``: what one environment of a domain-randomised sim simulates."""
+    m2 = _abi.Model.from_buffer_copy(m)
+    p2 = _abi.DofProps.from_buffer_copy(props)
+    for i in range(_abi.MAX_LINKS):
+        m2.link_mass[i] = m.link_mass[i] * mass
+        for k in range(6):
+            m2.link_inertia[i][k] = m.link_inertia[i][k] * mass
+    for i in range(_abi.MAX_DOF):
+        p2.stiffness[i] = props.stiffness[i] * kp
+        p2.damping[i] = props.damping[i] * kd
+    return m2, p2
+
+
+def check_env_scale(make_backend, robot="anymal", n=8, steps=10, seed=17):
+    """Tensorised domain randomisation (B2G_T_ENV_SCALE + B2G_T_FRICTION): every environment simulates its own mass / drive
+    gain / friction scales; each one is checked against the float64 oracle run on the correspondingly scaled model."""
+    art = load_robot(robot)
+    rng = np.random.default_rng(seed)
+    nd = art.num_dofs
+    sp = flat_params()
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 85.0, 2.0)
+    scale = np.ones((n, 4), np.float32)
+    scale[:, 0] = rng.uniform(0.5, 1.5, n)
+    scale[:, 1] = rng.uniform(0.5, 1.5, n)
+    scale[:, 2] = rng.uniform(0.5, 1.5, n)
+    scale[0, :3] = 1.0
+    fric = rng.uniform(0.4, 1.3, n).astype(np.float32)
+    root, dof = standing_state(art, n, rng, 0.55 if "anymal" in robot else 0.5)
+    m = _abi.pack_model(art)
+    # contact-free accelerations first (mass scale only matters)
+    be = make_backend(art, flat_params(ground=False), _abi.default_dof_props(art), n)
+    try:
+        fr, fd = random_flying_state(art, n, rng)
+        tau = (rng.normal(size=(n, nd)) * 20).astype(np.float32)
+        be.set_state(fr, fd)
+        be.set_env_scale(scale)
+        qdd, _ = be.forward_dynamics(tau)
+    finally:
+        be.close()
+    for e in range(n):
+        m2, _ = scaled_model_props(m, props, float(scale[e, 0]), 1.0, 1.0)
+        qo, _ = O.forward_dynamics(m2, flat_params(ground=False), fr[e:e + 1].astype(np.float64), fd[e:e + 1].astype(np.float64), tau[e:e + 1].astype(np.float64))
+        err = np.abs(qdd[e] - qo[0]).max() / np.abs(qo[0]).max()
+        assert err < 1e-3, f"env {e}: joint acceleration relative error {err:.2e} with mass scale {scale[e, 0]:.2f}"
+    assert np.abs(qdd[1] - qdd[0]).max() > 1e-3 or abs(scale[1, 0] - 1) < 1e-3
+    # then a contact horizon with every scale + friction active
+    be = make_backend(art, sp, props, n)
+    r64, d64 = root.astype(np.float64), dof.astype(np.float64)
+    q0 = default_pose(art)
+    worst = 0.0
+    try:
+        be.set_state(root, dof)
+        be.set_env_scale(scale, fric)
+        for _ in range(steps):
+            tgt = q0 + 0.5 * rng.uniform(-1, 1, (n, nd))
+            act = np.zeros((n, nd))
+            be.simulate(tgt, act)
+            for e in range(n):
+                m2, p2 = scaled_model_props(m, props, *[float(x) for x in scale[e, :3]])
+                re, de = r64[e:e + 1].copy(), d64[e:e + 1].copy()
+                O.simulate(m2, sp, p2, re, de, tgt[e:e + 1].astype(np.float64), act[e:e + 1].astype(np.float64), friction=fric[e:e + 1].astype(np.float64))
+                r64[e], d64[e] = re[0], de[0]
+            rb, db = be.get_state()
+            worst = max(worst, float(np.abs(rb - r64).max()), float(np.abs(db[:, :, 0] - d64[:, :, 0]).max()))
+    finally:
+        be.close()
+    assert worst < 1e-2, f"state deviation {worst:.2e} over {steps} steps with per-env scales"
+    return worst
+
+
 def check_simulate_horizon(make_backend, robot="anymal", n=16, steps=10, seed=1, drive="pos", tol=1e-2):
     """gym.simulate with ground contact for `steps` steps vs the float64 oracle: states within 1e-2."""
     art = load_robot(robot)
