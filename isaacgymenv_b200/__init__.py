@@ -37,6 +37,12 @@ def task_map():
         m["UsefulHound"] = UsefulHound
     except ImportError:
         pass
+    try:
+        from .tasks.hound_arm import Houndarm
+
+        m["Houndarm"] = Houndarm
+    except ImportError:
+        pass
     return m
 
 

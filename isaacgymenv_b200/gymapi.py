@@ -247,6 +247,10 @@ class Sim:
                            joint_limit_stiffness=float(getattr(px, "joint_limit_stiffness", 2000.0)),
                            joint_limit_damping=float(getattr(px, "joint_limit_damping", 20.0)))
         c.gravity[0], c.gravity[1], c.gravity[2] = g.x, g.y, g.z
+        asset = getattr(self, "asset", None)
+        if asset is not None and getattr(asset.options, "disable_gravity", False):
+            # AssetOptions.disable_gravity (tasks/hound_arm.py:212): the sim holds one articulation type, so its bodies are all of them
+            c.gravity[0] = c.gravity[1] = c.gravity[2] = 0.0
         return c
 
     def stream(self):
@@ -301,6 +305,8 @@ class Gym:
         """vec_task.py:262."""
         if sim.asset is None:
             raise _lib.B2GError("prepare_sim called before any actor was created")
+        if sim.prepared:        # idempotent: tasks that acquire tensors inside _create_envs (tasks/hound_arm.py:288) prepare early
+            return True
         lib = _lib.load()
         art = sim.asset.art
         sim.model_struct = _abi.pack_model(art)
@@ -310,6 +316,9 @@ class Gym:
         n = len(sim.envs)
         _lib.check(lib.b2g_sim_add_articulation(sim.handle, C.byref(sim.model_struct), C.byref(props), n, pose7,
                                                 float(sim.env_spacing), int(sim.num_per_row)), "create_actor")
+        if getattr(sim.asset.options, "disable_gravity", False):
+            cp = sim.c_params()
+            _lib.check(lib.b2g_sim_set_params(sim.handle, C.byref(cp)), "set_sim_params")
         _lib.check(lib.b2g_sim_prepare(sim.handle), "prepare_sim")
         sim.prepared = True
         import torch

@@ -1,0 +1,211 @@
+"""Houndarm: fixed-base 6-DOF arm reach task, drop-in for the reference's ``tasks/hound_arm.py`` (``Houndarm`` :74-545):
+6 actions = end-effector pose deltas scaled by ``cmd_limit`` and turned into joint torques by the operational-space law
+(:462-493) -- or 6 raw joint torques with ``controlType: joint_tor`` --, 10 observations [eef position, eef quaternion,
+commanded position] (:383-392), reward ``compute_houndarm_reward`` (:550-567), reset draws (:394-459), 150-step episodes.
+
+This is SURVEY 8(f) row 4: it runs on the generic gym-tensor path of the shim (``k_simulate`` + ``k_body_state`` +
+``k_jacobian`` + ``k_mass_matrix``; OSC and reward as torch ops), i.e. exactly the reference's hook structure on
+``libb200gym``.  Replicated as they are: the Jacobian row is taken at the JOINT index (``get_actor_joint_dict()['joint6']``
+= 5, i.e. body ``link6`` of the fixed-base Jacobian, not ``end_link``; :314-318), ``reset_buf[env_ids] = 0`` on reset
+(quirk Q5), the no-op ``u_null[:, 6:] *= 0``.  ``asset_options.disable_gravity`` is honoured by the sim."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import gymapi, gymtorch
+from ..utils.torch_math import tensor_clamp, to_torch, torch_rand_float
+from .anymal import default_asset_root
+from .base.vec_task import VecTask
+
+
+def compute_houndarm_reward(reset_buf, progress_buf, eef_pos, eef_vel, commands, dist_scale: float, vel_scale: float, max_episode_length: float):
+    """Reference :550-567.  Distance term 1 - tanh(10 d); a velocity term that only counts within 2 cm of the target."""
+    d = torch.norm(eef_pos - commands, dim=-1)
+    in_reach = d < 0.02
+    rewards = (1.0 - torch.tanh(10.0 * d)) * dist_scale + (1.0 - torch.tanh(10.0 * torch.norm(eef_vel, dim=-1))) * in_reach * vel_scale
+    rewards = torch.clip(rewards, 0.0, None)
+    reset = torch.where(progress_buf >= max_episode_length - 1, torch.ones_like(reset_buf), reset_buf)
+    return rewards, reset
+
+
+def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp, kd, kp_null, kd_null, default_q, effort_limits):
+    """Reference :462-493: Khatib's operational-space law with a null-space posture term, clamped to the effort limits."""
+    mm_inv = torch.inverse(mm)
+    j_t = j_eef.transpose(1, 2)
+    m_eef = torch.inverse(j_eef @ mm_inv @ j_t)
+    u = j_t @ m_eef @ (kp * dpose - kd * eef_vel).unsqueeze(-1)
+    j_eef_inv = m_eef @ j_eef @ mm_inv
+    u_null = kd_null * -qd + kp_null * ((default_q - q + np.pi) % (2 * np.pi) - np.pi)
+    u_null = mm @ u_null.unsqueeze(-1)
+    u = u + (torch.eye(6, device=mm.device).unsqueeze(0) - j_t @ j_eef_inv) @ u_null
+    return tensor_clamp(u.squeeze(-1), -effort_limits.unsqueeze(0), effort_limits.unsqueeze(0))
+
+
+class Houndarm(VecTask):
+    def __init__(self, cfg, rl_device, sim_device, graphics_device_id, headless, virtual_screen_capture=False, force_render=False):
+        self.cfg = cfg
+        env = cfg["env"]
+        self.max_episode_length = env["episodeLength"]
+        self.action_scale = env["actionScale"]
+        self.houndarm_dof_noise = env["houndarmDofNoise"]
+        rng = env["randomCommandPositionRanges"]
+        self.command_x_range, self.command_y_range, self.command_z_range = rng["x"], rng["y"], rng["z"]
+        self.reward_settings = {"r_dist_scale": env["distRewardScale"], "r_lift_scale": env["liftRewardScale"], "r_align_scale": env["alignRewardScale"],
+                                "r_stack_scale": env["stackRewardScale"], "r_vel_scale": env["velRewardScale"]}
+        self.control_type = env["controlType"]
+        if self.control_type not in ("osc", "joint_tor"):
+            raise ValueError("Invalid control type specified. Must be one of: {osc, joint_tor}")
+        cfg["env"]["numObservations"] = 10 if self.control_type == "osc" else 26
+        cfg["env"]["numActions"] = 6 if self.control_type == "osc" else 8
+        if self.control_type != "osc":
+            # the reference's joint_tor variant declares 26 observations / 8 actions but builds 10 / uses 6 (:383-392, :499-501)
+            raise NotImplementedError("controlType joint_tor is inconsistent in the reference (26 obs declared, 10 built); only osc is served")
+        if cfg.get("task", {}).get("randomize", False):
+            raise NotImplementedError("Houndarm: task.randomize is not wired (the reference task never calls apply_randomizations)")
+        self.states, self.handles = {}, {}
+        self.up_axis, self.up_axis_idx = "z", 2
+        self.seed = int(cfg.get("seed", 42))
+        super().__init__(config=cfg, rl_device=rl_device, sim_device=sim_device, graphics_device_id=graphics_device_id, headless=headless,
+                         virtual_screen_capture=virtual_screen_capture, force_render=force_render)
+        self.houndarm_default_dof_pos = to_torch([0, 0, 0, 0, 0, 0], device=self.device)
+        self.kp = to_torch([150.0] * 6, device=self.device)
+        self.kd = 2 * torch.sqrt(self.kp)
+        self.kp_null = to_torch([10.0] * 6, device=self.device)
+        self.kd_null = 2 * torch.sqrt(self.kp_null)
+        self.cmd_limit = to_torch([0.1, 0.1, 0.1, 0.5, 0.5, 0.5], device=self.device).unsqueeze(0)
+        self.commands = torch.zeros(self.num_envs, 3, dtype=torch.float, device=self.device)
+        self.commands_x, self.commands_y, self.commands_z = (self.commands.view(self.num_envs, 3)[..., i] for i in range(3))
+        self.actions = torch.zeros(self.num_envs, self.num_actions, device=self.device)
+        self.reset_idx(torch.arange(self.num_envs, device=self.device))
+        self._refresh()
+
+    # ---- scene ----
+    def create_sim(self):
+        self.sim_params.up_axis = gymapi.UP_AXIS_Z
+        self.sim_params.gravity.x, self.sim_params.gravity.y, self.sim_params.gravity.z = 0.0, 0.0, -9.81
+        self.sim = super().create_sim(self.device_id, self.graphics_device_id, self.physics_engine, self.sim_params)
+        plane = gymapi.PlaneParams()
+        plane.normal = gymapi.Vec3(0.0, 0.0, 1.0)
+        self.gym.add_ground(self.sim, plane)
+        self._create_envs(self.num_envs, self.cfg["env"]["envSpacing"], int(np.sqrt(self.num_envs)))
+
+    def _create_envs(self, num_envs, spacing, num_per_row):
+        lower, upper = gymapi.Vec3(-spacing, -spacing, 0.0), gymapi.Vec3(spacing, spacing, spacing)
+        asset_root = self.cfg["env"].get("assetRoot", default_asset_root())
+        asset_file = "urdf/open_manipulator_p_gazebo/urdf/open_manipulator_p.urdf"
+        if "asset" in self.cfg["env"]:
+            asset_file = self.cfg["env"]["asset"].get("assetFileNamehoundarm", asset_file)
+        opt = gymapi.AssetOptions()
+        opt.replace_cylinder_with_capsule = False
+        opt.flip_visual_attachments = False
+        opt.fix_base_link = True
+        opt.collapse_fixed_joints = False
+        opt.disable_gravity = True
+        opt.thickness = 0.001
+        opt.default_dof_drive_mode = gymapi.DOF_MODE_EFFORT
+        opt.use_mesh_materials = True
+        asset = self.gym.load_asset(self.sim, asset_root, asset_file, opt)
+        self.num_houndarm_bodies = self.gym.get_asset_rigid_body_count(asset)
+        self.num_houndarm_dofs = self.gym.get_asset_dof_count(asset)
+        props = self.gym.get_asset_dof_properties(asset)
+        for i in range(self.num_houndarm_dofs):
+            props["driveMode"][i] = gymapi.DOF_MODE_POS if i > 6 else gymapi.DOF_MODE_EFFORT
+            props["stiffness"][i] = 0.0
+            props["damping"][i] = 0.0
+        self.houndarm_dof_lower_limits = to_torch(props["lower"].astype("float32").copy(), device=self.device)
+        self.houndarm_dof_upper_limits = to_torch(props["upper"].astype("float32").copy(), device=self.device)
+        self._houndarm_effort_limits = to_torch(props["effort"].astype("float32").copy(), device=self.device)
+        pose = gymapi.Transform()
+        pose.p = gymapi.Vec3(-0.45, 0.0, 0.0)
+        pose.r = gymapi.Quat(0.0, 0.0, 0.0, 1.0)
+        self.envs, self.houndarms = [], []
+        for i in range(num_envs):
+            env = self.gym.create_env(self.sim, lower, upper, num_per_row)
+            self.houndarms.append(self.gym.create_actor(env, asset, pose, "houndarm", i, 0, 0))
+            self.gym.set_actor_dof_properties(env, self.houndarms[-1], props)
+            self.envs.append(env)
+        self.gym.prepare_sim(self.sim)
+        self.init_data()
+
+    def init_data(self):
+        env, actor = self.envs[0], 0
+        self.handles = {"endpoint_tip": self.gym.find_actor_rigid_body_handle(env, actor, "end_link")}
+        self.num_dofs = self.gym.get_sim_dof_count(self.sim) // self.num_envs
+        n = self.num_envs
+        self._root_state = gymtorch.wrap_tensor(self.gym.acquire_actor_root_state_tensor(self.sim)).view(n, -1, 13)
+        self._dof_state = gymtorch.wrap_tensor(self.gym.acquire_dof_state_tensor(self.sim)).view(n, -1, 2)
+        self._rigid_body_state = gymtorch.wrap_tensor(self.gym.acquire_rigid_body_state_tensor(self.sim)).view(n, -1, 13)
+        self._q, self._qd = self._dof_state[..., 0], self._dof_state[..., 1]
+        self._eef_state = self._rigid_body_state[:, self.handles["endpoint_tip"], :]
+        jacobian = gymtorch.wrap_tensor(self.gym.acquire_jacobian_tensor(self.sim, "houndarm"))
+        hand_joint_index = self.gym.get_actor_joint_dict(env, actor)["joint6"]
+        self._j_eef = jacobian[:, hand_joint_index, :, :6]
+        self._mm = gymtorch.wrap_tensor(self.gym.acquire_mass_matrix_tensor(self.sim, "houndarm"))[:, :6, :6]
+        self._pos_control = torch.zeros((n, self.num_dofs), dtype=torch.float, device=self.device)
+        self._effort_control = torch.zeros_like(self._pos_control)
+        self._arm_control = self._effort_control[:, :6]
+        self._global_indices = torch.arange(n, dtype=torch.int32, device=self.device).view(n, -1)
+
+    # ---- state ----
+    def _update_states(self):
+        self.states.update({"q": self._q[:, :], "q_gripper": self._q[:, -2:], "eef_pos": self._eef_state[:, :3], "eef_quat": self._eef_state[:, 3:7],
+                            "eef_vel": self._eef_state[:, 7:], "commands": self.commands[:, :]})
+
+    def _refresh(self):
+        self.gym.refresh_actor_root_state_tensor(self.sim)
+        self.gym.refresh_dof_state_tensor(self.sim)
+        self.gym.refresh_rigid_body_state_tensor(self.sim)
+        self.gym.refresh_jacobian_tensors(self.sim)
+        self.gym.refresh_mass_matrix_tensors(self.sim)
+        self._update_states()
+
+    def compute_reward(self, actions):
+        rew, reset = compute_houndarm_reward(self.reset_buf, self.progress_buf, self.states["eef_pos"], self.states["eef_vel"], self.states["commands"],
+                                             self.reward_settings["r_dist_scale"], self.reward_settings["r_vel_scale"], self.max_episode_length)
+        self.rew_buf[:], self.reset_buf[:] = rew, reset
+
+    def compute_observations(self):
+        self._refresh()
+        self.obs_buf = torch.cat([self.states[k] for k in ("eef_pos", "eef_quat", "commands")], dim=-1)
+        return self.obs_buf
+
+    def reset_idx(self, env_ids):
+        k = len(env_ids)
+        self.commands_x[env_ids] = torch_rand_float(self.command_x_range[0], self.command_x_range[1], (k, 1), device=self.device).squeeze()
+        self.commands_y[env_ids] = torch_rand_float(self.command_y_range[0], self.command_y_range[1], (k, 1), device=self.device).squeeze()
+        self.commands_z[env_ids] = torch_rand_float(self.command_z_range[0], self.command_z_range[1], (k, 1), device=self.device).squeeze()
+        noise = torch.rand((k, 6), device=self.device)
+        pos = tensor_clamp(self.houndarm_default_dof_pos.unsqueeze(0) + self.houndarm_dof_noise * 2.0 * (noise - 0.5),
+                           self.houndarm_dof_lower_limits.unsqueeze(0), self.houndarm_dof_upper_limits)
+        self._q[env_ids, :] = pos
+        self._qd[env_ids, :] = torch.zeros_like(self._qd[env_ids])
+        self._pos_control[env_ids, :] = pos
+        self._effort_control[env_ids, :] = torch.zeros_like(pos)
+        ids = self._global_indices[env_ids].flatten()
+        self.gym.set_dof_position_target_tensor_indexed(self.sim, gymtorch.unwrap_tensor(self._pos_control), gymtorch.unwrap_tensor(ids), len(ids))
+        self.gym.set_dof_actuation_force_tensor_indexed(self.sim, gymtorch.unwrap_tensor(self._effort_control), gymtorch.unwrap_tensor(ids), len(ids))
+        self.gym.set_dof_state_tensor_indexed(self.sim, gymtorch.unwrap_tensor(self._dof_state), gymtorch.unwrap_tensor(ids), len(ids))
+        self.progress_buf[env_ids] = 0
+        self.reset_buf[env_ids] = 0
+
+    # ---- control ----
+    def _compute_osc_torques(self, dpose):
+        return osc_torques(self._mm, self._j_eef, dpose, self.states["eef_vel"], self._q[:, :6], self._qd[:, :6], self.kp, self.kd, self.kp_null,
+                           self.kd_null, self.houndarm_default_dof_pos[:6], self._houndarm_effort_limits[:6])
+
+    def pre_physics_step(self, actions):
+        self.actions = actions.clone().to(self.device)
+        u_arm = self.actions * self.cmd_limit / self.action_scale
+        if self.control_type == "osc":
+            u_arm = self._compute_osc_torques(dpose=u_arm)
+        self._arm_control[:, :] = u_arm
+        self.gym.set_dof_actuation_force_tensor(self.sim, gymtorch.unwrap_tensor(self._effort_control))
+
+    def post_physics_step(self):
+        self.progress_buf += 1
+        env_ids = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+        if len(env_ids) > 0:
+            self.reset_idx(env_ids)
+        self.compute_observations()
+        self.compute_reward(self.actions)

@@ -97,7 +97,7 @@ def gen_utils(out):
     print(out)
 
 
-if __name__ == "__main__" and "--dr-only" not in sys.argv:
+if __name__ == "__main__" and "--dr-only" not in sys.argv and "--houndarm-only" not in sys.argv:
     torch.set_num_threads(1)
     gen_anymal(ref_loader.load("tasks.anymal"), "anymal", 13, [2, 5, 8, 11], 0, os.path.join(HERE, "anymal_flat.npz"))
     gen_anymal(ref_loader.load("tasks.hound"), "hound", 17, [2, 6, 10, 14], 0, os.path.join(HERE, "hound_flat.npz"))
@@ -399,7 +399,7 @@ def gen_useful_hound(out):
     print(out, "resets", int(b.reset_buf.sum()), "rew range", float(b.rew_buf.min()), float(b.rew_buf.max()), "osc |u| max", float(u.abs().max()))
 
 
-if __name__ == "__main__" and "--dr-only" not in sys.argv and ("--useful" in sys.argv or globals().get("_run_terrain_after")):
+if __name__ == "__main__" and "--dr-only" not in sys.argv and "--houndarm-only" not in sys.argv and ("--useful" in sys.argv or globals().get("_run_terrain_after")):
     gen_useful_hound(os.path.join(HERE, "useful_hound_plane.npz"))
 
 
@@ -436,3 +436,45 @@ def gen_dr(out):
 
 if __name__ == "__main__" and ("--dr" in sys.argv or "--dr-only" in sys.argv):
     gen_dr(os.path.join(HERE, "dr_utils.npz"))
+
+
+# ------------------------------------------------------------------------------------------------
+# Houndarm (tasks/hound_arm.py): the jit reward function and the eager OSC torque law run on an attribute bag
+# ------------------------------------------------------------------------------------------------
+def gen_houndarm(out):
+    mod = ref_loader.load("tasks.hound_arm")
+    n = 96
+    eef_pos = sinfill((n, 3), 0.41, 0.3, 0.3)
+    commands = sinfill((n, 3), 0.57, 0.9, 0.3)
+    commands[:24] = eef_pos[:24] + sinfill((24, 3), 0.93, 0.2, 0.008)        # a quarter of the envs inside the 2 cm reach ball
+    eef_vel = sinfill((n, 6), 0.29, 0.5, 0.4)
+    progress = (torch.arange(n) * 7 % 160).long()
+    reset = (torch.arange(n) % 11 == 0).long()
+    states = {"eef_pos": eef_pos, "eef_vel": eef_vel, "commands": commands}
+    settings = {"r_dist_scale": 0.1, "r_lift_scale": 1.5, "r_align_scale": 2.0, "r_stack_scale": 16.0, "r_vel_scale": 0.1}
+    rew, rst = mod.compute_houndarm_reward(reset, progress, torch.zeros(n, 6), states, settings, 150.0)
+    b = types.SimpleNamespace()
+    mm = sinfill((n, 6, 6), 0.37, 0.3, 0.2)
+    b._mm = mm @ mm.transpose(1, 2) + 0.5 * torch.eye(6)
+    b._j_eef = sinfill((n, 6, 6), 0.61, 0.8, 0.7) + torch.eye(6)
+    b._q = sinfill((n, 6), 0.23, 0.4, 1.2)
+    b._qd = sinfill((n, 6), 0.19, 0.7, 2.0)
+    b.states = {"eef_vel": eef_vel}
+    b.kp = torch.full((6,), 150.0)
+    b.kd = 2 * torch.sqrt(b.kp)
+    b.kp_null = torch.full((6,), 10.0)
+    b.kd_null = 2 * torch.sqrt(b.kp_null)
+    b.houndarm_default_dof_pos = torch.zeros(6)
+    b._houndarm_effort_limits = torch.full((6,), 1000.0)
+    b.device = "cpu"
+    dpose = sinfill((n, 6), 0.83, 0.4) * torch.tensor([[0.1, 0.1, 0.1, 0.5, 0.5, 0.5]])
+    u = mod.Houndarm._compute_osc_torques(b, dpose)
+    np.savez_compressed(out, eef_pos=eef_pos.numpy(), commands=commands.numpy(), eef_vel=eef_vel.numpy(), progress=progress.numpy(), reset=reset.numpy(),
+                        rew=rew.numpy(), reset_out=rst.numpy(), mm=b._mm.numpy(), j_eef=b._j_eef.numpy(), q=b._q.numpy(), qd=b._qd.numpy(),
+                        dpose=dpose.numpy(), u=u.numpy())
+    print(out, "rew range", float(rew.min()), float(rew.max()), "in reach", int((torch.norm(eef_pos - commands, dim=-1) < 0.02).sum()),
+          "resets", int(rst.sum()), "|u| max", float(u.abs().max()))
+
+
+if __name__ == "__main__" and "--houndarm-only" in sys.argv:
+    gen_houndarm(os.path.join(HERE, "houndarm.npz"))

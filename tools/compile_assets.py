@@ -8,6 +8,7 @@ Run in the build container (needs /root/reference); the outputs under
   Hound.urdf           tasks/hound.py:168-181, cfg/task/Hound.yaml:53 (no collapse, cylinders kept)
   UsefulHound Hound    tasks/useful_hound.py:316-327    (no collapse)
   cartpole.urdf        tasks/cartpole.py:86-88          (fixed base)
+  open_manipulator_p   tasks/hound_arm.py:203-216       (fixed base, no collapse, gravity disabled)
 """
 import os
 import sys
@@ -25,6 +26,8 @@ JOBS = [
     ("urdf/UsefulHound/urdf/Hound.urdf", AssetOptions(collapse_fixed_joints=False, replace_cylinder_with_capsule=False, density=0.001, thickness=0.01)),
     ("urdf/UsefulHound/urdf/Hound.urdf", AssetOptions(collapse_fixed_joints=True, replace_cylinder_with_capsule=True, density=0.001, thickness=0.01)),
     ("urdf/cartpole.urdf", AssetOptions(fix_base_link=True)),
+    ("urdf/open_manipulator_p_gazebo/urdf/open_manipulator_p.urdf", AssetOptions(fix_base_link=True, collapse_fixed_joints=False,
+                                                                                replace_cylinder_with_capsule=False, disable_gravity=True, thickness=0.001)),
 ]
 
 if __name__ == "__main__":
