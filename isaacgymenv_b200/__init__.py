@@ -77,7 +77,8 @@ def make(seed: int, task: str, num_envs: int, sim_device: str, rl_device: str, g
     ``utils/utils.py:89-94``)."""
     if cfg is None:
         cfg_dict = load_task_config(task, overrides)
-        cfg_dict["env"]["numEnvs"] = int(num_envs)
+        if num_envs is not None and num_envs != "":       # '' / None = the task yaml's own count (cfg/config.yaml:8 num_envs: '')
+            cfg_dict["env"]["numEnvs"] = int(num_envs)
     else:
         cfg_dict = copy.deepcopy(cfg)
         if overrides:

@@ -256,6 +256,57 @@ class PPO:
             fn()
         return g
 
+    # ------------------------------------------------------------------ checkpoints / evaluation
+    def state_dict(self):
+        """What rl_games keeps in its ``.pth`` files (``a2c_common.get_full_state_weights``): network, normalisers, optimiser."""
+        return {"model": self.model.state_dict(), "obs_rms": self.obs_rms.state_dict(), "val_rms": self.val_rms.state_dict(),
+                "optimizer": self.opt.state_dict(), "lr": float(self.lr_t) if torch.is_tensor(self.lr_t) else self.lr, "units": tuple(self.cfg.units)}
+
+    def load_state_dict(self, sd, load_optimizer=True):
+        self.model.load_state_dict(sd["model"])
+        self.obs_rms.load_state_dict(sd["obs_rms"])
+        self.val_rms.load_state_dict(sd["val_rms"])
+        if load_optimizer and "optimizer" in sd:
+            try:
+                self.opt.load_state_dict(sd["optimizer"])
+            except (ValueError, KeyError):
+                pass        # optimiser flavour differs (capturable / fused): keep the fresh one
+        self.lr = float(sd.get("lr", self.lr))
+        self.lr_t.fill_(self.lr)
+
+    def save(self, path):
+        import os
+
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        torch.save(self.state_dict(), path)
+
+    def load(self, path, load_optimizer=True):
+        self.load_state_dict(torch.load(path, map_location=self.device), load_optimizer)
+
+    @torch.no_grad()
+    def play(self, steps=1000, deterministic=True):
+        """``test=True`` of the reference's train.py: run the policy without learning; returns (mean episode reward, length)."""
+        env = self.env
+        obs = env.reset()["obs"].clone()
+        ep_rew = torch.zeros(env.num_envs, device=self.device)
+        ep_len = torch.zeros(env.num_envs, device=self.device)
+        tot = torch.zeros(3, device=self.device, dtype=torch.float64)
+        for _ in range(steps):
+            mu, log_std, _ = self.model(self.obs_rms.normalize(obs))
+            act = mu if deterministic else mu + log_std.exp() * torch.randn_like(mu)
+            o, rew, done, _ = env.step(torch.clamp(act, -1.0, 1.0))
+            obs = o["obs"].clone()
+            donef = (done != 0).float()
+            ep_rew += rew
+            ep_len += 1
+            tot[0] += (ep_rew * donef).sum()
+            tot[1] += (ep_len * donef).sum()
+            tot[2] += donef.sum()
+            ep_rew *= 1.0 - donef
+            ep_len *= 1.0 - donef
+        t = tot.tolist()
+        return (t[0] / t[2], t[1] / t[2]) if t[2] > 0 else (float(ep_rew.mean()), float(ep_len.mean()))
+
     def _episode_stats(self):
         s = self.fin.tolist()
         if s[2] > 0:
@@ -282,7 +333,8 @@ class PPO:
         steps = 0
         kl_lo, kl_hi = 0.5 * cfg.kl_threshold, 2.0 * cfg.kl_threshold
         n_mb = max((T * N) // self.mb, 1)
-        for epoch in range(max_epochs or cfg.max_epochs):
+        total_epochs = max_epochs or cfg.max_epochs
+        for epoch in range(total_epochs):
             if self._g_rollout is not None:
                 self._g_rollout.replay()
             else:
@@ -314,7 +366,7 @@ class PPO:
                         self.lr = min(self.lr * 1.5, 1e-2)
                     for g in self.opt.param_groups:
                         g["lr"] = self.lr
-            if (epoch + 1) % log_every == 0 or epoch == 0:
+            if (epoch + 1) % log_every == 0 or epoch == 0 or epoch + 1 == total_epochs:
                 if graph_update:
                     self.lr = float(self.lr_t)
                 r, l = self._episode_stats()

@@ -43,6 +43,9 @@ def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp, kd, kp_null, kd_null, defa
 
 
 class Houndarm(VecTask):
+    # post_physics_step finds the environments to reset with nonzero() (as the reference does): not CUDA-graph capturable
+    needs_host_sync = True
+
     def __init__(self, cfg, rl_device, sim_device, graphics_device_id, headless, virtual_screen_capture=False, force_render=False):
         self.cfg = cfg
         env = cfg["env"]
