@@ -53,9 +53,14 @@ for k in keys:
         i = h.index(k)
         rows.append(("metric", k, data[i], u[i]))
 for k in h:
-    if "tensor" in k and k not in keys and "pct" in k:
+    if "tensor" in k and k not in keys and "pct" in k and ".avg." in k:
         i = h.index(k)
-        rows.append(("metric", k, data[i], u[i]))
+        try:
+            nonzero = float(data[i]) != 0.0
+        except ValueError:
+            nonzero = False
+        if nonzero:
+            rows.append(("metric", k, data[i], u[i]))
 for (f, l), v in sorted(per.items(), key=lambda kv: -kv[1][0])[:30]:
     text = lines[l - 1].strip()[:110] if f == base and l and l <= len(lines) else ""
     rows.append(("line", f"{f}:{l}", f"inst {100 * v[0] / max(ti, 1):.1f}% samples {100 * v[1] / max(ts, 1):.1f}% sass {v[2]}", text))
