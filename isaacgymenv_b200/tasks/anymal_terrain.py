@@ -68,8 +68,8 @@ class AnymalTerrain(VecTask):
         for k in self.rew_scales:
             self.rew_scales[k] *= self.dt
         self.seed = int(cfg.get("seed", 42))
-        if cfg["task"]["randomize"]:
-            raise NotImplementedError("task.randomize=True (domain randomisation) is outside the B200 hot path")
+        # cfg["task"]["randomize"] is never read by the reference's terrain tasks (no apply_randomizations call in
+        # tasks/anymal_terrain.py); their only randomisation is the friction-bucket draw of _create_envs (:235-247), done below
 
         super().__init__(config=self.cfg, rl_device=rl_device, sim_device=sim_device, graphics_device_id=graphics_device_id, headless=headless,
                          virtual_screen_capture=virtual_screen_capture, force_render=force_render)
