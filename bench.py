@@ -41,6 +41,8 @@ TASKS = {
     "HoundTerrain": (2256, 4096, "k_terrain_phys", None, "HoundTerrain (plane), 4096 envs/GPU, explicit PD decimation 4 (+1), dt 0.005 s, random actions"),
     "UsefulHound": (2696, 4096, "k_terrain_phys", None, "UsefulHound hound + 6-DOF arm (OSC), 4096 envs/GPU, 18 actions, 204 obs, explicit PD decimation 4 (+1), "
                     "dt 0.005 s, random actions"),
+    "Houndarm": (356, 8192, "k_houndarm_step", None, "Houndarm fixed-base 6-DOF arm reach (OSC: two 6x6 inversions per step), 8192 envs/GPU, dt 0.01667 s x 2 sub-steps, "
+                 "random actions"),
 }
 
 

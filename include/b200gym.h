@@ -236,6 +236,24 @@ typedef struct b2g_cartpole_cfg {
 } b2g_cartpole_cfg;
 int b2g_task_cartpole_create(b2g_sim* sim, const b2g_cartpole_cfg* cfg);
 
+/* Fixed-base arm reach task Houndarm (reference: tasks/hound_arm.py:74-567), one launch per step: actions -> pose deltas
+ * (* cmd_limit / action_scale, :499-501) -> operational-space torques from the CURRENT mass matrix, Jacobian row and
+ * end-effector velocity (:462-493; the reference refreshes them at the end of the previous post_physics_step, after resets) ->
+ * sub-steps with effort drives -> post_physics_step: progress, reset_idx (:394-459: 3 command draws, 6 joint-noise draws,
+ * clamped to the limits, reset_buf = 0), observations [eef pos, eef quat, command] (:383-392), reward / reset (:550-567),
+ * time-outs and clamped observations (vec_task.py:394-402).  Needs a fixed-base single chain of <= 6 DOF. */
+typedef struct b2g_houndarm_cfg {
+    float clip_obs, clip_actions, action_scale, dof_noise;
+    float cmd_limit[6];
+    float kp, kp_null;                 /* kd = 2 sqrt(kp) (:166-169) */
+    float cmd_range[6];                /* x lo, x hi, y lo, y hi, z lo, z hi */
+    float dist_scale, vel_scale;
+    int32_t eef_body, jac_body;        /* API bodies: end-effector state row; row of the fixed-base Jacobian the task takes */
+    int64_t max_episode_length;
+    uint64_t seed;
+} b2g_houndarm_cfg;
+int b2g_task_houndarm_create(b2g_sim* sim, const b2g_houndarm_cfg* cfg);
+
 /* Rough-terrain locomotion task: AnymalTerrain / HoundTerrain (reference: tasks/anymal_terrain.py:45-538,
  * tasks/Hound_terrain.py same lines).  One step() = `decimation` sim steps with fresh explicit PD torques
  * (:441-451) + `extra_sim_steps` with the last torques (the generic VecTask loop, vec_task.py:379-382), then
@@ -341,7 +359,7 @@ int b2g_task_host_layout(const b2g_sim* sim, int64_t* offsets /*[4]*/, int64_t* 
 int64_t b2g_sim_launch_count(const b2g_sim* sim);
 
 /* sizeof() of the public PODs (0 model, 1 sim_params, 2 dof_props, 3 heightfield, 4 tensor_desc,
- * 5 anymal_cfg, 6 cartpole_cfg, 7 terrain_cfg) so a foreign-language mirror of this header can verify its layout */
+ * 5 anymal_cfg, 6 cartpole_cfg, 7 terrain_cfg, 8 houndarm_cfg) so a foreign-language mirror of this header can verify its layout */
 int b2g_sizeof(int which);
 
 /* gymtorch.wrap_tensor (tasks/anymal.py:121-126): wrap a tensor description as a DLPack

@@ -93,6 +93,12 @@ class CartpoleCfg(C.Structure):
                 ("max_episode_length", C.c_int64), ("seed", C.c_uint64)]
 
 
+class HoundarmCfg(C.Structure):
+    _fields_ = [("clip_obs", f32), ("clip_actions", f32), ("action_scale", f32), ("dof_noise", f32), ("cmd_limit", f32 * 6),
+                ("kp", f32), ("kp_null", f32), ("cmd_range", f32 * 6), ("dist_scale", f32), ("vel_scale", f32),
+                ("eef_body", i32), ("jac_body", i32), ("max_episode_length", C.c_int64), ("seed", C.c_uint64)]
+
+
 class TerrainCfg(C.Structure):
     _fields_ = [
         ("lin_vel_scale", f32), ("ang_vel_scale", f32), ("dof_pos_scale", f32), ("dof_vel_scale", f32), ("height_meas_scale", f32),

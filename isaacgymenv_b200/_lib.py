@@ -57,6 +57,7 @@ def load():
         "b2g_task_set_rand_override": [vp, ip],
         "b2g_task_anymal_step_host": [vp, vp, vp, vp, vp, vp, vp],
         "b2g_task_cartpole_create": [vp, C.POINTER(_abi.CartpoleCfg)],
+        "b2g_task_houndarm_create": [vp, C.POINTER(_abi.HoundarmCfg)],
         "b2g_task_terrain_create": [vp, C.POINTER(_abi.TerrainCfg), vp, vp],
         "b2g_task_terrain_set_step": [vp, C.c_int64],
         "b2g_task_terrain_set_init_done": [vp, ip],
@@ -82,7 +83,7 @@ def load():
         fn.restype = C.c_int
     if lib.b2g_abi_version() != _abi.B2G_ABI_VERSION:
         raise B2GError("libb200gym.so ABI version mismatch; rebuild")
-    for which, st in enumerate((_abi.Model, _abi.SimParams, _abi.DofProps, _abi.Heightfield, _abi.TensorDesc, _abi.AnymalCfg, _abi.CartpoleCfg, _abi.TerrainCfg)):
+    for which, st in enumerate((_abi.Model, _abi.SimParams, _abi.DofProps, _abi.Heightfield, _abi.TensorDesc, _abi.AnymalCfg, _abi.CartpoleCfg, _abi.TerrainCfg, _abi.HoundarmCfg)):
         if lib.b2g_sizeof(which) != C.sizeof(st):
             raise B2GError(f"struct layout mismatch for {st.__name__}: C {lib.b2g_sizeof(which)} vs ctypes {C.sizeof(st)}")
     _lib = lib
@@ -99,7 +100,7 @@ EXPORTED_SYMBOLS = [
     "b2g_abi_version", "b2g_last_error", "b2g_sim_create", "b2g_sim_destroy", "b2g_sim_set_params", "b2g_sim_get_params",
     "b2g_sim_add_ground", "b2g_sim_add_heightfield", "b2g_sim_add_articulation", "b2g_sim_prepare", "b2g_sim_set_dof_props",
     "b2g_sim_tensor", "b2g_sim_simulate", "b2g_sim_refresh", "b2g_sim_set_indexed", "b2g_sim_set_tensor",
-    "b2g_sim_forward_dynamics", "b2g_task_anymal_create", "b2g_task_tensor", "b2g_task_anymal_reset_all", "b2g_task_anymal_step", "b2g_task_set_rand_override", "b2g_task_anymal_post_only", "b2g_task_anymal_step_host", "b2g_task_cartpole_create", "b2g_task_terrain_create", "b2g_task_terrain_set_step", "b2g_task_terrain_set_init_done", "b2g_task_terrain_device_step", "b2g_task_step", "b2g_task_post_only", "b2g_task_osc_probe", "b2g_task_step_host", "b2g_sim_launch_count", "b2g_sizeof", "b2g_dlpack_from_desc", "b2g_task_host_layout",
+    "b2g_sim_forward_dynamics", "b2g_task_anymal_create", "b2g_task_tensor", "b2g_task_anymal_reset_all", "b2g_task_anymal_step", "b2g_task_set_rand_override", "b2g_task_anymal_post_only", "b2g_task_anymal_step_host", "b2g_task_cartpole_create", "b2g_task_houndarm_create", "b2g_task_terrain_create", "b2g_task_terrain_set_step", "b2g_task_terrain_set_init_done", "b2g_task_terrain_device_step", "b2g_task_step", "b2g_task_post_only", "b2g_task_osc_probe", "b2g_task_step_host", "b2g_sim_launch_count", "b2g_sizeof", "b2g_dlpack_from_desc", "b2g_task_host_layout",
     "b2g_policy_create", "b2g_policy_destroy", "b2g_policy_set_layer", "b2g_policy_set_obs_norm", "b2g_policy_forward", "b2g_policy_launch_count",
 ]
 

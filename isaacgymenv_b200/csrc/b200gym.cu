@@ -97,6 +97,13 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArg
     anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
 }
 
+__global__ void __launch_bounds__(kBlock) k_houndarm_step(SimArgs A, TaskArgs T) {
+    extern __shared__ float smem[];
+    int env, lane; bool valid; ScratchStrided sc; float* bf;
+    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    houndarm_step_thread(A, T, env, valid, sc, bf);
+}
+
 __global__ void __launch_bounds__(kBlock) k_cartpole_step(SimArgs A, TaskArgs T) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
@@ -260,11 +267,12 @@ struct b2g_sim {
     float* t[B2G_T_COUNT] = {nullptr};
     // task
     bool has_task = false;
-    int task_kind = 0;             // 1 = flat locomotion (Anymal/Hound), 2 = Cartpole
+    int task_kind = 0;             // 1 = flat locomotion (Anymal/Hound), 2 = Cartpole, 3 = rough terrain, 4 = Houndarm
     int num_obs = 0, num_act = 0, n_draws = 0, n_cmd = 3;
     unsigned long long seed = 0;
     b2g_anymal_cfg acfg{};
     b2g_cartpole_cfg ccfg{};
+    b2g_houndarm_cfg hcfg{};
     b2g_terrain_cfg tcfg{};
     float *torques = nullptr, *last_actions = nullptr, *last_dof_vel = nullptr, *feet_air_time = nullptr, *episode_sums = nullptr;
     float *env_origins = nullptr, *terrain_origins = nullptr, *scratch9 = nullptr, *resetw = nullptr, *report = nullptr, *measured = nullptr;
@@ -322,6 +330,7 @@ TaskArgs make_task_args(const b2g_sim* s, const float* actions_in, int post_only
     T.post_only = post_only;
     T.cfg = s->acfg;
     T.ccfg = s->ccfg;
+    T.hcfg = s->hcfg;
     T.seed = s->seed;
     T.actions_in = actions_in;
     T.obs = s->obs; T.obs_clamped = s->obs_clamped; T.rew = s->rew; T.reset = s->reset; T.progress = s->progress;
@@ -449,6 +458,14 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         CUDA_TRY(cudaGetLastError());
         return B2G_OK;
     }
+    if (s->task_kind == 4) {     // one thread per environment whatever the generic kernels' lane count is
+        const int g1 = (s->n_envs + kBlock - 1) / kBlock;
+        const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3);
+        k_houndarm_step<<<g1, kBlock, sm1, st>>>(A, T);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return B2G_OK;
+    }
     if (s->task_kind == 2) {
         k_cartpole_step<<<grid, kBlock, sm, st>>>(A, T);
         s->launches++;
@@ -487,6 +504,7 @@ int b2g_sizeof(int which) {
         case 5: return (int)sizeof(b2g_anymal_cfg);
         case 6: return (int)sizeof(b2g_cartpole_cfg);
         case 7: return (int)sizeof(b2g_terrain_cfg);
+        case 8: return (int)sizeof(b2g_houndarm_cfg);
         default: return -1;
     }
 }
@@ -806,6 +824,24 @@ int b2g_task_cartpole_create(b2g_sim* s, const b2g_cartpole_cfg* cfg) {
     s->task_kind = 2;
     if (s->has_task) return B2G_OK;
     return alloc_task_buffers(s, 4, 1, 4);
+}
+
+int b2g_task_houndarm_create(b2g_sim* s, const b2g_houndarm_cfg* cfg) {
+    if (!s || !cfg) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->prepared) return fail(B2G_ERR_STATE, "task created before prepare_sim");
+    if (!s->model.fixed_base || s->model.n_chains != 1 || s->model.n_dof < 1 || s->model.n_dof > 6)
+        return fail(B2G_ERR_UNSUPPORTED, "Houndarm needs a fixed-base single chain of at most 6 DOF");
+    if (cfg->eef_body < 0 || cfg->eef_body >= s->model.n_bodies || cfg->jac_body < 0 || cfg->jac_body >= s->model.n_bodies)
+        return fail(B2G_ERR_ARG, "eef_body / jac_body out of range");
+    if (!(cfg->action_scale != 0.0f)) return fail(B2G_ERR_ARG, "action_scale must be non-zero");
+    if (s->has_task && s->task_kind != 4) return fail(B2G_ERR_STATE, "another task already lives on this sim");
+    s->hcfg = *cfg;
+    s->seed = cfg->seed;
+    s->task_kind = 4;
+    if (s->has_task) return B2G_OK;
+    const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3);
+    cudaFuncSetAttribute(k_houndarm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    return alloc_task_buffers(s, 10, s->model.n_dof, 9);
 }
 
 int b2g_task_terrain_create(b2g_sim* s, const b2g_terrain_cfg* cfg, const int16_t* hs_host, const float* origins_host) {

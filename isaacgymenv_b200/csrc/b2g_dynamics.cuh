@@ -547,8 +547,8 @@ B2G_LINK_UNROLL
             st.q[j] += h * qp;
             st.qd[j] = qv;
             float f = 0.0f;
-            if (D.drive_mode == B2G_DOF_MODE_POS) f = D.kp * (st.tgt[j] - st.q[j]) - D.kd * qv;
-            else if (D.drive_mode == B2G_DOF_MODE_VEL) f = D.kd * (st.tgt[j] - qv);
+            if (D.drive_mode == B2G_DOF_MODE_POS) f = D.kp * dr.kp * (st.tgt[j] - st.q[j]) - D.kd * dr.kd * qv;
+            else if (D.drive_mode == B2G_DOF_MODE_VEL) f = D.kd * dr.kd * (st.tgt[j] - qv);
             else if (D.drive_mode == B2G_DOF_MODE_EFFORT) f = st.act[j];
             if (D.effort > 0.0f) f = fminf(fmaxf(f, -D.effort), D.effort);
             st.frc[j] = f;

@@ -24,6 +24,7 @@ struct SimArgs {
 struct TaskArgs {
     b2g_anymal_cfg cfg;
     b2g_cartpole_cfg ccfg;
+    b2g_houndarm_cfg hcfg;
     unsigned long long seed;
     const float* actions_in;   // (N,na)
     float* obs;                // (N,12+3*nd)
@@ -586,6 +587,142 @@ B2G_HD inline void arm_refresh(const SimArgs& A, const TerrainArgs& T, int env, 
         else { float s2 = sqrtf(1.0f + Rb.m[8] - Rb.m[0] - Rb.m[4]) * 2.0f; qw = (Rb.m[3] - Rb.m[1]) / s2; qx = (Rb.m[2] + Rb.m[6]) / s2; qy = (Rb.m[5] + Rb.m[7]) / s2; qz = 0.25f * s2; }
         e[3] = qx; e[4] = qy; e[5] = qz; e[6] = qw;
         e[7] = lin.x; e[8] = lin.y; e[9] = lin.z; e[10] = ev.w.x; e[11] = ev.w.y; e[12] = ev.w.z;
+    }
+}
+
+// ---- Houndarm (tasks/hound_arm.py): the whole VecTask.step of the fixed-base arm reach task, one thread per environment ----
+// kinematics of the single chain: link poses relative to the root origin (world axes), link spatial velocities, joint axes
+B2G_HD inline void arm_chain_kin(const DevModel* M, const LaneState<6>& st, int n, M3* Rl, V3* pl, SV* vl, V3* axw, V3* pj) {
+    Rl[0] = quat_to_m3(st.qx, st.qy, st.qz, st.qw);
+    pl[0] = V3{0, 0, 0};
+    vl[0] = sv0();
+    for (int j = 0; j < n; j++) {
+        const DevDof& D = M->dof[j];
+        M3 jr;
+        for (int k = 0; k < 9; k++) jr.m[k] = D.jrot[k];
+        const V3 ax = V3{D.axis[0], D.axis[1], D.axis[2]};
+        const M3 RJ = mul(Rl[j], jr);
+        pj[j] = pl[j] + mul(Rl[j], V3{D.jpos[0], D.jpos[1], D.jpos[2]});
+        axw[j] = mul(RJ, ax);
+        SV S;
+        if (D.type == B2G_JOINT_REVOLUTE) { Rl[j + 1] = mul(RJ, axis_angle_m3(ax, st.q[j])); pl[j + 1] = pj[j]; S = SV{axw[j], cross(pj[j], axw[j])}; }
+        else { Rl[j + 1] = RJ; pl[j + 1] = pj[j] + axw[j] * st.q[j]; S = SV{V3{0, 0, 0}, axw[j]}; }
+        vl[j + 1] = vl[j] + S * st.qd[j];
+    }
+}
+// rigid-body state row of API body b (same conventions as body_state_env): pos3, quat xyzw, linear velocity, angular velocity
+B2G_HD inline void arm_body_row(const DevModel* M, int b, const LaneState<6>& st, const M3* Rl, const V3* pl, const SV* vl, float* o) {
+    const int l = M->body_link[b];
+    const V3 p = pl[l] + mul(Rl[l], V3{M->body_pos[b][0], M->body_pos[b][1], M->body_pos[b][2]});
+    const M3 R = mul(Rl[l], quat_to_m3(M->body_quat[b][0], M->body_quat[b][1], M->body_quat[b][2], M->body_quat[b][3]));
+    float qx, qy, qz, qw;
+    const float tr = R.m[0] + R.m[4] + R.m[8];
+    if (tr > 0.0f) { float s = sqrtf(tr + 1.0f) * 2.0f; qw = 0.25f * s; qx = (R.m[7] - R.m[5]) / s; qy = (R.m[2] - R.m[6]) / s; qz = (R.m[3] - R.m[1]) / s; }
+    else if (R.m[0] > R.m[4] && R.m[0] > R.m[8]) { float s = sqrtf(1.0f + R.m[0] - R.m[4] - R.m[8]) * 2.0f; qw = (R.m[7] - R.m[5]) / s; qx = 0.25f * s; qy = (R.m[1] + R.m[3]) / s; qz = (R.m[2] + R.m[6]) / s; }
+    else if (R.m[4] > R.m[8]) { float s = sqrtf(1.0f + R.m[4] - R.m[0] - R.m[8]) * 2.0f; qw = (R.m[2] - R.m[6]) / s; qx = (R.m[1] + R.m[3]) / s; qy = 0.25f * s; qz = (R.m[5] + R.m[7]) / s; }
+    else { float s = sqrtf(1.0f + R.m[8] - R.m[0] - R.m[4]) * 2.0f; qw = (R.m[3] - R.m[1]) / s; qx = (R.m[2] + R.m[6]) / s; qy = (R.m[5] + R.m[7]) / s; qz = 0.25f * s; }
+    const V3 v = vl[l].v + cross(vl[l].w, p);
+    o[0] = st.rp.x + p.x; o[1] = st.rp.y + p.y; o[2] = st.rp.z + p.z;
+    o[3] = qx; o[4] = qy; o[5] = qz; o[6] = qw;
+    o[7] = v.x; o[8] = v.y; o[9] = v.z;
+    o[10] = vl[l].w.x; o[11] = vl[l].w.y; o[12] = vl[l].w.z;
+}
+
+B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, int env, bool valid, ScratchStrided sc, float* bf) {
+    const DevModel* M = A.M;
+    const b2g_houndarm_cfg& C = T.hcfg;
+    const int n = M->chain_len[0];
+    LaneState<6> st;
+    load_state<6>(A, env, n, 0, st);
+    float act[6];
+    for (int j = 0; j < 6; j++) {
+        float a = (j < n) ? T.actions_in[(size_t)env * n + j] : 0.0f;
+        act[j] = fminf(fmaxf(a, -C.clip_actions), C.clip_actions);
+        st.act[j] = 0.0f;
+        st.tgt[j] = 0.0f;
+        st.frc[j] = (j < n) ? A.dof_force[(size_t)env * n + j] : 0.0f;
+    }
+    M3 Rl[7];
+    V3 pl[7], axw[6], pj[6];
+    SV vl[7];
+    if (!T.post_only) {
+        // pre_physics_step (:495-507): OSC torques from the state as it is now
+        arm_chain_kin(M, st, n, Rl, pl, vl, axw, pj);
+        float eef[13], J[36], mm[36], dpose[6], effort[6], u[6];
+        arm_body_row(M, C.eef_body, st, Rl, pl, vl, eef);
+        const int l = M->body_link[C.jac_body];
+        const V3 pb = pl[l] + mul(Rl[l], V3{M->body_pos[C.jac_body][0], M->body_pos[C.jac_body][1], M->body_pos[C.jac_body][2]});
+        for (int i = 0; i < 36; i++) J[i] = 0.0f;
+        for (int d = 0; d <= l - 1; d++) {
+            if (M->dof[d].type == B2G_JOINT_REVOLUTE) {
+                const V3 lin = cross(axw[d], pb - pj[d]);
+                J[0 * 6 + d] = lin.x; J[1 * 6 + d] = lin.y; J[2 * 6 + d] = lin.z;
+                J[3 * 6 + d] = axw[d].x; J[4 * 6 + d] = axw[d].y; J[5 * 6 + d] = axw[d].z;
+            } else {
+                J[0 * 6 + d] = axw[d].x; J[1 * 6 + d] = axw[d].y; J[2 * 6 + d] = axw[d].z;
+            }
+        }
+        const float rq[4] = {st.qx, st.qy, st.qz, st.qw};
+        V3 dp; M3 dr; SV dv;
+        chain_crba(M, 0, n, rq, st.q, mm, -1, &dp, &dr, st.qd, V3{0, 0, 0}, V3{0, 0, 0}, &dv, A.env_scale ? A.env_scale[(size_t)(valid ? env : 0) * 4] : 1.0f);
+        for (int i = 0; i < 6; i++) {
+            dpose[i] = act[i] * C.cmd_limit[i] / C.action_scale;
+            effort[i] = (i < n) ? M->dof[i].effort : 0.0f;
+        }
+        OscPrepared P;
+        osc_prepare(mm, J, dpose, eef + 7, C.kp, P);
+        osc_apply(P, st.q, st.qd, C.kp_null, effort, u);
+        for (int j = 0; j < 6; j++) st.act[j] = (j < n) ? u[j] : 0.0f;
+        const EnvDr dr_env = load_env_dr(A.friction, A.env_scale, valid ? env : 0);
+#pragma unroll 1
+        for (int s = 0; s < A.P.substeps; s++)
+            substep<1, 6, true, false, false, false>(M, A.P, 0, n, 0, st, dr_env, s == A.P.substeps - 1, sc, bf);
+    }
+    // post_physics_step (:509-517)
+    long long progress = T.progress[env] + 1;
+    long long reset_prev = T.reset[env];
+    int rc = 0;
+    float cmd[3] = {T.commands[(size_t)env * 3 + 0], T.commands[(size_t)env * 3 + 1], T.commands[(size_t)env * 3 + 2]};
+    const bool do_reset = reset_prev != 0;
+    if (do_reset) {          // reset_idx (:394-459); draw order: command x, y, z, then the six joint-noise uniforms
+        rc = T.reset_count[env];
+        const int nd = 9;
+        for (int k = 0; k < 3; k++) cmd[k] = rand_range(C.cmd_range[2 * k], C.cmd_range[2 * k + 1], reset_uniform(T, env, rc, k, nd));
+        for (int j = 0; j < n; j++) {
+            const float r = reset_uniform(T, env, rc, 3 + j, nd);
+            const float p = 0.0f + C.dof_noise * 2.0f * (r - 0.5f);
+            st.q[j] = fminf(fmaxf(p, M->dof[j].lower), M->dof[j].upper);
+            st.qd[j] = 0.0f;
+        }
+        progress = 0;
+        reset_prev = 0;
+    }
+    // compute_observations (:383-392) on the refreshed state, compute_reward (:550-567)
+    arm_chain_kin(M, st, n, Rl, pl, vl, axw, pj);
+    float eef[13];
+    arm_body_row(M, C.eef_body, st, Rl, pl, vl, eef);
+    const float dx = eef[0] - cmd[0], dy = eef[1] - cmd[1], dz = eef[2] - cmd[2];
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    float vsq = 0.0f;
+    for (int k = 7; k < 13; k++) vsq += eef[k] * eef[k];
+    float rew = (1.0f - tanhf(10.0f * dist)) * C.dist_scale + (1.0f - tanhf(10.0f * sqrtf(vsq))) * (dist < 0.02f ? 1.0f : 0.0f) * C.vel_scale;
+    rew = fmaxf(rew, 0.0f);
+    const bool time_out = progress >= C.max_episode_length - 1;
+    const long long reset = time_out ? 1 : reset_prev;
+    if (valid) {
+        store_state<6>(A, env, 0, n, 0, st, true);
+        float* o = T.obs + (size_t)env * 10;
+        float* oc = T.obs_clamped + (size_t)env * 10;
+        for (int k = 0; k < 7; k++) o[k] = eef[k];
+        for (int k = 0; k < 3; k++) o[7 + k] = cmd[k];
+        for (int k = 0; k < 10; k++) oc[k] = fminf(fmaxf(o[k], -C.clip_obs), C.clip_obs);
+        T.rew[env] = rew;
+        T.reset[env] = reset;
+        T.progress[env] = progress;
+        T.timeout[env] = (time_out && reset != 0) ? 1 : 0;
+        for (int j = 0; j < n; j++) T.actions[(size_t)env * n + j] = act[j];
+        for (int k = 0; k < 3; k++) T.commands[(size_t)env * 3 + k] = cmd[k];
+        if (do_reset) T.reset_count[env] = rc + 1;
     }
 }
 

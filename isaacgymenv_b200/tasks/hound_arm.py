@@ -3,17 +3,23 @@
 (:462-493) -- or 6 raw joint torques with ``controlType: joint_tor`` --, 10 observations [eef position, eef quaternion,
 commanded position] (:383-392), reward ``compute_houndarm_reward`` (:550-567), reset draws (:394-459), 150-step episodes.
 
-This is SURVEY 8(f) row 4: it runs on the generic gym-tensor path of the shim (``k_simulate`` + ``k_body_state`` +
-``k_jacobian`` + ``k_mass_matrix``; OSC and reward as torch ops), i.e. exactly the reference's hook structure on
-``libb200gym``.  Replicated as they are: the Jacobian row is taken at the JOINT index (``get_actor_joint_dict()['joint6']``
-= 5, i.e. body ``link6`` of the fixed-base Jacobian, not ``end_link``; :314-318), ``reset_buf[env_ids] = 0`` on reset
-(quirk Q5), the no-op ``u_null[:, 6:] *= 0``.  ``asset_options.disable_gravity`` is honoured by the sim."""
+This is SURVEY 8(f) row 4.  Two execution paths, selected by ``cfg["env"]["fusedStep"]`` (default True):
+* fused: ``step()`` is ONE launch of ``k_houndarm_step`` (one thread per environment: OSC torques from the current mass matrix /
+  Jacobian row / end-effector velocity, the sub-steps, resets, observations, reward, time-outs) -- graph-capturable;
+* generic: the reference's hook structure on the gym-tensor API of the shim (``k_simulate`` + ``k_body_state`` + ``k_jacobian`` +
+  ``k_mass_matrix``; OSC and reward as torch ops).
+Replicated as they are: the Jacobian row is taken at the JOINT index (``get_actor_joint_dict()['joint6']`` = 5, which in the
+fixed-base Jacobian -- root body left out -- is body 6, ``end_link``; :314-318), ``reset_buf[env_ids] = 0`` on reset (quirk Q5),
+the no-op ``u_null[:, 6:] *= 0``.  ``asset_options.disable_gravity`` is honoured by the sim.  On the fused path ``self.states`` is
+refreshed on demand (``_refresh()``), not every step."""
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
 
-from .. import gymapi, gymtorch
+from .. import _abi, _lib, gymapi, gymtorch
 from ..utils.torch_math import tensor_clamp, to_torch, torch_rand_float
 from .anymal import default_asset_root
 from .base.vec_task import VecTask
@@ -43,9 +49,6 @@ def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp, kd, kp_null, kd_null, defa
 
 
 class Houndarm(VecTask):
-    # post_physics_step finds the environments to reset with nonzero() (as the reference does): not CUDA-graph capturable
-    needs_host_sync = True
-
     def __init__(self, cfg, rl_device, sim_device, graphics_device_id, headless, virtual_screen_capture=False, force_render=False):
         self.cfg = cfg
         env = cfg["env"]
@@ -67,6 +70,9 @@ class Houndarm(VecTask):
         if cfg.get("task", {}).get("randomize", False):
             raise NotImplementedError("Houndarm: task.randomize is not wired (the reference task never calls apply_randomizations)")
         self.states, self.handles = {}, {}
+        self.fused = bool(env.get("fusedStep", True))
+        # the generic path finds the environments to reset with nonzero() (as the reference does): not CUDA-graph capturable
+        self.needs_host_sync = not self.fused
         self.up_axis, self.up_axis_idx = "z", 2
         self.seed = int(cfg.get("seed", 42))
         super().__init__(config=cfg, rl_device=rl_device, sim_device=sim_device, graphics_device_id=graphics_device_id, headless=headless,
@@ -78,8 +84,10 @@ class Houndarm(VecTask):
         self.kd_null = 2 * torch.sqrt(self.kp_null)
         self.cmd_limit = to_torch([0.1, 0.1, 0.1, 0.5, 0.5, 0.5], device=self.device).unsqueeze(0)
         self.commands = torch.zeros(self.num_envs, 3, dtype=torch.float, device=self.device)
-        self.commands_x, self.commands_y, self.commands_z = (self.commands.view(self.num_envs, 3)[..., i] for i in range(3))
         self.actions = torch.zeros(self.num_envs, self.num_actions, device=self.device)
+        if self.fused:
+            self._create_fused_task()
+        self.commands_x, self.commands_y, self.commands_z = (self.commands.view(self.num_envs, 3)[..., i] for i in range(3))
         self.reset_idx(torch.arange(self.num_envs, device=self.device))
         self._refresh()
 
@@ -149,6 +157,51 @@ class Houndarm(VecTask):
         self._effort_control = torch.zeros_like(self._pos_control)
         self._arm_control = self._effort_control[:, :6]
         self._global_indices = torch.arange(n, dtype=torch.int32, device=self.device).view(n, -1)
+
+    # ---- fused path ----
+    def _create_fused_task(self):
+        self._lib = _lib.load()
+        e = self.cfg["env"]
+        c = _abi.HoundarmCfg(clip_obs=float(self.clip_obs), clip_actions=float(self.clip_actions), action_scale=float(self.action_scale),
+                             dof_noise=float(self.houndarm_dof_noise), kp=150.0, kp_null=10.0, dist_scale=float(e["distRewardScale"]),
+                             vel_scale=float(e["velRewardScale"]), eef_body=int(self.handles["endpoint_tip"]),
+                             jac_body=int(self.gym.get_actor_joint_dict(self.envs[0], 0)["joint6"]) + 1,
+                             max_episode_length=int(self.max_episode_length), seed=int(self.seed) & 0xFFFFFFFFFFFFFFFF)
+        for i, v in enumerate(self.cmd_limit.flatten().tolist()):
+            c.cmd_limit[i] = v
+        for i, v in enumerate(list(self.command_x_range) + list(self.command_y_range) + list(self.command_z_range)):
+            c.cmd_range[i] = float(v)
+        _lib.check(self._lib.b2g_task_houndarm_create(self.sim.handle, C.byref(c)), "task create")
+
+        def tt(kind):
+            d = _abi.TensorDesc()
+            _lib.check(self._lib.b2g_task_tensor(self.sim.handle, kind, C.byref(d)), "task tensor")
+            return _lib.desc_to_torch(d)
+
+        self.obs_buf, self.obs_clamped, self.rew_buf = tt(_abi.TT_OBS), tt(_abi.TT_OBS_CLAMPED), tt(_abi.TT_REW)
+        self.reset_buf, self.progress_buf, self.timeout_buf = tt(_abi.TT_RESET), tt(_abi.TT_PROGRESS), tt(_abi.TT_TIMEOUT)
+        self.commands, self.actions = tt(_abi.TT_COMMANDS), tt(_abi.TT_ACTIONS)
+        self.reset_buf.zero_()
+
+    def step(self, actions: torch.Tensor):
+        if not self.fused:
+            return super().step(actions)
+        a = actions.to(self.device, torch.float32)
+        if not a.is_contiguous():
+            a = a.contiguous()
+        self._last_actions_in = a          # keep a reference until the stream has consumed it
+        _lib.check(self._lib.b2g_task_step(self.sim.handle, C.c_void_p(a.data_ptr()), self.sim.stream()), "step")
+        self.control_steps += 1
+        self.sim.frame_count += 1
+        self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
+        self.obs_dict["obs"] = self.obs_clamped.to(self.rl_device)
+        return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
+
+    def reset(self):
+        if self.fused:
+            self.obs_dict["obs"] = self.obs_clamped.to(self.rl_device)
+            return self.obs_dict
+        return super().reset()
 
     # ---- state ----
     def _update_states(self):

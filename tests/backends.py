@@ -74,9 +74,22 @@ class EmuBackend:
                          reset=np.ones(n, np.int64), progress=np.zeros(n, np.int64), timeout=np.zeros(n, np.int64),
                          commands=np.zeros((n, 3), np.float32), actions=np.zeros((n, 1), np.float32), reset_count=np.zeros(n, np.int32))
 
+    def houndarm_create(self, cfg):
+        n, nd = self.n, self.art.num_dofs
+        self.cfg, self.kind = cfg, "houndarm"
+        self.task = dict(obs=np.zeros((n, 10), np.float32), obs_clamped=np.zeros((n, 10), np.float32), rew=np.zeros(n, np.float32),
+                         reset=np.ones(n, np.int64), progress=np.zeros(n, np.int64), timeout=np.zeros(n, np.int64),
+                         commands=np.zeros((n, 3), np.float32), actions=np.zeros((n, nd), np.float32), reset_count=np.zeros(n, np.int32))
+
     def task_step(self, actions, draws=None, post_only=False):
         if getattr(self, "kind", "anymal") == "terrain":
             self._terrain_step(actions, draws, post_only)
+        elif getattr(self, "kind", "anymal") == "houndarm":
+            self.emu.set_env_scale(getattr(self, "_scale", None))
+            try:
+                self.emu.houndarm(self.model, self.params, self.props, self.cfg, 2 if post_only else 1, self._bufs(), actions, draws)
+            finally:
+                self.emu.set_env_scale(None)
         elif getattr(self, "kind", "anymal") == "cartpole":
             self.emu.cartpole(self.model, self.params, self.props, self.cfg, 2 if post_only else 1, self._bufs(), actions, draws)
         elif post_only:
@@ -243,6 +256,12 @@ class CudaBackend:
 
     def cartpole_create(self, cfg):
         self._lib.check(self.lib.b2g_task_cartpole_create(self.sim, C.byref(cfg)), "task create")
+        kinds = dict(obs=_abi.TT_OBS, obs_clamped=_abi.TT_OBS_CLAMPED, rew=_abi.TT_REW, reset=_abi.TT_RESET, progress=_abi.TT_PROGRESS,
+                     timeout=_abi.TT_TIMEOUT, commands=_abi.TT_COMMANDS, actions=_abi.TT_ACTIONS, rand=_abi.TT_RAND_OVERRIDE)
+        self.task = {k: self._tensor(v, task=True) for k, v in kinds.items()}
+
+    def houndarm_create(self, cfg):
+        self._lib.check(self.lib.b2g_task_houndarm_create(self.sim, C.byref(cfg)), "task create")
         kinds = dict(obs=_abi.TT_OBS, obs_clamped=_abi.TT_OBS_CLAMPED, rew=_abi.TT_REW, reset=_abi.TT_RESET, progress=_abi.TT_PROGRESS,
                      timeout=_abi.TT_TIMEOUT, commands=_abi.TT_COMMANDS, actions=_abi.TT_ACTIONS, rand=_abi.TT_RAND_OVERRIDE)
         self.task = {k: self._tensor(v, task=True) for k, v in kinds.items()}

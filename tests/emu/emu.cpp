@@ -152,7 +152,7 @@ int emu_anymal(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = dof_force;
     A.contact = contact; A.friction = nullptr;
     TaskArgs T;
-    T.cfg = *cfg; T.seed = cfg->seed; memset(&T.ccfg, 0, sizeof(T.ccfg)); T.actions_in = actions_in; T.obs = obs; T.obs_clamped = obs_clamped; T.rew = rew; T.reset = reset;
+    T.cfg = *cfg; T.seed = cfg->seed; memset(&T.ccfg, 0, sizeof(T.ccfg)); memset(&T.hcfg, 0, sizeof(T.hcfg)); T.actions_in = actions_in; T.obs = obs; T.obs_clamped = obs_clamped; T.rew = rew; T.reset = reset;
     T.progress = progress; T.timeout = timeout; T.commands = commands; T.actions = actions; T.reset_count = reset_count;
     T.rand_override = rand_override;
     T.post_only = (mode == 2);
@@ -260,6 +260,7 @@ int emu_cartpole(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     A.contact = contact; A.friction = nullptr;
     TaskArgs T;
     memset(&T.cfg, 0, sizeof(T.cfg));
+    memset(&T.hcfg, 0, sizeof(T.hcfg));
     T.ccfg = *cfg; T.seed = cfg->seed; T.actions_in = actions_in; T.obs = obs; T.obs_clamped = obs_clamped; T.rew = rew; T.reset = reset;
     T.progress = progress; T.timeout = timeout; T.commands = nullptr; T.actions = actions; T.reset_count = reset_count;
     T.rand_override = rand_override; T.post_only = (mode == 2);
@@ -269,6 +270,37 @@ int emu_cartpole(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     for (int e = 0; e < n_envs; e++) {
         ScratchStrided sc{scratch.data(), 1};
         cartpole_step_thread(A, T, e, true, sc, bf.data());
+    }
+    delete dm;
+    return 0;
+}
+
+// Houndarm fused step: mode 1 = step, 2 = post_physics_step only
+int emu_houndarm(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, const b2g_houndarm_cfg* cfg, int mode,
+                 int n_envs, float* root, float* dof, float* dof_force, float* contact, const float* actions_in, float* obs,
+                 float* obs_clamped, float* rew, long long* reset, long long* progress, long long* timeout, float* commands, float* actions,
+                 int* reset_count, const float* rand_override) {
+    DevModel* dm = new DevModel;
+    const char* why;
+    if (pack_dev_model(*m, *dp, *dm, &why) != 0) { delete dm; return -1; }
+    if (!m->fixed_base || m->n_chains != 1 || m->n_dof > 6) { delete dm; return -2; }
+    SimArgs A;
+    A.M = dm;
+    pack_dev_params(*sp, nullptr, nullptr, A.P);
+    A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = dof_force;
+    A.contact = contact; A.friction = nullptr; A.env_scale = g_env_scale;
+    TaskArgs T;
+    memset(&T.cfg, 0, sizeof(T.cfg));
+    memset(&T.ccfg, 0, sizeof(T.ccfg));
+    T.hcfg = *cfg; T.seed = cfg->seed; T.actions_in = actions_in; T.obs = obs; T.obs_clamped = obs_clamped; T.rew = rew; T.reset = reset;
+    T.progress = progress; T.timeout = timeout; T.commands = commands; T.actions = actions; T.reset_count = reset_count;
+    T.rand_override = rand_override; T.post_only = (mode == 2);
+    std::vector<float> scratch((size_t)MAXC * CF_COUNT), bf((size_t)m->n_bodies * 3);
+    EmuGroup g; g.lanes = 1; g.count = 0; g.sense = 0;
+    emu_ctx.g = &g; emu_ctx.lane = 0; emu_ctx.local_sense = 0;
+    for (int e = 0; e < n_envs; e++) {
+        ScratchStrided sc{scratch.data(), 1};
+        houndarm_step_thread(A, T, e, true, sc, bf.data());
     }
     delete dm;
     return 0;

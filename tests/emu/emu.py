@@ -97,6 +97,18 @@ def cartpole(model, params, props, cfg, mode, bufs, actions, rand_override=None)
     assert rc == 0, rc
 
 
+def houndarm(model, params, props, cfg, mode, bufs, actions, rand_override=None):
+    """mode 1 = step, 2 = post_physics_step only."""
+    n = bufs["root"].shape[0]
+    ai = np.ascontiguousarray(actions, dtype=np.float32)
+    ro = None if rand_override is None else np.ascontiguousarray(rand_override, dtype=np.float32)
+    rc = lib().emu_houndarm(C.byref(model), C.byref(params), C.byref(props), C.byref(cfg), C.c_int(mode), C.c_int(n),
+                            _p(bufs["root"]), _p(bufs["dof"]), _p(bufs["dof_force"]), _p(bufs["contact"]), _p(ai), _p(bufs["obs"]),
+                            _p(bufs["obs_clamped"]), _p(bufs["rew"]), _p(bufs["reset"], C.c_longlong), _p(bufs["progress"], C.c_longlong),
+                            _p(bufs["timeout"], C.c_longlong), _p(bufs["commands"]), _p(bufs["actions"]), _p(bufs["reset_count"], C.c_int), _p(ro))
+    assert rc == 0, rc
+
+
 class _TerrainBufs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("root", "dof", "dof_force", "contact", "actions_in", "obs", "obs_clamped", "rew", "reset", "progress",
                                           "timeout", "commands", "actions", "torques", "last_actions", "last_dof_vel", "feet_air_time",

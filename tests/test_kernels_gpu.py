@@ -72,3 +72,7 @@ def test_useful_hound_step():
 @pytest.mark.parametrize("robot", ["useful_hound", "anymal", "cartpole"])
 def test_jacobian_mass_matrix(robot):
     kc.check_jacobian_mass_matrix(make, robot)
+
+
+def test_houndarm_fused_step():
+    kc.check_houndarm_step(make, n=48)
