@@ -440,31 +440,35 @@ B2G_HD B2G_INL float norm3(const float* f) { return sqrtf(f[0] * f[0] + f[1] * f
 
 
 // ---- hound + arm helpers (tasks/useful_hound.py) ----
-// general 6x6 inverse, Gauss-Jordan with partial pivoting (what torch.inverse does for the OSC law, :668-670)
-B2G_HD inline void inv6(const float* a, float* inv) {
-    float m[6][12];
+// general 6x6 inverse, Gauss-Jordan with partial pivoting (what torch.inverse does for the OSC law, :668-670).
+// The OSC law inverts M and J M^-1 J^T; on the arms of this repo (a 19 g last link) the second matrix reaches condition numbers of
+// 1e8-1e10, where a float32 evaluation -- the reference's included -- is dominated by round-off.  The handful of 6x6 operations
+// per policy step are therefore carried out in float64 (a few thousand DP flops per environment), inputs and outputs float32.
+typedef double osc_real;
+B2G_HD inline void inv6(const osc_real* a, osc_real* inv) {
+    osc_real m[6][12];
     for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) { m[i][j] = a[i * 6 + j]; m[i][6 + j] = (i == j) ? 1.0f : 0.0f; }
+        for (int j = 0; j < 6; j++) { m[i][j] = a[i * 6 + j]; m[i][6 + j] = (i == j) ? 1.0 : 0.0; }
     for (int c = 0; c < 6; c++) {
         int piv = c;
-        float best = fabsf(m[c][c]);
-        for (int r = c + 1; r < 6; r++) if (fabsf(m[r][c]) > best) { best = fabsf(m[r][c]); piv = r; }
-        if (piv != c) for (int j = 0; j < 12; j++) { const float t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
-        const float d = 1.0f / m[c][c];
+        osc_real best = fabs(m[c][c]);
+        for (int r = c + 1; r < 6; r++) if (fabs(m[r][c]) > best) { best = fabs(m[r][c]); piv = r; }
+        if (piv != c) for (int j = 0; j < 12; j++) { const osc_real t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
+        const osc_real d = 1.0 / m[c][c];
         for (int j = 0; j < 12; j++) m[c][j] *= d;
         for (int r = 0; r < 6; r++) {
             if (r == c) continue;
-            const float f = m[r][c];
+            const osc_real f = m[r][c];
             for (int j = 0; j < 12; j++) m[r][j] -= f * m[c][j];
         }
     }
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) inv[i * 6 + j] = m[i][6 + j];
 }
-B2G_HD inline void mm6(const float* a, const float* b, float* o, bool ta = false, bool tb = false) {
-    float t[36];
+B2G_HD inline void mm6(const osc_real* a, const osc_real* b, osc_real* o, bool ta = false, bool tb = false) {
+    osc_real t[36];
     for (int i = 0; i < 6; i++)
         for (int j = 0; j < 6; j++) {
-            float acc = 0.0f;
+            osc_real acc = 0.0;
             for (int k = 0; k < 6; k++) acc += (ta ? a[k * 6 + i] : a[i * 6 + k]) * (tb ? b[j * 6 + k] : b[k * 6 + j]);
             t[i * 6 + j] = acc;
         }
@@ -478,22 +482,24 @@ struct OscPrepared {
     float u_task[6];
     float N[36];
 };
-B2G_HD inline void osc_prepare(const float* mm, const float* j, const float* dpose, const float* eef_vel, float kp, OscPrepared& P) {
-    const float kd = 2.0f * sqrtf(kp);
-    float mm_inv[36], t[36], m_eef_inv[36], m_eef[36], j_eef_inv[36];
+B2G_HD inline void osc_prepare(const float* mm_f, const float* j_f, const float* dpose, const float* eef_vel, float kp, OscPrepared& P) {
+    const osc_real kd = 2.0 * sqrt((osc_real)kp);
+    osc_real mm[36], j[36], mm_inv[36], t[36], m_eef_inv[36], m_eef[36], j_eef_inv[36];
+    for (int i = 0; i < 36; i++) { mm[i] = mm_f[i]; j[i] = j_f[i]; }
     inv6(mm, mm_inv);
     mm6(j, mm_inv, t);
     mm6(t, j, m_eef_inv, false, true);
     inv6(m_eef_inv, m_eef);
-    float w[6], v[6];
-    for (int i = 0; i < 6; i++) w[i] = kp * dpose[i] - kd * eef_vel[i];
-    for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += m_eef[i * 6 + k] * w[k]; v[i] = acc; }
-    for (int i = 0; i < 6; i++) { float acc = 0; for (int k = 0; k < 6; k++) acc += j[k * 6 + i] * v[k]; P.u_task[i] = acc; }   // J^T (Lambda w)
+    osc_real w[6], v[6];
+    for (int i = 0; i < 6; i++) w[i] = (osc_real)kp * dpose[i] - kd * eef_vel[i];
+    for (int i = 0; i < 6; i++) { osc_real acc = 0; for (int k = 0; k < 6; k++) acc += m_eef[i * 6 + k] * w[k]; v[i] = acc; }
+    for (int i = 0; i < 6; i++) { osc_real acc = 0; for (int k = 0; k < 6; k++) acc += j[k * 6 + i] * v[k]; P.u_task[i] = (float)acc; }   // J^T (Lambda w)
     mm6(m_eef, j, t);
     mm6(t, mm_inv, j_eef_inv);
     mm6(j, j_eef_inv, t, true, false);                  // J^T j_eef_inv
-    for (int i = 0; i < 36; i++) t[i] = ((i / 6 == i % 6) ? 1.0f : 0.0f) - t[i];
-    mm6(t, mm, P.N);
+    for (int i = 0; i < 36; i++) t[i] = ((i / 6 == i % 6) ? 1.0 : 0.0) - t[i];
+    mm6(t, mm, t);
+    for (int i = 0; i < 36; i++) P.N[i] = (float)t[i];
 }
 B2G_HD inline void osc_apply(const OscPrepared& P, const float* q, const float* qd, float kp_null, const float* effort, float* u) {
     const float kdn = 2.0f * sqrtf(kp_null);

@@ -393,10 +393,14 @@ def terrain_post_physics(st, cfg, draws):
     return obs.astype(f), rew.astype(f), reset.astype(np.int64), timeout, measured, extras
 
 
-def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp=150.0, kp_null=10.0, effort=1000.0):
-    """tasks/useful_hound.py:660-691 (_compute_osc_torques): operational-space control of the 6-DOF arm.  ``mm`` (N,6,6) arm block of the
-    mass matrix, ``j_eef`` (N,6,6) the Jacobian slice the task takes, ``dpose`` (N,6), ``eef_vel`` (N,6), ``q``/``qd`` (N,6)."""
-    f = np.float32
+def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp=150.0, kp_null=10.0, effort=1000.0, exact=False):
+    """tasks/useful_hound.py:660-691 / tasks/hound_arm.py:462-493 (_compute_osc_torques): operational-space control of the 6-DOF arm.
+    ``mm`` (N,6,6) arm block of the mass matrix, ``j_eef`` (N,6,6) the Jacobian slice the task takes, ``dpose`` (N,6), ``eef_vel`` (N,6),
+    ``q``/``qd`` (N,6).  ``exact=False`` mimics the reference's float32 evaluation (float32 products around accurately inverted matrices);
+    ``exact=True`` evaluates the whole law in float64 -- what the kernels do, because J M^-1 J^T is too ill-conditioned for float32 on
+    these arms (see tests/kernel_checks.check_houndarm_step)."""
+    f = np.float64 if exact else np.float32
+    mm, j_eef, dpose, eef_vel, q, qd = (np.asarray(x).astype(f) for x in (mm, j_eef, dpose, eef_vel, q, qd))
     kp_v = np.full(6, kp, f)
     kd_v = (f(2) * np.sqrt(kp_v)).astype(f)
     kpn = np.full(6, kp_null, f)
@@ -410,4 +414,4 @@ def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp=150.0, kp_null=10.0, effort
     u_null = kdn * -qd + kpn * (np.mod(f(0.0) - q + f(np.pi), f(2 * np.pi)) - f(np.pi))      # python-style remainder (eager torch %)
     u_null = mm @ u_null[..., None]
     u = u + (np.eye(6, dtype=f)[None] - jt @ j_eef_inv) @ u_null
-    return np.clip(u[..., 0], -effort, effort).astype(f)
+    return np.clip(u[..., 0], -effort, effort).astype(np.float32)

@@ -980,21 +980,21 @@ def check_houndarm_step(make_backend, n=12, steps=40, seed=23):
             eef = houndarm_eef(art, r64, d64, c.eef_body)
             dpose = a * np.array([0.1, 0.1, 0.1, 0.5, 0.5, 0.5], np.float32) / np.float32(1.0)
             u = tm.osc_torques(MM[:, :6, :6].astype(np.float32), J[:, c.jac_body - 1, :, :6].astype(np.float32), dpose.astype(np.float32),
-                               eef[:, 7:].astype(np.float32), d64[:, :6, 0].astype(np.float32), d64[:, :6, 1].astype(np.float32), 150.0, 10.0, effort[:6])
+                               eef[:, 7:].astype(np.float32), d64[:, :6, 0].astype(np.float32), d64[:, :6, 1].astype(np.float32), 150.0, 10.0, effort[:6], exact=True)
             # --- kernel ---
             be.task_step(actions, draws)
             rk, dk = be.get_state()
             t = be.get_task()
             # the operational-space torques.  The law inverts J M^-1 J^T, whose condition number on this arm (last link 19 g: mass
-            # matrix 2e4, Jacobian 70-10000) is 4e6 ... 3e10 along a rollout -- ANY float32 evaluation, the reference's torch.inverse
-            # included, is off by eps x cond there (a numpy float32 evaluation deviates from float64 as much as the kernel does;
-            # measured).  So the torques are compared statistically where the problem is at least moderately conditioned (< 3e7;
-            # asserted after the loop), and the oracle is advanced with the kernel's torques so that the dynamics comparison below stays a
-            # dynamics comparison.  The law itself is pinned tightly on well-conditioned inputs (tests/test_hound_arm.py, golden).
+            # matrix 2e4, Jacobian 70-10000) is 4e6 ... 3e10 along a rollout.  A float32 evaluation -- the reference's torch.inverse
+            # included -- is off by eps x cond there (measured: percent-level to total), which is why the kernels evaluate the law
+            # in float64 (b2g_threads.cuh osc_prepare) and why the comparison is against the float64 restatement: agreement to
+            # ~1e-6 of the largest torque wherever the problem is not outright singular (< 1e10), asserted after the loop.  The
+            # oracle is advanced with the kernel's torques so that the dynamics comparison below stays a dynamics comparison.
             uk = t["dof_force"]
             jj = J[:, c.jac_body - 1, :, :6].astype(np.float64)
             cond = np.array([np.linalg.cond(jj[e] @ np.linalg.inv(MM[e, :6, :6].astype(np.float64)) @ jj[e].T) for e in range(n)])
-            ok = cond < 3e7
+            ok = cond < 1e10
             checked_torques += int(ok.sum())
             if ok.any():
                 torque_dev.extend((np.abs(uk[ok] - u[ok]).max(axis=1) / np.maximum(1.0, np.abs(u[ok]).max(axis=1))).tolist())
@@ -1038,7 +1038,7 @@ def check_houndarm_step(make_backend, n=12, steps=40, seed=23):
         be.close()
         jm.close()
     assert resets > 0 and timeouts > 0, "test must exercise resets and time-outs"
-    assert checked_torques > steps * n // 4, "too few moderately conditioned samples for the torque comparison"
+    assert checked_torques > steps * n * 3 // 4, "too few non-singular samples for the torque comparison"
     td = np.array(torque_dev)
-    assert np.median(td) < 2e-3 and np.quantile(td, 0.9) < 3e-2 and td.max() < 0.5, \
+    assert np.median(td) < 1e-5 and np.quantile(td, 0.9) < 1e-4 and td.max() < 1e-2, \
         f"OSC torque deviation (relative to the env's largest torque): median {np.median(td):.2e}, q90 {np.quantile(td, 0.9):.2e}, max {td.max():.2e}"

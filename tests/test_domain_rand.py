@@ -166,8 +166,12 @@ def test_anymal_with_domain_randomisation_on_gpu(fused):
         op, rp_, dp, _ = plain.step(a)
         assert torch.isfinite(o["obs"]).all() and torch.isfinite(r).all()
     sc = env._dr.env_scale
-    assert ((sc[:, :3] > 0.45) & (sc[:, :3] < 1.55)).all() and sc[:, :3].std(0).min() > 0.1
-    assert env._dr.num_applied() > n, "resets after `frequency` steps must re-randomise"
+    assert ((sc[:, :3] > 0.45) & (sc[:, :3] < 1.55)).all()
+    # the construction-time pass happens at frame 0, where the linear schedule still gives scale 1; the environments that were
+    # reset after `frequency` steps carry fresh draws
+    redrawn = (sc[:, 1:3] != 1.0).any(dim=1)
+    assert int(redrawn.sum()) >= 8 and sc[redrawn][:, 1:3].std(0).min() > 0.1, (int(redrawn.sum()), sc[redrawn][:, 1:3].std(0))
+    assert env._dr.num_applied() >= n + int(redrawn.sum()), "environments reset after `frequency` steps are re-randomised (possibly more than once)"
     assert "observations" in env.dr_randomizations and "actions" in env.dr_randomizations
     g = env.gym.get_sim_params(env.sim).gravity
     assert abs(g.z + 9.81) < 3.0 and (abs(g.x) > 1e-4 or abs(g.y) > 1e-4)
