@@ -210,7 +210,7 @@ def run_ours(args):
     warm_ms = e0.elapsed_time(e1)
     # ---- end to end: pinned host actions in, obs/rew/reset/time-outs out, through the C-ABI host call ----
     h_act = [p.cpu().pin_memory() for p in pool]
-    # result buffers carved from ONE pinned allocation in the layout the library asks for (one D2H copy per step)
+    # result buffers carved from ONE pinned allocation in the layout the library asks for
     offs, tot = (C.c_int64 * 4)(), C.c_int64()
     _lib.check(lib.b2g_task_host_layout(env.sim.handle, offs, C.byref(tot)), "host_layout")
     h_arena = torch.empty(tot.value, dtype=torch.uint8).pin_memory()
@@ -268,8 +268,10 @@ def run_ours(args):
                 "value_warm_l2": total / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / args.steps,
                 "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * na * 4,
                         "d2h_bytes_per_step": n * env.num_obs * 4 + n * 4 + n * 8 + n * 8, "ms_per_step": e2e_ms / args.steps,
-                        "path": "b2g_task_step_host (C ABI): pinned host actions (read in place by the kernel over PCIe) -> obs/rew/reset/time_outs in pinned host memory "
-                                "(one packed D2H copy, b2g_task_host_layout), stream sync per step"},
+                        "path": "b2g_task_step_host (C ABI), one blocking call per step: pinned host actions (read in place by the kernel over PCIe) -> "
+                                "obs/rew/reset/time_outs stored by the SMs into the caller's pinned buffer (b2g_task_host_layout; tail of the fused "
+                                "step kernel for the flat tasks, k_mirror_host otherwise), completion by a published sequence word the host polls"
+                                + (" [B2G_HOST_MIRROR=0: copy-engine D2H + stream sync]" if os.environ.get("B2G_HOST_MIRROR", "1")[:1] == "0" else "")},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "kernel": kernel_name, "peak_source": peak_src,

@@ -78,6 +78,66 @@ __device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int&
     bf = smem + kBlock * MAXC * CF_COUNT + eib * nb * 3;
 }
 
+// ---- host mirror (b2g_task_step_host): the step's outputs (obs_clamped | rew | reset | timeout, the b2g_task_host_layout arena)
+// are stored straight into the caller's page-locked buffer by the SMs and a sequence number is published last, so the host
+// neither queues a copy command nor waits on the stream: it polls one word of host memory.
+struct HostMirror {
+    unsigned char* dst = nullptr;         // device alias of the caller's pinned buffer (null = no mirror)
+    const unsigned char* src = nullptr;   // the device arena
+    unsigned long long off[4] = {0, 0, 0, 0};
+    int num_obs = 0;
+    unsigned* done_ctr = nullptr;         // device: blocks that have finished their stores
+    unsigned* flag = nullptr;             // device alias of the pinned sequence word
+    unsigned seq = 0;
+};
+
+// coalesced copy of `bytes` (multiple of 4) by the whole block; 16-byte units when both ends allow it.  Loads bypass L1
+// (the data was written by other threads of this block, or by a previous kernel).
+__device__ __forceinline__ void mirror_span(unsigned char* dst, const unsigned char* src, size_t bytes) {
+    if ((((size_t)dst | (size_t)src | bytes) & 15) == 0) {
+        for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x)
+            reinterpret_cast<uint4*>(dst)[i] = __ldcg(reinterpret_cast<const uint4*>(src) + i);
+    } else {
+        for (size_t i = threadIdx.x; i < bytes / 4; i += blockDim.x)
+            reinterpret_cast<unsigned*>(dst)[i] = __ldcg(reinterpret_cast<const unsigned*>(src) + i);
+    }
+}
+
+// every thread fences its own host stores; the block that arrives last publishes the sequence number
+__device__ __forceinline__ void mirror_publish(const HostMirror& H) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(H.done_ctr, 1u);
+        if (prev == gridDim.x - 1) {
+            *H.done_ctr = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(H.flag) = H.seq;
+        }
+    }
+}
+
+// tail of a fused step kernel: this block's environments [e0, e0 + cnt) go to the host as soon as the block is done, so the
+// PCIe transfer overlaps the blocks that are still computing
+__device__ __forceinline__ void mirror_block(const HostMirror& H, int e0, int cnt) {
+    __syncthreads();   // the block's own global stores are visible to all its threads
+    if (cnt > 0) {
+        const size_t ob = (size_t)H.num_obs * 4;
+        mirror_span(H.dst + H.off[0] + e0 * ob, H.src + H.off[0] + e0 * ob, cnt * ob);
+        mirror_span(H.dst + H.off[1] + (size_t)e0 * 4, H.src + H.off[1] + (size_t)e0 * 4, (size_t)cnt * 4);
+        mirror_span(H.dst + H.off[2] + (size_t)e0 * 8, H.src + H.off[2] + (size_t)e0 * 8, (size_t)cnt * 8);
+        mirror_span(H.dst + H.off[3] + (size_t)e0 * 8, H.src + H.off[3] + (size_t)e0 * 8, (size_t)cnt * 8);
+    }
+    mirror_publish(H);
+}
+
+// stand-alone mirror for the step kernels that do not carry the tail: whole arena, grid-stride
+__global__ void __launch_bounds__(256) k_mirror_host(HostMirror H, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(H.dst)[i] = __ldcg(reinterpret_cast<const uint4*>(H.src) + i);
+    mirror_publish(H);
+}
+
 template <int LANES, int NL, bool FIXED, bool HF>
 __global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
     extern __shared__ float smem[];
@@ -90,11 +150,16 @@ __global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
 // latency per warp, the 4096-env headline), 6 = 168 registers with a few spills (3 warps per sub-partition) for grids that
 // exceed one wave of the uncapped variant
 template <int LANES, int NL, bool HF, int MINB = 1>
-__global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArgs T) {
+__global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArgs T, HostMirror H) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
     anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
+    if (H.dst) {
+        constexpr int EPB = kBlock / LANES;
+        const int e0 = blockIdx.x * EPB, left = A.n_envs - e0;
+        mirror_block(H, e0, left < EPB ? left : EPB);
+    }
 }
 
 __global__ void __launch_bounds__(kBlock) k_houndarm_step(SimArgs A, TaskArgs T) {
@@ -293,6 +358,10 @@ struct b2g_sim {
     // single device-to-host copy when the caller's buffers follow the same layout (b2g_task_host_layout)
     unsigned char* out_arena = nullptr;
     size_t out_off[4] = {0, 0, 0, 0}, out_total = 0;
+    unsigned* host_flag = nullptr;      // page-locked sequence word the mirror kernels publish (b2g_task_step_host)
+    unsigned* host_flag_dev = nullptr;  // its device alias
+    unsigned* done_ctr = nullptr;       // device: finished-block counter of the mirror
+    unsigned host_seq = 0;
     int use_rand_override = 0;
     int64_t launches = 0;
 };
@@ -420,7 +489,7 @@ int launch_simulate(b2g_sim* s, cudaStream_t st) {
     return B2G_OK;
 }
 
-int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, int post_only = 0) {
+int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, int post_only = 0, const HostMirror* hm = nullptr) {
     const SimArgs A = make_args(s);
     const TaskArgs T = make_task_args(s, actions_dev, post_only);
     const int grid = grid_size(s);
@@ -472,12 +541,13 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         CUDA_TRY(cudaGetLastError());
         return B2G_OK;
     }
+    const HostMirror H = hm ? *hm : HostMirror{};     // flat tasks: the mirror is the kernel's own tail
     if (s->v.lanes == 4) {
-        if (s->has_hf) k_anymal_step<4, 3, true><<<grid, kBlock, sm, st>>>(A, T);
-        else if (grid > 4 * s->n_sm) k_anymal_step<4, 3, false, 6><<<grid, kBlock, sm, st>>>(A, T);     // more than one wave: occupancy build
-        else k_anymal_step<4, 3, false><<<grid, kBlock, sm, st>>>(A, T);
+        if (s->has_hf) k_anymal_step<4, 3, true><<<grid, kBlock, sm, st>>>(A, T, H);
+        else if (grid > 4 * s->n_sm) k_anymal_step<4, 3, false, 6><<<grid, kBlock, sm, st>>>(A, T, H);     // more than one wave: occupancy build
+        else k_anymal_step<4, 3, false><<<grid, kBlock, sm, st>>>(A, T, H);
     }
-    else { if (s->has_hf) k_anymal_step<8, 6, true><<<grid, kBlock, sm, st>>>(A, T); else k_anymal_step<8, 6, false><<<grid, kBlock, sm, st>>>(A, T); }
+    else { if (s->has_hf) k_anymal_step<8, 6, true><<<grid, kBlock, sm, st>>>(A, T, H); else k_anymal_step<8, 6, false><<<grid, kBlock, sm, st>>>(A, T, H); }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2G_OK;
@@ -533,8 +603,9 @@ int b2g_sim_destroy(b2g_sim* s) {
                         s->progress, s->reset_count, s->actions_in, s->torques, s->last_actions, s->last_dof_vel,
                         s->feet_air_time, s->episode_sums, s->env_origins, s->terrain_origins, s->scratch9, s->resetw, s->report, s->measured,
                         s->noise_override, s->push_override, s->extras, s->terrain_levels, s->terrain_types, s->height_samples,
-                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands, s->step_ctr};
+                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands, s->step_ctr, s->done_ctr};
         for (void* p : ptrs) if (p) cudaFree(p);
+        if (s->host_flag) cudaFreeHost(s->host_flag);
         return 0;
     });
     delete s;
@@ -776,6 +847,11 @@ static int alloc_task_buffers(b2g_sim* s, int num_obs, int num_act, int n_draws)
         CUDA_TRY(cudaMalloc(&s->commands, sizeof(float) * n * 4));
         CUDA_TRY(cudaMalloc(&s->actions, sizeof(float) * n * num_act));
         CUDA_TRY(cudaMalloc(&s->actions_in, sizeof(float) * n * num_act));
+        CUDA_TRY(cudaMalloc(&s->done_ctr, sizeof(unsigned)));
+        CUDA_TRY(cudaMemset(s->done_ctr, 0, sizeof(unsigned)));
+        CUDA_TRY(cudaHostAlloc(&s->host_flag, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        *s->host_flag = 0;
+        CUDA_TRY(cudaHostGetDevicePointer(&s->host_flag_dev, s->host_flag, 0));
         CUDA_TRY(cudaMalloc(&s->rand_override, sizeof(float) * n * n_draws));
         CUDA_TRY(cudaMalloc(&s->progress, sizeof(long long) * n));
         CUDA_TRY(cudaMalloc(&s->reset_count, sizeof(int) * n));
@@ -1044,14 +1120,56 @@ int b2g_task_anymal_step_host(b2g_sim* s, const float* actions_host, float* obs_
             cudaGetLastError();
             CUDA_TRY(cudaMemcpyAsync(s->actions_in, actions_host, sizeof(float) * n * nd, cudaMemcpyHostToDevice, st));
         }
-        const int rc = launch_anymal_step(s, actions_dev, st);
-        if (rc != B2G_OK) return rc;
         const unsigned char* base = reinterpret_cast<const unsigned char*>(obs_host);
         const bool packed = obs_host && rew_host && reset_host && timeout_host &&
                             reinterpret_cast<const unsigned char*>(rew_host) == base + s->out_off[1] &&
                             reinterpret_cast<const unsigned char*>(reset_host) == base + s->out_off[2] &&
                             reinterpret_cast<const unsigned char*>(timeout_host) == base + s->out_off[3];
-        if (packed) {   // the caller's buffers follow b2g_task_host_layout: one copy
+        // packed page-locked outputs (b2g_task_host_layout): the SMs store the results into the caller's buffer and publish a
+        // sequence number; no copy command, no stream synchronisation
+        HostMirror H;
+        static const bool mirror_on = !(getenv("B2G_HOST_MIRROR") && getenv("B2G_HOST_MIRROR")[0] == '0');   // =0: copy-engine path (A/B timing)
+        if (mirror_on && packed && cudaPointerGetAttributes(&pa, obs_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+            (reinterpret_cast<size_t>(pa.devicePointer) & 15) == 0) {
+            H.dst = static_cast<unsigned char*>(pa.devicePointer);
+            H.src = s->out_arena;
+            for (int i = 0; i < 4; i++) H.off[i] = s->out_off[i];
+            H.num_obs = s->num_obs;
+            H.done_ctr = s->done_ctr;
+            H.flag = s->host_flag_dev;
+            H.seq = ++s->host_seq;
+            if (H.seq == 0) H.seq = ++s->host_seq;     // 0 is the initial value of the word
+        } else {
+            cudaGetLastError();
+        }
+        const bool fused_tail = H.dst && s->task_kind == 1;
+        const int rc = launch_anymal_step(s, actions_dev, st, 0, fused_tail ? &H : nullptr);
+        if (rc != B2G_OK) return rc;
+        if (H.dst) {
+            if (!fused_tail) {
+                const size_t n16 = (s->out_off[3] + sizeof(long long) * n + 15) / 16;     // the arena is padded to 256 B
+                const int blocks = (int)((n16 + 255) / 256);
+                k_mirror_host<<<blocks < 2 * s->n_sm ? blocks : 2 * s->n_sm, 256, 0, st>>>(H, n16);
+                s->launches++;
+                CUDA_TRY(cudaGetLastError());
+            }
+            volatile unsigned* flag = s->host_flag;
+            for (unsigned spin = 1; *flag != H.seq; spin++) {
+                if ((spin & 0xFFFFu) == 0) {      // a failed launch / device fault never publishes: ask the stream now and then
+                    const cudaError_t q = cudaStreamQuery(st);
+                    if (q == cudaSuccess) {
+                        if (*flag == H.seq) break;
+                        CUDA_TRY(cudaStreamSynchronize(st));
+                        if (*flag != H.seq) return fail(B2G_ERR_CUDA, "step_host: the stream drained without publishing the results");
+                        break;
+                    }
+                    if (q != cudaErrorNotReady) return fail(B2G_ERR_CUDA, "step_host: %s", cudaGetErrorString(q));
+                }
+            }
+            __sync_synchronize();
+            return (int)B2G_OK;
+        }
+        if (packed) {   // pageable packed buffers: one copy
             CUDA_TRY(cudaMemcpyAsync(obs_host, s->out_arena, s->out_off[3] + sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
         } else {
             if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, s->obs_clamped, sizeof(float) * n * s->num_obs, cudaMemcpyDeviceToHost, st));

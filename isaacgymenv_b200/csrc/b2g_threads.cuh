@@ -733,7 +733,8 @@ B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, in
 }
 
 // kernel 1: pre_physics_step (decimation loop) + extra sim step + post_physics_step up to and including the reward
-template <int LANES, int NL, bool HF>
+// ARM = false compiles the operational-space arm law out (quadruped-only robots: no float64 code, no OSC stack frame)
+template <int LANES, int NL, bool HF, bool ARM = (NL >= 6)>
 B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, int env, int lane, bool valid, ScratchStrided sc, float* bf) {
     const DevModel* M = A.M;
     const b2g_terrain_cfg& C = T.cfg;
@@ -758,7 +759,7 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
             lqd[j] = T.last_dof_vel[k];
         }
     }
-    const bool is_arm = (C.arm_chain >= 0) && (lane == C.arm_chain);
+    const bool is_arm = ARM && (C.arm_chain >= 0) && (lane == C.arm_chain);
     // arm lane: OSC torque from the stored mass-matrix / Jacobian slices, the end-effector velocity row and the live arm DOFs
     OscPrepared osc;
     if (is_arm) {

@@ -205,11 +205,15 @@ def test_generic_jacobian_and_mass_matrix_agree_with_the_fused_arm_slices():
     torch.testing.assert_close(mm[alive][:, -6:, -6:], env._mm[alive], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("task,nact", [("Anymal", 12), ("Cartpole", 1), ("AnymalTerrain", 12)])
-def test_step_host_matches_device_step(task, nact):
+@pytest.mark.parametrize("task,nact,n", [("Anymal", 12, 128), ("Anymal", 12, 101), ("Hound", 12, 37), ("Cartpole", 1, 128), ("Cartpole", 1, 77),
+                                         ("AnymalTerrain", 12, 128), ("Houndarm", 6, 50)])
+def test_step_host_matches_device_step(task, nact, n):
     """b2g_task_step_host (the host-buffer entry the end-to-end benchmark times) against the device-pointer step on a twin
-    sim: (a) page-locked buffers in the packed b2g_task_host_layout (zero-copy actions, one D2H copy), (b) pageable numpy
-    buffers laid out separately (staged actions, one copy per result) -- all three bit-identical."""
+    sim: (a) page-locked buffers in the packed b2g_task_host_layout (zero-copy actions; the SMs store the results into the
+    caller's buffer -- as the tail of the fused flat-task kernel, or by k_mirror_host -- and the call returns when the published
+    sequence number arrives, without a stream synchronisation: the buffer is snapshotted right after the call returns),
+    (b) pageable numpy buffers laid out separately (staged actions, one copy per result) -- all three bit-identical.  Ragged
+    environment counts exercise the partial last block of the mirror."""
     import ctypes as C
 
     import torch
@@ -218,7 +222,6 @@ def test_step_host_matches_device_step(task, nact):
     from isaacgymenv_b200 import _lib
 
     lib = _lib.load()
-    n = 128
     over = {"env": {"terrain": {"terrainType": "plane"}}} if task == "AnymalTerrain" else None
     envs = []
     for _ in range(3):
@@ -248,15 +251,21 @@ def test_step_host_matches_device_step(task, nact):
         o, r, d, ex = envs[0].step(act.cuda())
         _lib.check(lib.b2g_task_step_host(envs[1].sim.handle, C.c_void_p(a_pin.data_ptr()), C.c_void_p(p_obs.data_ptr()), C.c_void_p(p_rew.data_ptr()),
                                           C.c_void_p(p_rs.data_ptr()), C.c_void_p(p_to.data_ptr()), sp), "step_host packed")
+        snap = arena.clone()        # no synchronisation in between: the call itself must have waited for the results
+        s_obs = snap[offs[0]:offs[0] + n * nobs * 4].view(torch.float32).view(n, nobs)
+        s_rew = snap[offs[1]:offs[1] + n * 4].view(torch.float32)
+        s_rs = snap[offs[2]:offs[2] + n * 8].view(torch.int64)
+        s_to = snap[offs[3]:offs[3] + n * 8].view(torch.int64)
         _lib.check(lib.b2g_task_step_host(envs[2].sim.handle, a_np.ctypes.data_as(C.c_void_p), q_obs.ctypes.data_as(C.c_void_p),
                                           q_rew.ctypes.data_as(C.c_void_p), q_rs.ctypes.data_as(C.c_void_p), q_to.ctypes.data_as(C.c_void_p), sp),
                    "step_host pageable")
         torch.cuda.synchronize()
         assert torch.equal(o["obs"].cpu(), torch.from_numpy(q_obs)), ("pageable", it, (o["obs"].cpu() - torch.from_numpy(q_obs)).abs().max(0))
-        assert torch.equal(o["obs"].cpu(), p_obs), ("packed", it, (o["obs"].cpu() - p_obs).abs().max(0))
-        assert torch.equal(r.cpu(), p_rew) and torch.equal(r.cpu(), torch.from_numpy(q_rew))
-        assert torch.equal(d.cpu().long(), p_rs) and torch.equal(d.cpu().long(), torch.from_numpy(q_rs))
-        assert torch.equal(ex["time_outs"].cpu().long(), p_to) and torch.equal(ex["time_outs"].cpu().long(), torch.from_numpy(q_to))
+        assert torch.equal(o["obs"].cpu(), s_obs), ("packed", it, (o["obs"].cpu() - s_obs).abs().max(0))
+        assert torch.equal(o["obs"].cpu(), p_obs)
+        assert torch.equal(r.cpu(), s_rew) and torch.equal(r.cpu(), torch.from_numpy(q_rew))
+        assert torch.equal(d.cpu().long(), s_rs) and torch.equal(d.cpu().long(), torch.from_numpy(q_rs))
+        assert torch.equal(ex["time_outs"].cpu().long(), s_to) and torch.equal(ex["time_outs"].cpu().long(), torch.from_numpy(q_to))
 
 
 @pytest.mark.parametrize("task,nact", [("AnymalTerrain", 12), ("UsefulHound", 18)])
