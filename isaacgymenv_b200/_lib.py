@@ -10,7 +10,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200gym.so")
+# B2G_LIB_PATH: development switch for A/B timing of experimental builds (tools/build_variant.sh)
+LIB_PATH = os.environ.get("B2G_LIB_PATH") or os.path.join(_HERE, "lib", "libb200gym.so")
 _lib = None
 
 

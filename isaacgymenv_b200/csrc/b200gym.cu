@@ -18,7 +18,17 @@ using namespace b2g;
 
 namespace {
 
-constexpr int kBlock = 64;
+#ifndef B2G_BLOCK
+#define B2G_BLOCK 64
+#endif
+constexpr int kBlock = B2G_BLOCK;
+// experiment switch: B2G_SPARSE = 2 leaves the upper half of every warp idle (half as many environments per warp, twice as
+// many warps): less divergence per warp, a second warp per scheduler at the 4096-env headline
+#ifndef B2G_SPARSE
+#define B2G_SPARSE 1
+#endif
+constexpr int kSparse = B2G_SPARSE;
+template <int LANES> struct EnvsPerBlock { static constexpr int value = (kBlock / 32) * (32 / LANES / kSparse); };
 
 thread_local char g_err[512] = "";
 
@@ -67,15 +77,17 @@ Variant pick_variant(const b2g_model& m) {
 template <int LANES>
 __device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int& env, int& lane, bool& valid, ScratchStrided& sc, float*& bf) {
     const int tid = threadIdx.x;
-    constexpr int EPB = kBlock / LANES;
-    const int eib = tid / LANES;
+    constexpr int EPW = 32 / LANES / kSparse, EPB = EnvsPerBlock<LANES>::value;
+    const int wl = tid & 31;
+    const bool live = wl < EPW * LANES;
+    const int eib = (tid >> 5) * EPW + (live ? wl / LANES : 0);
     lane = tid % LANES;
     const int e = blockIdx.x * EPB + eib;
-    valid = e < n_envs;
-    env = valid ? e : n_envs - 1;
+    valid = live && e < n_envs;
+    env = (e < n_envs) ? e : n_envs - 1;
     sc.base = smem + tid;
     sc.stride = kBlock;
-    bf = smem + kBlock * MAXC * CF_COUNT + eib * nb * 3;
+    bf = smem + kBlock * MAXC * CF_COUNT + (tid / LANES) * nb * 3;     // one accumulator per lane group, idle groups included
 }
 
 // ---- host mirror (b2g_task_step_host): the step's outputs (obs_clamped | rew | reset | timeout, the b2g_task_host_layout arena)
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArg
     thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
     anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
     if (H.dst) {
-        constexpr int EPB = kBlock / LANES;
+        constexpr int EPB = EnvsPerBlock<LANES>::value;
         const int e0 = blockIdx.x * EPB, left = A.n_envs - e0;
         mirror_block(H, e0, left < EPB ? left : EPB);
     }
@@ -202,11 +214,12 @@ __global__ void __launch_bounds__(kBlock) k_terrain_post(SimArgs A, TerrainArgs 
         cnorm = sqrtf(red[0]);
     }
     const int tid = threadIdx.x;
-    constexpr int EPB = kBlock / LANES;
-    const int lane = tid % LANES;
-    const int e = blockIdx.x * EPB + tid / LANES;
-    const bool valid = e < A.n_envs;
-    terrain_post_thread<LANES, NL>(A, T, valid ? e : A.n_envs - 1, lane, valid, cnorm);
+    constexpr int EPW = 32 / LANES / kSparse, EPB = EnvsPerBlock<LANES>::value;
+    const int lane = tid % LANES, wl = tid & 31;
+    const bool live = wl < EPW * LANES;
+    const int e = blockIdx.x * EPB + (tid >> 5) * EPW + (live ? wl / LANES : 0);
+    const bool valid = live && e < A.n_envs;
+    terrain_post_thread<LANES, NL>(A, T, e < A.n_envs ? e : A.n_envs - 1, lane, valid, cnorm);
 }
 
 // extras["episode"] (anymal_terrain.py:420-425): means over the envs that reset this step; one block, fixed order
@@ -374,7 +387,7 @@ size_t smem_bytes(const b2g_sim* s) {
 }
 
 int grid_size(const b2g_sim* s) {
-    const int epb = kBlock / s->v.lanes;
+    const int epb = (kBlock / 32) * (32 / s->v.lanes / kSparse);
     return (s->n_envs + epb - 1) / epb;
 }
 
@@ -528,7 +541,7 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         return B2G_OK;
     }
     if (s->task_kind == 4) {     // one thread per environment whatever the generic kernels' lane count is
-        const int g1 = (s->n_envs + kBlock - 1) / kBlock;
+        const int g1 = (s->n_envs + kBlock / kSparse - 1) / (kBlock / kSparse);
         const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3);
         k_houndarm_step<<<g1, kBlock, sm1, st>>>(A, T);
         s->launches++;
