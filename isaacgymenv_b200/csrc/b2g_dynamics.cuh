@@ -21,12 +21,15 @@
 namespace b2g {
 
 constexpr int MAXC = B2G_MAX_CONTACTS_PER_CHAIN;
-// per-link loops of the recursions: fully unrolled (link state in registers).  -DB2G_ROLL_LINKS keeps them rolled (link state
-// in local memory, ~1/3 of the code) -- an experiment switch, see DESIGN.md "code size"
-#ifdef B2G_ROLL_LINKS
+// per-link loops of the recursions: fully unrolled for the 3-link legs (link state in registers: 41 vs 49 us per Anymal step),
+// rolled for the long-chain variant (NL = 6: the unrolled kernel is 360 KB of SASS and spends 45 % of its stall cycles waiting for
+// instructions; rolled, with the link state in local memory, it is 1/3 of the code and 13 % faster -- measured)
+#if defined(B2G_ROLL_LINKS)
 #define B2G_LINK_UNROLL _Pragma("unroll 1")
-#else
+#elif defined(B2G_UNROLL_LINKS)
 #define B2G_LINK_UNROLL _Pragma("unroll")
+#else
+#define B2G_LINK_UNROLL _Pragma("unroll (NL <= 3 ? NL : 1)")
 #endif
 
 // per-thread scratch for the (dynamically indexed) contact slots
