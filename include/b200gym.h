@@ -344,15 +344,18 @@ int b2g_task_anymal_post_only(b2g_sim* sim, const float* actions_dev, void* stre
 /* use_rand_override != 0: reset draws come from the RAND_OVERRIDE tensor instead of Philox */
 int b2g_task_set_rand_override(b2g_sim* sim, int use_rand_override);
 
-/* host-buffer convenience used by the end-to-end benchmark and non-torch callers: copies actions
- * H2D, steps, copies obs/rew/reset/timeout D2H, synchronises the stream. */
+/* host-buffer entry used by the end-to-end benchmark and non-torch callers: blocking, returns when the results are in the
+ * caller's buffers.  Page-locked action buffers are read by the kernel in place, pageable ones are staged with one H2D copy.
+ * Page-locked result buffers in the packed b2g_task_host_layout are written by the SMs themselves (tail of the fused step
+ * kernel for the flat tasks, k_mirror_host otherwise) and the call returns when the published sequence word arrives -- no
+ * copy command, no stream synchronisation; any other buffers are served with D2H copies + cudaStreamSynchronize.
+ * Environment switch B2G_HOST_MIRROR=0 forces the copy path (A/B timing). */
 int b2g_task_anymal_step_host(b2g_sim* sim, const float* actions_host, float* obs_host, float* rew_host,
                               int64_t* reset_host, int64_t* timeout_host, void* stream);
 
-/* Host-buffer layout that makes b2g_task_step_host return everything with ONE device-to-host copy: byte offsets of
- * obs, rew, reset and time-outs inside a single (page-locked) host allocation of total_bytes; pass obs_host = base +
- * offsets[0], rew_host = base + offsets[1], ... Buffers laid out differently are served with one copy each. Page-locked
- * action buffers are read by the kernel in place, pageable ones are staged. */
+/* Host-buffer layout of the fast path of b2g_task_step_host: byte offsets of obs, rew, reset and time-outs inside a single
+ * page-locked host allocation of total_bytes (16-byte aligned); pass obs_host = base + offsets[0], rew_host = base +
+ * offsets[1], ... (pageable memory in this layout: one D2H copy; buffers laid out differently: one copy each). */
 int b2g_task_host_layout(const b2g_sim* sim, int64_t* offsets /*[4]*/, int64_t* total_bytes);
 
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */

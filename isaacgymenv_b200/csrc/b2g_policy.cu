@@ -78,6 +78,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
     __trap();
 }
+// accumulator-ready wait of the epilogue warps: ONE lane per warp polls (with a short back-off), the others park at the warp
+// barrier -- 256 threads spinning on try_wait starve the single thread that is issuing copies and MMAs next to them
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t done = 0;
+        for (uint32_t spin = 0; spin < (1u << 22); spin++) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
+            if (done) break;
+            __nanosleep(40);
+        }
+        if (!done) __trap();
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
@@ -336,7 +356,8 @@ k_policy_forward(PolicyDims d, const uint8_t* __restrict__ wpack, const float* _
                 tc_fence_after();
                 issue_layer(tmem_base, tcol[l], a_addr, smem_u32(smem + offs[l]), width[l], depth[l], bar_mma);
             }
-            mbar_wait(bar_mma, phase);
+            __syncwarp();      // lanes 1-31 of the issuing warp park here instead of spinning on the barrier next to lane 0
+            mbar_wait_warp(bar_mma, phase);
             phase ^= 1;
             tc_fence_after();
             if (l < 3) {
@@ -371,12 +392,285 @@ k_policy_forward(PolicyDims d, const uint8_t* __restrict__ wpack, const float* _
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// wide variant: networks whose weights do not fit in shared memory next to one activation tile (the rough-terrain policies,
+// units [512,256,128], 188 / 204 observations: cfg/train/AnymalTerrainPPO.yaml, UsefulHoundPPO.yaml).  Same tile, same MMA /
+// epilogue scheme; what changes is where the operands live:
+//   * the weights STREAM: one chunk = one K=16 slice of at most 256 output rows (<= 8 KB, two bulk copies), brought into a ring
+//     of kStages shared-memory stages by the TMA engine; full[s] counts the bytes in, empty[s] is armed by tcgen05.commit when the
+//     MMA that read stage s has retired.  One elected thread issues both the copies and the MMAs; the copies run kStages-1 chunks
+//     ahead in a fixed per-tile order (a table built by the host), across layer boundaries -- the next layer's first slices arrive
+//     under the current layer's epilogue;
+//   * two activation buffers ping-pong: Y = observations, then layer-2 output; X = layer-1 output, then layer-3 output;
+//   * a first layer wider than 256 is produced in ONE accumulator (all 512 tensor-memory columns) but handed to layer 2 in two
+//     halves through the 64 KB X buffer: epilogue of columns 0..n1/2 -> layer-2 MMAs over the first n1/2 of K -> epilogue of the
+//     other half -> layer-2 MMAs over the rest (accumulating).  Layer 2's accumulator reuses the columns the first half freed.
+struct WideDims {
+    int k0, k0p, n1, n2, n3, n_act, head_n;
+    int parts1;               // 1 or 2: column halves of layer 1
+    int off_x, off_y, off_ring, off_bias, off_norm, off_bar, total;
+    int stages, stage_bytes, n_chunks;
+};
+
+constexpr int kMaxStages = 12;
+
+
+// The ring is driven by ONE thread, so its bookkeeping is kept to adds and compares: no division, no 64-bit arithmetic (a
+// first version that derived stage and chunk from running counters with / and % spent ~0.5 us per chunk in that scalar code).
+// Chunk order of a tile = the order k_policy_forward_wide consumes them: layer 1 (K slices outer, column halves inner), layer 2,
+// layer 3, heads.  wpack holds the four matrices back to back in the canonical operand layout (k_pack_layer).
+struct WideRing {
+    uint32_t ring_addr, full0, empty0;     // shared addresses: ring base, full[0], empty[0] (consecutive 8-byte barriers)
+    uint32_t stages, stage_bytes;
+    const uint8_t* wpack;
+    // per segment (layer): chunks, byte offset of the matrix, bytes per 8-column slab of the whole matrix, bytes per slab of a chunk
+    uint32_t seg_cnt[4], seg_base[4], seg_pitch[4], seg_bytes[4];
+    uint32_t parts1;
+    // loader cursor
+    uint32_t tiles_left, ld_seg, ld_idx, ld_stage, ld_lap;
+    // consumer cursor
+    uint32_t cs_stage, cs_lap;
+    __device__ __forceinline__ void init(const WideDims& d, uint32_t my_tiles) {
+        const uint32_t h1 = d.n1 / d.parts1;
+        parts1 = d.parts1;
+        seg_cnt[0] = (d.k0p / 16) * d.parts1; seg_base[0] = 0; seg_pitch[0] = d.n1 * 16; seg_bytes[0] = h1 * 16;
+        seg_cnt[1] = d.n1 / 16; seg_base[1] = d.n1 * d.k0p * 2; seg_pitch[1] = d.n2 * 16; seg_bytes[1] = d.n2 * 16;
+        seg_cnt[2] = d.n2 / 16; seg_base[2] = seg_base[1] + d.n2 * d.n1 * 2; seg_pitch[2] = d.n3 * 16; seg_bytes[2] = d.n3 * 16;
+        seg_cnt[3] = d.n3 / 16; seg_base[3] = seg_base[2] + d.n3 * d.n2 * 2; seg_pitch[3] = d.head_n * 16; seg_bytes[3] = d.head_n * 16;
+        tiles_left = my_tiles; ld_seg = 0; ld_idx = 0; ld_stage = 0; ld_lap = 0; cs_stage = 0; cs_lap = 0;
+    }
+    __device__ __forceinline__ void load_next() {
+        if (tiles_left == 0) return;
+        if (ld_lap > 0) mbar_wait(empty0 + 8u * ld_stage, (ld_lap - 1) & 1);
+        uint32_t cnt, base, pitch, bytes;
+        // explicit selection keeps the four-entry tables in registers
+        if (ld_seg == 0) { cnt = seg_cnt[0]; base = seg_base[0]; pitch = seg_pitch[0]; bytes = seg_bytes[0]; }
+        else if (ld_seg == 1) { cnt = seg_cnt[1]; base = seg_base[1]; pitch = seg_pitch[1]; bytes = seg_bytes[1]; }
+        else if (ld_seg == 2) { cnt = seg_cnt[2]; base = seg_base[2]; pitch = seg_pitch[2]; bytes = seg_bytes[2]; }
+        else { cnt = seg_cnt[3]; base = seg_base[3]; pitch = seg_pitch[3]; bytes = seg_bytes[3]; }
+        uint32_t k16 = ld_idx, r0 = 0;
+        if (ld_seg == 0 && parts1 == 2) { k16 = ld_idx >> 1; r0 = (ld_idx & 1) * bytes; }
+        const uint32_t off0 = base + 2u * k16 * pitch + r0;
+        const uint32_t dst = ring_addr + ld_stage * stage_bytes, bar = full0 + 8u * ld_stage;
+        mbar_expect_tx(bar, 2u * bytes);
+        bulk_g2s(dst, wpack + off0, bytes, bar);
+        bulk_g2s(dst + bytes, wpack + off0 + pitch, bytes, bar);
+        if (++ld_idx == cnt) {
+            ld_idx = 0;
+            if (++ld_seg == 4) { ld_seg = 0; tiles_left--; }
+        }
+        if (++ld_stage == stages) { ld_stage = 0; ld_lap++; }
+    }
+    // one MMA: D[128 x n] (+)= A[128 x 16] (shared, k-slab pair at a_slice) . chunk^T
+    __device__ __forceinline__ void consume(uint32_t tmem_d, uint32_t a_slice, int n, uint32_t accumulate) {
+        mbar_wait(full0 + 8u * cs_stage, cs_lap & 1);
+        tc_fence_after();
+        const uint64_t ad = smem_desc(a_slice, kTileM * 16, 128);
+        const uint64_t bd = smem_desc(ring_addr + cs_stage * stage_bytes, (uint32_t)n * 16, 128);
+        umma_bf16(tmem_d, ad, bd, instr_desc(n), accumulate);
+        umma_commit(empty0 + 8u * cs_stage);
+        if (++cs_stage == stages) { cs_stage = 0; cs_lap++; }
+    }
+};
+
+// observation tile -> normalise -> bf16 A operand, any width (k0 % 4 == 0 and a 16-byte aligned base take float4 loads).
+// Four 4-column groups per thread and pass, all loads issued before the first use.
+__device__ __forceinline__ void obs_stage_wide(const float* __restrict__ obs, int row_base, int n_rows, int k0, int k0p, const float* norm_s,
+                                               float clip, int tid, uint8_t* a_smem, bool vec) {
+    const int q = k0p >> 2;                         // 4-column groups per (padded) row
+    const float inv = 1.0f / (float)q;              // idx < 2^13, q <= 64: (idx + 0.5) * inv truncates to idx / q exactly
+    const int total = kTileM * q;
+    for (int base = 0; base < total; base += 4 * kThreads) {
+        float x[4][4];
+        int rr[4], kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base + u * kThreads + tid;
+            const int r = __float2int_rz(((float)idx + 0.5f) * inv), k = (idx - r * q) * 4;
+            rr[u] = r; kk[u] = k;
+#pragma unroll
+            for (int j = 0; j < 4; j++) x[u][j] = 0.f;
+            if (idx < total && row_base + r < n_rows) {
+                const float* src = obs + (size_t)(row_base + r) * k0 + k;
+                if (vec && k + 3 < k0) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                    x[u][0] = v.x; x[u][1] = v.y; x[u][2] = v.z; x[u][3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (k + j < k0) x[u][j] = __ldg(src + j);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base + u * kThreads + tid, r = rr[u], k = kk[u];
+            if (idx < total) {
+                float y[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    y[j] = (k + j < k0 && row_base + r < n_rows) ? fminf(fmaxf((x[u][j] - norm_s[k + j]) * norm_s[k0 + k + j], -clip), clip) : 0.f;
+                *reinterpret_cast<uint2*>(a_smem + (size_t)(k >> 3) * (kTileM * 16) + r * 16 + (k & 7) * 2) =
+                    make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads + 32, 1)
+k_policy_forward_wide(WideDims d, const uint8_t* __restrict__ wpack, const float* __restrict__ bias_g,
+                      const float* __restrict__ norm_g, float clip, const float* __restrict__ obs, int n_rows, float* __restrict__ mu,
+                      float* __restrict__ value, int obs_aligned) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTileM - 1), half = tid >> 7;
+    float* bias_s = reinterpret_cast<float*>(smem + d.off_bias);
+    float* norm_s = reinterpret_cast<float*>(smem + d.off_norm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + d.off_bar);      // full[kMaxStages], empty[kMaxStages], mma
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+    const uint32_t bar_mma = smem_u32(&bars[2 * kMaxStages]);
+    uint8_t* x_smem = smem + d.off_x;
+    uint8_t* y_smem = smem + d.off_y;
+    const uint32_t x_addr = smem_u32(x_smem), y_addr = smem_u32(y_smem);
+    const int n_tiles = (n_rows + kTileM - 1) / kTileM;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const bool vec = obs_aligned && (d.k0 & 3) == 0;
+
+    WideRing ring;
+    ring.ring_addr = smem_u32(smem + d.off_ring);
+    ring.full0 = smem_u32(&bars[0]);
+    ring.empty0 = smem_u32(&bars[kMaxStages]);
+    ring.stages = (uint32_t)d.stages; ring.stage_bytes = (uint32_t)d.stage_bytes;
+    ring.wpack = wpack;
+    ring.init(d, (uint32_t)my_tiles);
+
+    if (tid == 0) {
+        for (int l = 0; l < 2 * kMaxStages + 1; l++) mbar_init(smem_u32(&bars[l]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const int n_bias = d.n1 + d.n2 + d.n3 + d.head_n;
+    for (int i = tid; i < n_bias; i += kThreads) bias_s[i] = bias_g[i];
+    for (int i = tid; i < 2 * d.k0; i += kThreads) norm_s[i] = norm_g[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kThreads / 32) {
+        // producer warp: lane 0 streams every chunk of every tile of this CTA through the ring, paced only by the empty barriers
+        if ((tid & 31) == 0)
+            while (ring.tiles_left) ring.load_next();
+        __syncwarp();
+        __syncthreads();      // teardown barrier (the epilogue warps synchronise among themselves on named barrier 1 until then)
+        return;
+    }
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float* bias1 = bias_s;
+    const float* bias2 = bias_s + d.n1;
+    const float* bias3 = bias_s + d.n1 + d.n2;
+    const float* biash = bias_s + d.n1 + d.n2 + d.n3;
+    const int h1 = d.n1 / d.parts1;       // columns of layer 1 handed to layer 2 at a time
+    uint32_t phase = 0;
+    // every phase below: [A operand complete] -> barrier -> thread 0 issues the MMAs of the phase -> all wait for the accumulator
+    auto phase_begin = [&]() {
+        fence_async_smem();
+        tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    auto phase_wait = [&]() {
+        mbar_wait_warp(bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+    };
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row_base = tile * kTileM;
+        obs_stage_wide(obs, row_base, n_rows, d.k0, d.k0p, norm_s, clip, tid, y_smem, vec);
+        // ---- layer 1: A = Y (observations), D = columns [0, n1) ----
+        phase_begin();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int k16 = 0; k16 < d.k0p / 16; k16++)
+                for (int p = 0; p < d.parts1; p++)
+                    ring.consume(tmem_base + (uint32_t)(p * h1), y_addr + (uint32_t)k16 * 2u * (kTileM * 16), h1, k16 > 0 ? 1u : 0u);
+            umma_commit(bar_mma);
+        }
+        __syncwarp();      // lanes 1-31 of the issuing warp park here instead of spinning on the barrier next to lane 0
+        phase_wait();
+        // ---- layer 2 in parts1 passes: epilogue of one column half of layer 1 -> X, then the MMAs over that part of K ----
+        for (int p = 0; p < d.parts1; p++) {
+            epilogue_hidden(tmem_row, p * h1, h1, bias1 + p * h1, x_smem, row, half);
+            phase_begin();
+            if (tid == 0) {
+                tc_fence_after();
+                // the second pass accumulates; the accumulator lives in columns [0, n2): freed by the first half's epilogue
+                for (int k16 = 0; k16 < h1 / 16; k16++)
+                    ring.consume(tmem_base, x_addr + (uint32_t)k16 * 2u * (kTileM * 16), d.n2, (p > 0 || k16 > 0) ? 1u : 0u);
+                umma_commit(bar_mma);
+            }
+            __syncwarp();
+            phase_wait();
+        }
+        // ---- layer 3: A = Y (layer-2 output), D = columns [256, 256 + n3) ----
+        epilogue_hidden(tmem_row, 0, d.n2, bias2, y_smem, row, half);
+        phase_begin();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int k16 = 0; k16 < d.n2 / 16; k16++)
+                ring.consume(tmem_base + 256u, y_addr + (uint32_t)k16 * 2u * (kTileM * 16), d.n3, k16 > 0 ? 1u : 0u);
+            umma_commit(bar_mma);
+        }
+        __syncwarp();      // lanes 1-31 of the issuing warp park here instead of spinning on the barrier next to lane 0
+        phase_wait();
+        // ---- heads: A = X (layer-3 output), D = columns [0, head_n) ----
+        epilogue_hidden(tmem_row, 256, d.n3, bias3, x_smem, row, half);
+        phase_begin();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int k16 = 0; k16 < d.n3 / 16; k16++)
+                ring.consume(tmem_base, x_addr + (uint32_t)k16 * 2u * (kTileM * 16), d.head_n, k16 > 0 ? 1u : 0u);
+            umma_commit(bar_mma);
+        }
+        __syncwarp();      // lanes 1-31 of the issuing warp park here instead of spinning on the barrier next to lane 0
+        phase_wait();
+        if (half == 0) {
+            const int grow = row_base + row;
+            for (int c = 0; c < d.head_n; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_row + (uint32_t)c, r);
+                if (grow < n_rows) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float o = __uint_as_float(r[i]) + biash[c + i];
+                        if (c + i < d.n_act) mu[(size_t)grow * d.n_act + c + i] = o;
+                        else if (c + i == d.n_act) value[grow] = o;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");    // both activation buffers and every accumulator column are free for the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
 struct b2g_policy {
     int device = 0;
+    bool wide = false;            // streamed-weights kernel (k_policy_forward_wide)
+    int head_n = kHeadN;          // mu + value columns, padded to a multiple of 16
+    WideDims wd{};
     PolicyDims d{};
     uint8_t* wpack = nullptr;     // the four packed weight matrices, back to back
     float* bias = nullptr;        // n1 + n2 + n3 + 16
@@ -392,16 +686,19 @@ int b2g_policy_create(int device, int n_obs, const int* units, int n_actions, b2
     if (!out || !units) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_create: null argument");
     *out = nullptr;
     if (n_obs < 1 || n_actions < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_create: n_obs and n_actions must be positive");
-    for (int i = 0; i < 3; i++)
-        if (units[i] < 16 || units[i] > 256 || units[i] % 16)
-            return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: hidden widths must be multiples of 16 in [16,256] (three layers)");
-    if (n_actions + 1 > kHeadN) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: n_actions + 1 must be <= 16");
-    if (units[0] + units[1] + units[2] + kHeadN > kTmemCols)
-        return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: accumulators exceed the 512 tensor-memory columns");
+    for (int i = 0; i < 3; i++) {
+        const int lim = i == 0 ? 512 : 256;
+        if (units[i] < 16 || units[i] > lim || units[i] % 16 || (units[i] > 256 && units[i] % 32))
+            return b2g::fail_msg(B2G_ERR_UNSUPPORTED,
+                                 "b2g_policy_create: three hidden layers, widths multiples of 16: first in [16,512] (multiple of 32 above 256), others in [16,256]");
+    }
+    if (n_actions + 1 > 32) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: n_actions + 1 must be <= 32");
+    if (n_obs > 256) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: n_obs must be <= 256");
     CUDA_TRY_P(cudaSetDevice(device));
     b2g_policy* p = new (std::nothrow) b2g_policy();
     if (!p) return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_create: out of memory");
     p->device = device;
+    p->head_n = round_up(n_actions + 1, 16);
     PolicyDims& d = p->d;
     d.k0 = n_obs;
     d.k0p = round_up(n_obs, 16);
@@ -412,7 +709,7 @@ int b2g_policy_create(int device, int n_obs, const int* units, int n_actions, b2
     d.w_bytes[0] = d.n1 * d.k0p * 2;
     d.w_bytes[1] = d.n2 * d.n1 * 2;
     d.w_bytes[2] = d.n3 * d.n2 * 2;
-    d.w_bytes[3] = kHeadN * d.n3 * 2;
+    d.w_bytes[3] = p->head_n * d.n3 * 2;
     int off = 0;
     d.off_w1 = off; off += round_up(d.w_bytes[0], 128);
     d.off_w2 = off; off += round_up(d.w_bytes[1], 128);
@@ -423,24 +720,48 @@ int b2g_policy_create(int device, int n_obs, const int* units, int n_actions, b2
     kmax = d.n2 > kmax ? d.n2 : kmax;
     kmax = d.n3 > kmax ? d.n3 : kmax;
     d.off_a = off; off += kTileM * kmax * 2;
-    d.off_bias = off; off += round_up((d.n1 + d.n2 + d.n3 + kHeadN) * 4, 16);
+    d.off_bias = off; off += round_up((d.n1 + d.n2 + d.n3 + p->head_n) * 4, 16);
     d.off_norm = off; off += round_up(2 * d.k0 * 4, 16);
     d.off_bar = off; off += 64;
     d.total = off;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (d.total > max_smem) {
-        delete p;
-        return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: weights + one activation tile do not fit in shared memory");
+    // resident-weight kernel when everything fits (weights + one activation tile in shared memory, all accumulators side by side in
+    // tensor memory, 16-column head); otherwise the weights stream (k_policy_forward_wide)
+    p->wide = d.total > max_smem || d.n1 > 256 || p->head_n != kHeadN || d.n1 + d.n2 + d.n3 + kHeadN > kTmemCols;
+    if (p->wide) {
+        WideDims& w = p->wd;
+        w.k0 = d.k0; w.k0p = d.k0p; w.n1 = d.n1; w.n2 = d.n2; w.n3 = d.n3; w.n_act = d.n_act; w.head_n = p->head_n;
+        w.parts1 = d.n1 > 256 ? 2 : 1;
+        const int h1 = d.n1 / w.parts1;
+        auto mx = [](int a, int b) { return a > b ? a : b; };
+        w.stage_bytes = 2 * 16 * mx(mx(h1, d.n2), mx(d.n3, p->head_n));
+        int o = 0;
+        w.off_x = o; o += kTileM * 2 * mx(h1, d.n3);
+        w.off_y = o; o += kTileM * 2 * mx(d.k0p, d.n2);
+        w.off_bias = o; o += round_up((d.n1 + d.n2 + d.n3 + p->head_n) * 4, 16);
+        w.off_norm = o; o += round_up(2 * d.k0 * 4, 16);
+        w.off_bar = o; o += 256;
+        o = round_up(o, 128);
+        w.off_ring = o;
+        w.stages = (max_smem - o) / w.stage_bytes;
+        if (w.stages > kMaxStages) w.stages = kMaxStages;
+        if (w.stages < 3) {
+            delete p;
+            return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_policy_create: activation tiles leave no room for the weight ring in shared memory");
+        }
+        w.total = o + w.stages * w.stage_bytes;
+        w.n_chunks = (d.k0p / 16) * w.parts1 + d.n1 / 16 + d.n2 / 16 + d.n3 / 16;
     }
     const size_t wtot = (size_t)d.w_bytes[0] + d.w_bytes[1] + d.w_bytes[2] + d.w_bytes[3];
     cudaError_t e = cudaMalloc(&p->wpack, wtot);
-    if (e == cudaSuccess) e = cudaMalloc(&p->bias, (size_t)(d.n1 + d.n2 + d.n3 + kHeadN) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->bias, (size_t)(d.n1 + d.n2 + d.n3 + p->head_n) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->norm, (size_t)2 * d.k0 * 4);
     if (e == cudaSuccess) e = cudaMemset(p->wpack, 0, wtot);
-    if (e == cudaSuccess) e = cudaMemset(p->bias, 0, (size_t)(d.n1 + d.n2 + d.n3 + kHeadN) * 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_policy_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, d.total);
+    if (e == cudaSuccess) e = cudaMemset(p->bias, 0, (size_t)(d.n1 + d.n2 + d.n3 + p->head_n) * 4);
+    if (e == cudaSuccess && !p->wide) e = cudaFuncSetAttribute(k_policy_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, d.total);
+    if (e == cudaSuccess && p->wide) e = cudaFuncSetAttribute(k_policy_forward_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, p->wd.total);
     if (e == cudaSuccess) {
         k_pack_norm<<<(d.k0 + 127) / 128, 128>>>(nullptr, nullptr, 0.f, d.k0, p->norm);   // identity normalisation
         e = cudaDeviceSynchronize();
@@ -474,11 +795,11 @@ int b2g_policy_set_layer(b2g_policy* p, int layer, const float* W_dev, const flo
         case B2G_POLICY_HIDDEN0: rows = d.n1; cols = d.k0; np = d.n1; slot = 0; break;
         case B2G_POLICY_HIDDEN1: rows = d.n2; cols = d.n1; np = d.n2; slot = 1; break;
         case B2G_POLICY_HIDDEN2: rows = d.n3; cols = d.n2; np = d.n3; slot = 2; break;
-        case B2G_POLICY_MU: rows = d.n_act; cols = d.n3; np = kHeadN; slot = 3; break;
-        case B2G_POLICY_VALUE: rows = 1; cols = d.n3; np = kHeadN; slot = 3; row0 = d.n_act; break;
+        case B2G_POLICY_MU: rows = d.n_act; cols = d.n3; np = p->head_n; slot = 3; break;
+        case B2G_POLICY_VALUE: rows = 1; cols = d.n3; np = p->head_n; slot = 3; row0 = d.n_act; break;
         default: return b2g::fail_msg(B2G_ERR_ARG, "b2g_policy_set_layer: layer must be one of B2G_POLICY_*");
     }
-    const int nb[4] = {d.n1, d.n2, d.n3, kHeadN};
+    const int nb[4] = {d.n1, d.n2, d.n3, p->head_n};
     for (int l = 0; l < slot; l++) {
         woff += (size_t)d.w_bytes[l];
         boff += (size_t)nb[l];
@@ -509,9 +830,13 @@ int b2g_policy_forward(b2g_policy* p, const float* obs_dev, int n_rows, float* m
     CUDA_TRY_P(cudaSetDevice(p->device));
     const int n_tiles = (n_rows + kTileM - 1) / kTileM;
     const int grid = n_tiles < p->n_sm ? n_tiles : p->n_sm;
-    k_policy_forward<<<grid, kThreads, p->d.total, (cudaStream_t)stream>>>(p->d, p->wpack, p->bias, p->norm, p->clip, obs_dev, n_rows,
-                                                                          mu_dev, value_dev,
-                                                                          (reinterpret_cast<uintptr_t>(obs_dev) & 15) == 0 ? 1 : 0);
+    const int aligned = (reinterpret_cast<uintptr_t>(obs_dev) & 15) == 0 ? 1 : 0;
+    if (p->wide)
+        k_policy_forward_wide<<<grid, kThreads + 32, p->wd.total, (cudaStream_t)stream>>>(p->wd, p->wpack, p->bias, p->norm, p->clip, obs_dev,
+                                                                                   n_rows, mu_dev, value_dev, aligned);
+    else
+        k_policy_forward<<<grid, kThreads, p->d.total, (cudaStream_t)stream>>>(p->d, p->wpack, p->bias, p->norm, p->clip, obs_dev, n_rows, mu_dev,
+                                                                              value_dev, aligned);
     CUDA_TRY_P(cudaGetLastError());
     p->launches++;
     return B2G_OK;

@@ -9,7 +9,7 @@
 ``key=value`` overrides as in Hydra; dotted keys reach into the task / train yaml (``task.env.learn.pushInterval_s=8``,
 ``train.params.config.horizon_length=16``).  Hyper-parameters come from ``cfg/train/<Task>PPO.yaml`` (the reference's files with
 the interpolations resolved); the learner is the in-repo PPO (``learning/ppo.py``) instead of rl_games, which is not installed.
-Extra switches of this repo: ``cuda_graphs=True`` (default), ``fused_rollout=True`` (tcgen05 policy kernel, [256,128,64] nets).
+Extra switches of this repo: ``cuda_graphs=True`` (default), ``fused_rollout=True`` (tcgen05 policy kernel: resident weights for [256,128,64], streamed weights for [512,256,128]).
 Checkpoints go to ``runs/<experiment or task>/nn/<name>.pth`` (rl_games' layout, ``docs/rl_examples.md``)."""
 from __future__ import annotations
 
@@ -109,7 +109,7 @@ def main(argv=None):
                                 overrides=task_over or None)
     cfg = ppo_config_from_train_cfg(tc, top["max_iterations"] if top["max_iterations"] != "" else None)
     cfg.tf32 = bool(top["tf32"])
-    fused = bool(top["fused_rollout"]) and len(cfg.units) == 3 and max(cfg.units) <= 256
+    fused = bool(top["fused_rollout"]) and len(cfg.units) == 3 and cfg.units[0] <= 512 and max(cfg.units[1:]) <= 256
     graphs = bool(top["cuda_graphs"]) and not getattr(env, "needs_host_sync", False)
     ppo = PPO(env, cfg, multi_gpu=multi, seed=int(top["seed"]) + info.rank, fused_rollout=fused, cuda_graphs=graphs)
     name = top["experiment"] or tc["params"]["config"]["name"]

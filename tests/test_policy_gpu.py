@@ -45,6 +45,14 @@ def _ref(model, obs, mean, var, eps, clip, emulate_bf16):
     (48, 12, (256, 128, 64), 148 * 128 * 2 + 77),   # more tiles than SMs: the persistent tile loop
     (4, 1, (32, 32, 16), 512),           # narrow network, padded K
     (37, 15, (64, 256, 32), 1000),       # odd observation width, widest middle layer, full head
+    # streamed-weights kernel (k_policy_forward_wide): the rough-terrain networks of cfg/train/AnymalTerrainPPO.yaml / UsefulHoundPPO.yaml
+    (188, 12, (512, 256, 128), 4096),    # AnymalTerrain / HoundTerrain
+    (204, 18, (512, 256, 128), 4096),    # UsefulHound: 19 head columns -> 32-column head
+    (204, 18, (512, 256, 128), 1),
+    (188, 12, (512, 256, 128), 148 * 128 + 131),   # a second tile on some CTAs, ragged last tile: the ring runs across tiles
+    (203, 18, (512, 256, 128), 300),     # observation width not a multiple of 4: scalar loads
+    (48, 20, (256, 128, 64), 700),       # narrow network with a 32-column head: streamed path, single column part
+    (250, 31, (320, 48, 16), 257),       # 160-column halves, tiny tail layers, widest supported head
 ])
 def test_policy_forward_matches_torch(num_obs, num_act, units, rows):
     from isaacgymenv_b200.learning.fused_policy import FusedPolicy
@@ -71,6 +79,9 @@ def test_policy_forward_matches_torch(num_obs, num_act, units, rows):
     assert (mu - mu_f).abs().max().item() < 5e-2
     assert (v - v_f).abs().max().item() < 5e-2
     assert pol.launches == 7
+    # the same call again (weights and ring barriers start from scratch in every launch): bit-identical
+    mu2, v2 = pol.forward(obs)
+    assert torch.equal(mu, mu2) and torch.equal(v, v2)
 
 
 def test_policy_identity_norm_and_sync():
@@ -112,8 +123,12 @@ def test_policy_rejects_unsupported_shapes():
     from isaacgymenv_b200.learning.fused_policy import FusedPolicy
 
     with pytest.raises(_lib.B2GError):
-        FusedPolicy(188, 12, (512, 256, 128), "cuda:0")      # rough-terrain network: too wide for the resident-weight kernel
+        FusedPolicy(188, 12, (1024, 256, 128), "cuda:0")     # first layer beyond the 512 accumulator columns
     with pytest.raises(_lib.B2GError):
-        FusedPolicy(48, 16, (256, 128, 64), "cuda:0")
+        FusedPolicy(188, 12, (512, 512, 128), "cuda:0")
+    with pytest.raises(_lib.B2GError):
+        FusedPolicy(48, 32, (256, 128, 64), "cuda:0")        # 33 head columns
+    with pytest.raises(_lib.B2GError):
+        FusedPolicy(300, 12, (256, 128, 64), "cuda:0")
     with pytest.raises(_lib.B2GError):
         FusedPolicy(48, 12, (250, 128, 64), "cuda:0")

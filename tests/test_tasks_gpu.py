@@ -329,3 +329,51 @@ def test_large_batch_occupancy_variant_is_bit_identical():
         resets += int(ds.sum())
     assert resets > 0
     assert torch.equal(big.root_states[:64], small.root_states) and torch.equal(big.dof_state.view(16384, -1)[:64], small.dof_state.view(64, -1))
+
+
+@pytest.mark.parametrize("task,n", [("Anymal", 4096), ("Anymal", 8192), ("Hound", 4096)])
+def test_full_size_batch_properties(task, n):
+    """BASELINE.json's full sizes (4096 and 8192 envs per GPU), through properties that do not need a per-env CPU run:
+    (a) environments are independent: the first 512 environments of the full batch follow, bit for bit, the trajectory of a
+        512-env sim given the same seed and the same actions (resets, Philox draws keyed by env index included);
+    (b) at every checked step the observation, reward and reset buffers equal the oracle's restatement of the reference's
+        compute_*_observations / compute_*_reward (tasks/anymal.py:311-386) evaluated on the sim's own state tensors for ALL
+        environments: 1e-5 relative for floats, masks bit-exact;
+    (c) time-outs: timeout_buf == (progress >= max_len - 1) & reset (vec_task.py:394)."""
+    import torch
+
+    import isaacgymenv_b200 as b2g
+    from oracle import task_math as tm
+
+    small = 512
+    big = b2g.make(seed=3, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True)
+    ref = b2g.make(seed=3, task=task, num_envs=small, sim_device="cuda:0", rl_device="cuda:0", headless=True)
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    total_resets = 0
+    for k in range(40):
+        a = 2 * torch.rand(n, 12, device="cuda:0", generator=g) - 1
+        ob, rb, db, eb = big.step(a)
+        os_, rs, ds, es = ref.step(a[:small].contiguous())
+        total_resets += int(db.sum())
+        assert torch.equal(ob["obs"][:small], os_["obs"]) and torch.equal(rb[:small], rs) and torch.equal(db[:small], ds), f"step {k}: prefix differs"
+        assert torch.equal(big.root_states[:small], ref.root_states) and torch.equal(big.dof_state.view(n, -1)[:small], ref.dof_state.view(small, -1))
+        if k % 8 == 7:
+            root = big.root_states.cpu().numpy()
+            dof = big.dof_state.view(n, -1, 2).cpu().numpy()
+            cmd = big.commands.cpu().numpy()
+            obs = tm.compute_anymal_observations(root, cmd, dof[..., 0], big.default_dof_pos.cpu().numpy(), dof[..., 1],
+                                                 np.tile(np.array([[0.0, 0.0, -1.0]], np.float32), (n, 1)), big.actions.cpu().numpy(),
+                                                 big.lin_vel_scale, big.ang_vel_scale, big.dof_pos_scale, big.dof_vel_scale)
+            np.testing.assert_allclose(big.obs_buf.cpu().numpy(), obs, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(ob["obs"].cpu().numpy(), np.clip(obs, -big.clip_obs, big.clip_obs), rtol=1e-5, atol=1e-5)
+            rew, reset = tm.compute_anymal_reward(root, cmd, big.torques.cpu().numpy(), big.contact_forces.cpu().numpy(),
+                                                  big.knee_indices.cpu().numpy(), big.progress_buf.cpu().numpy(), big.rew_scales,
+                                                  int(big.base_index), big.max_episode_length)
+            np.testing.assert_allclose(rb.cpu().numpy(), rew, rtol=1e-5, atol=1e-7)
+            # contact-force norms within 1e-4 of the 1 N threshold may legitimately fall either side of it
+            f = big.contact_forces.cpu().numpy()
+            near = (np.abs(np.linalg.norm(f, axis=2) - 1.0) < 1e-4).any(axis=1)
+            assert np.array_equal(db.cpu().numpy()[~near] != 0, reset[~near]) and int(near.sum()) < 8
+            to = (big.progress_buf >= big.max_episode_length - 1) & (db != 0)
+            assert torch.equal(eb["time_outs"] != 0, to)
+    assert total_resets > 100, "random actions must make robots fall and reset at this size too"

@@ -16,6 +16,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, nargs="+", default=[4096, 32768, 98304])
     ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--net", default="anymal", choices=["anymal", "terrain", "usefulhound"],
+                    help="anymal: 48->[256,128,64]->12 (resident weights); terrain: 188->[512,256,128]->12, usefulhound: 204->[512,256,128]->18 (streamed weights)")
     args = ap.parse_args()
     import torch
 
@@ -23,7 +25,7 @@ def main():
     from isaacgymenv_b200.learning.ppo import ActorCritic, RunningMeanStd
 
     dev = "cuda:0"
-    units, n_obs, n_act = (256, 128, 64), 48, 12
+    units, n_obs, n_act = {"anymal": ((256, 128, 64), 48, 12), "terrain": ((512, 256, 128), 188, 12), "usefulhound": ((512, 256, 128), 204, 18)}[args.net]
     torch.manual_seed(0)
     model = ActorCritic(n_obs, n_act, units).to(dev)
     rms = RunningMeanStd((n_obs,)).to(dev)
