@@ -377,9 +377,12 @@ int b2g_dlpack_from_desc(const b2g_tensor_desc* desc, void** out_managed);
  * evaluated once per VecTask.step for every environment. One fused tcgen05 kernel: bf16 operands, fp32 accumulation
  * in tensor memory, activations stay in shared memory between layers. Weights are given in nn.Linear layout
  * (out x in, row-major fp32, device memory) and packed once per update.
- * Limits (B2G_ERR_UNSUPPORTED otherwise): exactly three hidden layers, widths multiples of 16 in [16,256],
- * n_actions <= 15, weights + one 128-row activation tile must fit in shared memory (units [256,128,64] do;
- * the rough-terrain [512,256,128] network does not).
+ * Two kernels behind the same calls: when all weights + one 128-row activation tile fit in shared memory (units
+ * [256,128,64], cfg/train/AnymalPPO.yaml) they stay resident for every tile of a CTA; otherwise (the rough-terrain
+ * networks, units [512,256,128], cfg/train/AnymalTerrainPPO.yaml / UsefulHoundPPO.yaml) they stream through a
+ * shared-memory ring fed by the TMA engine.
+ * Limits (B2G_ERR_UNSUPPORTED otherwise): exactly three hidden layers, widths multiples of 16; first layer <= 512
+ * (a multiple of 32 above 256), the others <= 256; n_obs <= 256; n_actions <= 31.
  * --------------------------------------------------------------------------------------------------------------- */
 typedef struct b2g_policy b2g_policy;
 enum b2g_policy_layer { B2G_POLICY_HIDDEN0 = 0, B2G_POLICY_HIDDEN1 = 1, B2G_POLICY_HIDDEN2 = 2, B2G_POLICY_MU = 3, B2G_POLICY_VALUE = 4 };
