@@ -75,7 +75,7 @@ Variant pick_variant(const b2g_model& m) {
 // kernels
 // ------------------------------------------------------------------------------------------------
 template <int LANES>
-__device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int& env, int& lane, bool& valid, ScratchStrided& sc, float*& bf) {
+__device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int& env, int& lane, bool& valid, ScratchStrided& sc, float*& bf, int nd = 0) {
     const int tid = threadIdx.x;
     constexpr int EPW = 32 / LANES / kSparse, EPB = EnvsPerBlock<LANES>::value;
     const int wl = tid & 31;
@@ -88,6 +88,8 @@ __device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int&
     sc.base = smem + tid;
     sc.stride = kBlock;
     bf = smem + kBlock * MAXC * CF_COUNT + (tid / LANES) * nb * 3;     // one accumulator per lane group, idle groups included
+    // link store of the rolled long-chain variants (b2g_dynamics.cuh::links_in_shared): one LinkData per DOF per lane group
+    sc.links = smem + kBlock * MAXC * CF_COUNT + (kBlock / LANES) * nb * 3 + link_store_floats(tid / LANES, nd);
 }
 
 // ---- host mirror (b2g_task_step_host): the step's outputs (obs_clamped | rew | reset | timeout, the b2g_task_host_layout arena)
@@ -154,7 +156,7 @@ template <int LANES, int NL, bool FIXED, bool HF>
 __global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, valid, sc, bf);
 }
 
@@ -165,7 +167,7 @@ template <int LANES, int NL, bool HF, int MINB = 1>
 __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArgs T, HostMirror H) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
     if (H.dst) {
         constexpr int EPB = EnvsPerBlock<LANES>::value;
@@ -177,86 +179,100 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArg
 __global__ void __launch_bounds__(kBlock) k_houndarm_step(SimArgs A, TaskArgs T) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     houndarm_step_thread(A, T, env, valid, sc, bf);
 }
 
 __global__ void __launch_bounds__(kBlock) k_cartpole_step(SimArgs A, TaskArgs T) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     cartpole_step_thread(A, T, env, valid, sc, bf);
+}
+
+// Grid-wide "who finishes last": every thread's global writes are fenced, one thread per block takes a ticket; returns true
+// (block-uniformly) in the block that arrived last, with the counter already re-armed for the next launch.
+__device__ __forceinline__ bool last_block_arrives(unsigned* ticket) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *ticket = 0u;
+    }
+    __syncthreads();
+    const bool r = is_last != 0;
+    if (r) __threadfence();
+    return r;
 }
 
 template <int LANES, int NL, bool HF>
 __global__ void __launch_bounds__(kBlock) k_terrain_phys(SimArgs A, TerrainArgs T) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     terrain_phys_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
+    // curriculum scalar for ALL resetting envs (reference quirk: torch.norm without dim, anymal_terrain.py:432): the last
+    // block to arrive sums the N values in a fixed order (kBlock strided partial sums, pairwise tree) -> deterministic
+    if (T.cnorm && T.cfg.custom_origins && T.cfg.curriculum && T.init_done) {
+        __shared__ float red[kBlock];
+        if (last_block_arrives(T.tickets + 0)) {
+            float acc = 0.0f;
+            for (int i = threadIdx.x; i < A.n_envs; i += kBlock) acc += __ldcg(T.resetw + i);
+            red[threadIdx.x] = acc;
+            __syncthreads();
+            for (int o = kBlock / 2; o > 0; o >>= 1) {
+                if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) *T.cnorm = sqrtf(red[0]);
+        }
+    }
 }
 
+// 16 threads per environment (kPostSub), 16 environments per block
+constexpr int kPostSub = 16, kPostBlock = 256, kPostEnvs = kPostBlock / kPostSub;
 template <int LANES, int NL>
-__global__ void __launch_bounds__(kBlock) k_terrain_post(SimArgs A, TerrainArgs T) {
-    __shared__ float red[kBlock];
-    float cnorm = 0.0f;
-    if (T.cfg.custom_origins && T.cfg.curriculum && T.init_done) {
-        // one scalar for ALL resetting envs (reference quirk: torch.norm without dim, anymal_terrain.py:432); every block
-        // sums the same N values in the same order -> identical, deterministic result everywhere
-        float acc = 0.0f;
-        for (int i = threadIdx.x; i < A.n_envs; i += kBlock) acc += T.resetw[i];
-        red[threadIdx.x] = acc;
-        __syncthreads();
-        for (int o = kBlock / 2; o > 0; o >>= 1) {
-            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-            __syncthreads();
-        }
-        cnorm = sqrtf(red[0]);
-    }
+__global__ void __launch_bounds__(kPostBlock) k_terrain_post(SimArgs A, TerrainArgs T) {
+    static_assert(LANES <= kPostSub, "chain lanes are the first sub-threads of an environment");
+    // one scalar for ALL resetting envs, reduced once by the last block of k_terrain_phys
+    const float cnorm = (T.cfg.custom_origins && T.cfg.curriculum && T.init_done) ? *T.cnorm : 0.0f;
     const int tid = threadIdx.x;
-    constexpr int EPW = 32 / LANES / kSparse, EPB = EnvsPerBlock<LANES>::value;
-    const int lane = tid % LANES, wl = tid & 31;
-    const bool live = wl < EPW * LANES;
-    const int e = blockIdx.x * EPB + (tid >> 5) * EPW + (live ? wl / LANES : 0);
-    const bool valid = live && e < A.n_envs;
-    terrain_post_thread<LANES, NL>(A, T, e < A.n_envs ? e : A.n_envs - 1, lane, valid, cnorm);
-}
-
-// extras["episode"] (anymal_terrain.py:420-425): means over the envs that reset this step; one block, fixed order
-__global__ void k_terrain_extras(const float* report, const long long* reset, const long long* levels, float* extras, int n, float inv_len_s,
-                                 long long* step_ctr) {
-    __shared__ float red[256];
-    float vals[15];
-    for (int k = 0; k < 15; k++) vals[k] = 0.0f;
-    for (int i = threadIdx.x; i < n; i += 256) {
-        for (int k = 0; k < 13; k++) vals[k] += report[(size_t)k * n + i];
-        vals[13] += reset[i] != 0 ? 1.0f : 0.0f;
-        vals[14] += (float)levels[i];
+    constexpr int EPB = kPostEnvs;
+    const int e = blockIdx.x * EPB + tid / kPostSub;
+    const bool valid = e < A.n_envs;
+    terrain_post_thread<LANES, NL, kPostSub>(A, T, valid ? e : A.n_envs - 1, tid % kPostSub, valid, cnorm);
+    // extras["episode"] (anymal_terrain.py:420-425): means over the envs that reset this step.  Per-block sums in env order,
+    // then the last block to arrive adds the blocks in block order: fixed order, deterministic, no extra launch
+    if (!T.extras) return;
+    __shared__ float tot[16];
+    __syncthreads();
+    if (tid < 15) {
+        const int e0 = blockIdx.x * EPB, e1 = e0 + EPB < A.n_envs ? e0 + EPB : A.n_envs;
+        float acc = 0.0f;
+        for (int i = e0; i < e1; i++)
+            acc += tid < 13 ? T.report[(size_t)tid * A.n_envs + i] : tid == 13 ? (T.reset[i] != 0 ? 1.0f : 0.0f) : (float)T.terrain_levels[i];
+        T.extras_part[(size_t)blockIdx.x * 16 + tid] = acc;
     }
-    float tot[15];
-    for (int k = 0; k < 15; k++) {
-        red[threadIdx.x] = vals[k];
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-            __syncthreads();
+    if (last_block_arrives(T.tickets + 1)) {
+        if (tid < 15) {
+            float acc = 0.0f;
+            for (int b = 0; b < (int)gridDim.x; b++) acc += __ldcg(T.extras_part + (size_t)b * 16 + tid);
+            tot[tid] = acc;
         }
-        tot[k] = red[0];
         __syncthreads();
+        if (tid < 13 && tot[13] > 0.0f) T.extras[tid] = tot[tid] / tot[13] * (1.0f / T.cfg.max_episode_length_s);
+        if (tid == 13 && tot[13] > 0.0f) { T.extras[13] = tot[14] / (float)A.n_envs; T.extras[14] = tot[13]; }
+        if (tid == 0 && T.step_ctr_advance) *T.step_ctr_advance += 1;     // end of the step: the next step sees the next counter value
     }
-    if (threadIdx.x == 0 && tot[13] > 0.0f) {
-        for (int k = 0; k < 13; k++) extras[k] = tot[k] / tot[13] * inv_len_s;
-        extras[13] = tot[14] / (float)n;
-        extras[14] = tot[13];
-    }
-    if (threadIdx.x == 0 && step_ctr) *step_ctr += 1;     // last kernel of the step: the next step sees the next counter value
 }
 
 template <int LANES, int NL>
 __global__ void __launch_bounds__(kBlock) k_anymal_reset_all(SimArgs A, TaskArgs T) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     anymal_reset_all_thread<LANES, NL>(A, T, env, lane, valid);
 }
 
@@ -264,7 +280,7 @@ template <int LANES, int NL, bool FIXED>
 __global__ void __launch_bounds__(kBlock) k_probe(SimArgs A, float* qdd, float* a0) {
     extern __shared__ float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     const DevModel* M = A.M;
     const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
     const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
@@ -338,6 +354,10 @@ struct b2g_sim {
     b2g_heightfield hf{};
     int16_t* d_hf = nullptr;
     bool has_hf = false;
+    std::vector<int16_t> h_hf;     // host copy of the samples: the coarse bound is rebuilt when the model arrives later
+    float* d_hfc = nullptr;        // coarse conservative bound (build_hf_coarse)
+    int hfc_rows = 0, hfc_cols = 0;
+    float link_rmax = 0.0f;
     int n_envs = 0;
     float root_pose[7] = {0, 0, 0, 0, 0, 0, 1};
     Variant v{4, 3, false};
@@ -355,6 +375,8 @@ struct b2g_sim {
     float *torques = nullptr, *last_actions = nullptr, *last_dof_vel = nullptr, *feet_air_time = nullptr, *episode_sums = nullptr;
     float *env_origins = nullptr, *terrain_origins = nullptr, *scratch9 = nullptr, *resetw = nullptr, *report = nullptr, *measured = nullptr;
     float *noise_override = nullptr, *push_override = nullptr, *extras = nullptr;
+    float *cnorm = nullptr, *extras_part = nullptr;   // cross-block reductions of the terrain step
+    unsigned* tickets = nullptr;
     float *arm_mm = nullptr, *arm_jac = nullptr, *eef_state = nullptr, *arm_commands = nullptr;
     long long *terrain_levels = nullptr, *terrain_types = nullptr;
     int16_t* height_samples = nullptr;
@@ -383,7 +405,8 @@ namespace {
 
 size_t smem_bytes(const b2g_sim* s) {
     const int epb = kBlock / s->v.lanes;
-    return sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)epb * s->model.n_bodies * 3);
+    const size_t links = s->v.nl > 3 ? link_store_floats(epb, s->model.n_dof) : 0;     // links_in_shared variants
+    return sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)epb * s->model.n_bodies * 3 + links);
 }
 
 int grid_size(const b2g_sim* s) {
@@ -394,7 +417,7 @@ int grid_size(const b2g_sim* s) {
 SimArgs make_args(const b2g_sim* s) {
     SimArgs A;
     A.M = s->d_model;
-    pack_dev_params(s->params, s->has_hf ? &s->hf : nullptr, s->d_hf, A.P);
+    pack_dev_params(s->params, s->has_hf ? &s->hf : nullptr, s->d_hf, A.P, s->d_hfc, s->hfc_rows, s->hfc_cols);
     A.n_envs = s->n_envs;
     A.root = s->t[B2G_T_ROOT_STATE];
     A.dof = s->t[B2G_T_DOF_STATE];
@@ -421,6 +444,23 @@ TaskArgs make_task_args(const b2g_sim* s, const float* actions_in, int post_only
     return T;
 }
 
+// (Re)build the coarse heightfield bound; needs both the samples and the model's largest link radius.  B2G_NO_HFC=1 keeps
+// the kernels on the exhaustive candidate tests (A/B timing; results are identical either way).
+int rebuild_hfc(b2g_sim* s) {
+    if (s->d_hfc) { cudaFree(s->d_hfc); s->d_hfc = nullptr; }
+    s->hfc_rows = s->hfc_cols = 0;
+    const char* off = getenv("B2G_NO_HFC");
+    if (!s->has_hf || s->h_hf.empty() || (off && off[0] == '1')) return B2G_OK;
+    std::vector<float> c;
+    int cr = 0, cc = 0;
+    build_hf_coarse(s->h_hf.data(), s->hf.rows, s->hf.cols, s->hf.horizontal_scale, s->hf.vertical_scale, s->link_rmax, c, cr, cc);
+    cudaError_t e = cudaMalloc(&s->d_hfc, sizeof(float) * c.size());
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_hfc, c.data(), sizeof(float) * c.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(B2G_ERR_CUDA, "coarse heightfield upload: %s", cudaGetErrorString(e));
+    s->hfc_rows = cr; s->hfc_cols = cc;
+    return B2G_OK;
+}
+
 int upload_model(b2g_sim* s) {
     DevModel* h = (DevModel*)malloc(sizeof(DevModel));
     if (!h) return fail(B2G_ERR_ARG, "out of host memory");
@@ -432,8 +472,13 @@ int upload_model(b2g_sim* s) {
     cudaError_t e = cudaSuccess;
     if (!s->d_model) e = cudaMalloc(&s->d_model, sizeof(DevModel));
     if (e == cudaSuccess) e = cudaMemcpy(s->d_model, h, sizeof(DevModel), cudaMemcpyHostToDevice);
+    const float rmax = max_link_radius(*h);
     free(h);
     if (e != cudaSuccess) return fail(B2G_ERR_CUDA, "model upload: %s", cudaGetErrorString(e));
+    if (rmax != s->link_rmax || (s->has_hf && !s->d_hfc)) {
+        s->link_rmax = rmax;
+        if (s->has_hf) return rebuild_hfc(s);
+    }
     return B2G_OK;
 }
 
@@ -520,29 +565,29 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         R.noise_override = s->use_rand_override ? s->noise_override : nullptr;
         R.push_override = s->use_rand_override ? s->push_override : nullptr;
         R.common_step = s->common_step; R.step_ctr = s->auto_step ? s->step_ctr : nullptr; R.init_done = s->init_done; R.post_only = post_only; R.seed = s->seed;
+        const bool advance = s->auto_step && post_only == 0;
+        R.cnorm = s->cnorm; R.extras_part = s->extras_part; R.extras = s->extras; R.tickets = s->tickets;
+        R.step_ctr_advance = advance ? s->step_ctr : nullptr;
         if (s->v.lanes == 4) {
             if (s->has_hf) k_terrain_phys<4, 3, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<4, 3, false><<<grid, kBlock, sm, st>>>(A, R);
-            if (post_only != 2) k_terrain_post<4, 3><<<grid, kBlock, 0, st>>>(A, R);
+            if (post_only != 2) k_terrain_post<4, 3><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R);
         } else {
             if (s->has_hf) k_terrain_phys<8, 6, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<8, 6, false><<<grid, kBlock, sm, st>>>(A, R);
-            if (post_only != 2) k_terrain_post<8, 6><<<grid, kBlock, 0, st>>>(A, R);
+            if (post_only != 2) k_terrain_post<8, 6><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R);
         }
         if (post_only == 2) {
             s->launches += 1;
             CUDA_TRY(cudaGetLastError());
             return B2G_OK;
         }
-        const bool advance = s->auto_step && post_only == 0;
-        k_terrain_extras<<<1, 256, 0, st>>>(s->report, s->reset, s->terrain_levels, s->extras, s->n_envs, 1.0f / s->tcfg.max_episode_length_s,
-                                          advance ? s->step_ctr : nullptr);
         if (advance) s->common_step++;
-        s->launches += 3;
+        s->launches += 2;
         CUDA_TRY(cudaGetLastError());
         return B2G_OK;
     }
     if (s->task_kind == 4) {     // one thread per environment whatever the generic kernels' lane count is
         const int g1 = (s->n_envs + kBlock / kSparse - 1) / (kBlock / kSparse);
-        const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3);
+        const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + link_store_floats(kBlock, s->model.n_dof));
         k_houndarm_step<<<g1, kBlock, sm1, st>>>(A, T);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -612,11 +657,11 @@ int b2g_sim_destroy(b2g_sim* s) {
     if (!s) return fail(B2G_ERR_ARG, "null sim");
     with_device(s, [&]() {
         for (int k = 0; k < B2G_T_COUNT; k++) if (s->t[k]) cudaFree(s->t[k]);
-        void* ptrs[] = {s->d_model, s->d_hf, s->obs, s->out_arena, s->commands, s->actions, s->rand_override,
+        void* ptrs[] = {s->d_model, s->d_hf, s->d_hfc, s->obs, s->out_arena, s->commands, s->actions, s->rand_override,
                         s->progress, s->reset_count, s->actions_in, s->torques, s->last_actions, s->last_dof_vel,
                         s->feet_air_time, s->episode_sums, s->env_origins, s->terrain_origins, s->scratch9, s->resetw, s->report, s->measured,
                         s->noise_override, s->push_override, s->extras, s->terrain_levels, s->terrain_types, s->height_samples,
-                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands, s->step_ctr, s->done_ctr};
+                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands, s->step_ctr, s->done_ctr, s->cnorm, s->extras_part, s->tickets};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (s->host_flag) cudaFreeHost(s->host_flag);
         return 0;
@@ -659,6 +704,8 @@ int b2g_sim_add_heightfield(b2g_sim* s, const b2g_heightfield* hf, const int16_t
         CUDA_TRY(cudaMemcpy(s->d_hf, samples, bytes, cudaMemcpyHostToDevice));
         s->hf = *hf;
         s->has_hf = true;
+        s->h_hf.assign(samples, samples + (size_t)hf->rows * hf->cols);
+        if (s->has_model) return rebuild_hfc(s);
         return (int)B2G_OK;
     });
 }
@@ -725,6 +772,10 @@ int b2g_sim_prepare(b2g_sim* s) {
         cudaFuncSetAttribute(k_anymal_step<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_anymal_step<8, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_anymal_step<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_terrain_phys<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_terrain_phys<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_terrain_phys<8, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_terrain_phys<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
@@ -928,7 +979,7 @@ int b2g_task_houndarm_create(b2g_sim* s, const b2g_houndarm_cfg* cfg) {
     s->seed = cfg->seed;
     s->task_kind = 4;
     if (s->has_task) return B2G_OK;
-    const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3);
+    const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + link_store_floats(kBlock, s->model.n_dof));
     cudaFuncSetAttribute(k_houndarm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
     return alloc_task_buffers(s, 10, s->model.n_dof, 9);
 }
@@ -976,6 +1027,9 @@ int b2g_task_terrain_create(b2g_sim* s, const b2g_terrain_cfg* cfg, const int16_
         CUDA_TRY(zalloc((void**)&s->scratch9, sizeof(float) * n * 9));
         CUDA_TRY(zalloc((void**)&s->resetw, sizeof(float) * n));
         CUDA_TRY(zalloc((void**)&s->report, sizeof(float) * n * 13));
+        CUDA_TRY(zalloc((void**)&s->cnorm, sizeof(float)));
+        CUDA_TRY(zalloc((void**)&s->extras_part, sizeof(float) * 16 * (size_t)((n + kPostEnvs - 1) / kPostEnvs)));
+        CUDA_TRY(zalloc((void**)&s->tickets, sizeof(unsigned) * 2));
         CUDA_TRY(zalloc((void**)&s->measured, sizeof(float) * n * nhp));
         CUDA_TRY(zalloc((void**)&s->noise_override, sizeof(float) * n * no));
         CUDA_TRY(zalloc((void**)&s->push_override, sizeof(float) * n * 2));

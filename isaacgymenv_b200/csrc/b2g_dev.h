@@ -57,6 +57,13 @@ struct DevParams {
     const int16_t* hf;
     int hf_rows, hf_cols;
     float hf_hs, hf_vs, hf_ox, hf_oy;
+    // coarse conservative bound of the heightfield (b2g_host_pack.h::build_hf_coarse; null -> no early-out): per block of
+    // B2G_HFC_BLOCK x B2G_HFC_BLOCK samples, dilated by the largest link radius, {max height, min normal z}
+    const float* hfc;
+    int hfc_rows, hfc_cols;
 };
+
+constexpr int B2G_HFC_SHIFT = 3;
+constexpr int B2G_HFC_BLOCK = 1 << B2G_HFC_SHIFT;
 
 }  // namespace b2g

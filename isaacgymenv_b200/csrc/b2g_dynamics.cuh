@@ -53,6 +53,7 @@ struct EmuCtx {
     int local_sense;
 };
 extern thread_local EmuCtx emu_ctx;
+extern long long emu_hfc_tests, emu_hfc_skips;   // coarse-bound statistics (tests assert the early-out is not vacuous)
 inline void emu_barrier() {
     EmuGroup* g = emu_ctx.g;
     if (g->lanes == 1) return;
@@ -166,10 +167,40 @@ B2G_HD B2G_INL EnvDr load_env_dr(const float* friction, const float* env_scale, 
     return d;
 }
 
+// per-link state of the recursions
+struct LinkData {
+    M3 Rl;             // link rotation (world axes)
+    V3 pl;             // link origin relative to the root origin
+    SV S, cb, vl;      // joint motion subspace, velocity-product term, link velocity
+    SV U;              // I^A S
+    float tau, dext;   // joint-space force, joint-space diagonal (armature + implicit drive / limit terms)
+    float Dinv, u;
+    float pad;         // 41 words: lanes that walk their chains side by side land in different banks
+};
+// Rolled link loops (NL > 3) index the link state dynamically: as per-thread arrays it lives in local memory (960 B per thread,
+// more than L1 holds for a resident wave -- 28 % L1 misses and 90 MB of DRAM traffic per UsefulHound step, measured), so the
+// long-chain variant keeps it in shared memory instead: one LinkData per DOF of the environment, slot = DOF index.
+static_assert(sizeof(LinkData) == 41 * sizeof(float), "LinkData is 41 packed floats");
+template <int NL>
+B2G_HD constexpr bool links_in_shared() {
+#if defined(B2G_LINKS_LOCAL)
+    return false;
+#else
+    return NL > 3;
+#endif
+}
+#if defined(B2G_HOST_EMU)
+inline
+#else
+__host__ __device__ inline
+#endif
+size_t link_store_floats(int n_envs_per_block, int n_dof) { return (size_t)n_envs_per_block * n_dof * (sizeof(LinkData) / sizeof(float)); }
+
 // per-thread contact scratch: field f of slot s
 struct ScratchStrided {
     float* base;   // points at this thread's column
     int stride;    // number of threads sharing the buffer
+    float* links = nullptr;   // this environment's slice of the block's shared link store (links_in_shared variants only)
     B2G_HD B2G_INL float& at(int slot, int f) { return base[(slot * CF_COUNT + f) * stride]; }
 };
 
@@ -210,10 +241,11 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
     // ---------------- kinematics down the chain ----------------
     const M3 R0 = quat_to_m3(st.qx, st.qy, st.qz, st.qw);
     const SV v0 = FIXED ? sv0() : SV{st.rw, st.rv};
-    M3 Rl[NL];
-    V3 pl[NL];
-    SV S[NL], cb[NL], vl[NL];
-    float tau[NL], dext[NL];
+    // per-link state of this lane's chain: registers when the link loops are unrolled, this lane's slice of the block's
+    // shared-memory link store (sc.links) when they are rolled
+    constexpr bool LSH = links_in_shared<NL>();
+    LinkData Lreg[LSH ? 1 : NL];
+    LinkData* const L = LSH ? reinterpret_cast<LinkData*>(sc.links) + d0 : Lreg;   // sc.links = this environment's store, slot = DOF index
     {
         M3 Rp = R0;
         V3 pp = V3{0, 0, 0};
@@ -230,17 +262,17 @@ B2G_LINK_UNROLL
                 const V3 pj = pp + mul(Rp, V3{D.jpos[0], D.jpos[1], D.jpos[2]});
                 const V3 axw = mul(RJ, ax);
                 if (D.type == B2G_JOINT_REVOLUTE) {
-                    Rl[j] = mul(RJ, axis_angle_m3(ax, st.q[j]));
-                    pl[j] = pj;
-                    S[j] = SV{axw, cross(pj, axw)};
+                    L[j].Rl = mul(RJ, axis_angle_m3(ax, st.q[j]));
+                    L[j].pl = pj;
+                    L[j].S = SV{axw, cross(pj, axw)};
                 } else {
-                    Rl[j] = RJ;
-                    pl[j] = pj + axw * st.q[j];
-                    S[j] = SV{V3{0, 0, 0}, axw};
+                    L[j].Rl = RJ;
+                    L[j].pl = pj + axw * st.q[j];
+                    L[j].S = SV{V3{0, 0, 0}, axw};
                 }
-                const SV vj = S[j] * st.qd[j];
-                vl[j] = vp + vj;
-                cb[j] = crm(vl[j], vj);
+                const SV vj = L[j].S * st.qd[j];
+                L[j].vl = vp + vj;
+                L[j].cb = crm(L[j].vl, vj);
                 // drive
                 const float kp = D.kp * dr.kp, kd = D.kd * dr.kd;
                 float t = 0.0f, de = D.armature;
@@ -268,18 +300,16 @@ B2G_LINK_UNROLL
                         de += h * P.limit_kd + h * h * P.limit_kp;
                     }
                 }
-                tau[j] = t;
-                dext[j] = de;
-                Rp = Rl[j]; pp = pl[j]; vp = vl[j];
-            } else {
-                Rl[j] = R0; pl[j] = V3{0, 0, 0}; S[j] = sv0(); cb[j] = sv0(); vl[j] = sv0(); tau[j] = 0; dext[j] = 1.0f;
+                L[j].tau = t;
+                L[j].dext = de;
+                Rp = L[j].Rl; pp = L[j].pl; vp = L[j].vl;
+            } else if (!LSH) {      // unused link slots are never read; in registers they are defined anyway (no cost once unrolled)
+                L[j].Rl = R0; L[j].pl = V3{0, 0, 0}; L[j].S = sv0(); L[j].cb = sv0(); L[j].vl = sv0(); L[j].tau = 0; L[j].dext = 1.0f;
             }
         }
     }
 
     // ---------------- ABA backward: articulated inertias and bias forces ----------------
-    SV U[NL];
-    float Dinv[NL], u[NL];
     SI IAc;
     SV pAc = sv0();
     {
@@ -290,20 +320,20 @@ B2G_LINK_UNROLL
         for (int j = NL - 1; j >= 0; j--) {
             if (j < len) {
                 const DevDof& D = M->dof[d0 + j];
-                const V3 cw = pl[j] + mul(Rl[j], V3{D.com[0], D.com[1], D.com[2]});
-                const S3 iw = rotate_sym(Rl[j], S3{D.inertia[0] * dr.mass, D.inertia[1] * dr.mass, D.inertia[2] * dr.mass, D.inertia[3] * dr.mass,
+                const V3 cw = L[j].pl + mul(L[j].Rl, V3{D.com[0], D.com[1], D.com[2]});
+                const S3 iw = rotate_sym(L[j].Rl, S3{D.inertia[0] * dr.mass, D.inertia[1] * dr.mass, D.inertia[2] * dr.mass, D.inertia[3] * dr.mass,
                                                    D.inertia[4] * dr.mass, D.inertia[5] * dr.mass});
                 SI I = rigid_inertia(D.mass * dr.mass, cw, iw);
-                SV pA = crf(vl[j], mul(I, vl[j]));
+                SV pA = crf(L[j].vl, mul(I, L[j].vl));
                 if (j + 1 < len) { I += IAc; pA += pAc; }
-                U[j] = mul(I, S[j]);
-                const float Dj = dot(S[j], U[j]) + dext[j];
-                Dinv[j] = 1.0f / Dj;
-                u[j] = tau[j] - dot(S[j], pA);
-                IAc = rank1_sub(I, U[j], Dinv[j]);
-                pAc = pA + mul(IAc, cb[j]) + U[j] * (u[j] * Dinv[j]);
-            } else {
-                U[j] = sv0(); Dinv[j] = 0.0f; u[j] = 0.0f;
+                L[j].U = mul(I, L[j].S);
+                const float Dj = dot(L[j].S, L[j].U) + L[j].dext;
+                L[j].Dinv = 1.0f / Dj;
+                L[j].u = L[j].tau - dot(L[j].S, pA);
+                IAc = rank1_sub(I, L[j].U, L[j].Dinv);
+                pAc = pA + mul(IAc, L[j].cb) + L[j].U * (L[j].u * L[j].Dinv);
+            } else if (!LSH) {
+                L[j].U = sv0(); L[j].Dinv = 0.0f; L[j].u = 0.0f;
             }
         }
     }
@@ -336,9 +366,9 @@ B2G_LINK_UNROLL
 B2G_LINK_UNROLL
         for (int j = 0; j < NL; j++) {
             if (j < len) {
-                const SV ap = a + cb[j];
-                const float qdd = (u[j] - dot(U[j], ap)) * Dinv[j];
-                a = ap + S[j] * qdd;
+                const SV ap = a + L[j].cb;
+                const float qdd = (L[j].u - dot(L[j].U, ap)) * L[j].Dinv;
+                a = ap + L[j].S * qdd;
                 qdn[j] = st.qd[j] + h * qdd;
                 if (PROBE) st.frc[j] = qdd;
             } else {
@@ -366,8 +396,8 @@ B2G_LINK_UNROLL
 #pragma unroll
         for (int i = NL - 1; i >= 0; i--) {
             if (i <= jc) {
-                ud[i] = -dot(S[i], Pb);
-                Pb += U[i] * (ud[i] * Dinv[i]);
+                ud[i] = -dot(L[i].S, Pb);
+                Pb += L[i].U * (ud[i] * L[i].Dinv);
             } else {
                 ud[i] = 0.0f;
             }
@@ -402,11 +432,30 @@ B2G_LINK_UNROLL
         }
     };
     // plane ground: a link whose candidate bounding box clears the contact offset cannot touch (skips most loops)
+    // heightfield: the same test against a coarse conservative bound of the terrain under the box (max height and min
+    // normal z of the dilated block that holds the box centre, b2g_host_pack.h::build_hf_coarse): every candidate of the
+    // link has gap = (z - gh) nz - r >= (zlow - Hmax) nzmin - r (1 - nzmin), r <= the smallest half extent
     auto may_touch = [&](const M3& R, V3 p, const float* c, const float* hx) -> bool {
-        if (HF) return true;
+        if (HF && !P.hfc) return true;
         const float zc = st.rp.z + p.z + R.m[6] * c[0] + R.m[7] * c[1] + R.m[8] * c[2];
         const float ext = fabsf(R.m[6]) * hx[0] + fabsf(R.m[7]) * hx[1] + fabsf(R.m[8]) * hx[2];
-        return zc - ext < P.contact_offset;
+        if (!HF) return zc - ext < P.contact_offset;
+        const float xc = st.rp.x + p.x + R.m[0] * c[0] + R.m[1] * c[1] + R.m[2] * c[2];
+        const float yc = st.rp.y + p.y + R.m[3] * c[0] + R.m[4] * c[1] + R.m[5] * c[2];
+        const float inv_hs = 1.0f / P.hf_hs;
+        const float gx = fminf(fmaxf((xc - P.hf_ox) * inv_hs, 0.0f), (float)(P.hf_rows - 1));
+        const float gy = fminf(fmaxf((yc - P.hf_oy) * inv_hs, 0.0f), (float)(P.hf_cols - 1));
+        const int ci = ((int)gx) >> B2G_HFC_SHIFT, cj = ((int)gy) >> B2G_HFC_SHIFT;
+        const float* b = P.hfc + 2 * ((size_t)ci * P.hfc_cols + cj);
+        const float hmax = b[0], nzmin = b[1];
+        const float d = zc - ext - hmax;
+        const float rmin = fminf(hx[0], fminf(hx[1], hx[2]));
+        const bool skip = d > 0.0f && d * nzmin - rmin * (1.0f - nzmin) >= P.contact_offset;
+#if defined(B2G_HOST_EMU)
+        __atomic_add_fetch(&emu_hfc_tests, 1, __ATOMIC_RELAXED);
+        if (skip) __atomic_add_fetch(&emu_hfc_skips, 1, __ATOMIC_RELAXED);
+#endif
+        return !skip;
     };
     if (ground) {
 B2G_LINK_UNROLL
@@ -414,8 +463,8 @@ B2G_LINK_UNROLL
             if (j < len) {
                 const DevDof& D = M->dof[d0 + j];
                 const int c0 = D.cp_start, cn = D.cp_count;
-                if (cn > 0 && may_touch(Rl[j], pl[j], D.cp_c, D.cp_h))
-                    for (int i = c0; i < c0 + cn; i++) test_candidate(i, Rl[j], pl[j], j);
+                if (cn > 0 && may_touch(L[j].Rl, L[j].pl, D.cp_c, D.cp_h))
+                    for (int i = c0; i < c0 + cn; i++) test_candidate(i, L[j].Rl, L[j].pl, j);
             }
         }
         if (!FIXED) {
@@ -445,8 +494,8 @@ B2G_LINK_UNROLL
 #pragma unroll
                 for (int k = 0; k < NL; k++) {
                     if (k <= jc) {
-                        const float dq = (ud[k] - dot(U[k], a)) * Dinv[k];
-                        a += S[k] * dq;
+                        const float dq = (ud[k] - dot(L[k].U, a)) * L[k].Dinv;
+                        a += L[k].S * dq;
                     }
                 }
                 const V3 pv = a.v + cross(a.w, r);
@@ -491,7 +540,7 @@ B2G_LINK_UNROLL
                 SV lv = v0n;
 #pragma unroll
                 for (int k = 0; k < NL; k++)
-                    if (k <= jc) lv += S[k] * qdn[k];
+                    if (k <= jc) lv += L[k].S * qdn[k];
                 const V3 pv = lv.v + cross(lv.w, r);
                 float vn = dot(pv, n), vt1 = dot(pv, t1), vt2 = dot(pv, t2);
                 float tgt = -sc.at(s, CF_GAP) * inv_h;
@@ -524,8 +573,8 @@ B2G_LINK_UNROLL
 #pragma unroll
             for (int k = 0; k < NL; k++) {
                 if (k < len) {
-                    const float dq = (ud[k] - dot(U[k], a)) * Dinv[k];
-                    a += S[k] * dq;
+                    const float dq = (ud[k] - dot(L[k].U, a)) * L[k].Dinv;
+                    a += L[k].S * dq;
                     qdn[k] += dq;
                 }
             }

@@ -4,6 +4,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "b2g_dev.h"
 
 namespace b2g {
@@ -98,7 +100,68 @@ inline int pack_dev_model(const b2g_model& m, const b2g_dof_props& p, DevModel& 
     return 0;
 }
 
-inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, const int16_t* hf_dev, DevParams& d) {
+// Largest distance between a link's candidate bounding-box centre and any of its candidate centres (box half diagonal).
+inline float max_link_radius(const DevModel& d) {
+    float r2 = d.root_cp_h[0] * d.root_cp_h[0] + d.root_cp_h[1] * d.root_cp_h[1] + d.root_cp_h[2] * d.root_cp_h[2];
+    for (int l = 0; l < d.n_dof; l++) {
+        const float* h = d.dof[l].cp_h;
+        r2 = fmaxf(r2, h[0] * h[0] + h[1] * h[1] + h[2] * h[2]);
+    }
+    return sqrtf(r2);
+}
+
+// Conservative coarse bound of a heightfield for the per-link contact early-out (b2g_dynamics.cuh::may_touch).
+// Block (I, J) covers the samples [I*B, I*B+B) x [J*B, J*B+B) dilated by ceil(rmax / hs) + 2 samples on every side, so the
+// bound found from a link's bounding-box centre holds for every candidate of that link.  out[2*(I*ccols+J)] = max height
+// (+ 1e-4 m), out[..+1] = min over the dilated block's triangles of the normal's z (x 0.9999): the margins absorb the
+// kernels' approximate division / rsqrt, so skipping a link never changes a result.
+inline void build_hf_coarse(const int16_t* smp, int rows, int cols, float hs, float vs, float rmax, std::vector<float>& out, int& crows, int& ccols) {
+    const int B = B2G_HFC_BLOCK;
+    const int dil = (int)ceilf(rmax / hs) + 2;
+    crows = (rows + B - 1) / B; ccols = (cols + B - 1) / B;
+    // per fine cell: min normal z of its two triangles (same expressions as ground_sample)
+    std::vector<float> nz((size_t)(rows - 1) * (cols - 1));
+    for (int i = 0; i < rows - 1; i++) {
+        for (int j = 0; j < cols - 1; j++) {
+            const int16_t* s = smp + (size_t)i * cols + j;
+            const float h00 = vs * (float)s[0], h01 = vs * (float)s[1], h10 = vs * (float)s[cols], h11 = vs * (float)s[cols + 1];
+            const float ax = (h10 - h00) / hs, ay = (h11 - h10) / hs, bx = (h11 - h01) / hs, by = (h01 - h00) / hs;
+            const float na = 1.0f / sqrtf(ax * ax + ay * ay + 1.0f), nb = 1.0f / sqrtf(bx * bx + by * by + 1.0f);
+            nz[(size_t)i * (cols - 1) + j] = fminf(na, nb);
+        }
+    }
+    // separable window max / min: rows first, then columns
+    std::vector<float> hrow((size_t)crows * cols), nrow((size_t)crows * (cols - 1));
+    for (int I = 0; I < crows; I++) {
+        const int lo = I * B - dil < 0 ? 0 : I * B - dil;
+        const int hi = I * B + B - 1 + dil + 1 > rows - 1 ? rows - 1 : I * B + B - 1 + dil + 1;   // samples lo..hi, cells lo..hi-1
+        for (int j = 0; j < cols; j++) {
+            float m = -1e30f;
+            for (int i = lo; i <= hi; i++) m = fmaxf(m, vs * (float)smp[(size_t)i * cols + j]);
+            hrow[(size_t)I * cols + j] = m;
+        }
+        for (int j = 0; j < cols - 1; j++) {
+            float m = 1.0f;
+            for (int i = lo; i < hi; i++) m = fminf(m, nz[(size_t)i * (cols - 1) + j]);
+            nrow[(size_t)I * (cols - 1) + j] = m;
+        }
+    }
+    out.assign((size_t)crows * ccols * 2, 0.0f);
+    for (int I = 0; I < crows; I++) {
+        for (int J = 0; J < ccols; J++) {
+            const int lo = J * B - dil < 0 ? 0 : J * B - dil;
+            const int hi = J * B + B - 1 + dil + 1 > cols - 1 ? cols - 1 : J * B + B - 1 + dil + 1;
+            float mh = -1e30f, mn = 1.0f;
+            for (int j = lo; j <= hi; j++) mh = fmaxf(mh, hrow[(size_t)I * cols + j]);
+            for (int j = lo; j < hi; j++) mn = fminf(mn, nrow[(size_t)I * (cols - 1) + j]);
+            out[2 * ((size_t)I * ccols + J)] = mh + 1e-4f;
+            out[2 * ((size_t)I * ccols + J) + 1] = mn * 0.9999f;
+        }
+    }
+}
+
+inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, const int16_t* hf_dev, DevParams& d, const float* hfc_dev = nullptr,
+                            int hfc_rows = 0, int hfc_cols = 0) {
     memset(&d, 0, sizeof(d));
     const int sub = s.substeps > 0 ? s.substeps : 1;
     d.h = s.dt / (float)sub;
@@ -112,6 +175,7 @@ inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, 
     if (hf && hf_dev) {
         d.hf = hf_dev; d.hf_rows = hf->rows; d.hf_cols = hf->cols; d.hf_hs = hf->horizontal_scale; d.hf_vs = hf->vertical_scale;
         d.hf_ox = hf->origin_x; d.hf_oy = hf->origin_y;
+        d.hfc = hfc_dev; d.hfc_rows = hfc_rows; d.hfc_cols = hfc_cols;
     }
 }
 

@@ -402,6 +402,12 @@ struct TerrainArgs {
     float* resetw;               // (N) reset ? |cmd_xy|^2 : 0      (curriculum scalar, quirk Q10)
     float* report;               // (13,N) episode sums of the envs that reset this step (else 0)
     float* measured;             // (N,n_height_points)
+    // cross-block reductions of the step (device kernels only; the host emulator computes them in its driver)
+    float* cnorm = nullptr;            // curriculum scalar sqrt(sum resetw), written by the last block of k_terrain_phys
+    float* extras_part = nullptr;      // (blocks,16) per-block sums for extras["episode"]
+    float* extras = nullptr;           // (15) means over the envs that reset, mean terrain level, reset count
+    unsigned* tickets = nullptr;       // [0]: k_terrain_phys, [1]: k_terrain_post block-arrival counters
+    long long* step_ctr_advance = nullptr;   // counter the last block of the step increments (device-side step counter)
     float* arm_mm;               // (N,36) arm block of the mass matrix as of the last post_physics refresh (pre-reset)
     float* arm_jac;              // (N,36) Jacobian slice the task takes: base columns of body `jac_body`
     float* eef_state;            // (N,13) end-effector rigid-body row (never refreshed unless cfg.refresh_eef)
@@ -919,7 +925,10 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
 }
 
 // kernel 2: reset_idx (+ terrain curriculum), observations (+ height scan, noise), history, time-outs
-template <int LANES, int NL>
+// NSUB threads work on one environment: the first LANES of them are the chain lanes (reset draws, DOF columns), all of them
+// share the element-wise passes (height scan, noise + clamp, report rows).  The device kernel runs 16 per environment -- the
+// pass is a latency chain per element, so the extra warps are what hides it; the host emulator runs NSUB = LANES.
+template <int LANES, int NL, int NSUB = LANES>
 B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, int env, int lane, bool valid, float curriculum_norm) {
     const DevModel* M = A.M;
     const b2g_terrain_cfg& C = T.cfg;
@@ -942,7 +951,7 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
     long long level = T.terrain_levels[env];
     const long long type = T.terrain_types[env];
     // every lane has read the per-env inputs it replicates; only now may lane 0 overwrite them
-    Grp<LANES>::sync();
+    Grp<NSUB>::sync();
     const bool has_arm = C.arm_chain >= 0;
     const bool is_arm = has_arm && lane == C.arm_chain;
     const int nctrl = C.n_ctrl_dof > 0 ? C.n_ctrl_dof : nd;
@@ -1001,9 +1010,12 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
     float* o = T.obs + (size_t)env * no;
     float* oc = T.obs_clamped + (size_t)env * no;
     const unsigned step = (unsigned)(T.step_ctr ? *T.step_ctr : T.common_step);
+    // values are stored raw; the noise pass below adds the uniform noise and writes the clamped copy.  The noise stream draws
+    // column i from word i & 3 of Philox block i >> 2, so that pass walks the row in groups of four columns: one Philox
+    // evaluation per group instead of one per column (same stream, same values)
     auto put = [&](int idx, float val, float nscale) {
-        if (C.add_noise && nscale != 0.0f) val += (2.0f * terrain_uniform(T, T.noise_override, no, env, step, 2u, idx) - 1.0f) * nscale;
-        if (valid) { o[idx] = val; oc[idx] = fminf(fmaxf(val, -C.clip_obs), C.clip_obs); }
+        (void)nscale;
+        if (valid) o[idx] = val;
     };
     if (has_arm && lane == 0) {      // tasks/useful_hound.py:493-496: end-effector position, orientation, arm command
         const float* e = T.eef_state + (size_t)env * 13;
@@ -1043,15 +1055,16 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
         float yz = root[5], yw = root[6];
         const float yn = fmaxf(sqrtf(yz * yz + yw * yw), 1e-9f);
         yz /= yn; yw /= yn;
-        for (int p = lane; p < nhp; p += LANES) {
+        for (int p = lane; p < nhp; p += NSUB) {
             float h = 0.0f;
             if (T.height_samples) {
                 const V3 pt = quat_apply_v(0.0f, 0.0f, yz, yw, V3{C.hx[p / C.n_hy], C.hy[p % C.n_hy], 0.0f});
-                long long px = (long long)((pt.x + root[0] + C.border_size) / C.hscale);
-                long long py = (long long)((pt.y + root[1] + C.border_size) / C.hscale);
+                // (points + border).long() then clip (anymal_terrain.py:529-533); the float clamp keeps the 32-bit conversion exact
+                int px = (int)fminf(fmaxf((pt.x + root[0] + C.border_size) / C.hscale, -1.0f), (float)C.hs_rows);
+                int py = (int)fminf(fmaxf((pt.y + root[1] + C.border_size) / C.hscale, -1.0f), (float)C.hs_cols);
                 px = px < 0 ? 0 : (px > C.hs_rows - 2 ? C.hs_rows - 2 : px);
                 py = py < 0 ? 0 : (py > C.hs_cols - 2 ? C.hs_cols - 2 : py);
-                const short h1 = T.height_samples[px * C.hs_cols + py], h2 = T.height_samples[(px + 1) * C.hs_cols + py + 1];
+                const short h1 = T.height_samples[(size_t)px * C.hs_cols + py], h2 = T.height_samples[(size_t)(px + 1) * C.hs_cols + py + 1];
                 h = (float)(h1 < h2 ? h1 : h2) * C.vscale;
             }
             if (valid) T.measured[(size_t)env * nhp + p] = h;
@@ -1059,10 +1072,35 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
             put(12 + 2 * nctrl + p, v, C.noise_height);
         }
     }
+    // noise + clamp pass (noise scales per column block: anymal_terrain.py:163-178)
+    Grp<NSUB>::sync();
+    {
+        const int c_pos = 12, c_vel = 12 + nctrl, c_h = 12 + 2 * nctrl, c_end = c_h + nhp;
+        for (int g = lane; g * 4 < no; g += NSUB) {
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+            const bool noisy = C.add_noise && g * 4 < c_end;   // columns past the height scan (actions, arm state) carry no noise
+            if (noisy && !T.noise_override)
+                philox4x32((unsigned)env, step, (unsigned)g, 2u, (unsigned)(T.seed & 0xffffffffull), (unsigned)(T.seed >> 32), w);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int idx = g * 4 + c;
+                if (idx < no) {
+                    const float nscale = idx < 3 ? C.noise_lin_vel : idx < 6 ? C.noise_ang_vel : idx < 9 ? C.noise_gravity : idx < c_pos ? 0.0f
+                                       : idx < c_vel ? C.noise_dof_pos : idx < c_h ? C.noise_dof_vel : idx < c_end ? C.noise_height : 0.0f;
+                    float val = o[idx];
+                    if (C.add_noise && nscale != 0.0f) {
+                        const float u = T.noise_override ? T.noise_override[(size_t)env * no + idx] : (float)(w[c] >> 8) * (1.0f / 16777216.0f);
+                        val += (2.0f * u - 1.0f) * nscale;
+                    }
+                    if (valid) { o[idx] = val; oc[idx] = fminf(fmaxf(val, -C.clip_obs), C.clip_obs); }
+                }
+            }
+        }
+    }
     if (valid) {
-        for (int k = lane; k < C.n_feet; k += LANES)
+        for (int k = lane; k < C.n_feet; k += NSUB)
             if (reset) T.feet_air_time[(size_t)env * 4 + k] = 0.0f;
-        for (int k = lane; k < 13; k += LANES) {
+        for (int k = lane; k < 13; k += NSUB) {
             float* es = T.episode_sums + (size_t)k * N + env;
             T.report[(size_t)k * N + env] = reset ? *es : 0.0f;
             if (reset) *es = 0.0f;

@@ -16,6 +16,7 @@
 
 namespace b2g {
 thread_local EmuCtx emu_ctx;
+long long emu_hfc_tests = 0, emu_hfc_skips = 0;
 }
 using namespace b2g;
 
@@ -50,8 +51,9 @@ void run_group(int lanes, F&& body) {
 template <int LANES, int NL, bool FIXED, bool HF>
 void sim_env(const SimArgs& A, int env) {
     std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
     run_group(LANES, [&](int lane) {
-        ScratchStrided sc{scratch.data() + lane, LANES};
+        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data();
         simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, true, sc, bf.data());
     });
 }
@@ -59,6 +61,7 @@ void sim_env(const SimArgs& A, int env) {
 template <int LANES, int NL, bool FIXED>
 void probe_env(const SimArgs& A, int env, float* qdd, float* a0) {
     std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
     run_group(LANES, [&](int lane) {
         const DevModel* M = A.M;
         const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
@@ -66,7 +69,7 @@ void probe_env(const SimArgs& A, int env, float* qdd, float* a0) {
         LaneState<NL> st;
         load_state<NL>(A, env, len, d0, st);
         for (int j = 0; j < NL; j++) if (j < len) st.act[j] = A.actuation[(size_t)env * M->n_dof + d0 + j];
-        ScratchStrided sc{scratch.data() + lane, LANES};
+        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data();
         substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, load_env_dr(nullptr, A.env_scale, env), false, sc, bf.data());
         for (int j = 0; j < NL; j++) if (j < len) qdd[(size_t)env * M->n_dof + d0 + j] = st.frc[j];
         if (lane == 0) {
@@ -79,8 +82,9 @@ void probe_env(const SimArgs& A, int env, float* qdd, float* a0) {
 template <int LANES, int NL, bool HF>
 void anymal_env(const SimArgs& A, const TaskArgs& T, int env, int mode) {
     std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
     run_group(LANES, [&](int lane) {
-        ScratchStrided sc{scratch.data() + lane, LANES};
+        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data();
         if (mode == 0) anymal_reset_all_thread<LANES, NL>(A, T, env, lane, true);
         else anymal_step_thread<LANES, NL, HF>(A, T, env, lane, true, sc, bf.data());
     });
@@ -95,6 +99,11 @@ extern "C" {
 
 void emu_set_env_scale(const float* p) { g_env_scale = p; }
 
+void emu_hfc_stats(long long* out, int reset) {
+    out[0] = b2g::emu_hfc_tests; out[1] = b2g::emu_hfc_skips;
+    if (reset) b2g::emu_hfc_tests = b2g::emu_hfc_skips = 0;
+}
+
 int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp, const b2g_heightfield* hf,
                  const int16_t* hfs, const float* friction, int n_envs, float* root, float* dof, const float* target,
                  const float* actuation, float* dof_force, float* contact) {
@@ -104,6 +113,11 @@ int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, hf, hfs, A.P);
+    std::vector<float> hfc;   // coarse heightfield bound, as the library builds it (B2G_NO_HFC=1: exhaustive candidate tests)
+    if (hf && hfs && !(getenv("B2G_NO_HFC") && getenv("B2G_NO_HFC")[0] == '1')) {
+        build_hf_coarse(hfs, hf->rows, hf->cols, hf->horizontal_scale, hf->vertical_scale, max_link_radius(*dm), hfc, A.P.hfc_rows, A.P.hfc_cols);
+        A.P.hfc = hfc.data();
+    }
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = target; A.actuation = actuation;
     A.dof_force = dof_force; A.contact = contact; A.friction = friction; A.env_scale = g_env_scale;
     const Variant v = pick(*m);
@@ -191,6 +205,11 @@ int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_prop
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, hf, hfs, A.P);
+    std::vector<float> hfc;   // coarse heightfield bound, as the library builds it (B2G_NO_HFC=1: exhaustive candidate tests)
+    if (hf && hfs && !(getenv("B2G_NO_HFC") && getenv("B2G_NO_HFC")[0] == '1')) {
+        build_hf_coarse(hfs, hf->rows, hf->cols, hf->horizontal_scale, hf->vertical_scale, max_link_radius(*dm), hfc, A.P.hfc_rows, A.P.hfc_cols);
+        A.P.hfc = hfc.data();
+    }
     A.n_envs = n_envs; A.root = B->root; A.dof = B->dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = B->dof_force;
     A.contact = B->contact; A.friction = B->friction;
     TerrainArgs T;
@@ -207,8 +226,9 @@ int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_prop
     const bool HFm = hf && hfs;
     for (int e = 0; e < n_envs; e++) {
         std::vector<float> scratch((size_t)v.lanes * MAXC * CF_COUNT), bf((size_t)m->n_bodies * 3);
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
         run_group(v.lanes, [&](int lane) {
-            ScratchStrided sc{scratch.data() + lane, v.lanes};
+            ScratchStrided sc{scratch.data() + lane, v.lanes}; sc.links = links.data();
             if (v.lanes == 4) { if (HFm) terrain_phys_thread<4, 3, true>(A, T, e, lane, true, sc, bf.data()); else terrain_phys_thread<4, 3, false>(A, T, e, lane, true, sc, bf.data()); }
             else { if (HFm) terrain_phys_thread<8, 6, true>(A, T, e, lane, true, sc, bf.data()); else terrain_phys_thread<8, 6, false>(A, T, e, lane, true, sc, bf.data()); }
         });
@@ -265,10 +285,11 @@ int emu_cartpole(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     T.progress = progress; T.timeout = timeout; T.commands = nullptr; T.actions = actions; T.reset_count = reset_count;
     T.rand_override = rand_override; T.post_only = (mode == 2);
     std::vector<float> scratch((size_t)MAXC * CF_COUNT), bf((size_t)m->n_bodies * 3);
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
     EmuGroup g; g.lanes = 1; g.count = 0; g.sense = 0;
     emu_ctx.g = &g; emu_ctx.lane = 0; emu_ctx.local_sense = 0;
     for (int e = 0; e < n_envs; e++) {
-        ScratchStrided sc{scratch.data(), 1};
+        ScratchStrided sc{scratch.data(), 1}; sc.links = links.data();
         cartpole_step_thread(A, T, e, true, sc, bf.data());
     }
     delete dm;
@@ -296,10 +317,11 @@ int emu_houndarm(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     T.progress = progress; T.timeout = timeout; T.commands = commands; T.actions = actions; T.reset_count = reset_count;
     T.rand_override = rand_override; T.post_only = (mode == 2);
     std::vector<float> scratch((size_t)MAXC * CF_COUNT), bf((size_t)m->n_bodies * 3);
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
     EmuGroup g; g.lanes = 1; g.count = 0; g.sense = 0;
     emu_ctx.g = &g; emu_ctx.lane = 0; emu_ctx.local_sense = 0;
     for (int e = 0; e < n_envs; e++) {
-        ScratchStrided sc{scratch.data(), 1};
+        ScratchStrided sc{scratch.data(), 1}; sc.links = links.data();
         houndarm_step_thread(A, T, e, true, sc, bf.data());
     }
     delete dm;

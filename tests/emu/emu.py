@@ -47,6 +47,14 @@ def set_env_scale(scale):
     lib().emu_set_env_scale(_p(_env_scale_keep))
 
 
+def hfc_stats(reset=True):
+    """(links tested against the coarse heightfield bound, links skipped) since the last reset."""
+    out = (C.c_longlong * 2)()
+    lib().emu_hfc_stats.restype = None
+    lib().emu_hfc_stats(out, C.c_int(1 if reset else 0))
+    return int(out[0]), int(out[1])
+
+
 def simulate(model, params, props, root, dof, target, actuation, heightfield=None, hf_samples=None, friction=None):
     n = root.shape[0]
     assert root.dtype == np.float32 and dof.dtype == np.float32

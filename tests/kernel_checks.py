@@ -1042,3 +1042,51 @@ def check_houndarm_step(make_backend, n=12, steps=40, seed=23):
     td = np.array(torque_dev)
     assert np.median(td) < 1e-5 and np.quantile(td, 0.9) < 1e-4 and td.max() < 1e-2, \
         f"OSC torque deviation (relative to the env's largest torque): median {np.median(td):.2e}, q90 {np.quantile(td, 0.9):.2e}, max {td.max():.2e}"
+
+
+# ------------------------------------------------------------------------------------------------
+# coarse heightfield bound (contact early-out on rough terrain)
+# ------------------------------------------------------------------------------------------------
+def hf_coarse_case(robot="useful_hound", n=16, seed=5, slope_scale=1.0):
+    """Robots dropped from different heights / tilts onto a generated rough heightfield (steps, slopes, stairs)."""
+    from isaacgymenv_b200.terrain import Terrain
+
+    art = load_robot(robot)
+    rng = np.random.default_rng(seed)
+    tcfg = dict(terrainType="trimesh", curriculum=True, mapLength=8.0, mapWidth=8.0, numLevels=3, numTerrains=4,
+                terrainProportions=[0.1, 0.1, 0.35, 0.25, 0.2], slopeTreshold=0.5)
+    tr = Terrain(tcfg, n, seed=3)
+    hf_t = _abi.Heightfield(rows=tr.tot_rows, cols=tr.tot_cols, horizontal_scale=tr.horizontal_scale, vertical_scale=tr.vertical_scale * slope_scale,
+                            origin_x=-tr.border_size, origin_y=-tr.border_size, friction=1.0, restitution=0.0)
+    root, dof = standing_state(art, n, rng, 0.45)
+    origins = tr.env_origins.reshape(-1, 3).astype(np.float32)
+    root[:, :3] += origins[np.arange(n) % len(origins)] * np.array([1, 1, slope_scale], np.float32)
+    root[:, :2] += rng.uniform(-3, 3, (n, 2)).astype(np.float32)
+    root[n // 2:, 3:7] = rng.normal(size=(n - n // 2, 4))           # half of them tumbling: links at arbitrary attitudes
+    root[:, 3:7] /= np.linalg.norm(root[:, 3:7], axis=1, keepdims=True)
+    root[-2:, :2] = [-40.0, 500.0]                                  # far outside the field: clamped to the border samples
+    root[-2:, 2] = 0.3
+    return art, hf_t, tr.heightsamples, root, dof
+
+
+def check_hf_coarse_identical(simulate, robot="useful_hound", steps=25):
+    """The coarse-bound early-out must never change a result: B2G_NO_HFC=1 (exhaustive candidate tests) vs default, bit for bit.
+    `simulate(art, sp, props, hf_t, samples, root, dof, steps)` -> (root, dof, contact) after `steps` sim steps."""
+    art, hf_t, samples, root, dof = hf_coarse_case(robot)
+    sp = terrain_params()
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 80.0, 2.0)
+    outs = []
+    old = os.environ.get("B2G_NO_HFC")
+    try:
+        for flag in ("1", "0"):
+            os.environ["B2G_NO_HFC"] = flag
+            outs.append(simulate(art, sp, props, hf_t, samples, root.copy(), dof.copy(), steps))
+    finally:
+        if old is None:
+            os.environ.pop("B2G_NO_HFC", None)
+        else:
+            os.environ["B2G_NO_HFC"] = old
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b), "coarse heightfield bound changed a result"
+    assert np.abs(outs[0][2]).max() > 1.0, "the case must be in contact"
+    return outs[1]

@@ -72,3 +72,28 @@ def test_jacobian_mass_matrix(robot):
 
 def test_houndarm_fused_step():
     kc.check_houndarm_step(make, n=4)
+
+
+def _emu_sim_hf(art, sp, props, hf_t, samples, root, dof, steps):
+    from tests.emu import emu
+    from isaacgymenv_b200 import _abi
+    import numpy as np
+
+    m = _abi.pack_model(art)
+    tgt = dof[:, :, 0].copy()
+    zero = np.zeros_like(tgt)
+    contact = None
+    for _ in range(steps):
+        _, contact = emu.simulate(m, sp, props, root, dof, tgt, zero, heightfield=hf_t, hf_samples=samples)
+    return root, dof, contact
+
+
+@pytest.mark.parametrize("robot", ["useful_hound", "anymal_minimal"])
+def test_hf_coarse_bound_identical(robot):
+    from tests.emu import emu
+
+    emu.hfc_stats()
+    kc.check_hf_coarse_identical(_emu_sim_hf, robot)
+    tested, skipped = emu.hfc_stats()
+    print(f"{robot}: coarse bound skipped {skipped} of {tested} link tests")
+    assert tested > 0 and skipped > 0.25 * tested, (tested, skipped)
