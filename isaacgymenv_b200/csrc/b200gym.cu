@@ -89,7 +89,7 @@ __device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int&
     sc.stride = kBlock;
     bf = smem + kBlock * MAXC * CF_COUNT + (tid / LANES) * nb * 3;     // one accumulator per lane group, idle groups included
     // link store of the rolled long-chain variants (b2g_dynamics.cuh::links_in_shared): one LinkData per DOF per lane group
-    sc.links = smem + kBlock * MAXC * CF_COUNT + (kBlock / LANES) * nb * 3 + link_store_floats(tid / LANES, nd);
+    sc.links = smem + ((kBlock * MAXC * CF_COUNT + (kBlock / LANES) * nb * 3 + 3) & ~3) + link_store_floats(tid / LANES, nd);     // 16-byte aligned
 }
 
 // ---- host mirror (b2g_task_step_host): the step's outputs (obs_clamped | rew | reset | timeout, the b2g_task_host_layout arena)
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_mirror_host(HostMirror H, size_t n16) {
 
 template <int LANES, int NL, bool FIXED, bool HF>
 __global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, valid, sc, bf);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
 // exceed one wave of the uncapped variant
 template <int LANES, int NL, bool HF, int MINB = 1>
 __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArgs T, HostMirror H) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
@@ -177,14 +177,14 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArg
 }
 
 __global__ void __launch_bounds__(kBlock) k_houndarm_step(SimArgs A, TaskArgs T) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     houndarm_step_thread(A, T, env, valid, sc, bf);
 }
 
 __global__ void __launch_bounds__(kBlock) k_cartpole_step(SimArgs A, TaskArgs T) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     cartpole_step_thread(A, T, env, valid, sc, bf);
@@ -209,7 +209,7 @@ __device__ __forceinline__ bool last_block_arrives(unsigned* ticket) {
 
 template <int LANES, int NL, bool HF>
 __global__ void __launch_bounds__(kBlock) k_terrain_phys(SimArgs A, TerrainArgs T) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     terrain_phys_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kPostBlock) k_terrain_post(SimArgs A, TerrainA
 
 template <int LANES, int NL>
 __global__ void __launch_bounds__(kBlock) k_anymal_reset_all(SimArgs A, TaskArgs T) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     anymal_reset_all_thread<LANES, NL>(A, T, env, lane, valid);
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kBlock) k_anymal_reset_all(SimArgs A, TaskArgs
 
 template <int LANES, int NL, bool FIXED>
 __global__ void __launch_bounds__(kBlock) k_probe(SimArgs A, float* qdd, float* a0) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
     const DevModel* M = A.M;
@@ -405,7 +405,7 @@ namespace {
 
 size_t smem_bytes(const b2g_sim* s) {
     const int epb = kBlock / s->v.lanes;
-    const size_t links = s->v.nl > 3 ? link_store_floats(epb, s->model.n_dof) : 0;     // links_in_shared variants
+    const size_t links = kLinksShared && s->v.nl > 3 ? 4 + link_store_floats(epb, s->model.n_dof) : 0;     // links_in_shared variants
     return sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)epb * s->model.n_bodies * 3 + links);
 }
 
@@ -587,7 +587,7 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
     }
     if (s->task_kind == 4) {     // one thread per environment whatever the generic kernels' lane count is
         const int g1 = (s->n_envs + kBlock / kSparse - 1) / (kBlock / kSparse);
-        const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + link_store_floats(kBlock, s->model.n_dof));
+        const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + (kLinksShared ? 4 + link_store_floats(kBlock, s->model.n_dof) : 0));
         k_houndarm_step<<<g1, kBlock, sm1, st>>>(A, T);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -979,7 +979,7 @@ int b2g_task_houndarm_create(b2g_sim* s, const b2g_houndarm_cfg* cfg) {
     s->seed = cfg->seed;
     s->task_kind = 4;
     if (s->has_task) return B2G_OK;
-    const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + link_store_floats(kBlock, s->model.n_dof));
+    const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + (kLinksShared ? 4 + link_store_floats(kBlock, s->model.n_dof) : 0));
     cudaFuncSetAttribute(k_houndarm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
     return alloc_task_buffers(s, 10, s->model.n_dof, 9);
 }

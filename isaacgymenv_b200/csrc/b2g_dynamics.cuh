@@ -167,26 +167,43 @@ B2G_HD B2G_INL EnvDr load_env_dr(const float* friction, const float* env_scale, 
     return d;
 }
 
-// per-link state of the recursions
-struct LinkData {
+// per-link state of the recursions.  Members are grouped in 16-byte units so that the shared-memory variant moves them with
+// 128-bit accesses; 11 units per link (one of padding) keeps the eight lanes of an environment, which walk their chains side
+// by side, on different bank quads.
+struct alignas(16) LinkData {
     M3 Rl;             // link rotation (world axes)
     V3 pl;             // link origin relative to the root origin
-    SV S, cb, vl;      // joint motion subspace, velocity-product term, link velocity
-    SV U;              // I^A S
+    SV S, cb;          // joint motion subspace, velocity-product term
+    SV vl, U;          // link velocity, I^A S
     float tau, dext;   // joint-space force, joint-space diagonal (armature + implicit drive / limit terms)
     float Dinv, u;
-    float pad;         // 41 words: lanes that walk their chains side by side land in different banks
+    float pad[4];
 };
-// Rolled link loops (NL > 3) index the link state dynamically: as per-thread arrays it lives in local memory (960 B per thread,
-// more than L1 holds for a resident wave -- 28 % L1 misses and 90 MB of DRAM traffic per UsefulHound step, measured), so the
-// long-chain variant keeps it in shared memory instead: one LinkData per DOF of the environment, slot = DOF index.
-static_assert(sizeof(LinkData) == 41 * sizeof(float), "LinkData is 41 packed floats");
+// Rolled link loops (NL > 3) index the link state dynamically, so as per-thread arrays it lives in local memory (960 B per
+// thread, more than L1 holds for a resident wave: 28 % L1 misses measured on UsefulHound).  links_in_shared() moves it to shared
+// memory instead: one LinkData per DOF of the environment, slot = DOF index.
+static_assert(sizeof(LinkData) == 44 * sizeof(float), "LinkData is 11 x 16 bytes");
 template <int NL>
-B2G_HD constexpr bool links_in_shared() {
-#if defined(B2G_LINKS_LOCAL)
+B2G_HD constexpr bool link_loops_rolled() {
+#if defined(B2G_ROLL_LINKS)
+    return true;
+#elif defined(B2G_UNROLL_LINKS)
     return false;
 #else
     return NL > 3;
+#endif
+}
+#if defined(B2G_LINKS_SHARED)
+constexpr bool kLinksShared = true;
+#else
+constexpr bool kLinksShared = false;
+#endif
+template <int NL>
+B2G_HD constexpr bool links_in_shared() {
+#if defined(B2G_LINKS_SHARED)
+    return link_loops_rolled<NL>();
+#else
+    return false;
 #endif
 }
 #if defined(B2G_HOST_EMU)
@@ -303,7 +320,7 @@ B2G_LINK_UNROLL
                 L[j].tau = t;
                 L[j].dext = de;
                 Rp = L[j].Rl; pp = L[j].pl; vp = L[j].vl;
-            } else if (!LSH) {      // unused link slots are never read; in registers they are defined anyway (no cost once unrolled)
+            } else if (!link_loops_rolled<NL>()) {      // unused link slots are never read; in registers they are defined anyway (free once unrolled)
                 L[j].Rl = R0; L[j].pl = V3{0, 0, 0}; L[j].S = sv0(); L[j].cb = sv0(); L[j].vl = sv0(); L[j].tau = 0; L[j].dext = 1.0f;
             }
         }
@@ -332,7 +349,7 @@ B2G_LINK_UNROLL
                 L[j].u = L[j].tau - dot(L[j].S, pA);
                 IAc = rank1_sub(I, L[j].U, L[j].Dinv);
                 pAc = pA + mul(IAc, L[j].cb) + L[j].U * (L[j].u * L[j].Dinv);
-            } else if (!LSH) {
+            } else if (!link_loops_rolled<NL>()) {
                 L[j].U = sv0(); L[j].Dinv = 0.0f; L[j].u = 0.0f;
             }
         }
