@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kBlock) k_terrain_phys(SimArgs A, TerrainArgs 
 // 16 threads per environment (kPostSub), 16 environments per block
 constexpr int kPostSub = 16, kPostBlock = 256, kPostEnvs = kPostBlock / kPostSub;
 template <int LANES, int NL>
-__global__ void __launch_bounds__(kPostBlock) k_terrain_post(SimArgs A, TerrainArgs T) {
+__global__ void __launch_bounds__(kPostBlock) k_terrain_post(SimArgs A, TerrainArgs T, HostMirror H) {
     static_assert(LANES <= kPostSub, "chain lanes are the first sub-threads of an environment");
     // one scalar for ALL resetting envs, reduced once by the last block of k_terrain_phys
     const float cnorm = (T.cfg.custom_origins && T.cfg.curriculum && T.init_done) ? *T.cnorm : 0.0f;
@@ -243,6 +243,10 @@ __global__ void __launch_bounds__(kPostBlock) k_terrain_post(SimArgs A, TerrainA
     const int e = blockIdx.x * EPB + tid / kPostSub;
     const bool valid = e < A.n_envs;
     terrain_post_thread<LANES, NL, kPostSub>(A, T, valid ? e : A.n_envs - 1, tid % kPostSub, valid, cnorm);
+    if (H.dst) {      // b2g_task_step_host: this block's rows cross PCIe while the other blocks are still working
+        const int m0 = blockIdx.x * EPB, left = A.n_envs - m0;
+        mirror_block(H, m0, left < EPB ? left : EPB);
+    }
     // extras["episode"] (anymal_terrain.py:420-425): means over the envs that reset this step.  Per-block sums in env order,
     // then the last block to arrive adds the blocks in block order: fixed order, deterministic, no extra launch
     if (!T.extras) return;
@@ -568,12 +572,13 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         const bool advance = s->auto_step && post_only == 0;
         R.cnorm = s->cnorm; R.extras_part = s->extras_part; R.extras = s->extras; R.tickets = s->tickets;
         R.step_ctr_advance = advance ? s->step_ctr : nullptr;
+        const HostMirror H3 = (hm && post_only == 0) ? *hm : HostMirror{};     // the mirror is the tail of k_terrain_post
         if (s->v.lanes == 4) {
             if (s->has_hf) k_terrain_phys<4, 3, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<4, 3, false><<<grid, kBlock, sm, st>>>(A, R);
-            if (post_only != 2) k_terrain_post<4, 3><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R);
+            if (post_only != 2) k_terrain_post<4, 3><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R, H3);
         } else {
             if (s->has_hf) k_terrain_phys<8, 6, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<8, 6, false><<<grid, kBlock, sm, st>>>(A, R);
-            if (post_only != 2) k_terrain_post<8, 6><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R);
+            if (post_only != 2) k_terrain_post<8, 6><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R, H3);
         }
         if (post_only == 2) {
             s->launches += 1;
@@ -1209,7 +1214,7 @@ int b2g_task_anymal_step_host(b2g_sim* s, const float* actions_host, float* obs_
         } else {
             cudaGetLastError();
         }
-        const bool fused_tail = H.dst && s->task_kind == 1;
+        const bool fused_tail = H.dst && (s->task_kind == 1 || s->task_kind == 3);     // flat tasks: tail of k_anymal_step; rough terrain: tail of k_terrain_post
         const int rc = launch_anymal_step(s, actions_dev, st, 0, fused_tail ? &H : nullptr);
         if (rc != B2G_OK) return rc;
         if (H.dst) {

@@ -1069,10 +1069,10 @@ def hf_coarse_case(robot="useful_hound", n=16, seed=5, slope_scale=1.0):
     return art, hf_t, tr.heightsamples, root, dof
 
 
-def check_hf_coarse_identical(simulate, robot="useful_hound", steps=25):
+def check_hf_coarse_identical(simulate, robot="useful_hound", steps=25, n=16):
     """The coarse-bound early-out must never change a result: B2G_NO_HFC=1 (exhaustive candidate tests) vs default, bit for bit.
     `simulate(art, sp, props, hf_t, samples, root, dof, steps)` -> (root, dof, contact) after `steps` sim steps."""
-    art, hf_t, samples, root, dof = hf_coarse_case(robot)
+    art, hf_t, samples, root, dof = hf_coarse_case(robot, n=n)
     sp = terrain_params()
     props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 80.0, 2.0)
     outs = []

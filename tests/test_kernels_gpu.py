@@ -76,3 +76,30 @@ def test_jacobian_mass_matrix(robot):
 
 def test_houndarm_fused_step():
     kc.check_houndarm_step(make, n=48)
+
+
+def _gpu_sim_hf(art, sp, props, hf_t, samples, root, dof, steps):
+    import ctypes as C
+
+    import numpy as np
+
+    be = make(art, sp, props, root.shape[0])
+    try:
+        smp = np.ascontiguousarray(samples, np.int16)
+        be._lib.check(be.lib.b2g_sim_add_heightfield(be.sim, C.byref(hf_t), smp.ctypes.data_as(C.c_void_p)), "add_heightfield")
+        be.set_state(root, dof)
+        tgt = dof[:, :, 0].copy()
+        contact = None
+        for _ in range(steps):
+            _, contact = be.simulate(tgt, np.zeros_like(tgt))
+        r, d = be.get_state()
+    finally:
+        be.close()
+    return r, d, contact
+
+
+@pytest.mark.parametrize("robot", ["useful_hound", "hound", "anymal_minimal"])
+def test_hf_coarse_bound_identical(robot):
+    """The coarse heightfield bound (per-link contact early-out on rough terrain) never changes a result: library built with and
+    without it (B2G_NO_HFC=1), bit for bit, robots standing, tumbling and outside the field."""
+    kc.check_hf_coarse_identical(_gpu_sim_hf, robot, steps=30, n=256)
