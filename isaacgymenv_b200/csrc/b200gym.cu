@@ -218,8 +218,14 @@ __global__ void __launch_bounds__(kBlock) k_terrain_phys(SimArgs A, TerrainArgs 
     if (T.cnorm && T.cfg.custom_origins && T.cfg.curriculum && T.init_done) {
         __shared__ float red[kBlock];
         if (last_block_arrives(T.tickets + 0)) {
-            float acc = 0.0f;
-            for (int i = threadIdx.x; i < A.n_envs; i += kBlock) acc += __ldcg(T.resetw + i);
+            float acc = 0.0f;     // 16 loads in flight, added in index order (the + 0.0f of a missing tail element is exact)
+            for (int i0 = threadIdx.x; i0 < A.n_envs; i0 += kBlock * 16) {
+                float v[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) v[u] = i0 + u * kBlock < A.n_envs ? __ldcg(T.resetw + i0 + u * kBlock) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 16; u++) acc += v[u];
+            }
             red[threadIdx.x] = acc;
             __syncthreads();
             for (int o = kBlock / 2; o > 0; o >>= 1) {
@@ -242,32 +248,48 @@ __global__ void __launch_bounds__(kPostBlock) k_terrain_post(SimArgs A, TerrainA
     constexpr int EPB = kPostEnvs;
     const int e = blockIdx.x * EPB + tid / kPostSub;
     const bool valid = e < A.n_envs;
-    terrain_post_thread<LANES, NL, kPostSub>(A, T, valid ? e : A.n_envs - 1, tid % kPostSub, valid, cnorm);
+    __shared__ float rep[kPostEnvs][16];      // this block's report rows | reset flag | terrain level
+    __shared__ float red[15][kPostBlock];
+    terrain_post_thread<LANES, NL, kPostSub>(A, T, valid ? e : A.n_envs - 1, tid % kPostSub, valid, cnorm, valid ? rep[tid / kPostSub] : nullptr);
     if (H.dst) {      // b2g_task_step_host: this block's rows cross PCIe while the other blocks are still working
         const int m0 = blockIdx.x * EPB, left = A.n_envs - m0;
         mirror_block(H, m0, left < EPB ? left : EPB);
     }
     // extras["episode"] (anymal_terrain.py:420-425): means over the envs that reset this step.  Per-block sums in env order,
-    // then the last block to arrive adds the blocks in block order: fixed order, deterministic, no extra launch
+    // then the last block to arrive adds the blocks in a fixed order (strided partial sums, pairwise tree): deterministic, no
+    // extra launch
     if (!T.extras) return;
-    __shared__ float tot[16];
     __syncthreads();
     if (tid < 15) {
-        const int e0 = blockIdx.x * EPB, e1 = e0 + EPB < A.n_envs ? e0 + EPB : A.n_envs;
+        const int cnt = A.n_envs - blockIdx.x * EPB < EPB ? A.n_envs - blockIdx.x * EPB : EPB;
         float acc = 0.0f;
-        for (int i = e0; i < e1; i++)
-            acc += tid < 13 ? T.report[(size_t)tid * A.n_envs + i] : tid == 13 ? (T.reset[i] != 0 ? 1.0f : 0.0f) : (float)T.terrain_levels[i];
+        for (int i = 0; i < cnt; i++) acc += rep[i][tid];
         T.extras_part[(size_t)blockIdx.x * 16 + tid] = acc;
     }
     if (last_block_arrives(T.tickets + 1)) {
-        if (tid < 15) {
-            float acc = 0.0f;
-            for (int b = 0; b < (int)gridDim.x; b++) acc += __ldcg(T.extras_part + (size_t)b * 16 + tid);
-            tot[tid] = acc;
+        float acc[15];
+#pragma unroll
+        for (int k = 0; k < 15; k++) acc[k] = 0.0f;
+        for (int b = tid; b < (int)gridDim.x; b += kPostBlock) {
+            float v[15];
+#pragma unroll
+            for (int k = 0; k < 15; k++) v[k] = __ldcg(T.extras_part + (size_t)b * 16 + k);
+#pragma unroll
+            for (int k = 0; k < 15; k++) acc[k] += v[k];
         }
+#pragma unroll
+        for (int k = 0; k < 15; k++) red[k][tid] = acc[k];
         __syncthreads();
-        if (tid < 13 && tot[13] > 0.0f) T.extras[tid] = tot[tid] / tot[13] * (1.0f / T.cfg.max_episode_length_s);
-        if (tid == 13 && tot[13] > 0.0f) { T.extras[13] = tot[14] / (float)A.n_envs; T.extras[14] = tot[13]; }
+        for (int o = kPostBlock / 2; o > 0; o >>= 1) {
+            if (tid < o) {
+#pragma unroll
+                for (int k = 0; k < 15; k++) red[k][tid] += red[k][tid + o];
+            }
+            __syncthreads();
+        }
+        const float cnt = red[13][0];
+        if (tid < 13 && cnt > 0.0f) T.extras[tid] = red[tid][0] / cnt * (1.0f / T.cfg.max_episode_length_s);
+        if (tid == 13 && cnt > 0.0f) { T.extras[13] = red[14][0] / (float)A.n_envs; T.extras[14] = cnt; }
         if (tid == 0 && T.step_ctr_advance) *T.step_ctr_advance += 1;     // end of the step: the next step sees the next counter value
     }
 }

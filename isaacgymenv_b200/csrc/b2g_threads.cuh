@@ -929,7 +929,8 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
 // share the element-wise passes (height scan, noise + clamp, report rows).  The device kernel runs 16 per environment -- the
 // pass is a latency chain per element, so the extra warps are what hides it; the host emulator runs NSUB = LANES.
 template <int LANES, int NL, int NSUB = LANES>
-B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, int env, int lane, bool valid, float curriculum_norm) {
+B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, int env, int lane, bool valid, float curriculum_norm,
+                                        float* rep_row = nullptr) {   // rep_row: 16 floats of this environment for the block's extras sums
     const DevModel* M = A.M;
     const b2g_terrain_cfg& C = T.cfg;
     const int nd = M->n_dof, N = A.n_envs;
@@ -1102,9 +1103,12 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
             if (reset) T.feet_air_time[(size_t)env * 4 + k] = 0.0f;
         for (int k = lane; k < 13; k += NSUB) {
             float* es = T.episode_sums + (size_t)k * N + env;
-            T.report[(size_t)k * N + env] = reset ? *es : 0.0f;
+            const float rv = reset ? *es : 0.0f;
+            T.report[(size_t)k * N + env] = rv;
+            if (rep_row) rep_row[k] = rv;
             if (reset) *es = 0.0f;
         }
+        if (rep_row && lane == 0) { rep_row[13] = reset ? 1.0f : 0.0f; rep_row[14] = (float)level; }
         if (lane == 0) {
             if (reset) {
                 for (int k = 0; k < 13; k++) A.root[(size_t)env * 13 + k] = root[k];
