@@ -165,7 +165,10 @@ int b2g_sim_set_params(b2g_sim* sim, const b2g_sim_params* params);       /* gym
 int b2g_sim_get_params(const b2g_sim* sim, b2g_sim_params* out);          /* gym.get_sim_params */
 /* gym.add_ground (tasks/anymal.py:159-164): sets has_ground + friction in the params */
 int b2g_sim_add_ground(b2g_sim* sim, float static_friction, float dynamic_friction, float restitution);
-/* gym.add_triangle_mesh for a gridded terrain (tasks/anymal_terrain.py:196-209): host int16 samples */
+/* gym.add_triangle_mesh for a gridded terrain (tasks/anymal_terrain.py:196-209): host int16 samples.  Once the articulation is
+ * known as well, a coarse conservative bound of the field (max height / min normal z per 8x8-sample block, dilated by the largest
+ * link radius) is built for the kernels' per-link contact early-out; it never changes a result.  Environment switch
+ * B2G_NO_HFC=1 (read here) leaves it out (A/B timing, bit-identity tests). */
 int b2g_sim_add_heightfield(b2g_sim* sim, const b2g_heightfield* hf, const int16_t* samples_host);
 /* gym.load_asset + N x (create_env, create_actor, set_actor_dof_properties) (tasks/anymal.py:205-216).
  * root_pose7 = start pose (pos3, quat xyzw) given to create_actor; env_spacing/num_per_row = create_env grid. */

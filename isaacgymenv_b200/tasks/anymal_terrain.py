@@ -5,7 +5,7 @@ Same configuration keys, attributes and step semantics: explicit PD torques reco
 13-term reward, terrain curriculum, pushes, observation noise, ``extras["episode"]`` reward means, boolean ``reset_buf``.
 
 ``step()`` is two launches of hand-written sm_100a kernels (``k_terrain_phys``: 5 sim steps + termination + reward;
-``k_terrain_post``: reset + curriculum + observations + noise) plus a one-block reduction for ``extras``; every task
+``k_terrain_post``: reset + curriculum + observations + noise + the ``extras`` means, reduced by the last block to arrive); every task
 buffer (``commands``, ``torques``, ``last_actions``, ``feet_air_time``, ``episode_sums``, ``terrain_levels`` ...) aliases
 sim-owned device memory.  The terrain itself comes from ``isaacgymenv_b200.terrain`` (Isaac Gym's ``terrain_utils`` is not
 part of the reference tree) and is collided as a height grid.
