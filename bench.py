@@ -270,7 +270,7 @@ def run_ours(args):
                         "d2h_bytes_per_step": n * env.num_obs * 4 + n * 4 + n * 8 + n * 8, "ms_per_step": e2e_ms / args.steps,
                         "path": "b2g_task_step_host (C ABI), one blocking call per step: pinned host actions (read in place by the kernel over PCIe) -> "
                                 "obs/rew/reset/time_outs stored by the SMs into the caller's pinned buffer (b2g_task_host_layout; tail of the fused "
-                                "step kernel for the flat tasks, k_mirror_host otherwise), completion by a published sequence word the host polls"
+                                "step kernel for the flat tasks / of k_terrain_post for the rough-terrain tasks, k_mirror_host otherwise), completion by a published sequence word the host polls"
                                 + (" [B2G_HOST_MIRROR=0: copy-engine D2H + stream sync]" if os.environ.get("B2G_HOST_MIRROR", "1")[:1] == "0" else "")},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -350,7 +350,7 @@ int b2g_task_set_rand_override(b2g_sim* sim, int use_rand_override);
 /* host-buffer entry used by the end-to-end benchmark and non-torch callers: blocking, returns when the results are in the
  * caller's buffers.  Page-locked action buffers are read by the kernel in place, pageable ones are staged with one H2D copy.
  * Page-locked result buffers in the packed b2g_task_host_layout are written by the SMs themselves (tail of the fused step
- * kernel for the flat tasks, k_mirror_host otherwise) and the call returns when the published sequence word arrives -- no
+ * kernel for the flat tasks and of k_terrain_post for the rough-terrain tasks, k_mirror_host otherwise) and the call returns when the published sequence word arrives -- no
  * copy command, no stream synchronisation; any other buffers are served with D2H copies + cudaStreamSynchronize.
  * Environment switch B2G_HOST_MIRROR=0 forces the copy path (A/B timing). */
 int b2g_task_anymal_step_host(b2g_sim* sim, const float* actions_host, float* obs_host, float* rew_host,

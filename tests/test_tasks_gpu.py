@@ -212,7 +212,7 @@ def test_generic_jacobian_and_mass_matrix_agree_with_the_fused_arm_slices():
 def test_step_host_matches_device_step(task, nact, n):
     """b2g_task_step_host (the host-buffer entry the end-to-end benchmark times) against the device-pointer step on a twin
     sim: (a) page-locked buffers in the packed b2g_task_host_layout (zero-copy actions; the SMs store the results into the
-    caller's buffer -- as the tail of the fused flat-task kernel, or by k_mirror_host -- and the call returns when the published
+    caller's buffer -- as the tail of the fused flat-task kernel / of k_terrain_post, or by k_mirror_host -- and the call returns when the published
     sequence number arrives, without a stream synchronisation: the buffer is snapshotted right after the call returns),
     (b) pageable numpy buffers laid out separately (staged actions, one copy per result) -- all three bit-identical.  Ragged
     environment counts exercise the partial last block of the mirror."""
