@@ -179,9 +179,11 @@ struct alignas(16) LinkData {
     float Dinv, u;
     float pad[4];
 };
-// Rolled link loops (NL > 3) index the link state dynamically, so as per-thread arrays it lives in local memory (960 B per
-// thread, more than L1 holds for a resident wave: 28 % L1 misses measured on UsefulHound).  links_in_shared() moves it to shared
-// memory instead: one LinkData per DOF of the environment, slot = DOF index.
+// Rolled link loops (NL > 3) index the link state dynamically, so as per-thread arrays it lives in local memory (1056 B per
+// thread in lane-interleaved lines, more than L1 holds for a resident wave: 28-33 % L1 misses measured on UsefulHound).
+// -DB2G_LINKS_SHARED moves it to shared memory instead (one LinkData per DOF of the environment, slot = DOF index).  Measured on
+// B200: the stall class halves but the extra instructions cost more -- UsefulHound 372 us per step against
+// 350 us for the aligned per-thread arrays -- so the local-memory form is the default and the shared form an experiment switch.
 static_assert(sizeof(LinkData) == 44 * sizeof(float), "LinkData is 11 x 16 bytes");
 template <int NL>
 B2G_HD constexpr bool link_loops_rolled() {
