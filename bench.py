@@ -249,9 +249,10 @@ def run_ours(args):
         achieved = algo_bytes * n / kernel_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tp) and args.task == "Anymal":
+        if os.path.isfile(tp):      # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu captures
             try:
-                traffic = json.load(open(tp)).get("k_anymal_step_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("k_anymal_step_dram_bytes_per_launch") if args.task == "Anymal" else tj.get("per_task", {}).get(args.task, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         cpu = None
