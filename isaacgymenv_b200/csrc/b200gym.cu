@@ -80,16 +80,22 @@ __device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int&
     constexpr int EPW = 32 / LANES / kSparse, EPB = EnvsPerBlock<LANES>::value;
     const int wl = tid & 31;
     const bool live = wl < EPW * LANES;
-    const int eib = (tid >> 5) * EPW + (live ? wl / LANES : 0);
+    int eib = (tid >> 5) * EPW + (live ? wl / LANES : 0);
     lane = tid % LANES;
+    if (LANES == kSplit8) {      // Grp<8> layout: chains 0-3 in lanes 0-15 (environment-major), chains 4-7 in lanes 16-31 (chain-major)
+        static_assert(LANES != 8 || kSparse == 1, "the 8-lane layout assumes full warps");
+        eib = (tid >> 5) * EPW + (wl < 16 ? wl >> 2 : wl & 3);
+        lane = wl < 16 ? (wl & 3) : 4 + ((wl - 16) >> 2);
+    }
     const int e = blockIdx.x * EPB + eib;
     valid = live && e < n_envs;
     env = (e < n_envs) ? e : n_envs - 1;
     sc.base = smem + tid;
     sc.stride = kBlock;
-    bf = smem + kBlock * MAXC * CF_COUNT + (tid / LANES) * nb * 3;     // one accumulator per lane group, idle groups included
+    const int grp = LANES == kSplit8 ? eib : tid / LANES;
+    bf = smem + kBlock * MAXC * CF_COUNT + grp * nb * 3;     // one accumulator per lane group, idle groups included
     // link store of the rolled long-chain variants (b2g_dynamics.cuh::links_in_shared): one LinkData per DOF per lane group
-    sc.links = smem + ((kBlock * MAXC * CF_COUNT + (kBlock / LANES) * nb * 3 + 3) & ~3) + link_store_floats(tid / LANES, nd);     // 16-byte aligned
+    sc.links = smem + ((kBlock * MAXC * CF_COUNT + (kBlock / LANES) * nb * 3 + 3) & ~3) + link_store_floats(grp, nd);     // 16-byte aligned
 }
 
 // ---- host mirror (b2g_task_step_host): the step's outputs (obs_clamped | rew | reset | timeout, the b2g_task_host_layout arena)

@@ -101,13 +101,37 @@ struct Grp {
     static void sync() { emu_barrier(); }
 };
 #else
+// Warp layout of a lane group.  LANES <= 4: consecutive lanes.  LANES == 8 (the long-chain variant, 4 environments per warp):
+// chains 0-3 of the four environments sit in lanes 0-15 (lane = 4 e + c), chains 4-7 in lanes 16-31 chain-major
+// (lane = 16 + 4 (c - 4) + e).  The per-thread link state of that variant lives in local memory, whose lines interleave the 32
+// lanes word by word: with a hound + arm (chains 0-3 = legs, 4 = arm, 5-7 unused) the legs fill two 32-byte sectors and the four
+// arms share one, instead of every environment's 8 lanes half-filling a sector of its own.  The reduction pairs the same chains in
+// the same order as a plain xor butterfly (c ^ 4, c ^ 2, c ^ 1), so sums are bit-identical to the consecutive layout.
+#if defined(B2G_GRP8_CONSECUTIVE)      // A/B switch: the plain consecutive layout for the 8-lane variant as well
+constexpr int kSplit8 = 0;
+#else
+constexpr int kSplit8 = 8;
+#endif
 template <int LANES>
 struct Grp {
+    static __device__ __forceinline__ int phys_lane(int chain) {      // physical lane of chain `chain` of the caller's environment
+        const int wl = threadIdx.x & 31;
+        if (LANES != kSplit8) return (wl / LANES) * LANES + chain;
+        const int e = wl < 16 ? wl >> 2 : wl & 3;
+        return chain < 4 ? 4 * e + chain : 16 + 4 * (chain - 4) + e;
+    }
     static __device__ __forceinline__ float bcast(float x, int src) {
         if (LANES == 1) return x;
-        return __shfl_sync(0xffffffffu, x, src, LANES);
+        return __shfl_sync(0xffffffffu, x, phys_lane(src));
     }
     static __device__ __forceinline__ float sum(float x) {
+        if (LANES == kSplit8) {
+            const int wl = threadIdx.x & 31, up = wl >> 4;
+            x += __shfl_sync(0xffffffffu, x, up ? 4 * (wl & 3) + ((wl - 16) >> 2) : 16 + 4 * (wl & 3) + (wl >> 2));   // c ^ 4
+            x += __shfl_xor_sync(0xffffffffu, x, up ? 8 : 2);                                                            // c ^ 2
+            x += __shfl_xor_sync(0xffffffffu, x, up ? 4 : 1);                                                            // c ^ 1
+            return x;
+        }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         return x;
