@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(kBlock) k_terrain_phys(SimArgs A, TerrainArgs 
 }
 
 // 16 threads per environment (kPostSub), 16 environments per block
-constexpr int kPostSub = 16, kPostBlock = 256, kPostEnvs = kPostBlock / kPostSub;
+#ifndef B2G_POST_SUB
+#define B2G_POST_SUB 16
+#endif
+constexpr int kPostSub = B2G_POST_SUB, kPostBlock = 256, kPostEnvs = kPostBlock / kPostSub;
 template <int LANES, int NL>
 __global__ void __launch_bounds__(kPostBlock) k_terrain_post(SimArgs A, TerrainArgs T, HostMirror H) {
     static_assert(LANES <= kPostSub, "chain lanes are the first sub-threads of an environment");
