@@ -56,17 +56,50 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples during the timed region: NVML in a thread of this process (one light query per GPU every
+    10 ms -- a per-rank `nvidia-smi -lms` subprocess takes driver locks the ranks' launches then wait on), nvidia-smi as the
+    fallback.  Rank 0 samples every GPU of the job."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices):
+        self.indices = list(indices) if isinstance(indices, (list, tuple, range)) else [indices]
+        self.rows, self.proc, self.stop_flag, self.thread, self.mode = [], None, False, None, None
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self, nv, handles):
+        while not self.stop_flag:
+            for h in handles:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                    get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                    bits = int(get(h))
+                    for bit, name in self.REASONS:
+                        if bits & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.01)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+            handles = [nv.nvmlDeviceGetHandleByIndex(int(vis[i]) if i < len(vis) else i) for i in self.indices]
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handles), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(map(str, self.indices)), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -76,10 +109,14 @@ class ClockSampler:
             self.rows.append([t.strip() for t in line.split(",")])
 
     def stop(self):
+        if self.thread:
+            time.sleep(0.06)
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons = list(self.sm), list(self.mx), set(self.reasons)
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
@@ -89,24 +126,25 @@ class ClockSampler:
             except Exception:
                 pass
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.mode}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "source": self.mode,
+                "gpus": len(self.indices)}
 
 
 def oracle_setup(n_envs, threads):
-    import numpy as np
     from isaacgymenv_b200 import _abi
-    from oracle.cpu_baseline import CpuAnymalStep
+    from oracle.cpu_baseline import CpuAnymalStepNative
     from tests import kernel_checks as kc
 
     art = kc.load_robot("anymal")
     sp = kc.flat_params()
     props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 85.0, 2.0)
-    c = kc.anymal_cfg(art)
-    return CpuAnymalStep(_abi.pack_model(art), sp, props, kc.cfg_dict(c, art.num_dofs), n_envs, threads=threads, dtype=np.float32)
+    return CpuAnymalStepNative(_abi.pack_model(art), sp, props, kc.anymal_cfg(art), n_envs, threads=threads)
 
 
 def time_cpu(n_envs, steps, warmup, threads):
+    """The CPU restatement of the whole flat-task step (C, OpenMP over the environments, -O3 -march=native built on this
+    machine) on `threads` host threads: returns (env-steps/s, s per step, compiler flags)."""
     import numpy as np
 
     cpu = oracle_setup(n_envs, threads)
@@ -118,47 +156,50 @@ def time_cpu(n_envs, steps, warmup, threads):
     for i in range(steps):
         cpu.step(acts[i % 8])
     dt = time.perf_counter() - t0
-    return n_envs * steps / dt, dt / steps
+    return n_envs * steps / dt, dt / steps, cpu.flags
+
+
+def bench_config(task, n):
+    """`config` of the JSON line: identical for the two arms (the driver compares them)."""
+    return {"workload": TASKS[task][4], "task": task, "envs_per_gpu": n}
+
+
+CPU_PREROLL = 10      # untimed CPU steps so the robots have landed (contact steady state), on top of --warmup
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n_envs = 1024     # bounded sample of the 4096-env batch (envs are independent: throughput is per env-step)
-    value, per_step = time_cpu(n_envs, args.steps, args.warmup, threads)
+    threads = len(os.sched_getaffinity(0)) or 1
+    n_envs = ENVS_PER_GPU      # the whole 4096-env batch of the headline config
+    value, per_step, flags = time_cpu(n_envs, args.steps, args.warmup + CPU_PREROLL, threads)
+    sample = (f"all {n_envs} envs x {args.steps} steps after {args.warmup} warm-up + {CPU_PREROLL} pre-roll steps; CPU restatement of the whole step "
+              f"(oracle port in C, OpenMP over envs, gcc {flags}), NOT PhysX: Isaac Gym is a closed binary that is not installed")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{n_envs} envs per step"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{n_envs} of 4096 envs x {args.steps} steps; CPU restatement of the step (oracle), NOT PhysX: Isaac Gym is a closed binary that is not installed"},
+            "config": bench_config("Anymal", n_envs),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
+def measure_task(task, num_envs, steps, warmup, preroll, dev, rank, world, dist, sample_clocks=True):
+    """One hot-path config on this rank's GPU: pre-roll (untimed, so the robots have landed and the contact steady state is what
+    gets timed), warm-up, K timed steps three ways (L2 flushed / warm L2 / end to end through host buffers).  Times are maxima
+    over ranks."""
     import torch
-    import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = f"cuda:{local_rank}"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
     import isaacgymenv_b200
     from isaacgymenv_b200 import _lib
 
     lib = _lib.load()
-    algo_bytes, envs_per_gpu, kernel_name, overrides, workload = TASKS[args.task]
-    if args.num_envs > 0 and args.num_envs != envs_per_gpu:
-        envs_per_gpu = args.num_envs
+    algo_bytes, envs_per_gpu, kernel_name, overrides, workload = TASKS[task]
+    if num_envs > 0 and num_envs != envs_per_gpu:
+        envs_per_gpu = num_envs
         workload += f" [scaling study: {envs_per_gpu} envs per GPU instead of the config's count]"
-    env = isaacgymenv_b200.make(seed=42 + rank, task=args.task, num_envs=envs_per_gpu, sim_device=dev, rl_device=dev, headless=True, overrides=overrides)
+    local_rank = int(dev.split(":")[1])
+    env = isaacgymenv_b200.make(seed=42 + rank, task=task, num_envs=envs_per_gpu, sim_device=dev, rl_device=dev, headless=True, overrides=overrides)
     n, na = env.num_envs, env.num_actions
     is_terrain = hasattr(env, "common_step_counter")
     g = torch.Generator(device=dev).manual_seed(42 + rank)
@@ -181,17 +222,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    # clocks are sampled from the pre-roll to the end of the e2e loop (the same kernels under the same load as the timed steps)
+    sampler = ClockSampler(list(range(world)) if world > 1 else local_rank) if (sample_clocks and rank == 0) else None
+    if sampler:
+        sampler.start()
+    for i in range(preroll):
+        step_dev(i)
+    for i in range(max(warmup, 3)):
         step_dev(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     # ---- device-resident timing: per-step CUDA events, L2 flushed (untimed) between timed steps ----
     launches0 = lib.b2g_sim_launch_count(env.sim.handle)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     barrier()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(float(i))
         starts[i].record(stream)
         step_dev(i)
@@ -203,7 +248,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         step_dev(i)
     e1.record(stream)
     barrier()
@@ -229,55 +274,113 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         step_host(i)
     e1.record(stream)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     assert torch.isfinite(h_obs).all() and torch.isfinite(h_rew).all()
+    stats = None
+    if hasattr(lib, "b2g_sim_contact_stats"):
+        st = (C.c_int64 * 4)()
+        if lib.b2g_sim_contact_stats(env.sim.handle, st, 0) == 0:
+            stats = {"active_contacts": int(st[0]), "dropped_candidates": int(st[1]), "env_substeps_with_drop": int(st[2]), "env_substeps": int(st[3])}
 
     times = torch.tensor([cold_ms, warm_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     cold_ms, warm_ms, e2e_ms = times.tolist()
+    res = dict(task=task, n=n, na=na, num_obs=env.num_obs, algo_bytes=algo_bytes, kernel=kernel_name, workload=workload, cold_ms=cold_ms, warm_ms=warm_ms,
+               e2e_ms=e2e_ms, launches=int(launches), clocks=clocks, contact_stats=stats)
+    del env, flush, pool, h_arena
+    torch.cuda.empty_cache()
+    return res
+
+
+def traffic_for(task):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed `ncu --set full` captures
+    (profiles/traffic.json; the capture is cold-cache like the flushed timing)."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        tj = json.load(open(tp))
+        return tj.get("k_anymal_step_dram_bytes_per_launch") if task == "Anymal" else tj.get("per_task", {}).get(task, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def roofline_of(res, steps):
+    peak, peak_src = measured_peak()
+    kernel_s = res["cold_ms"] * 1e-3 / steps
+    achieved = res["algo_bytes"] * res["n"] / kernel_s / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_for(res["task"]),
+            "kernel": res["kernel"], "peak_source": peak_src, "algo_bytes_per_env_step": res["algo_bytes"],
+            "note": "latency/issue-bound by construction: the per-launch working set (a few MB) is L2-resident; see profiles/ and DESIGN.md"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from isaacgymenv_b200.utils import affinity
+
+    pin = affinity.pin_to_gpu_numa(local_rank, world)      # the e2e path polls host memory: keep this rank on its GPU's NUMA node
+    res = measure_task(args.task, args.num_envs, args.steps, args.warmup, args.preroll, dev, rank, world, dist)
+    n, na = res["n"], res["na"]
+    # the other BASELINE configs ride in the same line (shorter runs, one GPU only: they are parity-test configs, not the headline)
+    others = {}
+    if args.other_configs and world == 1 and args.task == "Anymal" and args.num_envs <= 0:
+        for t in ("AnymalTerrain", "UsefulHound", "Cartpole"):
+            try:
+                k = min(args.steps, 200)
+                r = measure_task(t, 0, k, min(args.warmup, 20), args.preroll, dev, rank, world, dist, sample_clocks=False)
+                tot = r["n"] * k
+                others[t] = {"workload": r["workload"], "envs": r["n"], "steps": k, "ms_per_step": r["cold_ms"] / k, "value": tot / (r["cold_ms"] * 1e-3),
+                             "value_warm_l2": tot / (r["warm_ms"] * 1e-3), "e2e_value": tot / (r["e2e_ms"] * 1e-3), "unit": UNIT,
+                             "gpu_launches": r["launches"], "roofline": roofline_of(r, k), "contact_stats": r["contact_stats"]}
+            except Exception as exc:      # never lose the headline line to a side config
+                others[t] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0:
         total = world * n * args.steps
+        cold_ms, warm_ms, e2e_ms = res["cold_ms"], res["warm_ms"], res["e2e_ms"]
         value = total / (cold_ms * 1e-3)
-        peak, peak_src = measured_peak()
-        kernel_s = cold_ms * 1e-3 / args.steps
-        achieved = algo_bytes * n / kernel_s / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tp):      # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu captures
-            try:
-                tj = json.load(open(tp))
-                traffic = tj.get("k_anymal_step_dram_bytes_per_launch") if args.task == "Anymal" else tj.get("per_task", {}).get(args.task, {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
         cpu = None
-        if args.task == "Anymal":
-            threads = os.cpu_count() or 1
-            cpu_steps = 6
-            cv, _ = time_cpu(1024, cpu_steps, 1, threads)
+        if args.task == "Anymal" and world == 1:      # CPU baseline beside it: rank 0 at N = 1 only
+            threads = len(os.sched_getaffinity(0)) or 1
+            cpu_steps = 40
+            cv, _, flags = time_cpu(ENVS_PER_GPU, cpu_steps, CPU_PREROLL, threads)
             cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"1024 of 4096 envs x {cpu_steps} steps; CPU restatement of the step (oracle), NOT PhysX (Isaac Gym not installed)"}
+                   "sample": f"all {ENVS_PER_GPU} envs x {cpu_steps} steps after {CPU_PREROLL} pre-roll steps; CPU restatement of the whole step (oracle port in C, "
+                             f"OpenMP over envs, gcc {flags}), NOT PhysX (Isaac Gym not installed)"}
+        cfg = bench_config(args.task, n)
+        if res["workload"] != cfg["workload"]:
+            cfg["workload"] = res["workload"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": cold_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "task": args.task, "envs_per_gpu": n, "l2": "flushed between timed steps (192 MiB fill, untimed)",
-                           "timing": "per-step CUDA events on the launch stream, summed; max over ranks"},
+                "config": cfg, "preroll_steps": args.preroll,
+                "l2": "flushed between timed steps (192 MiB fill, untimed)", "timing": "per-step CUDA events on the launch stream, summed; max over ranks",
                 "value_warm_l2": total / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / args.steps,
                 "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * na * 4,
-                        "d2h_bytes_per_step": n * env.num_obs * 4 + n * 4 + n * 8 + n * 8, "ms_per_step": e2e_ms / args.steps,
+                        "d2h_bytes_per_step": n * res["num_obs"] * 4 + n * 4 + n * 8 + n * 8, "ms_per_step": e2e_ms / args.steps,
                         "path": "b2g_task_step_host (C ABI), one blocking call per step: pinned host actions (read in place by the kernel over PCIe) -> "
                                 "obs/rew/reset/time_outs stored by the SMs into the caller's pinned buffer (b2g_task_host_layout; tail of the fused "
                                 "step kernel for the flat tasks / of k_terrain_post for the rough-terrain tasks, k_mirror_host otherwise), completion by a published sequence word the host polls"
-                                + (" [B2G_HOST_MIRROR=0: copy-engine D2H + stream sync]" if os.environ.get("B2G_HOST_MIRROR", "1")[:1] == "0" else "")},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": kernel_name, "peak_source": peak_src,
-                             "note": "latency/issue-bound by construction: the per-launch working set (a few MB) is L2-resident; see profiles/ and DESIGN.md"},
-                "cpu_baseline": cpu, "clocks": clocks}
+                                + (" [B2G_HOST_MIRROR=0: copy-engine D2H + stream sync]" if os.environ.get("B2G_HOST_MIRROR", "1")[:1] == "0" else ""),
+                        "cpu_affinity": pin},
+                "gpu_launches": res["launches"],
+                "roofline": roofline_of(res, args.steps),
+                "cpu_baseline": cpu, "clocks": res["clocks"], "contact_stats": res["contact_stats"]}
+        if others:
+            line["other_configs"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -291,12 +394,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--num-envs", type=int, default=0, help="environments per GPU (default: the config's own count, 4096 for Anymal); "
                     "other values are a scaling study, not the headline config")
+    ap.add_argument("--preroll", type=int, default=300, help="untimed steps before the warm-up (robots start above the ground and land around step 6; "
+                    "the timed region must be the contact steady state whatever --steps is)")
+    ap.add_argument("--other-configs", type=int, default=1, help="1: also time AnymalTerrain (trimesh), UsefulHound and Cartpole (N=1 only) and report them "
+                    "under other_configs")
     ap.add_argument("--task", default="Anymal", choices=sorted(TASKS), help="hot-path config to time (default: the headline Anymal config)")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps > 50:
-            args.steps = 50      # CPU arm: bounded so the run ends within minutes
-        args.warmup = min(args.warmup, 3)
+        if args.steps > 200:
+            args.steps = 200      # CPU arm: bounded so the run ends within minutes (13 ms per 4096-env step on 16 cores)
+        args.warmup = min(args.warmup, 50)
         run_reference(args)
     else:
         run_ours(args)

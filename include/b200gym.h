@@ -364,6 +364,13 @@ int b2g_task_host_layout(const b2g_sim* sim, int64_t* offsets /*[4]*/, int64_t* 
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 int64_t b2g_sim_launch_count(const b2g_sim* sim);
 
+/* Contact bookkeeping of every sub-step simulated since creation (or the last reset), so that the fixed number of contact
+ * slots per chain (B2G_MAX_CONTACTS_PER_CHAIN) can never bite silently -- PhysX, which the reference uses behind
+ * gym.simulate (vec_task.py:379-382), keeps every contact a body has.  out[0] = active contact points, out[1] = candidates
+ * inside the contact offset that found no free slot and were dropped, out[2] = environment sub-steps with at least one
+ * dropped candidate, out[3] = environment sub-steps simulated.  Synchronises the device.  reset != 0 zeroes the counters. */
+int b2g_sim_contact_stats(b2g_sim* sim, int64_t* out /*[4]*/, int reset);
+
 /* sizeof() of the public PODs (0 model, 1 sim_params, 2 dof_props, 3 heightfield, 4 tensor_desc,
  * 5 anymal_cfg, 6 cartpole_cfg, 7 terrain_cfg, 8 houndarm_cfg) so a foreign-language mirror of this header can verify its layout */
 int b2g_sizeof(int which);

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kBlock) k_probe(SimArgs A, float* qdd, float* 
 #pragma unroll
     for (int j = 0; j < NL; j++)
         if (j < len) st.act[j] = A.actuation[(size_t)env * M->n_dof + d0 + j];
-    substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, load_env_dr(nullptr, A.env_scale, valid ? env : 0), false, sc, bf);
+    substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, load_env_dr(nullptr, A.env_scale, valid ? env : 0, valid), false, sc, bf);
     if (valid) {
 #pragma unroll
         for (int j = 0; j < NL; j++)
@@ -434,6 +434,7 @@ struct b2g_sim {
     unsigned host_seq = 0;
     int use_rand_override = 0;
     int64_t launches = 0;
+    unsigned long long* d_stats = nullptr;   // contact statistics (DevParams::stats), 4 counters; B2G_CONTACT_STATS=0 switches them off
 };
 
 namespace {
@@ -453,6 +454,7 @@ SimArgs make_args(const b2g_sim* s) {
     SimArgs A;
     A.M = s->d_model;
     pack_dev_params(s->params, s->has_hf ? &s->hf : nullptr, s->d_hf, A.P, s->d_hfc, s->hfc_rows, s->hfc_cols);
+    A.P.stats = s->d_stats;
     A.n_envs = s->n_envs;
     A.root = s->t[B2G_T_ROOT_STATE];
     A.dof = s->t[B2G_T_DOF_STATE];
@@ -685,6 +687,15 @@ int b2g_sim_create(int device_id, const b2g_sim_params* params, b2g_sim** out) {
     cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, device_id);
     s->params = *params;
     if (s->params.substeps <= 0) s->params.substeps = 1;
+    const char* cs = getenv("B2G_CONTACT_STATS");
+    if (!(cs && cs[0] == '0')) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device_id);
+        if (cudaMalloc(&s->d_stats, 4 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(s->d_stats, 0, 4 * sizeof(unsigned long long));
+        else s->d_stats = nullptr;
+        cudaSetDevice(prev);
+    }
     *out = s;
     return B2G_OK;
 }
@@ -697,7 +708,7 @@ int b2g_sim_destroy(b2g_sim* s) {
                         s->progress, s->reset_count, s->actions_in, s->torques, s->last_actions, s->last_dof_vel,
                         s->feet_air_time, s->episode_sums, s->env_origins, s->terrain_origins, s->scratch9, s->resetw, s->report, s->measured,
                         s->noise_override, s->push_override, s->extras, s->terrain_levels, s->terrain_types, s->height_samples,
-                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands, s->step_ctr, s->done_ctr, s->cnorm, s->extras_part, s->tickets};
+                        s->arm_mm, s->arm_jac, s->eef_state, s->arm_commands, s->step_ctr, s->done_ctr, s->cnorm, s->extras_part, s->tickets, s->d_stats};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (s->host_flag) cudaFreeHost(s->host_flag);
         return 0;
@@ -1297,6 +1308,19 @@ int b2g_task_step_host(b2g_sim* s, const float* a, float* o, float* r, int64_t* 
 }
 
 int64_t b2g_sim_launch_count(const b2g_sim* s) { return s ? s->launches : 0; }
+
+int b2g_sim_contact_stats(b2g_sim* s, int64_t* out, int reset) {
+    if (!s || !out) return fail(B2G_ERR_ARG, "null argument");
+    if (!s->d_stats) return fail(B2G_ERR_STATE, "contact statistics are switched off (B2G_CONTACT_STATS=0)");
+    return with_device(s, [&]() -> int {
+        unsigned long long h[4];
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(h, s->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 4; i++) out[i] = (int64_t)h[i];
+        if (reset) CUDA_TRY(cudaMemset(s->d_stats, 0, sizeof(h)));
+        return B2G_OK;
+    });
+}
 
 // ---- DLPack export (dlpack v0.8 ABI, declared locally: plain C structs) ----
 typedef struct { int32_t device_type; int32_t device_id; } B2gDLDevice;

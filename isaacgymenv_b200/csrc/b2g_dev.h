@@ -61,6 +61,10 @@ struct DevParams {
     // B2G_HFC_BLOCK x B2G_HFC_BLOCK samples, dilated by the largest link radius, {max height, min normal z}
     const float* hfc;
     int hfc_rows, hfc_cols;
+    // contact statistics (b2g_sim_contact_stats; null -> not collected): [0] active contact points, [1] candidates inside the contact
+    // offset that found no free slot (B2G_MAX_CONTACTS_PER_CHAIN per lane) and were DROPPED, [2] environment sub-steps in which at
+    // least one candidate was dropped, [3] environment sub-steps simulated
+    unsigned long long* stats;
 };
 
 constexpr int B2G_HFC_SHIFT = 3;

@@ -164,6 +164,29 @@ B2G_HD B2G_INL SI grp_sum(const SI& s) {
     return o;
 }
 
+// contact statistics of one sub-step (DevParams::stats): warp-aggregated, at most four reductions without return value per warp
+template <int LANES>
+B2G_HD B2G_INL void contact_stats_add(unsigned long long* stats, int lane, bool live, int ncon, int ndrop) {
+    const float gdrop = Grp<LANES>::sum((float)ndrop);      // dropped candidates of the whole environment
+    const int act = live ? ncon : 0, drop = live ? ndrop : 0;
+    const int envdrop = (live && lane == 0 && gdrop > 0.0f) ? 1 : 0, envs = (live && lane == 0) ? 1 : 0;
+#if defined(B2G_HOST_EMU)
+    if (act) __atomic_add_fetch(stats + 0, (unsigned long long)act, __ATOMIC_RELAXED);
+    if (drop) __atomic_add_fetch(stats + 1, (unsigned long long)drop, __ATOMIC_RELAXED);
+    if (envdrop) __atomic_add_fetch(stats + 2, 1ull, __ATOMIC_RELAXED);
+    if (envs) __atomic_add_fetch(stats + 3, 1ull, __ATOMIC_RELAXED);
+#else
+    const unsigned full = 0xffffffffu;
+    const int wa = __reduce_add_sync(full, act), wd = __reduce_add_sync(full, drop), we = __reduce_add_sync(full, envdrop), wn = __reduce_add_sync(full, envs);
+    if ((threadIdx.x & 31) == 0) {
+        if (wa) atomicAdd(stats + 0, (unsigned long long)wa);
+        if (wd) atomicAdd(stats + 1, (unsigned long long)wd);
+        if (we) atomicAdd(stats + 2, (unsigned long long)we);
+        if (wn) atomicAdd(stats + 3, (unsigned long long)wn);
+    }
+#endif
+}
+
 // state one lane keeps in registers across the sub-steps of a simulate() call
 template <int NL>
 struct LaneState {
@@ -179,9 +202,11 @@ struct LaneState {
 // cfg/task/Anymal.yaml:104-170): shape friction, and scale factors on every link mass (+ inertia), drive stiffness and damping
 struct EnvDr {
     float mu = 1.0f, mass = 1.0f, kp = 1.0f, kd = 1.0f;
+    bool live = true;      // false for the padding threads of the last block (they shadow the last environment): not counted in the statistics
 };
-B2G_HD B2G_INL EnvDr load_env_dr(const float* friction, const float* env_scale, int env) {
+B2G_HD B2G_INL EnvDr load_env_dr(const float* friction, const float* env_scale, int env, bool live = true) {
     EnvDr d;
+    d.live = live;
     if (friction) d.mu = friction[env];
     if (env_scale) {
         d.mass = env_scale[(size_t)env * 4 + 0];
@@ -449,7 +474,7 @@ B2G_LINK_UNROLL
     };
 
     // ---------------- contact candidates ----------------
-    int ncon = 0;
+    int ncon = 0, ndrop = 0;
     const bool ground = HF || (P.has_ground != 0);
     auto test_candidate = [&](int i, const M3& R, V3 p, int jc) {
         const float cx = M->cp[i][0], cy = M->cp[i][1], cz = M->cp[i][2], cr = M->cp[i][3];
@@ -458,6 +483,7 @@ B2G_LINK_UNROLL
         V3 n = V3{0, 0, 1};
         if (HF) ground_sample(P, st.rp.x + rc.x, st.rp.y + rc.y, gh, n);
         const float gap = (st.rp.z + rc.z - gh) * n.z - cr;
+        if (gap < P.contact_offset && ncon >= MAXC) ndrop++;      // no free slot: the candidate is ignored this sub-step (counted, never silent)
         if (gap < P.contact_offset && ncon < MAXC) {
             const V3 r = rc - n * cr;
             V3 t1 = V3{1.0f - n.x * n.x, -n.x * n.y, -n.x * n.z};
@@ -518,6 +544,7 @@ B2G_LINK_UNROLL
     }
 
     const int maxs = Grp<LANES>::warp_max(ncon);
+    if (P.stats) contact_stats_add<LANES>(P.stats, lane, dr.live, ncon, ndrop);
 
     // local Delassus block of every active contact: response of the contact point to unit impulses along n, t1, t2
     // (one code instance for all links: the contact's link index is a run-time value, the chain loops are predicated)

@@ -97,7 +97,7 @@ B2G_HD B2G_INL void simulate_thread(const SimArgs& A, int env, int lane, bool va
             st.act[j] = A.actuation[k];
         }
     }
-    const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0);
+    const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0, valid);
     for (int s = 0; s < A.P.substeps; s++)
         substep<LANES, NL, FIXED, HF, false, (LANES == 4 && NL == 3) || (LANES == 1 && NL == 2)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
     if (valid) {
@@ -237,7 +237,7 @@ B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int 
         }
     }
     if (!T.post_only) {
-        const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0);
+        const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0, valid);
 #pragma unroll 1
         for (int s = 0; s < A.P.substeps; s++)
             substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
@@ -335,7 +335,7 @@ B2G_HD B2G_INL void cartpole_step_thread(const SimArgs& A, const TaskArgs& T, in
     st.act[1] = 0.0f;
     if (!T.post_only) {
         for (int s = 0; s < A.P.substeps; s++)
-            substep<1, 2, true, false, false, true>(M, A.P, 0, 2, 0, st, load_env_dr(nullptr, A.env_scale, valid ? env : 0), s == A.P.substeps - 1, sc, bf);
+            substep<1, 2, true, false, false, true>(M, A.P, 0, 2, 0, st, load_env_dr(nullptr, A.env_scale, valid ? env : 0, valid), s == A.P.substeps - 1, sc, bf);
     }
     long long progress = T.progress[env] + 1;
     long long reset_prev = T.reset[env];
@@ -685,7 +685,7 @@ B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, in
         osc_prepare(mm, J, dpose, eef + 7, C.kp, P);
         osc_apply(P, st.q, st.qd, C.kp_null, effort, u);
         for (int j = 0; j < 6; j++) st.act[j] = (j < n) ? u[j] : 0.0f;
-        const EnvDr dr_env = load_env_dr(A.friction, A.env_scale, valid ? env : 0);
+        const EnvDr dr_env = load_env_dr(A.friction, A.env_scale, valid ? env : 0, valid);
 #pragma unroll 1
         for (int s = 0; s < A.P.substeps; s++)
             substep<1, 6, true, false, false, false>(M, A.P, 0, n, 0, st, dr_env, s == A.P.substeps - 1, sc, bf);
@@ -796,7 +796,7 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
         return;
     }
     if (!T.post_only) {
-        const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0);
+        const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0, valid);
         const int total = C.decimation + C.extra_sim_steps;
 #pragma unroll 1
         for (int it = 0; it < total; it++) {

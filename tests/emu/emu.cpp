@@ -94,10 +94,17 @@ void anymal_env(const SimArgs& A, const TaskArgs& T, int env, int mode) {
 
 // per-env domain-randomisation scales (N,4) used by the next emu_simulate / emu_forward_dynamics calls; null = ones
 static const float* g_env_scale = nullptr;
+// contact statistics of the emulated sub-steps (same counters as b2g_sim_contact_stats)
+static unsigned long long g_stats[4] = {0, 0, 0, 0};
 
 extern "C" {
 
 void emu_set_env_scale(const float* p) { g_env_scale = p; }
+
+void emu_contact_stats(long long* out, int reset) {
+    for (int i = 0; i < 4; i++) out[i] = (long long)g_stats[i];
+    if (reset) for (int i = 0; i < 4; i++) g_stats[i] = 0;
+}
 
 void emu_hfc_stats(long long* out, int reset) {
     out[0] = b2g::emu_hfc_tests; out[1] = b2g::emu_hfc_skips;
@@ -113,6 +120,7 @@ int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, hf, hfs, A.P);
+    A.P.stats = g_stats;
     std::vector<float> hfc;   // coarse heightfield bound, as the library builds it (B2G_NO_HFC=1: exhaustive candidate tests)
     if (hf && hfs && !(getenv("B2G_NO_HFC") && getenv("B2G_NO_HFC")[0] == '1')) {
         build_hf_coarse(hfs, hf->rows, hf->cols, hf->horizontal_scale, hf->vertical_scale, max_link_radius(*dm), hfc, A.P.hfc_rows, A.P.hfc_cols);
@@ -140,6 +148,7 @@ int emu_forward_dynamics(const b2g_model* m, const b2g_sim_params* sp, const b2g
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, nullptr, nullptr, A.P);
+    A.P.stats = g_stats;
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = tau; A.actuation = tau; A.dof_force = nullptr; A.contact = nullptr; A.friction = nullptr; A.env_scale = g_env_scale;
     const Variant v = pick(*m);
     for (int e = 0; e < n_envs; e++) {
@@ -163,6 +172,7 @@ int emu_anymal(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, nullptr, nullptr, A.P);
+    A.P.stats = g_stats;
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = dof_force;
     A.contact = contact; A.friction = nullptr;
     TaskArgs T;
@@ -205,6 +215,7 @@ int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_prop
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, hf, hfs, A.P);
+    A.P.stats = g_stats;
     std::vector<float> hfc;   // coarse heightfield bound, as the library builds it (B2G_NO_HFC=1: exhaustive candidate tests)
     if (hf && hfs && !(getenv("B2G_NO_HFC") && getenv("B2G_NO_HFC")[0] == '1')) {
         build_hf_coarse(hfs, hf->rows, hf->cols, hf->horizontal_scale, hf->vertical_scale, max_link_radius(*dm), hfc, A.P.hfc_rows, A.P.hfc_cols);
@@ -276,6 +287,7 @@ int emu_cartpole(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, nullptr, nullptr, A.P);
+    A.P.stats = g_stats;
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = dof_force;
     A.contact = contact; A.friction = nullptr;
     TaskArgs T;
@@ -308,6 +320,7 @@ int emu_houndarm(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, nullptr, nullptr, A.P);
+    A.P.stats = g_stats;
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = dof_force;
     A.contact = contact; A.friction = nullptr; A.env_scale = g_env_scale;
     TaskArgs T;

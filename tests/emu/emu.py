@@ -154,3 +154,10 @@ def jacobian_mass_matrix(model, props, root, dof):
                           _p(jac), C.c_int(rows * 6 * ncol), _p(mm))
     assert rc == 0, rc
     return jac, mm
+
+
+def contact_stats(reset=False):
+    """[active contact points, dropped candidates, env sub-steps with a drop, env sub-steps] of the emulated sub-steps."""
+    out = (C.c_longlong * 4)()
+    lib().emu_contact_stats(out, C.c_int(1 if reset else 0))
+    return [int(v) for v in out]
