@@ -35,7 +35,7 @@ constexpr int MAXC = B2G_MAX_CONTACTS_PER_CHAIN;
 // per-thread scratch for the (dynamically indexed) contact slots
 enum ContactField {
     CF_RX, CF_RY, CF_RZ, CF_NX, CF_NY, CF_NZ, CF_T1X, CF_T1Y, CF_T1Z, CF_T2X, CF_T2Y, CF_T2Z,
-    CF_GAP, CF_JC, CF_BODY, CF_ANN, CF_ANT1, CF_ANT2, CF_AT1T1, CF_AT1T2, CF_AT2T2, CF_LN, CF_L1, CF_L2, CF_COUNT
+    CF_GAP, CF_JC, CF_BODY, CF_ANN, CF_ANT1, CF_ANT2, CF_AT1T1, CF_AT1T2, CF_AT2T2, CF_ATISO, CF_LN, CF_L1, CF_L2, CF_COUNT
 };
 
 #if defined(B2G_HOST_EMU)
@@ -575,6 +575,7 @@ B2G_LINK_UNROLL
             // diagonal entries are kept as reciprocals: the sweeps multiply instead of dividing
             sc.at(s, CF_ANN) = 1.0f / A[0]; sc.at(s, CF_ANT1) = A[3]; sc.at(s, CF_ANT2) = A[6];
             sc.at(s, CF_AT1T1) = 1.0f / A[4]; sc.at(s, CF_AT1T2) = A[7]; sc.at(s, CF_AT2T2) = 1.0f / A[8];
+            sc.at(s, CF_ATISO) = 1.0f / (fmaxf(A[4], A[8]) + fabsf(A[7]));      // scalar step length of the sliding branch: >= the largest eigenvalue of the tangential block
         }
     }
 
@@ -622,12 +623,23 @@ B2G_LINK_UNROLL
                 vt1 += sc.at(s, CF_ANT1) * dn;
                 vt2 += sc.at(s, CF_ANT2) * dn;
                 float l1 = l1o - vt1 * sc.at(s, CF_AT1T1);
-                vt2 += sc.at(s, CF_AT1T2) * (l1 - l1o);
-                float l2 = l2o - vt2 * sc.at(s, CF_AT2T2);
-                const float lim_t = mu * ln, mag = sqrtf(l1 * l1 + l2 * l2);
+                const float vt2s = vt2 + sc.at(s, CF_AT1T2) * (l1 - l1o);
+                float l2 = l2o - vt2s * sc.at(s, CF_AT2T2);
+                const float lim_t = mu * ln;
+                float mag = sqrtf(l1 * l1 + l2 * l2);
                 if (mag > lim_t) {
-                    const float scl = (mag > 0.0f) ? lim_t / mag : 0.0f;
-                    l1 *= scl; l2 *= scl;
+                    // The sticking impulse leaves the cone: the contact slides.  Scaling the sticking impulse back would keep ITS direction
+                    // (A_tt^-1 v_t), which is not opposite to the sliding velocity when the tangential Delassus block is anisotropic (a box
+                    // corner, a foot on a leg).  A proximal step with a SCALAR step length followed by the radial projection has the Coulomb
+                    // law as its fixed point: magnitude mu * lambda_n, opposite to the tangential velocity (block-on-a-slope known answer).
+                    const float ia = sc.at(s, CF_ATISO);
+                    l1 = l1o - vt1 * ia;
+                    l2 = l2o - vt2 * ia;
+                    mag = sqrtf(l1 * l1 + l2 * l2);
+                    if (mag > lim_t) {
+                        const float scl = (mag > 0.0f) ? lim_t / mag : 0.0f;
+                        l1 *= scl; l2 *= scl;
+                    }
                 }
                 sc.at(s, CF_LN) = ln; sc.at(s, CF_L1) = l1; sc.at(s, CF_L2) = l2;
                 const V3 dir = n * dn + t1 * (l1 - l1o) + t2 * (l2 - l2o);

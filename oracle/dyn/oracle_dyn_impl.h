@@ -486,10 +486,21 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
                 dl[0] = ln - cc->lam[0];
                 vt1 += cc->A[3] * dl[0]; vt2 += cc->A[6] * dl[0];
                 R l1 = cc->lam[1] - vt1 / cc->A[4];
-                vt2 += cc->A[7] * (l1 - cc->lam[1]);
-                R l2 = cc->lam[2] - vt2 / cc->A[8];
+                R vt2s = vt2 + cc->A[7] * (l1 - cc->lam[1]);
+                R l2 = cc->lam[2] - vt2s / cc->A[8];
                 R lim_t = mu * ln, mag = (R)sqrt((double)(l1 * l1 + l2 * l2));
-                if (mag > lim_t) { R sc = (mag > 0) ? lim_t / mag : 0; l1 *= sc; l2 *= sc; }
+                if (mag > lim_t) {
+                    /* the sticking impulse leaves the cone -> the contact slides.  Scaling the sticking impulse back would keep ITS
+                     * direction (A_tt^-1 v_t), which is not opposite to the sliding velocity when the tangential Delassus block is
+                     * anisotropic (a corner of a box, a foot on a leg).  A proximal step with a SCALAR step length followed by the
+                     * radial projection has the Coulomb law as its fixed point: friction of magnitude mu * lambda_n opposite to the
+                     * tangential velocity (maximum dissipation).  Checked by the block-on-a-slope known-answer test. */
+                    R ia = 1 / ((cc->A[4] > cc->A[8] ? cc->A[4] : cc->A[8]) + (cc->A[7] < 0 ? -cc->A[7] : cc->A[7]));
+                    l1 = cc->lam[1] - vt1 * ia;
+                    l2 = cc->lam[2] - vt2 * ia;
+                    mag = (R)sqrt((double)(l1 * l1 + l2 * l2));
+                    if (mag > lim_t) { R sc = (mag > 0) ? lim_t / mag : 0; l1 *= sc; l2 *= sc; }
+                }
                 dl[1] = l1 - cc->lam[1]; dl[2] = l2 - cc->lam[2];
                 cc->lam[0] = ln; cc->lam[1] = l1; cc->lam[2] = l2;
                 R dir[3];
@@ -567,6 +578,298 @@ int FN(orc_simulate)(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof
                                      contact + (size_t)e * nb * 3);
             if (st != 0) rc = st;
         }
+    }
+    return rc;
+}
+
+/*
+ * CONVERGED REFERENCE of one sub-step (what the production solver is measured against; tests/test_solver_convergence.py,
+ * DESIGN.md section 6).  Same free dynamics, same contact model (spheres against the plane / heightfield, Coulomb cone, the same
+ * penetration bias and position / velocity phases) -- but none of the production solver's shortcuts:
+ *   - EVERY candidate inside the contact offset becomes a contact (no B2G_MAX_CONTACTS_PER_CHAIN cap);
+ *   - plain sequential Gauss-Seidel over all contacts in one list (no Jacobi split across chains): each impulse is applied
+ *     before the next contact reads its velocity;
+ *   - each phase is iterated to convergence (max |delta lambda| <= tol (1 + max |lambda|), at most max_iter sweeps, >= 200 asked
+ *     for by the tests) instead of num_position_iterations + num_velocity_iterations sweeps;
+ *   - flags & 1: joint limits are HARD unilateral joint-space rows solved in the same sweeps (what PhysX does; the
+ *     reference configures them through the URDF limits, assets/urdf/anymal_c/urdf/anymal.urdf:624-631) instead of the
+ *     production path's one-sided implicit spring-dampers.
+ * It is still this repo's contact model, not PhysX: it bounds the error of the SOLVER, not of the model.
+ * info[0] = contacts, info[1] / info[2] = sweeps used by the position / velocity phase, info[3] = 1 if a phase hit max_iter.
+ */
+static int FN(orc_substep_ref)(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp,
+                               const b2g_heightfield* hf, const int16_t* hfs, R mu_shape, R h,
+                               R* root13, R* dof, const R* target, const R* actuation, R* dof_force, R* contact,
+                               int flags, int max_iter, R tol, int* info) {
+    int nd = m->n_dof;
+    const int hard = flags & 1;
+    FN(orc_kin)* k = (FN(orc_kin)*)malloc(sizeof(FN(orc_kin)));
+    FN(orc_contact)* con = (FN(orc_contact)*)malloc(sizeof(FN(orc_contact)) * B2G_MAX_CPTS);
+    if (!k || !con) { free(k); free(con); return -1; }
+    R q[B2G_MAX_DOF], qd[B2G_MAX_DOF], tau[B2G_MAX_DOF], dext[B2G_MAX_DOF], qdd[B2G_MAX_DOF], a0[6];
+    R grav[3] = {(R)sp->gravity[0], (R)sp->gravity[1], (R)sp->gravity[2]};
+    for (int d = 0; d < nd; d++) { q[d] = dof[2 * d]; qd[d] = dof[2 * d + 1]; }
+    for (int d = 0; d < nd; d++) {
+        R kp = (R)dp->stiffness[d], kd = (R)dp->damping[d];
+        dext[d] = (R)m->armature[d];
+        tau[d] = 0;
+        if (dp->drive_mode[d] == B2G_DOF_MODE_POS) {
+            tau[d] = kp * (target[d] - q[d]) - (kd + h * kp) * qd[d];
+            dext[d] += h * kd + h * h * kp;
+        } else if (dp->drive_mode[d] == B2G_DOF_MODE_VEL) {
+            tau[d] = kd * (target[d] - qd[d]);
+            dext[d] += h * kd;
+        } else if (dp->drive_mode[d] == B2G_DOF_MODE_EFFORT) {
+            R e = actuation[d], lim = (R)dp->effort[d];
+            if (lim > 0) { if (e > lim) e = lim; if (e < -lim) e = -lim; }
+            tau[d] = e;
+        }
+        if (!hard) {      /* the production path's spring-damper limits */
+            R lo = (R)dp->lower[d], hi = (R)dp->upper[d], kl = (R)sp->joint_limit_stiffness, dl = (R)sp->joint_limit_damping;
+            R qp = q[d] + h * qd[d];
+            R ref = 0; int on = 0;
+            if (lo > -1e30f && (q[d] < lo || qp < lo)) { ref = lo; on = 1; }
+            else if (hi < 1e30f && (q[d] > hi || qp > hi)) { ref = hi; on = 1; }
+            if (on) {
+                tau[d] += kl * (ref - q[d]) - (dl + h * kl) * qd[d];
+                dext[d] += h * dl + h * h * kl;
+            }
+        }
+    }
+    FN(orc_kinematics)(m, root13, q, qd, k);
+    if (FN(orc_aba_backward)(m, k, tau, dext) != 0) { free(k); free(con); return -2; }
+    FN(orc_aba_forward)(m, k, grav, qdd, a0);
+    R v0[6] = {0, 0, 0, 0, 0, 0};
+    if (!m->fixed_base) {
+        R w[3] = {k->vel[0][0], k->vel[0][1], k->vel[0][2]}, vl[3] = {k->vel[0][3], k->vel[0][4], k->vel[0][5]}, wxv[3];
+        FN(cross3)(w, vl, wxv);
+        for (int i = 0; i < 3; i++) { v0[i] = w[i] + h * a0[i]; v0[3 + i] = vl[i] + h * (a0[3 + i] + wxv[i]); }
+    }
+    for (int d = 0; d < nd; d++) qd[d] += h * qdd[d];
+
+    /* ---- every candidate inside the contact offset ---- */
+    int nc = 0;
+    R mu_g = hf && hfs ? (R)hf->friction : (R)sp->plane_dynamic_friction;
+    R mu = (R)0.5 * (mu_g + mu_shape);
+    int ground = (hf && hfs) || sp->has_ground;
+    for (int i = 0; i < m->n_cpts && ground; i++) {
+        int l = m->cp_link[i];
+        if (m->fixed_base && l == 0) continue;
+        R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
+        FN(matvec3)(k->rot[l], lp, rc);
+        for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];
+        FN(orc_ground)(hf, hfs, root13[0] + rc[0], root13[1] + rc[1], &gh, n);
+        R gap = (root13[2] + rc[2] - gh) * n[2] - (R)m->cp_radius[i];
+        if (gap >= (R)sp->contact_offset) continue;
+        FN(orc_contact)* cc = &con[nc++];
+        cc->link = l; cc->body = m->cp_body[i]; cc->gap = gap;
+        for (int a = 0; a < 3; a++) { cc->n[a] = n[a]; cc->r[a] = rc[a] - (R)m->cp_radius[i] * n[a]; cc->lam[a] = 0; }
+        R dn = n[0];
+        R t1[3] = {1 - dn * n[0], -dn * n[1], -dn * n[2]};
+        R inv = 1 / (R)sqrt((double)(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]));
+        for (int a = 0; a < 3; a++) cc->t1[a] = t1[a] * inv;
+        FN(cross3)(cc->n, cc->t1, cc->t2);
+        const R* dirs[3] = {cc->n, cc->t1, cc->t2};
+        for (int b = 0; b < 3; b++) {
+            R F[6], dv0[6] = {0, 0, 0, 0, 0, 0}, dqd[B2G_MAX_DOF], lv[6], pv[3];
+            for (int d = 0; d < nd; d++) dqd[d] = 0;
+            FN(orc_contact_wrench)(cc, dirs[b], F);
+            FN(orc_apply_impulse)(m, k, l, F, -1, 0, dv0, dqd);
+            FN(orc_link_velocity)(m, k, l, dv0, dqd, lv);
+            FN(orc_point_velocity)(cc, lv, pv);
+            for (int a = 0; a < 3; a++) cc->A[a * 3 + b] = pv[0] * dirs[a][0] + pv[1] * dirs[a][1] + pv[2] * dirs[a][2];
+        }
+    }
+    /* ---- hard joint-limit rows: sign * qd >= -gap / h ---- */
+    int nlim = 0, lim_d[2 * B2G_MAX_DOF];
+    R lim_sign[2 * B2G_MAX_DOF], lim_gap[2 * B2G_MAX_DOF], lim_W[2 * B2G_MAX_DOF], lim_lam[2 * B2G_MAX_DOF];
+    for (int d = 0; d < nd && hard; d++) {
+        R lo = (R)dp->lower[d], hi = (R)dp->upper[d];
+        R dv0[6] = {0, 0, 0, 0, 0, 0}, dqd[B2G_MAX_DOF];
+        if (!(lo > -1e30f) && !(hi < 1e30f)) continue;
+        for (int e = 0; e < nd; e++) dqd[e] = 0;
+        FN(orc_apply_impulse)(m, k, 0, 0, d, (R)1, dv0, dqd);
+        if (lo > -1e30f) { lim_d[nlim] = d; lim_sign[nlim] = 1; lim_gap[nlim] = q[d] - lo; lim_W[nlim] = dqd[d]; lim_lam[nlim] = 0; nlim++; }
+        if (hi < 1e30f) { lim_d[nlim] = d; lim_sign[nlim] = -1; lim_gap[nlim] = hi - q[d]; lim_W[nlim] = dqd[d]; lim_lam[nlim] = 0; nlim++; }
+    }
+
+    R maxdep = (R)sp->max_depenetration_velocity;
+    R vpos0[6], qdpos[B2G_MAX_DOF];
+    int capped = 0;
+    info[1] = info[2] = 0;
+    for (int phase = 0; phase < 2; phase++) {
+        int with_bias = phase == 0;
+        int skip = with_bias ? sp->num_position_iterations <= 0 : sp->num_velocity_iterations <= 0;
+        int it = 0;
+        for (; it < max_iter && !skip && (nc > 0 || nlim > 0); it++) {
+            /* convergence is judged on the VELOCITIES (root + joints) between the ends of two sweeps: with redundant contacts (four
+             * coplanar corners on one body) the impulse distribution is not unique and may keep drifting along the null space of the
+             * Delassus matrix while the motion and the net force per body have long converged */
+            R maxd = 0, maxl = 0, vprev[6 + B2G_MAX_DOF];
+            for (int i = 0; i < 6; i++) vprev[i] = v0[i];
+            for (int d = 0; d < nd; d++) vprev[6 + d] = qd[d];
+            for (int s = 0; s < nc; s++) {
+                FN(orc_contact)* cc = &con[s];
+                R lv[6], pv[3], F[6];
+                FN(orc_link_velocity)(m, k, cc->link, v0, qd, lv);
+                FN(orc_point_velocity)(cc, lv, pv);
+                R vn = pv[0] * cc->n[0] + pv[1] * cc->n[1] + pv[2] * cc->n[2];
+                R vt1 = pv[0] * cc->t1[0] + pv[1] * cc->t1[1] + pv[2] * cc->t1[2];
+                R vt2 = pv[0] * cc->t2[0] + pv[1] * cc->t2[1] + pv[2] * cc->t2[2];
+                R tgt = -cc->gap / h;
+                if (tgt > maxdep) tgt = maxdep;
+                if (!with_bias && tgt > 0) tgt = 0;
+                R dl[3];
+                R ln = cc->lam[0] - (vn - tgt) / cc->A[0];
+                if (ln < 0) ln = 0;
+                dl[0] = ln - cc->lam[0];
+                vt1 += cc->A[3] * dl[0]; vt2 += cc->A[6] * dl[0];
+                /* EXACT Coulomb solve of this contact's tangential rows for the normal impulse just computed: with b = the tangential
+                 * velocity the contact would have with zero tangential impulse, either the sticking impulse -A_tt^-1 b lies inside the
+                 * disc of radius mu * lambda_n, or the contact slides and lambda_t = -(A_tt + s I)^-1 b with s > 0 such that
+                 * |lambda_t| = mu * lambda_n -- friction opposite to the resulting sliding velocity (v_t = s lambda_t).  s by Newton on
+                 * 1/|lambda_t(s)| - 1/(mu lambda_n) (monotone from s = 0).  The production path reaches the same fixed point with a
+                 * cheaper update (block solve when sticking, scalar proximal step when sliding). */
+                R a = cc->A[4], c2 = cc->A[7], d2 = cc->A[8];
+                R b1 = vt1 - (a * cc->lam[1] + c2 * cc->lam[2]), b2 = vt2 - (c2 * cc->lam[1] + d2 * cc->lam[2]);
+                R lim_t = mu * ln;
+                R det = a * d2 - c2 * c2;
+                R l1 = -(d2 * b1 - c2 * b2) / det, l2 = -(a * b2 - c2 * b1) / det;
+                if ((R)sqrt((double)(l1 * l1 + l2 * l2)) > lim_t) {
+                    if (lim_t <= 0) { l1 = 0; l2 = 0; }
+                    else {
+                        R sft = 0;
+                        for (int nit = 0; nit < 60; nit++) {
+                            R aa = a + sft, dd = d2 + sft, dt2 = aa * dd - c2 * c2;
+                            R p1 = -(dd * b1 - c2 * b2) / dt2, p2 = -(aa * b2 - c2 * b1) / dt2;
+                            R pn = (R)sqrt((double)(p1 * p1 + p2 * p2));
+                            l1 = p1; l2 = p2;
+                            if (!(pn > 0)) break;
+                            R z1 = (dd * p1 - c2 * p2) / dt2, z2 = (aa * p2 - c2 * p1) / dt2;      /* (A_tt + s I)^-1 p */
+                            R phi = 1 / pn - 1 / lim_t, dphi = (p1 * z1 + p2 * z2) / (pn * pn * pn);
+                            if (phi > -(R)1e-14 / lim_t && phi < (R)1e-14 / lim_t) break;
+                            R step = -phi / dphi;
+                            sft += step;
+                            if (sft < 0) sft = 0;
+                            if ((step < 0 ? -step : step) <= (R)1e-15 * (1 + sft)) break;
+                        }
+                        R pn = (R)sqrt((double)(l1 * l1 + l2 * l2));
+                        if (pn > 0) { l1 *= lim_t / pn; l2 *= lim_t / pn; }
+                    }
+                }
+                dl[1] = l1 - cc->lam[1]; dl[2] = l2 - cc->lam[2];
+                cc->lam[0] = ln; cc->lam[1] = l1; cc->lam[2] = l2;
+                for (int a = 0; a < 3; a++) {
+                    R ad = dl[a] < 0 ? -dl[a] : dl[a], al = cc->lam[a] < 0 ? -cc->lam[a] : cc->lam[a];
+                    if (ad > maxd) maxd = ad;
+                    if (al > maxl) maxl = al;
+                }
+                R dir[3];
+                for (int a = 0; a < 3; a++) dir[a] = cc->n[a] * dl[0] + cc->t1[a] * dl[1] + cc->t2[a] * dl[2];
+                FN(orc_contact_wrench)(cc, dir, F);
+                FN(orc_apply_impulse)(m, k, cc->link, F, -1, 0, v0, qd);
+            }
+            for (int r = 0; r < nlim; r++) {
+                int d = lim_d[r];
+                R v = lim_sign[r] * qd[d];
+                R tgt = -lim_gap[r] / h;
+                if (!with_bias && tgt > 0) tgt = 0;
+                R ln = lim_lam[r] - (v - tgt) / lim_W[r];
+                if (ln < 0) ln = 0;
+                R dl = ln - lim_lam[r];
+                lim_lam[r] = ln;
+                R ad = dl < 0 ? -dl : dl;
+                if (ad > maxd) maxd = ad;
+                if (ln > maxl) maxl = ln;
+                if (dl != 0) FN(orc_apply_impulse)(m, k, 0, 0, d, lim_sign[r] * dl, v0, qd);
+            }
+            (void)maxl;
+            maxd = 0;
+            R vmax = 0;
+            for (int i = 0; i < 6 + nd; i++) {
+                R vn_ = i < 6 ? v0[i] : qd[i - 6];
+                R ad = vn_ - vprev[i]; if (ad < 0) ad = -ad;
+                R av = vn_ < 0 ? -vn_ : vn_;
+                if (ad > maxd) maxd = ad;
+                if (av > vmax) vmax = av;
+            }
+            if (maxd <= tol * (1 + vmax)) { it++; break; }
+        }
+        if (it >= max_iter && !skip && (nc > 0 || nlim > 0)) capped = 1;
+        info[1 + phase] = it;
+        if (with_bias) {
+            for (int i = 0; i < 6; i++) vpos0[i] = v0[i];
+            for (int d = 0; d < nd; d++) qdpos[d] = qd[d];
+        }
+    }
+    if (sp->num_velocity_iterations <= 0 || sp->num_position_iterations <= 0) {
+        /* single-phase configurations: positions integrate with the final velocity when there is no velocity phase */
+        if (sp->num_velocity_iterations <= 0) { for (int i = 0; i < 6; i++) vpos0[i] = v0[i]; for (int d = 0; d < nd; d++) qdpos[d] = qd[d]; }
+    }
+    info[0] = nc; info[3] = capped;
+
+    for (int d = 0; d < nd; d++) {
+        R vl = (R)dp->velocity[d];
+        if (vl > 0) { if (qd[d] > vl) qd[d] = vl; if (qd[d] < -vl) qd[d] = -vl; if (qdpos[d] > vl) qdpos[d] = vl; if (qdpos[d] < -vl) qdpos[d] = -vl; }
+        q[d] += h * qdpos[d];
+        dof[2 * d] = q[d]; dof[2 * d + 1] = qd[d];
+    }
+    if (!m->fixed_base) {
+        for (int i = 0; i < 3; i++) root13[i] += h * vpos0[3 + i];
+        R w[3] = {vpos0[0], vpos0[1], vpos0[2]};
+        R ang = (R)sqrt((double)(w[0] * w[0] + w[1] * w[1] + w[2] * w[2])) * h;
+        R dq[4] = {0, 0, 0, 1};
+        if (ang > (R)1e-12) {
+            R s = (R)sin((double)(ang / 2)) / (ang / h);
+            dq[0] = w[0] * s; dq[1] = w[1] * s; dq[2] = w[2] * s; dq[3] = (R)cos((double)(ang / 2));
+        }
+        R* qo = root13 + 3;
+        R x1 = dq[0], y1 = dq[1], z1 = dq[2], w1 = dq[3], x2 = qo[0], y2 = qo[1], z2 = qo[2], w2 = qo[3];
+        R nq[4] = {w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                   w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2};
+        R nn = 1 / (R)sqrt((double)(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]));
+        for (int i = 0; i < 4; i++) qo[i] = nq[i] * nn;
+        for (int i = 0; i < 3; i++) { root13[7 + i] = v0[3 + i]; root13[10 + i] = v0[i]; }
+    }
+    for (int d = 0; d < nd; d++) {
+        R f = 0, lim_e = (R)dp->effort[d];
+        if (dp->drive_mode[d] == B2G_DOF_MODE_POS) f = (R)dp->stiffness[d] * (target[d] - q[d]) - (R)dp->damping[d] * qd[d];
+        else if (dp->drive_mode[d] == B2G_DOF_MODE_VEL) f = (R)dp->damping[d] * (target[d] - qd[d]);
+        else if (dp->drive_mode[d] == B2G_DOF_MODE_EFFORT) f = actuation[d];
+        if (lim_e > 0) { if (f > lim_e) f = lim_e; if (f < -lim_e) f = -lim_e; }
+        dof_force[d] = f;
+    }
+    for (int b = 0; b < m->n_bodies * 3; b++) contact[b] = 0;
+    for (int s = 0; s < nc; s++) {
+        FN(orc_contact)* cc = &con[s];
+        for (int a = 0; a < 3; a++)
+            contact[cc->body * 3 + a] += (cc->n[a] * cc->lam[0] + cc->t1[a] * cc->lam[1] + cc->t2[a] * cc->lam[2]) / h;
+    }
+    free(k); free(con);
+    return 0;
+}
+
+/* gym.simulate with the converged reference solver.  info: (n_envs, 4) ints of the LAST sub-step of each environment. */
+int FN(orc_simulate_ref)(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props* dp,
+                         const b2g_heightfield* hf, const int16_t* hfs, const float* friction, int n_envs,
+                         R* root, R* dof, const R* target, const R* actuation, R* dof_force, R* contact,
+                         int flags, int max_iter, double tol, int* info) {
+    int nd = m->n_dof, nb = m->n_bodies;
+    int nsub = sp->substeps > 0 ? sp->substeps : 1;
+    R h = (R)sp->dt / (R)nsub;
+    int rc = 0;
+    for (int e = 0; e < n_envs; e++) {
+        R dummy_root[13] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0};
+        R* r = root ? root + (size_t)e * 13 : dummy_root;
+        int inf[4] = {0, 0, 0, 0}, worst = 0;
+        for (int s = 0; s < nsub; s++) {
+            int st = FN(orc_substep_ref)(m, sp, dp, hf, hfs, friction ? (R)friction[e] : (R)1, h, r, dof + (size_t)e * nd * 2,
+                                         target + (size_t)e * nd, actuation + (size_t)e * nd, dof_force + (size_t)e * nd,
+                                         contact + (size_t)e * nb * 3, flags, max_iter, (R)tol, inf);
+            if (st != 0) rc = st;
+            worst |= inf[3];
+        }
+        if (info) { info[e * 4] = inf[0]; info[e * 4 + 1] = inf[1]; info[e * 4 + 2] = inf[2]; info[e * 4 + 3] = worst; }
     }
     return rc;
 }

@@ -75,6 +75,32 @@ def simulate(model, params, props, root, dof, target, actuation, heightfield=Non
     return dof_force, contact
 
 
+def simulate_ref(model, params, props, root, dof, target, actuation, heightfield=None, hf_samples=None, friction=None, hard_limits=False,
+                 max_iter=500, tol=1e-9):
+    """One ``gym.simulate`` with the CONVERGED reference solver (every candidate a contact, sequential Gauss-Seidel to
+    convergence, optional hard joint limits): what the production solver's error is measured against.  Updates ``root`` /
+    ``dof`` in place; returns (dof_force, contact, info (N,4) = [contacts, position sweeps, velocity sweeps, hit max_iter])."""
+    suf, ct = _suffix_types(root.dtype)
+    n = root.shape[0]
+    nd, nb = model.n_dof, model.n_bodies
+    dof_force = np.zeros((n, nd), dtype=root.dtype)
+    contact = np.zeros((n, nb, 3), dtype=root.dtype)
+    info = np.zeros((n, 4), dtype=np.int32)
+    fr = None if friction is None else np.ascontiguousarray(friction, dtype=np.float32)
+    hs = None if hf_samples is None else np.ascontiguousarray(hf_samples, dtype=np.int16)
+    fn = getattr(lib(), "orc_simulate_ref" + suf)
+    fn.restype = C.c_int
+    rc = fn(C.byref(model), C.byref(params), C.byref(props),
+            C.byref(heightfield) if heightfield is not None else None, _ptr(hs, C.c_int16), _ptr(fr, C.c_float),
+            C.c_int(n), _ptr(root, ct), _ptr(dof, ct),
+            _ptr(np.ascontiguousarray(target, dtype=root.dtype), ct),
+            _ptr(np.ascontiguousarray(actuation, dtype=root.dtype), ct), _ptr(dof_force, ct), _ptr(contact, ct),
+            C.c_int(1 if hard_limits else 0), C.c_int(int(max_iter)), C.c_double(float(tol)), info.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc != 0:
+        raise RuntimeError(f"oracle reference simulate failed ({rc})")
+    return dof_force, contact, info
+
+
 def forward_dynamics(model, params, root, dof, tau):
     suf, ct = _suffix_types(root.dtype)
     n = root.shape[0]

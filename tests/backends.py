@@ -46,10 +46,21 @@ class EmuBackend:
         self._scale = np.ascontiguousarray(scale, np.float32)
         self._fric = None if friction is None else np.ascontiguousarray(friction, np.float32)
 
+    def add_heightfield(self, hf_t, samples):
+        self._hf = (hf_t, np.ascontiguousarray(samples, np.int16))
+
+    def set_friction(self, friction):
+        self._fric = np.ascontiguousarray(friction, np.float32)
+
+    def contact_stats(self, reset=False):
+        return self.emu.contact_stats(reset)
+
     def simulate(self, target, actuation):
         self.emu.set_env_scale(getattr(self, "_scale", None))
+        hf = getattr(self, "_hf", None)
         try:
-            f, c = self.emu.simulate(self.model, self.params, self.props, self.root, self.dof, target, actuation, friction=getattr(self, "_fric", None))
+            f, c = self.emu.simulate(self.model, self.params, self.props, self.root, self.dof, target, actuation, friction=getattr(self, "_fric", None),
+                                     heightfield=hf[0] if hf else None, hf_samples=hf[1] if hf else None)
         finally:
             self.emu.set_env_scale(None)
         self.dof_force[:], self.contact[:] = f, c
@@ -225,6 +236,18 @@ class CudaBackend:
         nd, nb = self.art.num_dofs, self.art.num_bodies
         return (self.t[_abi.T_DOF_FORCE].cpu().numpy().reshape(self.n, nd).copy(),
                 self.t[_abi.T_NET_CONTACT].cpu().numpy().reshape(self.n, nb, 3).copy())
+
+    def add_heightfield(self, hf_t, samples):
+        smp = np.ascontiguousarray(samples, np.int16)
+        self._lib.check(self.lib.b2g_sim_add_heightfield(self.sim, C.byref(hf_t), smp.ctypes.data_as(C.c_void_p)), "add_heightfield")
+
+    def set_friction(self, friction):
+        self._put(self._tensor(_abi.T_FRICTION), np.asarray(friction, np.float32))
+
+    def contact_stats(self, reset=False):
+        out = (C.c_int64 * 4)()
+        self._lib.check(self.lib.b2g_sim_contact_stats(self.sim, out, 1 if reset else 0), "contact_stats")
+        return [int(v) for v in out]
 
     def set_env_scale(self, scale, friction=None):
         """(N,4) per-env [mass, stiffness, damping, spare] scales (+ optional (N) shape friction)."""
