@@ -379,3 +379,175 @@ def test_full_size_batch_properties(task, n):
             to = (big.progress_buf >= big.max_episode_length - 1) & (db != 0)
             assert torch.equal(eb["time_outs"] != 0, to)
     assert total_resets > 100, "random actions must make robots fall and reset at this size too"
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3 and 4 at their own size: AnymalTerrain on the 10 x 20 trimesh field (1200 x 2000 samples), HoundTerrain and
+# UsefulHound, 4096 environments
+# ------------------------------------------------------------------------------------------------------------------------------------
+TRIMESH_FULL = {"env": {"terrain": {"terrainType": "trimesh", "numLevels": 10, "numTerrains": 20}}}
+
+
+def _sim_tensor(env, kind):
+    import ctypes as C
+
+    from isaacgymenv_b200 import _abi, _lib
+
+    d = _abi.TensorDesc()
+    _lib.check(_lib.load().b2g_sim_tensor(env.sim.handle, kind, C.byref(d)), "sim tensor")
+    return _lib.desc_to_torch(d)
+
+
+def _merge(a, b):
+    import copy
+
+    out = copy.deepcopy(a)
+    for k, v in b.items():
+        out[k] = _merge(out[k], v) if isinstance(v, dict) and isinstance(out.get(k), dict) else v
+    return out
+
+
+@pytest.mark.parametrize("task,ov", [("AnymalTerrain", TRIMESH_FULL), ("HoundTerrain", TRIMESH_FULL), ("HoundTerrain", {}), ("UsefulHound", TRIMESH_FULL),
+                                     ("UsefulHound", {})])
+def test_full_size_terrain_prefix_identity(task, ov):
+    """(a) Environments are independent once the curriculum's one global scalar is out of the way (terrain.curriculum: false): the
+    first 512 of 4096 environments follow, bit for bit, a 512-env sim that was handed the same per-env state (origins, levels,
+    types, friction, root / DOF state, commands) -- same seed, so the per-env Philox streams (resets, noise, pushes) coincide."""
+    import torch
+
+    import isaacgymenv_b200 as b2g
+    from isaacgymenv_b200 import _abi
+
+    n, small = 4096, 512
+    ov = _merge(ov, {"env": {"terrain": {"curriculum": False}, "learn": {"pushInterval_s": 0.6}}})
+    big = b2g.make(seed=7, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=ov)
+    twin = b2g.make(seed=7, task=task, num_envs=small, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=ov)
+    if big.custom_origins:
+        assert big.terrain.tot_rows == 1200 and big.terrain.tot_cols == 2000
+        assert torch.equal(big.height_samples, twin.height_samples)
+    names = ["root_states", "dof_state", "commands", "env_origins", "terrain_levels", "terrain_types"]
+    if task == "UsefulHound":
+        names += ["_mm", "_j_eef", "_eef_state", "arm_commands"]
+    for name in names:
+        src, dst = getattr(big, name), getattr(twin, name)
+        per = src.numel() // n
+        dst.view(-1).copy_(src.view(-1)[: small * per])
+    _sim_tensor(twin, _abi.T_FRICTION).copy_(_sim_tensor(big, _abi.T_FRICTION)[:small])
+    g = torch.Generator(device="cuda:0").manual_seed(11)
+    na = big.num_actions
+    resets = 0
+    for k in range(36):
+        a = 2 * torch.rand(n, na, device="cuda:0", generator=g) - 1
+        ob, rb, db, eb = big.step(a)
+        os_, rs, ds, es = twin.step(a[:small].contiguous())
+        assert torch.equal(ob["obs"][:small], os_["obs"]), f"step {k}: observations of the prefix differ"
+        assert torch.equal(rb[:small], rs) and torch.equal(db[:small], ds) and torch.equal(eb["time_outs"][:small], es["time_outs"]), k
+        assert torch.equal(big.root_states[:small], twin.root_states) and torch.equal(big.dof_state.view(n, -1)[:small], twin.dof_state.view(small, -1)), k
+        resets += int(db.sum())
+    assert torch.isfinite(ob["obs"]).all() and resets > 100
+    assert big.common_step_counter >= big.push_interval          # a push step was part of the comparison
+
+
+@pytest.mark.parametrize("task,ov", [("AnymalTerrain", TRIMESH_FULL), ("HoundTerrain", {}), ("UsefulHound", {}), ("UsefulHound", TRIMESH_FULL)])
+def test_full_size_terrain_post_physics_matches_reference_math(task, ov):
+    """(b) post_physics_step for ALL 4096 environments on the sim's own tensors against the numpy restatement of the reference
+    (oracle/task_math.py::terrain_post_physics, pinned to the reference's eager methods by the golden vectors): termination, the 13
+    reward terms, reset_idx with the terrain curriculum (incl. the one global torch.norm scalar, quirk Q10), the 140-point height
+    scan on the 1200 x 2000 field, noise, history, time-outs.  1e-5 relative, masks / counters / levels bit-exact."""
+    import ctypes as C
+
+    import torch
+
+    import isaacgymenv_b200 as b2g
+    from isaacgymenv_b200 import _abi, _lib
+    from oracle import task_math as tm
+
+    n = 4096
+    env = b2g.make(seed=9, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=ov)
+    lib = _lib.load()
+    na, nd = env.num_actions, env.num_dof
+    arm = task == "UsefulHound"
+    nleg = 12
+    g = torch.Generator(device="cuda:0").manual_seed(13)
+    rng = np.random.default_rng(17)
+    t_rand, t_noise, t_push = env._task_tensor(_abi.TT_RAND_OVERRIDE), env._task_tensor(_abi.TT_NOISE_OVERRIDE), env._task_tensor(_abi.TT_PUSH_OVERRIDE)
+    npy = lambda t: t.detach().cpu().numpy().copy()
+    rs = env.rew_scales
+    cfg = dict(rew_scales=np.array([rs[k] for k in tm.REW_ORDER], np.float32), knee=npy(env.knee_indices), feet=npy(env.feet_indices),
+               base_indices=npy(env.base_indices), base_body=int(env.base_index), allow_knee=bool(env.allow_knee_contacts), hound=bool(env.HOUND_TERMINATION),
+               base_height_target=float(env.BASE_HEIGHT_TARGET), noise_scale_vec=npy(env.noise_scale_vec) if env.add_noise else None, dt=float(env.dt),
+               max_len=int(env.max_episode_length), default_dof_pos=npy(env.default_dof_pos[0])[:nleg], init_root=np.array(env.base_init_state.tolist(), np.float32),
+               cmd_x=list(env.command_x_range), cmd_y=list(env.command_y_range), cmd_yaw=list(env.command_yaw_range), custom_origins=bool(env.custom_origins),
+               curriculum=bool(env.curriculum), terrain=None, max_episode_length_s=float(env.max_episode_length_s), lin_vel_scale=env.lin_vel_scale,
+               ang_vel_scale=env.ang_vel_scale, dof_pos_scale=env.dof_pos_scale, dof_vel_scale=env.dof_vel_scale, height_meas_scale=env.height_meas_scale)
+    if env.custom_origins:
+        t = env.terrain
+        cfg["terrain"] = dict(height_samples=np.asarray(t.heightsamples), border_size=float(t.border_size), hscale=t.horizontal_scale, vscale=t.vertical_scale,
+                              env_length=float(t.env_length), env_rows=t.env_rows, terrain_origins=np.asarray(t.env_origins, np.float32))
+    if arm:
+        cfg["arm"] = dict(dof_noise=float(env.houndarm_dof_noise), lower=npy(env.houndarm_dof_lower_limits), upper=npy(env.houndarm_dof_upper_limits))
+    checked = resets = moved = 0
+    for k in range(60):
+        a = 2 * torch.rand(n, na, device="cuda:0", generator=g) - 1
+        env.step(a)
+        if k < 20 or k % 10 != 9:
+            continue
+        # the sim's tensors as they are now = the state a post_physics_step would start from
+        torch.cuda.synchronize()
+        dof = npy(env.dof_state.view(n, nd, 2))
+        st = dict(root=npy(env.root_states), dof_pos=dof[:, :nleg, 0].copy(), dof_vel=dof[:, :nleg, 1].copy(), contact=npy(env.contact_forces),
+                  torques=npy(env.torques), commands=npy(env.commands), actions=npy(a), last_actions=npy(env.last_actions),
+                  last_dof_vel=npy(env.last_dof_vel)[:, :nleg], feet_air_time=npy(env.feet_air_time), progress=npy(env.progress_buf),
+                  timeout_prev=npy(env._timeout_i64) != 0, episode_sums=npy(env._episode_sums), terrain_levels=npy(env.terrain_levels),
+                  terrain_types=npy(env.terrain_types), env_origins=npy(env.env_origins))
+        if arm:
+            st.update(arm_q=dof[:, nleg:, 0].copy(), arm_qd=dof[:, nleg:, 1].copy(), eef_state=npy(env._eef_state), arm_commands=npy(env.arm_commands))
+        step = env.common_step_counter + 1
+        cfg["push"] = env.push_interval > 0 and step % env.push_interval == 0
+        draws = dict(reset=rng.random(tuple(t_rand.shape), dtype=np.float32), noise=rng.random(tuple(t_noise.shape), dtype=np.float32),
+                     push=rng.random(tuple(t_push.shape), dtype=np.float32))
+        for tt, key in ((t_rand, "reset"), (t_noise, "noise"), (t_push, "push")):
+            tt.copy_(torch.from_numpy(draws[key]).to(tt.device))
+        _lib.check(lib.b2g_task_set_rand_override(env.sim.handle, 1))
+        env.common_step_counter = step
+        _lib.check(lib.b2g_task_terrain_set_step(env.sim.handle, int(step)))
+        _lib.check(lib.b2g_task_post_only(env.sim.handle, C.c_void_p(a.data_ptr()), env.sim.stream()), "post_only")
+        torch.cuda.synchronize()
+        _lib.check(lib.b2g_task_set_rand_override(env.sim.handle, 0))
+        levels_before = st["terrain_levels"].copy()
+        obs, rew, reset, timeout, measured, extras = tm.terrain_post_physics(st, cfg, draws)
+        near = (np.abs(np.linalg.norm(npy(env.contact_forces), axis=2) - 1.0) < 1e-4).any(axis=1)      # force norms on the 1 N threshold may fall either side
+        ok = ~near
+        assert int(near.sum()) < 8
+        assert np.array_equal(npy(env._reset_i64)[ok] != 0, reset[ok] != 0), f"step {k}: reset masks differ"
+        if near.any():      # a differing reset decision changes that env's whole row: compare the others
+            same = (npy(env._reset_i64) != 0) == (reset != 0)
+            ok = ok & same
+        assert np.array_equal(npy(env.progress_buf)[ok], st["progress"][ok]) and np.array_equal(npy(env._timeout_i64)[ok], timeout[ok])
+        np.testing.assert_allclose(npy(env.rew_buf)[ok], rew[ok], rtol=1e-5, atol=2e-7)
+        # a scan point within an ulp of a cell edge may truncate into the neighbouring 0.1 m cell (the device divides with the hardware
+        # reciprocal): those few environments are counted and left out of the row comparison, everything else is exact
+        hbad = (np.abs(npy(env.measured_heights) - measured) > 1e-6).any(axis=1)
+        assert hbad.mean() < 0.03, hbad.mean()
+        ok = ok & ~hbad
+        np.testing.assert_allclose(npy(env.measured_heights)[ok], measured[ok], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(npy(env.obs_buf)[ok], obs[ok], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(npy(env.root_states)[ok], st["root"][ok], rtol=1e-5, atol=1e-6)
+        d2 = npy(env.dof_state.view(n, nd, 2))
+        np.testing.assert_allclose(d2[ok][:, :nleg, 0], st["dof_pos"][ok], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(d2[ok][:, :nleg, 1], st["dof_vel"][ok], rtol=1e-5, atol=1e-7)
+        if arm:
+            np.testing.assert_allclose(d2[ok][:, nleg:, 0], st["arm_q"][ok], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(npy(env.commands)[ok], st["commands"][ok], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(npy(env.feet_air_time)[ok], st["feet_air_time"][ok], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(npy(env._episode_sums)[:, ok], st["episode_sums"][:, ok], rtol=1e-5, atol=1e-6)
+        if env.custom_origins and not near.any():
+            lv_same = npy(env.terrain_levels) == st["terrain_levels"]
+            assert (~lv_same).sum() <= 2          # `dist < norm * ...` on a float boundary may fall either side
+            np.testing.assert_allclose(npy(env.env_origins)[lv_same], st["env_origins"][lv_same], rtol=0, atol=0)
+            moved += int((st["terrain_levels"] != levels_before).sum())
+        checked += 1
+        resets += int((reset != 0).sum())
+    assert checked >= 4 and resets > 50
+    if env.custom_origins and env.curriculum:
+        assert moved > 0, "the curriculum must have moved somebody in a 4096-env batch"
