@@ -54,9 +54,12 @@ class FusedPolicy:
                                                     C.c_void_p(v.data_ptr() if v is not None else None),
                                                     C.c_float(eps), C.c_float(clip), self._stream()), "b2g_policy_set_obs_norm")
 
-    def sync(self, model, obs_rms=None):
-        """Pack the parameters of a ``learning.ppo.ActorCritic`` (and its observation normaliser) for the kernel."""
-        linears = [m for m in model.trunk if isinstance(m, torch.nn.Linear)]
+    def sync(self, model, obs_rms=None, critic=False):
+        """Pack the parameters of a ``learning.ppo.ActorCritic`` (and its observation normaliser) for the kernel.  ``critic=True``
+        packs the critic tower of a ``separate`` network instead of the actor tower / shared trunk (the value head is the same
+        module either way; the caller then ignores the action head of this instance, and the value head of the actor instance)."""
+        trunk = model.critic_trunk if critic else model.trunk
+        linears = [m for m in trunk if isinstance(m, torch.nn.Linear)]
         for i, lin in enumerate(linears):
             self.set_layer(HIDDEN0 + i, lin.weight, lin.bias)
         self.set_layer(MU, model.mu.weight, model.mu.bias)

@@ -1,6 +1,7 @@
 """Minimal PPO learner for the hot-path tasks -- a stand-in for rl_games' ``a2c_continuous`` agent, which the reference
 delegates training to (``train.py:200-218``; hyper-parameters ``cfg/train/AnymalPPO.yaml``; loss structure as stated in-tree by
-``learning/common_agent.py:361-509``): shared-trunk actor-critic MLP (ELU), state-independent log-std, GAE(gamma, tau) with
+``learning/common_agent.py:361-509``): actor-critic MLP (ELU; shared trunk or, with ``network.separate: true`` as in the rough-terrain
+train configs, separate actor / critic towers), state-independent log-std, GAE(gamma, tau) with
 value bootstrap on time-outs (``extras["time_outs"]``), clipped surrogate + clipped value loss + bound loss, advantage /
 observation / value normalisation, adaptive-KL learning rate, gradient-norm clipping.
 
@@ -44,20 +45,48 @@ class RunningMeanStd(nn.Module):
 
 
 class ActorCritic(nn.Module):
-    def __init__(self, num_obs, num_actions, units=(256, 128, 64)):
+    """rl_games' ``actor_critic`` network builder as the train yamls configure it (``cfg/train/AnymalPPO.yaml:5-22``): ``separate:
+    false`` = one MLP trunk feeding both heads (flat tasks), ``separate: true`` = an actor tower and a critic tower of the same shape
+    (``cfg/train/AnymalTerrainPPO.yaml:8``, ``UsefulHoundPPO.yaml:8``).  ``trunk`` is the actor tower (and the shared trunk)."""
+
+    def __init__(self, num_obs, num_actions, units=(256, 128, 64), separate=False):
         super().__init__()
-        layers, last = [], num_obs
-        for u in units:
-            layers += [nn.Linear(last, u), nn.ELU()]
-            last = u
-        self.trunk = nn.Sequential(*layers)
+
+        def mlp():
+            layers, last = [], num_obs
+            for u in units:
+                layers += [nn.Linear(last, u), nn.ELU()]
+                last = u
+            return nn.Sequential(*layers), last
+
+        self.separate = bool(separate)
+        self.trunk, last = mlp()
+        self.critic_trunk = mlp()[0] if self.separate else None
         self.mu = nn.Linear(last, num_actions)
         self.value = nn.Linear(last, 1)
         self.log_std = nn.Parameter(torch.zeros(num_actions))      # sigma_init const 0 -> std 1, fixed_sigma (state independent)
 
     def forward(self, obs):
         h = self.trunk(obs)
-        return self.mu(h), self.log_std.expand(obs.shape[0], -1), self.value(h).squeeze(-1)
+        hv = self.critic_trunk(obs) if self.separate else h
+        return self.mu(h), self.log_std.expand(obs.shape[0], -1), self.value(hv).squeeze(-1)
+
+
+def compute_gae(rew, val, done, v_last, gamma, tau):
+    """Generalised advantage estimation exactly as rl_games' ``a2c_common.discount_values`` runs it for the hot-path tasks (the same
+    recursion the fork states in-tree for its AMP agent, ``learning/common_agent.py:406-418``): with ``done[t]`` the flag returned by
+    step t, delta_t = r_t + gamma V_{t+1} (1 - done_t) - V_t and A_t = delta_t + gamma tau (1 - done_t) A_{t+1}.
+    ``rew``, ``val``, ``done``: (T, N); ``v_last``: (N) value of the observation after the last step.  Returns the advantages (T, N)."""
+    T = rew.shape[0]
+    adv = torch.zeros_like(rew)
+    last = torch.zeros_like(v_last)
+    for t in reversed(range(T)):
+        nv = v_last if t == T - 1 else val[t + 1]
+        nonterm = 1.0 - done[t]
+        delta = rew[t] + gamma * nv * nonterm - val[t]
+        last = delta + gamma * tau * nonterm * last
+        adv[t] = last
+    return adv
 
 
 def neglogp(x, mu, log_std):
@@ -79,7 +108,10 @@ class PPOConfig:
     critic_coef: float = 2.0
     bounds_loss_coef: float = 0.001
     units: tuple = (256, 128, 64)
+    separate: bool = False      # network.separate of the train yaml: separate actor / critic towers
+    reward_scale: float = 1.0   # config.reward_shaper.scale_value (Cartpole: 0.1)
     max_epochs: int = 1000
+    save_frequency: int = 0     # config.save_frequency: checkpoint every so many epochs (0 = only at the end)
     tf32: bool = False          # TF32 tensor-core matmuls in the update (the reference trains with mixed_precision: True)
     fused_adam: bool = False    # single-kernel Adam (torch fused implementation)
 
@@ -95,7 +127,7 @@ class TrainLog:
 
 class PPO:
     def __init__(self, env, cfg: PPOConfig = PPOConfig(), multi_gpu: bool = False, seed: int = 42, fused_rollout: bool = False,
-                 cuda_graphs: bool = False):
+                 cuda_graphs: bool = False, graph_allreduce: bool = True):
         """``fused_rollout``: evaluate the policy during the rollout with the library's fused tcgen05 kernel
         (``learning/fused_policy.py``; bf16 operands, fp32 accumulation) instead of the torch modules. The update still
         differentiates the fp32 torch network; the behaviour policy's (mu, neglogp, value) are the kernel's.
@@ -103,18 +135,24 @@ class PPO:
         ``cuda_graphs``: capture the whole rollout (``horizon_length`` x [normalise, policy, sample, ``env.step``, bookkeeping] +
         GAE) as ONE CUDA graph and each minibatch update (forward, backward, clip, Adam) as another, so that an epoch is a
         handful of graph launches instead of ~2000 kernel launches from Python.  Needs a task whose ``step()`` is free of host
-        synchronisation and host-side per-step state (the fused flat tasks and Cartpole); the update graph is used on a
-        single GPU only (the multi-GPU path keeps its eager NCCL all-reduce)."""
+        synchronisation and host-side per-step state (the fused flat tasks and Cartpole).  With several GPUs the gradient
+        all-reduce (one flat NCCL all-reduce per minibatch) is captured inside the update graph (``graph_allreduce``); if the
+        capture is refused the update falls back to eager launches with the same all-reduce."""
         self.env, self.cfg, self.multi_gpu = env, cfg, multi_gpu
-        self.fused = None
-        self.cuda_graphs = bool(cuda_graphs)
+        self.fused = self.fused_critic = None
+        # a step() that synchronises with the host cannot be captured: such tasks roll out eagerly whatever the caller asked for
+        self.cuda_graphs = bool(cuda_graphs) and not getattr(env, "needs_host_sync", False)
         self.device = env.rl_device
         torch.manual_seed(seed)
-        self.model = ActorCritic(env.num_obs, env.num_acts, cfg.units).to(self.device)
+        self.model = ActorCritic(env.num_obs, env.num_acts, cfg.units, separate=cfg.separate).to(self.device)
         self.obs_rms = RunningMeanStd((env.num_obs,)).to(self.device)
         self.val_rms = RunningMeanStd(()).to(self.device)
         self.lr_t = torch.tensor(cfg.learning_rate, device=self.device, dtype=torch.float32)
-        graph_update = self.cuda_graphs and not multi_gpu
+        # the minibatch update is captured on one GPU, and on several when the NCCL all-reduce of the gradient can be captured with it
+        graph_update = self.cuda_graphs and (not multi_gpu or graph_allreduce)
+        self.graph_allreduce = bool(graph_allreduce) and multi_gpu
+        self.checkpoint_path = None
+        self.update_capture_error = None
         if cfg.tf32:
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
@@ -130,6 +168,8 @@ class PPO:
             from .fused_policy import FusedPolicy
 
             self.fused = FusedPolicy(env.num_obs, env.num_acts, cfg.units, self.device)
+            # separate towers: a second instance of the kernel evaluates the critic tower (its action head is unused)
+            self.fused_critic = FusedPolicy(env.num_obs, env.num_acts, cfg.units, self.device) if cfg.separate else None
         n, T, dev = env.num_envs, cfg.horizon_length, self.device
         self.ep_rew = torch.zeros(n, device=dev)
         self.ep_len = torch.zeros(n, device=dev)
@@ -172,6 +212,8 @@ class PPO:
         obs = self.obs
         if self.fused is not None:
             self.fused.sync(self.model)
+            if self.fused_critic is not None:
+                self.fused_critic.sync(self.model, critic=True)
         log_std = self.model.log_std.expand(N, -1)
         for t in range(T):
             self.obs_rms.update(obs)
@@ -179,6 +221,9 @@ class PPO:
             if self.fused is not None:
                 self.fused.set_obs_norm(self.obs_rms.mean, self.obs_rms.var, self.obs_rms.eps, 5.0)
                 mu, v = self.fused.forward(obs)
+                if self.fused_critic is not None:
+                    self.fused_critic.set_obs_norm(self.obs_rms.mean, self.obs_rms.var, self.obs_rms.eps, 5.0)
+                    _, v = self.fused_critic.forward(obs)
             else:
                 mu, _, v = self.model(nobs)
             act = mu + log_std.exp() * torch.randn_like(mu)
@@ -186,10 +231,11 @@ class PPO:
             self.b_val[t] = self.val_rms.denormalize(v)
             o, rew, done, extras = env.step(torch.clamp(act, -1.0, 1.0))
             obs.copy_(o["obs"])
-            # value bootstrap on time-outs (rl_games value_bootstrap, docs/release_notes.md:67)
-            rew = rew + cfg.gamma * self.b_val[t] * extras["time_outs"].float()
+            # rl_games play_steps: shaped = reward_shaper(r) (+ gamma V time_outs: value_bootstrap, docs/release_notes.md:67) goes to the
+            # buffer; the episode statistics accumulate the RAW reward
+            shaped = cfg.reward_scale * rew + cfg.gamma * self.b_val[t] * extras["time_outs"].float()
             donef = (done != 0).float()
-            self.b_rew[t], self.b_done[t] = rew, donef
+            self.b_rew[t], self.b_done[t] = shaped, donef
             self.ep_rew += rew
             self.ep_len += 1
             self.fin[0] += (self.ep_rew * donef).sum()
@@ -199,14 +245,7 @@ class PPO:
             self.ep_len *= 1.0 - donef
         _, _, v_last = self.model(self.obs_rms.normalize(obs))
         v_last = self.val_rms.denormalize(v_last)
-        adv = torch.zeros(T, N, device=self.device)
-        last = torch.zeros(N, device=self.device)
-        for t in reversed(range(T)):
-            nv = v_last if t == T - 1 else self.b_val[t + 1]
-            nonterm = 1.0 - self.b_done[t]
-            delta = self.b_rew[t] + cfg.gamma * nv * nonterm - self.b_val[t]
-            last = delta + cfg.gamma * cfg.tau * nonterm * last
-            adv[t] = last
+        adv = compute_gae(self.b_rew, self.b_val, self.b_done, v_last, cfg.gamma, cfg.tau)
         ret = adv + self.b_val
         self.val_rms.update(ret)
         self.f_ret.copy_((ret.reshape(-1) - self.val_rms.mean.float()) / torch.sqrt(self.val_rms.var.float() + 1e-5))
@@ -241,6 +280,24 @@ class PPO:
         with torch.no_grad():
             # KL between the old and the new diagonal Gaussians (same fixed sigma family)
             self.kl_acc += (((mu - f_mu[idx]) ** 2) / (2.0 * torch.exp(2.0 * log_std))).sum(-1).mean()
+
+    @torch.no_grad()
+    def _sync_normalisers(self):
+        """Several GPUs: every rank has the same weights, so it must also normalise inputs and value targets the same way.  After each
+        rollout the running moments are pooled over the ranks (equal sample counts per rank: mean of the means, mean of the second
+        moments) -- one small all-reduce per epoch instead of one per step."""
+        import torch.distributed as dist
+
+        w = dist.get_world_size()
+        for rms in (self.obs_rms, self.val_rms):
+            m2 = rms.var + rms.mean * rms.mean
+            buf = torch.cat([rms.mean.reshape(-1), m2.reshape(-1)])
+            dist.all_reduce(buf)
+            buf /= w
+            k = rms.mean.numel()
+            mean = buf[:k].view_as(rms.mean)
+            rms.mean.copy_(mean)
+            rms.var.copy_((buf[k:].view_as(rms.var) - mean * mean).clamp_min(1e-12))
 
     def _capture(self, fn, warmup=2):
         """Warm ``fn`` up on a side stream (cuBLAS handles, lazy state), then capture it."""
@@ -319,7 +376,13 @@ class PPO:
         T, N = cfg.horizon_length, env.num_envs
         log = TrainLog()
         self.obs.copy_(env.reset()["obs"])
-        graph_update = self.cuda_graphs and not self.multi_gpu
+        graph_update = self.cuda_graphs and (not self.multi_gpu or self.graph_allreduce)
+        if self.multi_gpu:
+            import torch.distributed as dist
+
+            for rms in (self.obs_rms, self.val_rms):      # same starting point on every rank
+                for b in (rms.mean, rms.var, rms.count):
+                    dist.broadcast(b, 0)
         if self.cuda_graphs and self._g_rollout is None:
             if hasattr(env, "enable_device_step_counter"):      # rough-terrain tasks: no per-step host state inside the graph
                 env.enable_device_step_counter(True)
@@ -327,7 +390,16 @@ class PPO:
             self._g_rollout = self._capture(self._rollout, warmup=1)
             if graph_update:
                 self.idx.copy_(torch.randperm(T * N, device=self.device)[:self.mb])
-                self._g_update = self._capture(self._update, warmup=2)
+                try:
+                    self._g_update = self._capture(self._update, warmup=2)
+                except Exception as exc:      # NCCL refused to be captured (old library, watchdog settings): eager update, same math
+                    if not self.multi_gpu:
+                        raise
+                    self._g_update = None
+                    self.update_capture_error = f"{type(exc).__name__}: {exc}"[:200]
+                    torch.cuda.synchronize(self.device)
+                    graph_update = False
+                    # the capturable Adam keeps its learning rate in a device tensor either way
             self.fin.zero_()
         t0 = time.time()
         steps = 0
@@ -339,6 +411,8 @@ class PPO:
                 self._g_rollout.replay()
             else:
                 self._rollout()
+            if self.multi_gpu:
+                self._sync_normalisers()
             steps += T * N
             for _ in range(cfg.mini_epochs):
                 perm = torch.randperm(T * N, device=self.device)
@@ -355,7 +429,7 @@ class PPO:
 
                     dist.all_reduce(kl)
                     kl /= dist.get_world_size()
-                if graph_update:       # adaptive learning rate on the device (the Adam graph reads self.lr_t)
+                if torch.is_tensor(self.opt.param_groups[0]["lr"]):       # adaptive learning rate on the device (the capturable Adam reads self.lr_t)
                     lr = self.lr_t
                     self.lr_t.copy_(torch.where(kl > kl_hi, torch.clamp(lr / 1.5, min=1e-6), torch.where(kl < kl_lo, torch.clamp(lr * 1.5, max=1e-2), lr)))
                 else:
@@ -367,7 +441,7 @@ class PPO:
                     for g in self.opt.param_groups:
                         g["lr"] = self.lr
             if (epoch + 1) % log_every == 0 or epoch == 0 or epoch + 1 == total_epochs:
-                if graph_update:
+                if torch.is_tensor(self.opt.param_groups[0]["lr"]):
                     self.lr = float(self.lr_t)
                 r, l = self._episode_stats()
                 log.epochs.append(epoch + 1)
@@ -377,4 +451,6 @@ class PPO:
                 log.wall_s.append(time.time() - t0)
                 if verbose:
                     print(f"epoch {epoch + 1:5d} env_steps {steps:10d} ep_rew {r:8.3f} ep_len {l:7.1f} lr {self.lr:.2e} wall {time.time() - t0:6.1f}s", flush=True)
+            if cfg.save_frequency > 0 and self.checkpoint_path and (epoch + 1) % cfg.save_frequency == 0 and epoch + 1 < total_epochs:
+                self.save(self.checkpoint_path)       # config.save_frequency of the train yaml: something survives a crash
         return log

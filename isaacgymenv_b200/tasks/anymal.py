@@ -66,6 +66,9 @@ class Anymal(VecTask):
         self.cfg["env"]["numObservations"] = 48
         self.cfg["env"]["numActions"] = 12
         self.fused = bool(cfg["env"].get("fusedStep", True))
+        # step() of the generic hook path synchronises with the host (reset_buf.nonzero()), and domain randomisation keeps host-side
+        # schedules and generators: neither can be replayed from a CUDA graph (learning/ppo.py and train.py look at this flag)
+        self.needs_host_sync = (not self.fused) or bool(self.randomize)
         self.seed = int(cfg.get("seed", 42))
 
         super().__init__(config=self.cfg, rl_device=rl_device, sim_device=sim_device, graphics_device_id=graphics_device_id,

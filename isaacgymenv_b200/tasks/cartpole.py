@@ -27,6 +27,7 @@ class Cartpole(VecTask):
         self.cfg["env"]["numObservations"] = 4
         self.cfg["env"]["numActions"] = 1
         self.fused = bool(cfg["env"].get("fusedStep", True))
+        self.needs_host_sync = (not self.fused) or bool(cfg.get("task", {}).get("randomize", False))      # see tasks/anymal.py
         self.seed = int(cfg.get("seed", 42))
         super().__init__(config=self.cfg, rl_device=rl_device, sim_device=sim_device, graphics_device_id=graphics_device_id,
                          headless=headless, virtual_screen_capture=virtual_screen_capture, force_render=force_render)

@@ -10,7 +10,8 @@
 ``train.params.config.horizon_length=16``).  Hyper-parameters come from ``cfg/train/<Task>PPO.yaml`` (the reference's files with
 the interpolations resolved); the learner is the in-repo PPO (``learning/ppo.py``) instead of rl_games, which is not installed.
 Extra switches of this repo: ``cuda_graphs=True`` (default), ``fused_rollout=True`` (tcgen05 policy kernel: resident weights for [256,128,64], streamed weights for [512,256,128]).
-Checkpoints go to ``runs/<experiment or task>/nn/<name>.pth`` (rl_games' layout, ``docs/rl_examples.md``)."""
+Checkpoints go to ``runs/<experiment or task>/nn/<name>.pth`` (rl_games' directory layout, ``docs/rl_examples.md``; the file holds this
+learner's own state dict -- network, normalisers, optimiser -- not rl_games' key names), every ``save_frequency`` epochs and at the end."""
 from __future__ import annotations
 
 import json
@@ -78,7 +79,10 @@ def ppo_config_from_train_cfg(tc: Dict[str, Any], max_iterations=None):
 
     c = tc["params"]["config"]
     units = tuple(tc["params"]["network"]["mlp"]["units"])
-    return PPOConfig(horizon_length=int(c["horizon_length"]), minibatch_size=int(c["minibatch_size"]), mini_epochs=int(c["mini_epochs"]),
+    separate = bool(tc["params"]["network"].get("separate", False))
+    shaper = c.get("reward_shaper") or {}
+    return PPOConfig(separate=separate, reward_scale=float(shaper.get("scale_value", 1.0)), save_frequency=int(c.get("save_frequency", 0) or 0),
+                     horizon_length=int(c["horizon_length"]), minibatch_size=int(c["minibatch_size"]), mini_epochs=int(c["mini_epochs"]),
                      gamma=float(c["gamma"]), tau=float(c["tau"]), e_clip=float(c["e_clip"]), entropy_coef=float(c.get("entropy_coef", 0.0)),
                      learning_rate=float(c["learning_rate"]), kl_threshold=float(c.get("kl_threshold", 0.008)), grad_norm=float(c.get("grad_norm", 1.0)),
                      critic_coef=float(c.get("critic_coef", 2.0)), bounds_loss_coef=float(c.get("bounds_loss_coef", 0.0) or 0.0), units=units,
@@ -110,10 +114,15 @@ def main(argv=None):
     cfg = ppo_config_from_train_cfg(tc, top["max_iterations"] if top["max_iterations"] != "" else None)
     cfg.tf32 = bool(top["tf32"])
     fused = bool(top["fused_rollout"]) and len(cfg.units) == 3 and cfg.units[0] <= 512 and max(cfg.units[1:]) <= 256
+    # a task whose step() synchronises with the host (generic hook path: reset_buf.nonzero(); domain randomisation: frame-count
+    # schedules and host-side generators) cannot be replayed from a CUDA graph -- it would freeze at its warm-up values
     graphs = bool(top["cuda_graphs"]) and not getattr(env, "needs_host_sync", False)
+    if top["save_frequency"] != "":
+        cfg.save_frequency = int(top["save_frequency"])
     ppo = PPO(env, cfg, multi_gpu=multi, seed=int(top["seed"]) + info.rank, fused_rollout=fused, cuda_graphs=graphs)
     name = top["experiment"] or tc["params"]["config"]["name"]
     ckpt = top["output"] or os.path.join("runs", name, "nn", f"{name}.pth")
+    ppo.checkpoint_path = ckpt if info.rank == 0 else None
     if top["checkpoint"]:
         ppo.load(top["checkpoint"], load_optimizer=not top["test"])
     if top["test"]:

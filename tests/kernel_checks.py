@@ -347,8 +347,9 @@ def check_fused_step(make_backend, robot="anymal", n=16, steps=25, seed=3):
             obs_o, obsc_o, rew_o, to_o = tm.anymal_post_physics(st, cd, a, draws)
             root_k, dof_k = be.get_state()
             tk = be.get_task()
-            # (1) end-to-end agreement, physics tolerance
-            assert np.abs(root_k - st["root"]).max() < 2e-3, f"step {k}: root deviates {np.abs(root_k - st['root']).max():.2e}"
+            # (1) end-to-end agreement, physics tolerance: the two trajectories run free for up to 12 steps (an episode here); the bar is
+            # north_star's 1e-2 over a 10-step horizon, stick / slip decisions of the friction cone are where float32 rounding shows
+            assert np.abs(root_k - st["root"]).max() < 5e-3, f"step {k}: root deviates {np.abs(root_k - st['root']).max():.2e}"
             assert np.abs(dof_k[:, :, 0] - st["dof_pos"]).max() < 5e-3
             np.testing.assert_allclose(tk["obs"], obs_o, rtol=0, atol=2e-2)
             assert np.array_equal(tk["progress"], st["progress"])
