@@ -298,6 +298,69 @@ def measure_task(task, num_envs, steps, warmup, preroll, dev, rank, world, dist,
     return res
 
 
+def measure_ppo(dev, rank, world, dist, num_envs=8192, epochs=10, warm=2):
+    """BASELINE.json config 5: Anymal, 8192 envs per GPU, PPO per cfg/train/AnymalPPO.yaml (horizon 24, minibatch 32768, 5 mini-epochs
+    -> 6 x 5 = 30 gradient all-reduces per iteration over NCCL), one process per GPU, seeds 42 + rank (reference README.md:165-172,
+    utils/utils.py:89-94).  Rollout (tcgen05 policy kernel + fused env step) and minibatch update (with its all-reduce) replay from
+    CUDA graphs.  Returns env-steps/s INCLUDING the learner, and the stand-alone cost of one iteration's all-reduces."""
+    import torch
+
+    import isaacgymenv_b200
+    from isaacgymenv_b200.learning.ppo import PPO
+    from isaacgymenv_b200.train import load_train_config, ppo_config_from_train_cfg
+
+    env = isaacgymenv_b200.make(seed=42 + rank, task="Anymal", num_envs=num_envs, sim_device=dev, rl_device=dev, headless=True)
+    cfg = ppo_config_from_train_cfg(load_train_config("AnymalPPO"))
+    cfg.tf32 = True
+    ppo = PPO(env, cfg, multi_gpu=world > 1, seed=42 + rank, fused_rollout=True, cuda_graphs=True)
+    ppo.train(max_epochs=warm, log_every=10 ** 9)          # graph capture + warm-up epochs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    log = ppo.train(max_epochs=epochs, log_every=10 ** 9)
+    e1.record()
+    barrier()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    T, N = cfg.horizon_length, env.num_envs
+    n_mb = max((T * N) // min(cfg.minibatch_size, T * N), 1)
+    n_ar = cfg.mini_epochs * n_mb
+    nparam = sum(p.numel() for p in ppo.model.parameters())
+    nccl_ms = 0.0
+    if world > 1:
+        buf = torch.zeros(nparam, device=dev)
+        for _ in range(5):
+            dist.all_reduce(buf)
+        barrier()
+        e0.record()
+        for _ in range(n_ar * 10):
+            dist.all_reduce(buf)
+        e1.record()
+        barrier()
+        nccl_ms = e0.elapsed_time(e1) / 10
+    t = torch.tensor([ms, nccl_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, nccl_ms = t.tolist()
+    per_iter = ms / epochs
+    out = {"workload": f"Anymal PPO (cfg/train/AnymalPPO.yaml), {N} envs/GPU, horizon {T}, minibatch {cfg.minibatch_size}, {cfg.mini_epochs} mini-epochs",
+           "envs_per_gpu": N, "n_gpus": world, "iterations": epochs, "ms_per_iteration": per_iter,
+           "env_steps_per_sec_incl_learner": world * N * T * epochs / (ms * 1e-3), "unit": UNIT,
+           "allreduces_per_iteration": n_ar if world > 1 else 0, "allreduce_bytes": nparam * 4,
+           "nccl_ms_per_iteration_standalone": nccl_ms, "nccl_share_of_iteration": (nccl_ms / per_iter) if per_iter > 0 else None,
+           "update_in_cuda_graph": ppo._g_update is not None, "rollout_in_cuda_graph": ppo._g_rollout is not None,
+           "update_capture_error": ppo.update_capture_error, "mean_episode_reward_last": (log.mean_episode_reward[-1] if log.mean_episode_reward else None)}
+    del ppo, env
+    torch.cuda.empty_cache()
+    return out
+
+
 def traffic_for(task):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed `ncu --set full` captures
     (profiles/traffic.json; the capture is cold-cache like the flushed timing)."""
@@ -349,6 +412,12 @@ def run_ours(args):
                              "gpu_launches": r["launches"], "roofline": roofline_of(r, k), "contact_stats": r["contact_stats"]}
             except Exception as exc:      # never lose the headline line to a side config
                 others[t] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    ppo = None
+    if args.ppo and args.task == "Anymal" and args.num_envs <= 0:      # config 5 rides in the same line at every N
+        try:
+            ppo = measure_ppo(dev, rank, world, dist)
+        except Exception as exc:
+            ppo = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0:
         total = world * n * args.steps
         cold_ms, warm_ms, e2e_ms = res["cold_ms"], res["warm_ms"], res["e2e_ms"]
@@ -381,6 +450,8 @@ def run_ours(args):
                 "cpu_baseline": cpu, "clocks": res["clocks"], "contact_stats": res["contact_stats"]}
         if others:
             line["other_configs"] = others
+        if ppo:
+            line["ppo_config5"] = ppo
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -398,6 +469,8 @@ def main():
                     "the timed region must be the contact steady state whatever --steps is)")
     ap.add_argument("--other-configs", type=int, default=1, help="1: also time AnymalTerrain (trimesh), UsefulHound and Cartpole (N=1 only) and report them "
                     "under other_configs")
+    ap.add_argument("--ppo", type=int, default=1, help="1: also run BASELINE config 5 (Anymal PPO, 8192 envs/GPU, NCCL gradient all-reduce when N > 1) "
+                    "for a few iterations and report it under ppo_config5")
     ap.add_argument("--task", default="Anymal", choices=sorted(TASKS), help="hot-path config to time (default: the headline Anymal config)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -99,17 +99,59 @@ def make(seed: int, task: str, num_envs: int, sim_device: str, rl_device: str, g
                virtual_screen_capture=virtual_screen_capture, force_render=force_render)
 
 
-def install_isaacgym_shim():
-    """Register this package's gym shim as ``isaacgym`` so task code written as ``from isaacgym import gymapi,
-    gymtorch`` runs unchanged."""
+def install_isaacgym_shim(reference_root: Optional[str] = None):
+    """Register this package as the ``isaacgym`` the reference's task files import, so that they run UNMODIFIED on libb200gym:
+
+    * ``isaacgym.gymapi`` / ``isaacgym.gymtorch``: this package's gym shim over the C ABI;
+    * ``isaacgym.terrain_utils``: the terrain generator (``from isaacgym.terrain_utils import *``, tasks/anymal_terrain.py:542);
+    * ``isaacgym.torch_utils``: the tensor helpers; ``isaacgym.gymutil``: viewer-side helpers as no-ops (headless only);
+    * ``gym`` / ``gym.spaces`` (tasks/base/vec_task.py:34-35) when OpenAI gym is not installed; ``np.Inf`` (vec_task.py:107, gone in numpy 2).
+
+    With ``reference_root`` (a checkout of the reference) the ``isaacgymenvs`` package is made importable WITHOUT running its
+    ``__init__`` (which pulls in hydra / omegaconf / rl_games, ``isaacgymenvs/__init__.py:1-5``), so
+    ``from isaacgymenvs.tasks.anymal import Anymal`` gives the reference's own class, ready to be constructed on this engine."""
+    import importlib.util
     import sys
     import types
 
-    from . import gymapi, gymtorch
+    import numpy as np
 
-    mod = types.ModuleType("isaacgym")
-    mod.gymapi, mod.gymtorch = gymapi, gymtorch
-    sys.modules.setdefault("isaacgym", mod)
-    sys.modules.setdefault("isaacgym.gymapi", gymapi)
-    sys.modules.setdefault("isaacgym.gymtorch", gymtorch)
+    from . import gymapi, gymtorch, spaces, terrain
+    from .utils import torch_math
+
+    mod = sys.modules.get("isaacgym")
+    if mod is None or not getattr(mod, "_b2g_shim", False):
+        mod = types.ModuleType("isaacgym")
+        mod._b2g_shim = True
+        sys.modules["isaacgym"] = mod
+    gymutil = types.ModuleType("isaacgym.gymutil")
+
+    class _Geometry:           # debug-visualisation helpers: constructed by viewer code only
+        def __init__(self, *a, **k):
+            pass
+
+    gymutil.AxesGeometry = gymutil.WireframeSphereGeometry = gymutil.WireframeBoxGeometry = _Geometry
+    gymutil.draw_lines = lambda *a, **k: None
+    gymutil.parse_arguments = lambda *a, **k: types.SimpleNamespace()
+    for name, m in (("gymapi", gymapi), ("gymtorch", gymtorch), ("terrain_utils", terrain), ("torch_utils", torch_math), ("gymutil", gymutil)):
+        setattr(mod, name, m)
+        sys.modules["isaacgym." + name] = m
+    if "gym" not in sys.modules and importlib.util.find_spec("gym") is None:
+        g = types.ModuleType("gym")
+        g.spaces = spaces
+        g.Space, g.Env = spaces.Space, object
+        g._b2g_shim = True
+        sys.modules["gym"], sys.modules["gym.spaces"] = g, spaces
+    if not hasattr(np, "Inf"):
+        np.Inf = np.inf
+    if reference_root:
+        base = os.path.join(reference_root, "isaacgymenvs")
+        if not os.path.isdir(base):
+            raise FileNotFoundError(f"no isaacgymenvs package under {reference_root}")
+        for name, path in (("isaacgymenvs", base), ("isaacgymenvs.tasks", os.path.join(base, "tasks")),
+                           ("isaacgymenvs.tasks.base", os.path.join(base, "tasks", "base")), ("isaacgymenvs.utils", os.path.join(base, "utils"))):
+            if name not in sys.modules:
+                pkg = types.ModuleType(name)
+                pkg.__path__ = [path]
+                sys.modules[name] = pkg
     return mod

@@ -497,6 +497,38 @@ class Gym:
         sim.actor_poses.append((pose.p.x, pose.p.y, pose.p.z, pose.r.x, pose.r.y, pose.r.z, pose.r.w))
         return 0
 
+    # ---- actor bookkeeping used by the reference's domain-randomisation code (tasks/base/vec_task.py:583, utils/dr_utils.py:233-237)
+    def get_actor_count(self, env: Env):
+        return len(env.actors)
+
+    def get_actor_handle(self, env: Env, index: int):
+        if not 0 <= int(index) < len(env.actors):
+            raise _lib.B2GError(f"actor index {index} out of range")
+        return int(index)
+
+    def get_actor_name(self, env: Env, actor: int):
+        return env.actors[int(actor)]
+
+    def find_actor_handle(self, env: Env, name: str):
+        return env.actors.index(name) if name in env.actors else -1
+
+    def get_actor_rigid_shape_count(self, env: Env, actor: int):
+        return env.sim.asset.n_shapes
+
+    def get_actor_tendon_properties(self, env: Env, actor: int):
+        return []           # no tendons in the articulation model of this engine
+
+    def set_actor_tendon_properties(self, env: Env, actor: int, props):
+        return True
+
+    def set_rigid_body_color(self, env: Env, actor: int, body: int, mesh_type=None, color=None):
+        return None         # rendering only (headless engine)
+
+    def set_actor_scale(self, env: Env, actor: int, scale: float):
+        """Isaac Gym returns False when the actor could not be rescaled; geometric scaling of a compiled articulation is not supported
+        here, so a request for anything but 1.0 reports failure the same way (vec_task.py:786 ignores the result)."""
+        return abs(float(scale) - 1.0) < 1e-12
+
     def get_actor_dof_properties(self, env: Env, actor: int):
         sim = env.sim
         return sim.dof_props.copy() if sim.dof_props is not None else self.get_asset_dof_properties(sim.asset)
