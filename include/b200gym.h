@@ -33,7 +33,8 @@ extern "C" {
 #define B2G_MAX_CHAINS 8
 #define B2G_MAX_CHAIN_LEN 6
 #define B2G_MAX_CPTS 128
-#define B2G_MAX_CONTACTS_PER_CHAIN 4
+#define B2G_LINK_SCALE_COLS 6
+#define B2G_MAX_CONTACTS_PER_CHAIN 8   /* contact slots per solver lane (chain); candidates beyond them are dropped AND counted (b2g_sim_contact_stats) */
 
 enum b2g_status {
     B2G_OK = 0,
@@ -143,6 +144,11 @@ enum b2g_tensor_kind {
     B2G_T_FRICTION = 9,         /* (N) f32 per-env shape friction coefficient                */
     B2G_T_ENV_SCALE = 10,       /* (N,4) f32 per-env scale of [link masses+inertias, drive stiffness, drive damping, spare]:
                                    tensorised domain randomisation (vec_task.py:610-840); ones until acquired */
+    B2G_T_LINK_SCALE = 11,      /* (N,nd+1,B2G_LINK_SCALE_COLS) f32 per-LINK randomisation, link 0 = root, link 1+d = child link of
+                                   DOF d: [scale of the link's mass+inertia, scale of DOF d's stiffness, scale of its damping,
+                                   offset added to its lower limit, offset added to its upper limit, spare]; the scales multiply
+                                   B2G_T_ENV_SCALE.  The reference randomises every body / DOF property entry on its own
+                                   (utils/dr_utils.py:135-238, cfg/task/Anymal.yaml:146-170); (1,1,1,0,0,0) until acquired */
     B2G_T_COUNT
 };
 

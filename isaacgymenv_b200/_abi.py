@@ -16,12 +16,13 @@ MAX_BODIES = 32
 MAX_CHAINS = 8
 MAX_CHAIN_LEN = 6
 MAX_CPTS = 128
-MAX_CONTACTS_PER_CHAIN = 4
+MAX_CONTACTS_PER_CHAIN = 8
+LINK_SCALE_COLS = 6
 
 DOF_MODE_NONE, DOF_MODE_POS, DOF_MODE_VEL, DOF_MODE_EFFORT = 0, 1, 2, 4
 
 (T_ROOT_STATE, T_DOF_STATE, T_NET_CONTACT, T_DOF_FORCE, T_RIGID_BODY_STATE, T_DOF_TARGET, T_DOF_ACTUATION,
- T_JACOBIAN, T_MASS_MATRIX, T_FRICTION, T_ENV_SCALE) = range(11)
+ T_JACOBIAN, T_MASS_MATRIX, T_FRICTION, T_ENV_SCALE, T_LINK_SCALE) = range(12)
 
 (TT_OBS, TT_OBS_CLAMPED, TT_REW, TT_RESET, TT_PROGRESS, TT_TIMEOUT, TT_COMMANDS, TT_ACTIONS, TT_RAND_OVERRIDE, TT_TORQUES, TT_LAST_ACTIONS,
  TT_LAST_DOF_VEL, TT_FEET_AIR_TIME, TT_EPISODE_SUMS, TT_ENV_ORIGINS, TT_TERRAIN_LEVELS, TT_TERRAIN_TYPES, TT_NOISE_OVERRIDE, TT_PUSH_OVERRIDE,

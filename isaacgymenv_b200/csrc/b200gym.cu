@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kBlock) k_probe(SimArgs A, float* qdd, float* 
 #pragma unroll
     for (int j = 0; j < NL; j++)
         if (j < len) st.act[j] = A.actuation[(size_t)env * M->n_dof + d0 + j];
-    substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, load_env_dr(nullptr, A.env_scale, valid ? env : 0, valid), false, sc, bf);
+    substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, env_dr(A, valid ? env : 0, valid, false), false, sc, bf);
     if (valid) {
 #pragma unroll
         for (int j = 0; j < NL; j++)
@@ -342,11 +342,12 @@ __global__ void k_body_state(const DevModel* M, const float* root, const float* 
     body_state_env(M, root + (size_t)e * 13, dof + (size_t)e * M->n_dof * 2, out + (size_t)e * M->n_bodies * 13);
 }
 
-__global__ void k_mass_matrix(const DevModel* M, const float* root, const float* dof, float* out, int n, const float* env_scale) {
+__global__ void k_mass_matrix(const DevModel* M, const float* root, const float* dof, float* out, int n, const float* env_scale,
+                              const float* link_scale) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     mass_matrix_env(M, root + (size_t)e * 13, dof + (size_t)e * M->n_dof * 2, out + (size_t)e * M->n_dof * M->n_dof,
-                    env_scale ? env_scale[(size_t)e * 4] : 1.0f);
+                    env_scale ? env_scale[(size_t)e * 4] : 1.0f, link_scale ? link_scale + (size_t)e * (M->n_dof + 1) * B2G_LINK_SCALE_COLS : nullptr);
 }
 
 __global__ void k_jacobian(const DevModel* M, const float* root, const float* dof, float* out, int n, int per_env) {
@@ -419,6 +420,7 @@ struct b2g_sim {
     long long* step_ctr = nullptr;   // device copy of the counter the NEXT step uses (b2g_task_terrain_device_step)
     int auto_step = 0;
     int env_scale_used = 0;          // set when B2G_T_ENV_SCALE is first acquired: until then the kernels skip the loads
+    int link_scale_used = 0;         // same for B2G_T_LINK_SCALE
     int init_done = 0;
     float *obs = nullptr, *obs_clamped = nullptr, *rew = nullptr, *commands = nullptr, *actions = nullptr, *rand_override = nullptr;
     long long *reset = nullptr, *progress = nullptr, *timeout = nullptr;
@@ -464,6 +466,7 @@ SimArgs make_args(const b2g_sim* s) {
     A.contact = s->t[B2G_T_NET_CONTACT];
     A.friction = s->t[B2G_T_FRICTION];
     A.env_scale = s->env_scale_used ? s->t[B2G_T_ENV_SCALE] : nullptr;   // ones until somebody acquires the tensor
+    A.link_scale = s->link_scale_used ? s->t[B2G_T_LINK_SCALE] : nullptr;
     return A;
 }
 
@@ -534,6 +537,7 @@ size_t tensor_floats(const b2g_sim* s, int kind) {
         case B2G_T_MASS_MATRIX: return n * nd * nd;
         case B2G_T_FRICTION: return n;
         case B2G_T_ENV_SCALE: return n * 4;
+        case B2G_T_LINK_SCALE: return n * (nd + 1) * B2G_LINK_SCALE_COLS;
         default: return 0;
     }
 }
@@ -556,6 +560,7 @@ void describe(const b2g_sim* s, int kind, b2g_tensor_desc* d) {
         case B2G_T_MASS_MATRIX: d->ndim = 3; d->shape[0] = n; d->shape[1] = nd; d->shape[2] = nd; break;
         case B2G_T_FRICTION: d->ndim = 1; d->shape[0] = n; break;
         case B2G_T_ENV_SCALE: d->ndim = 2; d->shape[0] = n; d->shape[1] = 4; break;
+        case B2G_T_LINK_SCALE: d->ndim = 3; d->shape[0] = n; d->shape[1] = nd + 1; d->shape[2] = B2G_LINK_SCALE_COLS; break;
         default: d->ndim = 0;
     }
 }
@@ -803,6 +808,16 @@ int b2g_sim_prepare(b2g_sim* s) {
         CUDA_TRY(cudaMemcpy(d_row, &one, sizeof(float), cudaMemcpyHostToDevice));
         k_fill_rows<<<(s->n_envs + 255) / 256, 256>>>(s->t[B2G_T_FRICTION], d_row, s->n_envs, 1);
         k_fill_rows<<<(s->n_envs * 4 + 255) / 256, 256>>>(s->t[B2G_T_ENV_SCALE], d_row, s->n_envs * 4, 1);
+        {
+            const float row[B2G_LINK_SCALE_COLS] = {1.0f, 1.0f, 1.0f, 0.0f, 0.0f, 0.0f};
+            float* d_row6 = nullptr;
+            CUDA_TRY(cudaMalloc(&d_row6, sizeof(row)));
+            CUDA_TRY(cudaMemcpy(d_row6, row, sizeof(row), cudaMemcpyHostToDevice));
+            const int nls = s->n_envs * (s->model.n_dof + 1);
+            k_fill_rows<<<(nls * B2G_LINK_SCALE_COLS + 255) / 256, 256>>>(s->t[B2G_T_LINK_SCALE], d_row6, nls, B2G_LINK_SCALE_COLS);
+            CUDA_TRY(cudaDeviceSynchronize());
+            cudaFree(d_row6);
+        }
         s->launches += 3;
         CUDA_TRY(cudaDeviceSynchronize());
         cudaFree(d_row);
@@ -846,6 +861,7 @@ int b2g_sim_tensor(b2g_sim* s, int kind, b2g_tensor_desc* out) {
         if (rc != B2G_OK) return rc;
     }
     if (kind == B2G_T_ENV_SCALE) s->env_scale_used = 1;
+    if (kind == B2G_T_LINK_SCALE) s->link_scale_used = 1;
     describe(s, kind, out);
     out->data = s->t[kind];
     return B2G_OK;
@@ -875,7 +891,8 @@ int b2g_sim_refresh(b2g_sim* s, int kind, void* stream) {
             cudaStream_t st = (cudaStream_t)stream;
             if (kind == B2G_T_MASS_MATRIX)
                 k_mass_matrix<<<(s->n_envs + 63) / 64, 64, 0, st>>>(s->d_model, s->t[B2G_T_ROOT_STATE], s->t[B2G_T_DOF_STATE], s->t[kind], s->n_envs,
-                                                                            s->env_scale_used ? s->t[B2G_T_ENV_SCALE] : nullptr);
+                                                                            s->env_scale_used ? s->t[B2G_T_ENV_SCALE] : nullptr,
+                                                                            s->link_scale_used ? s->t[B2G_T_LINK_SCALE] : nullptr);
             else
                 k_jacobian<<<(s->n_envs + 63) / 64, 64, 0, st>>>(s->d_model, s->t[B2G_T_ROOT_STATE], s->t[B2G_T_DOF_STATE], s->t[kind], s->n_envs,
                                                                  (int)(tensor_floats(s, kind) / s->n_envs));

@@ -203,10 +203,19 @@ struct LaneState {
 struct EnvDr {
     float mu = 1.0f, mass = 1.0f, kp = 1.0f, kd = 1.0f;
     bool live = true;      // false for the padding threads of the last block (they shadow the last environment): not counted in the statistics
+    const float* link = nullptr;   // this environment's (nd + 1, B2G_LINK_SCALE_COLS) per-link rows (B2G_T_LINK_SCALE) or null
+    // combined scales / limit offsets of link l (0 = root, 1 + d = child of DOF d)
+    B2G_HD B2G_INL float mass_of(int l) const { return link ? mass * link[B2G_LINK_SCALE_COLS * l] : mass; }
+    B2G_HD B2G_INL float kp_of(int l) const { return link ? kp * link[B2G_LINK_SCALE_COLS * l + 1] : kp; }
+    B2G_HD B2G_INL float kd_of(int l) const { return link ? kd * link[B2G_LINK_SCALE_COLS * l + 2] : kd; }
+    B2G_HD B2G_INL float lower_of(int l) const { return link ? link[B2G_LINK_SCALE_COLS * l + 3] : 0.0f; }
+    B2G_HD B2G_INL float upper_of(int l) const { return link ? link[B2G_LINK_SCALE_COLS * l + 4] : 0.0f; }
 };
-B2G_HD B2G_INL EnvDr load_env_dr(const float* friction, const float* env_scale, int env, bool live = true) {
+B2G_HD B2G_INL EnvDr load_env_dr(const float* friction, const float* env_scale, int env, bool live = true, const float* link_scale = nullptr,
+                                 int n_links = 0) {
     EnvDr d;
     d.live = live;
+    if (link_scale) d.link = link_scale + (size_t)env * n_links * B2G_LINK_SCALE_COLS;
     if (friction) d.mu = friction[env];
     if (env_scale) {
         d.mass = env_scale[(size_t)env * 4 + 0];
@@ -342,7 +351,7 @@ B2G_LINK_UNROLL
                 L[j].vl = vp + vj;
                 L[j].cb = crm(L[j].vl, vj);
                 // drive
-                const float kp = D.kp * dr.kp, kd = D.kd * dr.kd;
+                const float kp = D.kp * dr.kp_of(1 + d0 + j), kd = D.kd * dr.kd_of(1 + d0 + j);
                 float t = 0.0f, de = D.armature;
                 if (PROBE) {
                     t = st.act[j];
@@ -358,7 +367,7 @@ B2G_LINK_UNROLL
                 }
                 // joint limit: one-sided implicit spring-damper, folded in exactly like the implicit drive
                 {
-                    const float lo = D.lower, hi = D.upper, qp = st.q[j] + h * st.qd[j];
+                    const float lo = D.lower + dr.lower_of(1 + d0 + j), hi = D.upper + dr.upper_of(1 + d0 + j), qp = st.q[j] + h * st.qd[j];
                     float ref = 0.0f;
                     bool on = false;
                     if (lo > -1e30f && (st.q[j] < lo || qp < lo)) { ref = lo; on = true; }
@@ -389,9 +398,9 @@ B2G_LINK_UNROLL
             if (j < len) {
                 const DevDof& D = M->dof[d0 + j];
                 const V3 cw = L[j].pl + mul(L[j].Rl, V3{D.com[0], D.com[1], D.com[2]});
-                const S3 iw = rotate_sym(L[j].Rl, S3{D.inertia[0] * dr.mass, D.inertia[1] * dr.mass, D.inertia[2] * dr.mass, D.inertia[3] * dr.mass,
-                                                   D.inertia[4] * dr.mass, D.inertia[5] * dr.mass});
-                SI I = rigid_inertia(D.mass * dr.mass, cw, iw);
+                const float ms = dr.mass_of(1 + d0 + j);
+                const S3 iw = rotate_sym(L[j].Rl, S3{D.inertia[0] * ms, D.inertia[1] * ms, D.inertia[2] * ms, D.inertia[3] * ms, D.inertia[4] * ms, D.inertia[5] * ms});
+                SI I = rigid_inertia(D.mass * ms, cw, iw);
                 SV pA = crf(L[j].vl, mul(I, L[j].vl));
                 if (j + 1 < len) { I += IAc; pA += pAc; }
                 L[j].U = mul(I, L[j].S);
@@ -413,9 +422,10 @@ B2G_LINK_UNROLL
         SI IA0 = grp_sum<LANES>(IAc);
         SV pA0 = grp_sum<LANES>(pAc);
         const V3 cw = mul(R0, V3{M->root_com[0], M->root_com[1], M->root_com[2]});
-        const S3 iw = rotate_sym(R0, S3{M->root_inertia[0] * dr.mass, M->root_inertia[1] * dr.mass, M->root_inertia[2] * dr.mass,
-                                        M->root_inertia[3] * dr.mass, M->root_inertia[4] * dr.mass, M->root_inertia[5] * dr.mass});
-        SI I0 = rigid_inertia(M->root_mass * dr.mass, cw, iw);
+        const float ms0 = dr.mass_of(0);
+        const S3 iw = rotate_sym(R0, S3{M->root_inertia[0] * ms0, M->root_inertia[1] * ms0, M->root_inertia[2] * ms0, M->root_inertia[3] * ms0,
+                                        M->root_inertia[4] * ms0, M->root_inertia[5] * ms0});
+        SI I0 = rigid_inertia(M->root_mass * ms0, cw, iw);
         pA0 += crf(v0, mul(I0, v0));
         IA0 += I0;
         bool ok;
@@ -681,8 +691,8 @@ B2G_LINK_UNROLL
             st.q[j] += h * qp;
             st.qd[j] = qv;
             float f = 0.0f;
-            if (D.drive_mode == B2G_DOF_MODE_POS) f = D.kp * dr.kp * (st.tgt[j] - st.q[j]) - D.kd * dr.kd * qv;
-            else if (D.drive_mode == B2G_DOF_MODE_VEL) f = D.kd * dr.kd * (st.tgt[j] - qv);
+            if (D.drive_mode == B2G_DOF_MODE_POS) f = D.kp * dr.kp_of(1 + d0 + j) * (st.tgt[j] - st.q[j]) - D.kd * dr.kd_of(1 + d0 + j) * qv;
+            else if (D.drive_mode == B2G_DOF_MODE_VEL) f = D.kd * dr.kd_of(1 + d0 + j) * (st.tgt[j] - qv);
             else if (D.drive_mode == B2G_DOF_MODE_EFFORT) f = st.act[j];
             if (D.effort > 0.0f) f = fminf(fmaxf(f, -D.effort), D.effort);
             st.frc[j] = f;

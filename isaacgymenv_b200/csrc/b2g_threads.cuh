@@ -19,7 +19,13 @@ struct SimArgs {
     float* contact;          // (N,nb,3)
     const float* friction;   // (N) per-env shape friction
     const float* env_scale = nullptr;   // (N,4) per-env scale of link masses, drive stiffness, drive damping, (spare); null = ones
+    const float* link_scale = nullptr;  // (N,nd+1,B2G_LINK_SCALE_COLS) per-link randomisation rows (B2G_T_LINK_SCALE); null = none
 };
+
+// the randomisation scales of environment `env` as the sub-step reads them
+B2G_HD B2G_INL EnvDr env_dr(const SimArgs& A, int env, bool live, bool with_friction = true) {
+    return load_env_dr(with_friction ? A.friction : nullptr, A.env_scale, env, live, A.link_scale, A.M->n_dof + 1);
+}
 
 struct TaskArgs {
     b2g_anymal_cfg cfg;
@@ -97,7 +103,7 @@ B2G_HD B2G_INL void simulate_thread(const SimArgs& A, int env, int lane, bool va
             st.act[j] = A.actuation[k];
         }
     }
-    const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0, valid);
+    const EnvDr mu_shape = env_dr(A, valid ? env : 0, valid);
     for (int s = 0; s < A.P.substeps; s++)
         substep<LANES, NL, FIXED, HF, false, (LANES == 4 && NL == 3) || (LANES == 1 && NL == 2)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
     if (valid) {
@@ -237,7 +243,7 @@ B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int 
         }
     }
     if (!T.post_only) {
-        const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0, valid);
+        const EnvDr mu_shape = env_dr(A, valid ? env : 0, valid);
 #pragma unroll 1
         for (int s = 0; s < A.P.substeps; s++)
             substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
@@ -335,7 +341,7 @@ B2G_HD B2G_INL void cartpole_step_thread(const SimArgs& A, const TaskArgs& T, in
     st.act[1] = 0.0f;
     if (!T.post_only) {
         for (int s = 0; s < A.P.substeps; s++)
-            substep<1, 2, true, false, false, true>(M, A.P, 0, 2, 0, st, load_env_dr(nullptr, A.env_scale, valid ? env : 0, valid), s == A.P.substeps - 1, sc, bf);
+            substep<1, 2, true, false, false, true>(M, A.P, 0, 2, 0, st, env_dr(A, valid ? env : 0, valid, false), s == A.P.substeps - 1, sc, bf);
     }
     long long progress = T.progress[env] + 1;
     long long reset_prev = T.reset[env];
@@ -525,7 +531,7 @@ B2G_HD inline void osc_apply(const OscPrepared& P, const float* q, const float* 
 // Kinematics + composite-rigid-body pass over one chain: joint-space mass-matrix block of the chain (n x n, row-major in
 // mm[36]), the position (relative to the root origin) of link `want_link` (chain-local index, -1 = root) and its world rotation.
 B2G_HD inline void chain_crba(const DevModel* M, int d0, int n, const float* rootq, const float* q, float* mm, int want_link, V3* want_pos, M3* want_rot,
-                              const float* qd, V3 root_w, V3 root_v, SV* want_vel, float mass_scale = 1.0f) {
+                              const float* qd, V3 root_w, V3 root_v, SV* want_vel, float mass_scale = 1.0f, const float* link_scale = nullptr) {
     M3 R = quat_to_m3(rootq[0], rootq[1], rootq[2], rootq[3]);
     V3 p = V3{0, 0, 0};
     SV vel = SV{root_w, root_v};
@@ -544,7 +550,7 @@ B2G_HD inline void chain_crba(const DevModel* M, int d0, int n, const float* roo
         else { R = RJ; p = pj + axw * q[j]; S[j] = SV{V3{0, 0, 0}, axw}; }
         vel = vel + S[j] * qd[j];
         const V3 cw = p + mul(R, V3{D.com[0], D.com[1], D.com[2]});
-        const float ms = mass_scale;
+        const float ms = link_scale ? mass_scale * link_scale[B2G_LINK_SCALE_COLS * (1 + d0 + j)] : mass_scale;
         I[j] = rigid_inertia(D.mass * ms, cw, rotate_sym(R, S3{D.inertia[0] * ms, D.inertia[1] * ms, D.inertia[2] * ms, D.inertia[3] * ms, D.inertia[4] * ms,
                                                             D.inertia[5] * ms}));
         if (j == want_link) { *want_pos = p; *want_rot = R; *want_vel = vel; }
@@ -570,7 +576,8 @@ B2G_HD inline void arm_refresh(const SimArgs& A, const TerrainArgs& T, int env, 
     const int jl = M->body_link[C.jac_body];
     const int jloc = (jl == 0) ? -1 : jl - 1 - d0;
     V3 lp; M3 lr; SV lv;
-    chain_crba(M, d0, len, rq, st.q, mm, jloc, &lp, &lr, st.qd, st.rw, st.rv, &lv, A.env_scale ? A.env_scale[(size_t)env * 4] : 1.0f);
+    chain_crba(M, d0, len, rq, st.q, mm, jloc, &lp, &lr, st.qd, st.rw, st.rv, &lv, A.env_scale ? A.env_scale[(size_t)env * 4] : 1.0f,
+               A.link_scale ? A.link_scale + (size_t)env * (M->n_dof + 1) * B2G_LINK_SCALE_COLS : nullptr);
     const V3 r = lp + mul(lr, V3{M->body_pos[C.jac_body][0], M->body_pos[C.jac_body][1], M->body_pos[C.jac_body][2]});
     float* J = T.arm_jac + (size_t)env * 36;
     for (int i = 0; i < 36; i++) J[i] = 0.0f;
@@ -676,7 +683,8 @@ B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, in
         }
         const float rq[4] = {st.qx, st.qy, st.qz, st.qw};
         V3 dp; M3 dr; SV dv;
-        chain_crba(M, 0, n, rq, st.q, mm, -1, &dp, &dr, st.qd, V3{0, 0, 0}, V3{0, 0, 0}, &dv, A.env_scale ? A.env_scale[(size_t)(valid ? env : 0) * 4] : 1.0f);
+        chain_crba(M, 0, n, rq, st.q, mm, -1, &dp, &dr, st.qd, V3{0, 0, 0}, V3{0, 0, 0}, &dv, A.env_scale ? A.env_scale[(size_t)(valid ? env : 0) * 4] : 1.0f,
+                   A.link_scale ? A.link_scale + (size_t)(valid ? env : 0) * (M->n_dof + 1) * B2G_LINK_SCALE_COLS : nullptr);
         for (int i = 0; i < 6; i++) {
             dpose[i] = act[i] * C.cmd_limit[i] / C.action_scale;
             effort[i] = (i < n) ? M->dof[i].effort : 0.0f;
@@ -685,7 +693,7 @@ B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, in
         osc_prepare(mm, J, dpose, eef + 7, C.kp, P);
         osc_apply(P, st.q, st.qd, C.kp_null, effort, u);
         for (int j = 0; j < 6; j++) st.act[j] = (j < n) ? u[j] : 0.0f;
-        const EnvDr dr_env = load_env_dr(A.friction, A.env_scale, valid ? env : 0, valid);
+        const EnvDr dr_env = env_dr(A, valid ? env : 0, valid);
 #pragma unroll 1
         for (int s = 0; s < A.P.substeps; s++)
             substep<1, 6, true, false, false, false>(M, A.P, 0, n, 0, st, dr_env, s == A.P.substeps - 1, sc, bf);
@@ -796,7 +804,7 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
         return;
     }
     if (!T.post_only) {
-        const EnvDr mu_shape = load_env_dr(A.friction, A.env_scale, valid ? env : 0, valid);
+        const EnvDr mu_shape = env_dr(A, valid ? env : 0, valid);
         const int total = C.decimation + C.extra_sim_steps;
 #pragma unroll 1
         for (int it = 0; it < total; it++) {
@@ -1125,7 +1133,8 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
 // refresh_mass_matrix_tensors: joint-space block of the mass matrix, (nd x nd) per environment (Isaac Gym convention used by
 // tasks/useful_hound.py:452-455).  DOFs of different chains couple only through the root, which is not part of this block,
 // so the matrix is block diagonal over the chains.  One thread per environment.
-B2G_HD inline void mass_matrix_env(const DevModel* M, const float* root, const float* dof, float* out, float mass_scale = 1.0f) {
+B2G_HD inline void mass_matrix_env(const DevModel* M, const float* root, const float* dof, float* out, float mass_scale = 1.0f,
+                                   const float* link_scale = nullptr) {
     const int nd = M->n_dof;
     for (int i = 0; i < nd * nd; i++) out[i] = 0.0f;
     for (int c = 0; c < M->n_chains; c++) {
@@ -1133,7 +1142,7 @@ B2G_HD inline void mass_matrix_env(const DevModel* M, const float* root, const f
         float q[B2G_MAX_CHAIN_LEN], qd[B2G_MAX_CHAIN_LEN], mm[36];
         for (int j = 0; j < n; j++) { q[j] = dof[2 * (d0 + j)]; qd[j] = 0.0f; }
         V3 p; M3 r; SV v;
-        chain_crba(M, d0, n, root + 3, q, mm, -1, &p, &r, qd, V3{0, 0, 0}, V3{0, 0, 0}, &v, mass_scale);
+        chain_crba(M, d0, n, root + 3, q, mm, -1, &p, &r, qd, V3{0, 0, 0}, V3{0, 0, 0}, &v, mass_scale, link_scale);
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) out[(d0 + i) * nd + d0 + j] = mm[i * 6 + j];
     }

@@ -8,17 +8,21 @@ environment is one device tensor, and a randomisation pass is a handful of maske
 =====================================  ==========================================================================
 reference parameter                    tensor it lands in
 =====================================  ==========================================================================
-``rigid_body_properties.mass``         ``B2G_T_ENV_SCALE[:, 0]`` (scales every link mass and inertia of the env:
-                                       Isaac Gym's setter recomputes inertia, ``dr_utils.py:63``)
-``dof_properties.stiffness``           ``B2G_T_ENV_SCALE[:, 1]`` (one factor per env; the reference draws one per DOF)
-``dof_properties.damping``             ``B2G_T_ENV_SCALE[:, 2]``
+``rigid_body_properties.mass``         ``B2G_T_LINK_SCALE[:, l, 0]``: one factor per rigid body, as the reference draws them (``dr_utils.py:135-238``
+                                       walks every entry of the property list); it scales the mass and the inertia of the link the body rides
+                                       on (Isaac Gym's setter recomputes inertia, ``dr_utils.py:63``); bodies merged into one link share its
+                                       first body's factor
+``dof_properties.stiffness``           ``B2G_T_LINK_SCALE[:, 1 + d, 1]``: one factor per DOF
+``dof_properties.damping``             ``B2G_T_LINK_SCALE[:, 1 + d, 2]``
+``dof_properties.lower`` / ``upper``   ``B2G_T_LINK_SCALE[:, 1 + d, 3 / 4]``: additive offsets of the joint limits
 ``rigid_shape_properties.friction``    ``B2G_T_FRICTION`` (bucketed like ``dr_utils.get_bucketed_val``)
 ``sim_params.gravity``                 ``b2g_sim_set_params`` (global, host side)
 ``observations`` / ``actions``         noise closures applied by ``VecTask.step`` (same maths as ``vec_task.py:648-718``)
 =====================================  ==========================================================================
 
-Not modelled (recorded in :attr:`skipped`): ``color``, ``scale``, ``restitution`` (the contact model has e = 0), joint-limit
-offsets ``lower`` / ``upper`` (limits are per sim), tendon properties, external parameter generators.
+``B2G_T_ENV_SCALE`` (one mass / stiffness / damping factor per environment) stays available to callers that want a single factor;
+the kernels multiply the two.  Not modelled (recorded in :attr:`skipped`): ``color``, ``scale``, ``restitution`` (the contact model has
+e = 0), tendon properties, external parameter generators.
 
 Faithful quirk: this fork never advances ``randomize_buf`` (``vec_task.py:322,632-635`` are its only uses), so after the first
 pass only the non-environment parameters (noise, gravity) are re-drawn every ``frequency`` frames; ``count_steps=True`` restores
@@ -34,7 +38,7 @@ import torch
 
 from .. import _abi
 
-SCALE_COLUMN = {"mass": 0, "stiffness": 1, "damping": 2}
+LINK_COLUMN = {"mass": 0, "stiffness": 1, "damping": 2, "lower": 3, "upper": 4}
 
 
 def schedule_scaling(params: Dict[str, Any], step: int) -> float:
@@ -98,6 +102,7 @@ class DomainRandomizer:
         self.last_rand_step = 0
         self.skipped: List[str] = []
         self.env_scale = None
+        self.link_scale = None
         self.friction = None
         self.friction0 = None
         self.gravity0 = None
@@ -109,9 +114,23 @@ class DomainRandomizer:
         if self.env_scale is None:
             gym, sim = self.task.gym, self.task.sim
             self.env_scale = gym._tensor(sim, _abi.T_ENV_SCALE)
+            self.link_scale = gym._tensor(sim, _abi.T_LINK_SCALE)           # (N, nd + 1, 6)
             self.friction = gym._tensor(sim, _abi.T_FRICTION)
             self.friction0 = self.friction.clone()
-        return self.env_scale, self.friction
+            # rigid body b -> the link it rides on; a link keeps the factor of its first body
+            art = getattr(getattr(sim, "asset", None), "art", None)
+            nl = self.link_scale.shape[1]
+            first = torch.full((nl,), -1, dtype=torch.long)
+            if art is not None:
+                for b, l in enumerate(art.body_link):
+                    if first[int(l)] < 0:
+                        first[int(l)] = b
+                self.n_bodies = len(art.body_link)
+            else:
+                first = torch.arange(nl)
+                self.n_bodies = nl
+            self.link_first_body = first.clamp_min(0).to(self.device)
+        return self.link_scale, self.friction
 
     def _skip(self, what: str):
         if what not in self.skipped:
@@ -220,13 +239,20 @@ class DomainRandomizer:
                     smp = sample(p, (n,), step, self.device, self.gen)
                     new = self.friction0 * smp if p["operation"] == "scaling" else self.friction0 + smp
                     friction.copy_(torch.where(mask, bucketed(new, p), friction))
-                elif (prop_name, attr) in (("rigid_body_properties", "mass"), ("dof_properties", "stiffness"), ("dof_properties", "damping")):
-                    col = SCALE_COLUMN[attr]
-                    smp = sample(p, (n,), step, self.device, self.gen)
+                elif prop_name == "rigid_body_properties" and attr == "mass":
                     if p["operation"] != "scaling":
                         self._skip(f"{actor}.{prop_name}.{attr} (additive)")
                         continue
-                    scale[:, col] = torch.where(mask, smp.to(scale.dtype), scale[:, col])
+                    smp = sample(p, (n, self.n_bodies), step, self.device, self.gen)[:, self.link_first_body]      # (n, links)
+                    scale[:, :, 0] = torch.where(mask[:, None], smp.to(scale.dtype), scale[:, :, 0])
+                elif prop_name == "dof_properties" and attr in ("stiffness", "damping", "lower", "upper"):
+                    col = LINK_COLUMN[attr]
+                    additive = attr in ("lower", "upper")
+                    if (p["operation"] == "scaling") == additive:       # the kernels scale gains and offset limits
+                        self._skip(f"{actor}.{prop_name}.{attr} ({p['operation']})")
+                        continue
+                    smp = sample(p, (n, scale.shape[1] - 1), step, self.device, self.gen)                              # one draw per DOF
+                    scale[:, 1:, col] = torch.where(mask[:, None], smp.to(scale.dtype), scale[:, 1:, col])
                 else:
                     self._skip(f"{actor}.{prop_name}.{attr}")
 

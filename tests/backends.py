@@ -46,6 +46,9 @@ class EmuBackend:
         self._scale = np.ascontiguousarray(scale, np.float32)
         self._fric = None if friction is None else np.ascontiguousarray(friction, np.float32)
 
+    def set_link_scale(self, scale):
+        self._lscale = np.ascontiguousarray(scale, np.float32)
+
     def add_heightfield(self, hf_t, samples):
         self._hf = (hf_t, np.ascontiguousarray(samples, np.int16))
 
@@ -57,21 +60,25 @@ class EmuBackend:
 
     def simulate(self, target, actuation):
         self.emu.set_env_scale(getattr(self, "_scale", None))
+        self.emu.set_link_scale(getattr(self, "_lscale", None))
         hf = getattr(self, "_hf", None)
         try:
             f, c = self.emu.simulate(self.model, self.params, self.props, self.root, self.dof, target, actuation, friction=getattr(self, "_fric", None),
                                      heightfield=hf[0] if hf else None, hf_samples=hf[1] if hf else None)
         finally:
             self.emu.set_env_scale(None)
+            self.emu.set_link_scale(None)
         self.dof_force[:], self.contact[:] = f, c
         return f, c
 
     def forward_dynamics(self, tau):
         self.emu.set_env_scale(getattr(self, "_scale", None))
+        self.emu.set_link_scale(getattr(self, "_lscale", None))
         try:
             return self.emu.forward_dynamics(self.model, self.params, self.props, self.root.copy(), self.dof.copy(), tau)
         finally:
             self.emu.set_env_scale(None)
+            self.emu.set_link_scale(None)
 
     def jacobian_mass_matrix(self):
         return self.emu.jacobian_mass_matrix(self.model, self.props, self.root, self.dof)
@@ -248,6 +255,10 @@ class CudaBackend:
         out = (C.c_int64 * 4)()
         self._lib.check(self.lib.b2g_sim_contact_stats(self.sim, out, 1 if reset else 0), "contact_stats")
         return [int(v) for v in out]
+
+    def set_link_scale(self, scale):
+        """(N, nd + 1, 6) per-link [mass, stiffness, damping scale, lower, upper limit offset, spare] rows (B2G_T_LINK_SCALE)."""
+        self._put(self._tensor(_abi.T_LINK_SCALE), np.asarray(scale, np.float32))
 
     def set_env_scale(self, scale, friction=None):
         """(N,4) per-env [mass, stiffness, damping, spare] scales (+ optional (N) shape friction)."""

@@ -70,7 +70,7 @@ void probe_env(const SimArgs& A, int env, float* qdd, float* a0) {
         load_state<NL>(A, env, len, d0, st);
         for (int j = 0; j < NL; j++) if (j < len) st.act[j] = A.actuation[(size_t)env * M->n_dof + d0 + j];
         ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data();
-        substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, load_env_dr(nullptr, A.env_scale, env), false, sc, bf.data());
+        substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, env_dr(A, env, true, false), false, sc, bf.data());
         for (int j = 0; j < NL; j++) if (j < len) qdd[(size_t)env * M->n_dof + d0 + j] = st.frc[j];
         if (lane == 0) {
             float* o = a0 + (size_t)env * 6;
@@ -94,12 +94,14 @@ void anymal_env(const SimArgs& A, const TaskArgs& T, int env, int mode) {
 
 // per-env domain-randomisation scales (N,4) used by the next emu_simulate / emu_forward_dynamics calls; null = ones
 static const float* g_env_scale = nullptr;
+static const float* g_link_scale = nullptr;     // (N, nd + 1, 6) per-link rows (B2G_T_LINK_SCALE); null = none
 // contact statistics of the emulated sub-steps (same counters as b2g_sim_contact_stats)
 static unsigned long long g_stats[4] = {0, 0, 0, 0};
 
 extern "C" {
 
 void emu_set_env_scale(const float* p) { g_env_scale = p; }
+void emu_set_link_scale(const float* p) { g_link_scale = p; }
 
 void emu_contact_stats(long long* out, int reset) {
     for (int i = 0; i < 4; i++) out[i] = (long long)g_stats[i];
@@ -127,7 +129,7 @@ int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
         A.P.hfc = hfc.data();
     }
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = target; A.actuation = actuation;
-    A.dof_force = dof_force; A.contact = contact; A.friction = friction; A.env_scale = g_env_scale;
+    A.dof_force = dof_force; A.contact = contact; A.friction = friction; A.env_scale = g_env_scale; A.link_scale = g_link_scale;
     const Variant v = pick(*m);
     const bool HFm = hf && hfs;
     for (int e = 0; e < n_envs; e++) {
@@ -149,7 +151,7 @@ int emu_forward_dynamics(const b2g_model* m, const b2g_sim_params* sp, const b2g
     A.M = dm;
     pack_dev_params(*sp, nullptr, nullptr, A.P);
     A.P.stats = g_stats;
-    A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = tau; A.actuation = tau; A.dof_force = nullptr; A.contact = nullptr; A.friction = nullptr; A.env_scale = g_env_scale;
+    A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = tau; A.actuation = tau; A.dof_force = nullptr; A.contact = nullptr; A.friction = nullptr; A.env_scale = g_env_scale; A.link_scale = g_link_scale;
     const Variant v = pick(*m);
     for (int e = 0; e < n_envs; e++) {
         if (v.lanes == 1) probe_env<1, 2, true>(A, e, qdd, a0);
@@ -322,7 +324,7 @@ int emu_houndarm(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     pack_dev_params(*sp, nullptr, nullptr, A.P);
     A.P.stats = g_stats;
     A.n_envs = n_envs; A.root = root; A.dof = dof; A.target = nullptr; A.actuation = nullptr; A.dof_force = dof_force;
-    A.contact = contact; A.friction = nullptr; A.env_scale = g_env_scale;
+    A.contact = contact; A.friction = nullptr; A.env_scale = g_env_scale; A.link_scale = g_link_scale;
     TaskArgs T;
     memset(&T.cfg, 0, sizeof(T.cfg));
     memset(&T.ccfg, 0, sizeof(T.ccfg));

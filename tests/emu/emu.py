@@ -156,6 +156,17 @@ def jacobian_mass_matrix(model, props, root, dof):
     return jac, mm
 
 
+_link_scale_keep = None
+
+
+def set_link_scale(scale):
+    """(N, nd + 1, 6) per-link [mass, stiffness, damping scale, lower, upper limit offset, spare] rows used by the next emulated calls; None = ones."""
+    global _link_scale_keep
+    _link_scale_keep = None if scale is None else np.ascontiguousarray(scale, dtype=np.float32)
+    lib().emu_set_link_scale.restype = None
+    lib().emu_set_link_scale(_p(_link_scale_keep))
+
+
 def contact_stats(reset=False):
     """[active contact points, dropped candidates, env sub-steps with a drop, env sub-steps] of the emulated sub-steps."""
     out = (C.c_longlong * 4)()

@@ -116,6 +116,75 @@ def scaled_model_props(m, props, mass, kp, kd):
     return m2, p2
 
 
+def link_scaled_model_props(m, props, link_scale):
+    """Same with one [mass, stiffness, damping] triple per link (row l of ``link_scale``: link 0 = root, 1 + d = child of DOF d)."""
+    m2 = _abi.Model.from_buffer_copy(m)
+    p2 = _abi.DofProps.from_buffer_copy(props)
+    for l in range(link_scale.shape[0]):
+        m2.link_mass[l] = m.link_mass[l] * float(link_scale[l, 0])
+        for k in range(6):
+            m2.link_inertia[l][k] = m.link_inertia[l][k] * float(link_scale[l, 0])
+        if l > 0:
+            p2.stiffness[l - 1] = props.stiffness[l - 1] * float(link_scale[l, 1])
+            p2.damping[l - 1] = props.damping[l - 1] * float(link_scale[l, 2])
+            p2.lower[l - 1] = props.lower[l - 1] + float(link_scale[l, 3])
+            p2.upper[l - 1] = props.upper[l - 1] + float(link_scale[l, 4])
+    return m2, p2
+
+
+def check_link_scale(make_backend, robot="anymal", n=6, steps=8, seed=23):
+    """Per-link / per-DOF domain randomisation (B2G_T_LINK_SCALE: the reference draws every body mass and every DOF stiffness / damping
+    on its own, utils/dr_utils.py:135-238): each environment against the float64 oracle on its individually scaled model."""
+    art = load_robot(robot)
+    rng = np.random.default_rng(seed)
+    nd = art.num_dofs
+    sp = flat_params()
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 85.0, 2.0)
+    ls = np.zeros((n, nd + 1, _abi.LINK_SCALE_COLS), np.float32)
+    ls[:, :, :3] = rng.uniform(0.6, 1.4, (n, nd + 1, 3))
+    ls[:, :, 3] = rng.uniform(0.0, 0.3, (n, nd + 1))       # lower limits move up, upper limits down: the stops really bite
+    ls[:, :, 4] = -rng.uniform(0.0, 0.3, (n, nd + 1))
+    ls[0, :, :3], ls[0, :, 3:] = 1.0, 0.0
+    m = _abi.pack_model(art)
+    be = make_backend(art, flat_params(ground=False), _abi.default_dof_props(art), n)
+    try:
+        fr, fd = random_flying_state(art, n, rng)
+        tau = (rng.normal(size=(n, nd)) * 20).astype(np.float32)
+        be.set_state(fr, fd)
+        be.set_link_scale(ls)
+        qdd, _ = be.forward_dynamics(tau)
+    finally:
+        be.close()
+    for e in range(n):
+        m2, _ = link_scaled_model_props(m, props, ls[e])
+        qo, _ = O.forward_dynamics(m2, flat_params(ground=False), fr[e:e + 1].astype(np.float64), fd[e:e + 1].astype(np.float64), tau[e:e + 1].astype(np.float64))
+        err = np.abs(qdd[e] - qo[0]).max() / np.abs(qo[0]).max()
+        assert err < 1e-3, f"env {e}: joint acceleration relative error {err:.2e} with per-link mass scales"
+    root, dof = standing_state(art, n, rng, 0.55 if "anymal" in robot else 0.5)
+    be = make_backend(art, sp, props, n)
+    r64, d64 = root.astype(np.float64), dof.astype(np.float64)
+    q0 = default_pose(art)
+    worst = 0.0
+    try:
+        be.set_state(root, dof)
+        be.set_link_scale(ls)
+        for _ in range(steps):
+            tgt = q0 + 0.5 * rng.uniform(-1, 1, (n, nd))
+            act = np.zeros((n, nd))
+            f_dev, _ = be.simulate(tgt, act)
+            for e in range(n):
+                m2, p2 = link_scaled_model_props(m, props, ls[e])
+                re, de = r64[e:e + 1].copy(), d64[e:e + 1].copy()
+                f_o, _ = O.simulate(m2, sp, p2, re, de, tgt[e:e + 1].astype(np.float64), act[e:e + 1].astype(np.float64))
+                r64[e], d64[e] = re[0], de[0]
+            rb, db = be.get_state()
+            worst = max(worst, float(np.abs(rb - r64).max()), float(np.abs(db[:, :, 0] - d64[:, :, 0]).max()))
+    finally:
+        be.close()
+    assert worst < 1e-2, f"state deviation {worst:.2e} over {steps} steps with per-link scales"
+    return worst
+
+
 def check_env_scale(make_backend, robot="anymal", n=8, steps=10, seed=17):
     """Tensorised domain randomisation (B2G_T_ENV_SCALE + B2G_T_FRICTION): every environment simulates its own mass / drive
     gain / friction scales; each one is checked against the float64 oracle run on the correspondingly scaled model."""

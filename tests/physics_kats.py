@@ -245,10 +245,12 @@ def check_resting_force(make_backend, robot="anymal", n=8, settle_s=1.5):
     total = fz.sum(1)
     assert np.all(np.abs(r[:, 7:13]) < 2e-2), np.abs(r[:, 7:13]).max()       # at rest
     np.testing.assert_allclose(total, mg, rtol=0.01)
-    feet = [i for i, b in enumerate(art.body_names) if ("SHANK" in b or "FOOT" in b or "foot" in b or "calf" in b)]
-    loaded = [i for i in feet if fz[0, i] > 0.02 * mg]
-    assert len(loaded) == 4, (loaded, [art.body_names[i] for i in feet], fz[0])
-    share = fz[:, loaded] / mg
+    # everything that carries load is a distal leg body (shank / calf / foot), and the four legs share the weight
+    loaded = [i for i in range(art.num_bodies) if fz[0, i] > 0.02 * mg]
+    assert loaded and all(any(k in art.body_names[i] for k in ("SHANK", "FOOT", "foot", "calf")) for i in loaded), [art.body_names[i] for i in loaded]
+    legs = sorted({art.body_names[i][:2] for i in loaded})
+    assert len(legs) == 4, legs
+    share = np.stack([fz[:, [i for i in loaded if art.body_names[i][:2] == leg]].sum(1) for leg in legs], axis=1) / mg
     assert np.all(share > 0.12) and np.all(share < 0.40), share[0]
     # no horizontal net force at rest
     assert np.all(np.abs(c[:, :, :2].sum(1)) < 0.01 * mg)

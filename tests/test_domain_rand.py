@@ -46,7 +46,9 @@ def test_sampler_statistics_match_reference(name, step):
 class _FakeGym:
     def __init__(self, n):
         self.frame = 0
-        self.t = {DR._abi.T_ENV_SCALE: torch.ones(n, 4), DR._abi.T_FRICTION: torch.ones(n)}
+        ls = torch.zeros(n, 13, DR._abi.LINK_SCALE_COLS)
+        ls[:, :, :3] = 1.0
+        self.t = {DR._abi.T_ENV_SCALE: torch.ones(n, 4), DR._abi.T_FRICTION: torch.ones(n), DR._abi.T_LINK_SCALE: ls}
         self.gravity_sets = []
 
         class V:
@@ -101,11 +103,16 @@ def test_randomizer_masks_frequency_and_setup_only():
     dr = DR.DomainRandomizer(task, count_steps=True)
     p = _params()
     dr.apply(p)                                   # first pass: every env, every parameter, noise closures, gravity
-    sc, fr = task.gym.t[DR._abi.T_ENV_SCALE], task.gym.t[DR._abi.T_FRICTION]
-    assert ((sc[:, :3] >= 0.5) & (sc[:, :3] <= 1.5)).all() and sc[:, :3].std(0).min() > 0.05 and (sc[:, 3] == 1).all()
+    sc, fr = task.gym.t[DR._abi.T_LINK_SCALE], task.gym.t[DR._abi.T_FRICTION]
+    assert (task.gym.t[DR._abi.T_ENV_SCALE] == 1).all()          # the per-env factors stay at the caller's disposal
+    assert ((sc[:, :, 0] >= 0.5) & (sc[:, :, 0] <= 1.5)).all() and ((sc[:, 1:, 1:3] >= 0.5) & (sc[:, 1:, 1:3] <= 1.5)).all()
+    # one draw per body / per DOF (utils/dr_utils.py:135-238), not one per environment
+    assert sc[:, :, 0].std(1).min() > 0.05 and sc[:, 1:, 1].std(1).min() > 0.05 and sc[:, 1:, 2].std(1).min() > 0.05
+    assert (sc[:, 0, 1:3] == 1).all() and (sc[:, :, 4:] == 0).all()          # the root has no DOF; `upper` is not in this block
+    assert sc[:, 1:, 3].abs().max() < 0.06 and sc[:, 1:, 3].std() > 1e-3          # additive gaussian limit offsets
     assert ((fr >= 0.7) & (fr < 1.3)).all() and len(torch.unique(fr)) <= 50
     assert len(task.gym.gravity_sets) == 1 and set(task.dr_randomizations) == {"observations", "actions"}
-    assert sorted(dr.skipped) == ["anymal.color", "anymal.dof_properties.lower", "anymal.rigid_shape_properties.restitution"]
+    assert sorted(dr.skipped) == ["anymal.color", "anymal.rigid_shape_properties.restitution"]
     x = torch.zeros(64, 12)
     y = task.dr_randomizations["actions"]["noise_lambda"](x)
     assert 0.01 < y.std() < 0.03 and y.shape == x.shape
@@ -121,8 +128,8 @@ def test_randomizer_masks_frequency_and_setup_only():
     task.randomize_buf += 7
     dr.apply(p)
     assert len(task.gym.gravity_sets) == 2
-    assert torch.equal(sc[:, 0], sc0[:, 0]), "setup_only mass must not change after the first pass"
-    assert not torch.equal(sc[:8, 1:3], sc0[:8, 1:3]) and torch.equal(sc[8:], sc0[8:])
+    assert torch.equal(sc[:, :, 0], sc0[:, :, 0]), "setup_only mass must not change after the first pass"
+    assert not torch.equal(sc[:8, 1:, 1:3], sc0[:8, 1:, 1:3]) and torch.equal(sc[8:], sc0[8:])
     assert not torch.equal(fr[:8], fr0[:8]) and torch.equal(fr[8:], fr0[8:])
     assert (task.randomize_buf[:8] == 0).all() and (task.randomize_buf[8:] == 12).all()
     assert dr.num_applied() == 64 + 8
@@ -133,11 +140,11 @@ def test_reference_quirk_no_step_counting_means_no_rerandomisation():
     dr = DR.DomainRandomizer(task, count_steps=False)
     p = _params()
     dr.apply(p)
-    sc0 = task.gym.t[DR._abi.T_ENV_SCALE].clone()
+    sc0 = task.gym.t[DR._abi.T_LINK_SCALE].clone()
     task.gym.frame = 100
     task.reset_buf[:] = 1
     dr.apply(p)                                   # randomize_buf never advanced (vec_task.py:322,632-635): no env qualifies
-    assert torch.equal(task.gym.t[DR._abi.T_ENV_SCALE], sc0) and len(task.gym.gravity_sets) == 2
+    assert torch.equal(task.gym.t[DR._abi.T_LINK_SCALE], sc0) and len(task.gym.gravity_sets) == 2
 
 
 @pytest.mark.gpu
@@ -165,12 +172,12 @@ def test_anymal_with_domain_randomisation_on_gpu(fused):
         o, r, d, _ = env.step(a)
         op, rp_, dp, _ = plain.step(a)
         assert torch.isfinite(o["obs"]).all() and torch.isfinite(r).all()
-    sc = env._dr.env_scale
-    assert ((sc[:, :3] > 0.45) & (sc[:, :3] < 1.55)).all()
+    sc = env._dr.link_scale
+    assert ((sc[:, :, :3] > 0.45) & (sc[:, :, :3] < 1.55)).all()
     # the construction-time pass happens at frame 0, where the linear schedule still gives scale 1; the environments that were
-    # reset after `frequency` steps carry fresh draws
-    redrawn = (sc[:, 1:3] != 1.0).any(dim=1)
-    assert int(redrawn.sum()) >= 8 and sc[redrawn][:, 1:3].std(0).min() > 0.1, (int(redrawn.sum()), sc[redrawn][:, 1:3].std(0))
+    # reset after `frequency` steps carry fresh draws -- one per DOF
+    redrawn = (sc[:, 1:, 1:3] != 1.0).flatten(1).any(dim=1)
+    assert int(redrawn.sum()) >= 8 and sc[redrawn][:, 1:, 1].std(1).min() > 0.05, int(redrawn.sum())
     assert env._dr.num_applied() >= n + int(redrawn.sum()), "environments reset after `frequency` steps are re-randomised (possibly more than once)"
     assert "observations" in env.dr_randomizations and "actions" in env.dr_randomizations
     g = env.gym.get_sim_params(env.sim).gravity

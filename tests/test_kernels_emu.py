@@ -21,6 +21,11 @@ def test_env_scale_domain_randomisation(robot):
     kc.check_env_scale(make, robot, n=4)
 
 
+@pytest.mark.parametrize("robot", ["anymal", "useful_hound"])
+def test_link_scale_domain_randomisation(robot):
+    kc.check_link_scale(make, robot, n=3, steps=5)
+
+
 @pytest.mark.parametrize("robot,drive", [("anymal", "pos"), ("hound", "pos"), ("anymal_minimal", "effort")])
 def test_simulate_horizon(robot, drive):
     kc.check_simulate_horizon(make, robot, n=6, steps=10, drive=drive)

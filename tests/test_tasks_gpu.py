@@ -487,6 +487,9 @@ def test_full_size_terrain_post_physics_matches_reference_math(task, ov):
     if arm:
         cfg["arm"] = dict(dof_noise=float(env.houndarm_dof_noise), lower=npy(env.houndarm_dof_lower_limits), upper=npy(env.houndarm_dof_upper_limits))
     checked = resets = moved = 0
+    if env.custom_origins:      # spread the robots over all difficulty rows so that the curriculum has somewhere to move them
+        env.terrain_levels.copy_(torch.randint(0, env.terrain.env_rows, (n,), device="cuda:0", generator=g))
+        env.env_origins.copy_(env.terrain_origins[env.terrain_levels, env.terrain_types])
     for k in range(60):
         a = 2 * torch.rand(n, na, device="cuda:0", generator=g) - 1
         env.step(a)
