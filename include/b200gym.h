@@ -34,7 +34,8 @@ extern "C" {
 #define B2G_MAX_CHAIN_LEN 6
 #define B2G_MAX_CPTS 128
 #define B2G_LINK_SCALE_COLS 6
-#define B2G_MAX_CONTACTS_PER_CHAIN 8   /* contact slots per solver lane (chain); candidates beyond them are dropped AND counted (b2g_sim_contact_stats) */
+#define B2G_MAX_CONTACTS_PER_CHAIN 8   /* upper bound of b2g_sim_params::max_contacts_per_chain */
+#define B2G_DEFAULT_CONTACTS_PER_CHAIN 4
 
 enum b2g_status {
     B2G_OK = 0,
@@ -106,6 +107,10 @@ typedef struct b2g_sim_params {
     int32_t has_ground;               /* add_ground was called */
     float joint_limit_stiffness;      /* joint limits are one-sided implicit spring-dampers [N m/rad, N m s/rad]  */
     float joint_limit_damping;
+    int32_t max_contacts_per_chain;   /* contact slots per solver lane (chain), 1..B2G_MAX_CONTACTS_PER_CHAIN; 0 = 4.  PhysX keeps every
+                                         contact a body has; here candidates beyond the slots are dropped and counted
+                                         (b2g_sim_contact_stats) -- pick the smallest value whose drop count stays negligible: the
+                                         slots live in shared memory ([slot][field][thread]) and take L1 capacity from the kernels */
 } b2g_sim_params;
 
 /* per-DOF drive properties, identical for every env (reference: tasks/anymal.py:199-203,214) */

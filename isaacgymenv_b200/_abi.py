@@ -54,7 +54,7 @@ class SimParams(C.Structure):
         ("contact_offset", f32), ("rest_offset", f32), ("bounce_threshold_velocity", f32),
         ("max_depenetration_velocity", f32),
         ("plane_static_friction", f32), ("plane_dynamic_friction", f32), ("plane_restitution", f32),
-        ("has_ground", i32), ("joint_limit_stiffness", f32), ("joint_limit_damping", f32),
+        ("has_ground", i32), ("joint_limit_stiffness", f32), ("joint_limit_damping", f32), ("max_contacts_per_chain", i32),
     ]
 
 

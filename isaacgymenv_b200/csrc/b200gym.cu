@@ -75,7 +75,7 @@ Variant pick_variant(const b2g_model& m) {
 // kernels
 // ------------------------------------------------------------------------------------------------
 template <int LANES>
-__device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int& env, int& lane, bool& valid, ScratchStrided& sc, float*& bf, int nd = 0) {
+__device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int& env, int& lane, bool& valid, ScratchStrided& sc, float*& bf, int nd, int slots) {
     const int tid = threadIdx.x;
     constexpr int EPW = 32 / LANES / kSparse, EPB = EnvsPerBlock<LANES>::value;
     const int wl = tid & 31;
@@ -93,9 +93,9 @@ __device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int&
     sc.base = smem + tid;
     sc.stride = kBlock;
     const int grp = LANES == kSplit8 ? eib : tid / LANES;
-    bf = smem + kBlock * MAXC * CF_COUNT + grp * nb * 3;     // one accumulator per lane group, idle groups included
+    bf = smem + kBlock * slots * CF_COUNT + grp * nb * 3;     // one accumulator per lane group, idle groups included
     // link store of the rolled long-chain variants (b2g_dynamics.cuh::links_in_shared): one LinkData per DOF per lane group
-    sc.links = smem + ((kBlock * MAXC * CF_COUNT + (kBlock / LANES) * nb * 3 + 3) & ~3) + link_store_floats(grp, nd);     // 16-byte aligned
+    sc.links = smem + ((kBlock * slots * CF_COUNT + (kBlock / LANES) * nb * 3 + 3) & ~3) + link_store_floats(grp, nd);     // 16-byte aligned
 }
 
 // ---- host mirror (b2g_task_step_host): the step's outputs (obs_clamped | rew | reset | timeout, the b2g_task_host_layout arena)
@@ -162,7 +162,7 @@ template <int LANES, int NL, bool FIXED, bool HF>
 __global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
     simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, valid, sc, bf);
 }
 
@@ -173,7 +173,7 @@ template <int LANES, int NL, bool HF, int MINB = 1>
 __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArgs T, HostMirror H) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
     anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
     if (H.dst) {
         constexpr int EPB = EnvsPerBlock<LANES>::value;
@@ -185,14 +185,14 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArg
 __global__ void __launch_bounds__(kBlock) k_houndarm_step(SimArgs A, TaskArgs T) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
+    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
     houndarm_step_thread(A, T, env, valid, sc, bf);
 }
 
 __global__ void __launch_bounds__(kBlock) k_cartpole_step(SimArgs A, TaskArgs T) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
+    thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
     cartpole_step_thread(A, T, env, valid, sc, bf);
 }
 
@@ -217,7 +217,7 @@ template <int LANES, int NL, bool HF>
 __global__ void __launch_bounds__(kBlock) k_terrain_phys(SimArgs A, TerrainArgs T) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
     terrain_phys_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
     // curriculum scalar for ALL resetting envs (reference quirk: torch.norm without dim, anymal_terrain.py:432): the last
     // block to arrive sums the N values in a fixed order (kBlock strided partial sums, pairwise tree) -> deterministic
@@ -307,7 +307,7 @@ template <int LANES, int NL>
 __global__ void __launch_bounds__(kBlock) k_anymal_reset_all(SimArgs A, TaskArgs T) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
     anymal_reset_all_thread<LANES, NL>(A, T, env, lane, valid);
 }
 
@@ -315,7 +315,7 @@ template <int LANES, int NL, bool FIXED>
 __global__ void __launch_bounds__(kBlock) k_probe(SimArgs A, float* qdd, float* a0) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
     const DevModel* M = A.M;
     const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
     const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
@@ -444,7 +444,7 @@ namespace {
 size_t smem_bytes(const b2g_sim* s) {
     const int epb = kBlock / s->v.lanes;
     const size_t links = kLinksShared && s->v.nl > 3 ? 4 + link_store_floats(epb, s->model.n_dof) : 0;     // links_in_shared variants
-    return sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)epb * s->model.n_bodies * 3 + links);
+    return sizeof(float) * ((size_t)kBlock * contact_slots(s->params) * CF_COUNT + (size_t)epb * s->model.n_bodies * 3 + links);
 }
 
 int grid_size(const b2g_sim* s) {
@@ -630,7 +630,7 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
     }
     if (s->task_kind == 4) {     // one thread per environment whatever the generic kernels' lane count is
         const int g1 = (s->n_envs + kBlock / kSparse - 1) / (kBlock / kSparse);
-        const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + (kLinksShared ? 4 + link_store_floats(kBlock, s->model.n_dof) : 0));
+        const size_t sm1 = sizeof(float) * ((size_t)kBlock * contact_slots(s->params) * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + (kLinksShared ? 4 + link_store_floats(kBlock, s->model.n_dof) : 0));
         k_houndarm_step<<<g1, kBlock, sm1, st>>>(A, T);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -645,7 +645,7 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
     const HostMirror H = hm ? *hm : HostMirror{};     // flat tasks: the mirror is the kernel's own tail
     if (s->v.lanes == 4) {
         if (s->has_hf) k_anymal_step<4, 3, true><<<grid, kBlock, sm, st>>>(A, T, H);
-        else if (grid > 4 * s->n_sm) k_anymal_step<4, 3, false, 6><<<grid, kBlock, sm, st>>>(A, T, H);     // more than one wave: occupancy build
+        else if (grid > 4 * s->n_sm && sm * 6 <= 200 * 1024) k_anymal_step<4, 3, false, 6><<<grid, kBlock, sm, st>>>(A, T, H);     // more than one wave and six blocks' scratch fit an SM: occupancy build
         else k_anymal_step<4, 3, false><<<grid, kBlock, sm, st>>>(A, T, H);
     }
     else { if (s->has_hf) k_anymal_step<8, 6, true><<<grid, kBlock, sm, st>>>(A, T, H); else k_anymal_step<8, 6, false><<<grid, kBlock, sm, st>>>(A, T, H); }
@@ -725,9 +725,13 @@ int b2g_sim_destroy(b2g_sim* s) {
 int b2g_sim_set_params(b2g_sim* s, const b2g_sim_params* p) {
     if (!s || !p) return fail(B2G_ERR_ARG, "null argument");
     const int ground = s->params.has_ground;
+    const int slots = s->params.max_contacts_per_chain;
+    if (s->prepared && contact_slots(*p) != contact_slots(s->params))
+        return fail(B2G_ERR_STATE, "max_contacts_per_chain cannot change after b2g_sim_prepare (shared memory is sized there)");
     s->params = *p;
     if (s->params.substeps <= 0) s->params.substeps = 1;
     s->params.has_ground = ground || p->has_ground;
+    if (s->prepared) s->params.max_contacts_per_chain = slots;
     return B2G_OK;
 }
 
@@ -838,6 +842,7 @@ int b2g_sim_prepare(b2g_sim* s) {
         cudaFuncSetAttribute(k_terrain_phys<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_terrain_phys<8, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_terrain_phys<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_cartpole_step, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
@@ -1043,7 +1048,7 @@ int b2g_task_houndarm_create(b2g_sim* s, const b2g_houndarm_cfg* cfg) {
     s->seed = cfg->seed;
     s->task_kind = 4;
     if (s->has_task) return B2G_OK;
-    const size_t sm1 = sizeof(float) * ((size_t)kBlock * MAXC * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + (kLinksShared ? 4 + link_store_floats(kBlock, s->model.n_dof) : 0));
+    const size_t sm1 = sizeof(float) * ((size_t)kBlock * contact_slots(s->params) * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + (kLinksShared ? 4 + link_store_floats(kBlock, s->model.n_dof) : 0));
     cudaFuncSetAttribute(k_houndarm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
     return alloc_task_buffers(s, 10, s->model.n_dof, 9);
 }

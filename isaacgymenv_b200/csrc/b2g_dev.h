@@ -53,6 +53,7 @@ struct DevParams {
     float mu_ground;
     int has_ground;
     float limit_kp, limit_kd;   // joint-limit spring / damper
+    int max_contacts;           // contact slots per lane in use (<= B2G_MAX_CONTACTS_PER_CHAIN); sizes the shared-memory scratch
     // heightfield (null -> plane z = 0)
     const int16_t* hf;
     int hf_rows, hf_cols;

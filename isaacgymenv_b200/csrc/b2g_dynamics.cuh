@@ -493,8 +493,8 @@ B2G_LINK_UNROLL
         V3 n = V3{0, 0, 1};
         if (HF) ground_sample(P, st.rp.x + rc.x, st.rp.y + rc.y, gh, n);
         const float gap = (st.rp.z + rc.z - gh) * n.z - cr;
-        if (gap < P.contact_offset && ncon >= MAXC) ndrop++;      // no free slot: the candidate is ignored this sub-step (counted, never silent)
-        if (gap < P.contact_offset && ncon < MAXC) {
+        if (gap < P.contact_offset && ncon >= P.max_contacts) ndrop++;      // no free slot: the candidate is ignored this sub-step (counted, never silent)
+        if (gap < P.contact_offset && ncon < P.max_contacts) {
             const V3 r = rc - n * cr;
             V3 t1 = V3{1.0f - n.x * n.x, -n.x * n.y, -n.x * n.z};
             t1 = t1 * (1.0f / sqrtf(dot(t1, t1)));

@@ -160,6 +160,11 @@ inline void build_hf_coarse(const int16_t* smp, int rows, int cols, float hs, fl
     }
 }
 
+inline int contact_slots(const b2g_sim_params& s) {
+    const int n = s.max_contacts_per_chain > 0 ? s.max_contacts_per_chain : B2G_DEFAULT_CONTACTS_PER_CHAIN;
+    return n > B2G_MAX_CONTACTS_PER_CHAIN ? B2G_MAX_CONTACTS_PER_CHAIN : n;
+}
+
 inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, const int16_t* hf_dev, DevParams& d, const float* hfc_dev = nullptr,
                             int hfc_rows = 0, int hfc_cols = 0) {
     memset(&d, 0, sizeof(d));
@@ -172,6 +177,7 @@ inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, 
     d.mu_ground = (hf && hf_dev) ? hf->friction : s.plane_dynamic_friction;
     d.has_ground = s.has_ground;
     d.limit_kp = s.joint_limit_stiffness; d.limit_kd = s.joint_limit_damping;
+    d.max_contacts = contact_slots(s);
     if (hf && hf_dev) {
         d.hf = hf_dev; d.hf_rows = hf->rows; d.hf_cols = hf->cols; d.hf_hs = hf->horizontal_scale; d.hf_vs = hf->vertical_scale;
         d.hf_ox = hf->origin_x; d.hf_oy = hf->origin_y;

@@ -134,6 +134,8 @@ class _PhysXParams:
         # not Isaac Gym parameters: joint limits are one-sided implicit spring-dampers in this engine
         self.joint_limit_stiffness = 2000.0
         self.joint_limit_damping = 20.0
+        # not an Isaac Gym parameter either: contact slots per solver lane (0 = the library's default of 4), b2g_sim_params
+        self.max_contacts_per_chain = 0
 
 
 class _FlexParams:
@@ -245,7 +247,8 @@ class Sim:
                            max_depenetration_velocity=px.max_depenetration_velocity, plane_static_friction=1.0,
                            plane_dynamic_friction=1.0, plane_restitution=0.0, has_ground=0,
                            joint_limit_stiffness=float(getattr(px, "joint_limit_stiffness", 2000.0)),
-                           joint_limit_damping=float(getattr(px, "joint_limit_damping", 20.0)))
+                           joint_limit_damping=float(getattr(px, "joint_limit_damping", 20.0)),
+                           max_contacts_per_chain=int(getattr(px, "max_contacts_per_chain", 0) or 0))
         c.gravity[0], c.gravity[1], c.gravity[2] = g.x, g.y, g.z
         asset = getattr(self, "asset", None)
         if asset is not None and getattr(asset.options, "disable_gravity", False):
@@ -407,7 +410,7 @@ class Gym:
         if os.path.isfile(path):
             art = _urdf.compile_urdf(path, options)
         else:
-            comp = _store.find_compiled(filename, options)
+            comp = _store.find_compiled(filename, options, rootpath)
             if comp is None:
                 raise FileNotFoundError(f"asset {path} not found and no compiled model for it under {_store.COMPILED_DIR}")
             art = _store.load_articulation(comp)

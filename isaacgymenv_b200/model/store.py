@@ -58,6 +58,14 @@ def load_articulation(path: str) -> Articulation:
     return Articulation(**kw)
 
 
-def find_compiled(asset_file: str, opts: AssetOptions):
-    p = os.path.join(COMPILED_DIR, options_key(asset_file, opts) + ".json")
-    return p if os.path.isfile(p) else None
+def find_compiled(asset_file: str, opts: AssetOptions, rootpath: str = ""):
+    """Compiled model of ``asset_file`` (relative to the asset root, e.g. ``urdf/anymal_c/urdf/anymal.urdf``).  Callers split the
+    path between root and file name differently (the reference's Cartpole passes root ``.../assets/urdf`` and file ``cartpole.urdf``,
+    tasks/cartpole.py:82-88), so trailing components of ``rootpath`` are tried in front of the file name as well."""
+    parts = [c for c in os.path.normpath(rootpath).replace("\\", "/").split("/") if c not in ("", ".", "..")] if rootpath else []
+    for k in range(0, min(len(parts), 4) + 1):
+        rel = "/".join(parts[len(parts) - k:] + [asset_file]) if k else asset_file
+        p = os.path.join(COMPILED_DIR, options_key(rel, opts) + ".json")
+        if os.path.isfile(p):
+            return p
+    return None

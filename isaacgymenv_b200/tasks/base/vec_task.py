@@ -106,6 +106,8 @@ class Env(abc.ABC):
 
 
 class VecTask(Env):
+    CONTACT_SLOTS = 0      # 0 = library default (4); robots whose links rest on more candidates at once ask for more (Hound: 6)
+
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 24}
 
     def __init__(self, config, rl_device, sim_device, graphics_device_id, headless, virtual_screen_capture: bool = False,
@@ -117,6 +119,9 @@ class VecTask(Env):
         self.virtual_display = None
         self.force_render = force_render
         self.sim_params = self._parse_sim_params(self.cfg["physics_engine"], self.cfg["sim"])
+        # contact slots per solver lane (b2g_sim_params.max_contacts_per_chain): a yaml value under sim.physx wins, else the task's own
+        if self.CONTACT_SLOTS and not getattr(self.sim_params.physx, "max_contacts_per_chain", 0):
+            self.sim_params.physx.max_contacts_per_chain = int(self.CONTACT_SLOTS)
         if self.cfg["physics_engine"] == "physx":
             self.physics_engine = gymapi.SIM_PHYSX
         elif self.cfg["physics_engine"] == "flex":

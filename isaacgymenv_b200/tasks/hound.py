@@ -7,6 +7,9 @@ from .anymal import Anymal
 
 
 class Hound(Anymal):
+    # the calf box (4 corners) and the foot sphere rest on the ground together: 4 slots dropped 16 % of the candidates (counted by
+    # b2g_sim_contact_stats), 6 drop < 0.1 %
+    CONTACT_SLOTS = 6
     ASSET_FILE = "urdf/Hound_new/Hound.urdf"
     ACTOR_NAME = "hound"
     BASE_NAME = "trunk"

@@ -413,17 +413,19 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
     }
     for (int d = 0; d < nd; d++) qd[d] += h * qdd[d];
 
-    /* ---- collect contacts: per chain, candidates in model order, first B2G_MAX_CONTACTS_PER_CHAIN ---- */
+    /* ---- collect contacts: per chain, candidates in model order, the first max_contacts_per_chain of them ---- */
     FN(orc_contact) con[B2G_MAX_CHAINS][B2G_MAX_CONTACTS_PER_CHAIN];
     int ncon[B2G_MAX_CHAINS];
     R mu_g = hf && hfs ? (R)hf->friction : (R)sp->plane_dynamic_friction;
     R mu = (R)0.5 * (mu_g + mu_shape);   /* PhysX default combine mode: average */
     int ground = (hf && hfs) || sp->has_ground;
+    int maxc = sp->max_contacts_per_chain > 0 ? sp->max_contacts_per_chain : B2G_DEFAULT_CONTACTS_PER_CHAIN;
+    if (maxc > B2G_MAX_CONTACTS_PER_CHAIN) maxc = B2G_MAX_CONTACTS_PER_CHAIN;
     for (int c = 0; c < m->n_chains; c++) ncon[c] = 0;
     for (int i = 0; i < m->n_cpts && ground; i++) {
         int c = m->cp_chain[i], l = m->cp_link[i];
         if (m->fixed_base && l == 0) continue;
-        if (ncon[c] >= B2G_MAX_CONTACTS_PER_CHAIN) continue;
+        if (ncon[c] >= maxc) continue;
         R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
         FN(matvec3)(k->rot[l], lp, rc);
         for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];

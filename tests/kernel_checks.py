@@ -39,8 +39,8 @@ def default_pose(art):
     return np.array(out)
 
 
-def flat_params(dt=0.02, substeps=2, npos=4, nvel=1, ground=True):
-    sp = _abi.SimParams(dt=dt, substeps=substeps, num_position_iterations=npos, num_velocity_iterations=nvel, contact_offset=0.02,
+def flat_params(dt=0.02, substeps=2, npos=4, nvel=1, ground=True, slots=0):
+    sp = _abi.SimParams(max_contacts_per_chain=slots, dt=dt, substeps=substeps, num_position_iterations=npos, num_velocity_iterations=nvel, contact_offset=0.02,
                         rest_offset=0.0, bounce_threshold_velocity=0.2, max_depenetration_velocity=100.0, plane_static_friction=1.0,
                         plane_dynamic_friction=1.0, plane_restitution=0.0, has_ground=1 if ground else 0, joint_limit_stiffness=2000.0,
                         joint_limit_damping=20.0)
