@@ -298,7 +298,7 @@ def measure_task(task, num_envs, steps, warmup, preroll, dev, rank, world, dist,
     return res
 
 
-def measure_ppo(dev, rank, world, dist, num_envs=8192, epochs=10, warm=2):
+def measure_ppo(dev, rank, world, dist, num_envs=8192, epochs=10, warm=2, fused_update=True):
     """BASELINE.json config 5: Anymal, 8192 envs per GPU, PPO per cfg/train/AnymalPPO.yaml (horizon 24, minibatch 32768, 5 mini-epochs
     -> 6 x 5 = 30 gradient all-reduces per iteration over NCCL), one process per GPU, seeds 42 + rank (reference README.md:165-172,
     utils/utils.py:89-94).  Rollout (tcgen05 policy kernel + fused env step) and minibatch update (with its all-reduce) replay from
@@ -312,7 +312,7 @@ def measure_ppo(dev, rank, world, dist, num_envs=8192, epochs=10, warm=2):
     env = isaacgymenv_b200.make(seed=42 + rank, task="Anymal", num_envs=num_envs, sim_device=dev, rl_device=dev, headless=True)
     cfg = ppo_config_from_train_cfg(load_train_config("AnymalPPO"))
     cfg.tf32 = True
-    ppo = PPO(env, cfg, multi_gpu=world > 1, seed=42 + rank, fused_rollout=True, cuda_graphs=True)
+    ppo = PPO(env, cfg, multi_gpu=world > 1, seed=42 + rank, fused_rollout=True, cuda_graphs=True, fused_update=fused_update)
     ppo.train(max_epochs=warm, log_every=10 ** 9)          # graph capture + warm-up epochs
 
     def barrier():
@@ -354,7 +354,7 @@ def measure_ppo(dev, rank, world, dist, num_envs=8192, epochs=10, warm=2):
            "env_steps_per_sec_incl_learner": world * N * T * epochs / (ms * 1e-3), "unit": UNIT,
            "allreduces_per_iteration": n_ar if world > 1 else 0, "allreduce_bytes": nparam * 4,
            "nccl_ms_per_iteration_standalone": nccl_ms, "nccl_share_of_iteration": (nccl_ms / per_iter) if per_iter > 0 else None,
-           "update_in_cuda_graph": ppo._g_update is not None, "rollout_in_cuda_graph": ppo._g_rollout is not None,
+           "fused_update_kernels": bool(fused_update), "update_in_cuda_graph": ppo._g_update is not None, "rollout_in_cuda_graph": ppo._g_rollout is not None,
            "update_capture_error": ppo.update_capture_error, "mean_episode_reward_last": (log.mean_episode_reward[-1] if log.mean_episode_reward else None)}
     del ppo, env
     torch.cuda.empty_cache()

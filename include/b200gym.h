@@ -418,6 +418,61 @@ int b2g_policy_set_obs_norm(b2g_policy* policy, const float* mean_dev, const flo
 int b2g_policy_forward(b2g_policy* policy, const float* obs_dev, int n_rows, float* mu_dev, float* value_dev, void* stream);
 int64_t b2g_policy_launch_count(const b2g_policy* policy);
 
+/* ---- learner-side kernels of the PPO minibatch update.  Reference: the reference trains through rl_games'
+ * a2c_continuous (train.py:200-218, cfg/train/AnymalPPO.yaml); the fork states the same update in-tree for its AMP agent
+ * (learning/common_agent.py:312-400 calc_gradients: actor / critic / bound losses, clip_grad_norm_, optimizer step).  All pointers
+ * are device pointers, float32 unless stated. ---- */
+#define B2G_PPO_MAX_ACTIONS 24
+#define B2G_ADAM_MAX_PARTIALS 512
+
+/* Loss head of one minibatch: from the network outputs of the minibatch rows and the rollout buffers (gathered through `index`),
+ *   loss = a_loss + 0.5 critic_coef c_loss - entropy_coef entropy + bounds_loss_coef b_loss
+ * with a_loss = mean max(-A r, -A clip(r, 1 +- e_clip)), r = exp(old_neglogp - neglogp), c_loss = mean max((v - R)^2, (v_clip - R)^2),
+ * b_loss = mean sum_k relu(mu_k - mu_bound)^2 + relu(-mu_bound - mu_k)^2, entropy of the diagonal Gaussian; and the gradients of
+ * `loss` with respect to mu, value and log_std in closed form (what autograd would give, torch.max's tie rule included). */
+typedef struct b2g_ppo_head_args {
+    /* network outputs for the minibatch rows */
+    const float* mu;             /* (n_rows, n_actions) */
+    const float* value;          /* (n_rows) normalised value prediction */
+    const float* log_std;        /* (n_actions) */
+    /* rollout buffers, full size; row index[i] belongs to minibatch row i (null: identity) */
+    const int64_t* index;        /* (n_rows) */
+    const float* actions;        /* (*, n_actions) */
+    const float* old_mu;         /* (*, n_actions) */
+    const float* old_neglogp;    /* (*) */
+    const float* advantages;     /* (*) normalised */
+    const float* old_values;     /* (*) normalised */
+    const float* returns;        /* (*) normalised */
+    int32_t n_rows, n_actions;
+    float e_clip, critic_coef, entropy_coef, bounds_loss_coef, mu_bound;
+    /* outputs */
+    float* grad_mu;              /* (n_rows, n_actions) d loss / d mu */
+    float* grad_value;           /* (n_rows) */
+    float* grad_log_std;         /* (n_actions) */
+    float* out;                  /* (6): loss, a_loss, c_loss, b_loss, kl(old || new), entropy */
+    float* partial;              /* workspace, b2g_ppo_head_workspace_floats(n_rows) floats */
+} b2g_ppo_head_args;
+int b2g_ppo_head(const b2g_ppo_head_args* args, void* stream);
+int b2g_ppo_head_workspace_floats(int n_rows);
+
+/* Global-norm clipping + Adam on one flat parameter vector (torch.optim.Adam semantics: no weight decay, no amsgrad).  The effective
+ * gradient is grad * grad_scale (1 / world size after an all-reduce SUM); *step is advanced by one. */
+typedef struct b2g_adam_args {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int32_t n;
+    const float* lr;             /* device scalar (the adaptive-KL schedule rewrites it between graph replays) */
+    int64_t* step;               /* device scalar, number of updates so far */
+    float beta1, beta2, eps;
+    float max_grad_norm;         /* <= 0: no clipping */
+    float grad_scale;
+    float* partial;              /* workspace, B2G_ADAM_MAX_PARTIALS floats */
+    float* out_norm;             /* (2): gradient norm before clipping, clip coefficient */
+} b2g_adam_args;
+int b2g_adam_clip_step(const b2g_adam_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,175 @@
+"""Learner-side kernels of ``libb200gym`` behind torch (``b2g_ppo_head`` / ``b2g_adam_clip_step`` in ``include/b200gym.h``):
+
+* :class:`FlatParameters` -- the network's parameters (and their gradients) as views of ONE flat buffer each, so that the optimiser
+  and the multi-GPU all-reduce work on a single vector (no concatenation, no scatter back);
+* :func:`ppo_head_loss` -- the PPO loss head as one kernel (+ a one-block finalize) with closed-form gradients, exposed to autograd:
+  ``loss.backward()`` continues through the torch network from ``d loss / d mu`` and ``d loss / d value``;
+* :class:`FusedClipAdam` -- global-norm clipping + Adam in two launches, learning rate and step count in device memory;
+* :func:`ppo_head_reference` -- the same loss in plain torch ops (what ``learning/ppo.py`` runs without the library): the parity
+  reference of the kernel, and of the closed-form gradients through autograd.
+
+Loss structure: rl_games' ``a2c_continuous`` (the fork's in-tree statement: ``learning/common_agent.py:312-400``)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+MAX_ACTIONS = 24
+ADAM_MAX_PARTIALS = 512
+_fp = C.POINTER(C.c_float)
+
+
+class PpoHeadArgs(C.Structure):
+    _fields_ = [("mu", C.c_void_p), ("value", C.c_void_p), ("log_std", C.c_void_p), ("index", C.c_void_p), ("actions", C.c_void_p),
+                ("old_mu", C.c_void_p), ("old_neglogp", C.c_void_p), ("advantages", C.c_void_p), ("old_values", C.c_void_p), ("returns", C.c_void_p),
+                ("n_rows", C.c_int32), ("n_actions", C.c_int32), ("e_clip", C.c_float), ("critic_coef", C.c_float), ("entropy_coef", C.c_float),
+                ("bounds_loss_coef", C.c_float), ("mu_bound", C.c_float), ("grad_mu", C.c_void_p), ("grad_value", C.c_void_p),
+                ("grad_log_std", C.c_void_p), ("out", C.c_void_p), ("partial", C.c_void_p)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("n", C.c_int32),
+                ("lr", C.c_void_p), ("step", C.c_void_p), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("max_grad_norm", C.c_float), ("grad_scale", C.c_float), ("partial", C.c_void_p), ("out_norm", C.c_void_p)]
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ppo_head_reference(mu, value, log_std, actions, old_mu, old_neglogp, advantages, old_values, returns, e_clip, critic_coef, entropy_coef,
+                       bounds_loss_coef, mu_bound=1.1):
+    """Plain torch statement of the loss head; returns (loss, a_loss, c_loss, b_loss, kl, entropy)."""
+    ls = log_std.expand_as(mu)
+    nlp = 0.5 * (((actions - mu) / ls.exp()) ** 2).sum(-1) + ls.sum(-1) + 0.5 * mu.shape[-1] * 1.8378770664093453
+    ratio = torch.exp(old_neglogp - nlp)
+    a_loss = torch.max(-advantages * ratio, -advantages * torch.clamp(ratio, 1.0 - e_clip, 1.0 + e_clip)).mean()
+    v_clip = old_values + (value - old_values).clamp(-e_clip, e_clip)
+    c_loss = torch.max((value - returns) ** 2, (v_clip - returns) ** 2).mean()
+    b_loss = (torch.clamp(mu - mu_bound, min=0.0) ** 2 + torch.clamp(-mu_bound - mu, min=0.0) ** 2).sum(-1).mean()
+    entropy = (ls + 0.5 + 0.9189385332046727).sum(-1).mean()
+    loss = a_loss + 0.5 * critic_coef * c_loss - entropy_coef * entropy + bounds_loss_coef * b_loss
+    with torch.no_grad():
+        kl = (((mu - old_mu) ** 2) / (2.0 * torch.exp(2.0 * ls))).sum(-1).mean()
+    return loss, a_loss, c_loss, b_loss, kl, entropy
+
+
+class _PpoHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, value, log_std, head):
+        ctx.head = head
+        head.launch(mu, value, log_std)
+        return head.out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        h = ctx.head
+        return h.grad_mu * g, h.grad_value * g, h.grad_log_std * g, None
+
+
+class PpoHead:
+    """Static buffers + argument block of ``b2g_ppo_head`` for one minibatch size (graph-capturable: no allocation per call)."""
+
+    def __init__(self, n_rows, n_actions, device, e_clip, critic_coef, entropy_coef, bounds_loss_coef, mu_bound=1.1):
+        if n_actions > MAX_ACTIONS:
+            raise _lib.B2GError(f"b2g_ppo_head supports at most {MAX_ACTIONS} actions")
+        self.lib = _lib.load()
+        self.lib.b2g_ppo_head.argtypes = [C.POINTER(PpoHeadArgs), C.c_void_p]
+        self.lib.b2g_ppo_head.restype = C.c_int
+        self.lib.b2g_ppo_head_workspace_floats.restype = C.c_int
+        self.device = torch.device(device)
+        self.n_rows, self.n_actions = int(n_rows), int(n_actions)
+        self.grad_mu = torch.zeros(n_rows, n_actions, device=device)
+        self.grad_value = torch.zeros(n_rows, device=device)
+        self.grad_log_std = torch.zeros(n_actions, device=device)
+        self.out = torch.zeros(6, device=device)
+        self.partial = torch.zeros(int(self.lib.b2g_ppo_head_workspace_floats(int(n_rows))), device=device)
+        self.hyper = (float(e_clip), float(critic_coef), float(entropy_coef), float(bounds_loss_coef), float(mu_bound))
+        self.buffers = None
+
+    def bind(self, index, actions, old_mu, old_neglogp, advantages, old_values, returns):
+        """The rollout buffers (full size, contiguous float32) and the minibatch index vector (int64) this head reads."""
+        for t in (actions, old_mu, old_neglogp, advantages, old_values, returns):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        assert index is None or (index.dtype == torch.int64 and index.is_contiguous() and index.numel() == self.n_rows)
+        self.buffers = (index, actions, old_mu, old_neglogp, advantages, old_values, returns)
+
+    def launch(self, mu, value, log_std):
+        assert self.buffers is not None, "bind() the rollout buffers first"
+        mu, value, log_std = mu.contiguous(), value.contiguous(), log_std.contiguous()
+        assert mu.shape == (self.n_rows, self.n_actions) and value.shape == (self.n_rows,)
+        index, actions, old_mu, old_nlp, adv, old_val, ret = self.buffers
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        e, cc, ec, bc, mb = self.hyper
+        a = PpoHeadArgs(p(mu), p(value), p(log_std), p(index), p(actions), p(old_mu), p(old_nlp), p(adv), p(old_val), p(ret), self.n_rows, self.n_actions,
+                        e, cc, ec, bc, mb, p(self.grad_mu), p(self.grad_value), p(self.grad_log_std), p(self.out), p(self.partial))
+        self._keep = (mu, value, log_std)
+        _lib.check(self.lib.b2g_ppo_head(C.byref(a), _stream(self.device)), "b2g_ppo_head")
+
+    def loss(self, mu, value, log_std):
+        """Scalar loss with autograd edges to mu, value, log_std; ``self.out`` then holds (loss, a_loss, c_loss, b_loss, kl, entropy)."""
+        return _PpoHead.apply(mu, value, log_std, self)
+
+
+class FlatParameters:
+    """Re-homes every parameter of ``module`` into one flat float32 buffer (``.data`` becomes a view) and gives each a persistent
+    ``.grad`` view of a second flat buffer: autograd accumulates straight into it (use ``zero_()`` on :attr:`grad`, never
+    ``zero_grad(set_to_none=True)``)."""
+
+    def __init__(self, module: torch.nn.Module):
+        params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p.data)
+            p.grad = self.grad[off:off + k].view_as(p.data)
+            off += k
+        self.params, self.n = params, n
+
+
+class FusedClipAdam:
+    """``clip_grad_norm_`` + ``torch.optim.Adam`` (no weight decay, no amsgrad) on a :class:`FlatParameters` vector through
+    ``b2g_adam_clip_step``."""
+
+    def __init__(self, flat: FlatParameters, lr, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0, grad_scale=1.0):
+        self.lib = _lib.load()
+        self.lib.b2g_adam_clip_step.argtypes = [C.POINTER(AdamArgs), C.c_void_p]
+        self.lib.b2g_adam_clip_step.restype = C.c_int
+        self.flat = flat
+        dev = flat.flat.device
+        self.device = dev
+        self.lr = lr if torch.is_tensor(lr) else torch.tensor(float(lr), device=dev, dtype=torch.float32)
+        self.step_count = torch.zeros((), device=dev, dtype=torch.int64)
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_avg_sq = torch.zeros_like(flat.flat)
+        self.partial = torch.zeros(ADAM_MAX_PARTIALS, device=dev)
+        self.norm = torch.zeros(2, device=dev)          # gradient norm before clipping, clip coefficient
+        self.betas, self.eps, self.max_grad_norm, self.grad_scale = betas, float(eps), float(max_grad_norm), float(grad_scale)
+        # a param_groups-shaped view so that code written against torch optimisers (learning-rate schedules) keeps working
+        self.param_groups = [{"lr": self.lr, "params": flat.params}]
+
+    def step(self):
+        p = lambda t: C.c_void_p(t.data_ptr())
+        f = self.flat
+        a = AdamArgs(p(f.flat), p(f.grad), p(self.exp_avg), p(self.exp_avg_sq), f.n, p(self.lr), p(self.step_count), self.betas[0], self.betas[1],
+                     self.eps, self.max_grad_norm, self.grad_scale, p(self.partial), p(self.norm))
+        _lib.check(self.lib.b2g_adam_clip_step(C.byref(a), _stream(self.device)), "b2g_adam_clip_step")
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.grad.zero_()
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": int(self.step_count), "lr": float(self.lr)}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count.fill_(int(sd["step"]))

@@ -127,7 +127,7 @@ class TrainLog:
 
 class PPO:
     def __init__(self, env, cfg: PPOConfig = PPOConfig(), multi_gpu: bool = False, seed: int = 42, fused_rollout: bool = False,
-                 cuda_graphs: bool = False, graph_allreduce: bool = True):
+                 cuda_graphs: bool = False, graph_allreduce: bool = True, fused_update: bool = False):
         """``fused_rollout``: evaluate the policy during the rollout with the library's fused tcgen05 kernel
         (``learning/fused_policy.py``; bf16 operands, fp32 accumulation) instead of the torch modules. The update still
         differentiates the fp32 torch network; the behaviour policy's (mu, neglogp, value) are the kernel's.
@@ -137,7 +137,11 @@ class PPO:
         handful of graph launches instead of ~2000 kernel launches from Python.  Needs a task whose ``step()`` is free of host
         synchronisation and host-side per-step state (the fused flat tasks and Cartpole).  With several GPUs the gradient
         all-reduce (one flat NCCL all-reduce per minibatch) is captured inside the update graph (``graph_allreduce``); if the
-        capture is refused the update falls back to eager launches with the same all-reduce."""
+        capture is refused the update falls back to eager launches with the same all-reduce.
+
+        ``fused_update``: the loss head (clipped surrogate, clipped value loss, bound loss, entropy, KL and their gradients) as ONE
+        kernel of the library, parameters and gradients as one flat vector each, gradient clipping + Adam as two launches
+        (``learning/fused_update.py``); the linear layers stay with torch / cuBLAS."""
         self.env, self.cfg, self.multi_gpu = env, cfg, multi_gpu
         self.fused = self.fused_critic = None
         # a step() that synchronises with the host cannot be captured: such tasks roll out eagerly whatever the caller asked for
@@ -156,8 +160,21 @@ class PPO:
         if cfg.tf32:
             torch.backends.cuda.matmul.allow_tf32 = True
             torch.backends.cudnn.allow_tf32 = True
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t if graph_update else cfg.learning_rate, eps=1e-8,
-                                    capturable=graph_update, fused=True if cfg.fused_adam else None)
+        self.fused_update = bool(fused_update)
+        self.flatp = self.head = None
+        if self.fused_update:
+            from .fused_update import FlatParameters, FusedClipAdam
+
+            world = 1
+            if multi_gpu:
+                import torch.distributed as dist
+
+                world = dist.get_world_size()
+            self.flatp = FlatParameters(self.model)
+            self.opt = FusedClipAdam(self.flatp, lr=self.lr_t, eps=1e-8, max_grad_norm=cfg.grad_norm, grad_scale=1.0 / world)
+        else:
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t if graph_update else cfg.learning_rate, eps=1e-8,
+                                        capturable=graph_update, fused=True if cfg.fused_adam else None)
         self.lr = cfg.learning_rate
         if multi_gpu:
             import torch.distributed as dist
@@ -188,6 +205,11 @@ class PPO:
         self.mb = min(cfg.minibatch_size, T * n)
         self.idx = torch.zeros(self.mb, dtype=torch.long, device=dev)
         self.kl_acc = torch.zeros((), device=dev)
+        if self.fused_update:
+            from .fused_update import PpoHead
+
+            self.head = PpoHead(self.mb, env.num_acts, dev, cfg.e_clip, cfg.critic_coef, cfg.entropy_coef, cfg.bounds_loss_coef)
+            self.head.bind(self.idx, self.b_act.view(T * n, -1), self.b_mu.view(T * n, -1), self.b_nlp.view(-1), self.f_adv, self.f_val, self.f_ret)
         self._g_rollout = None
         self._g_update = None
 
@@ -258,6 +280,18 @@ class PPO:
         cfg = self.cfg
         T, N = cfg.horizon_length, self.env.num_envs
         idx = self.idx
+        if self.fused_update:
+            mu, _, v = self.model(self.b_obs.reshape(T * N, -1)[idx])
+            loss = self.head.loss(mu, v, self.model.log_std)
+            self.flatp.grad.zero_()
+            loss.backward()
+            if self.multi_gpu:
+                import torch.distributed as dist
+
+                dist.all_reduce(self.flatp.grad)          # SUM over ranks; the 1 / world factor is the optimiser's grad_scale
+            self.opt.step()                                # global-norm clip + Adam
+            self.kl_acc += self.head.out[4]
+            return
         f_obs, f_act = self.b_obs.reshape(T * N, -1), self.b_act.reshape(T * N, -1)
         f_nlp, f_mu = self.b_nlp.reshape(-1), self.b_mu.reshape(T * N, -1)
         mu, log_std, v = self.model(f_obs[idx])

@@ -9,7 +9,7 @@
 ``key=value`` overrides as in Hydra; dotted keys reach into the task / train yaml (``task.env.learn.pushInterval_s=8``,
 ``train.params.config.horizon_length=16``).  Hyper-parameters come from ``cfg/train/<Task>PPO.yaml`` (the reference's files with
 the interpolations resolved); the learner is the in-repo PPO (``learning/ppo.py``) instead of rl_games, which is not installed.
-Extra switches of this repo: ``cuda_graphs=True`` (default), ``fused_rollout=True`` (tcgen05 policy kernel: resident weights for [256,128,64], streamed weights for [512,256,128]).
+Extra switches of this repo: ``cuda_graphs=True`` (default), ``fused_update=True`` (loss head + clip + Adam kernels), ``fused_rollout=True`` (tcgen05 policy kernel: resident weights for [256,128,64], streamed weights for [512,256,128]).
 Checkpoints go to ``runs/<experiment or task>/nn/<name>.pth`` (rl_games' directory layout, ``docs/rl_examples.md``; the file holds this
 learner's own state dict -- network, normalisers, optimiser -- not rl_games' key names), every ``save_frequency`` epochs and at the end."""
 from __future__ import annotations
@@ -23,7 +23,7 @@ import yaml
 
 DEFAULTS = {"task": "Anymal", "train": "", "experiment": "", "num_envs": "", "seed": 42, "max_iterations": "", "sim_device": "cuda:0",
             "rl_device": "cuda:0", "graphics_device_id": 0, "test": False, "checkpoint": "", "multi_gpu": False, "headless": True,
-            "cuda_graphs": True, "fused_rollout": False, "tf32": True, "save_frequency": "", "output": ""}
+            "cuda_graphs": True, "fused_rollout": False, "fused_update": False, "tf32": True, "save_frequency": "", "output": ""}
 
 
 def _parse_value(v: str):
@@ -119,7 +119,8 @@ def main(argv=None):
     graphs = bool(top["cuda_graphs"]) and not getattr(env, "needs_host_sync", False)
     if top["save_frequency"] != "":
         cfg.save_frequency = int(top["save_frequency"])
-    ppo = PPO(env, cfg, multi_gpu=multi, seed=int(top["seed"]) + info.rank, fused_rollout=fused, cuda_graphs=graphs)
+    ppo = PPO(env, cfg, multi_gpu=multi, seed=int(top["seed"]) + info.rank, fused_rollout=fused, cuda_graphs=graphs,
+              fused_update=bool(top["fused_update"]) and env.num_acts <= 24)
     name = top["experiment"] or tc["params"]["config"]["name"]
     ckpt = top["output"] or os.path.join("runs", name, "nn", f"{name}.pth")
     ppo.checkpoint_path = ckpt if info.rank == 0 else None
