@@ -455,6 +455,85 @@ typedef struct b2g_ppo_head_args {
 int b2g_ppo_head(const b2g_ppo_head_args* args, void* stream);
 int b2g_ppo_head_workspace_floats(int n_rows);
 
+/* ---- rollout bookkeeping of the learner (what rl_games' play_steps does between two env steps; the fork states it in-tree for its AMP
+ * agent, learning/common_agent.py:250-310): a handful of launches per step instead of ~65 element-wise torch kernels ---- */
+
+/* rl_games RunningMeanStd on a (rows, cols) float32 batch: batch moments (float64 sums) merged into the running float64 (mean, var,
+ * count) by the parallel-variance formula; optional float32 copies of mean and 1 / sqrt(var + eps).  partial: b2g_stat_workspace_doubles. */
+int b2g_running_stat_update(const float* x, int rows, int cols, double* mean, double* var, double* count, double* partial, float* mean_f32,
+                            float* inv_std_f32, float eps, void* stream);
+int b2g_stat_workspace_doubles(int rows, int cols);
+/* out = clamp((x - mean) * inv_std, +-clip), element-wise over (rows, cols) */
+int b2g_normalize_store(const float* x, const float* mean_f32, const float* inv_std_f32, float* out, int rows, int cols, float clip, void* stream);
+
+/* Sampling of step t: a = mu + exp(log_std) * N(0, 1) with Philox4x32-10 + Box-Muller keyed by (seed, *rollout_counter, t, env), neglogp,
+ * the de-normalised value v * sqrt(var + eps) + mean, rows t of the rollout buffers, and the clamped action for the environment. */
+typedef struct b2g_rollout_sample_args {
+    const float* mu;              /* (N, A) policy mean of the current observations */
+    const float* value;           /* (N) normalised value prediction */
+    const float* log_std;         /* (A) */
+    const double* value_mean;     /* running statistics of the returns (scalars, float64) */
+    const double* value_var;
+    float value_eps, action_clip;
+    int32_t n_envs, n_actions, t;
+    uint64_t seed;
+    const int64_t* rollout_counter;   /* device scalar, advanced once per rollout (b2g_rollout_counter_advance) */
+    float* b_actions;             /* (T, N, A) */
+    float* b_mu;                  /* (T, N, A) */
+    float* b_neglogp;             /* (T, N) */
+    float* b_values;              /* (T, N) de-normalised */
+    float* env_actions;           /* (N, A) clamp(a, +-action_clip) */
+} b2g_rollout_sample_args;
+int b2g_rollout_sample(const b2g_rollout_sample_args* args, void* stream);
+int b2g_rollout_counter_advance(int64_t* counter, void* stream);
+
+/* After env.step of step t: b_rewards = reward_scale * r + gamma * V_t * time_out (reward_shaper + value_bootstrap), b_dones, and the RAW
+ * episode statistics (running per-env sums; `finished` += (sum of finished episodes' rewards, of their lengths, their count)). */
+typedef struct b2g_rollout_post_args {
+    const float* reward;          /* (N) */
+    const void* done;             /* (N) int64 or 1-byte flags (flag_bytes) */
+    const void* time_out;
+    int32_t flag_bytes;           /* 8 or 1 */
+    int32_t n_envs, t;
+    float reward_scale, gamma;
+    const float* b_values;        /* (T, N) */
+    float* b_rewards;             /* (T, N) */
+    float* b_dones;               /* (T, N) 0 / 1 */
+    float* ep_reward;             /* (N) */
+    float* ep_length;             /* (N) */
+    double* finished;             /* (3) */
+} b2g_rollout_post_args;
+int b2g_rollout_post(const b2g_rollout_post_args* args, void* stream);
+
+/* End of the rollout: GAE(gamma, tau) as rl_games' discount_values runs it (in-tree statement: learning/common_agent.py:406-418), returns =
+ * advantages + values, running statistics of the returns, then f_ret / f_val normalised by them and f_adv = (A - mean A) / (std A + 1e-8)
+ * with the unbiased standard deviation (torch.std).  partial: 4 * ceil(T N / 512) doubles. */
+typedef struct b2g_gae_args {
+    const float* rewards;         /* (T, N) */
+    const float* values;          /* (T, N) */
+    const float* dones;           /* (T, N) */
+    const float* v_last;          /* (N) value of the observation after the last step, de-normalised */
+    int32_t horizon, n_envs;
+    float gamma, tau, value_eps;
+    double* value_mean;           /* running statistics of the returns, updated */
+    double* value_var;
+    double* value_count;
+    float* adv;                   /* (T, N) scratch */
+    float* ret;                   /* (T, N) scratch */
+    float* f_ret;                 /* (T N) */
+    float* f_val;
+    float* f_adv;
+    double* partial;
+} b2g_gae_args;
+int b2g_gae_finish(const b2g_gae_args* args, void* stream);
+
+/* Hidden layer of the actor-critic MLP around the library GEMM: h = elu(z + bias) in place over the GEMM output z (rows x cols,
+ * row-major, cols % 4 == 0), and the backward pass of that pair fused with the bias gradient: dz = dh * elu'(z) (from the stored
+ * output h), dbias = column sums of dz (deterministic two-stage sum).  workspace: b2g_mlp_elu_backward_workspace_floats floats. */
+int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* stream);
+int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbias, float* partial, int rows, int cols, void* stream);
+int b2g_mlp_elu_backward_workspace_floats(int rows, int cols);
+
 /* Global-norm clipping + Adam on one flat parameter vector (torch.optim.Adam semantics: no weight decay, no amsgrad).  The effective
  * gradient is grad * grad_scale (1 / world size after an all-reduce SUM); *step is advanced by one. */
 typedef struct b2g_adam_args {

@@ -137,6 +137,245 @@ __global__ void __launch_bounds__(kHeadBlock) k_ppo_head_finalize(b2g_ppo_head_a
     if (threadIdx.x < A) a.grad_log_std[threadIdx.x] = tot[4 + threadIdx.x] - a.entropy_coef;
 }
 
+// ---- hidden layers of the actor-critic MLP: bias + ELU in one pass, and its backward fused with the bias gradient --------------------
+// forward: h = elu(z + b) in place over the GEMM output z (rows x cols, row-major)
+__global__ void __launch_bounds__(256) k_bias_elu(float* __restrict__ z, const float* __restrict__ b, size_t n4, int cols4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<float4*>(z)[i];
+        const float4 bb = reinterpret_cast<const float4*>(b)[i % cols4];
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        v.x = v.x > 0.0f ? v.x : expm1f(v.x); v.y = v.y > 0.0f ? v.y : expm1f(v.y);
+        v.z = v.z > 0.0f ? v.z : expm1f(v.z); v.w = v.w > 0.0f ? v.w : expm1f(v.w);
+        reinterpret_cast<float4*>(z)[i] = v;
+    }
+}
+
+// backward: dz = dh * elu'(z) with elu'(z) = 1 (h > 0) or h + 1 (h <= 0) from the stored OUTPUT h; column sums of dz (= the bias
+// gradient) per block of kColRows rows into partial[block][col].  Block = (cols / 4) column threads x row lanes.
+constexpr int kColRows = 256;
+__global__ void __launch_bounds__(256) k_elu_bwd_colsum(const float* __restrict__ dh, const float* __restrict__ h, float* __restrict__ dz,
+                                                        float* __restrict__ partial, int rows, int cols) {
+    extern __shared__ float4 red4[];      // (row lanes, cols / 4)
+    const int cols4 = cols >> 2;
+    const int c4 = threadIdx.x % cols4, lane = threadIdx.x / cols4, lanes = blockDim.x / cols4;
+    const int r0 = blockIdx.x * kColRows, r1 = min(r0 + kColRows, rows);
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (lane < lanes) {
+        for (int r = r0 + lane; r < r1; r += lanes) {
+            const size_t i = (size_t)r * cols4 + c4;
+            const float4 g = reinterpret_cast<const float4*>(dh)[i], o = reinterpret_cast<const float4*>(h)[i];
+            float4 d;
+            d.x = g.x * (o.x > 0.0f ? 1.0f : o.x + 1.0f); d.y = g.y * (o.y > 0.0f ? 1.0f : o.y + 1.0f);
+            d.z = g.z * (o.z > 0.0f ? 1.0f : o.z + 1.0f); d.w = g.w * (o.w > 0.0f ? 1.0f : o.w + 1.0f);
+            reinterpret_cast<float4*>(dz)[i] = d;
+            acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+        }
+        red4[lane * cols4 + c4] = acc;
+    }
+    __syncthreads();
+    if (lane == 0) {      // row lanes added in order: deterministic
+        for (int q = 1; q < lanes; q++) {
+            const float4 t = red4[q * cols4 + c4];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        reinterpret_cast<float4*>(partial)[(size_t)blockIdx.x * cols4 + c4] = acc;
+    }
+}
+
+__global__ void k_colsum_finalize(const float* __restrict__ partial, int n_blocks, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.0f;
+    for (int b = 0; b < n_blocks; b++) s += partial[(size_t)b * cols + c];
+    out[c] = s;
+}
+
+// ---- rollout bookkeeping of the learner: what rl_games' play_steps does between two env steps, as a handful of launches --------------
+// running mean / variance (rl_games RunningMeanStd, float64 state): per-column batch sums in double, then the parallel-variance merge
+constexpr int kStatRows = 512;
+__global__ void __launch_bounds__(256) k_stat_partial(const float* __restrict__ x, int rows, int cols, double* __restrict__ partial) {
+    extern __shared__ double redd[];      // (lanes, cols, 2)
+    const int lanes = cols <= 256 ? 256 / cols : 1;
+    const int c = threadIdx.x % cols, lane = threadIdx.x / cols;
+    const int r0 = blockIdx.x * kStatRows, r1 = min(r0 + kStatRows, rows);
+    for (int cc = c; cc < cols; cc += 256) {      // cols > 256: every thread walks several columns
+        double s = 0.0, q = 0.0;
+        if (lane < lanes)
+            for (int r = r0 + lane; r < r1; r += lanes) {
+                const double v = (double)x[(size_t)r * cols + cc];
+                s += v; q += v * v;
+            }
+        if (cols <= 256) {
+            if (lane < lanes) { redd[(lane * cols + c) * 2] = s; redd[(lane * cols + c) * 2 + 1] = q; }
+            __syncthreads();
+            if (lane == 0) {
+                for (int l = 1; l < lanes; l++) { s += redd[(l * cols + c) * 2]; q += redd[(l * cols + c) * 2 + 1]; }
+                partial[((size_t)blockIdx.x * cols + c) * 2] = s;
+                partial[((size_t)blockIdx.x * cols + c) * 2 + 1] = q;
+            }
+        } else {
+            partial[((size_t)blockIdx.x * cols + cc) * 2] = s;
+            partial[((size_t)blockIdx.x * cols + cc) * 2 + 1] = q;
+        }
+    }
+}
+
+// one thread per column: batch moments -> merged into the running (mean, var, count); float32 copies of mean and 1 / sqrt(var + eps)
+__global__ void k_stat_merge(const double* __restrict__ partial, int n_blocks, int rows, int cols, double* mean, double* var, double* count,
+                             int bump_count, float* mean_f, float* inv_std_f, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < n_blocks; b++) { s += partial[((size_t)b * cols + c) * 2]; q += partial[((size_t)b * cols + c) * 2 + 1]; }
+    const double bc = (double)rows, bm = s / bc;
+    double bv = q / bc - bm * bm;
+    if (bv < 0.0) bv = 0.0;
+    const double cnt = *count, tot = cnt + bc, delta = bm - mean[c];
+    const double m = mean[c] + delta * bc / tot;
+    const double v = (var[c] * cnt + bv * bc + delta * delta * cnt * bc / tot) / tot;
+    mean[c] = m; var[c] = v;
+    if (mean_f) mean_f[c] = (float)m;
+    if (inv_std_f) inv_std_f[c] = (float)(1.0 / sqrt(v + (double)eps));
+    if (bump_count && c == 0) {
+        // every column read `count` above; the single writer runs after a grid-wide agreement is not available here, so the count is
+        // advanced by a separate one-thread launch (k_count_add) queued behind this kernel
+    }
+}
+__global__ void k_count_add(double* count, double n) { *count += n; }
+
+// normalised observations of step t into the rollout buffer: clamp((x - mean) * inv_std, +-clip)
+__global__ void __launch_bounds__(256) k_normalize_store(const float* __restrict__ x, const float* __restrict__ mean_f, const float* __restrict__ inv_std_f,
+                                                         float* __restrict__ out, size_t n, int cols, float clip) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols);
+        out[i] = fminf(fmaxf((x[i] - mean_f[c]) * inv_std_f[c], -clip), clip);
+    }
+}
+
+__device__ __forceinline__ void philox4(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* o) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = (unsigned long long)c0 * 0xD2511F53ull, p1 = (unsigned long long)c2 * 0xCD9E8D57ull;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+// one thread per environment: a = mu + sigma * N(0, 1) (Philox4x32-10 + Box-Muller keyed by (seed, rollout counter, step, env)),
+// neglogp, de-normalised value, the step's rows of the rollout buffers, and the clamped action the environment receives
+__global__ void __launch_bounds__(256) k_rollout_sample(b2g_rollout_sample_args a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_envs) return;
+    const int A = a.n_actions;
+    const unsigned long long epoch = (unsigned long long)*a.rollout_counter;
+    float nlp = 0.5f * (float)A * 1.8378770664093453f;
+    const size_t row = ((size_t)a.t * a.n_envs + e) * A;
+    for (int k0 = 0; k0 < A; k0 += 4) {
+        unsigned w[4];
+        philox4((unsigned)e, (unsigned)a.t, (unsigned)(k0 >> 2), (unsigned)epoch, (unsigned)(a.seed & 0xffffffffull) ^ (unsigned)(epoch >> 32), (unsigned)(a.seed >> 32), w);
+        float g[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {      // two Box-Muller pairs per Philox block
+            const float u1 = ((float)(w[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)(w[2 * h + 1] >> 8) * (1.0f / 16777216.0f);
+            const float r = sqrtf(-2.0f * logf(u1));
+            float sn, cs;
+            sincosf(6.283185307179586f * u2, &sn, &cs);
+            g[2 * h] = r * cs; g[2 * h + 1] = r * sn;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j;
+            if (k < A) {
+                const float ls = a.log_std[k], m = a.mu[(size_t)e * A + k];
+                const float act = m + expf(ls) * g[j];
+                nlp += 0.5f * g[j] * g[j] + ls;
+                a.b_actions[row + k] = act;
+                a.b_mu[row + k] = m;
+                a.env_actions[(size_t)e * A + k] = fminf(fmaxf(act, -a.action_clip), a.action_clip);
+            }
+        }
+    }
+    const size_t i = (size_t)a.t * a.n_envs + e;
+    a.b_neglogp[i] = nlp;
+    a.b_values[i] = a.value[e] * sqrtf((float)(*a.value_var) + a.value_eps) + (float)(*a.value_mean);
+}
+__global__ void k_counter_add(int64_t* c) { *c += 1; }
+
+// one thread per environment after env.step: shaped reward (reward_shaper scale + value bootstrap on time-outs), done flags, raw
+// episode statistics
+__global__ void __launch_bounds__(256) k_rollout_post(b2g_rollout_post_args a) {
+    __shared__ double red[3][8];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    if (e < a.n_envs) {
+        const size_t i = (size_t)a.t * a.n_envs + e;
+        const float rew = a.reward[e];
+        const bool done = a.flag_bytes == 8 ? reinterpret_cast<const int64_t*>(a.done)[e] != 0 : reinterpret_cast<const unsigned char*>(a.done)[e] != 0;
+        const bool tout = a.flag_bytes == 8 ? reinterpret_cast<const int64_t*>(a.time_out)[e] != 0 : reinterpret_cast<const unsigned char*>(a.time_out)[e] != 0;
+        a.b_rewards[i] = a.reward_scale * rew + (tout ? a.gamma * a.b_values[i] : 0.0f);
+        a.b_dones[i] = done ? 1.0f : 0.0f;
+        const float er = a.ep_reward[e] + rew, el = a.ep_length[e] + 1.0f;
+        if (done) { f0 = er; f1 = el; f2 = 1.0; }
+        a.ep_reward[e] = done ? 0.0f : er;
+        a.ep_length[e] = done ? 0.0f : el;
+    }
+    // block sums, then one atomic per block (logging statistics only)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o); f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = f0; red[1][threadIdx.x >> 5] = f1; red[2][threadIdx.x >> 5] = f2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int q = 0; q < 8; q++) t += red[threadIdx.x][q];
+        if (t != 0.0) atomicAdd(a.finished + threadIdx.x, t);
+    }
+}
+
+// generalised advantage estimation, one thread per environment walking the horizon backwards (rl_games discount_values)
+__global__ void __launch_bounds__(256) k_gae(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ done,
+                                             const float* __restrict__ v_last, int T, int N, float gamma, float tau, float* __restrict__ adv,
+                                             float* __restrict__ ret) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    float last = 0.0f, nv = v_last[e];
+    for (int t = T - 1; t >= 0; t--) {
+        const size_t i = (size_t)t * N + e;
+        const float nonterm = 1.0f - done[i], v = val[i];
+        const float delta = rew[i] + gamma * nv * nonterm - v;
+        last = delta + gamma * tau * nonterm * last;
+        adv[i] = last;
+        ret[i] = last + v;
+        nv = v;
+    }
+}
+
+// after the return statistics are merged: normalised returns / values, and advantages normalised by their own mean and UNBIASED std
+__global__ void __launch_bounds__(256) k_finish_batch(const float* __restrict__ ret, const float* __restrict__ val, const float* __restrict__ adv,
+                                                      const double* __restrict__ vmean, const double* __restrict__ vvar, const double* __restrict__ adv_partial,
+                                                      int n_adv_blocks, size_t n, float eps_v, float* __restrict__ f_ret, float* __restrict__ f_val,
+                                                      float* __restrict__ f_adv) {
+    __shared__ float am_s, as_s;
+    if (threadIdx.x == 0) {
+        double s = 0.0, q = 0.0;
+        for (int b = 0; b < n_adv_blocks; b++) { s += adv_partial[2 * b]; q += adv_partial[2 * b + 1]; }
+        const double m = s / (double)n;
+        double var = (q - (double)n * m * m) / (double)(n > 1 ? n - 1 : 1);
+        if (var < 0.0) var = 0.0;
+        am_s = (float)m; as_s = (float)sqrt(var);
+    }
+    __syncthreads();
+    const float vm = (float)*vmean, vis = rsqrtf((float)*vvar + eps_v), am = am_s, ais = 1.0f / (as_s + 1e-8f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        f_ret[i] = (ret[i] - vm) * vis;
+        f_val[i] = (val[i] - vm) * vis;
+        f_adv[i] = (adv[i] - am) * ais;
+    }
+}
+
 constexpr int kAdamBlock = 256;
 
 __global__ void __launch_bounds__(kAdamBlock) k_sq_partial(const float* __restrict__ g, int n, float scale, float* __restrict__ partial) {
@@ -200,6 +439,94 @@ int b2g_ppo_head(const b2g_ppo_head_args* a, void* stream) {
 }
 
 int b2g_ppo_head_workspace_floats(int n_rows) { return ((n_rows + kHeadBlock - 1) / kHeadBlock) * kHeadCols; }
+
+int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* stream) {
+    if (!z || !bias || rows < 1 || cols < 4 || (cols & 3)) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_bias_elu: cols must be a positive multiple of 4");
+    const size_t n4 = (size_t)rows * cols / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    k_bias_elu<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, bias, n4, cols / 4);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_bias_elu: launch failed");
+}
+
+int b2g_mlp_elu_backward_workspace_floats(int rows, int cols) { return ((rows + kColRows - 1) / kColRows) * cols; }
+
+int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbias, float* partial, int rows, int cols, void* stream) {
+    if (!dh || !h || !dz || !dbias || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_elu_backward: null argument");
+    if (cols < 4 || (cols & 3) || cols > 1024) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_elu_backward: cols must be a multiple of 4, at most 1024");
+    const int cols4 = cols / 4;
+    int lanes = 256 / cols4;
+    if (lanes < 1) lanes = 1;
+    const int threads = lanes * cols4;          // <= 256
+    const int blocks = (rows + kColRows - 1) / kColRows;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_elu_bwd_colsum<<<blocks, threads, sizeof(float4) * lanes * cols4, st>>>(dh, h, dz, partial, rows, cols);
+    k_colsum_finalize<<<(cols + 127) / 128, 128, 0, st>>>(partial, blocks, cols, dbias);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_elu_backward: launch failed");
+}
+
+int b2g_stat_workspace_doubles(int rows, int cols) { return ((rows + kStatRows - 1) / kStatRows) * cols * 2; }
+
+int b2g_running_stat_update(const float* x, int rows, int cols, double* mean, double* var, double* count, double* partial, float* mean_f32,
+                            float* inv_std_f32, float eps, void* stream) {
+    if (!x || !mean || !var || !count || !partial || rows < 1 || cols < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_running_stat_update: bad argument");
+    const int blocks = (rows + kStatRows - 1) / kStatRows;
+    const int lanes = cols <= 256 ? 256 / cols : 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_stat_partial<<<blocks, 256, cols <= 256 ? sizeof(double) * 2 * lanes * cols : 0, st>>>(x, rows, cols, partial);
+    k_stat_merge<<<(cols + 127) / 128, 128, 0, st>>>(partial, blocks, rows, cols, mean, var, count, 1, mean_f32, inv_std_f32, eps);
+    k_count_add<<<1, 1, 0, st>>>(count, (double)rows);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_running_stat_update: launch failed");
+}
+
+int b2g_normalize_store(const float* x, const float* mean_f32, const float* inv_std_f32, float* out, int rows, int cols, float clip, void* stream) {
+    if (!x || !mean_f32 || !inv_std_f32 || !out || rows < 1 || cols < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_normalize_store: bad argument");
+    const size_t n = (size_t)rows * cols;
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    k_normalize_store<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, mean_f32, inv_std_f32, out, n, cols, clip);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_normalize_store: launch failed");
+}
+
+int b2g_rollout_sample(const b2g_rollout_sample_args* a, void* stream) {
+    if (!a || !a->mu || !a->value || !a->log_std || !a->b_actions || !a->b_mu || !a->b_neglogp || !a->b_values || !a->env_actions || !a->rollout_counter ||
+        !a->value_mean || !a->value_var)
+        return b2g::fail_msg(B2G_ERR_ARG, "b2g_rollout_sample: null argument");
+    k_rollout_sample<<<(a->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_rollout_sample: launch failed");
+}
+
+int b2g_rollout_counter_advance(int64_t* counter, void* stream) {
+    if (!counter) return b2g::fail_msg(B2G_ERR_ARG, "null counter");
+    k_counter_add<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "launch failed");
+}
+
+int b2g_rollout_post(const b2g_rollout_post_args* a, void* stream) {
+    if (!a || !a->reward || !a->done || !a->time_out || !a->b_values || !a->b_rewards || !a->b_dones || !a->ep_reward || !a->ep_length || !a->finished)
+        return b2g::fail_msg(B2G_ERR_ARG, "b2g_rollout_post: null argument");
+    if (a->flag_bytes != 1 && a->flag_bytes != 8) return b2g::fail_msg(B2G_ERR_ARG, "b2g_rollout_post: flags are 1-byte (bool / uint8) or 8-byte (int64)");
+    k_rollout_post<<<(a->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_rollout_post: launch failed");
+}
+
+int b2g_gae_finish(const b2g_gae_args* a, void* stream) {
+    if (!a || !a->rewards || !a->values || !a->dones || !a->v_last || !a->adv || !a->ret || !a->f_ret || !a->f_val || !a->f_adv || !a->value_mean ||
+        !a->value_var || !a->value_count || !a->partial)
+        return b2g::fail_msg(B2G_ERR_ARG, "b2g_gae_finish: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = a->horizon, N = a->n_envs;
+    const int n = T * N;
+    k_gae<<<(N + 255) / 256, 256, 0, st>>>(a->rewards, a->values, a->dones, a->v_last, T, N, a->gamma, a->tau, a->adv, a->ret);
+    // running statistics of the returns (value normaliser), then the advantages' own moments
+    const int blocks = (n + kStatRows - 1) / kStatRows;
+    k_stat_partial<<<blocks, 256, sizeof(double) * 2 * 256, st>>>(a->ret, n, 1, a->partial);
+    k_stat_merge<<<1, 128, 0, st>>>(a->partial, blocks, n, 1, a->value_mean, a->value_var, a->value_count, 1, nullptr, nullptr, 0.0f);
+    k_count_add<<<1, 1, 0, st>>>(a->value_count, (double)n);
+    k_stat_partial<<<blocks, 256, sizeof(double) * 2 * 256, st>>>(a->adv, n, 1, a->partial + 2 * blocks);
+    const int fb = (n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8;
+    k_finish_batch<<<fb, 256, 0, st>>>(a->ret, a->values, a->adv, a->value_mean, a->value_var, a->partial + 2 * blocks, blocks, (size_t)n, a->value_eps,
+                                       a->f_ret, a->f_val, a->f_adv);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_gae_finish: launch failed");
+}
 
 int b2g_adam_clip_step(const b2g_adam_args* a, void* stream) {
     if (!a || !a->param || !a->grad || !a->exp_avg || !a->exp_avg_sq || !a->lr || !a->step || !a->partial || !a->out_norm)

@@ -114,6 +114,144 @@ class PpoHead:
         return _PpoHead.apply(mu, value, log_std, self)
 
 
+class RolloutSampleArgs(C.Structure):
+    _fields_ = [("mu", C.c_void_p), ("value", C.c_void_p), ("log_std", C.c_void_p), ("value_mean", C.c_void_p), ("value_var", C.c_void_p),
+                ("value_eps", C.c_float), ("action_clip", C.c_float), ("n_envs", C.c_int32), ("n_actions", C.c_int32), ("t", C.c_int32),
+                ("seed", C.c_uint64), ("rollout_counter", C.c_void_p), ("b_actions", C.c_void_p), ("b_mu", C.c_void_p), ("b_neglogp", C.c_void_p),
+                ("b_values", C.c_void_p), ("env_actions", C.c_void_p)]
+
+
+class RolloutPostArgs(C.Structure):
+    _fields_ = [("reward", C.c_void_p), ("done", C.c_void_p), ("time_out", C.c_void_p), ("flag_bytes", C.c_int32), ("n_envs", C.c_int32), ("t", C.c_int32),
+                ("reward_scale", C.c_float), ("gamma", C.c_float), ("b_values", C.c_void_p), ("b_rewards", C.c_void_p), ("b_dones", C.c_void_p),
+                ("ep_reward", C.c_void_p), ("ep_length", C.c_void_p), ("finished", C.c_void_p)]
+
+
+class GaeArgs(C.Structure):
+    _fields_ = [("rewards", C.c_void_p), ("values", C.c_void_p), ("dones", C.c_void_p), ("v_last", C.c_void_p), ("horizon", C.c_int32), ("n_envs", C.c_int32),
+                ("gamma", C.c_float), ("tau", C.c_float), ("value_eps", C.c_float), ("value_mean", C.c_void_p), ("value_var", C.c_void_p),
+                ("value_count", C.c_void_p), ("adv", C.c_void_p), ("ret", C.c_void_p), ("f_ret", C.c_void_p), ("f_val", C.c_void_p), ("f_adv", C.c_void_p),
+                ("partial", C.c_void_p)]
+
+
+class RolloutKernels:
+    """The learner's per-step bookkeeping through ``libb200gym`` (``b2g_running_stat_update``, ``b2g_normalize_store``,
+    ``b2g_rollout_sample``, ``b2g_rollout_post``, ``b2g_gae_finish``): operates on the PPO object's static rollout buffers."""
+
+    def __init__(self, ppo, seed):
+        self.lib = lib = _lib.load()
+        vp = C.c_void_p
+        lib.b2g_running_stat_update.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, vp]
+        lib.b2g_stat_workspace_doubles.argtypes = [C.c_int, C.c_int]
+        lib.b2g_normalize_store.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, vp]
+        lib.b2g_rollout_sample.argtypes = [C.POINTER(RolloutSampleArgs), vp]
+        lib.b2g_rollout_counter_advance.argtypes = [vp, vp]
+        lib.b2g_rollout_post.argtypes = [C.POINTER(RolloutPostArgs), vp]
+        lib.b2g_gae_finish.argtypes = [C.POINTER(GaeArgs), vp]
+        for f in (lib.b2g_running_stat_update, lib.b2g_stat_workspace_doubles, lib.b2g_normalize_store, lib.b2g_rollout_sample,
+                  lib.b2g_rollout_counter_advance, lib.b2g_rollout_post, lib.b2g_gae_finish):
+            f.restype = C.c_int
+        self.p = ppo
+        env, cfg = ppo.env, ppo.cfg
+        dev = self.device = torch.device(ppo.device)
+        N, T, F, A = env.num_envs, cfg.horizon_length, env.num_obs, env.num_acts
+        self.N, self.T, self.F, self.A = N, T, F, A
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.counter = torch.zeros((), device=dev, dtype=torch.int64)
+        self.mean_f = torch.zeros(F, device=dev)
+        self.inv_std_f = torch.ones(F, device=dev)
+        self.obs_ws = torch.zeros(int(lib.b2g_stat_workspace_doubles(N, F)), device=dev, dtype=torch.float64)
+        self.gae_ws = torch.zeros(4 * ((T * N + 511) // 512), device=dev, dtype=torch.float64)
+        self.env_actions = torch.zeros(N, A, device=dev)
+        self.mu = torch.zeros(N, A, device=dev)
+        self.mu_scratch = torch.zeros(N, A, device=dev)          # action head of the critic instance of a separate network (unused)
+        self.value = torch.zeros(N, device=dev)
+        self.adv = torch.zeros(T, N, device=dev)
+        self.ret = torch.zeros(T, N, device=dev)
+        self.nobs_last = torch.zeros(N, F, device=dev)
+
+    def _s(self):
+        return _stream(self.device)
+
+    def obs_stats(self, obs):
+        """obs_rms.update(obs) + float32 mean / inverse std for the normalisation of this step."""
+        r = self.p.obs_rms
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(self.lib.b2g_running_stat_update(p(obs), self.N, self.F, p(r.mean), p(r.var), p(r.count), p(self.obs_ws), p(self.mean_f), p(self.inv_std_f),
+                                                    C.c_float(r.eps), self._s()), "b2g_running_stat_update")
+
+    def normalize(self, obs, out, clip=5.0):
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(self.lib.b2g_normalize_store(p(obs), p(self.mean_f), p(self.inv_std_f), p(out), self.N, self.F, C.c_float(clip), self._s()), "b2g_normalize_store")
+
+    def sample(self, t, mu, value, log_std):
+        P, p = self.p, (lambda x: C.c_void_p(x.data_ptr()))
+        a = RolloutSampleArgs(p(mu), p(value), p(log_std), p(P.val_rms.mean), p(P.val_rms.var), float(P.val_rms.eps), 1.0, self.N, self.A, int(t), self.seed,
+                              p(self.counter), p(P.b_act), p(P.b_mu), p(P.b_nlp), p(P.b_val), p(self.env_actions))
+        _lib.check(self.lib.b2g_rollout_sample(C.byref(a), self._s()), "b2g_rollout_sample")
+
+    def post(self, t, rew, done, time_outs):
+        P, p = self.p, (lambda x: C.c_void_p(x.data_ptr()))
+        if done.dtype != time_outs.dtype or done.dtype not in (torch.int64, torch.bool, torch.uint8):
+            done, time_outs = done.to(torch.int64), time_outs.to(torch.int64)
+        nbytes = 8 if done.dtype == torch.int64 else 1
+        self._keep = (rew, done, time_outs)
+        a = RolloutPostArgs(p(rew), p(done), p(time_outs), nbytes, self.N, int(t), float(P.cfg.reward_scale), float(P.cfg.gamma), p(P.b_val), p(P.b_rew),
+                            p(P.b_done), p(P.ep_rew), p(P.ep_len), p(P.fin))
+        _lib.check(self.lib.b2g_rollout_post(C.byref(a), self._s()), "b2g_rollout_post")
+
+    def gae_finish(self, v_last):
+        P, p = self.p, (lambda x: C.c_void_p(x.data_ptr()))
+        r = P.val_rms
+        a = GaeArgs(p(P.b_rew), p(P.b_val), p(P.b_done), p(v_last), self.T, self.N, float(P.cfg.gamma), float(P.cfg.tau), 1e-5, p(r.mean), p(r.var),
+                    p(r.count), p(self.adv), p(self.ret), p(P.f_ret), p(P.f_val), p(P.f_adv), p(self.gae_ws))
+        _lib.check(self.lib.b2g_gae_finish(C.byref(a), self._s()), "b2g_gae_finish")
+        _lib.check(self.lib.b2g_rollout_counter_advance(C.c_void_p(self.counter.data_ptr()), self._s()), "counter")
+
+
+class _LinearELU(torch.autograd.Function):
+    """h = elu(x W^T + b): the GEMMs stay with torch / cuBLAS (TF32 tensor cores), bias + ELU is one in-place pass over the GEMM output,
+    and the backward pass fuses ELU' with the bias gradient (``b2g_mlp_bias_elu`` / ``b2g_mlp_elu_backward``) -- instead of add, elu,
+    elu_backward and a 32768-row column reduction as four separate torch kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = _lib.load()
+        h = torch.mm(x, weight.t())
+        _lib.check(lib.b2g_mlp_bias_elu(C.c_void_p(h.data_ptr()), C.c_void_p(bias.data_ptr()), h.shape[0], h.shape[1], _stream(h.device)), "b2g_mlp_bias_elu")
+        ctx.save_for_backward(x, weight, h)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, weight, h = ctx.saved_tensors
+        lib = _lib.load()
+        dh = dh.contiguous()
+        rows, cols = h.shape
+        dz = torch.empty_like(h)
+        db = torch.empty(cols, device=h.device, dtype=h.dtype)
+        ws = torch.empty(int(lib.b2g_mlp_elu_backward_workspace_floats(rows, cols)), device=h.device, dtype=h.dtype)
+        _lib.check(lib.b2g_mlp_elu_backward(C.c_void_p(dh.data_ptr()), C.c_void_p(h.data_ptr()), C.c_void_p(dz.data_ptr()), C.c_void_p(db.data_ptr()),
+                                            C.c_void_p(ws.data_ptr()), rows, cols, _stream(h.device)), "b2g_mlp_elu_backward")
+        dx = torch.mm(dz, weight) if ctx.needs_input_grad[0] else None
+        dw = torch.mm(dz.t(), x) if ctx.needs_input_grad[1] else None
+        return dx, dw, db
+
+
+def linear_elu(x, weight, bias):
+    """``F.elu(F.linear(x, weight, bias))`` through the fused kernels (CUDA float32, width a multiple of 4)."""
+    lib = _lib.load()
+    if not getattr(lib, "_b2g_mlp_protos", False):
+        lib.b2g_mlp_bias_elu.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.b2g_mlp_bias_elu.restype = C.c_int
+        lib.b2g_mlp_elu_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.b2g_mlp_elu_backward.restype = C.c_int
+        lib.b2g_mlp_elu_backward_workspace_floats.argtypes = [C.c_int, C.c_int]
+        lib.b2g_mlp_elu_backward_workspace_floats.restype = C.c_int
+        lib._b2g_mlp_protos = True
+    return _LinearELU.apply(x.contiguous(), weight, bias)
+
+
 class FlatParameters:
     """Re-homes every parameter of ``module`` into one flat float32 buffer (``.data`` becomes a view) and gives each a persistent
     ``.grad`` view of a second flat buffer: autograd accumulates straight into it (use ``zero_()`` on :attr:`grad`, never

@@ -60,15 +60,26 @@ class ActorCritic(nn.Module):
             return nn.Sequential(*layers), last
 
         self.separate = bool(separate)
+        self.fused_layers = False      # set by PPO(fused_update=True): hidden layers through learning/fused_update.linear_elu in training mode
         self.trunk, last = mlp()
         self.critic_trunk = mlp()[0] if self.separate else None
         self.mu = nn.Linear(last, num_actions)
         self.value = nn.Linear(last, 1)
         self.log_std = nn.Parameter(torch.zeros(num_actions))      # sigma_init const 0 -> std 1, fixed_sigma (state independent)
 
+    def _tower(self, seq, x):
+        if not (self.fused_layers and x.is_cuda and torch.is_grad_enabled()):
+            return seq(x)
+        from .fused_update import linear_elu
+
+        for m in seq:
+            if isinstance(m, nn.Linear):
+                x = linear_elu(x, m.weight, m.bias)
+        return x
+
     def forward(self, obs):
-        h = self.trunk(obs)
-        hv = self.critic_trunk(obs) if self.separate else h
+        h = self._tower(self.trunk, obs)
+        hv = self._tower(self.critic_trunk, obs) if self.separate else h
         return self.mu(h), self.log_std.expand(obs.shape[0], -1), self.value(hv).squeeze(-1)
 
 
@@ -171,6 +182,7 @@ class PPO:
 
                 world = dist.get_world_size()
             self.flatp = FlatParameters(self.model)
+            self.model.fused_layers = all(u % 4 == 0 and u <= 1024 for u in cfg.units)
             self.opt = FusedClipAdam(self.flatp, lr=self.lr_t, eps=1e-8, max_grad_norm=cfg.grad_norm, grad_scale=1.0 / world)
         else:
             self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t if graph_update else cfg.learning_rate, eps=1e-8,
@@ -208,6 +220,9 @@ class PPO:
         if self.fused_update:
             from .fused_update import PpoHead
 
+            from .fused_update import RolloutKernels
+
+            self.rk = RolloutKernels(self, seed)
             self.head = PpoHead(self.mb, env.num_acts, dev, cfg.e_clip, cfg.critic_coef, cfg.entropy_coef, cfg.bounds_loss_coef)
             self.head.bind(self.idx, self.b_act.view(T * n, -1), self.b_mu.view(T * n, -1), self.b_nlp.view(-1), self.f_adv, self.f_val, self.f_ret)
         self._g_rollout = None
@@ -228,7 +243,46 @@ class PPO:
 
     # ------------------------------------------------------------------ rollout (static shapes, no host sync)
     @torch.no_grad()
+    def _rollout_kernels(self):
+        """The rollout with the library's bookkeeping kernels (``fused_update=True``): per step running statistics (2 launches + count),
+        normalise-and-store, policy, sample-and-store, the environment step, reward / done / episode bookkeeping; then GAE, return
+        statistics and the three normalisations in six launches.  Same mathematics as :meth:`_rollout`; the Gaussian noise comes
+        from the kernel's own Philox stream instead of torch's generator."""
+        cfg, env, rk = self.cfg, self.env, self.rk
+        T, N = cfg.horizon_length, env.num_envs
+        obs = self.obs
+        if self.fused is not None:
+            self.fused.sync(self.model)
+            self.fused.set_obs_norm(None, None, 1e-5, 1e30)          # observations reach the policy kernel already normalised
+            if self.fused_critic is not None:
+                self.fused_critic.sync(self.model, critic=True)
+                self.fused_critic.set_obs_norm(None, None, 1e-5, 1e30)
+        log_std = self.model.log_std
+        for t in range(T):
+            rk.obs_stats(obs)
+            rk.normalize(obs, self.b_obs[t])
+            if self.fused is not None:
+                self.fused.forward(self.b_obs[t], rk.mu, rk.value)
+                if self.fused_critic is not None:
+                    self.fused_critic.forward(self.b_obs[t], rk.mu_scratch, rk.value)
+                mu, v = rk.mu, rk.value
+            else:
+                mu, _, v = self.model(self.b_obs[t])
+                mu, v = mu.contiguous(), v.contiguous()
+            rk.sample(t, mu, v, log_std)
+            o, rew, done, extras = env.step(rk.env_actions)
+            obs = o["obs"]
+            rk.post(t, rew, done, extras["time_outs"])
+        self.obs.copy_(obs)
+        rk.normalize(self.obs, rk.nobs_last)
+        _, _, v_last = self.model(rk.nobs_last)
+        v_last = self.val_rms.denormalize(v_last).contiguous()
+        rk.gae_finish(v_last)
+
+    @torch.no_grad()
     def _rollout(self):
+        if self.fused_update and self.device != "cpu":
+            return self._rollout_kernels()
         cfg, env = self.cfg, self.env
         T, N = cfg.horizon_length, env.num_envs
         obs = self.obs

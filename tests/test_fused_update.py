@@ -159,3 +159,111 @@ def test_ppo_fused_update_tracks_torch_update(graphs):
         assert all(torch.isfinite(p).all() for p in ppo.model.parameters())
     # one epoch = 4 optimiser steps from identical data: parameters agree to rounding (later epochs diverge chaotically through the env)
     assert (res[0] - res[1]).abs().max().item() < 2e-5, (res[0] - res[1]).abs().max().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,k,cols", [(32768, 48, 256), (1000, 256, 128), (777, 188, 512), (64, 128, 64)])
+def test_linear_elu_matches_torch(rows, k, cols):
+    from isaacgymenv_b200.learning.fused_update import linear_elu
+
+    dev = "cuda:0"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device=dev).manual_seed(rows)
+    x = torch.randn(rows, k, device=dev, generator=g)
+    w = (torch.randn(cols, k, device=dev, generator=g) / k ** 0.5)
+    b = 0.1 * torch.randn(cols, device=dev, generator=g)
+    up = torch.randn(rows, cols, device=dev, generator=g)
+    xa, wa, ba = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    xb, wb, bb = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    ha = linear_elu(xa, wa, ba)
+    hb = torch.nn.functional.elu(torch.nn.functional.linear(xb, wb, bb))
+    (ha * up).sum().backward()
+    (hb * up).sum().backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(ha.detach().cpu().numpy(), hb.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
+    for a, bref, name in ((xa.grad, xb.grad, "dx"), (wa.grad, wb.grad, "dw"), (ba.grad, bb.grad, "db")):
+        scale = float(bref.abs().max())
+        np.testing.assert_allclose(a.cpu().numpy(), bref.cpu().numpy(), rtol=1e-4, atol=2e-5 * scale, err_msg=name)
+    # the first layer's input needs no gradient: none is computed
+    xc = x.clone()
+    hc = linear_elu(xc, wa.detach().requires_grad_(), ba.detach().requires_grad_())
+    hc.sum().backward()
+    assert xc.grad is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols", [(4096, 48), (8192, 188), (1000, 300), (98304, 1), (7, 4)])
+def test_running_stat_kernel_matches_running_mean_std(rows, cols):
+    import ctypes as C
+
+    from isaacgymenv_b200 import _lib
+    from isaacgymenv_b200.learning.ppo import RunningMeanStd
+
+    dev = "cuda:0"
+    lib = _lib.load()
+    vp = C.c_void_p
+    lib.b2g_running_stat_update.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, vp]
+    lib.b2g_stat_workspace_doubles.argtypes = [C.c_int, C.c_int]
+    a, b = RunningMeanStd((cols,)).to(dev), RunningMeanStd((cols,)).to(dev)
+    ws = torch.zeros(int(lib.b2g_stat_workspace_doubles(rows, cols)), device=dev, dtype=torch.float64)
+    mean_f, inv_f = torch.zeros(cols, device=dev), torch.zeros(cols, device=dev)
+    g = torch.Generator(device=dev).manual_seed(rows + cols)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for k in range(4):
+        x = (3.0 * torch.randn(rows, cols, device=dev, generator=g) + 10.0 * k).contiguous()
+        _lib.check(lib.b2g_running_stat_update(p(x), rows, cols, p(a.mean), p(a.var), p(a.count), p(ws), p(mean_f), p(inv_f), C.c_float(1e-5), s))
+        b.update(x)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(a.mean.cpu().numpy(), b.mean.cpu().numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(a.var.cpu().numpy(), b.var.cpu().numpy(), rtol=1e-8, atol=1e-9)
+    assert float(a.count) == float(b.count) == 1 + 4 * rows
+    np.testing.assert_allclose(inv_f.cpu().numpy(), (1.0 / torch.sqrt(b.var.float() + 1e-5)).cpu().numpy(), rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task,separate,fused_policy", [("Anymal", False, True), ("Cartpole", False, False), ("AnymalTerrain", True, True)])
+def test_rollout_kernels_fill_the_buffers_like_the_torch_rollout(task, separate, fused_policy):
+    """After one rollout through the bookkeeping kernels every buffer satisfies the relations the torch rollout establishes: stored
+    neglogp = neglogp(stored action | stored mean, log_std); stored observations are the normalised observations; shaped rewards, GAE,
+    returns and the three normalisations recomputed in torch from the raw buffers; unit-variance Gaussian noise."""
+    import isaacgymenv_b200
+    from isaacgymenv_b200.learning.ppo import PPO, PPOConfig, compute_gae, neglogp
+
+    n, T = 512, 8
+    env = isaacgymenv_b200.make(seed=3, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True)
+    units = (512, 256, 128) if separate else (256, 128, 64)
+    cfg = PPOConfig(horizon_length=T, minibatch_size=n * T, mini_epochs=1, units=units, separate=separate, reward_scale=0.5, gamma=0.97, tau=0.9)
+    ppo = PPO(env, cfg, seed=7, fused_rollout=fused_policy, fused_update=True)
+    ppo.obs.copy_(env.reset()["obs"])
+    for _ in range(3):          # a few rollouts so that episodes end, time-outs aside
+        vm0, vv0, vc0 = ppo.val_rms.mean.clone(), ppo.val_rms.var.clone(), ppo.val_rms.count.clone()
+        ppo._rollout()
+    torch.cuda.synchronize()
+    ls = ppo.model.log_std.detach()
+    np.testing.assert_allclose(ppo.b_nlp.cpu().numpy(), neglogp(ppo.b_act, ppo.b_mu, ls.expand_as(ppo.b_mu)).cpu().numpy(), rtol=1e-4, atol=1e-4)
+    z = ((ppo.b_act - ppo.b_mu) / ls.exp()).flatten()
+    assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05 and float(z.abs().max()) < 7.0
+    assert float(ppo.b_obs.abs().max()) <= 5.0 + 1e-6
+    # GAE / returns / normalisations from the raw buffers
+    with torch.no_grad():
+        nobs = ppo.obs_rms.normalize(ppo.obs)
+        _, _, v_last = ppo.model(nobs)
+        # val_rms was updated by the rollout: v_last was de-normalised with the statistics BEFORE that update
+        v_last = v_last * torch.sqrt(vv0.float() + 1e-5) + vm0.float()
+    adv = compute_gae(ppo.b_rew, ppo.b_val, ppo.b_done, v_last, cfg.gamma, cfg.tau)
+    ret = adv + ppo.b_val
+    vm, vs = ppo.val_rms.mean.float(), torch.sqrt(ppo.val_rms.var.float() + 1e-5)
+    np.testing.assert_allclose(ppo.f_ret.cpu().numpy(), ((ret.reshape(-1) - vm) / vs).cpu().numpy(), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(ppo.f_val.cpu().numpy(), ((ppo.b_val.reshape(-1) - vm) / vs).cpu().numpy(), rtol=1e-4, atol=1e-4)
+    a = adv.reshape(-1)
+    np.testing.assert_allclose(ppo.f_adv.cpu().numpy(), ((a - a.mean()) / (a.std() + 1e-8)).cpu().numpy(), rtol=2e-3, atol=2e-3)
+    # the value normaliser saw exactly the returns
+    from isaacgymenv_b200.learning.ppo import RunningMeanStd
+
+    chk = RunningMeanStd(()).to("cuda:0")
+    chk.mean.copy_(vm0); chk.var.copy_(vv0); chk.count.copy_(vc0)
+    chk.update(ret)
+    assert float(ppo.val_rms.mean) == pytest.approx(float(chk.mean), rel=1e-3, abs=1e-4) and float(ppo.val_rms.var) == pytest.approx(float(chk.var), rel=1e-3)
+    assert set(torch.unique(ppo.b_done).tolist()) <= {0.0, 1.0} and float(ppo.fin[2]) >= 0
+    assert torch.isfinite(ppo.f_adv).all() and torch.isfinite(ppo.b_rew).all()
