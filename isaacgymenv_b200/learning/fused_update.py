@@ -257,11 +257,14 @@ class FlatParameters:
     ``.grad`` view of a second flat buffer: autograd accumulates straight into it (use ``zero_()`` on :attr:`grad`, never
     ``zero_grad(set_to_none=True)``)."""
 
+    ALIGN = 32      # floats: every parameter starts on a 128-byte boundary (the kernels read rows of them as float4)
+
     def __init__(self, module: torch.nn.Module):
         params = [p for p in module.parameters() if p.requires_grad]
-        n = sum(p.numel() for p in params)
+        pad = lambda k: (k + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        n = sum(pad(p.numel()) for p in params)
         dev = params[0].device
-        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)       # the gaps stay zero: zero gradient, zero Adam update
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
         for p in params:
@@ -269,7 +272,7 @@ class FlatParameters:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
-            off += k
+            off += pad(k)
         self.params, self.n = params, n
 
 
