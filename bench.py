@@ -412,12 +412,7 @@ def run_ours(args):
                              "gpu_launches": r["launches"], "roofline": roofline_of(r, k), "contact_stats": r["contact_stats"]}
             except Exception as exc:      # never lose the headline line to a side config
                 others[t] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    ppo = None
-    if args.ppo and args.task == "Anymal" and args.num_envs <= 0:      # config 5 rides in the same line at every N
-        try:
-            ppo = measure_ppo(dev, rank, world, dist)
-        except Exception as exc:
-            ppo = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    line = None
     if rank == 0:
         total = world * n * args.steps
         cold_ms, warm_ms, e2e_ms = res["cold_ms"], res["warm_ms"], res["e2e_ms"]
@@ -450,11 +445,39 @@ def run_ours(args):
                 "cpu_baseline": cpu, "clocks": res["clocks"], "contact_stats": res["contact_stats"]}
         if others:
             line["other_configs"] = others
-        if ppo:
+    # ---- config 5 rides in the same line at every N.  The headline line above is complete before it starts, and a watchdog prints that
+    # line and leaves if the learner leg does not come back (a stuck collective must never cost the measurement) ----
+    if args.ppo and args.task == "Anymal" and args.num_envs <= 0:
+        finished = threading.Event()
+
+        def watchdog():
+            if not finished.wait(timeout=float(args.ppo_timeout)):
+                if rank == 0:
+                    line["ppo_config5"] = {"error": f"learner leg did not finish within {args.ppo_timeout} s"}
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+        try:
+            ppo = measure_ppo(dev, rank, world, dist)
+        except Exception as exc:
+            ppo = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        finished.set()
+        if rank == 0:
             line["ppo_config5"] = ppo
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # no destroy_process_group(): tearing a communicator down while CUDA graphs that captured its all-reduces are still alive has
+        # been seen to hang (2 x B200, torch 2.11 / NCCL 2.28); the ranks agree that everybody is done and leave
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
@@ -471,6 +494,7 @@ def main():
                     "under other_configs")
     ap.add_argument("--ppo", type=int, default=1, help="1: also run BASELINE config 5 (Anymal PPO, 8192 envs/GPU, NCCL gradient all-reduce when N > 1) "
                     "for a few iterations and report it under ppo_config5")
+    ap.add_argument("--ppo-timeout", type=int, default=240, help="seconds the learner leg may take before the line is printed without it")
     ap.add_argument("--task", default="Anymal", choices=sorted(TASKS), help="hot-path config to time (default: the headline Anymal config)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -50,3 +50,26 @@ def reduce_max(values, device=None):
 def aggregate_env_steps_per_sec(envs_per_rank: int, steps: int, elapsed_s_max: float, world_size: int) -> float:
     """Whole-job throughput: every rank's env-steps divided by the slowest rank's time."""
     return float(world_size) * envs_per_rank * steps / elapsed_s_max
+
+
+def shutdown(ppo=None, grace_s: float = 30.0):
+    """Leave a multi-rank run: release captured graphs, agree that everybody is done, destroy the process group -- and if the teardown
+    does not return within ``grace_s`` (seen with graphs that captured NCCL work), exit the process: all results are out by now."""
+    import os
+    import sys
+    import threading
+
+    import torch.distributed as dist
+
+    if ppo is not None and hasattr(ppo, "release_graphs"):
+        ppo.release_graphs()
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    t = threading.Timer(grace_s, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()

@@ -401,6 +401,16 @@ class PPO:
             fn()
         return g
 
+    def release_graphs(self):
+        """Drop the captured CUDA graphs (call before ``torch.distributed.destroy_process_group``: tearing a NCCL communicator down
+        while graphs that captured its all-reduces are alive has been seen to hang)."""
+        import gc
+
+        self._g_rollout = self._g_update = None
+        gc.collect()
+        if str(self.device) != "cpu":
+            torch.cuda.synchronize(self.device)
+
     # ------------------------------------------------------------------ checkpoints / evaluation
     def state_dict(self):
         """What rl_games keeps in its ``.pth`` files (``a2c_common.get_full_state_weights``): network, normalisers, optimiser."""

@@ -138,8 +138,9 @@ def main(argv=None):
                               "mean_episode_reward": log.mean_episode_reward[-1] if log.mean_episode_reward else None,
                               "wall_s": log.wall_s[-1] if log.wall_s else None, "checkpoint": ckpt}))
     if multi:
-        dist.barrier()
-        dist.destroy_process_group()
+        from .distributed import shutdown
+
+        shutdown(ppo)
 
 
 if __name__ == "__main__":

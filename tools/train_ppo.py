@@ -50,7 +50,9 @@ def main():
         dist.barrier()
     if info.rank != 0:
         if multi:
-            dist.destroy_process_group()
+            from isaacgymenv_b200.distributed import shutdown
+
+            shutdown(ppo)
         return
     out = {"task": args.task, "fused_rollout": bool(args.fused_rollout), "cuda_graphs": bool(args.cuda_graphs), "num_envs_per_gpu": args.num_envs, "n_gpus": info.world_size, "env_steps_all_gpus": [s * info.world_size for s in log.env_steps], "epochs": log.epochs, "env_steps": log.env_steps, "mean_episode_reward": log.mean_episode_reward,
            "mean_episode_length": log.mean_episode_length, "wall_s": log.wall_s, "gpu": torch.cuda.get_device_name(0),
@@ -60,7 +62,9 @@ def main():
             json.dump(out, fh)
     print(json.dumps({k: (v[-1] if isinstance(v, list) and v else v) for k, v in out.items()}))
     if multi:
-        dist.destroy_process_group()
+        from isaacgymenv_b200.distributed import shutdown
+
+        shutdown(ppo)
 
 
 if __name__ == "__main__":
