@@ -530,9 +530,16 @@ int b2g_gae_finish(const b2g_gae_args* args, void* stream);
 /* Hidden layer of the actor-critic MLP around the library GEMM: h = elu(z + bias) in place over the GEMM output z (rows x cols,
  * row-major, cols % 4 == 0), and the backward pass of that pair fused with the bias gradient: dz = dh * elu'(z) (from the stored
  * output h), dbias = column sums of dz (deterministic two-stage sum).  workspace: b2g_mlp_elu_backward_workspace_floats floats. */
-int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* stream);
-int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbias, float* partial, int rows, int cols, void* stream);
+int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* h_bf16 /* optional (rows, cols) bf16 copy of the output */, void* stream);
+int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbias, float* partial, int rows, int cols,
+                         void* dz_bf16 /* optional bf16 copy of dz */, void* stream);
 int b2g_mlp_elu_backward_workspace_floats(int rows, int cols);
+/* Backward of the two output heads on the last hidden layer h (rows x hidden): mu = h W_mu^T + b_mu (n_actions rows), value = h W_v^T + b_v.
+ * dh = dmu W_mu + dv W_v; dw_cat ((n_actions + 1) x (hidden + 1), row-major) = [dmu | dv]^T [h | 1]: rows 0..A-1 = d W_mu | d b_mu, row A =
+ * d W_v | d b_v.  One pass over the minibatch instead of two K = rows GEMMs with a dozen output rows, two bias reductions and an add. */
+int b2g_mlp_heads_backward(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
+                           float* dh, float* dw_cat, float* partial, void* stream);
+int b2g_mlp_heads_backward_workspace_floats(int rows, int hidden, int n_actions);
 
 /* Global-norm clipping + Adam on one flat parameter vector (torch.optim.Adam semantics: no weight decay, no amsgrad).  The effective
  * gradient is grad * grad_scale (1 / world size after an all-reduce SUM); *step is advanced by one. */

@@ -11,6 +11,7 @@
 //                       count in device memory so the pair replays from a CUDA graph while the adaptive-KL schedule changes the rate.
 //
 // Everything is deterministic: block partial sums are added in a fixed order, no floating-point atomics.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -139,7 +140,14 @@ __global__ void __launch_bounds__(kHeadBlock) k_ppo_head_finalize(b2g_ppo_head_a
 
 // ---- hidden layers of the actor-critic MLP: bias + ELU in one pass, and its backward fused with the bias gradient --------------------
 // forward: h = elu(z + b) in place over the GEMM output z (rows x cols, row-major)
-__global__ void __launch_bounds__(256) k_bias_elu(float* __restrict__ z, const float* __restrict__ b, size_t n4, int cols4) {
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, size_t i4, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned*>(&lo); u.y = *reinterpret_cast<unsigned*>(&hi);
+    reinterpret_cast<uint2*>(dst)[i4] = u;
+}
+
+__global__ void __launch_bounds__(256) k_bias_elu(float* __restrict__ z, const float* __restrict__ b, size_t n4, int cols4, __nv_bfloat16* __restrict__ h16) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<float4*>(z)[i];
         const float4 bb = reinterpret_cast<const float4*>(b)[i % cols4];
@@ -147,6 +155,7 @@ __global__ void __launch_bounds__(256) k_bias_elu(float* __restrict__ z, const f
         v.x = v.x > 0.0f ? v.x : expm1f(v.x); v.y = v.y > 0.0f ? v.y : expm1f(v.y);
         v.z = v.z > 0.0f ? v.z : expm1f(v.z); v.w = v.w > 0.0f ? v.w : expm1f(v.w);
         reinterpret_cast<float4*>(z)[i] = v;
+        if (h16) store_bf16x4(h16, i, v);      // bf16 copy for the next layer's weight-gradient GEMM
     }
 }
 
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(256) k_bias_elu(float* __restrict__ z, const f
 // gradient) per block of kColRows rows into partial[block][col].  Block = (cols / 4) column threads x row lanes.
 constexpr int kColRows = 256;
 __global__ void __launch_bounds__(256) k_elu_bwd_colsum(const float* __restrict__ dh, const float* __restrict__ h, float* __restrict__ dz,
-                                                        float* __restrict__ partial, int rows, int cols) {
+                                                        float* __restrict__ partial, int rows, int cols, __nv_bfloat16* __restrict__ dz16) {
     extern __shared__ float4 red4[];      // (row lanes, cols / 4)
     const int cols4 = cols >> 2;
     const int c4 = threadIdx.x % cols4, lane = threadIdx.x / cols4, lanes = blockDim.x / cols4;
@@ -168,6 +177,7 @@ __global__ void __launch_bounds__(256) k_elu_bwd_colsum(const float* __restrict_
             d.x = g.x * (o.x > 0.0f ? 1.0f : o.x + 1.0f); d.y = g.y * (o.y > 0.0f ? 1.0f : o.y + 1.0f);
             d.z = g.z * (o.z > 0.0f ? 1.0f : o.z + 1.0f); d.w = g.w * (o.w > 0.0f ? 1.0f : o.w + 1.0f);
             reinterpret_cast<float4*>(dz)[i] = d;
+            if (dz16) store_bf16x4(dz16, i, d);
             acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
         }
         red4[lane * cols4 + c4] = acc;
@@ -376,6 +386,53 @@ __global__ void __launch_bounds__(256) k_finish_batch(const float* __restrict__ 
     }
 }
 
+// ---- backward of the two output heads (mu: A rows, value: 1 row of W, O = A + 1 outputs of the last hidden layer h, width H) in one
+// pass over the minibatch: dh = dY W  (rows x H)  and  dWcat = dY^T [h | 1]  (O x (H + 1); the last column is the bias gradient).
+// A K = 32768 GEMM with 13 output rows is a poor fit for the library (66 us measured, tools/gemm_probe.py); here one block stages
+// kHeadRows rows of dY and h in shared memory, every thread owns a few entries of dWcat and half a row of dh, and block partial sums
+// are added in a fixed order by k_colsum_finalize.
+constexpr int kHeadRows = 64;
+__global__ void __launch_bounds__(256) k_heads_backward(const float* __restrict__ h, const float* __restrict__ dmu, const float* __restrict__ dv,
+                                                        const float* __restrict__ w_mu, const float* __restrict__ w_v, int rows, int H, int A,
+                                                        float* __restrict__ dh, float* __restrict__ partial) {
+    extern __shared__ float sm[];
+    const int O = A + 1;
+    float* s_h = sm;                            // (kHeadRows, H)
+    float* s_dy = s_h + kHeadRows * H;          // (kHeadRows, O)
+    float* s_w = s_dy + kHeadRows * O;          // (O, H)
+    const int r0 = blockIdx.x * kHeadRows;
+    const int nr = min(kHeadRows, rows - r0);
+    for (int i = threadIdx.x; i < kHeadRows * H; i += blockDim.x) {
+        const int r = i / H;
+        s_h[i] = r < nr ? h[(size_t)(r0 + r) * H + (i - r * H)] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < kHeadRows * O; i += blockDim.x) {
+        const int r = i / O, o = i - r * O;
+        s_dy[i] = r < nr ? (o < A ? dmu[(size_t)(r0 + r) * A + o] : dv[r0 + r]) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < O * H; i += blockDim.x) s_w[i] = i < A * H ? w_mu[i] : w_v[i - A * H];
+    __syncthreads();
+    // dWcat entries (o, c), c = H is the bias column
+    const int n_out = O * (H + 1);
+    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
+        const int o = e / (H + 1), c = e - o * (H + 1);
+        float acc = 0.0f;
+        if (c < H) {
+            for (int r = 0; r < kHeadRows; r++) acc += s_dy[r * O + o] * s_h[r * H + c];
+        } else {
+            for (int r = 0; r < kHeadRows; r++) acc += s_dy[r * O + o];
+        }
+        partial[(size_t)blockIdx.x * n_out + e] = acc;
+    }
+    // dh rows: thread t -> row t / 4, a quarter of the columns
+    for (int i = threadIdx.x; i < nr * H; i += blockDim.x) {
+        const int r = i / H, c = i - r * H;
+        float acc = 0.0f;
+        for (int o = 0; o < O; o++) acc += s_dy[r * O + o] * s_w[o * H + c];
+        dh[(size_t)(r0 + r) * H + c] = acc;
+    }
+}
+
 constexpr int kAdamBlock = 256;
 
 __global__ void __launch_bounds__(kAdamBlock) k_sq_partial(const float* __restrict__ g, int n, float scale, float* __restrict__ partial) {
@@ -440,17 +497,17 @@ int b2g_ppo_head(const b2g_ppo_head_args* a, void* stream) {
 
 int b2g_ppo_head_workspace_floats(int n_rows) { return ((n_rows + kHeadBlock - 1) / kHeadBlock) * kHeadCols; }
 
-int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* stream) {
+int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* h_bf16, void* stream) {
     if (!z || !bias || rows < 1 || cols < 4 || (cols & 3)) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_bias_elu: cols must be a positive multiple of 4");
     const size_t n4 = (size_t)rows * cols / 4;
     const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-    k_bias_elu<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, bias, n4, cols / 4);
+    k_bias_elu<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, bias, n4, cols / 4, reinterpret_cast<__nv_bfloat16*>(h_bf16));
     return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_bias_elu: launch failed");
 }
 
 int b2g_mlp_elu_backward_workspace_floats(int rows, int cols) { return ((rows + kColRows - 1) / kColRows) * cols; }
 
-int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbias, float* partial, int rows, int cols, void* stream) {
+int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbias, float* partial, int rows, int cols, void* dz_bf16, void* stream) {
     if (!dh || !h || !dz || !dbias || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_elu_backward: null argument");
     if (cols < 4 || (cols & 3) || cols > 1024) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_elu_backward: cols must be a multiple of 4, at most 1024");
     const int cols4 = cols / 4;
@@ -459,7 +516,7 @@ int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbia
     const int threads = lanes * cols4;          // <= 256
     const int blocks = (rows + kColRows - 1) / kColRows;
     cudaStream_t st = (cudaStream_t)stream;
-    k_elu_bwd_colsum<<<blocks, threads, sizeof(float4) * lanes * cols4, st>>>(dh, h, dz, partial, rows, cols);
+    k_elu_bwd_colsum<<<blocks, threads, sizeof(float4) * lanes * cols4, st>>>(dh, h, dz, partial, rows, cols, reinterpret_cast<__nv_bfloat16*>(dz_bf16));
     k_colsum_finalize<<<(cols + 127) / 128, 128, 0, st>>>(partial, blocks, cols, dbias);
     return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_elu_backward: launch failed");
 }
@@ -526,6 +583,27 @@ int b2g_gae_finish(const b2g_gae_args* a, void* stream) {
     k_finish_batch<<<fb, 256, 0, st>>>(a->ret, a->values, a->adv, a->value_mean, a->value_var, a->partial + 2 * blocks, blocks, (size_t)n, a->value_eps,
                                        a->f_ret, a->f_val, a->f_adv);
     return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_gae_finish: launch failed");
+}
+
+int b2g_mlp_heads_backward_workspace_floats(int rows, int hidden, int n_actions) {
+    return ((rows + kHeadRows - 1) / kHeadRows) * (n_actions + 1) * (hidden + 1);
+}
+
+int b2g_mlp_heads_backward(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
+                           float* dh, float* dw_cat, float* partial, void* stream) {
+    if (!h || !dmu || !dv || !w_mu || !w_v || !dh || !dw_cat || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_heads_backward: null argument");
+    if (hidden < 1 || hidden > 256 || n_actions < 1 || n_actions > kMaxAct) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_heads_backward: hidden <= 256, actions <= 24");
+    const int O = n_actions + 1;
+    const size_t smem = sizeof(float) * ((size_t)kHeadRows * (hidden + O) + (size_t)O * hidden);
+    static bool opted = false;
+    if (!opted) { cudaFuncSetAttribute(k_heads_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); opted = true; }
+    if (smem > 96 * 1024) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_heads_backward: tile does not fit shared memory");
+    const int blocks = (rows + kHeadRows - 1) / kHeadRows;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_heads_backward<<<blocks, 256, smem, st>>>(h, dmu, dv, w_mu, w_v, rows, hidden, n_actions, dh, partial);
+    const int n_out = O * (hidden + 1);
+    k_colsum_finalize<<<(n_out + 127) / 128, 128, 0, st>>>(partial, blocks, n_out, dw_cat);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_heads_backward: launch failed");
 }
 
 int b2g_adam_clip_step(const b2g_adam_args* a, void* stream) {

@@ -209,47 +209,108 @@ class RolloutKernels:
         _lib.check(self.lib.b2g_rollout_counter_advance(C.c_void_p(self.counter.data_ptr()), self._s()), "counter")
 
 
+def _mm_f32(a16, b16):
+    """bf16 x bf16 -> float32 (tensor cores, fp32 accumulation); older torch returns bf16, widened afterwards."""
+    try:
+        return torch.mm(a16, b16, out_dtype=torch.float32)
+    except TypeError:
+        return torch.mm(a16, b16).float()
+
+
 class _LinearELU(torch.autograd.Function):
-    """h = elu(x W^T + b): the GEMMs stay with torch / cuBLAS (TF32 tensor cores), bias + ELU is one in-place pass over the GEMM output,
-    and the backward pass fuses ELU' with the bias gradient (``b2g_mlp_bias_elu`` / ``b2g_mlp_elu_backward``) -- instead of add, elu,
-    elu_backward and a 32768-row column reduction as four separate torch kernels."""
+    """h = elu(x W^T + b): the GEMMs stay with torch / cuBLAS, bias + ELU is one in-place pass over the GEMM output, and the backward
+    pass fuses ELU' with the bias gradient (``b2g_mlp_bias_elu`` / ``b2g_mlp_elu_backward``) -- instead of add, elu, elu_backward and a
+    32768-row column reduction as four separate torch kernels.  With ``x16`` (a bf16 copy of the input) the weight gradient
+    dW = dZ^T X -- the K = minibatch GEMM, the slowest of the three -- runs on bf16 operands with float32 accumulation and output
+    (the reference trains with ``mixed_precision: True``, cfg/train/AnymalPPO.yaml:44); the two kernels write the bf16 copies of the
+    activations and of dZ on the way, so no separate cast pass exists.  Returns (h, bf16 copy of h or None)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, x16):
         lib = _lib.load()
         h = torch.mm(x, weight.t())
-        _lib.check(lib.b2g_mlp_bias_elu(C.c_void_p(h.data_ptr()), C.c_void_p(bias.data_ptr()), h.shape[0], h.shape[1], _stream(h.device)), "b2g_mlp_bias_elu")
-        ctx.save_for_backward(x, weight, h)
-        return h
+        h16 = torch.empty_like(h, dtype=torch.bfloat16) if x16 is not None else None
+        _lib.check(lib.b2g_mlp_bias_elu(C.c_void_p(h.data_ptr()), C.c_void_p(bias.data_ptr()), h.shape[0], h.shape[1],
+                                        C.c_void_p(h16.data_ptr()) if h16 is not None else None, _stream(h.device)), "b2g_mlp_bias_elu")
+        ctx.save_for_backward(x, weight, h, x16)
+        ctx.mark_non_differentiable(*([h16] if h16 is not None else []))
+        return h, h16
 
     @staticmethod
-    def backward(ctx, dh):
-        x, weight, h = ctx.saved_tensors
+    def backward(ctx, dh, _unused=None):
+        x, weight, h, x16 = ctx.saved_tensors
         lib = _lib.load()
         dh = dh.contiguous()
         rows, cols = h.shape
         dz = torch.empty_like(h)
+        dz16 = torch.empty_like(h, dtype=torch.bfloat16) if x16 is not None else None
         db = torch.empty(cols, device=h.device, dtype=h.dtype)
         ws = torch.empty(int(lib.b2g_mlp_elu_backward_workspace_floats(rows, cols)), device=h.device, dtype=h.dtype)
         _lib.check(lib.b2g_mlp_elu_backward(C.c_void_p(dh.data_ptr()), C.c_void_p(h.data_ptr()), C.c_void_p(dz.data_ptr()), C.c_void_p(db.data_ptr()),
-                                            C.c_void_p(ws.data_ptr()), rows, cols, _stream(h.device)), "b2g_mlp_elu_backward")
+                                            C.c_void_p(ws.data_ptr()), rows, cols, C.c_void_p(dz16.data_ptr()) if dz16 is not None else None,
+                                            _stream(h.device)), "b2g_mlp_elu_backward")
         dx = torch.mm(dz, weight) if ctx.needs_input_grad[0] else None
-        dw = torch.mm(dz.t(), x) if ctx.needs_input_grad[1] else None
-        return dx, dw, db
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = _mm_f32(dz16.t(), x16) if x16 is not None else torch.mm(dz.t(), x)
+        return dx, dw, db, None
 
 
-def linear_elu(x, weight, bias):
-    """``F.elu(F.linear(x, weight, bias))`` through the fused kernels (CUDA float32, width a multiple of 4)."""
+def _protos():
     lib = _lib.load()
     if not getattr(lib, "_b2g_mlp_protos", False):
-        lib.b2g_mlp_bias_elu.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        vp = C.c_void_p
+        lib.b2g_mlp_bias_elu.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
         lib.b2g_mlp_bias_elu.restype = C.c_int
-        lib.b2g_mlp_elu_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.b2g_mlp_elu_backward.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
         lib.b2g_mlp_elu_backward.restype = C.c_int
         lib.b2g_mlp_elu_backward_workspace_floats.argtypes = [C.c_int, C.c_int]
         lib.b2g_mlp_elu_backward_workspace_floats.restype = C.c_int
+        lib.b2g_mlp_heads_backward.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+        lib.b2g_mlp_heads_backward.restype = C.c_int
+        lib.b2g_mlp_heads_backward_workspace_floats.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.b2g_mlp_heads_backward_workspace_floats.restype = C.c_int
         lib._b2g_mlp_protos = True
-    return _LinearELU.apply(x.contiguous(), weight, bias)
+    return lib
+
+
+def linear_elu(x, weight, bias, x16=None):
+    """``F.elu(F.linear(x, weight, bias))`` through the fused kernels (CUDA float32, width a multiple of 4).  Returns (h, h16): h16 is a
+    bf16 copy of h when a bf16 copy of the input (``x16``) was given -- pass it on to the next layer."""
+    _protos()
+    return _LinearELU.apply(x.contiguous(), weight, bias, x16)
+
+
+class _Heads(torch.autograd.Function):
+    """(mu, value) = (h W_mu^T + b_mu, h W_v^T + b_v); the backward of both heads is one kernel (``b2g_mlp_heads_backward``)."""
+
+    @staticmethod
+    def forward(ctx, h, w_mu, b_mu, w_v, b_v):
+        mu = torch.addmm(b_mu, h, w_mu.t())
+        v = torch.addmm(b_v, h, w_v.t()).squeeze(-1)
+        ctx.save_for_backward(h, w_mu, w_v)
+        return mu, v
+
+    @staticmethod
+    def backward(ctx, dmu, dv):
+        h, w_mu, w_v = ctx.saved_tensors
+        lib = _lib.load()
+        rows, hid = h.shape
+        A = w_mu.shape[0]
+        dmu, dv = dmu.contiguous(), dv.contiguous()
+        dh = torch.empty_like(h)
+        cat = torch.empty(A + 1, hid + 1, device=h.device, dtype=h.dtype)
+        ws = torch.empty(int(lib.b2g_mlp_heads_backward_workspace_floats(rows, hid, A)), device=h.device, dtype=h.dtype)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.b2g_mlp_heads_backward(p(h), p(dmu), p(dv), p(w_mu), p(w_v), rows, hid, A, p(dh), p(cat), p(ws), _stream(h.device)),
+                   "b2g_mlp_heads_backward")
+        return dh, cat[:A, :hid], cat[:A, hid], cat[A:, :hid], cat[A:, hid]
+
+
+def heads(h, w_mu, b_mu, w_v, b_v):
+    """Both output heads of the actor-critic on the last hidden layer (shared-trunk networks: one ``h`` feeds both)."""
+    _protos()
+    return _Heads.apply(h.contiguous(), w_mu, b_mu, w_v, b_v)
 
 
 class FlatParameters:

@@ -61,25 +61,35 @@ class ActorCritic(nn.Module):
 
         self.separate = bool(separate)
         self.fused_layers = False      # set by PPO(fused_update=True): hidden layers through learning/fused_update.linear_elu in training mode
+        self.bf16_wgrad = False        # weight-gradient GEMMs on bf16 operands (fp32 accumulate / output): PPOConfig.mixed_precision
         self.trunk, last = mlp()
         self.critic_trunk = mlp()[0] if self.separate else None
         self.mu = nn.Linear(last, num_actions)
         self.value = nn.Linear(last, 1)
         self.log_std = nn.Parameter(torch.zeros(num_actions))      # sigma_init const 0 -> std 1, fixed_sigma (state independent)
 
-    def _tower(self, seq, x):
-        if not (self.fused_layers and x.is_cuda and torch.is_grad_enabled()):
-            return seq(x)
+    def _tower(self, seq, x, x16):
         from .fused_update import linear_elu
 
         for m in seq:
             if isinstance(m, nn.Linear):
-                x = linear_elu(x, m.weight, m.bias)
+                x, x16 = linear_elu(x, m.weight, m.bias, x16)
         return x
 
     def forward(self, obs):
-        h = self._tower(self.trunk, obs)
-        hv = self._tower(self.critic_trunk, obs) if self.separate else h
+        if self.fused_layers and obs.is_cuda and torch.is_grad_enabled():
+            # training pass through the library's kernels around the cuBLAS GEMMs (learning/fused_update.py)
+            from .fused_update import heads
+
+            x16 = obs.to(torch.bfloat16) if self.bf16_wgrad else None
+            h = self._tower(self.trunk, obs, x16)
+            if not self.separate:
+                mu, v = heads(h, self.mu.weight, self.mu.bias, self.value.weight, self.value.bias)
+                return mu, self.log_std.expand(obs.shape[0], -1), v
+            hv = self._tower(self.critic_trunk, obs, x16)
+            return self.mu(h), self.log_std.expand(obs.shape[0], -1), self.value(hv).squeeze(-1)
+        h = self.trunk(obs)
+        hv = self.critic_trunk(obs) if self.separate else h
         return self.mu(h), self.log_std.expand(obs.shape[0], -1), self.value(hv).squeeze(-1)
 
 
@@ -120,6 +130,8 @@ class PPOConfig:
     bounds_loss_coef: float = 0.001
     units: tuple = (256, 128, 64)
     separate: bool = False      # network.separate of the train yaml: separate actor / critic towers
+    mixed_precision: bool = False   # config.mixed_precision of the train yaml (True in every hot-path yaml): with fused_update, the K = minibatch
+                                    # weight-gradient GEMMs take bf16 operands (fp32 accumulation and output); everything else stays fp32 / TF32
     reward_scale: float = 1.0   # config.reward_shaper.scale_value (Cartpole: 0.1)
     max_epochs: int = 1000
     save_frequency: int = 0     # config.save_frequency: checkpoint every so many epochs (0 = only at the end)
@@ -182,7 +194,8 @@ class PPO:
 
                 world = dist.get_world_size()
             self.flatp = FlatParameters(self.model)
-            self.model.fused_layers = all(u % 4 == 0 and u <= 1024 for u in cfg.units)
+            self.model.fused_layers = all(u % 4 == 0 and u <= 1024 for u in cfg.units) and cfg.units[-1] <= 256
+            self.model.bf16_wgrad = bool(cfg.mixed_precision)
             self.opt = FusedClipAdam(self.flatp, lr=self.lr_t, eps=1e-8, max_grad_norm=cfg.grad_norm, grad_scale=1.0 / world)
         else:
             self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t if graph_update else cfg.learning_rate, eps=1e-8,

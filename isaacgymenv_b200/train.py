@@ -81,7 +81,7 @@ def ppo_config_from_train_cfg(tc: Dict[str, Any], max_iterations=None):
     units = tuple(tc["params"]["network"]["mlp"]["units"])
     separate = bool(tc["params"]["network"].get("separate", False))
     shaper = c.get("reward_shaper") or {}
-    return PPOConfig(separate=separate, reward_scale=float(shaper.get("scale_value", 1.0)), save_frequency=int(c.get("save_frequency", 0) or 0),
+    return PPOConfig(mixed_precision=bool(c.get("mixed_precision", False)), separate=separate, reward_scale=float(shaper.get("scale_value", 1.0)), save_frequency=int(c.get("save_frequency", 0) or 0),
                      horizon_length=int(c["horizon_length"]), minibatch_size=int(c["minibatch_size"]), mini_epochs=int(c["mini_epochs"]),
                      gamma=float(c["gamma"]), tau=float(c["tau"]), e_clip=float(c["e_clip"]), entropy_coef=float(c.get("entropy_coef", 0.0)),
                      learning_rate=float(c["learning_rate"]), kl_threshold=float(c.get("kl_threshold", 0.008)), grad_norm=float(c.get("grad_norm", 1.0)),

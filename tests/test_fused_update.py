@@ -190,7 +190,8 @@ def test_linear_elu_matches_torch(rows, k, cols):
     up = torch.randn(rows, cols, device=dev, generator=g)
     xa, wa, ba = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
     xb, wb, bb = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
-    ha = linear_elu(xa, wa, ba)
+    ha, none16 = linear_elu(xa, wa, ba)
+    assert none16 is None
     hb = torch.nn.functional.elu(torch.nn.functional.linear(xb, wb, bb))
     (ha * up).sum().backward()
     (hb * up).sum().backward()
@@ -201,7 +202,7 @@ def test_linear_elu_matches_torch(rows, k, cols):
         np.testing.assert_allclose(a.cpu().numpy(), bref.cpu().numpy(), rtol=1e-4, atol=2e-5 * scale, err_msg=name)
     # the first layer's input needs no gradient: none is computed
     xc = x.clone()
-    hc = linear_elu(xc, wa.detach().requires_grad_(), ba.detach().requires_grad_())
+    hc, _ = linear_elu(xc, wa.detach().requires_grad_(), ba.detach().requires_grad_())
     hc.sum().backward()
     assert xc.grad is None
 
@@ -282,3 +283,61 @@ def test_rollout_kernels_fill_the_buffers_like_the_torch_rollout(task, separate,
     assert float(ppo.val_rms.mean) == pytest.approx(float(chk.mean), rel=1e-3, abs=1e-4) and float(ppo.val_rms.var) == pytest.approx(float(chk.var), rel=1e-3)
     assert set(torch.unique(ppo.b_done).tolist()) <= {0.0, 1.0} and float(ppo.fin[2]) >= 0
     assert torch.isfinite(ppo.f_adv).all() and torch.isfinite(ppo.b_rew).all()
+
+
+@pytest.mark.gpu
+def test_linear_elu_bf16_weight_gradient():
+    """mixed_precision: the weight-gradient GEMM on bf16 copies written by the two kernels (no cast pass): float32 accumulation over the
+    32768 rows, so the result is within bf16 input rounding of the float32 one; h, dx and db are untouched float32."""
+    from isaacgymenv_b200.learning.fused_update import linear_elu
+
+    dev = "cuda:0"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(32768, 48, device=dev, generator=g)
+    w1, b1 = torch.randn(256, 48, device=dev, generator=g) / 7, 0.1 * torch.randn(256, device=dev, generator=g)
+    w2, b2 = torch.randn(128, 256, device=dev, generator=g) / 16, 0.1 * torch.randn(128, device=dev, generator=g)
+    up = torch.randn(32768, 128, device=dev, generator=g)
+    outs = []
+    for use16 in (False, True):
+        p = [t.clone().requires_grad_() for t in (w1, b1, w2, b2)]
+        x16 = x.to(torch.bfloat16) if use16 else None
+        h1, h16 = linear_elu(x, p[0], p[1], x16)
+        h2, h216 = linear_elu(h1, p[2], p[3], h16)
+        assert (h16 is not None) == use16 and (h216 is not None) == use16
+        if use16:
+            assert h16.dtype == torch.bfloat16 and torch.allclose(h16.float(), h1, rtol=1e-2, atol=1e-2)
+        (h2 * up).sum().backward()
+        outs.append([h2.detach()] + [t.grad for t in p])
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0])                                  # forward identical
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-4) and torch.allclose(outs[0][4], outs[1][4], rtol=1e-5, atol=1e-4)   # db float32
+    for i in (1, 3):                                                            # dW1, dW2
+        ref, got = outs[0][i], outs[1][i]
+        assert (got - ref).norm().item() < 1e-2 * ref.norm().item(), ((got - ref).norm().item(), ref.norm().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,hid,A", [(32768, 64, 12), (1000, 128, 18), (70, 64, 1)])
+def test_heads_backward_kernel_matches_torch(rows, hid, A):
+    from isaacgymenv_b200.learning.fused_update import heads
+
+    dev = "cuda:0"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device=dev).manual_seed(rows)
+    h = torch.randn(rows, hid, device=dev, generator=g)
+    wm, bm = torch.randn(A, hid, device=dev, generator=g) / 8, torch.randn(A, device=dev, generator=g)
+    wv, bv = torch.randn(1, hid, device=dev, generator=g) / 8, torch.randn(1, device=dev, generator=g)
+    um, uv = torch.randn(rows, A, device=dev, generator=g), torch.randn(rows, device=dev, generator=g)
+    a = [t.clone().requires_grad_() for t in (h, wm, bm, wv, bv)]
+    b = [t.clone().requires_grad_() for t in (h, wm, bm, wv, bv)]
+    mu_a, v_a = heads(*a)
+    mu_b, v_b = torch.nn.functional.linear(b[0], b[1], b[2]), torch.nn.functional.linear(b[0], b[3], b[4]).squeeze(-1)
+    ((mu_a * um).sum() + (v_a * uv).sum()).backward()
+    ((mu_b * um).sum() + (v_b * uv).sum()).backward()
+    torch.cuda.synchronize()
+    assert torch.allclose(mu_a, mu_b, rtol=1e-5, atol=1e-5) and torch.allclose(v_a, v_b, rtol=1e-5, atol=1e-5)
+    for x, y, name in zip(a, b, ("dh", "dw_mu", "db_mu", "dw_v", "db_v")):
+        scale = float(y.grad.abs().max())
+        assert x.grad.shape == y.grad.shape, name
+        assert torch.allclose(x.grad, y.grad, rtol=1e-4, atol=2e-5 * scale), (name, float((x.grad - y.grad).abs().max()), scale)
