@@ -164,7 +164,8 @@ class Terrain:
         self.type = cfg["terrainType"]
         if self.type in ("none", "plane"):
             return
-        self.rng = np.random.default_rng(seed)
+        # seed=None draws from numpy's global generator, exactly where the reference's Terrain draws from (tests compare the two classes)
+        self.rng = np.random.default_rng(seed) if seed is not None else np.random
         self.horizontal_scale = 0.1
         self.vertical_scale = 0.005
         self.border_size = 20

@@ -160,3 +160,30 @@ def test_reference_anymal_and_cartpole_step_on_libb200gym():
     for k in range(30):
         o, r, d, e = cart.step(2 * torch.rand(32, 1, device="cuda:0", generator=g) - 1)
     assert o["obs"].shape == (32, 4) and torch.isfinite(o["obs"]).all() and torch.isfinite(r).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("curriculum", [True, False])
+def test_terrain_grid_equals_the_references_terrain_class(curriculum):
+    """The reference's own ``Terrain`` class (tasks/anymal_terrain.py:543-673), executed unmodified with ``isaacgym.terrain_utils`` =
+    this package's sub-terrain builders, against this package's ``Terrain``: same tile layout, curriculum mapping (column -> type,
+    row -> difficulty), border, height samples and environment origins, value for value, from the same numpy random stream.  (The
+    sub-terrain builders themselves restate Isaac Gym's published ``terrain_utils`` -- that module is not in the reference tree.)"""
+    import numpy as np
+
+    import isaacgymenv_b200 as b2g
+    from isaacgymenv_b200.terrain import Terrain
+
+    b2g.install_isaacgym_shim(REF)
+    ref_mod = importlib.import_module("isaacgymenvs.tasks.anymal_terrain")
+    cfg = dict(terrainType="trimesh", curriculum=curriculum, mapLength=8.0, mapWidth=8.0, numLevels=4, numTerrains=10,
+               terrainProportions=[0.1, 0.1, 0.35, 0.25, 0.2], slopeTreshold=0.5)
+    np.random.seed(7)
+    ref = ref_mod.Terrain(cfg, 256)
+    np.random.seed(7)
+    ours = Terrain(cfg, 256, seed=None)
+    assert ref.height_field_raw.shape == ours.height_field_raw.shape == (4 * 80 + 400, 10 * 80 + 400)
+    assert np.array_equal(ref.height_field_raw, ours.height_field_raw)
+    assert np.array_equal(ref.env_origins, ours.env_origins)
+    assert (ref.tot_rows, ref.tot_cols, ref.border, ref.env_rows, ref.env_cols) == (ours.tot_rows, ours.tot_cols, ours.border, ours.env_rows, ours.env_cols)
+    assert np.abs(ours.height_field_raw).max() > 20 and len(np.unique(ours.env_origins[:, :, 2])) > 3
