@@ -1,0 +1,41 @@
+#!/bin/bash
+# round-2 refresh: every number DESIGN.md quotes, one GPU
+out=gpurun_out
+python -m pytest tests -m gpu -q 2>&1 | tail -30 > $out/r02n_tests.log; tail -3 $out/r02n_tests.log
+python bench.py > $out/r02n_bench_plain.json 2> $out/r02n_bench_plain.err
+python bench.py --impl reference --steps 20 --warmup 5 > $out/r02n_bench_reference.json 2>/dev/null
+python bench.py --steps 20 --warmup 5 > $out/r02n_bench_driver.json 2>/dev/null
+for t in Hound Cartpole AnymalTerrain HoundTerrain UsefulHound Houndarm; do
+  python bench.py --task $t --steps 300 --warmup 30 --ppo 0 > $out/r02n_bench_$t.json 2>/dev/null
+done
+echo "[" > $out/r02n_sweep_envs.json
+first=1
+for n in 1024 2048 4096 8192 16384 32768 65536; do
+  [ $first = 1 ] || echo "," >> $out/r02n_sweep_envs.json
+  first=0
+  python bench.py --num-envs $n --steps 300 --warmup 30 --ppo 0 2>/dev/null | tail -n 1 >> $out/r02n_sweep_envs.json
+done
+echo "]" >> $out/r02n_sweep_envs.json
+python tools/train_ppo.py --task Anymal --epochs 1000 --tf32 --cuda-graphs --fused-rollout --fused-update --yaml --out $out/r02n_ppo_anymal_fused_update_1000epochs.json > $out/r02n_ppo_anymal.log 2>&1
+timeout 600 python tools/train_ppo.py --task AnymalTerrain --epochs 300 --tf32 --cuda-graphs --fused-rollout --fused-update --yaml --out $out/r02n_ppo_anymal_terrain_separate_300epochs.json > $out/r02n_ppo_at.log 2>&1
+timeout 300 python tools/train_ppo.py --task Cartpole --num-envs 512 --epochs 100 --tf32 --cuda-graphs --fused-update --yaml --out $out/r02n_ppo_cartpole_100epochs.json > $out/r02n_ppo_cp.log 2>&1
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/r02n_bench_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split("/")[-1], f"{d['ms_per_step']*1e3:.1f}us {d['value']/1e6:.2f}M/s warm {d.get('value_warm_l2',0)/1e6:.1f} e2e {d['e2e'].get('ms_per_step',0)*1e3:.1f}us {d['e2e']['value']/1e6:.2f}M/s", d.get("contact_stats"))
+    except Exception as e:
+        print(f, "ERR", e)
+try:
+    for d in json.load(open("gpurun_out/r02n_sweep_envs.json")):
+        print("sweep", d["config"]["envs_per_gpu"], f"{d['ms_per_step']*1e3:.1f}us {d['value']/1e6:.1f}M/s e2e {d['e2e']['value']/1e6:.1f}M/s")
+except Exception as e:
+    print("sweep ERR", e)
+for name in ("anymal_fused_update_1000epochs", "anymal_terrain_separate_300epochs", "cartpole_100epochs"):
+    try:
+        d = json.load(open(f"gpurun_out/r02n_ppo_{name}.json"))
+        print("ppo", name, d["mean_episode_reward"][-3:], d["mean_episode_length"][-1], d["wall_s"][-1], d["env_steps"][-1])
+    except Exception as e:
+        print("ppo ERR", name, e)
+PY

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--fused-adam", action="store_true")
     ap.add_argument("--cuda-graphs", action="store_true", help="capture the rollout and the minibatch update as CUDA graphs")
     ap.add_argument("--fused-rollout", action="store_true", help="evaluate the policy in the rollout with the fused tcgen05 kernel")
+    ap.add_argument("--fused-update", action="store_true", help="loss head / bias+ELU / clip+Adam / rollout bookkeeping through the library's kernels")
+    ap.add_argument("--yaml", action="store_true", help="hyper-parameters and network from cfg/train/<Task>PPO.yaml (separate towers, mixed precision, ...)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -43,8 +45,13 @@ def main():
         cfg = PPOConfig(units=(256, 128, 64), horizon_length=32, minibatch_size=16384, mini_epochs=5)
     if args.task == "Cartpole":
         cfg = PPOConfig(units=(32, 32), horizon_length=16, minibatch_size=8192, mini_epochs=8)
+    if args.yaml:
+        from isaacgymenv_b200.train import load_train_config, ppo_config_from_train_cfg
+
+        cfg = ppo_config_from_train_cfg(load_train_config(f"{args.task}PPO"))
     cfg.tf32, cfg.fused_adam = args.tf32, args.fused_adam
-    ppo = PPO(env, cfg, multi_gpu=multi, seed=args.seed + info.rank, fused_rollout=args.fused_rollout, cuda_graphs=args.cuda_graphs)
+    ppo = PPO(env, cfg, multi_gpu=multi, seed=args.seed + info.rank, fused_rollout=args.fused_rollout, cuda_graphs=args.cuda_graphs,
+              fused_update=args.fused_update and env.num_acts <= 24)
     log = ppo.train(max_epochs=args.epochs, log_every=10, verbose=info.rank == 0)
     if multi:
         dist.barrier()
@@ -54,7 +61,8 @@ def main():
 
             shutdown(ppo)
         return
-    out = {"task": args.task, "fused_rollout": bool(args.fused_rollout), "cuda_graphs": bool(args.cuda_graphs), "num_envs_per_gpu": args.num_envs, "n_gpus": info.world_size, "env_steps_all_gpus": [s * info.world_size for s in log.env_steps], "epochs": log.epochs, "env_steps": log.env_steps, "mean_episode_reward": log.mean_episode_reward,
+    out = {"task": args.task, "fused_rollout": bool(args.fused_rollout), "cuda_graphs": bool(args.cuda_graphs), "fused_update": bool(args.fused_update), "yaml": bool(args.yaml),
+           "separate": bool(cfg.separate), "mixed_precision": bool(cfg.mixed_precision), "num_envs_per_gpu": args.num_envs, "n_gpus": info.world_size, "env_steps_all_gpus": [s * info.world_size for s in log.env_steps], "epochs": log.epochs, "env_steps": log.env_steps, "mean_episode_reward": log.mean_episode_reward,
            "mean_episode_length": log.mean_episode_length, "wall_s": log.wall_s, "gpu": torch.cuda.get_device_name(0),
            "env_steps_per_sec_incl_learner": (log.env_steps[-1] * info.world_size / log.wall_s[-1]) if log.wall_s else None}
     if args.out:
