@@ -58,6 +58,7 @@ namespace {
 struct Variant {
     int lanes, nl;
     bool fixed;
+    bool seg = false;      // <8,3>: chains cut into pieces of at most three links (DevModel::seg_*)
 };
 
 Variant pick_variant(const b2g_model& m) {
@@ -68,6 +69,13 @@ Variant pick_variant(const b2g_model& m) {
     // the specialised variants assume FULL chains (every lane has exactly NL links)
     if (m.fixed_base && m.n_chains == 1 && maxlen == 2) return {1, 2, true};
     if (!m.fixed_base && m.n_chains == 4 && maxlen == 3 && minlen == 3) return {4, 3, false};
+    // B2G_SEGMENTS=1: chains cut into pieces of at most three links that own a lane each (<8,3>, link state in registers) when the
+    // pieces fit the eight lanes.  Parity-green and measured: 438 us per UsefulHound step against 397 us for the
+    // whole-chain kernels -- the recursions stay serial over six links -- so it is an opt-in experiment, not the default.
+    int pieces = m.n_chains;
+    for (int c = 0; c < m.n_chains; c++) pieces += m.chain_len[c] > kSegLinks ? 1 : 0;
+    const char* seg = getenv("B2G_SEGMENTS");
+    if (seg && seg[0] == '1' && !m.fixed_base && m.n_chains > 0 && pieces <= B2G_MAX_CHAINS) return {8, 3, false, true};
     return {8, 6, m.fixed_base != 0};
 }
 
@@ -75,7 +83,7 @@ Variant pick_variant(const b2g_model& m) {
 // kernels
 // ------------------------------------------------------------------------------------------------
 template <int LANES>
-__device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int& env, int& lane, bool& valid, ScratchStrided& sc, float*& bf, int nd, int slots) {
+__device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int& env, int& lane, bool& valid, ScratchStrided& sc, float*& bf, int nd, int slots, int nstore = 0) {
     const int tid = threadIdx.x;
     constexpr int EPW = 32 / LANES / kSparse, EPB = EnvsPerBlock<LANES>::value;
     const int wl = tid & 31;
@@ -96,6 +104,8 @@ __device__ __forceinline__ void thread_ids(int n_envs, int nb, float* smem, int&
     bf = smem + kBlock * slots * CF_COUNT + grp * nb * 3;     // one accumulator per lane group, idle groups included
     // link store of the rolled long-chain variants (b2g_dynamics.cuh::links_in_shared): one LinkData per DOF per lane group
     sc.links = smem + ((kBlock * slots * CF_COUNT + (kBlock / LANES) * nb * 3 + 3) & ~3) + link_store_floats(grp, nd);     // 16-byte aligned
+    // ancestor store of the segment variant (b2g_dynamics.cuh::kAncFloats per piece that has a child), same 16-byte aligned base
+    sc.anc = smem + ((kBlock * slots * CF_COUNT + (kBlock / LANES) * nb * 3 + 3) & ~3) + (kLinksShared ? link_store_floats(kBlock / LANES, nd) : 0) + grp * nstore * kAncFloats;
 }
 
 // ---- host mirror (b2g_task_step_host): the step's outputs (obs_clamped | rew | reset | timeout, the b2g_task_host_layout arena)
@@ -162,7 +172,7 @@ template <int LANES, int NL, bool FIXED, bool HF>
 __global__ void __launch_bounds__(kBlock) k_simulate(SimArgs A) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts, A.M->n_seg_store);
     simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, valid, sc, bf);
 }
 
@@ -173,7 +183,7 @@ template <int LANES, int NL, bool HF, int MINB = 1>
 __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArgs T, HostMirror H) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts, A.M->n_seg_store);
     anymal_step_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
     if (H.dst) {
         constexpr int EPB = EnvsPerBlock<LANES>::value;
@@ -217,7 +227,7 @@ template <int LANES, int NL, bool HF>
 __global__ void __launch_bounds__(kBlock) k_terrain_phys(SimArgs A, TerrainArgs T) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts, A.M->n_seg_store);
     terrain_phys_thread<LANES, NL, HF>(A, T, env, lane, valid, sc, bf);
     // curriculum scalar for ALL resetting envs (reference quirk: torch.norm without dim, anymal_terrain.py:432): the last
     // block to arrive sums the N values in a fixed order (kBlock strided partial sums, pairwise tree) -> deterministic
@@ -307,7 +317,7 @@ template <int LANES, int NL>
 __global__ void __launch_bounds__(kBlock) k_anymal_reset_all(SimArgs A, TaskArgs T) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts, A.M->n_seg_store);
     anymal_reset_all_thread<LANES, NL>(A, T, env, lane, valid);
 }
 
@@ -315,10 +325,10 @@ template <int LANES, int NL, bool FIXED>
 __global__ void __launch_bounds__(kBlock) k_probe(SimArgs A, float* qdd, float* a0) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
-    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
+    thread_ids<LANES>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts, A.M->n_seg_store);
     const DevModel* M = A.M;
-    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
-    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    int len, d0;
+    lane_span<LANES, NL>(M, lane, len, d0);
     LaneState<NL> st;
     load_state<NL>(A, env, len, d0, st);
 #pragma unroll
@@ -398,6 +408,7 @@ struct b2g_sim {
     float root_pose[7] = {0, 0, 0, 0, 0, 0, 1};
     Variant v{4, 3, false};
     DevModel* d_model = nullptr;
+    int n_seg_store = 0;      // pieces with a child (DevModel::n_seg_store): sizes the segment variant's shared-memory ancestor store
     float* t[B2G_T_COUNT] = {nullptr};
     // task
     bool has_task = false;
@@ -444,7 +455,8 @@ namespace {
 size_t smem_bytes(const b2g_sim* s) {
     const int epb = kBlock / s->v.lanes;
     const size_t links = kLinksShared && s->v.nl > 3 ? 4 + link_store_floats(epb, s->model.n_dof) : 0;     // links_in_shared variants
-    return sizeof(float) * ((size_t)kBlock * contact_slots(s->params) * CF_COUNT + (size_t)epb * s->model.n_bodies * 3 + links);
+    const size_t anc = s->v.seg ? 4 + (size_t)epb * s->n_seg_store * kAncFloats : 0;     // segment variant's ancestor store
+    return sizeof(float) * ((size_t)kBlock * contact_slots(s->params) * CF_COUNT + (size_t)epb * s->model.n_bodies * 3 + links + anc);
 }
 
 int grid_size(const b2g_sim* s) {
@@ -513,6 +525,7 @@ int upload_model(b2g_sim* s) {
     if (!s->d_model) e = cudaMalloc(&s->d_model, sizeof(DevModel));
     if (e == cudaSuccess) e = cudaMemcpy(s->d_model, h, sizeof(DevModel), cudaMemcpyHostToDevice);
     const float rmax = max_link_radius(*h);
+    s->n_seg_store = h->n_seg_store;
     free(h);
     if (e != cudaSuccess) return fail(B2G_ERR_CUDA, "model upload: %s", cudaGetErrorString(e));
     if (rmax != s->link_rmax || (s->has_hf && !s->d_hfc)) {
@@ -583,6 +596,7 @@ int launch_simulate(b2g_sim* s, cudaStream_t st) {
     if (s->v.lanes == 1) k_simulate<1, 2, true, false><<<grid, kBlock, sm, st>>>(A);
     else if (s->v.lanes == 4) { if (hf) k_simulate<4, 3, false, true><<<grid, kBlock, sm, st>>>(A); else k_simulate<4, 3, false, false><<<grid, kBlock, sm, st>>>(A); }
     else if (s->v.fixed) k_simulate<8, 6, true, false><<<grid, kBlock, sm, st>>>(A);
+    else if (s->v.seg) { if (hf) k_simulate<8, 3, false, true><<<grid, kBlock, sm, st>>>(A); else k_simulate<8, 3, false, false><<<grid, kBlock, sm, st>>>(A); }
     else { if (hf) k_simulate<8, 6, false, true><<<grid, kBlock, sm, st>>>(A); else k_simulate<8, 6, false, false><<<grid, kBlock, sm, st>>>(A); }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -614,6 +628,9 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         if (s->v.lanes == 4) {
             if (s->has_hf) k_terrain_phys<4, 3, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<4, 3, false><<<grid, kBlock, sm, st>>>(A, R);
             if (post_only != 2) k_terrain_post<4, 3><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R, H3);
+        } else if (s->v.seg) {
+            if (s->has_hf) k_terrain_phys<8, 3, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<8, 3, false><<<grid, kBlock, sm, st>>>(A, R);
+            if (post_only != 2) k_terrain_post<8, 3><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R, H3);
         } else {
             if (s->has_hf) k_terrain_phys<8, 6, true><<<grid, kBlock, sm, st>>>(A, R); else k_terrain_phys<8, 6, false><<<grid, kBlock, sm, st>>>(A, R);
             if (post_only != 2) k_terrain_post<8, 6><<<(s->n_envs + kPostEnvs - 1) / kPostEnvs, kPostBlock, 0, st>>>(A, R, H3);
@@ -648,6 +665,7 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
         else if (grid > 4 * s->n_sm && sm * 6 <= 200 * 1024) k_anymal_step<4, 3, false, 6><<<grid, kBlock, sm, st>>>(A, T, H);     // more than one wave and six blocks' scratch fit an SM: occupancy build
         else k_anymal_step<4, 3, false><<<grid, kBlock, sm, st>>>(A, T, H);
     }
+    else if (s->v.seg) { if (s->has_hf) k_anymal_step<8, 3, true><<<grid, kBlock, sm, st>>>(A, T, H); else k_anymal_step<8, 3, false><<<grid, kBlock, sm, st>>>(A, T, H); }
     else { if (s->has_hf) k_anymal_step<8, 6, true><<<grid, kBlock, sm, st>>>(A, T, H); else k_anymal_step<8, 6, false><<<grid, kBlock, sm, st>>>(A, T, H); }
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -830,6 +848,13 @@ int b2g_sim_prepare(b2g_sim* s) {
         cudaFuncSetAttribute(k_simulate<1, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_simulate<4, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_simulate<4, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_simulate<8, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_simulate<8, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_anymal_step<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_anymal_step<8, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_terrain_phys<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_terrain_phys<8, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_probe<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_simulate<8, 6, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_simulate<8, 6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_simulate<8, 6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
@@ -952,6 +977,7 @@ int b2g_sim_forward_dynamics(b2g_sim* s, float* qdd, float* a0, void* stream) {
         if (s->v.lanes == 1) k_probe<1, 2, true><<<grid, kBlock, sm, st>>>(A, qdd, a0);
         else if (s->v.lanes == 4) k_probe<4, 3, false><<<grid, kBlock, sm, st>>>(A, qdd, a0);
         else if (s->v.fixed) k_probe<8, 6, true><<<grid, kBlock, sm, st>>>(A, qdd, a0);
+        else if (s->v.seg) k_probe<8, 3, false><<<grid, kBlock, sm, st>>>(A, qdd, a0);
         else k_probe<8, 6, false><<<grid, kBlock, sm, st>>>(A, qdd, a0);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1212,6 +1238,7 @@ int b2g_task_anymal_reset_all(b2g_sim* s, void* stream) {
         const TaskArgs T = make_task_args(s, nullptr);
         const int grid = grid_size(s);
         if (s->v.lanes == 4) k_anymal_reset_all<4, 3><<<grid, kBlock, 0, (cudaStream_t)stream>>>(A, T);
+        else if (s->v.seg) k_anymal_reset_all<8, 3><<<grid, kBlock, 0, (cudaStream_t)stream>>>(A, T);
         else k_anymal_reset_all<8, 6><<<grid, kBlock, 0, (cudaStream_t)stream>>>(A, T);
         s->launches++;
         CUDA_TRY(cudaGetLastError());

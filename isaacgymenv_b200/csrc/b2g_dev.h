@@ -31,6 +31,16 @@ struct DevModel {
     int chain_len[B2G_MAX_CHAINS];
     int root_cp_start[B2G_MAX_CHAINS];   // root-link candidates owned by each lane
     int root_cp_count[B2G_MAX_CHAINS];
+    // Segment view of the chains (the <8,3> kernels): every chain is cut into pieces of at most three links that own a lane each.
+    // Lane c < n_chains holds the proximal piece of chain c (so root candidates and task code that name a chain keep their lane);
+    // the distal pieces of chains longer than three links follow in chain order.  n_seg = 0: the model does not fit (more than
+    // B2G_MAX_CHAINS pieces) and the kernels that walk whole chains are used instead.
+    int n_seg;
+    int seg_start[B2G_MAX_CHAINS], seg_len[B2G_MAX_CHAINS];
+    int seg_par[B2G_MAX_CHAINS];      // lane of the piece this one hangs off (its last link), -1 = the root
+    int seg_child[B2G_MAX_CHAINS];    // lane of the piece hanging off this one, -1 = none
+    int seg_store[B2G_MAX_CHAINS];    // index of this piece's slot in the shared-memory ancestor store (pieces with a child), -1 = none
+    int n_seg_store;
     float root_mass;
     float root_com[3];
     float root_inertia[6];
@@ -53,6 +63,7 @@ struct DevParams {
     float mu_ground;
     int has_ground;
     float limit_kp, limit_kd;   // joint-limit spring / damper
+    int block_align;            // bit mask of the points of a sub-step at which the block's warps re-align (b2g_dynamics.cuh::block_align)
     int max_contacts;           // contact slots per lane in use (<= B2G_MAX_CONTACTS_PER_CHAIN); sizes the shared-memory scratch
     // heightfield (null -> plane z = 0)
     const int16_t* hf;

@@ -148,6 +148,17 @@ B2G_HD B2G_INL SV grp_bcast(SV s, int src) {
               V3{Grp<LANES>::bcast(s.v.x, src), Grp<LANES>::bcast(s.v.y, src), Grp<LANES>::bcast(s.v.z, src)}};
 }
 template <int LANES>
+B2G_HD B2G_INL SI grp_bcast(const SI& s, int src) {
+    SI o;
+    o.A.xx = Grp<LANES>::bcast(s.A.xx, src); o.A.xy = Grp<LANES>::bcast(s.A.xy, src); o.A.xz = Grp<LANES>::bcast(s.A.xz, src);
+    o.A.yy = Grp<LANES>::bcast(s.A.yy, src); o.A.yz = Grp<LANES>::bcast(s.A.yz, src); o.A.zz = Grp<LANES>::bcast(s.A.zz, src);
+    o.C.xx = Grp<LANES>::bcast(s.C.xx, src); o.C.xy = Grp<LANES>::bcast(s.C.xy, src); o.C.xz = Grp<LANES>::bcast(s.C.xz, src);
+    o.C.yy = Grp<LANES>::bcast(s.C.yy, src); o.C.yz = Grp<LANES>::bcast(s.C.yz, src); o.C.zz = Grp<LANES>::bcast(s.C.zz, src);
+#pragma unroll
+    for (int k = 0; k < 9; k++) o.B.m[k] = Grp<LANES>::bcast(s.B.m[k], src);
+    return o;
+}
+template <int LANES>
 B2G_HD B2G_INL SV grp_sum(SV s) {
     return SV{V3{Grp<LANES>::sum(s.w.x), Grp<LANES>::sum(s.w.y), Grp<LANES>::sum(s.w.z)},
               V3{Grp<LANES>::sum(s.v.x), Grp<LANES>::sum(s.v.y), Grp<LANES>::sum(s.v.z)}};
@@ -273,11 +284,20 @@ __host__ __device__ inline
 #endif
 size_t link_store_floats(int n_envs_per_block, int n_dof) { return (size_t)n_envs_per_block * n_dof * (sizeof(LinkData) / sizeof(float)); }
 
+// Segment variant (LANES = 8, NL = 3): a chain longer than three links is cut into pieces that own a lane each (DevModel::seg_*).
+// The recursions run in two dependency stages with the piece boundary passed by shuffles; a distal piece reaches the links of its
+// parent piece (joint axis S, U = I^A S, 1 / D) through shared memory when it propagates a contact impulse to the root.
+template <int LANES, int NL>
+B2G_HD constexpr bool is_segmented() { return LANES == 8 && NL == 3; }
+constexpr int kAncLinkFloats = 16;                    // S (6) | U (6) | 1/D | 3 pad: 16-byte rows
+constexpr int kAncFloats = 3 * kAncLinkFloats;        // a piece with a child is always full
+
 // per-thread contact scratch: field f of slot s
 struct ScratchStrided {
     float* base;   // points at this thread's column
     int stride;    // number of threads sharing the buffer
     float* links = nullptr;   // this environment's slice of the block's shared link store (links_in_shared variants only)
+    float* anc = nullptr;     // this environment's ancestor store (segment variant only): kAncFloats per piece that has a child
     B2G_HD B2G_INL float& at(int slot, int f) { return base[(slot * CF_COUNT + f) * stride]; }
 };
 
@@ -301,6 +321,16 @@ B2G_HD B2G_INL void ground_sample(const DevParams& P, float x, float y, float& h
     n = V3{nx * inv, ny * inv, inv};
 }
 
+// The warps of a block run the same instruction stream, each through its own instruction-cache lines once it has drifted away from
+// the others (data-dependent contact loops).  A block barrier at a few points of the sub-step keeps them within one cache window.
+B2G_HD B2G_INL void block_align(const DevParams& P, int bit) {
+#if defined(__CUDA_ARCH__)
+    if (P.block_align & bit) __syncthreads();
+#else
+    (void)P; (void)bit;
+#endif
+}
+
 // One sub-step.  `len` = links in this lane's chain (0 for an idle lane), `d0` = first DOF of the chain.
 // `bf` = this environment's body-force accumulator (n_bodies*3 floats, shared by the group), written on
 // the last sub-step only.
@@ -312,8 +342,15 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
                             LaneState<NL>& st, const EnvDr dr, bool last, ScratchStrided sc, float* bf) {
     // FULL: every lane's chain has exactly NL links (the quadrupeds) -> the `j < len` predicates fold away
     const int len = FULL ? NL : len_in;
+    constexpr bool SEG = is_segmented<LANES, NL>();
+    constexpr int NSTG = SEG ? 2 : 1;                          // dependency stages of the recursions: proximal pieces, then distal ones
+    const int par = SEG ? M->seg_par[lane] : -1;               // lane of the piece this lane's piece hangs off
+    const int child = SEG ? M->seg_child[lane] : -1;           // lane of the piece hanging off this one
+    const bool distal = SEG && par >= 0;
+    const int up_lane = distal ? par : lane, down_lane = child >= 0 ? child : lane;      // shuffle sources (self = no-op)
     const float h = P.h;
     const V3 grav = V3{P.g[0], P.g[1], P.g[2]};
+    block_align(P, 1);
 
     // ---------------- kinematics down the chain ----------------
     const M3 R0 = quat_to_m3(st.qx, st.qy, st.qz, st.qw);
@@ -327,6 +364,17 @@ B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, 
         M3 Rp = R0;
         V3 pp = V3{0, 0, 0};
         SV vp = v0;
+#pragma unroll 1
+        for (int stg = 0; stg < NSTG; stg++) {
+        if (SEG && stg == 1) {      // distal pieces start from the frame and velocity of their parent's last link
+            M3 Rq;
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rq.m[k] = Grp<LANES>::bcast(Rp.m[k], up_lane);
+            const V3 pq = V3{Grp<LANES>::bcast(pp.x, up_lane), Grp<LANES>::bcast(pp.y, up_lane), Grp<LANES>::bcast(pp.z, up_lane)};
+            const SV vq = grp_bcast<LANES>(vp, up_lane);
+            Rp = Rq; pp = pq; vp = vq;
+        }
+        if (SEG && distal != (stg == 1)) continue;
 B2G_LINK_UNROLL
         for (int j = 0; j < NL; j++) {
             if (j < len) {
@@ -384,6 +432,7 @@ B2G_LINK_UNROLL
                 L[j].Rl = R0; L[j].pl = V3{0, 0, 0}; L[j].S = sv0(); L[j].cb = sv0(); L[j].vl = sv0(); L[j].tau = 0; L[j].dext = 1.0f;
             }
         }
+        }
     }
 
     // ---------------- ABA backward: articulated inertias and bias forces ----------------
@@ -393,6 +442,14 @@ B2G_LINK_UNROLL
         IAc.A = S3{0, 0, 0, 0, 0, 0}; IAc.C = S3{0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 9; k++) IAc.B.m[k] = 0;
+#pragma unroll 1
+        for (int stg = NSTG - 1; stg >= 0; stg--) {
+        if (SEG && stg == 0) {      // a distal piece hands its articulated inertia and bias force to its parent's last link
+            const SI Iq = grp_bcast<LANES>(IAc, down_lane);
+            const SV pq = grp_bcast<LANES>(pAc, down_lane);
+            if (child >= 0) { IAc = Iq; pAc = pq; }
+        }
+        if (SEG && distal != (stg == 1)) continue;
 B2G_LINK_UNROLL
         for (int j = NL - 1; j >= 0; j--) {
             if (j < len) {
@@ -402,7 +459,7 @@ B2G_LINK_UNROLL
                 const S3 iw = rotate_sym(L[j].Rl, S3{D.inertia[0] * ms, D.inertia[1] * ms, D.inertia[2] * ms, D.inertia[3] * ms, D.inertia[4] * ms, D.inertia[5] * ms});
                 SI I = rigid_inertia(D.mass * ms, cw, iw);
                 SV pA = crf(L[j].vl, mul(I, L[j].vl));
-                if (j + 1 < len) { I += IAc; pA += pAc; }
+                if (j + 1 < len || (SEG && child >= 0)) { I += IAc; pA += pAc; }
                 L[j].U = mul(I, L[j].S);
                 const float Dj = dot(L[j].S, L[j].U) + L[j].dext;
                 L[j].Dinv = 1.0f / Dj;
@@ -413,12 +470,19 @@ B2G_LINK_UNROLL
                 L[j].U = sv0(); L[j].Dinv = 0.0f; L[j].u = 0.0f;
             }
         }
+        }
     }
 
     // ---------------- root: sum the chains, solve ----------------
     P6 inv;
     SV a0 = sv0();   // relative root acceleration a' = a - a_g
     if (!FIXED) {
+        if (SEG && distal) {      // already inside its parent's terms
+            pAc = sv0();
+            IAc.A = S3{0, 0, 0, 0, 0, 0}; IAc.C = S3{0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 9; k++) IAc.B.m[k] = 0;
+        }
         SI IA0 = grp_sum<LANES>(IAc);
         SV pA0 = grp_sum<LANES>(pAc);
         const V3 cw = mul(R0, V3{M->root_com[0], M->root_com[1], M->root_com[2]});
@@ -441,6 +505,10 @@ B2G_LINK_UNROLL
     SV v0n = sv0();
     {
         SV a = FIXED ? SV{V3{0, 0, 0}, -grav} : a0;
+#pragma unroll 1
+        for (int stg = 0; stg < NSTG; stg++) {
+        if (SEG && stg == 1) a = grp_bcast<LANES>(a, up_lane);      // acceleration of the parent's last link
+        if (SEG && distal != (stg == 1)) continue;
 B2G_LINK_UNROLL
         for (int j = 0; j < NL; j++) {
             if (j < len) {
@@ -452,6 +520,7 @@ B2G_LINK_UNROLL
             } else {
                 qdn[j] = 0.0f;
             }
+        }
         }
         if (!FIXED) {
             // root origin is a body-fixed point: classical acceleration = spatial + w x v
@@ -469,7 +538,34 @@ B2G_LINK_UNROLL
     // impulse helpers -----------------------------------------------------------------
     // backward half: impulse F on link `jc` of this chain (-1 = root): returns the root-level bias Pb and the per-joint
     // terms ud[] the forward half needs
-    auto push_up = [&](int jc, SV F, float* ud) -> SV {
+    // Segment variant: pieces with a child publish S, U, 1/D of their links; a distal piece continues its impulse recursion through them.
+    // vbase = velocity of the link the piece hangs off (the root's for proximal pieces, where v0n is used instead).
+    SV vbase = v0n;
+    const float* anc = nullptr;
+    if (SEG) {
+        Grp<LANES>::sync();
+        const int slot = M->seg_store[lane];
+        if (slot >= 0) {
+#pragma unroll
+            for (int j = 0; j < NL; j++) {
+                float* a = sc.anc + slot * kAncFloats + j * kAncLinkFloats;
+                a[0] = L[j].S.w.x; a[1] = L[j].S.w.y; a[2] = L[j].S.w.z; a[3] = L[j].S.v.x; a[4] = L[j].S.v.y; a[5] = L[j].S.v.z;
+                a[6] = L[j].U.w.x; a[7] = L[j].U.w.y; a[8] = L[j].U.w.z; a[9] = L[j].U.v.x; a[10] = L[j].U.v.y; a[11] = L[j].U.v.z;
+                a[12] = L[j].Dinv;
+            }
+        }
+        SV vend = v0n;      // free velocity of this piece's last link
+#pragma unroll
+        for (int j = 0; j < NL; j++)
+            if (j < len) vend += L[j].S * qdn[j];
+        const SV vq = grp_bcast<LANES>(vend, up_lane);
+        if (distal) { vbase = vq; anc = sc.anc + M->seg_store[par] * kAncFloats; }
+        Grp<LANES>::sync();
+    }
+    auto anc_S = [&](int i) -> SV { const float* a = anc + i * kAncLinkFloats; return SV{V3{a[0], a[1], a[2]}, V3{a[3], a[4], a[5]}}; };
+    auto anc_U = [&](int i) -> SV { const float* a = anc + i * kAncLinkFloats; return SV{V3{a[6], a[7], a[8]}, V3{a[9], a[10], a[11]}}; };
+    auto anc_Dinv = [&](int i) -> float { return anc[i * kAncLinkFloats + 12]; };
+    auto push_up = [&](int jc, SV F, float* ud, float* uda) -> SV {
         SV Pb = -F;
 #pragma unroll
         for (int i = NL - 1; i >= 0; i--) {
@@ -480,10 +576,26 @@ B2G_LINK_UNROLL
                 ud[i] = 0.0f;
             }
         }
+        if (SEG && distal) {      // on through the parent piece
+#pragma unroll
+            for (int i = 2; i >= 0; i--) {
+                uda[i] = -dot(anc_S(i), Pb);
+                Pb += anc_U(i) * (uda[i] * anc_Dinv(i));
+            }
+        }
         return Pb;
+    };
+    // forward half through the parent piece's links (distal pieces)
+    auto run_anc = [&](SV& a, const float* uda) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float dq = (uda[i] - dot(anc_U(i), a)) * anc_Dinv(i);
+            a += anc_S(i) * dq;
+        }
     };
 
     // ---------------- contact candidates ----------------
+    if (!PROBE) block_align(P, 2);
     int ncon = 0, ndrop = 0;
     const bool ground = HF || (P.has_ground != 0);
     auto test_candidate = [&](int i, const M3& R, V3 p, int jc) {
@@ -553,12 +665,20 @@ B2G_LINK_UNROLL
         }
     }
 
-    const int maxs = Grp<LANES>::warp_max(ncon);
+    // Segment variant: the contacts of a chain stay Gauss-Seidel ordered, distal piece first (the order of the whole-chain kernels):
+    // a piece with a child starts its slots `off` steps late
+    int off = 0;
+    if (SEG) {
+        const float nc = Grp<LANES>::bcast((float)ncon, down_lane);
+        off = child >= 0 ? (int)nc : 0;
+    }
+    const int maxc = Grp<LANES>::warp_max(ncon);
+    const int maxs = SEG ? Grp<LANES>::warp_max(off + ncon) : maxc;
     if (P.stats) contact_stats_add<LANES>(P.stats, lane, dr.live, ncon, ndrop);
 
     // local Delassus block of every active contact: response of the contact point to unit impulses along n, t1, t2
     // (one code instance for all links: the contact's link index is a run-time value, the chain loops are predicated)
-    for (int s = 0; s < maxs; s++) {
+    for (int s = 0; s < maxc; s++) {
         if (s < ncon) {
             const V3 r = V3{sc.at(s, CF_RX), sc.at(s, CF_RY), sc.at(s, CF_RZ)};
             const V3 dirs[3] = {V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)}, V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)},
@@ -567,10 +687,11 @@ B2G_LINK_UNROLL
             float A[9];
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                float ud[NL];
+                float ud[NL], uda[3];
                 const SV F = SV{cross(r, dirs[b]), dirs[b]};
-                const SV Pb = push_up(jc, F, ud);
+                const SV Pb = push_up(jc, F, ud, uda);
                 SV a = FIXED ? sv0() : -mul(inv, Pb);
+                if (SEG && distal) run_anc(a, uda);
 #pragma unroll
                 for (int k = 0; k < NL; k++) {
                     if (k <= jc) {
@@ -590,6 +711,7 @@ B2G_LINK_UNROLL
     }
 
     // ---------------- projected relaxation: Gauss-Seidel along a lane, Jacobi across lanes ----------------
+    block_align(P, 4);
     // Contacts of different chains couple only through the (heavy) root, so slot s of every lane is updated from the
     // same velocities; the root-level biases are summed with one shuffle butterfly and applied once.
     SV v0pos = v0n;
@@ -607,18 +729,19 @@ B2G_LINK_UNROLL
             for (int j = 0; j < NL; j++) qdpos[j] = qdn[j];
         }
         const bool with_bias = it < P.npos;
-        for (int s = 0; s < maxs; s++) {
+        for (int step = 0; step < maxs; step++) {
             SV Pb = sv0();
-            float ud[NL];
+            float ud[NL], uda[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
             for (int k = 0; k < NL; k++) ud[k] = 0.0f;
-            if (s < ncon) {
+            const int s = SEG ? step - off : step;
+            if (s >= 0 && s < ncon) {
                 const V3 r = V3{sc.at(s, CF_RX), sc.at(s, CF_RY), sc.at(s, CF_RZ)};
                 const V3 n = V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)};
                 const V3 t1 = V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)};
                 const V3 t2 = V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)};
                 const int jc = (int)sc.at(s, CF_JC);
-                SV lv = v0n;
+                SV lv = distal ? vbase : v0n;
 #pragma unroll
                 for (int k = 0; k < NL; k++)
                     if (k <= jc) lv += L[k].S * qdn[k];
@@ -653,7 +776,14 @@ B2G_LINK_UNROLL
                 }
                 sc.at(s, CF_LN) = ln; sc.at(s, CF_L1) = l1; sc.at(s, CF_L2) = l2;
                 const V3 dir = n * dn + t1 * (l1 - l1o) + t2 * (l2 - l2o);
-                Pb = push_up(jc, SV{cross(r, dir), dir}, ud);
+                Pb = push_up(jc, SV{cross(r, dir), dir}, ud, uda);
+            }
+            if (SEG) {      // the joint terms a distal piece found for its parent's links
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const float g = Grp<LANES>::bcast(uda[i], down_lane);
+                    if (child >= 0) ud[i] += g;
+                }
             }
             // all lanes' impulses reach the root together, then run down every chain
             SV a = sv0();
@@ -662,12 +792,25 @@ B2G_LINK_UNROLL
                 a = -mul(inv, Psum);
                 v0n += a;
             }
+            auto run_own = [&]() {
 #pragma unroll
-            for (int k = 0; k < NL; k++) {
-                if (k < len) {
-                    const float dq = (ud[k] - dot(L[k].U, a)) * L[k].Dinv;
-                    a += L[k].S * dq;
-                    qdn[k] += dq;
+                for (int k = 0; k < NL; k++) {
+                    if (k < len) {
+                        const float dq = (ud[k] - dot(L[k].U, a)) * L[k].Dinv;
+                        a += L[k].S * dq;
+                        qdn[k] += dq;
+                    }
+                }
+            };
+            if (!SEG) {
+                run_own();
+            } else {      // proximal pieces first; the velocity change of their last link is where the distal piece starts
+                if (!distal) run_own();
+                const SV aq = grp_bcast<LANES>(a, up_lane);
+                if (distal) {
+                    vbase += aq;
+                    a = aq;
+                    run_own();
                 }
             }
         }

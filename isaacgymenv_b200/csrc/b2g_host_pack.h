@@ -2,6 +2,7 @@
 #pragma once
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -15,6 +16,32 @@ inline void quat_to_rot9(const float* q, float* m) {
     m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - z * w); m[2] = 2 * (x * z + y * w);
     m[3] = 2 * (x * y + z * w); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - x * w);
     m[6] = 2 * (x * z - y * w); m[7] = 2 * (y * z + x * w); m[8] = 1 - 2 * (x * x + y * y);
+}
+
+constexpr int kSegLinks = 3;      // links per lane of the segment kernels
+
+// Segment view of the chains (DevModel::seg_*): proximal pieces in lanes 0..n_chains-1, distal pieces behind them.
+inline void build_segments(DevModel& d) {
+    for (int c = 0; c < B2G_MAX_CHAINS; c++) { d.seg_start[c] = 0; d.seg_len[c] = 0; d.seg_par[c] = -1; d.seg_child[c] = -1; d.seg_store[c] = -1; }
+    d.n_seg = 0; d.n_seg_store = 0;
+    int n = d.n_chains;
+    for (int c = 0; c < d.n_chains; c++) n += d.chain_len[c] > kSegLinks ? 1 : 0;
+    if (n > B2G_MAX_CHAINS || d.n_chains == 0) return;
+    int next = d.n_chains;
+    for (int c = 0; c < d.n_chains; c++) {
+        const int len = d.chain_len[c];
+        d.seg_start[c] = d.chain_start[c];
+        d.seg_len[c] = len > kSegLinks ? kSegLinks : len;
+        if (len > kSegLinks) {      // B2G_MAX_CHAIN_LEN = 2 kSegLinks: one distal piece at most
+            d.seg_start[next] = d.chain_start[c] + kSegLinks;
+            d.seg_len[next] = len - kSegLinks;
+            d.seg_par[next] = c;
+            d.seg_child[c] = next;
+            d.seg_store[c] = d.n_seg_store++;
+            next++;
+        }
+    }
+    d.n_seg = next;
 }
 
 // Returns 0 on success, <0 when the model violates an assumption of the kernels (message in *why).
@@ -37,6 +64,7 @@ inline int pack_dev_model(const b2g_model& m, const b2g_dof_props& p, DevModel& 
         expect += m.chain_len[c];
     }
     if (expect != m.n_dof) { *why = "chain lengths do not add up to n_dof"; return -1; }
+    build_segments(d);
     d.root_mass = m.link_mass[0];
     for (int i = 0; i < 3; i++) d.root_com[i] = m.link_com[0][i];
     // public order xx,yy,zz,xy,xz,yz -> kernel order xx,xy,xz,yy,yz,zz
@@ -178,6 +206,10 @@ inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, 
     d.has_ground = s.has_ground;
     d.limit_kp = s.joint_limit_stiffness; d.limit_kd = s.joint_limit_damping;
     d.max_contacts = contact_slots(s);
+    {
+        const char* ba = getenv("B2G_BLOCK_ALIGN");
+        d.block_align = ba ? atoi(ba) : 1;      // default: the block's warps re-align at the start of every sub-step (B2G_BLOCK_ALIGN=0: never)
+    }
     if (hf && hf_dev) {
         d.hf = hf_dev; d.hf_rows = hf->rows; d.hf_cols = hf->cols; d.hf_hs = hf->horizontal_scale; d.hf_vs = hf->vertical_scale;
         d.hf_ox = hf->origin_x; d.hf_oy = hf->origin_y;

@@ -46,6 +46,18 @@ struct TaskArgs {
     int post_only;              // 1: skip the physics, run post_physics_step on the tensors as they are (parity tests)
 };
 
+// DOF range of a lane: the whole chain, or (segment variant) the lane's piece of at most three links
+template <int LANES, int NL>
+B2G_HD B2G_INL void lane_span(const DevModel* M, int lane, int& len, int& d0) {
+    if (is_segmented<LANES, NL>()) {
+        len = lane < M->n_seg ? M->seg_len[lane] : 0;
+        d0 = lane < M->n_seg ? M->seg_start[lane] : 0;
+    } else {
+        len = lane < M->n_chains ? M->chain_len[lane] : 0;
+        d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    }
+}
+
 template <int NL>
 B2G_HD B2G_INL void load_state(const SimArgs& A, int env, int len, int d0, LaneState<NL>& st) {
     const float* r = A.root + (size_t)env * 13;
@@ -90,8 +102,8 @@ B2G_HD B2G_INL void store_state(const SimArgs& A, int env, int lane, int len, in
 template <int LANES, int NL, bool FIXED, bool HF>
 B2G_HD B2G_INL void simulate_thread(const SimArgs& A, int env, int lane, bool valid, ScratchStrided sc, float* bf) {
     const DevModel* M = A.M;
-    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
-    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    int len, d0;
+    lane_span<LANES, NL>(M, lane, len, d0);
     LaneState<NL> st;
     load_state<NL>(A, env, len, d0, st);
     const int nd = M->n_dof;
@@ -192,8 +204,8 @@ B2G_HD B2G_INL void anymal_reset_lane(const TaskArgs& T, int env, int lane, int 
 template <int LANES, int NL>
 B2G_HD B2G_INL void anymal_reset_all_thread(const SimArgs& A, const TaskArgs& T, int env, int lane, bool valid) {
     const DevModel* M = A.M;
-    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
-    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    int len, d0;
+    lane_span<LANES, NL>(M, lane, len, d0);
     LaneState<NL> st;
     load_state<NL>(A, env, len, d0, st);
     float cmd[3];
@@ -220,8 +232,8 @@ template <int LANES, int NL, bool HF>
 B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int env, int lane, bool valid, ScratchStrided sc, float* bf) {
     const DevModel* M = A.M;
     const int nd = M->n_dof;
-    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
-    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    int len, d0;
+    lane_span<LANES, NL>(M, lane, len, d0);
     const b2g_anymal_cfg& C = T.cfg;
     LaneState<NL> st;
     load_state<NL>(A, env, len, d0, st);
@@ -565,8 +577,9 @@ B2G_HD inline void chain_crba(const DevModel* M, int d0, int n, const float* roo
 }
 // what post_physics_step's refresh_jacobian / refresh_mass_matrix leave for the next step's OSC (pre-reset state), plus the
 // optional live end-effector row
+// q / qd = the arm's joint state (whole chain), st = the caller's lane state (root part used)
 template <int NL>
-B2G_HD inline void arm_refresh(const SimArgs& A, const TerrainArgs& T, int env, int d0, int len, const LaneState<NL>& st) {
+B2G_HD inline void arm_refresh(const SimArgs& A, const TerrainArgs& T, int env, int d0, int len, const LaneState<NL>& st, const float* q, const float* qd) {
     const DevModel* M = A.M;
     const b2g_terrain_cfg& C = T.cfg;
     const float rq[4] = {st.qx, st.qy, st.qz, st.qw};
@@ -576,7 +589,7 @@ B2G_HD inline void arm_refresh(const SimArgs& A, const TerrainArgs& T, int env, 
     const int jl = M->body_link[C.jac_body];
     const int jloc = (jl == 0) ? -1 : jl - 1 - d0;
     V3 lp; M3 lr; SV lv;
-    chain_crba(M, d0, len, rq, st.q, mm, jloc, &lp, &lr, st.qd, st.rw, st.rv, &lv, A.env_scale ? A.env_scale[(size_t)env * 4] : 1.0f,
+    chain_crba(M, d0, len, rq, q, mm, jloc, &lp, &lr, qd, st.rw, st.rv, &lv, A.env_scale ? A.env_scale[(size_t)env * 4] : 1.0f,
                A.link_scale ? A.link_scale + (size_t)env * (M->n_dof + 1) * B2G_LINK_SCALE_COLS : nullptr);
     const V3 r = lp + mul(lr, V3{M->body_pos[C.jac_body][0], M->body_pos[C.jac_body][1], M->body_pos[C.jac_body][2]});
     float* J = T.arm_jac + (size_t)env * 36;
@@ -590,7 +603,7 @@ B2G_HD inline void arm_refresh(const SimArgs& A, const TerrainArgs& T, int env, 
         const int eloc = (el == 0) ? -1 : el - 1 - d0;
         float dummy[36];
         V3 ep; M3 er; SV ev;
-        chain_crba(M, d0, len, rq, st.q, dummy, eloc, &ep, &er, st.qd, st.rw, st.rv, &ev);
+        chain_crba(M, d0, len, rq, q, dummy, eloc, &ep, &er, qd, st.rw, st.rv, &ev);
         const V3 off = mul(er, V3{M->body_pos[C.eef_body][0], M->body_pos[C.eef_body][1], M->body_pos[C.eef_body][2]});
         const V3 pos = ep + off;
         const V3 lin = ev.v + cross(ev.w, pos);
@@ -748,13 +761,13 @@ B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, in
 
 // kernel 1: pre_physics_step (decimation loop) + extra sim step + post_physics_step up to and including the reward
 // ARM = false compiles the operational-space arm law out (quadruped-only robots: no float64 code, no OSC stack frame)
-template <int LANES, int NL, bool HF, bool ARM = (NL >= 6)>
+template <int LANES, int NL, bool HF, bool ARM = (NL >= 6 || is_segmented<LANES, NL>())>
 B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, int env, int lane, bool valid, ScratchStrided sc, float* bf) {
     const DevModel* M = A.M;
     const b2g_terrain_cfg& C = T.cfg;
     const int nd = M->n_dof;
-    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
-    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    int len, d0;
+    lane_span<LANES, NL>(M, lane, len, d0);
     LaneState<NL> st;
     load_state<NL>(A, env, len, d0, st);
     const long long progress = T.progress[env] + 1;
@@ -773,32 +786,57 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
             lqd[j] = T.last_dof_vel[k];
         }
     }
-    const bool is_arm = ARM && (C.arm_chain >= 0) && (lane == C.arm_chain);
+    // arm: lane arm_chain holds the chain (segment variant: its first three joints, lane arm2 the rest) and evaluates the torque law
+    constexpr bool SEG = is_segmented<LANES, NL>();
+    const bool has_arm = ARM && (C.arm_chain >= 0);
+    const bool is_arm = has_arm && (lane == C.arm_chain);
+    const int arm2 = (SEG && has_arm) ? M->seg_child[C.arm_chain] : -1;
+    const bool is_arm2 = arm2 >= 0 && lane == arm2;
+    const int arm_d0 = has_arm ? M->chain_start[C.arm_chain] : 0, arm_len = has_arm ? M->chain_len[C.arm_chain] : 0;
+    // the six arm values of a per-DOF array, complete in lane arm_chain (segment variant: a warp-wide exchange, every lane calls it)
+    auto arm_gather = [&](const float* x, float* o6) {
+        for (int j = 0; j < 6; j++) o6[j] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NL; j++)
+            if (j < 6 && j < len) o6[j] = x[j];
+        if (SEG) {
+#pragma unroll
+            for (int j = 0; j < NL; j++) {
+                const float v = Grp<LANES>::bcast(x[j], arm2 >= 0 ? arm2 : lane);
+                if (arm2 >= 0 && NL + j < 6) o6[NL + j] = v;
+            }
+        }
+    };
     // arm lane: OSC torque from the stored mass-matrix / Jacobian slices, the end-effector velocity row and the live arm DOFs
     OscPrepared osc;
-    if (is_arm) {
-        float dpose[6];
-        for (int j = 0; j < 6; j++) dpose[j] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NL; j++)
-            if (j < 6 && j < len) dpose[j] = act[j] * C.arm_cmd_limit[j] / C.arm_action_scale;
-        osc_prepare(T.arm_mm + (size_t)env * 36, T.arm_jac + (size_t)env * 36, dpose, T.eef_state + (size_t)env * 13 + 7, C.arm_kp, osc);
+    if (SEG ? has_arm : is_arm) {
+        float a6[6], dpose[6];
+        arm_gather(act, a6);
+        for (int j = 0; j < 6; j++) dpose[j] = (j < arm_len) ? a6[j] * C.arm_cmd_limit[j] / C.arm_action_scale : 0.0f;
+        if (is_arm) osc_prepare(T.arm_mm + (size_t)env * 36, T.arm_jac + (size_t)env * 36, dpose, T.eef_state + (size_t)env * 13 + 7, C.arm_kp, osc);
     }
+    // whole-chain variant: called by the arm lane; segment variant: called by every lane of the warp (has_arm is uniform)
     auto arm_osc = [&](float* out) {
         float qa[6], qda[6], eff[6], u[6];
-        for (int j = 0; j < 6; j++) { qa[j] = 0; qda[j] = 0; eff[j] = 0; }
+        arm_gather(st.q, qa);
+        arm_gather(st.qd, qda);
+        for (int j = 0; j < 6; j++) { eff[j] = (j < arm_len) ? M->dof[arm_d0 + j].effort : 0.0f; u[j] = 0.0f; }
+        if (is_arm) osc_apply(osc, qa, qda, C.arm_kp_null, eff, u);
 #pragma unroll
         for (int j = 0; j < NL; j++)
-            if (j < 6 && j < len) { qa[j] = st.q[j]; qda[j] = st.qd[j]; eff[j] = M->dof[d0 + j].effort; }
-        osc_apply(osc, qa, qda, C.arm_kp_null, eff, u);
+            if (is_arm && j < 6 && j < len) out[j] = u[j];
+        if (SEG) {
 #pragma unroll
-        for (int j = 0; j < NL; j++)
-            if (j < 6 && j < len) out[j] = u[j];
+            for (int j = 0; j < NL; j++) {
+                const float v = Grp<LANES>::bcast(NL + j < 6 ? u[NL + j] : 0.0f, C.arm_chain);
+                if (is_arm2 && j < len) out[j] = v;
+            }
+        }
     };
     if (T.post_only == 2) {        // OSC probe (parity tests): one evaluation of the torque law, nothing else
-        if (is_arm) {
+        if (SEG ? has_arm : is_arm) {
             arm_osc(tq);
-            if (valid)
+            if (valid && (is_arm || is_arm2))
                 for (int j = 0; j < len; j++) T.torques[(size_t)env * nd + d0 + j] = tq[j];
         }
         return;
@@ -809,9 +847,8 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
 #pragma unroll 1
         for (int it = 0; it < total; it++) {
             if (it < C.decimation) {      // tasks/anymal_terrain.py:444-445: fresh explicit PD torque, clipped
-                if (is_arm) {             // tasks/useful_hound.py:704-716: operational-space torques for the arm, every decimation step
-                    arm_osc(tq);
-                } else {
+                if (SEG ? has_arm : is_arm) arm_osc(tq);      // tasks/useful_hound.py:704-716: operational-space torques for the arm, every decimation step
+                if (!is_arm && !is_arm2) {
 #pragma unroll
                     for (int j = 0; j < NL; j++) {
                         if (j < len) {
@@ -904,6 +941,8 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
     float rew = r_lin_xy + r_ang_z + r_lin_z + r_ang_xy + r_orient + r_height + r_torque + r_jacc + r_coll + r_arate + r_air + r_hip + r_stumble;
     rew = fmaxf(rew, 0.0f);
     if (reset && !timeout_prev) rew += C.rew[0];
+    float q6[6], qd6[6];
+    if (SEG ? has_arm : is_arm) { arm_gather(st.q, q6); arm_gather(st.qd, qd6); }
     if (valid) {
         store_state<NL>(A, env, lane, len, d0, st, false);
         const int nb3 = M->n_bodies * 3;
@@ -916,7 +955,7 @@ B2G_HD B2G_INL void terrain_phys_thread(const SimArgs& A, const TerrainArgs& T, 
                 T.torques[k] = tq[j];
             }
         }
-        if (is_arm) arm_refresh<NL>(A, T, env, d0, len, st);      // refresh_jacobian / refresh_mass_matrix (useful_hound.py:731-732)
+        if (is_arm) arm_refresh<NL>(A, T, env, arm_d0, arm_len, st, q6, qd6);      // refresh_jacobian / refresh_mass_matrix (useful_hound.py:731-732)
         if (lane == 0) {
             T.rew[env] = rew;
             T.reset[env] = reset ? 1 : 0;
@@ -942,8 +981,8 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
     const DevModel* M = A.M;
     const b2g_terrain_cfg& C = T.cfg;
     const int nd = M->n_dof, N = A.n_envs;
-    const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
-    const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+    int len, d0;
+    lane_span<LANES, NL>(M, lane, len, d0);
     const bool reset = T.reset[env] != 0;
     float root[13];
     for (int k = 0; k < 13; k++) root[k] = A.root[(size_t)env * 13 + k];
@@ -962,7 +1001,7 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
     // every lane has read the per-env inputs it replicates; only now may lane 0 overwrite them
     Grp<NSUB>::sync();
     const bool has_arm = C.arm_chain >= 0;
-    const bool is_arm = has_arm && lane == C.arm_chain;
+    const bool is_arm = has_arm && (lane == C.arm_chain || (is_segmented<LANES, NL>() && lane == M->seg_child[C.arm_chain]));
     const int nctrl = C.n_ctrl_dof > 0 ? C.n_ctrl_dof : nd;
     if (reset) {        // reset_idx, tasks/anymal_terrain.py:384-425 (useful_hound.py:569-637); draw order of the random calls
         const int ndraw = 2 * nctrl + 5 + (has_arm ? 6 : 0);
@@ -975,7 +1014,7 @@ B2G_HD B2G_INL void terrain_post_thread(const SimArgs& A, const TerrainArgs& T, 
                     q[j] = C.default_dof_pos[d] * rand_range(0.5f, 1.5f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, d));
                     qd[j] = rand_range(-0.1f, 0.1f, terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, nctrl + d));
                 } else {      // arm joints <- clamp(0 + noise * 2 (u - 0.5), lower, upper), zero velocity (useful_hound.py:594-601)
-                    const float u = terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, arm_col + j);
+                    const float u = terrain_uniform(T, T.reset_override, ndraw, env, (unsigned)rc, 1u, arm_col + d - M->chain_start[C.arm_chain]);
                     const float v = 0.0f + C.arm_dof_noise * 2.0f * (u - 0.5f);
                     q[j] = fminf(fmaxf(v, M->dof[d].lower), M->dof[d].upper);
                     qd[j] = 0.0f;

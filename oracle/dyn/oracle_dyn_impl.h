@@ -413,19 +413,28 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
     }
     for (int d = 0; d < nd; d++) qd[d] += h * qdd[d];
 
-    /* ---- collect contacts: per chain, candidates in model order, the first max_contacts_per_chain of them ---- */
-    FN(orc_contact) con[B2G_MAX_CHAINS][B2G_MAX_CONTACTS_PER_CHAIN];
-    int ncon[B2G_MAX_CHAINS];
+    /* ---- collect contacts: per chain, candidates in model order (tip first), the first max_contacts_per_chain of them.
+     * With B2G_SEGMENTS=1 in the environment, floating-base robots whose chains, cut into pieces of at most three links, fit
+     * eight lanes run the segment kernels (b2g_host_pack.h::build_segments): there every PIECE has max_contacts_per_chain
+     * slots of its own (root candidates count with the proximal piece); the order of a chain's contacts -- distal piece
+     * first -- is the same. ---- */
+    FN(orc_contact) con[B2G_MAX_CHAINS][2 * B2G_MAX_CONTACTS_PER_CHAIN];
+    int ncon[B2G_MAX_CHAINS], npiece[B2G_MAX_CHAINS][2];
+    int pieces = m->n_chains;
+    for (int c = 0; c < m->n_chains; c++) pieces += m->chain_len[c] > 3 ? 1 : 0;
+    const char* seg_env = getenv("B2G_SEGMENTS");
+    const int by_piece = seg_env && seg_env[0] == '1' && !m->fixed_base && m->n_chains > 0 && pieces <= B2G_MAX_CHAINS;
     R mu_g = hf && hfs ? (R)hf->friction : (R)sp->plane_dynamic_friction;
     R mu = (R)0.5 * (mu_g + mu_shape);   /* PhysX default combine mode: average */
     int ground = (hf && hfs) || sp->has_ground;
     int maxc = sp->max_contacts_per_chain > 0 ? sp->max_contacts_per_chain : B2G_DEFAULT_CONTACTS_PER_CHAIN;
     if (maxc > B2G_MAX_CONTACTS_PER_CHAIN) maxc = B2G_MAX_CONTACTS_PER_CHAIN;
-    for (int c = 0; c < m->n_chains; c++) ncon[c] = 0;
+    for (int c = 0; c < m->n_chains; c++) { ncon[c] = 0; npiece[c][0] = npiece[c][1] = 0; }
     for (int i = 0; i < m->n_cpts && ground; i++) {
         int c = m->cp_chain[i], l = m->cp_link[i];
         if (m->fixed_base && l == 0) continue;
-        if (ncon[c] >= maxc) continue;
+        const int piece = (by_piece && l > 0 && l - 1 - m->chain_start[c] >= 3) ? 1 : 0;
+        if (by_piece ? npiece[c][piece] >= maxc : ncon[c] >= maxc) continue;
         R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
         FN(matvec3)(k->rot[l], lp, rc);
         for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];
@@ -433,6 +442,7 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
         R gap = (root13[2] + rc[2] - gh) * n[2] - (R)m->cp_radius[i];
         if (gap >= (R)sp->contact_offset) continue;
         FN(orc_contact)* cc = &con[c][ncon[c]++];
+        npiece[c][piece]++;
         cc->link = l; cc->body = m->cp_body[i]; cc->gap = gap;
         for (int a = 0; a < 3; a++) { cc->n[a] = n[a]; cc->r[a] = rc[a] - (R)m->cp_radius[i] * n[a]; cc->lam[a] = 0; }
         /* tangent basis: t1 = normalise(x_world - (x.n) n), t2 = n x t1 */
@@ -467,7 +477,7 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
         int with_bias = it < npos;
         /* slot s of every chain is updated from the SAME velocities (Jacobi across chains: they couple only through
          * the root), then all impulses are applied; slots of one chain follow each other (Gauss-Seidel within a chain) */
-        for (int s = 0; s < B2G_MAX_CONTACTS_PER_CHAIN; s++) {
+        for (int s = 0; s < 2 * B2G_MAX_CONTACTS_PER_CHAIN; s++) {
             R Fall[B2G_MAX_CHAINS][6];
             for (int c = 0; c < m->n_chains; c++) {
                 for (int a = 0; a < 6; a++) Fall[c][a] = 0;

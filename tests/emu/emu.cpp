@@ -22,7 +22,7 @@ using namespace b2g;
 
 namespace {
 
-struct Variant { int lanes, nl; bool fixed; };
+struct Variant { int lanes, nl; bool fixed; bool seg = false; };
 
 Variant pick(const b2g_model& m) {
     int maxlen = 0;
@@ -32,6 +32,10 @@ Variant pick(const b2g_model& m) {
     // the specialised variants assume FULL chains (every lane has exactly NL links)
     if (m.fixed_base && m.n_chains == 1 && maxlen == 2) return {1, 2, true};
     if (!m.fixed_base && m.n_chains == 4 && maxlen == 3 && minlen == 3) return {4, 3, false};
+    int pieces = m.n_chains;      // same rule as b200gym.cu::pick_variant
+    for (int c = 0; c < m.n_chains; c++) pieces += m.chain_len[c] > kSegLinks ? 1 : 0;
+    const char* seg = getenv("B2G_SEGMENTS");
+    if (seg && seg[0] == '1' && !m.fixed_base && m.n_chains > 0 && pieces <= B2G_MAX_CHAINS) return {8, 3, false, true};
     return {8, 6, m.fixed_base != 0};
 }
 
@@ -51,9 +55,9 @@ void run_group(int lanes, F&& body) {
 template <int LANES, int NL, bool FIXED, bool HF>
 void sim_env(const SimArgs& A, int env) {
     std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
-    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF)), anc((size_t)B2G_MAX_CHAINS * kAncFloats);
     run_group(LANES, [&](int lane) {
-        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data();
+        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data(); sc.anc = anc.data();
         simulate_thread<LANES, NL, FIXED, HF>(A, env, lane, true, sc, bf.data());
     });
 }
@@ -61,15 +65,15 @@ void sim_env(const SimArgs& A, int env) {
 template <int LANES, int NL, bool FIXED>
 void probe_env(const SimArgs& A, int env, float* qdd, float* a0) {
     std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
-    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF)), anc((size_t)B2G_MAX_CHAINS * kAncFloats);
     run_group(LANES, [&](int lane) {
         const DevModel* M = A.M;
-        const int len = lane < M->n_chains ? M->chain_len[lane] : 0;
-        const int d0 = lane < M->n_chains ? M->chain_start[lane] : 0;
+        int len, d0;
+        lane_span<LANES, NL>(M, lane, len, d0);
         LaneState<NL> st;
         load_state<NL>(A, env, len, d0, st);
         for (int j = 0; j < NL; j++) if (j < len) st.act[j] = A.actuation[(size_t)env * M->n_dof + d0 + j];
-        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data();
+        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data(); sc.anc = anc.data();
         substep<LANES, NL, FIXED, false, true>(M, A.P, lane, len, d0, st, env_dr(A, env, true, false), false, sc, bf.data());
         for (int j = 0; j < NL; j++) if (j < len) qdd[(size_t)env * M->n_dof + d0 + j] = st.frc[j];
         if (lane == 0) {
@@ -82,9 +86,9 @@ void probe_env(const SimArgs& A, int env, float* qdd, float* a0) {
 template <int LANES, int NL, bool HF>
 void anymal_env(const SimArgs& A, const TaskArgs& T, int env, int mode) {
     std::vector<float> scratch((size_t)LANES * MAXC * CF_COUNT), bf((size_t)A.M->n_bodies * 3);
-    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF)), anc((size_t)B2G_MAX_CHAINS * kAncFloats);
     run_group(LANES, [&](int lane) {
-        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data();
+        ScratchStrided sc{scratch.data() + lane, LANES}; sc.links = links.data(); sc.anc = anc.data();
         if (mode == 0) anymal_reset_all_thread<LANES, NL>(A, T, env, lane, true);
         else anymal_step_thread<LANES, NL, HF>(A, T, env, lane, true, sc, bf.data());
     });
@@ -136,6 +140,7 @@ int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
         if (v.lanes == 1) sim_env<1, 2, true, false>(A, e);
         else if (v.lanes == 4) { if (HFm) sim_env<4, 3, false, true>(A, e); else sim_env<4, 3, false, false>(A, e); }
         else if (v.fixed) sim_env<8, 6, true, false>(A, e);
+        else if (v.seg) { if (HFm) sim_env<8, 3, false, true>(A, e); else sim_env<8, 3, false, false>(A, e); }
         else { if (HFm) sim_env<8, 6, false, true>(A, e); else sim_env<8, 6, false, false>(A, e); }
     }
     delete dm;
@@ -157,6 +162,7 @@ int emu_forward_dynamics(const b2g_model* m, const b2g_sim_params* sp, const b2g
         if (v.lanes == 1) probe_env<1, 2, true>(A, e, qdd, a0);
         else if (v.lanes == 4) probe_env<4, 3, false>(A, e, qdd, a0);
         else if (v.fixed) probe_env<8, 6, true>(A, e, qdd, a0);
+        else if (v.seg) probe_env<8, 3, false>(A, e, qdd, a0);
         else probe_env<8, 6, false>(A, e, qdd, a0);
     }
     delete dm;
@@ -186,6 +192,7 @@ int emu_anymal(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_props
     if (v.fixed) { delete dm; return -2; }
     for (int e = 0; e < n_envs; e++) {
         if (v.lanes == 4) anymal_env<4, 3, false>(A, T, e, mode);
+        else if (v.seg) anymal_env<8, 3, false>(A, T, e, mode);
         else anymal_env<8, 6, false>(A, T, e, mode);
     }
     delete dm;
@@ -239,10 +246,11 @@ int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_prop
     const bool HFm = hf && hfs;
     for (int e = 0; e < n_envs; e++) {
         std::vector<float> scratch((size_t)v.lanes * MAXC * CF_COUNT), bf((size_t)m->n_bodies * 3);
-    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF)), anc((size_t)B2G_MAX_CHAINS * kAncFloats);
         run_group(v.lanes, [&](int lane) {
-            ScratchStrided sc{scratch.data() + lane, v.lanes}; sc.links = links.data();
+            ScratchStrided sc{scratch.data() + lane, v.lanes}; sc.links = links.data(); sc.anc = anc.data();
             if (v.lanes == 4) { if (HFm) terrain_phys_thread<4, 3, true>(A, T, e, lane, true, sc, bf.data()); else terrain_phys_thread<4, 3, false>(A, T, e, lane, true, sc, bf.data()); }
+            else if (v.seg) { if (HFm) terrain_phys_thread<8, 3, true>(A, T, e, lane, true, sc, bf.data()); else terrain_phys_thread<8, 3, false>(A, T, e, lane, true, sc, bf.data()); }
             else { if (HFm) terrain_phys_thread<8, 6, true>(A, T, e, lane, true, sc, bf.data()); else terrain_phys_thread<8, 6, false>(A, T, e, lane, true, sc, bf.data()); }
         });
     }
@@ -258,6 +266,7 @@ int emu_terrain(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_prop
     for (int e = 0; e < n_envs; e++) {
         run_group(v.lanes, [&](int lane) {
             if (v.lanes == 4) terrain_post_thread<4, 3>(A, T, e, lane, true, cnorm);
+            else if (v.seg) terrain_post_thread<8, 3>(A, T, e, lane, true, cnorm);
             else terrain_post_thread<8, 6>(A, T, e, lane, true, cnorm);
         });
     }
@@ -299,11 +308,11 @@ int emu_cartpole(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     T.progress = progress; T.timeout = timeout; T.commands = nullptr; T.actions = actions; T.reset_count = reset_count;
     T.rand_override = rand_override; T.post_only = (mode == 2);
     std::vector<float> scratch((size_t)MAXC * CF_COUNT), bf((size_t)m->n_bodies * 3);
-    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF)), anc((size_t)B2G_MAX_CHAINS * kAncFloats);
     EmuGroup g; g.lanes = 1; g.count = 0; g.sense = 0;
     emu_ctx.g = &g; emu_ctx.lane = 0; emu_ctx.local_sense = 0;
     for (int e = 0; e < n_envs; e++) {
-        ScratchStrided sc{scratch.data(), 1}; sc.links = links.data();
+        ScratchStrided sc{scratch.data(), 1}; sc.links = links.data(); sc.anc = anc.data();
         cartpole_step_thread(A, T, e, true, sc, bf.data());
     }
     delete dm;
@@ -332,11 +341,11 @@ int emu_houndarm(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     T.progress = progress; T.timeout = timeout; T.commands = commands; T.actions = actions; T.reset_count = reset_count;
     T.rand_override = rand_override; T.post_only = (mode == 2);
     std::vector<float> scratch((size_t)MAXC * CF_COUNT), bf((size_t)m->n_bodies * 3);
-    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF));
+    std::vector<float> links(link_store_floats(1, B2G_MAX_DOF)), anc((size_t)B2G_MAX_CHAINS * kAncFloats);
     EmuGroup g; g.lanes = 1; g.count = 0; g.sense = 0;
     emu_ctx.g = &g; emu_ctx.lane = 0; emu_ctx.local_sense = 0;
     for (int e = 0; e < n_envs; e++) {
-        ScratchStrided sc{scratch.data(), 1}; sc.links = links.data();
+        ScratchStrided sc{scratch.data(), 1}; sc.links = links.data(); sc.anc = anc.data();
         houndarm_step_thread(A, T, e, true, sc, bf.data());
     }
     delete dm;

@@ -102,3 +102,25 @@ def test_hf_coarse_bound_identical(robot):
     tested, skipped = emu.hfc_stats()
     print(f"{robot}: coarse bound skipped {skipped} of {tested} link tests")
     assert tested > 0 and skipped > 0.25 * tested, (tested, skipped)
+
+
+# ---- opt-in segment variant (B2G_SEGMENTS=1): chains cut into pieces of at most three links that own a lane each ----
+@pytest.fixture
+def segments(monkeypatch):
+    monkeypatch.setenv("B2G_SEGMENTS", "1")      # read by the emulator's variant choice and by the oracle's per-piece contact cap
+
+
+def test_segment_variant_forward_dynamics(segments):
+    kc.check_forward_dynamics(make, "useful_hound", n=6)
+
+
+def test_segment_variant_simulate_horizon(segments):
+    kc.check_simulate_horizon(make, "useful_hound", n=6, steps=10, drive="effort")
+
+
+def test_segment_variant_useful_step(segments):
+    kc.check_useful_step(make, n=4)
+
+
+def test_segment_variant_hf_coarse_bound_identical(segments):
+    test_hf_coarse_bound_identical("useful_hound")

@@ -108,3 +108,25 @@ def test_hf_coarse_bound_identical(robot):
     """The coarse heightfield bound (per-link contact early-out on rough terrain) never changes a result: library built with and
     without it (B2G_NO_HFC=1), bit for bit, robots standing, tumbling and outside the field."""
     kc.check_hf_coarse_identical(_gpu_sim_hf, robot, steps=30, n=256)
+
+
+# ---- opt-in segment variant (B2G_SEGMENTS=1, read when the sim is created): <8,3> kernels ----
+@pytest.fixture
+def segments(monkeypatch):
+    monkeypatch.setenv("B2G_SEGMENTS", "1")
+
+
+def test_segment_variant_forward_dynamics(segments):
+    kc.check_forward_dynamics(make, "useful_hound", n=256)
+
+
+def test_segment_variant_simulate_horizon(segments):
+    kc.check_simulate_horizon(make, "useful_hound", n=128, steps=10, drive="effort")
+
+
+def test_segment_variant_useful_step(segments):
+    kc.check_useful_step(make, n=64)
+
+
+def test_segment_variant_useful_golden(segments):
+    kc.check_useful_golden(make)
