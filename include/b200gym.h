@@ -531,7 +531,7 @@ int b2g_gae_finish(const b2g_gae_args* args, void* stream);
  * row-major, cols % 4 == 0), and the backward pass of that pair fused with the bias gradient: dz = dh * elu'(z) (from the stored
  * output h), dbias = column sums of dz (deterministic two-stage sum).  workspace: b2g_mlp_elu_backward_workspace_floats floats. */
 int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* h_bf16 /* optional (rows, cols) bf16 copy of the output */, void* stream);
-int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbias, float* partial, int rows, int cols,
+int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz /* may be null when dz_bf16 is given */, float* dbias, float* partial, int rows, int cols,
                          void* dz_bf16 /* optional bf16 copy of dz */, void* stream);
 int b2g_mlp_elu_backward_workspace_floats(int rows, int cols);
 /* Backward of the two output heads on the last hidden layer h (rows x hidden): mu = h W_mu^T + b_mu (n_actions rows), value = h W_v^T + b_v.
@@ -540,6 +540,13 @@ int b2g_mlp_elu_backward_workspace_floats(int rows, int cols);
 int b2g_mlp_heads_backward(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
                            float* dh, float* dw_cat, float* partial, void* stream);
 int b2g_mlp_heads_backward_workspace_floats(int rows, int hidden, int n_actions);
+/* Same pass, the four parameter gradients stored where the caller keeps them (e.g. the .grad views of one flat gradient vector): no
+ * packed matrix, no split-and-accumulate kernels behind it. */
+int b2g_mlp_heads_backward_scatter(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
+                                   float* dh, float* dw_mu, float* db_mu, float* dw_v, float* db_v, float* partial, void* stream);
+/* Minibatch gather of the update: dst[r] = src[index[r]] for (rows, cols) float32 rows (cols % 4 == 0), as float32 (dst) and / or bf16
+ * (dst_bf16) in one pass (torch: index_select + a cast kernel). */
+int b2g_gather_rows(const float* src, const int64_t* index, int rows, int cols, float* dst, void* dst_bf16, void* stream);
 
 /* Global-norm clipping + Adam on one flat parameter vector (torch.optim.Adam semantics: no weight decay, no amsgrad).  The effective
  * gradient is grad * grad_scale (1 / world size after an all-reduce SUM); *step is advanced by one. */

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) k_elu_bwd_colsum(const float* __restrict_
             float4 d;
             d.x = g.x * (o.x > 0.0f ? 1.0f : o.x + 1.0f); d.y = g.y * (o.y > 0.0f ? 1.0f : o.y + 1.0f);
             d.z = g.z * (o.z > 0.0f ? 1.0f : o.z + 1.0f); d.w = g.w * (o.w > 0.0f ? 1.0f : o.w + 1.0f);
-            reinterpret_cast<float4*>(dz)[i] = d;
+            if (dz) reinterpret_cast<float4*>(dz)[i] = d;      // null: the caller only needs the bf16 copy (first layer: no dX)
             if (dz16) store_bf16x4(dz16, i, d);
             acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
         }
@@ -192,12 +192,46 @@ __global__ void __launch_bounds__(256) k_elu_bwd_colsum(const float* __restrict_
     }
 }
 
-__global__ void k_colsum_finalize(const float* __restrict__ partial, int n_blocks, int cols, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// second stage of the column sums: 32 columns x 8 row lanes per block; lane q adds partial rows q, q + 8, ... and the lanes are added
+// in order (deterministic).  `out` may be scattered: column c goes to out_of(c).
+constexpr int kFinLanes = 8;
+template <class OutOf>
+__device__ __forceinline__ void colsum_finalize_body(const float* __restrict__ partial, int n_blocks, int cols, OutOf out_of) {
+    __shared__ float red[kFinLanes][33];
+    const int tx = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float s = 0.0f;
-    for (int b = 0; b < n_blocks; b++) s += partial[(size_t)b * cols + c];
-    out[c] = s;
+    if (c < cols)
+        for (int b = q; b < n_blocks; b += kFinLanes) s += partial[(size_t)b * cols + c];
+    red[q][tx] = s;
+    __syncthreads();
+    if (q == 0 && c < cols) {
+        for (int k = 1; k < kFinLanes; k++) s += red[k][tx];
+        *out_of(c) = s;
+    }
+}
+__global__ void __launch_bounds__(32 * kFinLanes) k_colsum_finalize(const float* __restrict__ partial, int n_blocks, int cols, float* __restrict__ out) {
+    colsum_finalize_body(partial, n_blocks, cols, [=](int c) { return out + c; });
+}
+// heads: entry e = o (H + 1) + c of dWcat goes to the four parameter gradients (d W_mu | d b_mu | d W_v | d b_v)
+__global__ void __launch_bounds__(32 * kFinLanes) k_heads_finalize_scatter(const float* __restrict__ partial, int n_blocks, int H, int A, float* __restrict__ dw_mu,
+                                                                          float* __restrict__ db_mu, float* __restrict__ dw_v, float* __restrict__ db_v) {
+    colsum_finalize_body(partial, n_blocks, (A + 1) * (H + 1), [=](int e) {
+        const int o = e / (H + 1), c = e - o * (H + 1);
+        return o < A ? (c < H ? dw_mu + o * H + c : db_mu + o) : (c < H ? dw_v + c : db_v);
+    });
+}
+
+// rows idx[r] of src (cols % 4 == 0) -> dst (float32) and / or dst16 (bf16): the minibatch gather of the update
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ src, const long long* __restrict__ idx, int rows, int cols4, float* __restrict__ dst,
+                                                     __nv_bfloat16* __restrict__ dst16) {
+    const size_t n4 = (size_t)rows * cols4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols4), c4 = (int)(i - (size_t)r * cols4);
+        const float4 v = reinterpret_cast<const float4*>(src)[(size_t)idx[r] * cols4 + c4];
+        if (dst) reinterpret_cast<float4*>(dst)[i] = v;
+        if (dst16) store_bf16x4(dst16, i, v);
+    }
 }
 
 // ---- rollout bookkeeping of the learner: what rl_games' play_steps does between two env steps, as a handful of launches --------------
@@ -508,7 +542,7 @@ int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* h_bf
 int b2g_mlp_elu_backward_workspace_floats(int rows, int cols) { return ((rows + kColRows - 1) / kColRows) * cols; }
 
 int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbias, float* partial, int rows, int cols, void* dz_bf16, void* stream) {
-    if (!dh || !h || !dz || !dbias || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_elu_backward: null argument");
+    if (!dh || !h || (!dz && !dz_bf16) || !dbias || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_elu_backward: null argument");
     if (cols < 4 || (cols & 3) || cols > 1024) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_elu_backward: cols must be a multiple of 4, at most 1024");
     const int cols4 = cols / 4;
     int lanes = 256 / cols4;
@@ -517,7 +551,7 @@ int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbia
     const int blocks = (rows + kColRows - 1) / kColRows;
     cudaStream_t st = (cudaStream_t)stream;
     k_elu_bwd_colsum<<<blocks, threads, sizeof(float4) * lanes * cols4, st>>>(dh, h, dz, partial, rows, cols, reinterpret_cast<__nv_bfloat16*>(dz_bf16));
-    k_colsum_finalize<<<(cols + 127) / 128, 128, 0, st>>>(partial, blocks, cols, dbias);
+    k_colsum_finalize<<<(cols + 31) / 32, 32 * kFinLanes, 0, st>>>(partial, blocks, cols, dbias);
     return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_elu_backward: launch failed");
 }
 
@@ -589,21 +623,52 @@ int b2g_mlp_heads_backward_workspace_floats(int rows, int hidden, int n_actions)
     return ((rows + kHeadRows - 1) / kHeadRows) * (n_actions + 1) * (hidden + 1);
 }
 
-int b2g_mlp_heads_backward(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
-                           float* dh, float* dw_cat, float* partial, void* stream) {
-    if (!h || !dmu || !dv || !w_mu || !w_v || !dh || !dw_cat || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_heads_backward: null argument");
+static int heads_backward_launch(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
+                                 float* dh, float* partial, cudaStream_t st, int& blocks) {
+    if (!h || !dmu || !dv || !w_mu || !w_v || !dh || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_heads_backward: null argument");
     if (hidden < 1 || hidden > 256 || n_actions < 1 || n_actions > kMaxAct) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_heads_backward: hidden <= 256, actions <= 24");
     const int O = n_actions + 1;
     const size_t smem = sizeof(float) * ((size_t)kHeadRows * (hidden + O) + (size_t)O * hidden);
     static bool opted = false;
     if (!opted) { cudaFuncSetAttribute(k_heads_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); opted = true; }
     if (smem > 96 * 1024) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_heads_backward: tile does not fit shared memory");
-    const int blocks = (rows + kHeadRows - 1) / kHeadRows;
-    cudaStream_t st = (cudaStream_t)stream;
+    blocks = (rows + kHeadRows - 1) / kHeadRows;
     k_heads_backward<<<blocks, 256, smem, st>>>(h, dmu, dv, w_mu, w_v, rows, hidden, n_actions, dh, partial);
-    const int n_out = O * (hidden + 1);
-    k_colsum_finalize<<<(n_out + 127) / 128, 128, 0, st>>>(partial, blocks, n_out, dw_cat);
+    return B2G_OK;
+}
+
+int b2g_mlp_heads_backward(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
+                           float* dh, float* dw_cat, float* partial, void* stream) {
+    if (!dw_cat) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_heads_backward: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int blocks = 0;
+    const int rc = heads_backward_launch(h, dmu, dv, w_mu, w_v, rows, hidden, n_actions, dh, partial, st, blocks);
+    if (rc != B2G_OK) return rc;
+    const int n_out = (n_actions + 1) * (hidden + 1);
+    k_colsum_finalize<<<(n_out + 31) / 32, 32 * kFinLanes, 0, st>>>(partial, blocks, n_out, dw_cat);
     return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_heads_backward: launch failed");
+}
+
+int b2g_mlp_heads_backward_scatter(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
+                                   float* dh, float* dw_mu, float* db_mu, float* dw_v, float* db_v, float* partial, void* stream) {
+    if (!dw_mu || !db_mu || !dw_v || !db_v) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_heads_backward_scatter: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int blocks = 0;
+    const int rc = heads_backward_launch(h, dmu, dv, w_mu, w_v, rows, hidden, n_actions, dh, partial, st, blocks);
+    if (rc != B2G_OK) return rc;
+    const int n_out = (n_actions + 1) * (hidden + 1);
+    k_heads_finalize_scatter<<<(n_out + 31) / 32, 32 * kFinLanes, 0, st>>>(partial, blocks, hidden, n_actions, dw_mu, db_mu, dw_v, db_v);
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_heads_backward_scatter: launch failed");
+}
+
+int b2g_gather_rows(const float* src, const int64_t* index, int rows, int cols, float* dst, void* dst_bf16, void* stream) {
+    if (!src || !index || (!dst && !dst_bf16) || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_gather_rows: null argument");
+    if (cols < 4 || (cols & 3)) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_gather_rows: cols must be a multiple of 4");
+    const size_t n4 = (size_t)rows * (cols >> 2);
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    k_gather_rows<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<const long long*>(index), rows, cols >> 2, dst,
+                                                            reinterpret_cast<__nv_bfloat16*>(dst_bf16));
+    return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_gather_rows: launch failed");
 }
 
 int b2g_adam_clip_step(const b2g_adam_args* a, void* stream) {

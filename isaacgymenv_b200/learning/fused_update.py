@@ -70,6 +70,20 @@ class _PpoHead(torch.autograd.Function):
         return h.grad_mu * g, h.grad_value * g, h.grad_log_std * g, None
 
 
+class _PpoHeadSeed(torch.autograd.Function):
+    """Backward seed of :meth:`PpoHead.backward_direct`: a dummy scalar whose backward hands (mu, value) the gradients the head kernel
+    has already computed, unscaled (the caller's contract: ``.backward()`` with the default unit gradient)."""
+
+    @staticmethod
+    def forward(ctx, mu, value, head, grads):
+        ctx.grads = grads
+        return mu.new_empty(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.grads[0], ctx.grads[1], None, None
+
+
 class PpoHead:
     """Static buffers + argument block of ``b2g_ppo_head`` for one minibatch size (graph-capturable: no allocation per call)."""
 
@@ -97,7 +111,9 @@ class PpoHead:
         assert index is None or (index.dtype == torch.int64 and index.is_contiguous() and index.numel() == self.n_rows)
         self.buffers = (index, actions, old_mu, old_neglogp, advantages, old_values, returns)
 
-    def launch(self, mu, value, log_std):
+    def launch(self, mu, value, log_std, grad_log_std=None, grad_mu=None, grad_value=None):
+        """``grad_log_std``: where d loss / d log_std is stored (default: the head's own buffer) -- pass the parameter's ``.grad`` view
+        to skip the autograd edge (see :meth:`backward_direct`)."""
         assert self.buffers is not None, "bind() the rollout buffers first"
         mu, value, log_std = mu.contiguous(), value.contiguous(), log_std.contiguous()
         assert mu.shape == (self.n_rows, self.n_actions) and value.shape == (self.n_rows,)
@@ -105,9 +121,21 @@ class PpoHead:
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         e, cc, ec, bc, mb = self.hyper
         a = PpoHeadArgs(p(mu), p(value), p(log_std), p(index), p(actions), p(old_mu), p(old_nlp), p(adv), p(old_val), p(ret), self.n_rows, self.n_actions,
-                        e, cc, ec, bc, mb, p(self.grad_mu), p(self.grad_value), p(self.grad_log_std), p(self.out), p(self.partial))
+                        e, cc, ec, bc, mb, p(self.grad_mu if grad_mu is None else grad_mu), p(self.grad_value if grad_value is None else grad_value),
+                        p(self.grad_log_std if grad_log_std is None else grad_log_std), p(self.out), p(self.partial))
         self._keep = (mu, value, log_std)
         _lib.check(self.lib.b2g_ppo_head(C.byref(a), _stream(self.device)), "b2g_ppo_head")
+
+    def backward_direct(self, mu, value, log_std):
+        """Loss + backward without the scalar detour: the head kernel leaves d loss / d(mu, value) in its buffers and writes
+        d loss / d log_std straight into ``log_std.grad``; the network's backward starts from (mu, value).  Saves the clone, the
+        ones-like seed, three scale kernels and the log_std accumulation of ``loss(...).backward()``.  ``self.out`` holds the losses."""
+        assert log_std.grad is not None and log_std.grad.is_contiguous()
+        # gradients of (mu, value) in tensors allocated on the calling stream: handing the autograd engine buffers that were allocated on
+        # another stream (the head's persistent ones) makes it wait on that stream, which a CUDA-graph capture rejects
+        g_mu, g_v = torch.empty_like(mu), torch.empty_like(value)
+        self.launch(mu, value, log_std, grad_log_std=log_std.grad, grad_mu=g_mu, grad_value=g_v)
+        _PpoHeadSeed.apply(mu, value, self, (g_mu, g_v)).backward()
 
     def loss(self, mu, value, log_std):
         """Scalar loss with autograd edges to mu, value, log_std; ``self.out`` then holds (loss, a_loss, c_loss, b_loss, kl, entropy)."""
@@ -209,8 +237,23 @@ class RolloutKernels:
         _lib.check(self.lib.b2g_rollout_counter_advance(C.c_void_p(self.counter.data_ptr()), self._s()), "counter")
 
 
-def _mm_f32(a16, b16):
-    """bf16 x bf16 -> float32 (tensor cores, fp32 accumulation); older torch returns bf16, widened afterwards."""
+_MM_OUT_OK = None      # does torch.mm(..., out_dtype=float32, out=...) work in this torch? (probed once)
+
+
+def _mm_f32(a16, b16, out=None):
+    """bf16 x bf16 -> float32 (tensor cores, fp32 accumulation), optionally into ``out``; older torch returns bf16, widened afterwards."""
+    global _MM_OUT_OK
+    if out is not None:
+        if _MM_OUT_OK is None:
+            try:
+                torch.mm(a16, b16, out_dtype=torch.float32, out=out)
+                _MM_OUT_OK = True
+                return out
+            except (TypeError, RuntimeError):
+                _MM_OUT_OK = False
+        if _MM_OUT_OK:
+            return torch.mm(a16, b16, out_dtype=torch.float32, out=out)
+        return out.copy_(_mm_f32(a16, b16))
     try:
         return torch.mm(a16, b16, out_dtype=torch.float32)
     except TypeError:
@@ -226,34 +269,41 @@ class _LinearELU(torch.autograd.Function):
     activations and of dZ on the way, so no separate cast pass exists.  Returns (h, bf16 copy of h or None)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, x16):
+    def forward(ctx, x, weight, bias, x16, direct):
         lib = _lib.load()
+        ctx.direct = bool(direct)
+        ctx.set_materialize_grads(False)      # the bf16 copy is not differentiable: no zero tensor for its gradient
         h = torch.mm(x, weight.t())
         h16 = torch.empty_like(h, dtype=torch.bfloat16) if x16 is not None else None
         _lib.check(lib.b2g_mlp_bias_elu(C.c_void_p(h.data_ptr()), C.c_void_p(bias.data_ptr()), h.shape[0], h.shape[1],
                                         C.c_void_p(h16.data_ptr()) if h16 is not None else None, _stream(h.device)), "b2g_mlp_bias_elu")
-        ctx.save_for_backward(x, weight, h, x16)
+        ctx.save_for_backward(x, weight, h, x16, bias)
         ctx.mark_non_differentiable(*([h16] if h16 is not None else []))
         return h, h16
 
     @staticmethod
     def backward(ctx, dh, _unused=None):
-        x, weight, h, x16 = ctx.saved_tensors
+        x, weight, h, x16, bias = ctx.saved_tensors
         lib = _lib.load()
         dh = dh.contiguous()
         rows, cols = h.shape
-        dz = torch.empty_like(h)
+        need_dx = ctx.needs_input_grad[0]
+        direct = ctx.direct and weight.grad is not None and bias.grad is not None      # store into the .grad views, return no gradient
         dz16 = torch.empty_like(h, dtype=torch.bfloat16) if x16 is not None else None
-        db = torch.empty(cols, device=h.device, dtype=h.dtype)
+        dz = torch.empty_like(h) if (need_dx or dz16 is None) else None               # first layer with a bf16 copy: nobody reads the float32 dz
+        db = bias.grad if direct else torch.empty(cols, device=h.device, dtype=h.dtype)
         ws = torch.empty(int(lib.b2g_mlp_elu_backward_workspace_floats(rows, cols)), device=h.device, dtype=h.dtype)
-        _lib.check(lib.b2g_mlp_elu_backward(C.c_void_p(dh.data_ptr()), C.c_void_p(h.data_ptr()), C.c_void_p(dz.data_ptr()), C.c_void_p(db.data_ptr()),
+        _lib.check(lib.b2g_mlp_elu_backward(C.c_void_p(dh.data_ptr()), C.c_void_p(h.data_ptr()), C.c_void_p(dz.data_ptr()) if dz is not None else None, C.c_void_p(db.data_ptr()),
                                             C.c_void_p(ws.data_ptr()), rows, cols, C.c_void_p(dz16.data_ptr()) if dz16 is not None else None,
                                             _stream(h.device)), "b2g_mlp_elu_backward")
-        dx = torch.mm(dz, weight) if ctx.needs_input_grad[0] else None
+        dx = torch.mm(dz, weight) if need_dx else None
         dw = None
         if ctx.needs_input_grad[1]:
-            dw = _mm_f32(dz16.t(), x16) if x16 is not None else torch.mm(dz.t(), x)
-        return dx, dw, db, None
+            if direct:
+                _mm_f32(dz16.t(), x16, out=weight.grad) if x16 is not None else torch.mm(dz.t(), x, out=weight.grad)
+            else:
+                dw = _mm_f32(dz16.t(), x16) if x16 is not None else torch.mm(dz.t(), x)
+        return dx, dw, (None if direct else db), None, None
 
 
 def _protos():
@@ -270,47 +320,71 @@ def _protos():
         lib.b2g_mlp_heads_backward.restype = C.c_int
         lib.b2g_mlp_heads_backward_workspace_floats.argtypes = [C.c_int, C.c_int, C.c_int]
         lib.b2g_mlp_heads_backward_workspace_floats.restype = C.c_int
+        lib.b2g_mlp_heads_backward_scatter.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+        lib.b2g_mlp_heads_backward_scatter.restype = C.c_int
+        lib.b2g_gather_rows.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        lib.b2g_gather_rows.restype = C.c_int
         lib._b2g_mlp_protos = True
     return lib
 
 
-def linear_elu(x, weight, bias, x16=None):
+def linear_elu(x, weight, bias, x16=None, direct_grad=False):
     """``F.elu(F.linear(x, weight, bias))`` through the fused kernels (CUDA float32, width a multiple of 4).  Returns (h, h16): h16 is a
-    bf16 copy of h when a bf16 copy of the input (``x16``) was given -- pass it on to the next layer."""
+    bf16 copy of h when a bf16 copy of the input (``x16``) was given -- pass it on to the next layer.  ``direct_grad``: the backward
+    pass STORES d weight / d bias into the parameters' existing ``.grad`` tensors (overwrite, not accumulate: every parameter used once
+    per backward, as in the PPO minibatch step) and hands autograd no gradient for them -- no accumulation kernels."""
     _protos()
-    return _LinearELU.apply(x.contiguous(), weight, bias, x16)
+    return _LinearELU.apply(x.contiguous(), weight, bias, x16, direct_grad)
 
 
 class _Heads(torch.autograd.Function):
     """(mu, value) = (h W_mu^T + b_mu, h W_v^T + b_v); the backward of both heads is one kernel (``b2g_mlp_heads_backward``)."""
 
     @staticmethod
-    def forward(ctx, h, w_mu, b_mu, w_v, b_v):
+    def forward(ctx, h, w_mu, b_mu, w_v, b_v, direct):
+        ctx.direct = bool(direct)
         mu = torch.addmm(b_mu, h, w_mu.t())
         v = torch.addmm(b_v, h, w_v.t()).squeeze(-1)
-        ctx.save_for_backward(h, w_mu, w_v)
+        ctx.save_for_backward(h, w_mu, w_v, b_mu, b_v)
         return mu, v
 
     @staticmethod
     def backward(ctx, dmu, dv):
-        h, w_mu, w_v = ctx.saved_tensors
+        h, w_mu, w_v, b_mu, b_v = ctx.saved_tensors
         lib = _lib.load()
         rows, hid = h.shape
         A = w_mu.shape[0]
         dmu, dv = dmu.contiguous(), dv.contiguous()
         dh = torch.empty_like(h)
-        cat = torch.empty(A + 1, hid + 1, device=h.device, dtype=h.dtype)
         ws = torch.empty(int(lib.b2g_mlp_heads_backward_workspace_floats(rows, hid, A)), device=h.device, dtype=h.dtype)
         p = lambda t: C.c_void_p(t.data_ptr())
+        if ctx.direct and all(t.grad is not None for t in (w_mu, b_mu, w_v)):      # store into the .grad views (see linear_elu)
+            # ... except the one-element value bias, which still goes back through autograd: with NO gradient accumulation node left
+            # in the backward pass, capturing it into a CUDA graph fails (torch 2.11: "dependency created on uncaptured work in
+            # another stream"); one 1-element accumulation keeps the engine on the path it takes for every ordinary network
+            db_v = torch.empty_like(b_v)
+            _lib.check(lib.b2g_mlp_heads_backward_scatter(p(h), p(dmu), p(dv), p(w_mu), p(w_v), rows, hid, A, p(dh), p(w_mu.grad), p(b_mu.grad),
+                                                          p(w_v.grad), p(db_v), p(ws), _stream(h.device)), "b2g_mlp_heads_backward_scatter")
+            return dh, None, None, None, db_v, None
+        cat = torch.empty(A + 1, hid + 1, device=h.device, dtype=h.dtype)
         _lib.check(lib.b2g_mlp_heads_backward(p(h), p(dmu), p(dv), p(w_mu), p(w_v), rows, hid, A, p(dh), p(cat), p(ws), _stream(h.device)),
                    "b2g_mlp_heads_backward")
-        return dh, cat[:A, :hid], cat[:A, hid], cat[A:, :hid], cat[A:, hid]
+        return dh, cat[:A, :hid], cat[:A, hid], cat[A:, :hid], cat[A:, hid], None
 
 
-def heads(h, w_mu, b_mu, w_v, b_v):
+def heads(h, w_mu, b_mu, w_v, b_v, direct_grad=False):
     """Both output heads of the actor-critic on the last hidden layer (shared-trunk networks: one ``h`` feeds both)."""
     _protos()
-    return _Heads.apply(h.contiguous(), w_mu, b_mu, w_v, b_v)
+    return _Heads.apply(h.contiguous(), w_mu, b_mu, w_v, b_v, direct_grad)
+
+
+def gather_rows(src, index, out=None, out_bf16=None):
+    """``src[index]`` for a (rows, cols) float32 CUDA matrix (cols % 4 == 0) into ``out`` (float32) and / or ``out_bf16`` in one pass."""
+    lib = _protos()
+    rows, cols = int(index.numel()), int(src.shape[1])
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(lib.b2g_gather_rows(p(src), p(index), rows, cols, p(out), p(out_bf16), _stream(src.device)), "b2g_gather_rows")
+    return out, out_bf16
 
 
 class FlatParameters:

@@ -62,6 +62,7 @@ class ActorCritic(nn.Module):
         self.separate = bool(separate)
         self.fused_layers = False      # set by PPO(fused_update=True): hidden layers through learning/fused_update.linear_elu in training mode
         self.bf16_wgrad = False        # weight-gradient GEMMs on bf16 operands (fp32 accumulate / output): PPOConfig.mixed_precision
+        self.direct_grad = False       # fused layers store parameter gradients into the existing .grad views (PPO fused update: one use per backward)
         self.trunk, last = mlp()
         self.critic_trunk = mlp()[0] if self.separate else None
         self.mu = nn.Linear(last, num_actions)
@@ -73,18 +74,18 @@ class ActorCritic(nn.Module):
 
         for m in seq:
             if isinstance(m, nn.Linear):
-                x, x16 = linear_elu(x, m.weight, m.bias, x16)
+                x, x16 = linear_elu(x, m.weight, m.bias, x16, self.direct_grad)
         return x
 
-    def forward(self, obs):
+    def forward(self, obs, obs16=None):
         if self.fused_layers and obs.is_cuda and torch.is_grad_enabled():
             # training pass through the library's kernels around the cuBLAS GEMMs (learning/fused_update.py)
             from .fused_update import heads
 
-            x16 = obs.to(torch.bfloat16) if self.bf16_wgrad else None
+            x16 = (obs16 if obs16 is not None else obs.to(torch.bfloat16)) if self.bf16_wgrad else None
             h = self._tower(self.trunk, obs, x16)
             if not self.separate:
-                mu, v = heads(h, self.mu.weight, self.mu.bias, self.value.weight, self.value.bias)
+                mu, v = heads(h, self.mu.weight, self.mu.bias, self.value.weight, self.value.bias, self.direct_grad)
                 return mu, self.log_std.expand(obs.shape[0], -1), v
             hv = self._tower(self.critic_trunk, obs, x16)
             return self.mu(h), self.log_std.expand(obs.shape[0], -1), self.value(hv).squeeze(-1)
@@ -238,6 +239,9 @@ class PPO:
             self.rk = RolloutKernels(self, seed)
             self.head = PpoHead(self.mb, env.num_acts, dev, cfg.e_clip, cfg.critic_coef, cfg.entropy_coef, cfg.bounds_loss_coef)
             self.head.bind(self.idx, self.b_act.view(T * n, -1), self.b_mu.view(T * n, -1), self.b_nlp.view(-1), self.f_adv, self.f_val, self.f_ret)
+            self.mb_obs = torch.zeros(self.mb, env.num_obs, device=dev)
+            self.mb_obs16 = torch.zeros(self.mb, env.num_obs, device=dev, dtype=torch.bfloat16)
+            self.model.direct_grad = True
         self._g_rollout = None
         self._g_update = None
 
@@ -348,10 +352,16 @@ class PPO:
         T, N = cfg.horizon_length, self.env.num_envs
         idx = self.idx
         if self.fused_update:
-            mu, _, v = self.model(self.b_obs.reshape(T * N, -1)[idx])
-            loss = self.head.loss(mu, v, self.model.log_std)
-            self.flatp.grad.zero_()
-            loss.backward()
+            from .fused_update import gather_rows
+
+            f_obs = self.b_obs.reshape(T * N, -1)
+            if f_obs.shape[1] % 4 == 0:      # minibatch rows as float32 + bf16 in one pass
+                gather_rows(f_obs, idx, self.mb_obs, self.mb_obs16 if self.model.bf16_wgrad else None)
+                mu, _, v = self.model(self.mb_obs, self.mb_obs16 if self.model.bf16_wgrad else None)
+            else:
+                mu, _, v = self.model(f_obs[idx])
+            self.flatp.grad.zero_()          # parameters outside the fused layers (separate-tower heads) still accumulate
+            self.head.backward_direct(mu, v, self.model.log_std)
             if self.multi_gpu:
                 import torch.distributed as dist
 
@@ -410,6 +420,9 @@ class PPO:
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:      # the parameters' accumulation nodes were created by the eager warm-up, on another stream: expected here
+            quiet(False)
         with torch.cuda.graph(g):
             fn()
         return g

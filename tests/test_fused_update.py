@@ -341,3 +341,53 @@ def test_heads_backward_kernel_matches_torch(rows, hid, A):
         scale = float(y.grad.abs().max())
         assert x.grad.shape == y.grad.shape, name
         assert torch.allclose(x.grad, y.grad, rtol=1e-4, atol=2e-5 * scale), (name, float((x.grad - y.grad).abs().max()), scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use16", [False, True])
+def test_direct_gradient_stores_equal_autograd_accumulation(use16):
+    """direct_grad=True: the fused layers and heads STORE the parameter gradients into pre-existing .grad tensors (pre-filled with junk
+    here: overwrite, not accumulate) and hand autograd nothing -- same numbers as the autograd path."""
+    from isaacgymenv_b200.learning.fused_update import heads, linear_elu
+
+    dev = "cuda:0"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device=dev).manual_seed(11)
+    rows = 4096
+    x = torch.randn(rows, 48, device=dev, generator=g)
+    shapes = [(256, 48), (256,), (64, 256), (64,), (12, 64), (12,), (1, 64), (1,)]
+    init = [torch.randn(*s, device=dev, generator=g) / 8 for s in shapes]
+    um, uv = torch.randn(rows, 12, device=dev, generator=g), torch.randn(rows, device=dev, generator=g)
+    res = []
+    for direct in (False, True):
+        p = [t.clone().requires_grad_() for t in init]
+        if direct:
+            for i, t in enumerate(p):      # junk everywhere the backward pass stores; the value bias (one element) still accumulates
+                t.grad = torch.full_like(t, 123.0) if i != 7 else torch.zeros_like(t)
+        x16 = x.to(torch.bfloat16) if use16 else None
+        h1, h16 = linear_elu(x, p[0], p[1], x16, direct)
+        h2, _ = linear_elu(h1, p[2], p[3], h16, direct)
+        mu, v = heads(h2, p[4], p[5], p[6], p[7], direct)
+        torch.autograd.backward([mu, v], [um, uv])
+        res.append([t.grad.clone() for t in p])
+    torch.cuda.synchronize()
+    for a, b, s in zip(res[0], res[1], shapes):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(a.abs().max())), (s, float((a - b).abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,n", [(32768, 48, 196608), (1000, 188, 5000), (5, 4, 9)])
+def test_gather_rows_kernel(rows, cols, n):
+    from isaacgymenv_b200.learning.fused_update import gather_rows
+
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(rows)
+    src = torch.randn(n, cols, device=dev, generator=g)
+    idx = torch.randint(0, n, (rows,), device=dev, generator=g)
+    out, out16 = torch.zeros(rows, cols, device=dev), torch.zeros(rows, cols, device=dev, dtype=torch.bfloat16)
+    gather_rows(src, idx, out, out16)
+    torch.cuda.synchronize()
+    assert torch.equal(out, src[idx]) and torch.equal(out16, src[idx].to(torch.bfloat16))
+    only16 = torch.zeros_like(out16)
+    gather_rows(src, idx, None, only16)
+    assert torch.equal(only16, out16)
