@@ -43,6 +43,8 @@ TASKS = {
                     "dt 0.005 s, random actions"),
     "Houndarm": (356, 8192, "k_houndarm_step", None, "Houndarm fixed-base 6-DOF arm reach (OSC: two 6x6 inversions per step), 8192 envs/GPU, dt 0.01667 s x 2 sub-steps, "
                  "random actions"),
+    "Manipulator": (376, 8192, "k_houndarm_step", None, "Manipulator fixed-base 7-DOF Franka arm reach (OSC: a 7x7 and a 6x6 inversion per step), 8192 envs/GPU, "
+                    "dt 0.01667 s x 2 sub-steps, random actions"),
 }
 
 

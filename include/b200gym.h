@@ -31,7 +31,8 @@ extern "C" {
 #define B2G_MAX_LINKS (B2G_MAX_DOF + 1)
 #define B2G_MAX_BODIES 32
 #define B2G_MAX_CHAINS 8
-#define B2G_MAX_CHAIN_LEN 6
+#define B2G_MAX_CHAIN_LEN 6        /* chains of a floating-base robot */
+#define B2G_MAX_FIXED_CHAIN_LEN 7  /* the single chain of a fixed-base arm (Manipulator: 7-DOF Franka) */
 #define B2G_MAX_CPTS 128
 #define B2G_LINK_SCALE_COLS 6
 #define B2G_MAX_CONTACTS_PER_CHAIN 8   /* upper bound of b2g_sim_params::max_contacts_per_chain */
@@ -255,7 +256,10 @@ int b2g_task_cartpole_create(b2g_sim* sim, const b2g_cartpole_cfg* cfg);
  * end-effector velocity (:462-493; the reference refreshes them at the end of the previous post_physics_step, after resets) ->
  * sub-steps with effort drives -> post_physics_step: progress, reset_idx (:394-459: 3 command draws, 6 joint-noise draws,
  * clamped to the limits, reset_buf = 0), observations [eef pos, eef quat, command] (:383-392), reward / reset (:550-567),
- * time-outs and clamped observations (vec_task.py:394-402).  Needs a fixed-base single chain of <= 6 DOF. */
+ * time-outs and clamped observations (vec_task.py:394-402).  Needs a fixed-base single chain of <= 6 DOF.
+ * The same struct drives Manipulator (tasks/manipulator.py: the same task on the 7-DOF Franka arm): n DOFs <= B2G_MAX_FIXED_CHAIN_LEN,
+ * six actions, null-space posture and reset around default_dof_pos (:153-155, :407-414), the last n_reset_tail joints reset to their
+ * default without noise (:417, written for a gripper the asset does not have: it hits the arm's last two joints). */
 typedef struct b2g_houndarm_cfg {
     float clip_obs, clip_actions, action_scale, dof_noise;
     float cmd_limit[6];
@@ -265,6 +269,9 @@ typedef struct b2g_houndarm_cfg {
     int32_t eef_body, jac_body;        /* API bodies: end-effector state row; row of the fixed-base Jacobian the task takes */
     int64_t max_episode_length;
     uint64_t seed;
+    float default_dof_pos[8];          /* zeros for Houndarm (hound_arm.py:160-162) */
+    int32_t n_reset_tail;              /* 0 for Houndarm, 2 for Manipulator */
+    int32_t pad_;
 } b2g_houndarm_cfg;
 int b2g_task_houndarm_create(b2g_sim* sim, const b2g_houndarm_cfg* cfg);
 

@@ -38,9 +38,10 @@ def task_map():
     except ImportError:
         pass
     try:
-        from .tasks.hound_arm import Houndarm
+        from .tasks.hound_arm import Houndarm, Manipulator
 
         m["Houndarm"] = Houndarm
+        m["Manipulator"] = Manipulator
     except ImportError:
         pass
     return m

@@ -15,6 +15,7 @@ MAX_LINKS = MAX_DOF + 1
 MAX_BODIES = 32
 MAX_CHAINS = 8
 MAX_CHAIN_LEN = 6
+MAX_FIXED_CHAIN_LEN = 7
 MAX_CPTS = 128
 MAX_CONTACTS_PER_CHAIN = 8
 LINK_SCALE_COLS = 6
@@ -97,7 +98,8 @@ class CartpoleCfg(C.Structure):
 class HoundarmCfg(C.Structure):
     _fields_ = [("clip_obs", f32), ("clip_actions", f32), ("action_scale", f32), ("dof_noise", f32), ("cmd_limit", f32 * 6),
                 ("kp", f32), ("kp_null", f32), ("cmd_range", f32 * 6), ("dist_scale", f32), ("vel_scale", f32),
-                ("eef_body", i32), ("jac_body", i32), ("max_episode_length", C.c_int64), ("seed", C.c_uint64)]
+                ("eef_body", i32), ("jac_body", i32), ("max_episode_length", C.c_int64), ("seed", C.c_uint64),
+                ("default_dof_pos", f32 * 8), ("n_reset_tail", i32), ("pad_", i32)]
 
 
 class TerrainCfg(C.Structure):
@@ -133,7 +135,7 @@ def _fill(dst, src):
 def pack_model(art) -> Model:
     """``model.urdf.Articulation`` -> C ``b2g_model`` (float32 parameters)."""
     nd, nb, ncp, nc = art.num_dofs, art.num_bodies, len(art.cp_link), len(art.chain_start)
-    if nd > MAX_DOF or nb > MAX_BODIES or ncp > MAX_CPTS or nc > MAX_CHAINS or (nc and max(art.chain_len) > MAX_CHAIN_LEN):
+    if nd > MAX_DOF or nb > MAX_BODIES or ncp > MAX_CPTS or nc > MAX_CHAINS or (nc and max(art.chain_len) > (MAX_FIXED_CHAIN_LEN if (art.fixed_base and nc == 1) else MAX_CHAIN_LEN)):
         raise ValueError(f"articulation too large for the ABI limits (dof {nd}, bodies {nb}, contact points {ncp}, chains {nc})")
     m = Model()
     m.fixed_base = int(art.fixed_base)

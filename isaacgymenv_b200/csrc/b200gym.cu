@@ -76,7 +76,8 @@ Variant pick_variant(const b2g_model& m) {
     for (int c = 0; c < m.n_chains; c++) pieces += m.chain_len[c] > kSegLinks ? 1 : 0;
     const char* seg = getenv("B2G_SEGMENTS");
     if (seg && seg[0] == '1' && !m.fixed_base && m.n_chains > 0 && pieces <= B2G_MAX_CHAINS) return {8, 3, false, true};
-    return {8, 6, m.fixed_base != 0};
+    if (m.fixed_base) return {8, B2G_MAX_FIXED_CHAIN_LEN, true};      // one lane in use: the arm's single chain (<= 7 links)
+    return {8, 6, false};
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -192,11 +193,12 @@ __global__ void __launch_bounds__(kBlock, MINB) k_anymal_step(SimArgs A, TaskArg
     }
 }
 
+template <int NJ>
 __global__ void __launch_bounds__(kBlock) k_houndarm_step(SimArgs A, TaskArgs T) {
     extern __shared__ __align__(16) float smem[];
     int env, lane; bool valid; ScratchStrided sc; float* bf;
     thread_ids<1>(A.n_envs, A.M->n_bodies, smem, env, lane, valid, sc, bf, A.M->n_dof, A.P.max_contacts);
-    houndarm_step_thread(A, T, env, valid, sc, bf);
+    houndarm_step_thread<NJ>(A, T, env, valid, sc, bf);
 }
 
 __global__ void __launch_bounds__(kBlock) k_cartpole_step(SimArgs A, TaskArgs T) {
@@ -595,7 +597,7 @@ int launch_simulate(b2g_sim* s, cudaStream_t st) {
     const bool hf = s->has_hf;
     if (s->v.lanes == 1) k_simulate<1, 2, true, false><<<grid, kBlock, sm, st>>>(A);
     else if (s->v.lanes == 4) { if (hf) k_simulate<4, 3, false, true><<<grid, kBlock, sm, st>>>(A); else k_simulate<4, 3, false, false><<<grid, kBlock, sm, st>>>(A); }
-    else if (s->v.fixed) k_simulate<8, 6, true, false><<<grid, kBlock, sm, st>>>(A);
+    else if (s->v.fixed) k_simulate<8, 7, true, false><<<grid, kBlock, sm, st>>>(A);
     else if (s->v.seg) { if (hf) k_simulate<8, 3, false, true><<<grid, kBlock, sm, st>>>(A); else k_simulate<8, 3, false, false><<<grid, kBlock, sm, st>>>(A); }
     else { if (hf) k_simulate<8, 6, false, true><<<grid, kBlock, sm, st>>>(A); else k_simulate<8, 6, false, false><<<grid, kBlock, sm, st>>>(A); }
     s->launches++;
@@ -648,7 +650,8 @@ int launch_anymal_step(b2g_sim* s, const float* actions_dev, cudaStream_t st, in
     if (s->task_kind == 4) {     // one thread per environment whatever the generic kernels' lane count is
         const int g1 = (s->n_envs + kBlock / kSparse - 1) / (kBlock / kSparse);
         const size_t sm1 = sizeof(float) * ((size_t)kBlock * contact_slots(s->params) * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + (kLinksShared ? 4 + link_store_floats(kBlock, s->model.n_dof) : 0));
-        k_houndarm_step<<<g1, kBlock, sm1, st>>>(A, T);
+        if (s->model.n_dof > 6) k_houndarm_step<7><<<g1, kBlock, sm1, st>>>(A, T);      // Manipulator (7-DOF Franka)
+        else k_houndarm_step<6><<<g1, kBlock, sm1, st>>>(A, T);
         s->launches++;
         CUDA_TRY(cudaGetLastError());
         return B2G_OK;
@@ -855,7 +858,7 @@ int b2g_sim_prepare(b2g_sim* s) {
         cudaFuncSetAttribute(k_terrain_phys<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_terrain_phys<8, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(k_simulate<8, 6, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_simulate<8, 7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_simulate<8, 6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_simulate<8, 6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_anymal_step<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
@@ -870,7 +873,7 @@ int b2g_sim_prepare(b2g_sim* s) {
         cudaFuncSetAttribute(k_cartpole_step, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-        cudaFuncSetAttribute(k_probe<8, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+        cudaFuncSetAttribute(k_probe<8, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         cudaFuncSetAttribute(k_probe<8, 6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
         s->prepared = true;
         return (int)B2G_OK;
@@ -976,7 +979,7 @@ int b2g_sim_forward_dynamics(b2g_sim* s, float* qdd, float* a0, void* stream) {
         cudaStream_t st = (cudaStream_t)stream;
         if (s->v.lanes == 1) k_probe<1, 2, true><<<grid, kBlock, sm, st>>>(A, qdd, a0);
         else if (s->v.lanes == 4) k_probe<4, 3, false><<<grid, kBlock, sm, st>>>(A, qdd, a0);
-        else if (s->v.fixed) k_probe<8, 6, true><<<grid, kBlock, sm, st>>>(A, qdd, a0);
+        else if (s->v.fixed) k_probe<8, 7, true><<<grid, kBlock, sm, st>>>(A, qdd, a0);
         else if (s->v.seg) k_probe<8, 3, false><<<grid, kBlock, sm, st>>>(A, qdd, a0);
         else k_probe<8, 6, false><<<grid, kBlock, sm, st>>>(A, qdd, a0);
         s->launches++;
@@ -1064,8 +1067,9 @@ int b2g_task_cartpole_create(b2g_sim* s, const b2g_cartpole_cfg* cfg) {
 int b2g_task_houndarm_create(b2g_sim* s, const b2g_houndarm_cfg* cfg) {
     if (!s || !cfg) return fail(B2G_ERR_ARG, "null argument");
     if (!s->prepared) return fail(B2G_ERR_STATE, "task created before prepare_sim");
-    if (!s->model.fixed_base || s->model.n_chains != 1 || s->model.n_dof < 1 || s->model.n_dof > 6)
-        return fail(B2G_ERR_UNSUPPORTED, "Houndarm needs a fixed-base single chain of at most 6 DOF");
+    if (!s->model.fixed_base || s->model.n_chains != 1 || s->model.n_dof < 1 || s->model.n_dof > B2G_MAX_FIXED_CHAIN_LEN)
+        return fail(B2G_ERR_UNSUPPORTED, "Houndarm / Manipulator need a fixed-base single chain of at most 7 DOF");
+    if (cfg->n_reset_tail < 0 || cfg->n_reset_tail > s->model.n_dof) return fail(B2G_ERR_ARG, "n_reset_tail out of range");
     if (cfg->eef_body < 0 || cfg->eef_body >= s->model.n_bodies || cfg->jac_body < 0 || cfg->jac_body >= s->model.n_bodies)
         return fail(B2G_ERR_ARG, "eef_body / jac_body out of range");
     if (!(cfg->action_scale != 0.0f)) return fail(B2G_ERR_ARG, "action_scale must be non-zero");
@@ -1075,8 +1079,9 @@ int b2g_task_houndarm_create(b2g_sim* s, const b2g_houndarm_cfg* cfg) {
     s->task_kind = 4;
     if (s->has_task) return B2G_OK;
     const size_t sm1 = sizeof(float) * ((size_t)kBlock * contact_slots(s->params) * CF_COUNT + (size_t)kBlock * s->model.n_bodies * 3 + (kLinksShared ? 4 + link_store_floats(kBlock, s->model.n_dof) : 0));
-    cudaFuncSetAttribute(k_houndarm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-    return alloc_task_buffers(s, 10, s->model.n_dof, 9);
+    cudaFuncSetAttribute(k_houndarm_step<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    cudaFuncSetAttribute(k_houndarm_step<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    return alloc_task_buffers(s, 10, 6, 3 + s->model.n_dof);      // six actions (end-effector pose change), 3 command + n joint-noise draws per reset
 }
 
 int b2g_task_terrain_create(b2g_sim* s, const b2g_terrain_cfg* cfg, const int16_t* hs_host, const float* origins_host) {

@@ -26,7 +26,7 @@ inline void build_segments(DevModel& d) {
     d.n_seg = 0; d.n_seg_store = 0;
     int n = d.n_chains;
     for (int c = 0; c < d.n_chains; c++) n += d.chain_len[c] > kSegLinks ? 1 : 0;
-    if (n > B2G_MAX_CHAINS || d.n_chains == 0) return;
+    if (n > B2G_MAX_CHAINS || d.n_chains == 0 || d.fixed_base) return;
     int next = d.n_chains;
     for (int c = 0; c < d.n_chains; c++) {
         const int len = d.chain_len[c];
@@ -56,8 +56,9 @@ inline int pack_dev_model(const b2g_model& m, const b2g_dof_props& p, DevModel& 
     d.fixed_base = m.fixed_base; d.n_dof = m.n_dof; d.n_bodies = m.n_bodies; d.n_chains = m.n_chains;
     int expect = 0;
     for (int c = 0; c < m.n_chains; c++) {
-        if (m.chain_start[c] != expect || m.chain_len[c] < 1 || m.chain_len[c] > B2G_MAX_CHAIN_LEN) {
-            *why = "chains must be contiguous, non-empty and at most B2G_MAX_CHAIN_LEN long";
+        const int max_len = (m.fixed_base && m.n_chains == 1) ? B2G_MAX_FIXED_CHAIN_LEN : B2G_MAX_CHAIN_LEN;
+        if (m.chain_start[c] != expect || m.chain_len[c] < 1 || m.chain_len[c] > max_len) {
+            *why = "chains must be contiguous, non-empty and at most B2G_MAX_CHAIN_LEN (fixed-base single chain: B2G_MAX_FIXED_CHAIN_LEN) long";
             return -1;
         }
         d.chain_start[c] = m.chain_start[c]; d.chain_len[c] = m.chain_len[c];

@@ -469,86 +469,100 @@ B2G_HD B2G_INL float norm3(const float* f) { return sqrtf(f[0] * f[0] + f[1] * f
 // 1e8-1e10, where a float32 evaluation -- the reference's included -- is dominated by round-off.  The handful of 6x6 operations
 // per policy step are therefore carried out in float64 (a few thousand DP flops per environment), inputs and outputs float32.
 typedef double osc_real;
-B2G_HD inline void inv6(const osc_real* a, osc_real* inv) {
-    osc_real m[6][12];
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) { m[i][j] = a[i * 6 + j]; m[i][6 + j] = (i == j) ? 1.0 : 0.0; }
-    for (int c = 0; c < 6; c++) {
+// n x n inverse, row-major with leading dimension n (n <= 7)
+B2G_HD inline void inv_n(const osc_real* a, osc_real* inv, int n) {
+    osc_real m[7][14];
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) { m[i][j] = a[i * n + j]; m[i][n + j] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < n; c++) {
         int piv = c;
         osc_real best = fabs(m[c][c]);
-        for (int r = c + 1; r < 6; r++) if (fabs(m[r][c]) > best) { best = fabs(m[r][c]); piv = r; }
-        if (piv != c) for (int j = 0; j < 12; j++) { const osc_real t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
+        for (int r = c + 1; r < n; r++) if (fabs(m[r][c]) > best) { best = fabs(m[r][c]); piv = r; }
+        if (piv != c) for (int j = 0; j < 2 * n; j++) { const osc_real t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
         const osc_real d = 1.0 / m[c][c];
-        for (int j = 0; j < 12; j++) m[c][j] *= d;
-        for (int r = 0; r < 6; r++) {
+        for (int j = 0; j < 2 * n; j++) m[c][j] *= d;
+        for (int r = 0; r < n; r++) {
             if (r == c) continue;
             const osc_real f = m[r][c];
-            for (int j = 0; j < 12; j++) m[r][j] -= f * m[c][j];
+            for (int j = 0; j < 2 * n; j++) m[r][j] -= f * m[c][j];
         }
     }
-    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) inv[i * 6 + j] = m[i][6 + j];
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) inv[i * n + j] = m[i][n + j];
 }
-B2G_HD inline void mm6(const osc_real* a, const osc_real* b, osc_real* o, bool ta = false, bool tb = false) {
-    osc_real t[36];
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) {
+// o (r x c) = op(a) op(b), inner dimension k; a is stored (r x k) or, with ta, (k x r); b (k x c) or, with tb, (c x k); o may alias a or b
+B2G_HD inline void mat_mul(const osc_real* a, const osc_real* b, osc_real* o, int r, int k, int c, bool ta = false, bool tb = false) {
+    osc_real t[49];
+    for (int i = 0; i < r; i++)
+        for (int j = 0; j < c; j++) {
             osc_real acc = 0.0;
-            for (int k = 0; k < 6; k++) acc += (ta ? a[k * 6 + i] : a[i * 6 + k]) * (tb ? b[j * 6 + k] : b[k * 6 + j]);
-            t[i * 6 + j] = acc;
+            for (int q = 0; q < k; q++) acc += (ta ? a[q * r + i] : a[i * k + q]) * (tb ? b[j * k + q] : b[q * c + j]);
+            t[i * c + j] = acc;
         }
-    for (int i = 0; i < 36; i++) o[i] = t[i];
+    for (int i = 0; i < r * c; i++) o[i] = t[i];
 }
-// _compute_osc_torques (tasks/useful_hound.py:660-691), split in two because the mass-matrix block, the Jacobian slice, the
-// commanded pose change and the end-effector velocity row do not change inside one policy step:
+// _compute_osc_torques (tasks/useful_hound.py:660-691, hound_arm.py / manipulator.py:534-560), split in two because the mass-matrix
+// block, the Jacobian slice, the commanded pose change and the end-effector velocity row do not change inside one policy step:
 //   prepare (once per step):  u_task = J^T Lambda (kp dpose - kd eef_vel),  N = (I - J^T Lambda J M^-1) M
-//   apply   (every decimation step):  u = clamp(u_task + N (kd_null (-qd) + kp_null wrap(-q)), +-effort)
-struct OscPrepared {
-    float u_task[6];
-    float N[36];
+//   apply   (every decimation step):  u = clamp(u_task + N (kd_null (-qd) + kp_null wrap(q_default - q)), +-effort)
+// NJ joints (6: the hound's arm; 7: the Franka), six task dimensions; mm is NJ x NJ, J is 6 x NJ, both dense row-major.
+template <int NJ>
+struct OscPreparedN {
+    float u_task[NJ];
+    float N[NJ * NJ];
 };
-B2G_HD inline void osc_prepare(const float* mm_f, const float* j_f, const float* dpose, const float* eef_vel, float kp, OscPrepared& P) {
+typedef OscPreparedN<6> OscPrepared;
+template <int NJ>
+B2G_HD inline void osc_prepare_n(const float* mm_f, const float* j_f, const float* dpose, const float* eef_vel, float kp, OscPreparedN<NJ>& P) {
     const osc_real kd = 2.0 * sqrt((osc_real)kp);
-    osc_real mm[36], j[36], mm_inv[36], t[36], m_eef_inv[36], m_eef[36], j_eef_inv[36];
-    for (int i = 0; i < 36; i++) { mm[i] = mm_f[i]; j[i] = j_f[i]; }
-    inv6(mm, mm_inv);
-    mm6(j, mm_inv, t);
-    mm6(t, j, m_eef_inv, false, true);
-    inv6(m_eef_inv, m_eef);
+    osc_real mm[NJ * NJ], j[6 * NJ], mm_inv[NJ * NJ], t[49], m_eef_inv[36], m_eef[36], j_eef_inv[6 * NJ];
+    for (int i = 0; i < NJ * NJ; i++) mm[i] = mm_f[i];
+    for (int i = 0; i < 6 * NJ; i++) j[i] = j_f[i];
+    inv_n(mm, mm_inv, NJ);
+    mat_mul(j, mm_inv, t, 6, NJ, NJ);                       // J M^-1
+    mat_mul(t, j, m_eef_inv, 6, NJ, 6, false, true);        // J M^-1 J^T
+    inv_n(m_eef_inv, m_eef, 6);
     osc_real w[6], v[6];
     for (int i = 0; i < 6; i++) w[i] = (osc_real)kp * dpose[i] - kd * eef_vel[i];
     for (int i = 0; i < 6; i++) { osc_real acc = 0; for (int k = 0; k < 6; k++) acc += m_eef[i * 6 + k] * w[k]; v[i] = acc; }
-    for (int i = 0; i < 6; i++) { osc_real acc = 0; for (int k = 0; k < 6; k++) acc += j[k * 6 + i] * v[k]; P.u_task[i] = (float)acc; }   // J^T (Lambda w)
-    mm6(m_eef, j, t);
-    mm6(t, mm_inv, j_eef_inv);
-    mm6(j, j_eef_inv, t, true, false);                  // J^T j_eef_inv
-    for (int i = 0; i < 36; i++) t[i] = ((i / 6 == i % 6) ? 1.0 : 0.0) - t[i];
-    mm6(t, mm, t);
-    for (int i = 0; i < 36; i++) P.N[i] = (float)t[i];
+    for (int i = 0; i < NJ; i++) { osc_real acc = 0; for (int k = 0; k < 6; k++) acc += j[k * NJ + i] * v[k]; P.u_task[i] = (float)acc; }   // J^T (Lambda w)
+    mat_mul(m_eef, j, t, 6, 6, NJ);
+    mat_mul(t, mm_inv, j_eef_inv, 6, NJ, NJ);
+    mat_mul(j, j_eef_inv, t, NJ, 6, NJ, true, false);       // J^T j_eef_inv
+    for (int i = 0; i < NJ * NJ; i++) t[i] = ((i / NJ == i % NJ) ? 1.0 : 0.0) - t[i];
+    mat_mul(t, mm, t, NJ, NJ, NJ);
+    for (int i = 0; i < NJ * NJ; i++) P.N[i] = (float)t[i];
 }
-B2G_HD inline void osc_apply(const OscPrepared& P, const float* q, const float* qd, float kp_null, const float* effort, float* u) {
+template <int NJ>
+B2G_HD inline void osc_apply_n(const OscPreparedN<NJ>& P, const float* q, const float* qd, float kp_null, const float* effort, float* u, const float* q_default = nullptr) {
     const float kdn = 2.0f * sqrtf(kp_null);
     const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
-    float un[6];
-    for (int i = 0; i < 6; i++) {
-        float a = 0.0f - q[i] + pi;
+    float un[NJ];
+    for (int i = 0; i < NJ; i++) {
+        float a = (q_default ? q_default[i] : 0.0f) - q[i] + pi;
         a = a - two_pi * floorf(a / two_pi);            // python-style remainder (eager torch %)
         un[i] = kdn * -qd[i] + kp_null * (a - pi);
     }
-    for (int i = 0; i < 6; i++) {
+    for (int i = 0; i < NJ; i++) {
         float acc = P.u_task[i];
-        for (int k = 0; k < 6; k++) acc += P.N[i * 6 + k] * un[k];
+        for (int k = 0; k < NJ; k++) acc += P.N[i * NJ + k] * un[k];
         u[i] = fminf(fmaxf(acc, -effort[i]), effort[i]);
     }
 }
+B2G_HD inline void osc_prepare(const float* mm_f, const float* j_f, const float* dpose, const float* eef_vel, float kp, OscPrepared& P) {
+    osc_prepare_n<6>(mm_f, j_f, dpose, eef_vel, kp, P);
+}
+B2G_HD inline void osc_apply(const OscPrepared& P, const float* q, const float* qd, float kp_null, const float* effort, float* u) {
+    osc_apply_n<6>(P, q, qd, kp_null, effort, u);
+}
 // Kinematics + composite-rigid-body pass over one chain: joint-space mass-matrix block of the chain (n x n, row-major in
-// mm[36]), the position (relative to the root origin) of link `want_link` (chain-local index, -1 = root) and its world rotation.
+// mm[ld * ld], leading dimension ld >= n), the position (relative to the root origin) of link `want_link` (chain-local index, -1 = root) and its world rotation.
 B2G_HD inline void chain_crba(const DevModel* M, int d0, int n, const float* rootq, const float* q, float* mm, int want_link, V3* want_pos, M3* want_rot,
-                              const float* qd, V3 root_w, V3 root_v, SV* want_vel, float mass_scale = 1.0f, const float* link_scale = nullptr) {
+                              const float* qd, V3 root_w, V3 root_v, SV* want_vel, float mass_scale = 1.0f, const float* link_scale = nullptr, int ld = 6) {
     M3 R = quat_to_m3(rootq[0], rootq[1], rootq[2], rootq[3]);
     V3 p = V3{0, 0, 0};
     SV vel = SV{root_w, root_v};
-    SV S[B2G_MAX_CHAIN_LEN];
-    SI I[B2G_MAX_CHAIN_LEN];
+    SV S[B2G_MAX_FIXED_CHAIN_LEN];
+    SI I[B2G_MAX_FIXED_CHAIN_LEN];
     if (want_link < 0) { *want_pos = p; *want_rot = R; *want_vel = vel; }
     for (int j = 0; j < n; j++) {
         const DevDof& D = M->dof[d0 + j];
@@ -568,11 +582,11 @@ B2G_HD inline void chain_crba(const DevModel* M, int d0, int n, const float* roo
         if (j == want_link) { *want_pos = p; *want_rot = R; *want_vel = vel; }
     }
     for (int j = n - 2; j >= 0; j--) I[j] += I[j + 1];
-    for (int i = 0; i < 36; i++) mm[i] = 0.0f;
+    for (int i = 0; i < ld * ld; i++) mm[i] = 0.0f;
     for (int i = 0; i < n; i++) {
         const SV F = mul(I[i], S[i]);
-        mm[i * 6 + i] = dot(S[i], F) + M->dof[d0 + i].armature;
-        for (int k = 0; k < i; k++) { const float v = dot(S[k], F); mm[i * 6 + k] = v; mm[k * 6 + i] = v; }
+        mm[i * ld + i] = dot(S[i], F) + M->dof[d0 + i].armature;
+        for (int k = 0; k < i; k++) { const float v = dot(S[k], F); mm[i * ld + k] = v; mm[k * ld + i] = v; }
     }
 }
 // what post_physics_step's refresh_jacobian / refresh_mass_matrix leave for the next step's OSC (pre-reset state), plus the
@@ -624,7 +638,8 @@ B2G_HD inline void arm_refresh(const SimArgs& A, const TerrainArgs& T, int env, 
 
 // ---- Houndarm (tasks/hound_arm.py): the whole VecTask.step of the fixed-base arm reach task, one thread per environment ----
 // kinematics of the single chain: link poses relative to the root origin (world axes), link spatial velocities, joint axes
-B2G_HD inline void arm_chain_kin(const DevModel* M, const LaneState<6>& st, int n, M3* Rl, V3* pl, SV* vl, V3* axw, V3* pj) {
+template <int NJ>
+B2G_HD inline void arm_chain_kin(const DevModel* M, const LaneState<NJ>& st, int n, M3* Rl, V3* pl, SV* vl, V3* axw, V3* pj) {
     Rl[0] = quat_to_m3(st.qx, st.qy, st.qz, st.qw);
     pl[0] = V3{0, 0, 0};
     vl[0] = sv0();
@@ -643,7 +658,8 @@ B2G_HD inline void arm_chain_kin(const DevModel* M, const LaneState<6>& st, int 
     }
 }
 // rigid-body state row of API body b (same conventions as body_state_env): pos3, quat xyzw, linear velocity, angular velocity
-B2G_HD inline void arm_body_row(const DevModel* M, int b, const LaneState<6>& st, const M3* Rl, const V3* pl, const SV* vl, float* o) {
+template <int NJ>
+B2G_HD inline void arm_body_row(const DevModel* M, int b, const LaneState<NJ>& st, const M3* Rl, const V3* pl, const SV* vl, float* o) {
     const int l = M->body_link[b];
     const V3 p = pl[l] + mul(Rl[l], V3{M->body_pos[b][0], M->body_pos[b][1], M->body_pos[b][2]});
     const M3 R = mul(Rl[l], quat_to_m3(M->body_quat[b][0], M->body_quat[b][1], M->body_quat[b][2], M->body_quat[b][3]));
@@ -660,56 +676,60 @@ B2G_HD inline void arm_body_row(const DevModel* M, int b, const LaneState<6>& st
     o[10] = vl[l].w.x; o[11] = vl[l].w.y; o[12] = vl[l].w.z;
 }
 
+// NJ = 6: Houndarm, 7: Manipulator (the same task on the Franka; b2g_houndarm_cfg::default_dof_pos / n_reset_tail).  Six actions either way.
+template <int NJ>
 B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, int env, bool valid, ScratchStrided sc, float* bf) {
     const DevModel* M = A.M;
     const b2g_houndarm_cfg& C = T.hcfg;
     const int n = M->chain_len[0];
-    LaneState<6> st;
-    load_state<6>(A, env, n, 0, st);
-    float act[6];
-    for (int j = 0; j < 6; j++) {
-        float a = (j < n) ? T.actions_in[(size_t)env * n + j] : 0.0f;
+    constexpr int NA = 6;      // actions: the commanded end-effector pose change
+    LaneState<NJ> st;
+    load_state<NJ>(A, env, n, 0, st);
+    float act[NA];
+    for (int j = 0; j < NA; j++) {
+        const float a = T.actions_in[(size_t)env * NA + j];
         act[j] = fminf(fmaxf(a, -C.clip_actions), C.clip_actions);
+    }
+    for (int j = 0; j < NJ; j++) {
         st.act[j] = 0.0f;
         st.tgt[j] = 0.0f;
         st.frc[j] = (j < n) ? A.dof_force[(size_t)env * n + j] : 0.0f;
     }
-    M3 Rl[7];
-    V3 pl[7], axw[6], pj[6];
-    SV vl[7];
+    M3 Rl[NJ + 1];
+    V3 pl[NJ + 1], axw[NJ], pj[NJ];
+    SV vl[NJ + 1];
     if (!T.post_only) {
         // pre_physics_step (:495-507): OSC torques from the state as it is now
-        arm_chain_kin(M, st, n, Rl, pl, vl, axw, pj);
-        float eef[13], J[36], mm[36], dpose[6], effort[6], u[6];
-        arm_body_row(M, C.eef_body, st, Rl, pl, vl, eef);
+        arm_chain_kin<NJ>(M, st, n, Rl, pl, vl, axw, pj);
+        float eef[13], J[6 * NJ], mm[NJ * NJ], dpose[6], effort[NJ], u[NJ];
+        arm_body_row<NJ>(M, C.eef_body, st, Rl, pl, vl, eef);
         const int l = M->body_link[C.jac_body];
         const V3 pb = pl[l] + mul(Rl[l], V3{M->body_pos[C.jac_body][0], M->body_pos[C.jac_body][1], M->body_pos[C.jac_body][2]});
-        for (int i = 0; i < 36; i++) J[i] = 0.0f;
+        for (int i = 0; i < 6 * NJ; i++) J[i] = 0.0f;
         for (int d = 0; d <= l - 1; d++) {
             if (M->dof[d].type == B2G_JOINT_REVOLUTE) {
                 const V3 lin = cross(axw[d], pb - pj[d]);
-                J[0 * 6 + d] = lin.x; J[1 * 6 + d] = lin.y; J[2 * 6 + d] = lin.z;
-                J[3 * 6 + d] = axw[d].x; J[4 * 6 + d] = axw[d].y; J[5 * 6 + d] = axw[d].z;
+                J[0 * NJ + d] = lin.x; J[1 * NJ + d] = lin.y; J[2 * NJ + d] = lin.z;
+                J[3 * NJ + d] = axw[d].x; J[4 * NJ + d] = axw[d].y; J[5 * NJ + d] = axw[d].z;
             } else {
-                J[0 * 6 + d] = axw[d].x; J[1 * 6 + d] = axw[d].y; J[2 * 6 + d] = axw[d].z;
+                J[0 * NJ + d] = axw[d].x; J[1 * NJ + d] = axw[d].y; J[2 * NJ + d] = axw[d].z;
             }
         }
         const float rq[4] = {st.qx, st.qy, st.qz, st.qw};
         V3 dp; M3 dr; SV dv;
         chain_crba(M, 0, n, rq, st.q, mm, -1, &dp, &dr, st.qd, V3{0, 0, 0}, V3{0, 0, 0}, &dv, A.env_scale ? A.env_scale[(size_t)(valid ? env : 0) * 4] : 1.0f,
-                   A.link_scale ? A.link_scale + (size_t)(valid ? env : 0) * (M->n_dof + 1) * B2G_LINK_SCALE_COLS : nullptr);
-        for (int i = 0; i < 6; i++) {
-            dpose[i] = act[i] * C.cmd_limit[i] / C.action_scale;
-            effort[i] = (i < n) ? M->dof[i].effort : 0.0f;
-        }
-        OscPrepared P;
-        osc_prepare(mm, J, dpose, eef + 7, C.kp, P);
-        osc_apply(P, st.q, st.qd, C.kp_null, effort, u);
-        for (int j = 0; j < 6; j++) st.act[j] = (j < n) ? u[j] : 0.0f;
+                   A.link_scale ? A.link_scale + (size_t)(valid ? env : 0) * (M->n_dof + 1) * B2G_LINK_SCALE_COLS : nullptr, NJ);
+        for (int i = n; i < NJ; i++) mm[i * NJ + i] = 1.0f;      // a shorter chain: keep the padded block invertible
+        for (int i = 0; i < 6; i++) dpose[i] = act[i] * C.cmd_limit[i] / C.action_scale;
+        for (int i = 0; i < NJ; i++) effort[i] = (i < n) ? M->dof[i].effort : 0.0f;
+        OscPreparedN<NJ> P;
+        osc_prepare_n<NJ>(mm, J, dpose, eef + 7, C.kp, P);
+        osc_apply_n<NJ>(P, st.q, st.qd, C.kp_null, effort, u, C.default_dof_pos);
+        for (int j = 0; j < NJ; j++) st.act[j] = (j < n) ? u[j] : 0.0f;
         const EnvDr dr_env = env_dr(A, valid ? env : 0, valid);
 #pragma unroll 1
         for (int s = 0; s < A.P.substeps; s++)
-            substep<1, 6, true, false, false, false>(M, A.P, 0, n, 0, st, dr_env, s == A.P.substeps - 1, sc, bf);
+            substep<1, NJ, true, false, false, false>(M, A.P, 0, n, 0, st, dr_env, s == A.P.substeps - 1, sc, bf);
     }
     // post_physics_step (:509-517)
     long long progress = T.progress[env] + 1;
@@ -717,23 +737,24 @@ B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, in
     int rc = 0;
     float cmd[3] = {T.commands[(size_t)env * 3 + 0], T.commands[(size_t)env * 3 + 1], T.commands[(size_t)env * 3 + 2]};
     const bool do_reset = reset_prev != 0;
-    if (do_reset) {          // reset_idx (:394-459); draw order: command x, y, z, then the six joint-noise uniforms
+    if (do_reset) {          // reset_idx (:394-459); draw order: command x, y, z, then one joint-noise uniform per DOF
         rc = T.reset_count[env];
-        const int nd = 9;
+        const int nd = 3 + n;
         for (int k = 0; k < 3; k++) cmd[k] = rand_range(C.cmd_range[2 * k], C.cmd_range[2 * k + 1], reset_uniform(T, env, rc, k, nd));
         for (int j = 0; j < n; j++) {
             const float r = reset_uniform(T, env, rc, 3 + j, nd);
-            const float p = 0.0f + C.dof_noise * 2.0f * (r - 0.5f);
+            const float p = C.default_dof_pos[j] + C.dof_noise * 2.0f * (r - 0.5f);
             st.q[j] = fminf(fmaxf(p, M->dof[j].lower), M->dof[j].upper);
+            if (j >= n - C.n_reset_tail) st.q[j] = C.default_dof_pos[j];      // manipulator.py:417 (after the clamp, no noise)
             st.qd[j] = 0.0f;
         }
         progress = 0;
         reset_prev = 0;
     }
     // compute_observations (:383-392) on the refreshed state, compute_reward (:550-567)
-    arm_chain_kin(M, st, n, Rl, pl, vl, axw, pj);
+    arm_chain_kin<NJ>(M, st, n, Rl, pl, vl, axw, pj);
     float eef[13];
-    arm_body_row(M, C.eef_body, st, Rl, pl, vl, eef);
+    arm_body_row<NJ>(M, C.eef_body, st, Rl, pl, vl, eef);
     const float dx = eef[0] - cmd[0], dy = eef[1] - cmd[1], dz = eef[2] - cmd[2];
     const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
     float vsq = 0.0f;
@@ -743,7 +764,7 @@ B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, in
     const bool time_out = progress >= C.max_episode_length - 1;
     const long long reset = time_out ? 1 : reset_prev;
     if (valid) {
-        store_state<6>(A, env, 0, n, 0, st, true);
+        store_state<NJ>(A, env, 0, n, 0, st, true);
         float* o = T.obs + (size_t)env * 10;
         float* oc = T.obs_clamped + (size_t)env * 10;
         for (int k = 0; k < 7; k++) o[k] = eef[k];
@@ -753,7 +774,7 @@ B2G_HD B2G_INL void houndarm_step_thread(const SimArgs& A, const TaskArgs& T, in
         T.reset[env] = reset;
         T.progress[env] = progress;
         T.timeout[env] = (time_out && reset != 0) ? 1 : 0;
-        for (int j = 0; j < n; j++) T.actions[(size_t)env * n + j] = act[j];
+        for (int j = 0; j < NA; j++) T.actions[(size_t)env * NA + j] = act[j];
         for (int k = 0; k < 3; k++) T.commands[(size_t)env * 3 + k] = cmd[k];
         if (do_reset) T.reset_count[env] = rc + 1;
     }
@@ -1178,12 +1199,13 @@ B2G_HD inline void mass_matrix_env(const DevModel* M, const float* root, const f
     for (int i = 0; i < nd * nd; i++) out[i] = 0.0f;
     for (int c = 0; c < M->n_chains; c++) {
         const int d0 = M->chain_start[c], n = M->chain_len[c];
-        float q[B2G_MAX_CHAIN_LEN], qd[B2G_MAX_CHAIN_LEN], mm[36];
+        constexpr int LD = B2G_MAX_FIXED_CHAIN_LEN;
+        float q[LD], qd[LD], mm[LD * LD];
         for (int j = 0; j < n; j++) { q[j] = dof[2 * (d0 + j)]; qd[j] = 0.0f; }
         V3 p; M3 r; SV v;
-        chain_crba(M, d0, n, root + 3, q, mm, -1, &p, &r, qd, V3{0, 0, 0}, V3{0, 0, 0}, &v, mass_scale, link_scale);
+        chain_crba(M, d0, n, root + 3, q, mm, -1, &p, &r, qd, V3{0, 0, 0}, V3{0, 0, 0}, &v, mass_scale, link_scale, LD);
         for (int i = 0; i < n; i++)
-            for (int j = 0; j < n; j++) out[(d0 + i) * nd + d0 + j] = mm[i * 6 + j];
+            for (int j = 0; j < n; j++) out[(d0 + i) * nd + d0 + j] = mm[i * LD + j];
     }
 }
 

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import os
 import struct
+import re
 import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
@@ -113,6 +114,7 @@ class Shape:
     rot: np.ndarray                # 3x3
     size: np.ndarray               # box: full extents; sphere: [r]; cylinder/capsule: [r, length]; mesh: aabb lo+hi (6)
     body: str = ""                 # API body (URDF link) the shape belongs to
+    hull: object = None            # mesh: (volume, centroid, unit-density inertia about it) of the convex hull, or None
 
 
 @dataclass
@@ -143,10 +145,17 @@ class RawJoint:
     has_limits: bool = False
 
 
-def _stl_aabb(path, scale):
-    """Axis-aligned bounds of a (binary or ASCII) STL, scaled."""
+def _mesh_points(path, scale):
+    """Vertices of a (binary or ASCII) STL or a Wavefront OBJ, scaled."""
     with open(path, "rb") as f:
         data = f.read()
+    if path.lower().endswith(".obj"):
+        vals = []
+        for line in data.decode("ascii", "ignore").splitlines():
+            t = line.split()
+            if len(t) >= 4 and t[0] == "v":
+                vals.append([float(t[1]), float(t[2]), float(t[3])])
+        return np.array(vals, dtype=np.float64).reshape(-1, 3) * scale
     pts = None
     if len(data) >= 84:
         ntri = struct.unpack_from("<I", data, 80)[0]
@@ -160,12 +169,60 @@ def _stl_aabb(path, scale):
             if len(t) == 4 and t[0] == "vertex":
                 vals.append([float(t[1]), float(t[2]), float(t[3])])
         pts = np.array(vals, dtype=np.float64)
-    pts = pts * scale
+    return pts * scale
+
+
+def _stl_aabb(path, scale):
+    """Axis-aligned bounds of a mesh file, scaled."""
+    pts = _mesh_points(path, scale)
     return pts.min(0), pts.max(0)
 
 
+def _hull_mass_properties(pts):
+    """(volume, centroid, inertia about the centroid for unit density) of the convex hull of ``pts`` -- PhysX cooks collision meshes
+    into convex hulls and derives a link's mass properties from them when the URDF has no <inertial> (franka_panda_manipulator.urdf).
+    None when the hull is degenerate or scipy is unavailable (the caller falls back to the bounding box)."""
+    try:
+        from scipy.spatial import ConvexHull
+
+        hull = ConvexHull(pts)
+    except Exception:
+        return None
+    vol, first, second = 0.0, np.zeros(3), np.zeros((3, 3))
+    for simplex, eq in zip(hull.simplices, hull.equations):
+        a, b, c = pts[simplex[0]], pts[simplex[1]], pts[simplex[2]]
+        if np.dot(np.cross(b - a, c - a), eq[:3]) < 0.0:
+            b, c = c, b
+        v = np.dot(a, np.cross(b, c)) / 6.0      # signed volume of the tetrahedron (origin, a, b, c)
+        s = a + b + c
+        vol += v
+        first += v * s / 4.0
+        second += v / 20.0 * (np.outer(s, s) + np.outer(a, a) + np.outer(b, b) + np.outer(c, c))
+    if vol <= 1e-12:
+        return None
+    com = first / vol
+    i0 = np.trace(second) * np.eye(3) - second
+    return vol, com, i0 - vol * (np.dot(com, com) * np.eye(3) - np.outer(com, com))
+
+
+def _parse_xml_lenient(path: str):
+    """``ET.parse`` that, like the forgiving XML readers URDF importers use, stops at the end of the root element: the reference's
+    ``franka_panda_manipulator.urdf`` closes ``</robot>`` after ``panda_joint7`` and then carries the hand and the fingers inside a
+    comment that itself contains comments -- not XML, and outside the document anyway.  8 links and 7 revolute joints remain, which is
+    what ``tasks/manipulator.py`` is written against (7-entry gain vectors indexed over ``num_franka_dofs``, :216-234)."""
+    text = open(path, "r", encoding="utf-8", errors="replace").read()
+    try:
+        return ET.fromstring(text)
+    except ET.ParseError:
+        m = re.search(r"<\s*([A-Za-z_][\w:.-]*)", re.sub(r"<\?.*?\?>|<!--.*?-->", "", text, flags=re.S))
+        end = text.find(f"</{m.group(1)}>") if m else -1
+        if end < 0:
+            raise
+        return ET.fromstring(text[:end + len(m.group(1)) + 3])
+
+
 def parse_urdf(path: str):
-    root = ET.parse(path).getroot()
+    root = _parse_xml_lenient(path)
     base_dir = os.path.dirname(os.path.abspath(path))
     links: Dict[str, RawLink] = {}
     for le in root.findall("link"):
@@ -206,11 +263,18 @@ def parse_urdf(path: str):
                     if fn.startswith(prefix):
                         fn = fn[len(prefix):]
                 cand = [os.path.join(base_dir, fn), os.path.join(base_dir, os.path.basename(fn))]
+                up = base_dir
+                for _ in range(4):      # package://<pkg>/... : the package directory is an ancestor of the URDF's directory
+                    up = os.path.dirname(up)
+                    cand.append(os.path.join(up, fn))
                 mp = next((c for c in cand if os.path.isfile(c)), None)
-                if mp is None or not mp.lower().endswith(".stl"):
+                if mp is None or not mp.lower().endswith((".stl", ".obj")):
                     continue  # visual-only formats (.dae) carry no collision here
-                lo, hi = _stl_aabb(mp, scale)
-                sh = Shape("mesh", pos, rot, np.concatenate([lo, hi]), lk.name)
+                pts = _mesh_points(mp, scale)
+                if len(pts) == 0:
+                    continue
+                sh = Shape("mesh", pos, rot, np.concatenate([pts.min(0), pts.max(0)]), lk.name)
+                sh.hull = _hull_mass_properties(pts)
             else:
                 continue
             lk.shapes.append(sh)
@@ -356,6 +420,9 @@ def _shape_inertia(sh: Shape, density: float):
         r, l = sh.size
         m = density * np.pi * r * r * l
         i = np.diag([m * (3 * r * r + l * l) / 12.0, m * (3 * r * r + l * l) / 12.0, 0.5 * m * r * r])
+    elif getattr(sh, "hull", None) is not None:      # mesh: convex hull
+        vol, c, i = sh.hull
+        return density * vol, sh.pos + sh.rot @ c, density * (sh.rot @ i @ sh.rot.T)
     else:
         lo, hi = sh.size[:3], sh.size[3:]
         x, y, z = hi - lo

@@ -1,4 +1,4 @@
-"""Houndarm: fixed-base 6-DOF arm reach task, drop-in for the reference's ``tasks/hound_arm.py`` (``Houndarm`` :74-545):
+"""Houndarm / Manipulator: fixed-base 6-DOF (7-DOF Franka: class ``Manipulator`` at the end) arm reach task, drop-in for the reference's ``tasks/hound_arm.py`` (``Houndarm`` :74-545):
 6 actions = end-effector pose deltas scaled by ``cmd_limit`` and turned into joint torques by the operational-space law
 (:462-493) -- or 6 raw joint torques with ``controlType: joint_tor`` --, 10 observations [eef position, eef quaternion,
 commanded position] (:383-392), reward ``compute_houndarm_reward`` (:550-567), reset draws (:394-459), 150-step episodes.
@@ -44,17 +44,29 @@ def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp, kd, kp_null, kd_null, defa
     j_eef_inv = m_eef @ j_eef @ mm_inv
     u_null = kd_null * -qd + kp_null * ((default_q - q + np.pi) % (2 * np.pi) - np.pi)
     u_null = mm @ u_null.unsqueeze(-1)
-    u = u + (torch.eye(6, device=mm.device).unsqueeze(0) - j_t @ j_eef_inv) @ u_null
+    u = u + (torch.eye(mm.shape[-1], device=mm.device).unsqueeze(0) - j_t @ j_eef_inv) @ u_null
     return tensor_clamp(u.squeeze(-1), -effort_limits.unsqueeze(0), effort_limits.unsqueeze(0))
 
 
 class Houndarm(VecTask):
+    # what distinguishes the reference's two arm-reach task files (hound_arm.py is manipulator.py with these changed); the attribute names
+    # the reference spells with the arm's name (``houndarm_dof_noise`` / ``franka_dof_noise`` ...) exist under both spellings' own prefix
+    ARM = "houndarm"
+    N_ARM_DOFS = 6
+    DEFAULT_DOF_POS = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)                     # hound_arm.py:160-162
+    ASSET_FILE = "urdf/open_manipulator_p_gazebo/urdf/open_manipulator_p.urdf"
+    ASSET_KEY = "assetFileNamehoundarm"
+    EEF_LINK, EEF_JOINT = "end_link", "joint6"
+    RESET_TAIL = 0                                                         # joints at the end of the chain reset without noise
+    FLIP_VISUAL = False
+
     def __init__(self, cfg, rl_device, sim_device, graphics_device_id, headless, virtual_screen_capture=False, force_render=False):
         self.cfg = cfg
         env = cfg["env"]
         self.max_episode_length = env["episodeLength"]
         self.action_scale = env["actionScale"]
-        self.houndarm_dof_noise = env["houndarmDofNoise"]
+        self.arm_dof_noise = env[f"{self.ARM}DofNoise"]
+        setattr(self, f"{self.ARM}_dof_noise", self.arm_dof_noise)
         rng = env["randomCommandPositionRanges"]
         self.command_x_range, self.command_y_range, self.command_z_range = rng["x"], rng["y"], rng["z"]
         self.reward_settings = {"r_dist_scale": env["distRewardScale"], "r_lift_scale": env["liftRewardScale"], "r_align_scale": env["alignRewardScale"],
@@ -68,7 +80,7 @@ class Houndarm(VecTask):
             # the reference's joint_tor variant declares 26 observations / 8 actions but builds 10 / uses 6 (:383-392, :499-501)
             raise NotImplementedError("controlType joint_tor is inconsistent in the reference (26 obs declared, 10 built); only osc is served")
         if cfg.get("task", {}).get("randomize", False):
-            raise NotImplementedError("Houndarm: task.randomize is not wired (the reference task never calls apply_randomizations)")
+            raise NotImplementedError(f"{type(self).__name__}: task.randomize is not wired (the reference task never calls apply_randomizations)")
         self.states, self.handles = {}, {}
         self.fused = bool(env.get("fusedStep", True))
         # the generic path finds the environments to reset with nonzero() (as the reference does): not CUDA-graph capturable
@@ -77,10 +89,11 @@ class Houndarm(VecTask):
         self.seed = int(cfg.get("seed", 42))
         super().__init__(config=cfg, rl_device=rl_device, sim_device=sim_device, graphics_device_id=graphics_device_id, headless=headless,
                          virtual_screen_capture=virtual_screen_capture, force_render=force_render)
-        self.houndarm_default_dof_pos = to_torch([0, 0, 0, 0, 0, 0], device=self.device)
+        self.arm_default_dof_pos = to_torch(list(self.DEFAULT_DOF_POS), device=self.device)
+        setattr(self, f"{self.ARM}_default_dof_pos", self.arm_default_dof_pos)
         self.kp = to_torch([150.0] * 6, device=self.device)
         self.kd = 2 * torch.sqrt(self.kp)
-        self.kp_null = to_torch([10.0] * 6, device=self.device)
+        self.kp_null = to_torch([10.0] * self.N_ARM_DOFS, device=self.device)
         self.kd_null = 2 * torch.sqrt(self.kp_null)
         self.cmd_limit = to_torch([0.1, 0.1, 0.1, 0.5, 0.5, 0.5], device=self.device).unsqueeze(0)
         self.commands = torch.zeros(self.num_envs, 3, dtype=torch.float, device=self.device)
@@ -104,12 +117,12 @@ class Houndarm(VecTask):
     def _create_envs(self, num_envs, spacing, num_per_row):
         lower, upper = gymapi.Vec3(-spacing, -spacing, 0.0), gymapi.Vec3(spacing, spacing, spacing)
         asset_root = self.cfg["env"].get("assetRoot", default_asset_root())
-        asset_file = "urdf/open_manipulator_p_gazebo/urdf/open_manipulator_p.urdf"
+        asset_file = self.ASSET_FILE
         if "asset" in self.cfg["env"]:
-            asset_file = self.cfg["env"]["asset"].get("assetFileNamehoundarm", asset_file)
+            asset_file = self.cfg["env"]["asset"].get(self.ASSET_KEY, asset_file)
         opt = gymapi.AssetOptions()
         opt.replace_cylinder_with_capsule = False
-        opt.flip_visual_attachments = False
+        opt.flip_visual_attachments = self.FLIP_VISUAL
         opt.fix_base_link = True
         opt.collapse_fixed_joints = False
         opt.disable_gravity = True
@@ -117,31 +130,39 @@ class Houndarm(VecTask):
         opt.default_dof_drive_mode = gymapi.DOF_MODE_EFFORT
         opt.use_mesh_materials = True
         asset = self.gym.load_asset(self.sim, asset_root, asset_file, opt)
-        self.num_houndarm_bodies = self.gym.get_asset_rigid_body_count(asset)
-        self.num_houndarm_dofs = self.gym.get_asset_dof_count(asset)
+        self.num_arm_bodies = self.gym.get_asset_rigid_body_count(asset)
+        self.num_arm_dofs = self.gym.get_asset_dof_count(asset)
+        setattr(self, f"num_{self.ARM}_bodies", self.num_arm_bodies)
+        setattr(self, f"num_{self.ARM}_dofs", self.num_arm_dofs)
+        if self.num_arm_dofs != self.N_ARM_DOFS:
+            raise ValueError(f"{type(self).__name__} expects a {self.N_ARM_DOFS}-DOF arm, the asset has {self.num_arm_dofs}")
         props = self.gym.get_asset_dof_properties(asset)
-        for i in range(self.num_houndarm_dofs):
+        for i in range(self.num_arm_dofs):
             props["driveMode"][i] = gymapi.DOF_MODE_POS if i > 6 else gymapi.DOF_MODE_EFFORT
             props["stiffness"][i] = 0.0
             props["damping"][i] = 0.0
-        self.houndarm_dof_lower_limits = to_torch(props["lower"].astype("float32").copy(), device=self.device)
-        self.houndarm_dof_upper_limits = to_torch(props["upper"].astype("float32").copy(), device=self.device)
-        self._houndarm_effort_limits = to_torch(props["effort"].astype("float32").copy(), device=self.device)
+        self.arm_dof_lower_limits = to_torch(props["lower"].astype("float32").copy(), device=self.device)
+        self.arm_dof_upper_limits = to_torch(props["upper"].astype("float32").copy(), device=self.device)
+        self._arm_effort_limits = to_torch(props["effort"].astype("float32").copy(), device=self.device)
+        setattr(self, f"{self.ARM}_dof_lower_limits", self.arm_dof_lower_limits)
+        setattr(self, f"{self.ARM}_dof_upper_limits", self.arm_dof_upper_limits)
+        setattr(self, f"_{self.ARM}_effort_limits", self._arm_effort_limits)
         pose = gymapi.Transform()
         pose.p = gymapi.Vec3(-0.45, 0.0, 0.0)
         pose.r = gymapi.Quat(0.0, 0.0, 0.0, 1.0)
-        self.envs, self.houndarms = [], []
+        self.envs, self.arms = [], []
+        setattr(self, f"{self.ARM}s", self.arms)
         for i in range(num_envs):
             env = self.gym.create_env(self.sim, lower, upper, num_per_row)
-            self.houndarms.append(self.gym.create_actor(env, asset, pose, "houndarm", i, 0, 0))
-            self.gym.set_actor_dof_properties(env, self.houndarms[-1], props)
+            self.arms.append(self.gym.create_actor(env, asset, pose, self.ARM, i, 0, 0))
+            self.gym.set_actor_dof_properties(env, self.arms[-1], props)
             self.envs.append(env)
         self.gym.prepare_sim(self.sim)
         self.init_data()
 
     def init_data(self):
         env, actor = self.envs[0], 0
-        self.handles = {"endpoint_tip": self.gym.find_actor_rigid_body_handle(env, actor, "end_link")}
+        self.handles = {"endpoint_tip": self.gym.find_actor_rigid_body_handle(env, actor, self.EEF_LINK)}
         self.num_dofs = self.gym.get_sim_dof_count(self.sim) // self.num_envs
         n = self.num_envs
         self._root_state = gymtorch.wrap_tensor(self.gym.acquire_actor_root_state_tensor(self.sim)).view(n, -1, 13)
@@ -149,13 +170,14 @@ class Houndarm(VecTask):
         self._rigid_body_state = gymtorch.wrap_tensor(self.gym.acquire_rigid_body_state_tensor(self.sim)).view(n, -1, 13)
         self._q, self._qd = self._dof_state[..., 0], self._dof_state[..., 1]
         self._eef_state = self._rigid_body_state[:, self.handles["endpoint_tip"], :]
-        jacobian = gymtorch.wrap_tensor(self.gym.acquire_jacobian_tensor(self.sim, "houndarm"))
-        hand_joint_index = self.gym.get_actor_joint_dict(env, actor)["joint6"]
-        self._j_eef = jacobian[:, hand_joint_index, :, :6]
-        self._mm = gymtorch.wrap_tensor(self.gym.acquire_mass_matrix_tensor(self.sim, "houndarm"))[:, :6, :6]
+        k = self.N_ARM_DOFS
+        jacobian = gymtorch.wrap_tensor(self.gym.acquire_jacobian_tensor(self.sim, self.ARM))
+        hand_joint_index = self.gym.get_actor_joint_dict(env, actor)[self.EEF_JOINT]
+        self._j_eef = jacobian[:, hand_joint_index, :, :k]
+        self._mm = gymtorch.wrap_tensor(self.gym.acquire_mass_matrix_tensor(self.sim, self.ARM))[:, :k, :k]
         self._pos_control = torch.zeros((n, self.num_dofs), dtype=torch.float, device=self.device)
         self._effort_control = torch.zeros_like(self._pos_control)
-        self._arm_control = self._effort_control[:, :6]
+        self._arm_control = self._effort_control[:, :k]
         self._global_indices = torch.arange(n, dtype=torch.int32, device=self.device).view(n, -1)
 
     # ---- fused path ----
@@ -163,10 +185,13 @@ class Houndarm(VecTask):
         self._lib = _lib.load()
         e = self.cfg["env"]
         c = _abi.HoundarmCfg(clip_obs=float(self.clip_obs), clip_actions=float(self.clip_actions), action_scale=float(self.action_scale),
-                             dof_noise=float(self.houndarm_dof_noise), kp=150.0, kp_null=10.0, dist_scale=float(e["distRewardScale"]),
+                             dof_noise=float(self.arm_dof_noise), kp=150.0, kp_null=10.0, dist_scale=float(e["distRewardScale"]),
                              vel_scale=float(e["velRewardScale"]), eef_body=int(self.handles["endpoint_tip"]),
-                             jac_body=int(self.gym.get_actor_joint_dict(self.envs[0], 0)["joint6"]) + 1,
-                             max_episode_length=int(self.max_episode_length), seed=int(self.seed) & 0xFFFFFFFFFFFFFFFF)
+                             jac_body=int(self.gym.get_actor_joint_dict(self.envs[0], 0)[self.EEF_JOINT]) + 1,
+                             max_episode_length=int(self.max_episode_length), seed=int(self.seed) & 0xFFFFFFFFFFFFFFFF,
+                             n_reset_tail=int(self.RESET_TAIL))
+        for i, v in enumerate(self.DEFAULT_DOF_POS):
+            c.default_dof_pos[i] = float(v)
         for i, v in enumerate(self.cmd_limit.flatten().tolist()):
             c.cmd_limit[i] = v
         for i, v in enumerate(list(self.command_x_range) + list(self.command_y_range) + list(self.command_z_range)):
@@ -231,9 +256,11 @@ class Houndarm(VecTask):
         self.commands_x[env_ids] = torch_rand_float(self.command_x_range[0], self.command_x_range[1], (k, 1), device=self.device).squeeze()
         self.commands_y[env_ids] = torch_rand_float(self.command_y_range[0], self.command_y_range[1], (k, 1), device=self.device).squeeze()
         self.commands_z[env_ids] = torch_rand_float(self.command_z_range[0], self.command_z_range[1], (k, 1), device=self.device).squeeze()
-        noise = torch.rand((k, 6), device=self.device)
-        pos = tensor_clamp(self.houndarm_default_dof_pos.unsqueeze(0) + self.houndarm_dof_noise * 2.0 * (noise - 0.5),
-                           self.houndarm_dof_lower_limits.unsqueeze(0), self.houndarm_dof_upper_limits)
+        noise = torch.rand((k, self.N_ARM_DOFS), device=self.device)
+        pos = tensor_clamp(self.arm_default_dof_pos.unsqueeze(0) + self.arm_dof_noise * 2.0 * (noise - 0.5),
+                           self.arm_dof_lower_limits.unsqueeze(0), self.arm_dof_upper_limits)
+        if self.RESET_TAIL:      # manipulator.py:417 ("gripper" positions; on this asset they are the arm's last joints)
+            pos[:, -self.RESET_TAIL:] = self.arm_default_dof_pos[-self.RESET_TAIL:]
         self._q[env_ids, :] = pos
         self._qd[env_ids, :] = torch.zeros_like(self._qd[env_ids])
         self._pos_control[env_ids, :] = pos
@@ -247,8 +274,9 @@ class Houndarm(VecTask):
 
     # ---- control ----
     def _compute_osc_torques(self, dpose):
-        return osc_torques(self._mm, self._j_eef, dpose, self.states["eef_vel"], self._q[:, :6], self._qd[:, :6], self.kp, self.kd, self.kp_null,
-                           self.kd_null, self.houndarm_default_dof_pos[:6], self._houndarm_effort_limits[:6])
+        k = self.N_ARM_DOFS
+        return osc_torques(self._mm, self._j_eef, dpose, self.states["eef_vel"], self._q[:, :k], self._qd[:, :k], self.kp, self.kd, self.kp_null,
+                           self.kd_null, self.arm_default_dof_pos[:k], self._arm_effort_limits[:k])
 
     def pre_physics_step(self, actions):
         self.actions = actions.clone().to(self.device)
@@ -265,3 +293,19 @@ class Houndarm(VecTask):
             self.reset_idx(env_ids)
         self.compute_observations()
         self.compute_reward(self.actions)
+
+
+class Manipulator(Houndarm):
+    """``tasks/manipulator.py`` (``Manipulator`` :75-617): the same reach task on the 7-DOF Franka arm (the asset's hand and fingers sit
+    behind the end of its ``<robot>`` element, ``model/urdf.py::_parse_xml_lenient``): six pose-change actions -> seven joint torques
+    through the 7 x 7 operational-space law with the null-space posture ``franka_default_dof_pos`` (:153-155), 1000-step episodes, reset
+    around that posture with the last two joints set back without noise (:407-417).  Mass properties: the URDF has no <inertial>, Isaac
+    Gym derives them from the collision meshes' convex hulls at the default density -- so does the model compiler (18.98 kg)."""
+    ARM = "franka"
+    N_ARM_DOFS = 7
+    DEFAULT_DOF_POS = (0.0, 0.1963, 0.0, -2.6180, 0.0, 2.9416, 0.7854)
+    ASSET_FILE = "urdf/franka_description/robots/franka_panda_manipulator.urdf"
+    ASSET_KEY = "assetFileNameFranka"
+    EEF_LINK, EEF_JOINT = "panda_link7", "panda_joint7"
+    RESET_TAIL = 2
+    FLIP_VISUAL = True

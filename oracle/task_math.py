@@ -393,17 +393,19 @@ def terrain_post_physics(st, cfg, draws):
     return obs.astype(f), rew.astype(f), reset.astype(np.int64), timeout, measured, extras
 
 
-def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp=150.0, kp_null=10.0, effort=1000.0, exact=False):
-    """tasks/useful_hound.py:660-691 / tasks/hound_arm.py:462-493 (_compute_osc_torques): operational-space control of the 6-DOF arm.
-    ``mm`` (N,6,6) arm block of the mass matrix, ``j_eef`` (N,6,6) the Jacobian slice the task takes, ``dpose`` (N,6), ``eef_vel`` (N,6),
-    ``q``/``qd`` (N,6).  ``exact=False`` mimics the reference's float32 evaluation (float32 products around accurately inverted matrices);
+def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp=150.0, kp_null=10.0, effort=1000.0, exact=False, default_q=0.0):
+    """tasks/useful_hound.py:660-691 / tasks/hound_arm.py:462-493 / tasks/manipulator.py:534-560 (_compute_osc_torques): operational-space
+    control of the k-DOF arm (k = 6, or 7 for the Franka).  ``mm`` (N,k,k) arm block of the mass matrix, ``j_eef`` (N,6,k) the Jacobian
+    slice the task takes, ``dpose`` (N,6), ``eef_vel`` (N,6), ``q``/``qd`` (N,k), ``default_q`` the null-space posture (zeros for the
+    hound's arm, ``franka_default_dof_pos`` for the Manipulator).  ``exact=False`` mimics the reference's float32 evaluation (float32 products around accurately inverted matrices);
     ``exact=True`` evaluates the whole law in float64 -- what the kernels do, because J M^-1 J^T is too ill-conditioned for float32 on
     these arms (see tests/kernel_checks.check_houndarm_step)."""
     f = np.float64 if exact else np.float32
     mm, j_eef, dpose, eef_vel, q, qd = (np.asarray(x).astype(f) for x in (mm, j_eef, dpose, eef_vel, q, qd))
     kp_v = np.full(6, kp, f)
     kd_v = (f(2) * np.sqrt(kp_v)).astype(f)
-    kpn = np.full(6, kp_null, f)
+    k = mm.shape[-1]
+    kpn = np.full(k, kp_null, f)
     kdn = (f(2) * np.sqrt(kpn)).astype(f)
     mm_inv = np.linalg.inv(mm.astype(np.float64)).astype(f)
     jt = np.transpose(j_eef, (0, 2, 1))
@@ -411,7 +413,7 @@ def osc_torques(mm, j_eef, dpose, eef_vel, q, qd, kp=150.0, kp_null=10.0, effort
     m_eef = np.linalg.inv(m_eef_inv.astype(np.float64)).astype(f)
     u = jt @ m_eef @ (kp_v * dpose - kd_v * eef_vel)[..., None]
     j_eef_inv = m_eef @ j_eef @ mm_inv
-    u_null = kdn * -qd + kpn * (np.mod(f(0.0) - q + f(np.pi), f(2 * np.pi)) - f(np.pi))      # python-style remainder (eager torch %)
+    u_null = kdn * -qd + kpn * (np.mod(np.asarray(default_q).astype(f) - q + f(np.pi), f(2 * np.pi)) - f(np.pi))      # python-style remainder (eager torch %)
     u_null = mm @ u_null[..., None]
-    u = u + (np.eye(6, dtype=f)[None] - jt @ j_eef_inv) @ u_null
+    u = u + (np.eye(k, dtype=f)[None] - jt @ j_eef_inv) @ u_null
     return np.clip(u[..., 0], -effort, effort).astype(np.float32)

@@ -97,7 +97,7 @@ class EmuBackend:
         self.cfg, self.kind = cfg, "houndarm"
         self.task = dict(obs=np.zeros((n, 10), np.float32), obs_clamped=np.zeros((n, 10), np.float32), rew=np.zeros(n, np.float32),
                          reset=np.ones(n, np.int64), progress=np.zeros(n, np.int64), timeout=np.zeros(n, np.int64),
-                         commands=np.zeros((n, 3), np.float32), actions=np.zeros((n, nd), np.float32), reset_count=np.zeros(n, np.int32))
+                         commands=np.zeros((n, 3), np.float32), actions=np.zeros((n, 6), np.float32), reset_count=np.zeros(n, np.int32))
 
     def task_step(self, actions, draws=None, post_only=False):
         if getattr(self, "kind", "anymal") == "terrain":

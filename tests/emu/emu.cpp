@@ -36,7 +36,8 @@ Variant pick(const b2g_model& m) {
     for (int c = 0; c < m.n_chains; c++) pieces += m.chain_len[c] > kSegLinks ? 1 : 0;
     const char* seg = getenv("B2G_SEGMENTS");
     if (seg && seg[0] == '1' && !m.fixed_base && m.n_chains > 0 && pieces <= B2G_MAX_CHAINS) return {8, 3, false, true};
-    return {8, 6, m.fixed_base != 0};
+    if (m.fixed_base) return {8, B2G_MAX_FIXED_CHAIN_LEN, true};
+    return {8, 6, false};
 }
 
 template <class F>
@@ -139,7 +140,7 @@ int emu_simulate(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     for (int e = 0; e < n_envs; e++) {
         if (v.lanes == 1) sim_env<1, 2, true, false>(A, e);
         else if (v.lanes == 4) { if (HFm) sim_env<4, 3, false, true>(A, e); else sim_env<4, 3, false, false>(A, e); }
-        else if (v.fixed) sim_env<8, 6, true, false>(A, e);
+        else if (v.fixed) sim_env<8, 7, true, false>(A, e);
         else if (v.seg) { if (HFm) sim_env<8, 3, false, true>(A, e); else sim_env<8, 3, false, false>(A, e); }
         else { if (HFm) sim_env<8, 6, false, true>(A, e); else sim_env<8, 6, false, false>(A, e); }
     }
@@ -161,7 +162,7 @@ int emu_forward_dynamics(const b2g_model* m, const b2g_sim_params* sp, const b2g
     for (int e = 0; e < n_envs; e++) {
         if (v.lanes == 1) probe_env<1, 2, true>(A, e, qdd, a0);
         else if (v.lanes == 4) probe_env<4, 3, false>(A, e, qdd, a0);
-        else if (v.fixed) probe_env<8, 6, true>(A, e, qdd, a0);
+        else if (v.fixed) probe_env<8, 7, true>(A, e, qdd, a0);
         else if (v.seg) probe_env<8, 3, false>(A, e, qdd, a0);
         else probe_env<8, 6, false>(A, e, qdd, a0);
     }
@@ -327,7 +328,7 @@ int emu_houndarm(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     DevModel* dm = new DevModel;
     const char* why;
     if (pack_dev_model(*m, *dp, *dm, &why) != 0) { delete dm; return -1; }
-    if (!m->fixed_base || m->n_chains != 1 || m->n_dof > 6) { delete dm; return -2; }
+    if (!m->fixed_base || m->n_chains != 1 || m->n_dof > B2G_MAX_FIXED_CHAIN_LEN) { delete dm; return -2; }
     SimArgs A;
     A.M = dm;
     pack_dev_params(*sp, nullptr, nullptr, A.P);
@@ -346,7 +347,8 @@ int emu_houndarm(const b2g_model* m, const b2g_sim_params* sp, const b2g_dof_pro
     emu_ctx.g = &g; emu_ctx.lane = 0; emu_ctx.local_sense = 0;
     for (int e = 0; e < n_envs; e++) {
         ScratchStrided sc{scratch.data(), 1}; sc.links = links.data(); sc.anc = anc.data();
-        houndarm_step_thread(A, T, e, true, sc, bf.data());
+        if (m->n_dof > 6) houndarm_step_thread<7>(A, T, e, true, sc, bf.data());
+        else houndarm_step_thread<6>(A, T, e, true, sc, bf.data());
     }
     delete dm;
     return 0;

@@ -97,7 +97,7 @@ def gen_utils(out):
     print(out)
 
 
-if __name__ == "__main__" and "--dr-only" not in sys.argv and "--houndarm-only" not in sys.argv:
+if __name__ == "__main__" and "--dr-only" not in sys.argv and "--houndarm-only" not in sys.argv and "--manipulator-only" not in sys.argv:
     torch.set_num_threads(1)
     gen_anymal(ref_loader.load("tasks.anymal"), "anymal", 13, [2, 5, 8, 11], 0, os.path.join(HERE, "anymal_flat.npz"))
     gen_anymal(ref_loader.load("tasks.hound"), "hound", 17, [2, 6, 10, 14], 0, os.path.join(HERE, "hound_flat.npz"))
@@ -399,7 +399,7 @@ def gen_useful_hound(out):
     print(out, "resets", int(b.reset_buf.sum()), "rew range", float(b.rew_buf.min()), float(b.rew_buf.max()), "osc |u| max", float(u.abs().max()))
 
 
-if __name__ == "__main__" and "--dr-only" not in sys.argv and "--houndarm-only" not in sys.argv and ("--useful" in sys.argv or globals().get("_run_terrain_after")):
+if __name__ == "__main__" and "--dr-only" not in sys.argv and "--houndarm-only" not in sys.argv and "--manipulator-only" not in sys.argv and ("--useful" in sys.argv or globals().get("_run_terrain_after")):
     gen_useful_hound(os.path.join(HERE, "useful_hound_plane.npz"))
 
 
@@ -478,3 +478,75 @@ def gen_houndarm(out):
 
 if __name__ == "__main__" and "--houndarm-only" in sys.argv:
     gen_houndarm(os.path.join(HERE, "houndarm.npz"))
+
+
+# ------------------------------------------------------------------------------------------------
+# Manipulator (tasks/manipulator.py): reward function, the 7-joint OSC torque law and the reset draw logic (incl. the two trailing joints
+# set back without noise, :417) run on an attribute bag
+# ------------------------------------------------------------------------------------------------
+def gen_manipulator(out):
+    mod = ref_loader.load("tasks.manipulator")
+    n = 96
+    eef_pos = sinfill((n, 3), 0.43, 0.3, 0.3)
+    commands = sinfill((n, 3), 0.59, 0.9, 0.3)
+    commands[:24] = eef_pos[:24] + sinfill((24, 3), 0.91, 0.2, 0.008)
+    eef_vel = sinfill((n, 6), 0.31, 0.5, 0.4)
+    progress = (torch.arange(n) * 47 % 1100).long()
+    reset = (torch.arange(n) % 11 == 0).long()
+    states = {"eef_pos": eef_pos, "eef_vel": eef_vel, "commands": commands}
+    settings = {"r_dist_scale": 0.1, "r_lift_scale": 1.5, "r_align_scale": 2.0, "r_stack_scale": 16.0, "r_vel_scale": 0.1}
+    rew, rst = mod.compute_franka_reward(reset, progress, torch.zeros(n, 6), states, settings, 1000.0)
+    b = types.SimpleNamespace()
+    mm = sinfill((n, 7, 7), 0.37, 0.3, 0.2)
+    b._mm = mm @ mm.transpose(1, 2) + 0.5 * torch.eye(7)
+    b._j_eef = sinfill((n, 6, 7), 0.61, 0.8, 0.7) + torch.eye(6, 7)
+    b._q = sinfill((n, 7), 0.23, 0.4, 1.2)
+    b._qd = sinfill((n, 7), 0.19, 0.7, 2.0)
+    b.states = {"eef_vel": eef_vel}
+    b.kp = torch.full((6,), 150.0)
+    b.kd = 2 * torch.sqrt(b.kp)
+    b.kp_null = torch.full((7,), 10.0)
+    b.kd_null = 2 * torch.sqrt(b.kp_null)
+    b.franka_default_dof_pos = torch.tensor([0, 0.1963, 0, -2.6180, 0, 2.9416, 0.7854])
+    b._franka_effort_limits = torch.tensor([87.0, 87.0, 87.0, 87.0, 12.0, 12.0, 12.0])
+    b.device = "cpu"
+    dpose = sinfill((n, 6), 0.83, 0.4) * torch.tensor([[0.1, 0.1, 0.1, 0.5, 0.5, 0.5]])
+    u = mod.Manipulator._compute_osc_torques(b, dpose)
+    # reset_idx (:385-447) on a bag whose gym calls are no-ops; torch's global generator supplies the draws, recorded for the test
+    r = types.SimpleNamespace()
+    r.device = "cpu"
+    r.command_x_range, r.command_y_range, r.command_z_range = [-0.5, 0.5], [-0.5, 0.5], [0.2, 0.6]
+    r.commands = torch.zeros(n, 3)
+    r.commands_x, r.commands_y, r.commands_z = (r.commands.view(n, 3)[..., i] for i in range(3))
+    r.franka_default_dof_pos = b.franka_default_dof_pos
+    r.franka_dof_noise = 0.25
+    r.franka_dof_lower_limits = torch.tensor([-2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973])
+    r.franka_dof_upper_limits = torch.tensor([2.8973, 1.7628, 2.8973, -0.0698, 2.8973, 3.7525, 2.8973])
+    r._q, r._qd = sinfill((n, 7), 0.3, 0.2, 1.0), sinfill((n, 7), 0.7, 0.2, 1.0)
+    r._pos_control, r._effort_control = torch.zeros(n, 7), torch.ones(n, 7)
+    r._global_indices = torch.arange(n, dtype=torch.int32).view(n, -1)
+    r._dof_state = torch.zeros(n, 7, 2)
+    noop = lambda *a, **k: None
+    r.gym = types.SimpleNamespace(set_dof_position_target_tensor_indexed=noop, set_dof_actuation_force_tensor_indexed=noop, set_dof_state_tensor_indexed=noop)
+    r.sim = None
+    r.progress_buf, r.reset_buf = torch.full((n,), 5, dtype=torch.long), torch.ones(n, dtype=torch.long)
+    env_ids = torch.arange(0, n, 3)
+    torch.manual_seed(123)
+    st = torch.get_rng_state()
+    k = len(env_ids)
+    draws = torch.cat([torch.rand(k, 1), torch.rand(k, 1), torch.rand(k, 1), torch.rand(k, 7)], dim=1)      # the order reset_idx draws in
+    torch.set_rng_state(st)
+    q_before = r._q.clone()
+    mod.Manipulator.reset_idx(r, env_ids)
+    np.savez_compressed(out, eef_pos=eef_pos.numpy(), commands=commands.numpy(), eef_vel=eef_vel.numpy(), progress=progress.numpy(), reset=reset.numpy(),
+                        rew=rew.numpy(), reset_out=rst.numpy(), mm=b._mm.numpy(), j_eef=b._j_eef.numpy(), q=b._q.numpy(), qd=b._qd.numpy(),
+                        dpose=dpose.numpy(), u=u.numpy(), effort=b._franka_effort_limits.numpy(), default_q=b.franka_default_dof_pos.numpy(),
+                        reset_env_ids=env_ids.numpy(), reset_draws=draws.numpy(), reset_q_before=q_before.numpy(), reset_q=r._q.numpy(), reset_qd=r._qd.numpy(),
+                        reset_commands=r.commands.numpy(), reset_progress=r.progress_buf.numpy(), reset_reset=r.reset_buf.numpy(),
+                        lower=r.franka_dof_lower_limits.numpy(), upper=r.franka_dof_upper_limits.numpy())
+    print(out, "rew range", float(rew.min()), float(rew.max()), "resets", int(rst.sum()), "|u| max", float(u.abs().max()),
+          "clamped torques", int((u.abs() >= b._franka_effort_limits - 1e-6).sum()))
+
+
+if __name__ == "__main__" and "--manipulator-only" in sys.argv:
+    gen_manipulator(os.path.join(HERE, "manipulator.npz"))

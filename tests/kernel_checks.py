@@ -26,7 +26,8 @@ HOUND_DEFAULT = {"roll": 0.0, "hip": 0.7854, "knee": -1.5708}
 def load_robot(name):
     files = {"anymal": "urdf__anymal_c__urdf__anymal.c1k1f0.json", "anymal_minimal": "urdf__anymal_c__urdf__anymal_minimal.c1k1f0.json",
              "hound": "urdf__Hound_new__Hound.c0k0f0.json", "useful_hound": "urdf__UsefulHound__urdf__Hound.c0k0f0.json",
-             "cartpole": "urdf__cartpole.c0k0f1.json", "houndarm": "urdf__open_manipulator_p_gazebo__urdf__open_manipulator_p.c0k0f1.json"}
+             "cartpole": "urdf__cartpole.c0k0f1.json", "houndarm": "urdf__open_manipulator_p_gazebo__urdf__open_manipulator_p.c0k0f1.json",
+             "manipulator": "urdf__franka_description__robots__franka_panda_manipulator.c0k0f1.json"}
     return load_articulation(os.path.join(COMPILED_DIR, files[name]))
 
 
@@ -962,13 +963,23 @@ def houndarm_params():
     return sp          # gravity zero: asset_options.disable_gravity (tasks/hound_arm.py:212)
 
 
+FRANKA_DEFAULT = (0.0, 0.1963, 0.0, -2.6180, 0.0, 2.9416, 0.7854)      # tasks/manipulator.py:153-155
+
+
 def houndarm_cfg(art, seed=42):
+    """Houndarm (6-DOF open_manipulator_p) or, for the 7-DOF Franka model, Manipulator (tasks/manipulator.py, cfg/task/Manipulator.yaml)."""
+    franka = art.num_dofs == 7
     c = _abi.HoundarmCfg(clip_obs=5.0, clip_actions=1.0, action_scale=1.0, dof_noise=0.25, kp=150.0, kp_null=10.0, dist_scale=0.1, vel_scale=0.1,
-                         eef_body=art.body_names.index("end_link"), jac_body=art.joint_dict["joint6"] + 1, max_episode_length=150, seed=seed)
+                         eef_body=art.body_names.index("panda_link7" if franka else "end_link"),
+                         jac_body=art.joint_dict["panda_joint7" if franka else "joint6"] + 1, max_episode_length=1000 if franka else 150, seed=seed,
+                         n_reset_tail=2 if franka else 0)
     for i, v in enumerate([0.1, 0.1, 0.1, 0.5, 0.5, 0.5]):
         c.cmd_limit[i] = v
-    for i, v in enumerate([-0.3, 0.3, -0.3, 0.3, 0.1, 0.3]):
+    for i, v in enumerate([-0.5, 0.5, -0.5, 0.5, 0.2, 0.6] if franka else [-0.3, 0.3, -0.3, 0.3, 0.1, 0.3]):
         c.cmd_range[i] = v
+    if franka:
+        for i, v in enumerate(FRANKA_DEFAULT):
+            c.default_dof_pos[i] = v
     return c
 
 
@@ -1009,13 +1020,26 @@ def houndarm_eef(art, root, dof, body):
     return out
 
 
-def check_houndarm_step(make_backend, n=12, steps=40, seed=23):
+def arm_reset_positions(default_q, noise, draws, lower, upper, tail):
+    """Joint positions after reset_idx of the arm reach tasks (hound_arm.py:441-446 / manipulator.py:407-417), float32 like the reference:
+    clamp(default + noise * 2 (u - 0.5), limits), then the last ``tail`` joints set back to their default (pinned to the reference's own
+    reset_idx by tests/test_manipulator.py)."""
+    q = np.clip(np.asarray(default_q, np.float32) + np.float32(noise) * np.float32(2.0) * (np.asarray(draws, np.float32) - np.float32(0.5)),
+                np.asarray(lower, np.float32), np.asarray(upper, np.float32))
+    if tail:
+        q[:, -tail:] = np.asarray(default_q, np.float32)[-tail:]
+    return q
+
+
+def check_houndarm_step(make_backend, n=12, steps=40, seed=23, robot="houndarm"):
     """Fused Houndarm step vs a composition of independent pieces: OSC torques (numpy restatement of the reference law) from the
     kernels' own Jacobian / mass-matrix tensors (themselves pinned to the oracle elsewhere), the float64 dynamics oracle for the
     sub-steps, reset draws, and observations / reward from the model compiler's numpy kinematics."""
-    art = load_robot("houndarm")
+    art = load_robot(robot)      # "manipulator": the same task on the 7-DOF Franka (six actions, seven torques, posture + reset quirks)
     sp, c = houndarm_params(), houndarm_cfg(art)
     c.max_episode_length = 17
+    default_q = np.array([c.default_dof_pos[i] for i in range(art.num_dofs)], np.float32)
+    tail = int(c.n_reset_tail)
     props = _abi.default_dof_props(art, _abi.DOF_MODE_EFFORT, 0.0, 0.0)
     m = _abi.pack_model(art)
     nd = art.num_dofs
@@ -1031,7 +1055,7 @@ def check_houndarm_step(make_backend, n=12, steps=40, seed=23):
         root = np.zeros((n, 13), np.float32)
         root[:, 0], root[:, 6] = -0.45, 1.0
         dof = np.zeros((n, nd, 2), np.float32)
-        dof[:, :, 0] = rng.uniform(-0.3, 0.3, (n, nd))
+        dof[:, :, 0] = np.clip(default_q + rng.uniform(-0.3, 0.3, (n, nd)), lower, upper)
         be.set_state(root, dof)
         commands = rng.uniform(-0.2, 0.3, (n, 3)).astype(np.float32)
         commands[:, 2] = np.abs(commands[:, 2])
@@ -1041,16 +1065,17 @@ def check_houndarm_step(make_backend, n=12, steps=40, seed=23):
         for k in range(steps):
             # moderate commands (a tenth of the entries beyond the clip range): violent motion drives the arm into configurations where
             # float32 cannot evaluate the law at all (see the tolerance note below)
-            actions = (rng.uniform(-0.5, 0.5, (n, nd)) * np.where(rng.uniform(0, 1, (n, nd)) < 0.1, 3.0, 1.0)).astype(np.float32)
-            draws = rng.uniform(0, 1, (n, 9)).astype(np.float32)
+            actions = (rng.uniform(-0.5, 0.5, (n, 6)) * np.where(rng.uniform(0, 1, (n, 6)) < 0.1, 3.0, 1.0)).astype(np.float32)
+            draws = rng.uniform(0, 1, (n, 3 + nd)).astype(np.float32)
             # --- oracle composition ---
             a = np.clip(actions, -1, 1)
             jm.set_state(r64.astype(np.float32), d64.astype(np.float32))
             J, MM = jm.jacobian_mass_matrix()
             eef = houndarm_eef(art, r64, d64, c.eef_body)
             dpose = a * np.array([0.1, 0.1, 0.1, 0.5, 0.5, 0.5], np.float32) / np.float32(1.0)
-            u = tm.osc_torques(MM[:, :6, :6].astype(np.float32), J[:, c.jac_body - 1, :, :6].astype(np.float32), dpose.astype(np.float32),
-                               eef[:, 7:].astype(np.float32), d64[:, :6, 0].astype(np.float32), d64[:, :6, 1].astype(np.float32), 150.0, 10.0, effort[:6], exact=True)
+            u = tm.osc_torques(MM[:, :nd, :nd].astype(np.float32), J[:, c.jac_body - 1, :, :nd].astype(np.float32), dpose.astype(np.float32),
+                               eef[:, 7:].astype(np.float32), d64[:, :nd, 0].astype(np.float32), d64[:, :nd, 1].astype(np.float32), 150.0, 10.0, effort[:nd], exact=True,
+                               default_q=default_q)
             # --- kernel ---
             be.task_step(actions, draws)
             rk, dk = be.get_state()
@@ -1062,8 +1087,8 @@ def check_houndarm_step(make_backend, n=12, steps=40, seed=23):
             # ~1e-6 of the largest torque wherever the problem is not outright singular (< 1e10), asserted after the loop.  The
             # oracle is advanced with the kernel's torques so that the dynamics comparison below stays a dynamics comparison.
             uk = t["dof_force"]
-            jj = J[:, c.jac_body - 1, :, :6].astype(np.float64)
-            cond = np.array([np.linalg.cond(jj[e] @ np.linalg.inv(MM[e, :6, :6].astype(np.float64)) @ jj[e].T) for e in range(n)])
+            jj = J[:, c.jac_body - 1, :, :nd].astype(np.float64)
+            cond = np.array([np.linalg.cond(jj[e] @ np.linalg.inv(MM[e, :nd, :nd].astype(np.float64)) @ jj[e].T) for e in range(n)])
             ok = cond < 1e10
             checked_torques += int(ok.sum())
             if ok.any():
@@ -1073,7 +1098,7 @@ def check_houndarm_step(make_backend, n=12, steps=40, seed=23):
             ids = np.nonzero(reset)[0]
             for kk in range(3):
                 commands[ids, kk] = (c.cmd_range[2 * kk + 1] - c.cmd_range[2 * kk]) * draws[ids, kk] + c.cmd_range[2 * kk]
-            newq = np.clip(np.float32(0.25) * np.float32(2.0) * (draws[ids, 3:9] - np.float32(0.5)), lower, upper)
+            newq = arm_reset_positions(default_q, 0.25, draws[ids, 3:3 + nd], lower, upper, tail)
             d64[ids, :, 0], d64[ids, :, 1] = newq, 0.0
             progress[ids], reset[ids] = 0, 0
             eef = houndarm_eef(art, r64, d64, c.eef_body)

@@ -21,7 +21,7 @@ HAVE_REF = os.path.isdir(os.path.join(REF, "isaacgymenvs", "tasks"))
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="no reference checkout (B2G_REFERENCE_ROOT)")
 
 HOT_PATH_FILES = ["tasks/base/vec_task.py", "tasks/anymal.py", "tasks/hound.py", "tasks/cartpole.py", "tasks/anymal_terrain.py", "tasks/Hound_terrain.py",
-                  "tasks/useful_hound.py", "tasks/hound_arm.py", "utils/dr_utils.py"]
+                  "tasks/useful_hound.py", "tasks/hound_arm.py", "tasks/manipulator.py", "utils/dr_utils.py"]
 # names only reached with a viewer / camera sensors / an external params generator (headless=True training never calls them;
 # SURVEY 8(b) "viewer / DR (not needed headless)")
 VIEWER_ONLY = {"create_viewer", "subscribe_viewer_keyboard_event", "query_viewer_has_closed", "query_viewer_action_events", "poll_viewer_events",
@@ -70,7 +70,7 @@ def test_shim_covers_every_gym_name_the_hot_path_files_use():
 
 @needs_ref
 @pytest.mark.parametrize("module,cls", [("tasks.anymal", "Anymal"), ("tasks.hound", "Hound"), ("tasks.cartpole", "Cartpole"), ("tasks.anymal_terrain", "AnymalTerrain"),
-                                        ("tasks.Hound_terrain", "HoundTerrain"), ("tasks.useful_hound", "UsefulHound"), ("tasks.hound_arm", "Houndarm")])
+                                        ("tasks.Hound_terrain", "HoundTerrain"), ("tasks.useful_hound", "UsefulHound"), ("tasks.hound_arm", "Houndarm"), ("tasks.manipulator", "Manipulator")])
 def test_reference_task_modules_import_unmodified_under_the_shim(module, cls):
     import isaacgymenv_b200 as b2g
 

@@ -11,7 +11,7 @@ def make(art, params, props, n):
     return EmuBackend(art, params, props, n)
 
 
-@pytest.mark.parametrize("robot", ["anymal", "hound", "useful_hound", "cartpole"])
+@pytest.mark.parametrize("robot", ["anymal", "hound", "useful_hound", "cartpole", "houndarm", "manipulator"])
 def test_forward_dynamics(robot):
     kc.check_forward_dynamics(make, robot, n=6)
 
@@ -70,13 +70,17 @@ def test_useful_hound_step():
     kc.check_useful_step(make, n=4)
 
 
-@pytest.mark.parametrize("robot", ["useful_hound", "anymal", "cartpole"])
+@pytest.mark.parametrize("robot", ["useful_hound", "anymal", "cartpole", "houndarm", "manipulator"])
 def test_jacobian_mass_matrix(robot):
     kc.check_jacobian_mass_matrix(make, robot)
 
 
 def test_houndarm_fused_step():
     kc.check_houndarm_step(make, n=4)
+
+
+def test_manipulator_fused_step():
+    kc.check_houndarm_step(make, n=4, robot="manipulator")
 
 
 def _emu_sim_hf(art, sp, props, hf_t, samples, root, dof, steps):

@@ -9,6 +9,8 @@ Run in the build container (needs /root/reference); the outputs under
   UsefulHound Hound    tasks/useful_hound.py:316-327    (no collapse)
   cartpole.urdf        tasks/cartpole.py:86-88          (fixed base)
   open_manipulator_p   tasks/hound_arm.py:203-216       (fixed base, no collapse, gravity disabled)
+  franka_panda_manipulator  tasks/manipulator.py:199-214  (fixed base, no collapse, gravity disabled; no <inertial>: mass properties
+                                                          from the convex hulls of the collision meshes at the default density)
 """
 import os
 import sys
@@ -28,6 +30,8 @@ JOBS = [
     ("urdf/cartpole.urdf", AssetOptions(fix_base_link=True)),
     ("urdf/open_manipulator_p_gazebo/urdf/open_manipulator_p.urdf", AssetOptions(fix_base_link=True, collapse_fixed_joints=False,
                                                                                 replace_cylinder_with_capsule=False, disable_gravity=True, thickness=0.001)),
+    ("urdf/franka_description/robots/franka_panda_manipulator.urdf", AssetOptions(fix_base_link=True, collapse_fixed_joints=False, disable_gravity=True,
+                                                                                  thickness=0.001)),
 ]
 
 if __name__ == "__main__":

@@ -41,7 +41,7 @@ def main():
     cfg = PPOConfig()
     if args.task != "Anymal" and args.task != "Hound":
         cfg = PPOConfig(units=(512, 256, 128), minibatch_size=16384, entropy_coef=0.001)
-    if args.task == "Houndarm":      # cfg/train/HoundarmPPO.yaml:24,65-67
+    if args.task in ("Houndarm", "Manipulator"):      # cfg/train/HoundarmPPO.yaml / ManipulatorPPO.yaml:24,65-67
         cfg = PPOConfig(units=(256, 128, 64), horizon_length=32, minibatch_size=16384, mini_epochs=5)
     if args.task == "Cartpole":
         cfg = PPOConfig(units=(32, 32), horizon_length=16, minibatch_size=8192, mini_epochs=8)
