@@ -112,6 +112,9 @@ typedef struct b2g_sim_params {
                                          contact a body has; here candidates beyond the slots are dropped and counted
                                          (b2g_sim_contact_stats) -- pick the smallest value whose drop count stays negligible: the
                                          slots live in shared memory ([slot][field][thread]) and take L1 capacity from the kernels */
+    float max_linear_velocity;        /* gymapi.AssetOptions.max_linear_velocity / max_angular_velocity (defaults 1000 m/s, 64 rad/s; the     */
+    float max_angular_velocity;       /* hot-path tasks leave them alone): the root body's velocity is clamped to them after the contact solve,  */
+                                      /* as PhysX clamps a body's velocity.  0 = no limit                                                        */
 } b2g_sim_params;
 
 /* per-DOF drive properties, identical for every env (reference: tasks/anymal.py:199-203,214) */

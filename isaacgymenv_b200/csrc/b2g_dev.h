@@ -64,6 +64,7 @@ struct DevParams {
     int has_ground;
     float limit_kp, limit_kd;   // joint-limit spring / damper
     int block_align;            // bit mask of the points of a sub-step at which the block's warps re-align (b2g_dynamics.cuh::block_align)
+    float max_lin_vel, max_ang_vel;   // root velocity clamps (0 = none), b2g_sim_params::max_linear_velocity / max_angular_velocity
     int max_contacts;           // contact slots per lane in use (<= B2G_MAX_CONTACTS_PER_CHAIN); sizes the shared-memory scratch
     // heightfield (null -> plane z = 0)
     const int16_t* hf;

@@ -821,6 +821,17 @@ B2G_LINK_UNROLL
         for (int j = 0; j < NL; j++) qdpos[j] = qdn[j];
     }
 
+    // root velocity limits (PhysX clamps a body's linear / angular velocity: AssetOptions.max_linear_velocity / max_angular_velocity):
+    // inactive in any sane state -- no arithmetic happens then -- and the guard that keeps a diverging controller from reaching inf / nan
+    if (!FIXED) {
+        auto clamp_norm = [](V3& v, float lim) {
+            const float n2 = dot(v, v);
+            if (lim > 0.0f && n2 > lim * lim) v = v * (lim / sqrtf(n2));
+        };
+        clamp_norm(v0n.v, P.max_lin_vel); clamp_norm(v0pos.v, P.max_lin_vel);
+        clamp_norm(v0n.w, P.max_ang_vel); clamp_norm(v0pos.w, P.max_ang_vel);
+    }
+
     // ---------------- integrate ----------------
 #pragma unroll
     for (int j = 0; j < NL; j++) {

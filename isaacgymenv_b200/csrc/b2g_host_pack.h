@@ -207,6 +207,8 @@ inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, 
     d.has_ground = s.has_ground;
     d.limit_kp = s.joint_limit_stiffness; d.limit_kd = s.joint_limit_damping;
     d.max_contacts = contact_slots(s);
+    d.max_lin_vel = s.max_linear_velocity > 0.0f ? s.max_linear_velocity : 0.0f;
+    d.max_ang_vel = s.max_angular_velocity > 0.0f ? s.max_angular_velocity : 0.0f;
     {
         const char* ba = getenv("B2G_BLOCK_ALIGN");
         d.block_align = ba ? atoi(ba) : 1;      // default: the block's warps re-align at the start of every sub-step (B2G_BLOCK_ALIGN=0: never)

@@ -254,6 +254,10 @@ class Sim:
         if asset is not None and getattr(asset.options, "disable_gravity", False):
             # AssetOptions.disable_gravity (tasks/hound_arm.py:212): the sim holds one articulation type, so its bodies are all of them
             c.gravity[0] = c.gravity[1] = c.gravity[2] = 0.0
+        # AssetOptions.max_linear_velocity / max_angular_velocity (Isaac Gym defaults 1000 m/s, 64 rad/s; no hot-path task changes them)
+        opts = getattr(asset, "options", None)
+        c.max_linear_velocity = float(getattr(opts, "max_linear_velocity", 1000.0) or 0.0)
+        c.max_angular_velocity = float(getattr(opts, "max_angular_velocity", 64.0) or 0.0)
         return c
 
     def stream(self):

@@ -530,6 +530,16 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
         for (int d = 0; d < nd; d++) qdpos[d] = qd[d];
     }
 
+    if (!m->fixed_base) {   /* root velocity limits (b2g_sim_params::max_linear_velocity / max_angular_velocity; 0 = none) */
+        R* vs[2] = {v0, vpos0};
+        for (int k = 0; k < 2; k++) {
+            R* v = vs[k];
+            R lim_w = (R)sp->max_angular_velocity, lim_v = (R)sp->max_linear_velocity;
+            R w2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], l2 = v[3] * v[3] + v[4] * v[4] + v[5] * v[5];
+            if (lim_w > 0 && w2 > lim_w * lim_w) { R sc = lim_w / (R)sqrt((double)w2); v[0] *= sc; v[1] *= sc; v[2] *= sc; }
+            if (lim_v > 0 && l2 > lim_v * lim_v) { R sc = lim_v / (R)sqrt((double)l2); v[3] *= sc; v[4] *= sc; v[5] *= sc; }
+        }
+    }
     /* ---- integrate positions with the post-position-iteration velocity ---- */
     for (int d = 0; d < nd; d++) {
         R vl = (R)dp->velocity[d];
@@ -820,6 +830,16 @@ static int FN(orc_substep_ref)(const b2g_model* m, const b2g_sim_params* sp, con
     }
     info[0] = nc; info[3] = capped;
 
+    if (!m->fixed_base) {   /* root velocity limits (b2g_sim_params::max_linear_velocity / max_angular_velocity; 0 = none) */
+        R* vs[2] = {v0, vpos0};
+        for (int k = 0; k < 2; k++) {
+            R* v = vs[k];
+            R lim_w = (R)sp->max_angular_velocity, lim_v = (R)sp->max_linear_velocity;
+            R w2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], l2 = v[3] * v[3] + v[4] * v[4] + v[5] * v[5];
+            if (lim_w > 0 && w2 > lim_w * lim_w) { R sc = lim_w / (R)sqrt((double)w2); v[0] *= sc; v[1] *= sc; v[2] *= sc; }
+            if (lim_v > 0 && l2 > lim_v * lim_v) { R sc = lim_v / (R)sqrt((double)l2); v[3] *= sc; v[4] *= sc; v[5] *= sc; }
+        }
+    }
     for (int d = 0; d < nd; d++) {
         R vl = (R)dp->velocity[d];
         if (vl > 0) { if (qd[d] > vl) qd[d] = vl; if (qd[d] < -vl) qd[d] = -vl; if (qdpos[d] > vl) qdpos[d] = vl; if (qdpos[d] < -vl) qdpos[d] = -vl; }

@@ -287,6 +287,48 @@ def check_simulate_horizon(make_backend, robot="anymal", n=16, steps=10, seed=1,
     return worst
 
 
+def check_root_velocity_limits(make_backend, robot="anymal", n=8, seed=4):
+    """b2g_sim_params::max_linear_velocity / max_angular_velocity (AssetOptions defaults 1000 m/s, 64 rad/s): a robot in free flight that
+    spins at 150 rad/s and moves at 2500 m/s leaves the step at exactly the limits; one inside them is untouched; limits of 0 switch the
+    clamp off.  Kernel == oracle in all three cases."""
+    art = load_robot(robot)
+    rng = np.random.default_rng(seed)
+    nd = art.num_dofs
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 85.0, 2.0)
+    m = _abi.pack_model(art)
+    q0 = default_pose(art)
+    for lim_v, lim_w in ((1000.0, 64.0), (0.0, 0.0)):
+        sp = flat_params(ground=False)
+        sp.gravity[2] = 0.0
+        sp.max_linear_velocity, sp.max_angular_velocity = lim_v, lim_w
+        root, dof = standing_state(art, n, rng, 5.0)
+        dof[:, :, 1] = 0.0
+        fast = np.arange(n) % 2 == 0
+        root[fast, 7:10] = np.array([2500.0, 0.0, 0.0], np.float32)
+        root[fast, 10:13] = np.array([0.0, 0.0, 150.0], np.float32)
+        root[~fast, 7:10] = np.array([1.0, -2.0, 0.5], np.float32)
+        root[~fast, 10:13] = np.array([0.3, 0.2, -0.4], np.float32)
+        be = make_backend(art, sp, props, n)
+        try:
+            be.set_state(root, dof)
+            r64, d64 = root.astype(np.float64), dof.astype(np.float64)
+            tgt = np.tile(q0, (n, 1))
+            be.simulate(tgt, np.zeros((n, nd)))
+            O.simulate(m, sp, props, r64, d64, tgt.astype(np.float64), np.zeros((n, nd)))
+            rb, _ = be.get_state()
+        finally:
+            be.close()
+        speed, spin = np.linalg.norm(rb[:, 7:10], axis=1), np.linalg.norm(rb[:, 10:13], axis=1)
+        if lim_v > 0:
+            assert np.all(speed[fast] <= lim_v * (1 + 1e-5)) and np.all(speed[fast] > 0.99 * lim_v), speed
+            assert np.all(spin[fast] <= lim_w * (1 + 1e-5)) and np.all(spin[fast] > 0.9 * lim_w), spin      # (momentum moves between the base and the legs inside the step)
+        else:
+            assert np.all(speed[fast] > 2000.0) and np.all(spin[fast] > 100.0)
+        assert np.all(speed[~fast] < 3.0) and np.all(spin[~fast] < 1.0)
+        np.testing.assert_allclose(rb[:, 7:13], r64[:, 7:13], rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(rb[~fast, :3], r64[~fast, :3], atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------
 def anymal_cfg(art, seed=42, robot="anymal"):
     c = _abi.AnymalCfg()

@@ -75,6 +75,10 @@ def test_jacobian_mass_matrix(robot):
     kc.check_jacobian_mass_matrix(make, robot)
 
 
+def test_root_velocity_limits():
+    kc.check_root_velocity_limits(make)
+
+
 def test_houndarm_fused_step():
     kc.check_houndarm_step(make, n=4)
 
