@@ -115,6 +115,10 @@ typedef struct b2g_sim_params {
     float max_linear_velocity;        /* gymapi.AssetOptions.max_linear_velocity / max_angular_velocity (defaults 1000 m/s, 64 rad/s; the     */
     float max_angular_velocity;       /* hot-path tasks leave them alone): the root body's velocity is clamped to them after the contact solve,  */
                                       /* as PhysX clamps a body's velocity.  0 = no limit                                                        */
+    int32_t self_collision;           /* 1: the candidate spheres of every link that does not hang off the root directly also collide with the
+                                         root's bounding box (the reference's rough-terrain tasks create their actors with collision filter
+                                         0 = self-collision on, tasks/anymal_terrain.py:282; the flat tasks with 1 = off).  A leg or arm
+                                         can then no longer swing through the base.  Link-link pairs are not modelled.                        */
 } b2g_sim_params;
 
 /* per-DOF drive properties, identical for every env (reference: tasks/anymal.py:199-203,214) */

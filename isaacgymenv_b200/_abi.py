@@ -56,7 +56,7 @@ class SimParams(C.Structure):
         ("max_depenetration_velocity", f32),
         ("plane_static_friction", f32), ("plane_dynamic_friction", f32), ("plane_restitution", f32),
         ("has_ground", i32), ("joint_limit_stiffness", f32), ("joint_limit_damping", f32), ("max_contacts_per_chain", i32),
-        ("max_linear_velocity", f32), ("max_angular_velocity", f32),
+        ("max_linear_velocity", f32), ("max_angular_velocity", f32), ("self_collision", i32),
     ]
 
 

@@ -45,6 +45,7 @@ struct DevModel {
     float root_com[3];
     float root_inertia[6];
     float root_cp_c[3], root_cp_h[3];    // bounding box of the root-link contact candidates
+    float self_box_c[3], self_box_h[3];  // self-collision box: bounding box of the candidates of API body 0 (the base itself, without bodies fixed to it)
     DevDof dof[B2G_MAX_DOF];
     float cp[B2G_MAX_CPTS][4];   // link-frame position, radius
     int cp_body[B2G_MAX_CPTS];
@@ -65,6 +66,7 @@ struct DevParams {
     float limit_kp, limit_kd;   // joint-limit spring / damper
     int block_align;            // bit mask of the points of a sub-step at which the block's warps re-align (b2g_dynamics.cuh::block_align)
     float max_lin_vel, max_ang_vel;   // root velocity clamps (0 = none), b2g_sim_params::max_linear_velocity / max_angular_velocity
+    int self_collide;           // b2g_sim_params::self_collision: link candidates also collide with the root's bounding box
     int max_contacts;           // contact slots per lane in use (<= B2G_MAX_CONTACTS_PER_CHAIN); sizes the shared-memory scratch
     // heightfield (null -> plane z = 0)
     const int16_t* hf;

@@ -289,6 +289,7 @@ size_t link_store_floats(int n_envs_per_block, int n_dof) { return (size_t)n_env
 // parent piece (joint axis S, U = I^A S, 1 / D) through shared memory when it propagates a contact impulse to the root.
 template <int LANES, int NL>
 B2G_HD constexpr bool is_segmented() { return LANES == 8 && NL == 3; }
+constexpr int kSelfJc = 64;                           // CF_JC of a self-collision slot = link index + kSelfJc
 constexpr int kAncLinkFloats = 16;                    // S (6) | U (6) | 1/D | 3 pad: 16-byte rows
 constexpr int kAncFloats = 3 * kAncLinkFloats;        // a piece with a child is always full
 
@@ -622,6 +623,38 @@ B2G_LINK_UNROLL
             sc.at(s, CF_LN) = 0.0f; sc.at(s, CF_L1) = 0.0f; sc.at(s, CF_L2) = 0.0f;
         }
     };
+    // Self-collision (DevParams::self_collide): the candidate sphere against the BASE's bounding box (self_box_c / self_box_h: the box, in the
+    // root frame, around the candidates of API body 0 and their radii -- bodies fixed to the base, e.g. an arm's mount, are left out).  Signed distance = the largest of the three slab distances (exact over
+    // a face, a lower bound next to an edge), normal = that face's outward normal.  The slot is marked by kSelfJc added to its link index:
+    // the impulse acts on the link and, with the opposite sign, on the root; velocities at the contact are relative to the root.
+    auto test_self = [&](int i, const M3& R, V3 p, int jc) {
+        const float cx = M->cp[i][0], cy = M->cp[i][1], cz = M->cp[i][2], cr = M->cp[i][3];
+        const V3 rc = p + mul(R, V3{cx, cy, cz});
+        const V3 q = mulT(R0, rc) - V3{M->self_box_c[0], M->self_box_c[1], M->self_box_c[2]};
+        const float dx = fabsf(q.x) - M->self_box_h[0] - cr, dy = fabsf(q.y) - M->self_box_h[1] - cr, dz = fabsf(q.z) - M->self_box_h[2] - cr;
+        int best = 0;
+        float gap = dx;
+        if (dy > gap) { gap = dy; best = 1; }
+        if (dz > gap) { gap = dz; best = 2; }
+        if (gap < P.contact_offset && ncon >= P.max_contacts) ndrop++;
+        if (gap < P.contact_offset && ncon < P.max_contacts) {
+            const float sgn = (best == 0 ? q.x : best == 1 ? q.y : q.z) < 0.0f ? -1.0f : 1.0f;
+            const V3 n = V3{R0.m[best], R0.m[3 + best], R0.m[6 + best]} * sgn;
+            const V3 r = rc - n * cr;
+            V3 t1 = V3{1.0f - n.x * n.x, -n.x * n.y, -n.x * n.z};
+            t1 = t1 * (1.0f / sqrtf(dot(t1, t1)));
+            const V3 t2 = cross(n, t1);
+            const int s = ncon++;
+            sc.at(s, CF_RX) = r.x; sc.at(s, CF_RY) = r.y; sc.at(s, CF_RZ) = r.z;
+            sc.at(s, CF_NX) = n.x; sc.at(s, CF_NY) = n.y; sc.at(s, CF_NZ) = n.z;
+            sc.at(s, CF_T1X) = t1.x; sc.at(s, CF_T1Y) = t1.y; sc.at(s, CF_T1Z) = t1.z;
+            sc.at(s, CF_T2X) = t2.x; sc.at(s, CF_T2Y) = t2.y; sc.at(s, CF_T2Z) = t2.z;
+            sc.at(s, CF_GAP) = gap;
+            sc.at(s, CF_JC) = (float)(jc + kSelfJc);
+            sc.at(s, CF_BODY) = (float)M->cp_body[i];
+            sc.at(s, CF_LN) = 0.0f; sc.at(s, CF_L1) = 0.0f; sc.at(s, CF_L2) = 0.0f;
+        }
+    };
     // plane ground: a link whose candidate bounding box clears the contact offset cannot touch (skips most loops)
     // heightfield: the same test against a coarse conservative bound of the terrain under the box (max height and min
     // normal z of the dilated block that holds the box centre, b2g_host_pack.h::build_hf_coarse): every candidate of the
@@ -648,17 +681,20 @@ B2G_LINK_UNROLL
 #endif
         return !skip;
     };
-    if (ground) {
+    const bool self_col = P.self_collide != 0;
+    if (ground || self_col) {
 B2G_LINK_UNROLL
         for (int j = NL - 1; j >= 0; j--) {
             if (j < len) {
                 const DevDof& D = M->dof[d0 + j];
                 const int c0 = D.cp_start, cn = D.cp_count;
-                if (cn > 0 && may_touch(L[j].Rl, L[j].pl, D.cp_c, D.cp_h))
+                if (ground && cn > 0 && may_touch(L[j].Rl, L[j].pl, D.cp_c, D.cp_h))
                     for (int i = c0; i < c0 + cn; i++) test_candidate(i, L[j].Rl, L[j].pl, j);
+                if (self_col && (j >= 1 || distal))      // not the link that hangs off the root directly (PhysX: no parent-child collision)
+                    for (int i = c0; i < c0 + cn; i++) test_self(i, L[j].Rl, L[j].pl, j);
             }
         }
-        if (!FIXED) {
+        if (!FIXED && ground) {
             const int c0 = M->root_cp_start[lane], cn = M->root_cp_count[lane];
             if (cn > 0 && may_touch(R0, V3{0, 0, 0}, M->root_cp_c, M->root_cp_h))
                 for (int i = c0; i < c0 + cn; i++) test_candidate(i, R0, V3{0, 0, 0}, -1);
@@ -683,14 +719,18 @@ B2G_LINK_UNROLL
             const V3 r = V3{sc.at(s, CF_RX), sc.at(s, CF_RY), sc.at(s, CF_RZ)};
             const V3 dirs[3] = {V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)}, V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)},
                                 V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)}};
-            const int jc = (int)sc.at(s, CF_JC);
+            const int jcf = (int)sc.at(s, CF_JC);
+            const bool selfc = jcf >= kSelfJc / 2;
+            const int jc = selfc ? jcf - kSelfJc : jcf;
             float A[9];
 #pragma unroll
             for (int b = 0; b < 3; b++) {
                 float ud[NL], uda[3];
                 const SV F = SV{cross(r, dirs[b]), dirs[b]};
-                const SV Pb = push_up(jc, F, ud, uda);
+                SV Pb = push_up(jc, F, ud, uda);
+                if (selfc && !FIXED) Pb += F;      // the reaction -F acts on the root
                 SV a = FIXED ? sv0() : -mul(inv, Pb);
+                const SV a_root = a;
                 if (SEG && distal) run_anc(a, uda);
 #pragma unroll
                 for (int k = 0; k < NL; k++) {
@@ -699,6 +739,7 @@ B2G_LINK_UNROLL
                         a += L[k].S * dq;
                     }
                 }
+                if (selfc) a = a - a_root;         // response of the velocity RELATIVE to the root
                 const V3 pv = a.v + cross(a.w, r);
 #pragma unroll
                 for (int c = 0; c < 3; c++) A[c * 3 + b] = dot(pv, dirs[c]);
@@ -740,8 +781,11 @@ B2G_LINK_UNROLL
                 const V3 n = V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)};
                 const V3 t1 = V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)};
                 const V3 t2 = V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)};
-                const int jc = (int)sc.at(s, CF_JC);
+                const int jcf = (int)sc.at(s, CF_JC);
+                const bool selfc = jcf >= kSelfJc / 2;
+                const int jc = selfc ? jcf - kSelfJc : jcf;
                 SV lv = distal ? vbase : v0n;
+                if (selfc) lv = distal ? vbase - v0n : sv0();      // relative to the root
 #pragma unroll
                 for (int k = 0; k < NL; k++)
                     if (k <= jc) lv += L[k].S * qdn[k];
@@ -777,6 +821,7 @@ B2G_LINK_UNROLL
                 sc.at(s, CF_LN) = ln; sc.at(s, CF_L1) = l1; sc.at(s, CF_L2) = l2;
                 const V3 dir = n * dn + t1 * (l1 - l1o) + t2 * (l2 - l2o);
                 Pb = push_up(jc, SV{cross(r, dir), dir}, ud, uda);
+                if (selfc && !FIXED) Pb += SV{cross(r, dir), dir};
             }
             if (SEG) {      // the joint terms a distal piece found for its parent's links
 #pragma unroll
@@ -889,9 +934,11 @@ B2G_LINK_UNROLL
                 for (int s = 0; s < ncon; s++) {
                     const float ln = sc.at(s, CF_LN) * ih, l1 = sc.at(s, CF_L1) * ih, l2 = sc.at(s, CF_L2) * ih;
                     const int b = (int)sc.at(s, CF_BODY);
-                    bf[b * 3 + 0] += sc.at(s, CF_NX) * ln + sc.at(s, CF_T1X) * l1 + sc.at(s, CF_T2X) * l2;
-                    bf[b * 3 + 1] += sc.at(s, CF_NY) * ln + sc.at(s, CF_T1Y) * l1 + sc.at(s, CF_T2Y) * l2;
-                    bf[b * 3 + 2] += sc.at(s, CF_NZ) * ln + sc.at(s, CF_T1Z) * l1 + sc.at(s, CF_T2Z) * l2;
+                    const float fx = sc.at(s, CF_NX) * ln + sc.at(s, CF_T1X) * l1 + sc.at(s, CF_T2X) * l2;
+                    const float fy = sc.at(s, CF_NY) * ln + sc.at(s, CF_T1Y) * l1 + sc.at(s, CF_T2Y) * l2;
+                    const float fz = sc.at(s, CF_NZ) * ln + sc.at(s, CF_T1Z) * l1 + sc.at(s, CF_T2Z) * l2;
+                    bf[b * 3 + 0] += fx; bf[b * 3 + 1] += fy; bf[b * 3 + 2] += fz;
+                    if ((int)sc.at(s, CF_JC) >= kSelfJc / 2) { bf[0] -= fx; bf[1] -= fy; bf[2] -= fz; }      // self contact: the reaction on the root body (API body 0)
                 }
             }
             Grp<LANES>::sync();

@@ -121,6 +121,19 @@ inline int pack_dev_model(const b2g_model& m, const b2g_dof_props& p, DevModel& 
         float* h = l == 0 ? d.root_cp_h : d.dof[l - 1].cp_h;
         for (int a = 0; a < 3; a++) { c[a] = cnt ? 0.5f * (lo[a] + hi[a]) : 0.0f; h[a] = cnt ? 0.5f * (hi[a] - lo[a]) : 0.0f; }
     }
+    {   // self-collision box (b2g_sim_params::self_collision): the base body's own candidates and their radii
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        int cnt = 0;
+        for (int i = 0; i < m.n_cpts; i++) {
+            if (m.cp_link[i] != 0 || m.cp_body[i] != 0) continue;
+            cnt++;
+            for (int a = 0; a < 3; a++) {
+                lo[a] = fminf(lo[a], m.cp_pos[i][a] - m.cp_radius[i]);
+                hi[a] = fmaxf(hi[a], m.cp_pos[i][a] + m.cp_radius[i]);
+            }
+        }
+        for (int a = 0; a < 3; a++) { d.self_box_c[a] = cnt ? 0.5f * (lo[a] + hi[a]) : 0.0f; d.self_box_h[a] = cnt ? 0.5f * (hi[a] - lo[a]) : -1e30f; }
+    }
     for (int b = 0; b < m.n_bodies; b++) {
         d.body_link[b] = m.body_link[b];
         for (int a = 0; a < 3; a++) d.body_pos[b][a] = m.body_pos[b][a];
@@ -207,6 +220,7 @@ inline void pack_dev_params(const b2g_sim_params& s, const b2g_heightfield* hf, 
     d.has_ground = s.has_ground;
     d.limit_kp = s.joint_limit_stiffness; d.limit_kd = s.joint_limit_damping;
     d.max_contacts = contact_slots(s);
+    d.self_collide = s.self_collision != 0;
     d.max_lin_vel = s.max_linear_velocity > 0.0f ? s.max_linear_velocity : 0.0f;
     d.max_ang_vel = s.max_angular_velocity > 0.0f ? s.max_angular_velocity : 0.0f;
     {

@@ -258,6 +258,8 @@ class Sim:
         opts = getattr(asset, "options", None)
         c.max_linear_velocity = float(getattr(opts, "max_linear_velocity", 1000.0) or 0.0)
         c.max_angular_velocity = float(getattr(opts, "max_angular_velocity", 64.0) or 0.0)
+        sc = getattr(px, "self_collision", None)
+        c.self_collision = int(bool(getattr(self, "self_collision", False) if sc is None else sc))
         return c
 
     def stream(self):
@@ -323,9 +325,9 @@ class Gym:
         n = len(sim.envs)
         _lib.check(lib.b2g_sim_add_articulation(sim.handle, C.byref(sim.model_struct), C.byref(props), n, pose7,
                                                 float(sim.env_spacing), int(sim.num_per_row)), "create_actor")
-        if getattr(sim.asset.options, "disable_gravity", False):
-            cp = sim.c_params()
-            _lib.check(lib.b2g_sim_set_params(sim.handle, C.byref(cp)), "set_sim_params")
+        # what the actor brings to the sim parameters: AssetOptions.disable_gravity and velocity limits, create_actor's collision filter
+        cp = sim.c_params()
+        _lib.check(lib.b2g_sim_set_params(sim.handle, C.byref(cp)), "set_sim_params")
         _lib.check(lib.b2g_sim_prepare(sim.handle), "prepare_sim")
         sim.prepared = True
         import torch
@@ -490,9 +492,12 @@ class Gym:
         return env
 
     def create_actor(self, env: Env, asset: Asset, pose: Transform, name: str = "", group: int = -1, filter: int = -1, segmentationId: int = 0):
-        """tasks/anymal.py:213.  One actor (articulation type) per env; `filter` = self-collision mask is ignored
-        (links of one robot never collide with each other in this engine -- DESIGN.md deviations)."""
+        """tasks/anymal.py:213.  One actor (articulation type) per env.  `filter` is Isaac Gym's collision-filter mask: bodies whose masks share
+        a bit do not collide, so 0 (the rough-terrain tasks, tasks/anymal_terrain.py:282) switches self-collision ON and 1 (the flat tasks)
+        off.  On -> b2g_sim_params.self_collision: the links that do not hang off the base directly collide with the base's box
+        (link-link pairs are not modelled, DESIGN.md deviations); `sim.physx.self_collision` in the yaml overrides it."""
         sim = env.sim
+        sim.self_collision = int(filter) == 0
         if sim.asset is None:
             sim.asset, sim.actor_name, sim.actor_pose = asset, name, pose
         elif sim.asset is not asset:

@@ -336,6 +336,7 @@ static void FN(orc_ground)(const b2g_heightfield* hf, const int16_t* s, R x, R y
 
 typedef struct FN(orc_contact) {
     int link, body;
+    int self_c;      /* 1: the other body is the robot's own root link (self-collision), 0: the ground */
     R r[3];          /* contact point relative to O */
     R n[3], t1[3], t2[3];
     R gap;
@@ -347,6 +348,87 @@ static void FN(orc_contact_wrench)(const FN(orc_contact)* c, const R* dir, R* F)
     R mom[3];
     FN(cross3)(c->r, dir, mom);
     for (int i = 0; i < 3; i++) { F[i] = mom[i]; F[3 + i] = dir[i]; }
+}
+
+static void FN(orc_point_velocity)(const FN(orc_contact)* c, const R* v, R* out);
+static void FN(orc_contact_wrench)(const FN(orc_contact)* c, const R* dir, R* F);
+
+/* impulse F on the contact's link; a self contact puts the reaction -F on the root */
+static void FN(orc_apply_contact_impulse)(const b2g_model* m, const FN(orc_kin)* k, const FN(orc_contact)* cc, const R* F, R* v0, R* qd) {
+    FN(orc_apply_impulse)(m, k, cc->link, F, -1, 0, v0, qd);
+    if (cc->self_c && !m->fixed_base) {
+        R Fm[6];
+        for (int i = 0; i < 6; i++) Fm[i] = -F[i];
+        FN(orc_apply_impulse)(m, k, 0, Fm, -1, 0, v0, qd);
+    }
+}
+
+/* velocity of the contact point on the link relative to the other body: the ground (at rest) or, for a self contact, the root */
+static void FN(orc_contact_velocity)(const b2g_model* m, const FN(orc_kin)* k, const FN(orc_contact)* cc, const R* v0, const R* qd, R* pv) {
+    R lv[6];
+    FN(orc_link_velocity)(m, k, cc->link, v0, qd, lv);
+    if (cc->self_c && !m->fixed_base) for (int i = 0; i < 6; i++) lv[i] -= v0[i];
+    FN(orc_point_velocity)(cc, lv, pv);
+}
+
+/* tangent frame, zero impulse and local Delassus block of a contact whose link, point, normal and gap are set */
+static void FN(orc_finish_contact)(const b2g_model* m, const FN(orc_kin)* k, FN(orc_contact)* cc) {
+    int nd = m->n_dof;
+    for (int a = 0; a < 3; a++) cc->lam[a] = 0;
+    /* tangent basis: t1 = normalise(x_world - (x.n) n), t2 = n x t1 */
+    R dn = cc->n[0];
+    R t1[3] = {1 - dn * cc->n[0], -dn * cc->n[1], -dn * cc->n[2]};
+    R inv = 1 / (R)sqrt((double)(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]));
+    for (int a = 0; a < 3; a++) cc->t1[a] = t1[a] * inv;
+    FN(cross3)(cc->n, cc->t1, cc->t2);
+    const R* dirs[3] = {cc->n, cc->t1, cc->t2};
+    for (int b = 0; b < 3; b++) {
+        R F[6], dv0[6] = {0, 0, 0, 0, 0, 0}, dqd[B2G_MAX_DOF], pv[3];
+        for (int d = 0; d < nd; d++) dqd[d] = 0;
+        FN(orc_contact_wrench)(cc, dirs[b], F);
+        FN(orc_apply_contact_impulse)(m, k, cc, F, dv0, dqd);
+        FN(orc_contact_velocity)(m, k, cc, dv0, dqd, pv);
+        for (int a = 0; a < 3; a++) cc->A[a * 3 + b] = pv[0] * dirs[a][0] + pv[1] * dirs[a][1] + pv[2] * dirs[a][2];
+    }
+}
+
+/* Self-collision (b2g_sim_params::self_collision; the reference enables it for the rough-terrain tasks, tasks/anymal_terrain.py:282):
+ * the candidate spheres of every link that is not attached to the root directly (PhysX does not collide a link with its parent)
+ * against the BASE's bounding box -- the axis-aligned box, in the root frame, around the candidates of API body 0 and their radii.
+ * Signed distance = the largest of the three slab distances (exact over a face, a lower bound next to an edge), normal = that face's
+ * outward normal, contact point on the sphere's surface.  Returns 1 and fills link / point / normal / gap when inside the offset. */
+static void FN(orc_root_box)(const b2g_model* m, R* c, R* hx) {
+    R lo[3] = {(R)1e30, (R)1e30, (R)1e30}, hi[3] = {(R)-1e30, (R)-1e30, (R)-1e30};
+    int cnt = 0;
+    for (int i = 0; i < m->n_cpts; i++) {
+        if (m->cp_link[i] != 0 || m->cp_body[i] != 0) continue;      /* the base body itself, not the bodies fixed to it */
+        cnt++;
+        for (int a = 0; a < 3; a++) {
+            R p = (R)m->cp_pos[i][a], r = (R)m->cp_radius[i];
+            if (p - r < lo[a]) lo[a] = p - r;
+            if (p + r > hi[a]) hi[a] = p + r;
+        }
+    }
+    for (int a = 0; a < 3; a++) { c[a] = cnt ? (R)0.5 * (lo[a] + hi[a]) : 0; hx[a] = cnt ? (R)0.5 * (hi[a] - lo[a]) : (R)-1e30; }
+}
+static int FN(orc_self_candidate)(const b2g_model* m, const FN(orc_kin)* k, int i, R offset, const R* bc, const R* bh, FN(orc_contact)* cc) {
+    int l = m->cp_link[i];
+    R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], q[3];
+    FN(matvec3)(k->rot[l], lp, rc);
+    for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];
+    for (int a = 0; a < 3; a++) q[a] = k->rot[0][0 * 3 + a] * rc[0] + k->rot[0][1 * 3 + a] * rc[1] + k->rot[0][2 * 3 + a] * rc[2] - bc[a];   /* R0^T rc */
+    R rad = (R)m->cp_radius[i];
+    int best = 0;
+    R gap = (q[0] < 0 ? -q[0] : q[0]) - bh[0] - rad;
+    for (int a = 1; a < 3; a++) {
+        R d = (q[a] < 0 ? -q[a] : q[a]) - bh[a] - rad;
+        if (d > gap) { gap = d; best = a; }
+    }
+    if (gap >= offset) return 0;
+    R sgn = q[best] < 0 ? (R)-1 : (R)1;
+    cc->link = l; cc->body = m->cp_body[i]; cc->gap = gap; cc->self_c = 1;
+    for (int a = 0; a < 3; a++) { cc->n[a] = sgn * k->rot[0][a * 3 + best]; cc->r[a] = rc[a] - rad * cc->n[a]; }
+    return 1;
 }
 
 static void FN(orc_point_velocity)(const FN(orc_contact)* c, const R* v, R* out) {
@@ -430,39 +512,38 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
     int maxc = sp->max_contacts_per_chain > 0 ? sp->max_contacts_per_chain : B2G_DEFAULT_CONTACTS_PER_CHAIN;
     if (maxc > B2G_MAX_CONTACTS_PER_CHAIN) maxc = B2G_MAX_CONTACTS_PER_CHAIN;
     for (int c = 0; c < m->n_chains; c++) { ncon[c] = 0; npiece[c][0] = npiece[c][1] = 0; }
-    for (int i = 0; i < m->n_cpts && ground; i++) {
-        int c = m->cp_chain[i], l = m->cp_link[i];
-        if (m->fixed_base && l == 0) continue;
+    R box_c[3], box_h[3];
+    FN(orc_root_box)(m, box_c, box_h);
+    /* candidates come grouped by link (tip first within a chain, root candidates last): per link the ground tests, then -- links that do
+     * not hang off the root directly -- the self-collision tests against the root's box; both kinds share the chain's (piece's) slots */
+    for (int i0 = 0; i0 < m->n_cpts;) {
+        int c = m->cp_chain[i0], l = m->cp_link[i0], i1 = i0;
+        while (i1 < m->n_cpts && m->cp_link[i1] == l && m->cp_chain[i1] == c) i1++;
         const int piece = (by_piece && l > 0 && l - 1 - m->chain_start[c] >= 3) ? 1 : 0;
-        if (by_piece ? npiece[c][piece] >= maxc : ncon[c] >= maxc) continue;
-        R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
-        FN(matvec3)(k->rot[l], lp, rc);
-        for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];
-        FN(orc_ground)(hf, hfs, root13[0] + rc[0], root13[1] + rc[1], &gh, n);
-        R gap = (root13[2] + rc[2] - gh) * n[2] - (R)m->cp_radius[i];
-        if (gap >= (R)sp->contact_offset) continue;
-        FN(orc_contact)* cc = &con[c][ncon[c]++];
-        npiece[c][piece]++;
-        cc->link = l; cc->body = m->cp_body[i]; cc->gap = gap;
-        for (int a = 0; a < 3; a++) { cc->n[a] = n[a]; cc->r[a] = rc[a] - (R)m->cp_radius[i] * n[a]; cc->lam[a] = 0; }
-        /* tangent basis: t1 = normalise(x_world - (x.n) n), t2 = n x t1 */
-        R ex[3] = {1, 0, 0};
-        R dn = n[0];
-        R t1[3] = {ex[0] - dn * n[0], ex[1] - dn * n[1], ex[2] - dn * n[2]};
-        R inv = 1 / (R)sqrt((double)(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]));
-        for (int a = 0; a < 3; a++) cc->t1[a] = t1[a] * inv;
-        FN(cross3)(cc->n, cc->t1, cc->t2);
-        /* local Delassus block */
-        const R* dirs[3] = {cc->n, cc->t1, cc->t2};
-        for (int b = 0; b < 3; b++) {
-            R F[6], dv0[6] = {0, 0, 0, 0, 0, 0}, dqd[B2G_MAX_DOF], lv[6], pv[3];
-            for (int d = 0; d < nd; d++) dqd[d] = 0;
-            FN(orc_contact_wrench)(cc, dirs[b], F);
-            FN(orc_apply_impulse)(m, k, l, F, -1, 0, dv0, dqd);
-            FN(orc_link_velocity)(m, k, l, dv0, dqd, lv);
-            FN(orc_point_velocity)(cc, lv, pv);
-            for (int a = 0; a < 3; a++) cc->A[a * 3 + b] = pv[0] * dirs[a][0] + pv[1] * dirs[a][1] + pv[2] * dirs[a][2];
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 0 && (!ground || (m->fixed_base && l == 0))) continue;
+            if (pass == 1 && !(sp->self_collision && l > 0 && l - 1 - m->chain_start[c] >= 1)) continue;
+            for (int i = i0; i < i1; i++) {
+                if (by_piece ? npiece[c][piece] >= maxc : ncon[c] >= maxc) continue;
+                FN(orc_contact)* cc = &con[c][ncon[c]];
+                if (pass == 0) {
+                    R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
+                    FN(matvec3)(k->rot[l], lp, rc);
+                    for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];
+                    FN(orc_ground)(hf, hfs, root13[0] + rc[0], root13[1] + rc[1], &gh, n);
+                    R gap = (root13[2] + rc[2] - gh) * n[2] - (R)m->cp_radius[i];
+                    if (gap >= (R)sp->contact_offset) continue;
+                    cc->link = l; cc->body = m->cp_body[i]; cc->gap = gap; cc->self_c = 0;
+                    for (int a = 0; a < 3; a++) { cc->n[a] = n[a]; cc->r[a] = rc[a] - (R)m->cp_radius[i] * n[a]; }
+                } else if (!FN(orc_self_candidate)(m, k, i, (R)sp->contact_offset, box_c, box_h, cc)) {
+                    continue;
+                }
+                ncon[c]++;
+                npiece[c][piece]++;
+                FN(orc_finish_contact)(m, k, cc);
+            }
         }
+        i0 = i1;
     }
     /* ---- projected Gauss-Seidel: position iterations (with bias), integrate, velocity iterations ---- */
     int npos = sp->num_position_iterations, nvel = sp->num_velocity_iterations;
@@ -483,9 +564,8 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
                 for (int a = 0; a < 6; a++) Fall[c][a] = 0;
                 if (s >= ncon[c]) continue;
                 FN(orc_contact)* cc = &con[c][s];
-                R lv[6], pv[3];
-                FN(orc_link_velocity)(m, k, cc->link, v0, qd, lv);
-                FN(orc_point_velocity)(cc, lv, pv);
+                R pv[3];
+                FN(orc_contact_velocity)(m, k, cc, v0, qd, pv);
                 R vn = pv[0] * cc->n[0] + pv[1] * cc->n[1] + pv[2] * cc->n[2];
                 R vt1 = pv[0] * cc->t1[0] + pv[1] * cc->t1[1] + pv[2] * cc->t1[2];
                 R vt2 = pv[0] * cc->t2[0] + pv[1] * cc->t2[1] + pv[2] * cc->t2[2];
@@ -521,7 +601,7 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
             }
             for (int c = 0; c < m->n_chains; c++) {
                 if (s >= ncon[c]) continue;
-                FN(orc_apply_impulse)(m, k, con[c][s].link, Fall[c], -1, 0, v0, qd);
+                FN(orc_apply_contact_impulse)(m, k, &con[c][s], Fall[c], v0, qd);
             }
         }
     }
@@ -577,8 +657,11 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
     for (int c = 0; c < m->n_chains; c++)
         for (int s = 0; s < ncon[c]; s++) {
             FN(orc_contact)* cc = &con[c][s];
-            for (int a = 0; a < 3; a++)
-                contact[cc->body * 3 + a] += (cc->n[a] * cc->lam[0] + cc->t1[a] * cc->lam[1] + cc->t2[a] * cc->lam[2]) / h;
+            for (int a = 0; a < 3; a++) {
+                R f = (cc->n[a] * cc->lam[0] + cc->t1[a] * cc->lam[1] + cc->t2[a] * cc->lam[2]) / h;
+                contact[cc->body * 3 + a] += f;
+                if (cc->self_c) contact[0 * 3 + a] -= f;      /* the reaction on the root body (API body 0) */
+            }
         }
     free(k);
     return 0;
@@ -626,7 +709,7 @@ static int FN(orc_substep_ref)(const b2g_model* m, const b2g_sim_params* sp, con
     int nd = m->n_dof;
     const int hard = flags & 1;
     FN(orc_kin)* k = (FN(orc_kin)*)malloc(sizeof(FN(orc_kin)));
-    FN(orc_contact)* con = (FN(orc_contact)*)malloc(sizeof(FN(orc_contact)) * B2G_MAX_CPTS);
+    FN(orc_contact)* con = (FN(orc_contact)*)malloc(sizeof(FN(orc_contact)) * 2 * B2G_MAX_CPTS);
     if (!k || !con) { free(k); free(con); return -1; }
     R q[B2G_MAX_DOF], qd[B2G_MAX_DOF], tau[B2G_MAX_DOF], dext[B2G_MAX_DOF], qdd[B2G_MAX_DOF], a0[6];
     R grav[3] = {(R)sp->gravity[0], (R)sp->gravity[1], (R)sp->gravity[2]};
@@ -674,32 +757,28 @@ static int FN(orc_substep_ref)(const b2g_model* m, const b2g_sim_params* sp, con
     R mu_g = hf && hfs ? (R)hf->friction : (R)sp->plane_dynamic_friction;
     R mu = (R)0.5 * (mu_g + mu_shape);
     int ground = (hf && hfs) || sp->has_ground;
-    for (int i = 0; i < m->n_cpts && ground; i++) {
+    R box_c[3], box_h[3];
+    FN(orc_root_box)(m, box_c, box_h);
+    for (int i = 0; i < m->n_cpts; i++) {
         int l = m->cp_link[i];
-        if (m->fixed_base && l == 0) continue;
-        R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
-        FN(matvec3)(k->rot[l], lp, rc);
-        for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];
-        FN(orc_ground)(hf, hfs, root13[0] + rc[0], root13[1] + rc[1], &gh, n);
-        R gap = (root13[2] + rc[2] - gh) * n[2] - (R)m->cp_radius[i];
-        if (gap >= (R)sp->contact_offset) continue;
-        FN(orc_contact)* cc = &con[nc++];
-        cc->link = l; cc->body = m->cp_body[i]; cc->gap = gap;
-        for (int a = 0; a < 3; a++) { cc->n[a] = n[a]; cc->r[a] = rc[a] - (R)m->cp_radius[i] * n[a]; cc->lam[a] = 0; }
-        R dn = n[0];
-        R t1[3] = {1 - dn * n[0], -dn * n[1], -dn * n[2]};
-        R inv = 1 / (R)sqrt((double)(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]));
-        for (int a = 0; a < 3; a++) cc->t1[a] = t1[a] * inv;
-        FN(cross3)(cc->n, cc->t1, cc->t2);
-        const R* dirs[3] = {cc->n, cc->t1, cc->t2};
-        for (int b = 0; b < 3; b++) {
-            R F[6], dv0[6] = {0, 0, 0, 0, 0, 0}, dqd[B2G_MAX_DOF], lv[6], pv[3];
-            for (int d = 0; d < nd; d++) dqd[d] = 0;
-            FN(orc_contact_wrench)(cc, dirs[b], F);
-            FN(orc_apply_impulse)(m, k, l, F, -1, 0, dv0, dqd);
-            FN(orc_link_velocity)(m, k, l, dv0, dqd, lv);
-            FN(orc_point_velocity)(cc, lv, pv);
-            for (int a = 0; a < 3; a++) cc->A[a * 3 + b] = pv[0] * dirs[a][0] + pv[1] * dirs[a][1] + pv[2] * dirs[a][2];
+        for (int pass = 0; pass < 2; pass++) {
+            FN(orc_contact)* cc = &con[nc];
+            if (pass == 0) {
+                if (!ground || (m->fixed_base && l == 0)) continue;
+                R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
+                FN(matvec3)(k->rot[l], lp, rc);
+                for (int a = 0; a < 3; a++) rc[a] += k->pos[l][a];
+                FN(orc_ground)(hf, hfs, root13[0] + rc[0], root13[1] + rc[1], &gh, n);
+                R gap = (root13[2] + rc[2] - gh) * n[2] - (R)m->cp_radius[i];
+                if (gap >= (R)sp->contact_offset) continue;
+                cc->link = l; cc->body = m->cp_body[i]; cc->gap = gap; cc->self_c = 0;
+                for (int a = 0; a < 3; a++) { cc->n[a] = n[a]; cc->r[a] = rc[a] - (R)m->cp_radius[i] * n[a]; }
+            } else {
+                if (!(sp->self_collision && l > 0 && l - 1 - m->chain_start[m->cp_chain[i]] >= 1)) continue;
+                if (!FN(orc_self_candidate)(m, k, i, (R)sp->contact_offset, box_c, box_h, cc)) continue;
+            }
+            nc++;
+            FN(orc_finish_contact)(m, k, cc);
         }
     }
     /* ---- hard joint-limit rows: sign * qd >= -gap / h ---- */
@@ -732,9 +811,8 @@ static int FN(orc_substep_ref)(const b2g_model* m, const b2g_sim_params* sp, con
             for (int d = 0; d < nd; d++) vprev[6 + d] = qd[d];
             for (int s = 0; s < nc; s++) {
                 FN(orc_contact)* cc = &con[s];
-                R lv[6], pv[3], F[6];
-                FN(orc_link_velocity)(m, k, cc->link, v0, qd, lv);
-                FN(orc_point_velocity)(cc, lv, pv);
+                R pv[3], F[6];
+                FN(orc_contact_velocity)(m, k, cc, v0, qd, pv);
                 R vn = pv[0] * cc->n[0] + pv[1] * cc->n[1] + pv[2] * cc->n[2];
                 R vt1 = pv[0] * cc->t1[0] + pv[1] * cc->t1[1] + pv[2] * cc->t1[2];
                 R vt2 = pv[0] * cc->t2[0] + pv[1] * cc->t2[1] + pv[2] * cc->t2[2];
@@ -789,7 +867,7 @@ static int FN(orc_substep_ref)(const b2g_model* m, const b2g_sim_params* sp, con
                 R dir[3];
                 for (int a = 0; a < 3; a++) dir[a] = cc->n[a] * dl[0] + cc->t1[a] * dl[1] + cc->t2[a] * dl[2];
                 FN(orc_contact_wrench)(cc, dir, F);
-                FN(orc_apply_impulse)(m, k, cc->link, F, -1, 0, v0, qd);
+                FN(orc_apply_contact_impulse)(m, k, cc, F, v0, qd);
             }
             for (int r = 0; r < nlim; r++) {
                 int d = lim_d[r];
@@ -874,8 +952,11 @@ static int FN(orc_substep_ref)(const b2g_model* m, const b2g_sim_params* sp, con
     for (int b = 0; b < m->n_bodies * 3; b++) contact[b] = 0;
     for (int s = 0; s < nc; s++) {
         FN(orc_contact)* cc = &con[s];
-        for (int a = 0; a < 3; a++)
-            contact[cc->body * 3 + a] += (cc->n[a] * cc->lam[0] + cc->t1[a] * cc->lam[1] + cc->t2[a] * cc->lam[2]) / h;
+        for (int a = 0; a < 3; a++) {
+            R f = (cc->n[a] * cc->lam[0] + cc->t1[a] * cc->lam[1] + cc->t2[a] * cc->lam[2]) / h;
+            contact[cc->body * 3 + a] += f;
+            if (cc->self_c) contact[0 * 3 + a] -= f;
+        }
     }
     free(k); free(con);
     return 0;

@@ -329,6 +329,83 @@ def check_root_velocity_limits(make_backend, robot="anymal", n=8, seed=4):
         np.testing.assert_allclose(rb[~fast, :3], r64[~fast, :3], atol=1e-4)
 
 
+def root_box(art):
+    """The base body's bounding box (centre, half extents; root frame) around its own contact candidates and their radii."""
+    pts = np.array([p for l, b, p in zip(art.cp_link, art.cp_body, art.cp_pos) if l == 0 and b == 0], np.float64)
+    rad = np.array([r for l, b, r in zip(art.cp_link, art.cp_body, art.cp_radius) if l == 0 and b == 0], np.float64)
+    lo, hi = (pts - rad[:, None]).min(0), (pts + rad[:, None]).max(0)
+    return 0.5 * (lo + hi), 0.5 * (hi - lo)
+
+
+def self_penetration(art, root, dof):
+    """Deepest penetration (m, >= 0) of any candidate sphere of a link that does not hang off the root directly into the root's box."""
+    from isaacgymenv_b200.model.urdf import forward_kinematics as link_poses
+
+    bc, bh = root_box(art)
+    first = set(int(s) + 1 for s in art.chain_start)      # links attached to the root
+    worst = np.zeros(root.shape[0])
+    for e in range(root.shape[0]):
+        pos, rot = link_poses(art, dof[e, :, 0].astype(np.float64), np.zeros(3), np.array([0.0, 0.0, 0.0, 1.0]))      # in the root frame
+        for l, cp, r in zip(art.cp_link, art.cp_pos, art.cp_radius):
+            if l == 0 or int(l) in first:
+                continue
+            q = pos[l] + rot[l] @ cp - bc
+            gap = (np.abs(q) - bh - r).max()
+            worst[e] = max(worst[e], -gap)
+    return worst
+
+
+def check_self_collision(make_backend, robot="useful_hound", n=8, steps=30, seed=9):
+    """b2g_sim_params::self_collision: robots in free flight (no ground, no gravity) whose joints are driven towards targets that fold the legs /
+    the arm INTO the base.  (a) kernel == float64 oracle along the rollout; (b) with the flag the links stop at the base's box (a few
+    millimetres of solver slack), without it they pass through by centimetres; (c) the contact is an internal force pair: the force
+    reported on the root body is the opposite of the sum over the links."""
+    art = load_robot(robot)
+    rng = np.random.default_rng(seed)
+    nd = art.num_dofs
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, 60.0, 3.0)
+    m = _abi.pack_model(art)
+    q0 = default_pose(art)
+    lower, upper = np.array(art.lower, np.float64), np.array(art.upper, np.float64)
+    tgt = np.clip(q0 + rng.uniform(-1.6, 1.6, (n, nd)), np.where(np.isfinite(lower), lower, -3.0), np.where(np.isfinite(upper), upper, 3.0))
+    pen = {}
+    for flag in (1, 0):
+        sp = flat_params(dt=0.01, substeps=2, ground=False)
+        sp.gravity[2] = 0.0
+        sp.self_collision = flag
+        root = np.zeros((n, 13), np.float32)
+        root[:, 2], root[:, 6] = 3.0, 1.0
+        dof = np.zeros((n, nd, 2), np.float32)
+        dof[:, :, 0] = q0
+        be = make_backend(art, sp, props, n)
+        try:
+            be.set_state(root, dof)
+            r64, d64 = root.astype(np.float64), dof.astype(np.float64)
+            saw, worst_dev = False, 0.0
+            for k in range(steps):
+                f, c = be.simulate(tgt, np.zeros((n, nd)))
+                f64, c64 = O.simulate(m, sp, props, r64, d64, tgt.astype(np.float64), np.zeros((n, nd)))
+                rb, db = be.get_state()
+                worst_dev = max(worst_dev, float(np.abs(rb - r64).max()), float(np.abs(db[:, :, 0] - d64[:, :, 0]).max()))
+                c3, c643 = c.reshape(n, -1, 3), c64.reshape(n, -1, 3)
+                if flag:
+                    saw = saw or bool((np.abs(c643) > 1.0).any())
+                    np.testing.assert_allclose(c3.sum(1), 0.0, atol=2e-2 * max(1.0, np.abs(c3).max()))        # (c): action = -reaction
+                    assert np.abs(c3 - c643).max() < 5e-2 * max(1.0, np.abs(c643).max()) + 0.5
+                else:
+                    assert np.abs(c3).max() == 0.0
+                r64, d64 = rb.astype(np.float64), db.astype(np.float64)      # stay on the kernel's trajectory
+            assert worst_dev < 2e-3, f"self_collision={flag}: kernel deviates from the oracle by {worst_dev:.2e} within a step"
+            if flag:
+                assert saw, "the folded pose never produced a self contact"
+            pen[flag] = self_penetration(art, r64, d64)
+        finally:
+            be.close()
+    assert pen[0].max() > 0.02, f"without the flag the test pose does not fold into the base ({pen[0].max():.3f} m)"
+    assert pen[1].max() < 0.012, f"links penetrate the base by {pen[1].max():.3f} m with self-collision on"
+    return pen
+
+
 # ------------------------------------------------------------------------------------------------
 def anymal_cfg(art, seed=42, robot="anymal"):
     c = _abi.AnymalCfg()

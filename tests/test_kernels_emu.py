@@ -75,6 +75,11 @@ def test_jacobian_mass_matrix(robot):
     kc.check_jacobian_mass_matrix(make, robot)
 
 
+@pytest.mark.parametrize("robot", ["useful_hound", "anymal_minimal"])
+def test_self_collision_against_the_base(robot):
+    kc.check_self_collision(make, robot, n=4)
+
+
 def test_root_velocity_limits():
     kc.check_root_velocity_limits(make)
 
