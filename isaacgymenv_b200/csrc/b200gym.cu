@@ -1038,6 +1038,9 @@ int b2g_task_anymal_create(b2g_sim* s, const b2g_anymal_cfg* cfg) {
     if (!s || !cfg) return fail(B2G_ERR_ARG, "null argument");
     if (!s->prepared) return fail(B2G_ERR_STATE, "task created before prepare_sim");
     if (s->model.fixed_base) return fail(B2G_ERR_UNSUPPORTED, "the flat locomotion task needs a floating base");
+    if (s->params.self_collision && s->v.lanes == 4)
+        return fail(B2G_ERR_UNSUPPORTED, "the fused flat-terrain step of the quadrupeds is built without self-collision (the reference's flat tasks create their actors "
+                                         "with collision filter 1 = off); clear b2g_sim_params.self_collision or use the generic path");
     if (cfg->base_body < 0 || cfg->base_body >= s->model.n_bodies || cfg->n_knee < 0 || cfg->n_knee > 8)
         return fail(B2G_ERR_ARG, "bad base/knee body indices");
     for (int k = 0; k < cfg->n_knee; k++)

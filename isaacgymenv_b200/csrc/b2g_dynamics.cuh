@@ -338,7 +338,8 @@ B2G_HD B2G_INL void block_align(const DevParams& P, int bit) {
 // FULL = true promises len == NL on every lane.  PROBE = true turns the call into the forward-dynamics probe of the parity tests: efforts st.act are
 // applied raw (no drives), the function returns after the ABA with joint accelerations in st.frc and the
 // root's spatial acceleration (angular, linear) in st.rw / st.rv.
-template <int LANES, int NL, bool FIXED, bool HF, bool PROBE = false, bool FULL = false>
+// SC = false compiles the self-collision code out (the fused flat-terrain step of the quadrupeds, whose tasks never enable it).
+template <int LANES, int NL, bool FIXED, bool HF, bool PROBE = false, bool FULL = false, bool SC = true>
 B2G_HD B2G_INL void substep(const DevModel* __restrict__ M, const DevParams& P, int lane, int len_in, int d0,
                             LaneState<NL>& st, const EnvDr dr, bool last, ScratchStrided sc, float* bf) {
     // FULL: every lane's chain has exactly NL links (the quadrupeds) -> the `j < len` predicates fold away
@@ -681,7 +682,17 @@ B2G_LINK_UNROLL
 #endif
         return !skip;
     };
-    const bool self_col = P.self_collide != 0;
+    const bool self_col = SC && P.self_collide != 0;
+    // a link whose candidate bounding sphere stays clear of the base box's bounding sphere by two contact offsets cannot produce a self
+    // contact (the slab distance used above is at least 1 / sqrt(3) of the Euclidean one): skips the per-candidate loop, never a result
+    auto may_self = [&](const M3& R, V3 p, const float* c, const float* hx) -> bool {
+        if (M->self_box_h[0] < 0.0f) return false;      // the base has no candidates of its own: no box
+        const V3 d = p + mul(R, V3{c[0], c[1], c[2]}) - mul(R0, V3{M->self_box_c[0], M->self_box_c[1], M->self_box_c[2]});
+        const float rl = sqrtf(hx[0] * hx[0] + hx[1] * hx[1] + hx[2] * hx[2]);
+        const float rb = sqrtf(M->self_box_h[0] * M->self_box_h[0] + M->self_box_h[1] * M->self_box_h[1] + M->self_box_h[2] * M->self_box_h[2]);
+        const float reach = rl + rb + 2.0f * P.contact_offset;
+        return dot(d, d) <= reach * reach;
+    };
     if (ground || self_col) {
 B2G_LINK_UNROLL
         for (int j = NL - 1; j >= 0; j--) {
@@ -690,7 +701,7 @@ B2G_LINK_UNROLL
                 const int c0 = D.cp_start, cn = D.cp_count;
                 if (ground && cn > 0 && may_touch(L[j].Rl, L[j].pl, D.cp_c, D.cp_h))
                     for (int i = c0; i < c0 + cn; i++) test_candidate(i, L[j].Rl, L[j].pl, j);
-                if (self_col && (j >= 1 || distal))      // not the link that hangs off the root directly (PhysX: no parent-child collision)
+                if (self_col && (j >= 1 || distal) && cn > 0 && may_self(L[j].Rl, L[j].pl, D.cp_c, D.cp_h))      // not the link that hangs off the root directly (PhysX: no parent-child collision)
                     for (int i = c0; i < c0 + cn; i++) test_self(i, L[j].Rl, L[j].pl, j);
             }
         }
@@ -720,7 +731,7 @@ B2G_LINK_UNROLL
             const V3 dirs[3] = {V3{sc.at(s, CF_NX), sc.at(s, CF_NY), sc.at(s, CF_NZ)}, V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)},
                                 V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)}};
             const int jcf = (int)sc.at(s, CF_JC);
-            const bool selfc = jcf >= kSelfJc / 2;
+            const bool selfc = SC && jcf >= kSelfJc / 2;
             const int jc = selfc ? jcf - kSelfJc : jcf;
             float A[9];
 #pragma unroll
@@ -782,7 +793,7 @@ B2G_LINK_UNROLL
                 const V3 t1 = V3{sc.at(s, CF_T1X), sc.at(s, CF_T1Y), sc.at(s, CF_T1Z)};
                 const V3 t2 = V3{sc.at(s, CF_T2X), sc.at(s, CF_T2Y), sc.at(s, CF_T2Z)};
                 const int jcf = (int)sc.at(s, CF_JC);
-                const bool selfc = jcf >= kSelfJc / 2;
+                const bool selfc = SC && jcf >= kSelfJc / 2;
                 const int jc = selfc ? jcf - kSelfJc : jcf;
                 SV lv = distal ? vbase : v0n;
                 if (selfc) lv = distal ? vbase - v0n : sv0();      // relative to the root
@@ -938,7 +949,7 @@ B2G_LINK_UNROLL
                     const float fy = sc.at(s, CF_NY) * ln + sc.at(s, CF_T1Y) * l1 + sc.at(s, CF_T2Y) * l2;
                     const float fz = sc.at(s, CF_NZ) * ln + sc.at(s, CF_T1Z) * l1 + sc.at(s, CF_T2Z) * l2;
                     bf[b * 3 + 0] += fx; bf[b * 3 + 1] += fy; bf[b * 3 + 2] += fz;
-                    if ((int)sc.at(s, CF_JC) >= kSelfJc / 2) { bf[0] -= fx; bf[1] -= fy; bf[2] -= fz; }      // self contact: the reaction on the root body (API body 0)
+                    if (SC && (int)sc.at(s, CF_JC) >= kSelfJc / 2) { bf[0] -= fx; bf[1] -= fy; bf[2] -= fz; }      // self contact: the reaction on the root body (API body 0)
                 }
             }
             Grp<LANES>::sync();

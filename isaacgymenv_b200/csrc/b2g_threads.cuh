@@ -258,7 +258,7 @@ B2G_HD B2G_INL void anymal_step_thread(const SimArgs& A, const TaskArgs& T, int 
         const EnvDr mu_shape = env_dr(A, valid ? env : 0, valid);
 #pragma unroll 1
         for (int s = 0; s < A.P.substeps; s++)
-            substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);
+            substep<LANES, NL, false, HF, false, (LANES == 4 && NL == 3), !(LANES == 4 && NL == 3)>(M, A.P, lane, len, d0, st, mu_shape, s == A.P.substeps - 1, sc, bf);      // quadruped variant: no self-collision code (b2g_task_anymal_create refuses the flag)
     } else {
         // torques and contact forces come from the sim tensors instead of a physics step
 #pragma unroll
