@@ -600,6 +600,21 @@ B2G_LINK_UNROLL
     if (!PROBE) block_align(P, 2);
     int ncon = 0, ndrop = 0;
     const bool ground = HF || (P.has_ground != 0);
+    // A candidate inside the contact offset takes a free slot; when the lane's slots are full it is counted as dropped -- but the DEEPEST
+    // candidates are the ones kept: it replaces the slot with the largest gap if it penetrates further than that one (PhysX's contact
+    // reduction keeps the deepest points too).  A candidate left without a slot while it sinks would otherwise be picked up centimetres
+    // deep and pushed out at max_depenetration_velocity.
+    auto claim_slot = [&](float gap) -> int {
+        if (ncon < P.max_contacts) return ncon++;
+        ndrop++;
+        int w = 0;
+        float gw = sc.at(0, CF_GAP);
+        for (int q = 1; q < P.max_contacts; q++) {
+            const float g = sc.at(q, CF_GAP);
+            if (g > gw) { gw = g; w = q; }
+        }
+        return gap < gw ? w : -1;
+    };
     auto test_candidate = [&](int i, const M3& R, V3 p, int jc) {
         const float cx = M->cp[i][0], cy = M->cp[i][1], cz = M->cp[i][2], cr = M->cp[i][3];
         const V3 rc = p + mul(R, V3{cx, cy, cz});
@@ -607,13 +622,12 @@ B2G_LINK_UNROLL
         V3 n = V3{0, 0, 1};
         if (HF) ground_sample(P, st.rp.x + rc.x, st.rp.y + rc.y, gh, n);
         const float gap = (st.rp.z + rc.z - gh) * n.z - cr;
-        if (gap < P.contact_offset && ncon >= P.max_contacts) ndrop++;      // no free slot: the candidate is ignored this sub-step (counted, never silent)
-        if (gap < P.contact_offset && ncon < P.max_contacts) {
+        const int s = gap < P.contact_offset ? claim_slot(gap) : -1;      // -1 with the slots full: this candidate (or the one it replaces) is dropped, counted, never silent
+        if (s >= 0) {
             const V3 r = rc - n * cr;
             V3 t1 = V3{1.0f - n.x * n.x, -n.x * n.y, -n.x * n.z};
             t1 = t1 * (1.0f / sqrtf(dot(t1, t1)));
             const V3 t2 = cross(n, t1);
-            const int s = ncon++;
             sc.at(s, CF_RX) = r.x; sc.at(s, CF_RY) = r.y; sc.at(s, CF_RZ) = r.z;
             sc.at(s, CF_NX) = n.x; sc.at(s, CF_NY) = n.y; sc.at(s, CF_NZ) = n.z;
             sc.at(s, CF_T1X) = t1.x; sc.at(s, CF_T1Y) = t1.y; sc.at(s, CF_T1Z) = t1.z;
@@ -637,15 +651,14 @@ B2G_LINK_UNROLL
         float gap = dx;
         if (dy > gap) { gap = dy; best = 1; }
         if (dz > gap) { gap = dz; best = 2; }
-        if (gap < P.contact_offset && ncon >= P.max_contacts) ndrop++;
-        if (gap < P.contact_offset && ncon < P.max_contacts) {
+        const int s = gap < P.contact_offset ? claim_slot(gap) : -1;
+        if (s >= 0) {
             const float sgn = (best == 0 ? q.x : best == 1 ? q.y : q.z) < 0.0f ? -1.0f : 1.0f;
             const V3 n = V3{R0.m[best], R0.m[3 + best], R0.m[6 + best]} * sgn;
             const V3 r = rc - n * cr;
             V3 t1 = V3{1.0f - n.x * n.x, -n.x * n.y, -n.x * n.z};
             t1 = t1 * (1.0f / sqrtf(dot(t1, t1)));
             const V3 t2 = cross(n, t1);
-            const int s = ncon++;
             sc.at(s, CF_RX) = r.x; sc.at(s, CF_RY) = r.y; sc.at(s, CF_RZ) = r.z;
             sc.at(s, CF_NX) = n.x; sc.at(s, CF_NY) = n.y; sc.at(s, CF_NZ) = n.z;
             sc.at(s, CF_T1X) = t1.x; sc.at(s, CF_T1Y) = t1.y; sc.at(s, CF_T1Z) = t1.z;

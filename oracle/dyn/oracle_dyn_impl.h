@@ -501,7 +501,7 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
      * slots of its own (root candidates count with the proximal piece); the order of a chain's contacts -- distal piece
      * first -- is the same. ---- */
     FN(orc_contact) con[B2G_MAX_CHAINS][2 * B2G_MAX_CONTACTS_PER_CHAIN];
-    int ncon[B2G_MAX_CHAINS], npiece[B2G_MAX_CHAINS][2];
+    int ncon[B2G_MAX_CHAINS], npiece[B2G_MAX_CHAINS][2], cpiece[B2G_MAX_CHAINS][2 * B2G_MAX_CONTACTS_PER_CHAIN];
     int pieces = m->n_chains;
     for (int c = 0; c < m->n_chains; c++) pieces += m->chain_len[c] > 3 ? 1 : 0;
     const char* seg_env = getenv("B2G_SEGMENTS");
@@ -524,8 +524,11 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
             if (pass == 0 && (!ground || (m->fixed_base && l == 0))) continue;
             if (pass == 1 && !(sp->self_collision && l > 0 && l - 1 - m->chain_start[c] >= 1)) continue;
             for (int i = i0; i < i1; i++) {
-                if (by_piece ? npiece[c][piece] >= maxc : ncon[c] >= maxc) continue;
-                FN(orc_contact)* cc = &con[c][ncon[c]];
+                /* slots full: the candidate goes into a scratch record first and replaces the chain's (piece's) shallowest contact only
+                 * if it penetrates further -- the deepest candidates are the ones kept */
+                const int full = by_piece ? npiece[c][piece] >= maxc : ncon[c] >= maxc;
+                FN(orc_contact) spare;
+                FN(orc_contact)* cc = full ? &spare : &con[c][ncon[c]];
                 if (pass == 0) {
                     R lp[3] = {m->cp_pos[i][0], m->cp_pos[i][1], m->cp_pos[i][2]}, rc[3], gh, n[3];
                     FN(matvec3)(k->rot[l], lp, rc);
@@ -538,8 +541,20 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
                 } else if (!FN(orc_self_candidate)(m, k, i, (R)sp->contact_offset, box_c, box_h, cc)) {
                     continue;
                 }
-                ncon[c]++;
-                npiece[c][piece]++;
+                if (full) {
+                    int w = -1;
+                    for (int q = 0; q < ncon[c]; q++) {
+                        if (by_piece && cpiece[c][q] != piece) continue;
+                        if (w < 0 || con[c][q].gap > con[c][w].gap) w = q;
+                    }
+                    if (w < 0 || !(cc->gap < con[c][w].gap)) continue;
+                    con[c][w] = *cc;
+                    cc = &con[c][w];
+                } else {
+                    cpiece[c][ncon[c]] = piece;
+                    ncon[c]++;
+                    npiece[c][piece]++;
+                }
                 FN(orc_finish_contact)(m, k, cc);
             }
         }

@@ -569,8 +569,9 @@ def test_useful_hound_plausibility_under_random_leg_actions(refresh):
     """Config 4 as a simulation: 1024 robots, random leg actions, ZERO arm actions, 300 policy steps.  The reference's arm law is passive
     in this setting (its Jacobian slice is the base's six columns, square and invertible, so the null-space projector vanishes and with
     a never-refreshed end-effector row the task term is zero): a hound carrying a limp arm.  Gate: every state finite, the typical
-    robot stays at standing height, and the tail -- arm links pinned between the 49 kg body and the ground (no self-collision here) and
-    pushed out at up to max_depenetration_velocity = 100 m/s, the yaml's value -- stays a tail (DESIGN.md section 6 has the numbers).
+    robot stays at standing height, and the tail -- an arm lying on the ground offers more candidates than a lane has slots; the ones
+    left out sink and are later pushed out at up to max_depenetration_velocity = 100 m/s, the yaml's value; keeping the DEEPEST
+    candidates cut it from 9 % of the robots above 1 m to 1.7 % -- stays a tail (DESIGN.md section 6 has the numbers).
     refreshEefState=True (NOT the reference: the live end-effector velocity is fed back through that same base-column Jacobian) is
     unstable by construction; there only finiteness is asserted (root velocity limits of the asset options keep it bounded)."""
     import torch
@@ -591,5 +592,5 @@ def test_useful_hound_plausibility_under_random_leg_actions(refresh):
         assert float(env.root_states[:, 7:10].norm(dim=-1).max()) <= 1000.0 * (1 + 1e-4) and float(env.root_states[:, 10:13].norm(dim=-1).max()) <= 64.0 * (1 + 1e-4)
     if not refresh:
         assert float(zmax.median()) < 0.8, float(zmax.median())
-        assert float(zmax.quantile(0.99)) < 2.5, float(zmax.quantile(0.99))
-        assert float((zmax > 2.0).float().mean()) < 0.02
+        assert float(zmax.quantile(0.99)) < 1.6, float(zmax.quantile(0.99))
+        assert float((zmax > 2.0).float().mean()) < 0.01
