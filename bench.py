@@ -404,7 +404,7 @@ def run_ours(args):
     # the other BASELINE configs ride in the same line (shorter runs, one GPU only: they are parity-test configs, not the headline)
     others = {}
     if args.other_configs and world == 1 and args.task == "Anymal" and args.num_envs <= 0:
-        for t in ("AnymalTerrain", "UsefulHound", "Cartpole"):
+        for t in ("AnymalTerrain", "UsefulHound", "Cartpole", "Manipulator"):
             try:
                 k = min(args.steps, 200)
                 r = measure_task(t, 0, k, min(args.warmup, 20), args.preroll, dev, rank, world, dist, sample_clocks=False)
