@@ -293,6 +293,12 @@ constexpr int kSelfJc = 64;                           // CF_JC of a self-collisi
 constexpr int kAncLinkFloats = 16;                    // S (6) | U (6) | 1/D | 3 pad: 16-byte rows
 constexpr int kAncFloats = 3 * kAncLinkFloats;        // a piece with a child is always full
 
+#if defined(B2G_HOST_EMU)
+#define B2G_NOINLINE
+#else
+#define B2G_NOINLINE __noinline__
+#endif
+
 // per-thread contact scratch: field f of slot s
 struct ScratchStrided {
     float* base;   // points at this thread's column
@@ -301,6 +307,18 @@ struct ScratchStrided {
     float* anc = nullptr;     // this environment's ancestor store (segment variant only): kAncFloats per piece that has a child
     B2G_HD B2G_INL float& at(int slot, int f) { return base[(slot * CF_COUNT + f) * stride]; }
 };
+
+// slot with the largest gap (the shallowest contact) among the first `nslots`; out of line: only reached when a lane's slots are full
+B2G_HD B2G_NOINLINE int shallowest_slot(const float* base, int stride, int nslots, float* gap_out) {
+    int w = 0;
+    float gw = base[(0 * CF_COUNT + CF_GAP) * stride];
+    for (int q = 1; q < nslots; q++) {
+        const float g = base[(q * CF_COUNT + CF_GAP) * stride];
+        if (g > gw) { gw = g; w = q; }
+    }
+    *gap_out = gw;
+    return w;
+}
 
 B2G_HD B2G_INL void ground_sample(const DevParams& P, float x, float y, float& hgt, V3& n) {
     float gx = (x - P.hf_ox) / P.hf_hs, gy = (y - P.hf_oy) / P.hf_hs;
@@ -607,12 +625,8 @@ B2G_LINK_UNROLL
     auto claim_slot = [&](float gap) -> int {
         if (ncon < P.max_contacts) return ncon++;
         ndrop++;
-        int w = 0;
-        float gw = sc.at(0, CF_GAP);
-        for (int q = 1; q < P.max_contacts; q++) {
-            const float g = sc.at(q, CF_GAP);
-            if (g > gw) { gw = g; w = q; }
-        }
+        float gw;
+        const int w = shallowest_slot(sc.base, sc.stride, P.max_contacts, &gw);
         return gap < gw ? w : -1;
     };
     auto test_candidate = [&](int i, const M3& R, V3 p, int jc) {
