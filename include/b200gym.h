@@ -537,7 +537,7 @@ typedef struct b2g_gae_args {
     float* f_ret;                 /* (T N) */
     float* f_val;
     float* f_adv;
-    double* partial;
+    double* partial;              /* 2 x b2g_stat_workspace_doubles(horizon * n_envs, 1) doubles */
 } b2g_gae_args;
 int b2g_gae_finish(const b2g_gae_args* args, void* stream);
 

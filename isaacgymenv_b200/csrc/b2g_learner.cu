@@ -236,12 +236,20 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ s
 
 // ---- rollout bookkeeping of the learner: what rl_games' play_steps does between two env steps, as a handful of launches --------------
 // running mean / variance (rl_games RunningMeanStd, float64 state): per-column batch sums in double, then the parallel-variance merge
-constexpr int kStatRows = 512;
-__global__ void __launch_bounds__(256) k_stat_partial(const float* __restrict__ x, int rows, int cols, double* __restrict__ partial) {
+// rows per block: at most ~256 blocks, at least 64 rows each (8192 observation rows -> 128 blocks; a fixed 512 left 16 blocks on 148 SMs)
+static inline int stat_rows_per_block(int rows) {
+    const int r = (rows + 255) / 256;
+    return r < 64 ? 64 : r;
+}
+static inline int stat_blocks(int rows) {
+    const int rpb = stat_rows_per_block(rows);
+    return (rows + rpb - 1) / rpb;
+}
+__global__ void __launch_bounds__(256) k_stat_partial(const float* __restrict__ x, int rows, int cols, double* __restrict__ partial, int rows_per_block) {
     extern __shared__ double redd[];      // (lanes, cols, 2)
     const int lanes = cols <= 256 ? 256 / cols : 1;
     const int c = threadIdx.x % cols, lane = threadIdx.x / cols;
-    const int r0 = blockIdx.x * kStatRows, r1 = min(r0 + kStatRows, rows);
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, rows);
     for (int cc = c; cc < cols; cc += 256) {      // cols > 256: every thread walks several columns
         double s = 0.0, q = 0.0;
         if (lane < lanes)
@@ -555,15 +563,15 @@ int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz, float* dbia
     return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_mlp_elu_backward: launch failed");
 }
 
-int b2g_stat_workspace_doubles(int rows, int cols) { return ((rows + kStatRows - 1) / kStatRows) * cols * 2; }
+int b2g_stat_workspace_doubles(int rows, int cols) { return stat_blocks(rows) * cols * 2; }
 
 int b2g_running_stat_update(const float* x, int rows, int cols, double* mean, double* var, double* count, double* partial, float* mean_f32,
                             float* inv_std_f32, float eps, void* stream) {
     if (!x || !mean || !var || !count || !partial || rows < 1 || cols < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_running_stat_update: bad argument");
-    const int blocks = (rows + kStatRows - 1) / kStatRows;
+    const int blocks = stat_blocks(rows);
     const int lanes = cols <= 256 ? 256 / cols : 1;
     cudaStream_t st = (cudaStream_t)stream;
-    k_stat_partial<<<blocks, 256, cols <= 256 ? sizeof(double) * 2 * lanes * cols : 0, st>>>(x, rows, cols, partial);
+    k_stat_partial<<<blocks, 256, cols <= 256 ? sizeof(double) * 2 * lanes * cols : 0, st>>>(x, rows, cols, partial, stat_rows_per_block(rows));
     k_stat_merge<<<(cols + 127) / 128, 128, 0, st>>>(partial, blocks, rows, cols, mean, var, count, 1, mean_f32, inv_std_f32, eps);
     k_count_add<<<1, 1, 0, st>>>(count, (double)rows);
     return cudaGetLastError() == cudaSuccess ? B2G_OK : b2g::fail_msg(B2G_ERR_CUDA, "b2g_running_stat_update: launch failed");
@@ -608,11 +616,11 @@ int b2g_gae_finish(const b2g_gae_args* a, void* stream) {
     const int n = T * N;
     k_gae<<<(N + 255) / 256, 256, 0, st>>>(a->rewards, a->values, a->dones, a->v_last, T, N, a->gamma, a->tau, a->adv, a->ret);
     // running statistics of the returns (value normaliser), then the advantages' own moments
-    const int blocks = (n + kStatRows - 1) / kStatRows;
-    k_stat_partial<<<blocks, 256, sizeof(double) * 2 * 256, st>>>(a->ret, n, 1, a->partial);
+    const int blocks = stat_blocks(n), rpb = stat_rows_per_block(n);
+    k_stat_partial<<<blocks, 256, sizeof(double) * 2 * 256, st>>>(a->ret, n, 1, a->partial, rpb);
     k_stat_merge<<<1, 128, 0, st>>>(a->partial, blocks, n, 1, a->value_mean, a->value_var, a->value_count, 1, nullptr, nullptr, 0.0f);
     k_count_add<<<1, 1, 0, st>>>(a->value_count, (double)n);
-    k_stat_partial<<<blocks, 256, sizeof(double) * 2 * 256, st>>>(a->adv, n, 1, a->partial + 2 * blocks);
+    k_stat_partial<<<blocks, 256, sizeof(double) * 2 * 256, st>>>(a->adv, n, 1, a->partial + 2 * blocks, rpb);
     const int fb = (n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8;
     k_finish_batch<<<fb, 256, 0, st>>>(a->ret, a->values, a->adv, a->value_mean, a->value_var, a->partial + 2 * blocks, blocks, (size_t)n, a->value_eps,
                                        a->f_ret, a->f_val, a->f_adv);

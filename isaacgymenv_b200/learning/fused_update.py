@@ -189,7 +189,7 @@ class RolloutKernels:
         self.mean_f = torch.zeros(F, device=dev)
         self.inv_std_f = torch.ones(F, device=dev)
         self.obs_ws = torch.zeros(int(lib.b2g_stat_workspace_doubles(N, F)), device=dev, dtype=torch.float64)
-        self.gae_ws = torch.zeros(4 * ((T * N + 511) // 512), device=dev, dtype=torch.float64)
+        self.gae_ws = torch.zeros(2 * int(lib.b2g_stat_workspace_doubles(T * N, 1)), device=dev, dtype=torch.float64)      # returns' and advantages' partial moments
         self.env_actions = torch.zeros(N, A, device=dev)
         self.mu = torch.zeros(N, A, device=dev)
         self.mu_scratch = torch.zeros(N, A, device=dev)          # action head of the critic instance of a separate network (unused)
