@@ -113,22 +113,17 @@ __global__ void __launch_bounds__(kHeadBlock) k_ppo_head(b2g_ppo_head_args a) {
 
 // one block: out[0] = loss, out[1..4] = a_loss, c_loss, b_loss, kl, out[5] = entropy; grad_log_std[k]
 __global__ void __launch_bounds__(kHeadBlock) k_ppo_head_finalize(b2g_ppo_head_args a, int n_blocks) {
-    __shared__ float red[kHeadBlock / 32];
     __shared__ float tot[kHeadCols];
     const int A = a.n_actions;
-    for (int k = 0; k < 4 + A; k++) {
+    // one warp per column (columns warp, warp + n_warps, ...): lane l adds blocks l, l + 32, ... and the lanes are reduced by the fixed
+    // shuffle tree -- deterministic, one barrier instead of two per column
+    for (int k = threadIdx.x >> 5; k < 4 + A; k += kHeadBlock / 32) {
         float s = 0.0f;
-        for (int b = threadIdx.x; b < n_blocks; b += kHeadBlock) s += a.partial[(size_t)b * kHeadCols + k];
+        for (int b = threadIdx.x & 31; b < n_blocks; b += 32) s += a.partial[(size_t)b * kHeadCols + k];
         s = warp_sum(s);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = 0.0f;
-            for (int q = 0; q < kHeadBlock / 32; q++) t += red[q];
-            tot[k] = t;
-        }
-        __syncthreads();
+        if ((threadIdx.x & 31) == 0) tot[k] = s;
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         float ent = 0.0f;
         for (int k = 0; k < A; k++) ent += a.log_std[k] + 0.5f + 0.9189385332046727f;
@@ -439,14 +434,15 @@ __global__ void __launch_bounds__(256) k_heads_backward(const float* __restrict_
                                                         float* __restrict__ dh, float* __restrict__ partial) {
     extern __shared__ float sm[];
     const int O = A + 1;
-    float* s_h = sm;                            // (kHeadRows, H)
-    float* s_dy = s_h + kHeadRows * H;          // (kHeadRows, O)
+    const int H1 = H + 1;
+    float* s_h = sm;                            // (kHeadRows, H + 1): [h | 1] -- the ones column makes the bias gradient one more column of dWcat
+    float* s_dy = s_h + kHeadRows * H1;         // (kHeadRows, O)
     float* s_w = s_dy + kHeadRows * O;          // (O, H)
     const int r0 = blockIdx.x * kHeadRows;
     const int nr = min(kHeadRows, rows - r0);
-    for (int i = threadIdx.x; i < kHeadRows * H; i += blockDim.x) {
-        const int r = i / H;
-        s_h[i] = r < nr ? h[(size_t)(r0 + r) * H + (i - r * H)] : 0.0f;
+    for (int i = threadIdx.x; i < kHeadRows * H1; i += blockDim.x) {
+        const int r = i / H1, c = i - r * H1;
+        s_h[i] = c == H ? 1.0f : (r < nr ? h[(size_t)(r0 + r) * H + c] : 0.0f);
     }
     for (int i = threadIdx.x; i < kHeadRows * O; i += blockDim.x) {
         const int r = i / O, o = i - r * O;
@@ -459,11 +455,8 @@ __global__ void __launch_bounds__(256) k_heads_backward(const float* __restrict_
     for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
         const int o = e / (H + 1), c = e - o * (H + 1);
         float acc = 0.0f;
-        if (c < H) {
-            for (int r = 0; r < kHeadRows; r++) acc += s_dy[r * O + o] * s_h[r * H + c];
-        } else {
-            for (int r = 0; r < kHeadRows; r++) acc += s_dy[r * O + o];
-        }
+#pragma unroll 8
+        for (int r = 0; r < kHeadRows; r++) acc += s_dy[r * O + o] * s_h[r * H1 + c];
         partial[(size_t)blockIdx.x * n_out + e] = acc;
     }
     // dh rows: thread t -> row t / 4, a quarter of the columns
@@ -636,7 +629,7 @@ static int heads_backward_launch(const float* h, const float* dmu, const float* 
     if (!h || !dmu || !dv || !w_mu || !w_v || !dh || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_heads_backward: null argument");
     if (hidden < 1 || hidden > 256 || n_actions < 1 || n_actions > kMaxAct) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_heads_backward: hidden <= 256, actions <= 24");
     const int O = n_actions + 1;
-    const size_t smem = sizeof(float) * ((size_t)kHeadRows * (hidden + O) + (size_t)O * hidden);
+    const size_t smem = sizeof(float) * ((size_t)kHeadRows * (hidden + 1 + O) + (size_t)O * hidden);
     static bool opted = false;
     if (!opted) { cudaFuncSetAttribute(k_heads_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); opted = true; }
     if (smem > 96 * 1024) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_heads_backward: tile does not fit shared memory");
