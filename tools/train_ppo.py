@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--fused-rollout", action="store_true", help="evaluate the policy in the rollout with the fused tcgen05 kernel")
     ap.add_argument("--fused-update", action="store_true", help="loss head / bias+ELU / clip+Adam / rollout bookkeeping through the library's kernels")
     ap.add_argument("--yaml", action="store_true", help="hyper-parameters and network from cfg/train/<Task>PPO.yaml (separate towers, mixed precision, ...)")
+    ap.add_argument("--self-collision", type=int, default=-1, help="override sim.physx.self_collision (1 / 0); default: what the task's create_actor asks for")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -36,8 +37,9 @@ def main():
     if multi:      # one process per GPU (torchrun); envs sharded by rank, gradients all-reduced over NCCL
         torch.cuda.set_device(info.local_rank)
         dist.init_process_group("nccl", device_id=torch.device(info.device))
+    overrides = {"sim": {"physx": {"self_collision": bool(args.self_collision)}}} if args.self_collision >= 0 else None
     env = isaacgymenv_b200.make(seed=args.seed, task=args.task, num_envs=args.num_envs, sim_device=info.device, rl_device=info.device, headless=True,
-                                multi_gpu=multi)
+                                multi_gpu=multi, overrides=overrides)
     cfg = PPOConfig()
     if args.task != "Anymal" and args.task != "Hound":
         cfg = PPOConfig(units=(512, 256, 128), minibatch_size=16384, entropy_coef=0.001)
@@ -61,7 +63,7 @@ def main():
 
             shutdown(ppo)
         return
-    out = {"task": args.task, "fused_rollout": bool(args.fused_rollout), "cuda_graphs": bool(args.cuda_graphs), "fused_update": bool(args.fused_update), "yaml": bool(args.yaml),
+    out = {"task": args.task, "self_collision_override": args.self_collision, "fused_rollout": bool(args.fused_rollout), "cuda_graphs": bool(args.cuda_graphs), "fused_update": bool(args.fused_update), "yaml": bool(args.yaml),
            "separate": bool(cfg.separate), "mixed_precision": bool(cfg.mixed_precision), "num_envs_per_gpu": args.num_envs, "n_gpus": info.world_size, "env_steps_all_gpus": [s * info.world_size for s in log.env_steps], "epochs": log.epochs, "env_steps": log.env_steps, "mean_episode_reward": log.mean_episode_reward,
            "mean_episode_length": log.mean_episode_length, "wall_s": log.wall_s, "gpu": torch.cuda.get_device_name(0),
            "env_steps_per_sec_incl_learner": (log.env_steps[-1] * info.world_size / log.wall_s[-1]) if log.wall_s else None}
