@@ -424,11 +424,23 @@ B2G_LINK_UNROLL
                 if (PROBE) {
                     t = st.act[j];
                 } else if (D.drive_mode == B2G_DOF_MODE_POS) {
-                    t = kp * (st.tgt[j] - st.q[j]) - (kd + h * kp) * st.qd[j];
-                    de += h * kd + h * h * kp;
+                    // implicit PD drive; saturated at the effort limit (PhysX clamps the drive force to maxForce): when the torque estimated at
+                    // the end-of-step position exceeds it, the drive is a constant torque of that size and contributes no implicit terms
+                    const float te = kp * (st.tgt[j] - st.q[j] - h * st.qd[j]) - kd * st.qd[j];
+                    if (D.effort > 0.0f && fabsf(te) > D.effort) {
+                        t = copysignf(D.effort, te);
+                    } else {
+                        t = kp * (st.tgt[j] - st.q[j]) - (kd + h * kp) * st.qd[j];
+                        de += h * kd + h * h * kp;
+                    }
                 } else if (D.drive_mode == B2G_DOF_MODE_VEL) {
-                    t = kd * (st.tgt[j] - st.qd[j]);
-                    de += h * kd;
+                    const float te = kd * (st.tgt[j] - st.qd[j]);
+                    if (D.effort > 0.0f && fabsf(te) > D.effort) {
+                        t = copysignf(D.effort, te);
+                    } else {
+                        t = te;
+                        de += h * kd;
+                    }
                 } else if (D.drive_mode == B2G_DOF_MODE_EFFORT) {
                     t = st.act[j];
                     if (D.effort > 0.0f) t = fminf(fmaxf(t, -D.effort), D.effort);

@@ -456,12 +456,25 @@ static int FN(orc_substep)(const b2g_model* m, const b2g_sim_params* sp, const b
         R kp = (R)dp->stiffness[d], kd = (R)dp->damping[d];
         dext[d] = (R)m->armature[d];
         tau[d] = 0;
+        /* implicit PD / velocity drive; a drive whose torque -- estimated at the end-of-step position with the current velocity -- exceeds
+         * the effort limit is saturated: a constant torque of that size, no implicit terms (PhysX clamps the drive force to maxForce) */
+        R lim_d = (R)dp->effort[d];
         if (dp->drive_mode[d] == B2G_DOF_MODE_POS) {
-            tau[d] = kp * (target[d] - q[d]) - (kd + h * kp) * qd[d];
-            dext[d] += h * kd + h * h * kp;
+            R te = kp * (target[d] - q[d] - h * qd[d]) - kd * qd[d];
+            if (lim_d > 0 && (te > lim_d || te < -lim_d)) {
+                tau[d] = te > 0 ? lim_d : -lim_d;
+            } else {
+                tau[d] = kp * (target[d] - q[d]) - (kd + h * kp) * qd[d];
+                dext[d] += h * kd + h * h * kp;
+            }
         } else if (dp->drive_mode[d] == B2G_DOF_MODE_VEL) {
-            tau[d] = kd * (target[d] - qd[d]);
-            dext[d] += h * kd;
+            R te = kd * (target[d] - qd[d]);
+            if (lim_d > 0 && (te > lim_d || te < -lim_d)) {
+                tau[d] = te > 0 ? lim_d : -lim_d;
+            } else {
+                tau[d] = te;
+                dext[d] += h * kd;
+            }
         } else if (dp->drive_mode[d] == B2G_DOF_MODE_EFFORT) {
             R e = actuation[d], lim = (R)dp->effort[d];
             if (lim > 0) { if (e > lim) e = lim; if (e < -lim) e = -lim; }
@@ -733,12 +746,25 @@ static int FN(orc_substep_ref)(const b2g_model* m, const b2g_sim_params* sp, con
         R kp = (R)dp->stiffness[d], kd = (R)dp->damping[d];
         dext[d] = (R)m->armature[d];
         tau[d] = 0;
+        /* implicit PD / velocity drive; a drive whose torque -- estimated at the end-of-step position with the current velocity -- exceeds
+         * the effort limit is saturated: a constant torque of that size, no implicit terms (PhysX clamps the drive force to maxForce) */
+        R lim_d = (R)dp->effort[d];
         if (dp->drive_mode[d] == B2G_DOF_MODE_POS) {
-            tau[d] = kp * (target[d] - q[d]) - (kd + h * kp) * qd[d];
-            dext[d] += h * kd + h * h * kp;
+            R te = kp * (target[d] - q[d] - h * qd[d]) - kd * qd[d];
+            if (lim_d > 0 && (te > lim_d || te < -lim_d)) {
+                tau[d] = te > 0 ? lim_d : -lim_d;
+            } else {
+                tau[d] = kp * (target[d] - q[d]) - (kd + h * kp) * qd[d];
+                dext[d] += h * kd + h * h * kp;
+            }
         } else if (dp->drive_mode[d] == B2G_DOF_MODE_VEL) {
-            tau[d] = kd * (target[d] - qd[d]);
-            dext[d] += h * kd;
+            R te = kd * (target[d] - qd[d]);
+            if (lim_d > 0 && (te > lim_d || te < -lim_d)) {
+                tau[d] = te > 0 ? lim_d : -lim_d;
+            } else {
+                tau[d] = te;
+                dext[d] += h * kd;
+            }
         } else if (dp->drive_mode[d] == B2G_DOF_MODE_EFFORT) {
             R e = actuation[d], lim = (R)dp->effort[d];
             if (lim > 0) { if (e > lim) e = lim; if (e < -lim) e = -lim; }

@@ -329,6 +329,43 @@ def check_root_velocity_limits(make_backend, robot="anymal", n=8, seed=4):
         np.testing.assert_allclose(rb[~fast, :3], r64[~fast, :3], atol=1e-4)
 
 
+def check_drive_saturation(make_backend, robot="anymal", n=6, seed=12):
+    """An implicit position drive whose torque would exceed the DOF's effort limit acts as a constant torque of that size (PhysX clamps the
+    drive force to maxForce): with every target 2 rad away (85 N m / rad x 2 rad against 80 N m) a step in position mode equals the step
+    of an effort-mode twin fed +-effort, on the kernel and on the oracle; with targets 0.2 rad away nothing saturates and the two differ."""
+    art = load_robot(robot)
+    rng = np.random.default_rng(seed)
+    nd = art.num_dofs
+    m = _abi.pack_model(art)
+    sp = flat_params(ground=False)
+    sp.gravity[2] = 0.0
+    effort = np.array(art.effort, np.float64)
+    assert (effort > 0).all() and (effort < 85.0 * 1.5).all()
+    root, dof = standing_state(art, n, rng, 3.0)
+    sign = np.where(rng.uniform(size=(n, nd)) < 0.5, -1.0, 1.0)
+    out = {}
+    for name, mode, tgt, act in (("pos_far", _abi.DOF_MODE_POS, dof[:, :, 0] + 2.0 * sign, np.zeros((n, nd))),
+                                 ("effort", _abi.DOF_MODE_EFFORT, np.zeros((n, nd)), sign * effort),
+                                 ("pos_near", _abi.DOF_MODE_POS, dof[:, :, 0] + 0.2 * sign, np.zeros((n, nd)))):
+        props = _abi.default_dof_props(art, mode, 85.0 if mode == _abi.DOF_MODE_POS else 0.0, 2.0 if mode == _abi.DOF_MODE_POS else 0.0)
+        be = make_backend(art, sp, props, n)
+        try:
+            be.set_state(root.copy(), dof.copy())
+            r64, d64 = root.astype(np.float64), dof.astype(np.float64)
+            f, _ = be.simulate(tgt, act)
+            f64, _ = O.simulate(m, sp, props, r64, d64, tgt.astype(np.float64), act.astype(np.float64))
+            rb, db = be.get_state()
+        finally:
+            be.close()
+        np.testing.assert_allclose(db[:, :, 0], d64[:, :, 0], atol=2e-4, err_msg=name)
+        np.testing.assert_allclose(db[:, :, 1], d64[:, :, 1], rtol=2e-3, atol=2e-3, err_msg=name)
+        out[name] = (rb, db, f)
+    np.testing.assert_allclose(out["pos_far"][1], out["effort"][1], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(out["pos_far"][0], out["effort"][0], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(np.abs(out["pos_far"][2]), np.tile(effort, (n, 1)), rtol=1e-6)      # the reported DOF force sits on the limit
+    assert np.abs(out["pos_near"][1][:, :, 1] - out["effort"][1][:, :, 1]).max() > 1.0
+
+
 def root_box(art):
     """The base body's bounding box (centre, half extents; root frame) around its own contact candidates and their radii."""
     pts = np.array([p for l, b, p in zip(art.cp_link, art.cp_body, art.cp_pos) if l == 0 and b == 0], np.float64)

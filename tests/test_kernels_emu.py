@@ -80,6 +80,10 @@ def test_self_collision_against_the_base(robot):
     kc.check_self_collision(make, robot, n=4)
 
 
+def test_drive_saturates_at_the_effort_limit():
+    kc.check_drive_saturation(make)
+
+
 def test_root_velocity_limits():
     kc.check_root_velocity_limits(make)
 
