@@ -594,3 +594,48 @@ def test_useful_hound_plausibility_under_random_leg_actions(refresh):
         assert float(zmax.median()) < 0.8, float(zmax.median())
         assert float(zmax.quantile(0.99)) < 1.6, float(zmax.quantile(0.99))
         assert float((zmax > 2.0).float().mean()) < 0.01
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["Houndarm", "Manipulator"])
+def test_arm_tasks_full_size_batch_properties(task):
+    """The arm reach tasks at their configured size (8192 envs, cfg/task/{Houndarm,Manipulator}.yaml): (a) the first 512 environments of
+    the full batch follow a 512-env sim bit for bit over a window with resets and time-outs (Philox draws keyed by env index, one thread
+    per environment); (b) observations and reward of ALL environments equal the reference's formulas (:383-392, :550-567) evaluated on the
+    sim's own rigid-body tensor; (c) every reset lands inside the joint limits, the Manipulator's last two joints exactly on their default."""
+    import torch
+
+    import isaacgymenv_b200 as b2g
+
+    n, small = 8192, 512
+    ov = {"env": {"episodeLength": 30}}
+    big = b2g.make(seed=3, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=ov)
+    ref = b2g.make(seed=3, task=task, num_envs=small, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=ov)
+    # the construction-time reset draws come from torch's global generator (one call per sim): make the two sims agree on the prefix
+    ref._dof_state.copy_(big._dof_state[:small])
+    ref.commands.copy_(big.commands[:small])
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    resets = 0
+    for k in range(70):
+        a = 2 * torch.rand(n, 6, device="cuda:0", generator=g) - 1
+        ob, rb, db, eb = big.step(a)
+        os_, rs, ds, es = ref.step(a[:small].contiguous())
+        assert torch.equal(ob["obs"][:small], os_["obs"]) and torch.equal(rb[:small], rs) and torch.equal(db[:small], ds), f"step {k}: prefix differs"
+        assert torch.equal(big._dof_state[:small], ref._dof_state) and torch.equal(eb["time_outs"][:small], es["time_outs"])
+        resets += int(db.sum())
+        if k % 10 == 9:
+            big._refresh()
+            eef, cmd = big.states["eef_pos"], big.states["commands"]
+            obs = torch.cat([eef, big.states["eef_quat"], cmd], dim=-1)
+            assert torch.allclose(ob["obs"], obs.clamp(-big.clip_obs, big.clip_obs), rtol=1e-5, atol=2e-6)
+            d = (eef - cmd).norm(dim=-1)
+            rew = ((1 - torch.tanh(10 * d)) * 0.1 + (1 - torch.tanh(10 * big.states["eef_vel"].norm(dim=-1))) * (d < 0.02) * 0.1).clamp(min=0)
+            sure = (d - 0.02).abs() > 1e-4
+            assert torch.allclose(rb[sure], rew[sure], rtol=1e-4, atol=2e-6)
+        fresh = big.progress_buf == 0
+        if bool(fresh.any()):
+            q = big._q[fresh]
+            assert ((q >= big.arm_dof_lower_limits - 1e-6) & (q <= big.arm_dof_upper_limits + 1e-6)).all()
+            if big.RESET_TAIL:
+                assert torch.equal(q[:, -big.RESET_TAIL:], big.arm_default_dof_pos[-big.RESET_TAIL:].expand(q.shape[0], -1))
+    assert resets >= 2 * n, "two episode ends per environment expected in the window"
