@@ -210,7 +210,7 @@ def test_generic_jacobian_and_mass_matrix_agree_with_the_fused_arm_slices():
 
 
 @pytest.mark.parametrize("task,nact,n", [("Anymal", 12, 128), ("Anymal", 12, 101), ("Hound", 12, 37), ("Cartpole", 1, 128), ("Cartpole", 1, 77),
-                                         ("AnymalTerrain", 12, 128), ("AnymalTerrain", 12, 101), ("UsefulHound", 18, 37), ("Houndarm", 6, 50)])
+                                         ("AnymalTerrain", 12, 128), ("AnymalTerrain", 12, 101), ("UsefulHound", 18, 37), ("Houndarm", 6, 50), ("Manipulator", 6, 45)])
 def test_step_host_matches_device_step(task, nact, n):
     """b2g_task_step_host (the host-buffer entry the end-to-end benchmark times) against the device-pointer step on a twin
     sim: (a) page-locked buffers in the packed b2g_task_host_layout (zero-copy actions; the SMs store the results into the
