@@ -618,7 +618,12 @@ class Gym:
     # ---------------- tensors ----------------
     def _desc(self, sim: Sim, kind: int) -> _abi.TensorDesc:
         if not sim.prepared:
-            raise _lib.B2GError("acquire_*_tensor before prepare_sim")
+            # Isaac Gym hands out tensor descriptors before prepare_sim (the reference's arm tasks acquire theirs inside _create_envs,
+            # tasks/manipulator.py:300-323, and VecTask.__init__ prepares afterwards): every actor exists by then, so prepare now --
+            # prepare_sim is idempotent
+            if sim.asset is None or not sim.envs:
+                raise _lib.B2GError("acquire_*_tensor before any actor was created")
+            self.prepare_sim(sim)
         d = _abi.TensorDesc()
         _lib.check(_lib.load().b2g_sim_tensor(sim.handle, kind, C.byref(d)), "acquire tensor")
         return d

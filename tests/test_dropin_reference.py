@@ -187,3 +187,47 @@ def test_terrain_grid_equals_the_references_terrain_class(curriculum):
     assert np.array_equal(ref.env_origins, ours.env_origins)
     assert (ref.tot_rows, ref.tot_cols, ref.border, ref.env_rows, ref.env_cols) == (ours.tot_rows, ours.tot_cols, ours.border, ours.env_rows, ours.env_cols)
     assert np.abs(ours.height_field_raw).max() > 20 and len(np.unique(ours.env_origins[:, :, 2])) > 3
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("module,cls,task,nd", [("tasks.manipulator", "Manipulator", "Manipulator", 7), ("tasks.hound_arm", "Houndarm", "Houndarm", 6)])
+def test_reference_arm_tasks_step_on_libb200gym(module, cls, task, nd):
+    """The reference's own arm-reach classes, unmodified, on the shim: load_asset resolves their URDF (or its compiled model when the asset
+    tree is absent), acquire_jacobian_tensor / acquire_mass_matrix_tensor feed their torch OSC law, set_dof_actuation_force_tensor +
+    simulate move the arm.  Closed loop: their controller drives the end effector towards the command; this package's generic task,
+    glued to the same state each step, returns the same observations and reward."""
+    import torch
+
+    import isaacgymenv_b200 as b2g
+
+    b2g.install_isaacgym_shim(REF)
+    vt = importlib.import_module("isaacgymenvs.tasks.base.vec_task")
+    vt.EXISTING_SIM = None
+    n = 64
+    torch.manual_seed(11)
+    ref = getattr(importlib.import_module("isaacgymenvs." + module), cls)(cfg=_task_cfg(task, n), rl_device="cuda:0", sim_device="cuda:0", graphics_device_id=-1,
+                                                                         headless=True, virtual_screen_capture=False, force_render=False)
+    assert ref.num_envs == n and ref.num_dofs == nd and ref.obs_buf.shape == (n, 10) and ref._mm.shape == (n, nd, nd) and ref._j_eef.shape == (n, 6, nd)
+    torch.manual_seed(11)
+    ours = b2g.make(seed=11, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides={"env": {"fusedStep": False}})
+    ref._refresh()
+    ref.commands[:] = ref.states["eef_pos"] + torch.tensor([0.05, -0.04, 0.03], device="cuda:0")
+    d0 = float((ref.states["eef_pos"] - ref.commands).norm(dim=-1).mean())
+    for k in range(60):
+        ours._dof_state.copy_(ref._dof_state); ours.commands.copy_(ref.commands)
+        ours.progress_buf.copy_(ref.progress_buf); ours.reset_buf.copy_(ref.reset_buf)
+        ours._refresh()
+        ref._refresh()
+        err = ref.commands - ref.states["eef_pos"]
+        a = torch.cat([torch.clamp(err / 0.1, -1, 1), torch.zeros(n, 3, device="cuda:0")], dim=1)
+        o_r, r_r, d_r, e_r = ref.step(a)
+        o_o, r_o, d_o, e_o = ours.step(a)
+        assert torch.isfinite(o_r["obs"]).all() and torch.isfinite(r_r).all() and not d_r.any()
+        # the same kernels under both; the OSC law is float32 torch.inverse in both (ill-conditioned on these arms): agreement to ~1e-3
+        assert torch.allclose(o_r["obs"], o_o["obs"], rtol=2e-3, atol=2e-3), (k, float((o_r["obs"] - o_o["obs"]).abs().max()))
+        assert torch.allclose(r_r, r_o, rtol=2e-3, atol=1e-4) and torch.equal(d_r, d_o)
+    ref._refresh()
+    d1 = float((ref.states["eef_pos"] - ref.commands).norm(dim=-1).mean())
+    assert d1 < 0.35 * d0, (d0, d1)
+    vt.EXISTING_SIM = None
