@@ -231,3 +231,56 @@ def test_reference_arm_tasks_step_on_libb200gym(module, cls, task, nd):
     d1 = float((ref.states["eef_pos"] - ref.commands).norm(dim=-1).mean())
     assert d1 < 0.35 * d0, (d0, d1)
     vt.EXISTING_SIM = None
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("module,cls,task,nact,nobs", [("tasks.anymal_terrain", "AnymalTerrain", "AnymalTerrain", 12, 188), ("tasks.Hound_terrain", "HoundTerrain", "HoundTerrain", 12, 188),
+                                                       ("tasks.useful_hound", "UsefulHound", "UsefulHound", 18, 204)])
+@pytest.mark.parametrize("terrain", ["plane", "trimesh"])
+def test_reference_rough_terrain_tasks_step_on_libb200gym(module, cls, task, nact, nobs, terrain):
+    """BASELINE configs 3 and 4 through the reference's own task classes, unmodified, on the shim: their ``Terrain`` class builds the
+    height field on this package's ``terrain_utils``, ``add_triangle_mesh`` / ``add_ground`` hand it to the library, the decimation loop
+    (``set_dof_actuation_force_tensor`` + ``simulate`` + ``refresh_dof_state_tensor`` four times per step), reward, height scan, curriculum,
+    pushes and resets are the reference's code.  Contract checks over a rollout: shapes, finiteness, robots stand under small actions until
+    the episode limit resets them, fall and get reset under random actions, the height scan sees the terrain."""
+    import torch
+
+    import isaacgymenv_b200 as b2g
+
+    b2g.install_isaacgym_shim(REF)
+    vt = importlib.import_module("isaacgymenvs.tasks.base.vec_task")
+    vt.EXISTING_SIM = None
+    n = 128
+    cfg = _task_cfg(task, n)
+    cfg["env"]["terrain"]["terrainType"] = terrain
+    if terrain == "trimesh":
+        cfg["env"]["terrain"].update(numLevels=3, numTerrains=4, mapLength=8.0, mapWidth=8.0)
+    cfg["env"]["learn"]["episodeLength_s"] = 1.0      # 50 policy steps: time-outs inside the window
+    torch.manual_seed(5)
+    ref = getattr(importlib.import_module("isaacgymenvs." + module), cls)(cfg=cfg, rl_device="cuda:0", sim_device="cuda:0", graphics_device_id=-1, headless=True,
+                                                                         virtual_screen_capture=False, force_render=False)
+    assert ref.num_envs == n and ref.num_actions == nact and ref.obs_buf.shape == (n, nobs)
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    resets = early = at_limit = 0
+    for k in range(120):
+        a = 2 * torch.rand(n, nact, device="cuda:0", generator=g) - 1
+        if k < 56:
+            a = 0.05 * a      # first a quiet stretch: the robots keep standing until the 50-step episode limit; then random actions throw them over
+        o, r, d, e = ref.step(a)
+        assert o["obs"].shape == (n, nobs) and torch.isfinite(o["obs"]).all() and torch.isfinite(r).all() and torch.isfinite(ref.root_states).all(), k
+        assert e["time_outs"].shape == (n,)      # (always False here: the reference's post_physics_step has reset progress_buf before VecTask.step looks)
+        resets += int(d.sum())
+        early += int(d.sum()) if k < 45 else 0
+        at_limit += int(d.sum()) if 47 <= k <= 51 else 0
+    if cls == "AnymalTerrain":      # ANYmal stands under small actions until the episode limit; the hound's reset poses (default angles x 0.5 .. 1.5 under
+        # its explicit PD gains) put a thigh on the ground for part of the robots, which the Hound variant of check_termination ends at once
+        assert early < n // 4, f"{early} robots fell while standing still"
+        assert at_limit >= n // 2, f"only {at_limit} episodes ended at the 50-step limit"
+        assert resets > at_limit + n // 2, (resets, at_limit)
+    else:
+        assert resets > n, resets
+    assert float(ref.root_states[:, 2].max()) < 25.0
+    if terrain == "trimesh":
+        assert float(ref.measured_heights.std()) > 1e-3        # the scan reads a non-flat field
+    vt.EXISTING_SIM = None
