@@ -284,3 +284,29 @@ def test_reference_rough_terrain_tasks_step_on_libb200gym(module, cls, task, nac
     if terrain == "trimesh":
         assert float(ref.measured_heights.std()) > 1e-3        # the scan reads a non-flat field
     vt.EXISTING_SIM = None
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_hound_steps_on_libb200gym():
+    """The reference's flat-terrain ``Hound`` class (tasks/hound.py), unmodified, on the shim: contract, finiteness, resets under random actions."""
+    import torch
+
+    import isaacgymenv_b200 as b2g
+
+    b2g.install_isaacgym_shim(REF)
+    vt = importlib.import_module("isaacgymenvs.tasks.base.vec_task")
+    vt.EXISTING_SIM = None
+    n = 64
+    torch.manual_seed(2)
+    ref = importlib.import_module("isaacgymenvs.tasks.hound").Hound(cfg=_task_cfg("Hound", n), rl_device="cuda:0", sim_device="cuda:0", graphics_device_id=-1,
+                                                                    headless=True, virtual_screen_capture=False, force_render=False)
+    assert ref.obs_buf.shape == (n, 48) and ref.num_actions == 12
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    resets = 0
+    for k in range(80):
+        o, r, d, e = ref.step(2 * torch.rand(n, 12, device="cuda:0", generator=g) - 1)
+        assert torch.isfinite(o["obs"]).all() and torch.isfinite(r).all()
+        resets += int(d.sum())
+    assert resets > 0
+    vt.EXISTING_SIM = None
