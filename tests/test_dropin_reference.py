@@ -310,3 +310,72 @@ def test_reference_hound_steps_on_libb200gym():
         resets += int(d.sum())
     assert resets > 0
     vt.EXISTING_SIM = None
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("module,cls,task,nact", [("tasks.anymal_terrain", "AnymalTerrain", "AnymalTerrain", 12), ("tasks.Hound_terrain", "HoundTerrain", "HoundTerrain", 12)])
+def test_fused_terrain_step_equals_the_reference_class_on_the_same_physics(module, cls, task, nact):
+    """The whole policy step of BASELINE config 3, two ways on the same state and actions: (a) the REFERENCE's class, unmodified -- its own
+    decimation loop (explicit PD torques, set_dof_actuation_force_tensor, gym.simulate x 4 + the base class's fifth), its post_physics_step
+    in torch / TorchScript -- on the library's generic kernels; (b) this package's fused task (k_terrain_phys + k_terrain_post).  Noise and
+    pushes off (they draw from different generators), environments that reset in the step left out (so do the reset draws).  What must
+    agree: observations incl. the height scan, reward, the reset decision -- to the rounding two instantiations of the same sub-step code
+    leave after five sim steps."""
+    import torch
+
+    import isaacgymenv_b200 as b2g
+
+    b2g.install_isaacgym_shim(REF)
+    vt = importlib.import_module("isaacgymenvs.tasks.base.vec_task")
+    n = 64
+
+    def cfg_of():
+        cfg = _task_cfg(task, n)
+        cfg["env"]["learn"]["addNoise"] = False
+        cfg["env"]["learn"]["pushInterval_s"] = 1.0e6
+        return cfg
+
+    vt.EXISTING_SIM = None
+    ref_cls = getattr(importlib.import_module("isaacgymenvs." + module), cls)       # first import draws from torch's generator: do it before seeding
+    torch.manual_seed(9)
+    ref = ref_cls(cfg=cfg_of(), rl_device="cuda:0", sim_device="cuda:0", graphics_device_id=-1, headless=True, virtual_screen_capture=False, force_render=False)
+    torch.manual_seed(9)
+    ov = {"env": {"learn": {"addNoise": False, "pushInterval_s": 1.0e6}}}
+    ours = b2g.make(seed=9, task=task, num_envs=n, sim_device="cuda:0", rl_device="cuda:0", headless=True, overrides=ov)
+    # same physics needs the same per-environment friction: both classes draw the 100 buckets first thing after the seed (anymal_terrain.py:239)
+    assert max(abs(x - y) for x, y in zip(ref.sim.env_friction, ours.sim.env_friction)) < 1e-6
+    g = torch.Generator(device="cuda:0").manual_seed(4)
+    compared, dobs, dscan, drew = 0, [], [], []
+    for k in range(30):
+        for name in ("root_states", "dof_state", "commands", "last_actions", "last_dof_vel", "feet_air_time", "progress_buf"):
+            getattr(ours, name).copy_(getattr(ref, name).view_as(getattr(ours, name)))
+        ours.reset_buf.copy_(ref.reset_buf.to(ours.reset_buf.dtype))
+        a = 0.6 * (2 * torch.rand(n, nact, device="cuda:0", generator=g) - 1)
+        o_r, r_r, d_r, _ = ref.step(a)
+        o_o, r_o, d_o, _ = ours.step(a)
+        d_r, d_o = d_r != 0, d_o != 0
+        keep = ~d_r & ~d_o
+        # a contact force within rounding of the 1 N termination threshold may fall either side of it in the two paths
+        assert int((d_r != d_o).sum()) <= 1, (k, int((d_r != d_o).sum()))
+        if int(keep.sum()) == 0:
+            continue
+        compared += int(keep.sum())
+        dd = (o_r["obs"][keep] - o_o["obs"][keep]).abs()
+        dobs.append(torch.cat([dd[:, :48], dd[:, 188:]], dim=1).flatten())      # base velocities, gravity, commands, joint state, actions
+        dscan.append(dd[:, 48:188].flatten())                                    # the 140-point height scan
+        drew.append((r_r[keep] - r_o[keep]).abs())
+    assert compared > 10 * n
+    dobs, dscan, drew = torch.cat(dobs), torch.cat(dscan), torch.cat(drew)
+    # height scan on the default plane: 5 x (root z - 0.5), so this is the root height's agreement
+    scan_off = float((dscan > 1e-3).float().mean())
+    assert scan_off < 0.01, scan_off
+    # one step = five contact-rich sim steps through two differently compiled instantiations of the same code: nearly every entry agrees to
+    # float32 rounding, a foot that makes or breaks contact a sub-step earlier in one of them shows up in that environment's velocities
+    q = lambda t, p: float(t.float().kthvalue(max(1, int(p * t.numel()))).values)
+    stats = dict(obs_median=q(dobs, 0.5), obs_p99=q(dobs, 0.99), obs_p999=q(dobs, 0.999), obs_max=float(dobs.max()), rew_p99=q(drew, 0.99), rew_max=float(drew.max()))
+    print(f"{task}: {compared} env-steps compared, scan points off {scan_off:.4f}", {k_: f"{v:.2e}" for k_, v in stats.items()})
+    # measured on a B200 (profiles/r02_dropin_fused_vs_reference_class.log): median 0, p99 5e-7, p99.9 2e-6 (Anymal) / 1e-3 (Hound), max 8e-5 / 2.5e-2
+    assert stats["obs_median"] < 1e-6 and stats["obs_p99"] < 1e-4 and stats["obs_p999"] < 1e-2 and stats["obs_max"] < 0.2, stats
+    assert stats["rew_p99"] < 1e-5 and stats["rew_max"] < 5e-3, stats
+    vt.EXISTING_SIM = None
