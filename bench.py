@@ -278,9 +278,12 @@ def measure_task(task, num_envs, steps, warmup, preroll, dev, rank, world, dist,
     e0.record(stream)
     for i in range(steps):
         step_host(i)
+    # b2g_task_step_host blocks until the results are in the caller's host buffers: the K steps end HERE on this rank.  The closing
+    # barrier stays outside the interval (an NCCL barrier costs a noticeable share of a 20-step, 1.2 ms region); max over ranks below
+    wall_ms = (time.perf_counter() - t0) * 1e3
     e1.record(stream)
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)
     clocks = sampler.stop() if sampler else None
     assert torch.isfinite(h_obs).all() and torch.isfinite(h_rew).all()
     stats = None
