@@ -123,10 +123,12 @@ __global__ void __launch_bounds__(kHeadBlock) k_ppo_head_finalize(b2g_ppo_head_a
         s = warp_sum(s);
         if ((threadIdx.x & 31) == 0) tot[k] = s;
     }
+    __shared__ float ls[kMaxAct];      // one parallel read of log_std: a serial loop over global loads costs a memory latency per action
+    if (threadIdx.x < A) ls[threadIdx.x] = a.log_std[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
         float ent = 0.0f;
-        for (int k = 0; k < A; k++) ent += a.log_std[k] + 0.5f + 0.9189385332046727f;
+        for (int k = 0; k < A; k++) ent += ls[k] + 0.5f + 0.9189385332046727f;
         a.out[1] = tot[0]; a.out[2] = tot[1]; a.out[3] = tot[2]; a.out[4] = tot[3]; a.out[5] = ent;
         a.out[0] = tot[0] + 0.5f * a.critic_coef * tot[1] - a.entropy_coef * ent + a.bounds_loss_coef * tot[2];
     }
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(256) k_bias_elu(float* __restrict__ z, const f
 
 // backward: dz = dh * elu'(z) with elu'(z) = 1 (h > 0) or h + 1 (h <= 0) from the stored OUTPUT h; column sums of dz (= the bias
 // gradient) per block of kColRows rows into partial[block][col].  Block = (cols / 4) column threads x row lanes.
-constexpr int kColRows = 256;
+constexpr int kColRows = 64;       // 512 blocks for a 32768-row minibatch: the pass is a pure stream (14 B per element), it wants every SM loaded several times over
 __global__ void __launch_bounds__(256) k_elu_bwd_colsum(const float* __restrict__ dh, const float* __restrict__ h, float* __restrict__ dz,
                                                         float* __restrict__ partial, int rows, int cols, __nv_bfloat16* __restrict__ dz16) {
     extern __shared__ float4 red4[];      // (row lanes, cols / 4)
@@ -164,16 +166,28 @@ __global__ void __launch_bounds__(256) k_elu_bwd_colsum(const float* __restrict_
     const int c4 = threadIdx.x % cols4, lane = threadIdx.x / cols4, lanes = blockDim.x / cols4;
     const int r0 = blockIdx.x * kColRows, r1 = min(r0 + kColRows, rows);
     float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    auto one = [&](const float4 g, const float4 o, size_t i) {
+        float4 d;
+        d.x = g.x * (o.x > 0.0f ? 1.0f : o.x + 1.0f); d.y = g.y * (o.y > 0.0f ? 1.0f : o.y + 1.0f);
+        d.z = g.z * (o.z > 0.0f ? 1.0f : o.z + 1.0f); d.w = g.w * (o.w > 0.0f ? 1.0f : o.w + 1.0f);
+        if (dz) reinterpret_cast<float4*>(dz)[i] = d;      // null: the caller only needs the bf16 copy (first layer: no dX)
+        if (dz16) store_bf16x4(dz16, i, d);
+        acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+    };
     if (lane < lanes) {
-        for (int r = r0 + lane; r < r1; r += lanes) {
+        int r = r0 + lane;
+        // four rows per trip: all eight loads are issued before the first use (rows added in the same order as a one-row loop)
+        for (; r + 3 * lanes < r1; r += 4 * lanes) {
+            const size_t i0 = (size_t)r * cols4 + c4, st = (size_t)lanes * cols4;
+            const float4 g0 = *(reinterpret_cast<const float4*>(dh) + i0), o0 = *(reinterpret_cast<const float4*>(h) + i0);
+            const float4 g1 = *(reinterpret_cast<const float4*>(dh) + i0 + st), o1 = *(reinterpret_cast<const float4*>(h) + i0 + st);
+            const float4 g2 = *(reinterpret_cast<const float4*>(dh) + i0 + 2 * st), o2 = *(reinterpret_cast<const float4*>(h) + i0 + 2 * st);
+            const float4 g3 = *(reinterpret_cast<const float4*>(dh) + i0 + 3 * st), o3 = *(reinterpret_cast<const float4*>(h) + i0 + 3 * st);
+            one(g0, o0, i0); one(g1, o1, i0 + st); one(g2, o2, i0 + 2 * st); one(g3, o3, i0 + 3 * st);
+        }
+        for (; r < r1; r += lanes) {
             const size_t i = (size_t)r * cols4 + c4;
-            const float4 g = reinterpret_cast<const float4*>(dh)[i], o = reinterpret_cast<const float4*>(h)[i];
-            float4 d;
-            d.x = g.x * (o.x > 0.0f ? 1.0f : o.x + 1.0f); d.y = g.y * (o.y > 0.0f ? 1.0f : o.y + 1.0f);
-            d.z = g.z * (o.z > 0.0f ? 1.0f : o.z + 1.0f); d.w = g.w * (o.w > 0.0f ? 1.0f : o.w + 1.0f);
-            if (dz) reinterpret_cast<float4*>(dz)[i] = d;      // null: the caller only needs the bf16 copy (first layer: no dX)
-            if (dz16) store_bf16x4(dz16, i, d);
-            acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+            one(*(reinterpret_cast<const float4*>(dh) + i), *(reinterpret_cast<const float4*>(h) + i), i);
         }
         red4[lane * cols4 + c4] = acc;
     }
@@ -187,17 +201,27 @@ __global__ void __launch_bounds__(256) k_elu_bwd_colsum(const float* __restrict_
     }
 }
 
-// second stage of the column sums: 32 columns x 8 row lanes per block; lane q adds partial rows q, q + 8, ... and the lanes are added
-// in order (deterministic).  `out` may be scattered: column c goes to out_of(c).
-constexpr int kFinLanes = 8;
+// second stage of the column sums: 32 columns x 32 row lanes per block; lane q adds partial rows q, q + 32, ... (four independent running
+// sums, so four loads are in flight per thread -- the stage is latency-bound: a few thousand threads reading an L2-resident table) and the
+// lanes are added in order (deterministic).  `out` may be scattered: column c goes to out_of(c).
+constexpr int kFinLanes = 32;
 template <class OutOf>
 __device__ __forceinline__ void colsum_finalize_body(const float* __restrict__ partial, int n_blocks, int cols, OutOf out_of) {
     __shared__ float red[kFinLanes][33];
     const int tx = threadIdx.x & 31, q = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     float s = 0.0f;
-    if (c < cols)
-        for (int b = q; b < n_blocks; b += kFinLanes) s += partial[(size_t)b * cols + c];
+    if (c < cols) {
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        int b = q;
+        for (; b + 3 * kFinLanes < n_blocks; b += 4 * kFinLanes) {
+            const float v0 = partial[(size_t)b * cols + c], v1 = partial[(size_t)(b + kFinLanes) * cols + c];
+            const float v2 = partial[(size_t)(b + 2 * kFinLanes) * cols + c], v3 = partial[(size_t)(b + 3 * kFinLanes) * cols + c];
+            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        }
+        for (; b < n_blocks; b += kFinLanes) s0 += partial[(size_t)b * cols + c];
+        s = (s0 + s1) + (s2 + s3);
+    }
     red[q][tx] = s;
     __syncthreads();
     if (q == 0 && c < cols) {
@@ -429,42 +453,117 @@ __global__ void __launch_bounds__(256) k_finish_batch(const float* __restrict__ 
 // kHeadRows rows of dY and h in shared memory, every thread owns a few entries of dWcat and half a row of dh, and block partial sums
 // are added in a fixed order by k_colsum_finalize.
 constexpr int kHeadRows = 64;
+constexpr int kHeadGroups = 4;                       // row groups of a tile: 256 threads = 64 columns x 4 groups of 16 rows
+constexpr int kHeadGroupRows = kHeadRows / kHeadGroups;
+// Thread (c, g) owns column c (of a 64-wide column chunk) for the 16 rows of group g.  Both products then read ONE value per row that differs
+// between the lanes of a warp -- h[r][c], consecutive c: conflict-free -- and the row's O gradients as broadcast 128-bit loads (the rows of
+// dY and the rows of W are zero-padded to NQ quads, so no predicate sits in the inner loops):
+//   dWcat[o][c] = sum_r dY[r][o] h[r][c]   accumulators acc[o] in registers, the four row groups added in order through shared memory;
+//   dh[r][c]    = sum_o dY[r][o] W[o][c]   the column of W in registers, one coalesced store per row.
+// The earlier form (one dWcat entry per thread, 64-long dot products out of shared memory, two 32-bit loads per FMA) spent 35 us per
+// minibatch in the load/store unit; this one issues ~1/6 of the shared-memory instructions.
+template <int NQ>
 __global__ void __launch_bounds__(256) k_heads_backward(const float* __restrict__ h, const float* __restrict__ dmu, const float* __restrict__ dv,
                                                         const float* __restrict__ w_mu, const float* __restrict__ w_v, int rows, int H, int A,
                                                         float* __restrict__ dh, float* __restrict__ partial) {
-    extern __shared__ float sm[];
-    const int O = A + 1;
-    const int H1 = H + 1;
-    float* s_h = sm;                            // (kHeadRows, H + 1): [h | 1] -- the ones column makes the bias gradient one more column of dWcat
-    float* s_dy = s_h + kHeadRows * H1;         // (kHeadRows, O)
-    float* s_w = s_dy + kHeadRows * O;          // (O, H)
+    extern __shared__ __align__(16) float sm[];
+    constexpr int OP = 4 * NQ;                  // padded number of outputs
+    const int O = A + 1, H1 = H + 1;
+    float* s_dy = sm;                           // (kHeadRows, OP)
+    float* s_w = s_dy + kHeadRows * OP;         // (H, OP): W transposed, so that thread c reads its column as quads
+    float* s_h = s_w + H * OP;                  // (kHeadRows, H)
+    float* s_red = s_h + kHeadRows * H;         // (kHeadGroups - 1, OP, 64)
+    const int tc = threadIdx.x & 63, g = threadIdx.x >> 6;
     const int r0 = blockIdx.x * kHeadRows;
     const int nr = min(kHeadRows, rows - r0);
-    for (int i = threadIdx.x; i < kHeadRows * H1; i += blockDim.x) {
-        const int r = i / H1, c = i - r * H1;
-        s_h[i] = c == H ? 1.0f : (r < nr ? h[(size_t)(r0 + r) * H + c] : 0.0f);
+    if ((H & 3) == 0) {      // the tile is contiguous in h: 128-bit loads, four in flight per thread before the first store
+        const int H4 = H >> 2, total4 = kHeadRows * H4;
+        const float4* src = reinterpret_cast<const float4*>(h + (size_t)r0 * H);
+        for (int base = 0; base < total4; base += 4 * 256) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 256 + threadIdx.x;
+                v[u] = (i < total4 && i / H4 < nr) ? src[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 256 + threadIdx.x;
+                if (i < total4) reinterpret_cast<float4*>(s_h)[i] = v[u];
+            }
+        }
+    } else {
+        for (int r = g; r < kHeadRows; r += kHeadGroups)
+            for (int c = tc; c < H; c += 64) s_h[r * H + c] = r < nr ? h[(size_t)(r0 + r) * H + c] : 0.0f;
     }
-    for (int i = threadIdx.x; i < kHeadRows * O; i += blockDim.x) {
-        const int r = i / O, o = i - r * O;
-        s_dy[i] = r < nr ? (o < A ? dmu[(size_t)(r0 + r) * A + o] : dv[r0 + r]) : 0.0f;
+    for (int i = threadIdx.x; i < kHeadRows * OP; i += blockDim.x) {
+        const int r = i / OP, o = i - r * OP;
+        s_dy[i] = (r < nr && o < O) ? (o < A ? dmu[(size_t)(r0 + r) * A + o] : dv[r0 + r]) : 0.0f;
     }
-    for (int i = threadIdx.x; i < O * H; i += blockDim.x) s_w[i] = i < A * H ? w_mu[i] : w_v[i - A * H];
+    for (int i = threadIdx.x; i < H * OP; i += blockDim.x) {
+        const int c = i / OP, o = i - c * OP;
+        s_w[i] = o < A ? w_mu[o * H + c] : (o == A ? w_v[c] : 0.0f);
+    }
     __syncthreads();
-    // dWcat entries (o, c), c = H is the bias column
-    const int n_out = O * (H + 1);
-    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
-        const int o = e / (H + 1), c = e - o * (H + 1);
-        float acc = 0.0f;
-#pragma unroll 8
-        for (int r = 0; r < kHeadRows; r++) acc += s_dy[r * O + o] * s_h[r * H1 + c];
-        partial[(size_t)blockIdx.x * n_out + e] = acc;
+    const int n_out = O * H1;
+    float* part = partial + (size_t)blockIdx.x * n_out;
+    const float4* dy4 = reinterpret_cast<const float4*>(s_dy) + (size_t)g * kHeadGroupRows * NQ;
+    for (int cc = 0; cc < H; cc += 64) {
+        const int c = cc + tc;
+        const bool live = c < H;
+        // ---- dWcat ----
+        float acc[OP];
+#pragma unroll
+        for (int o = 0; o < OP; o++) acc[o] = 0.0f;
+        if (live) {
+#pragma unroll 4
+            for (int r = 0; r < kHeadGroupRows; r++) {
+                const float hv = s_h[(g * kHeadGroupRows + r) * H + c];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    const float4 d = dy4[r * NQ + q];
+                    acc[4 * q + 0] += d.x * hv; acc[4 * q + 1] += d.y * hv; acc[4 * q + 2] += d.z * hv; acc[4 * q + 3] += d.w * hv;
+                }
+            }
+        }
+        if (cc) __syncthreads();      // the previous chunk's s_red has been read
+        if (g > 0) {
+#pragma unroll
+            for (int o = 0; o < OP; o++) s_red[((g - 1) * OP + o) * 64 + tc] = acc[o];
+        }
+        __syncthreads();
+        if (g == 0 && live) {         // groups added in order: deterministic
+#pragma unroll
+            for (int o = 0; o < OP; o++) {
+                float t = acc[o];
+#pragma unroll
+                for (int k = 0; k < kHeadGroups - 1; k++) t += s_red[(k * OP + o) * 64 + tc];
+                if (o < O) part[o * H1 + c] = t;
+            }
+        }
+        // ---- dh ----
+        if (live) {
+            float4 wq[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) wq[q] = reinterpret_cast<const float4*>(s_w)[(size_t)c * NQ + q];
+#pragma unroll 4
+            for (int r = 0; r < kHeadGroupRows; r++) {
+                const int rr = g * kHeadGroupRows + r;
+                float t = 0.0f;
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    const float4 d = dy4[r * NQ + q];
+                    t += d.x * wq[q].x; t += d.y * wq[q].y; t += d.z * wq[q].z; t += d.w * wq[q].w;
+                }
+                if (rr < nr) dh[(size_t)(r0 + rr) * H + c] = t;
+            }
+        }
     }
-    // dh rows: thread t -> row t / 4, a quarter of the columns
-    for (int i = threadIdx.x; i < nr * H; i += blockDim.x) {
-        const int r = i / H, c = i - r * H;
-        float acc = 0.0f;
-        for (int o = 0; o < O; o++) acc += s_dy[r * O + o] * s_w[o * H + c];
-        dh[(size_t)(r0 + r) * H + c] = acc;
+    // bias column of dWcat: column sums of dY over the tile, rows in order
+    if (threadIdx.x < O) {
+        float t = 0.0f;
+        for (int r = 0; r < kHeadRows; r++) t += s_dy[r * OP + threadIdx.x];
+        part[threadIdx.x * H1 + H] = t;
     }
 }
 
@@ -628,13 +727,24 @@ static int heads_backward_launch(const float* h, const float* dmu, const float* 
                                  float* dh, float* partial, cudaStream_t st, int& blocks) {
     if (!h || !dmu || !dv || !w_mu || !w_v || !dh || !partial || rows < 1) return b2g::fail_msg(B2G_ERR_ARG, "b2g_mlp_heads_backward: null argument");
     if (hidden < 1 || hidden > 256 || n_actions < 1 || n_actions > kMaxAct) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_heads_backward: hidden <= 256, actions <= 24");
-    const int O = n_actions + 1;
-    const size_t smem = sizeof(float) * ((size_t)kHeadRows * (hidden + 1 + O) + (size_t)O * hidden);
-    static bool opted = false;
-    if (!opted) { cudaFuncSetAttribute(k_heads_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); opted = true; }
+    const int O = n_actions + 1, NQ = (O + 3) / 4, OP = 4 * NQ;
+    const size_t smem = sizeof(float) * ((size_t)kHeadRows * OP + (size_t)hidden * OP + (size_t)kHeadRows * hidden + (size_t)(kHeadGroups - 1) * OP * 64);
     if (smem > 96 * 1024) return b2g::fail_msg(B2G_ERR_UNSUPPORTED, "b2g_mlp_heads_backward: tile does not fit shared memory");
     blocks = (rows + kHeadRows - 1) / kHeadRows;
-    k_heads_backward<<<blocks, 256, smem, st>>>(h, dmu, dv, w_mu, w_v, rows, hidden, n_actions, dh, partial);
+    static bool opted[8] = {false, false, false, false, false, false, false, false};      // per instantiation; first use is the learner's warm-up, outside any capture
+    auto go = [&](auto kern) {
+        if (!opted[NQ < 7 ? NQ : 7]) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); opted[NQ < 7 ? NQ : 7] = true; }
+        kern<<<blocks, 256, smem, st>>>(h, dmu, dv, w_mu, w_v, rows, hidden, n_actions, dh, partial);
+    };
+    switch (NQ) {
+        case 1: go(k_heads_backward<1>); break;
+        case 2: go(k_heads_backward<2>); break;
+        case 3: go(k_heads_backward<3>); break;
+        case 4: go(k_heads_backward<4>); break;
+        case 5: go(k_heads_backward<5>); break;
+        case 6: go(k_heads_backward<6>); break;
+        default: go(k_heads_backward<7>); break;
+    }
     return B2G_OK;
 }
 
