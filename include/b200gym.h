@@ -548,6 +548,10 @@ int b2g_mlp_bias_elu(float* z, const float* bias, int rows, int cols, void* h_bf
 int b2g_mlp_elu_backward(const float* dh, const float* h, float* dz /* may be null when dz_bf16 is given */, float* dbias, float* partial, int rows, int cols,
                          void* dz_bf16 /* optional bf16 copy of dz */, void* stream);
 int b2g_mlp_elu_backward_workspace_floats(int rows, int cols);
+/* Forward of the two output heads on the last hidden layer h (rows x hidden, row-major): mu (rows x n_actions) = h W_mu^T + b_mu, value (rows) =
+ * h W_v^T + b_v, float32 accumulation, one pass over h (replaces torch.addmm x 2 of the learner's forward, learning/fused_update.py). */
+int b2g_mlp_heads_forward(const float* h, const float* w_mu, const float* b_mu, const float* w_v, const float* b_v, int rows, int hidden, int n_actions,
+                          float* mu, float* value, void* stream);
 /* Backward of the two output heads on the last hidden layer h (rows x hidden): mu = h W_mu^T + b_mu (n_actions rows), value = h W_v^T + b_v.
  * dh = dmu W_mu + dv W_v; dw_cat ((n_actions + 1) x (hidden + 1), row-major) = [dmu | dv]^T [h | 1]: rows 0..A-1 = d W_mu | d b_mu, row A =
  * d W_v | d b_v.  One pass over the minibatch instead of two K = rows GEMMs with a dozen output rows, two bias reductions and an add. */

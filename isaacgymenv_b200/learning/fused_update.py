@@ -316,6 +316,8 @@ def _protos():
         lib.b2g_mlp_elu_backward.restype = C.c_int
         lib.b2g_mlp_elu_backward_workspace_floats.argtypes = [C.c_int, C.c_int]
         lib.b2g_mlp_elu_backward_workspace_floats.restype = C.c_int
+        lib.b2g_mlp_heads_forward.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+        lib.b2g_mlp_heads_forward.restype = C.c_int
         lib.b2g_mlp_heads_backward.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
         lib.b2g_mlp_heads_backward.restype = C.c_int
         lib.b2g_mlp_heads_backward_workspace_floats.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -343,8 +345,13 @@ class _Heads(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, w_mu, b_mu, w_v, b_v, direct):
         ctx.direct = bool(direct)
-        mu = torch.addmm(b_mu, h, w_mu.t())
-        v = torch.addmm(b_v, h, w_v.t()).squeeze(-1)
+        lib = _lib.load()
+        rows, hid = h.shape
+        A = w_mu.shape[0]
+        mu = torch.empty(rows, A, device=h.device, dtype=h.dtype)
+        v = torch.empty(rows, device=h.device, dtype=h.dtype)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.b2g_mlp_heads_forward(p(h), p(w_mu), p(b_mu), p(w_v), p(b_v), rows, hid, A, p(mu), p(v), _stream(h.device)), "b2g_mlp_heads_forward")
         ctx.save_for_backward(h, w_mu, w_v, b_mu, b_v)
         return mu, v
 

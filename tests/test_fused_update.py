@@ -318,7 +318,7 @@ def test_linear_elu_bf16_weight_gradient():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("rows,hid,A", [(32768, 64, 12), (1000, 128, 18), (70, 64, 1)])
+@pytest.mark.parametrize("rows,hid,A", [(32768, 64, 12), (1000, 128, 18), (70, 64, 1), (130, 52, 24), (200, 50, 5), (300, 256, 3)])
 def test_heads_backward_kernel_matches_torch(rows, hid, A):
     from isaacgymenv_b200.learning.fused_update import heads
 
