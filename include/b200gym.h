@@ -562,6 +562,9 @@ int b2g_mlp_heads_backward_workspace_floats(int rows, int hidden, int n_actions)
  * packed matrix, no split-and-accumulate kernels behind it. */
 int b2g_mlp_heads_backward_scatter(const float* h, const float* dmu, const float* dv, const float* w_mu, const float* w_v, int rows, int hidden, int n_actions,
                                    float* dh, float* dw_mu, float* db_mu, float* dw_v, float* db_v, float* partial, void* stream);
+/* Pseudo-random permutation of 0..n-1 into out (int64): the shuffle of a mini-epoch's minibatches (the role of torch.randperm in the learner,
+ * learning/ppo.py).  Keyed Feistel bijection with cycle walking, one thread per index, deterministic in (seed, counter). */
+int b2g_random_permutation(int64_t* out, int n, uint64_t seed, uint64_t counter, void* stream);
 /* Minibatch gather of the update: dst[r] = src[index[r]] for (rows, cols) float32 rows (cols % 4 == 0), as float32 (dst) and / or bf16
  * (dst_bf16) in one pass (torch: index_select + a cast kernel). */
 int b2g_gather_rows(const float* src, const int64_t* index, int rows, int cols, float* dst, void* dst_bf16, void* stream);

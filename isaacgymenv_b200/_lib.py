@@ -105,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "b2g_sim_tensor", "b2g_sim_simulate", "b2g_sim_refresh", "b2g_sim_set_indexed", "b2g_sim_set_tensor",
     "b2g_sim_forward_dynamics", "b2g_task_anymal_create", "b2g_task_tensor", "b2g_task_anymal_reset_all", "b2g_task_anymal_step", "b2g_task_set_rand_override", "b2g_task_anymal_post_only", "b2g_task_anymal_step_host", "b2g_task_cartpole_create", "b2g_task_houndarm_create", "b2g_task_terrain_create", "b2g_task_terrain_set_step", "b2g_task_terrain_set_init_done", "b2g_task_terrain_device_step", "b2g_task_step", "b2g_task_post_only", "b2g_task_osc_probe", "b2g_task_step_host", "b2g_sim_launch_count", "b2g_sim_contact_stats", "b2g_sizeof", "b2g_dlpack_from_desc", "b2g_task_host_layout",
     "b2g_ppo_head", "b2g_ppo_head_workspace_floats", "b2g_adam_clip_step", "b2g_running_stat_update", "b2g_stat_workspace_doubles", "b2g_normalize_store", "b2g_rollout_sample", "b2g_rollout_counter_advance", "b2g_rollout_post", "b2g_gae_finish",
-    "b2g_mlp_bias_elu", "b2g_mlp_elu_backward", "b2g_mlp_elu_backward_workspace_floats", "b2g_mlp_heads_forward", "b2g_mlp_heads_backward", "b2g_mlp_heads_backward_workspace_floats", "b2g_mlp_heads_backward_scatter", "b2g_gather_rows",
+    "b2g_mlp_bias_elu", "b2g_mlp_elu_backward", "b2g_mlp_elu_backward_workspace_floats", "b2g_mlp_heads_forward", "b2g_mlp_heads_backward", "b2g_mlp_heads_backward_workspace_floats", "b2g_mlp_heads_backward_scatter", "b2g_gather_rows", "b2g_random_permutation",
     "b2g_policy_create", "b2g_policy_destroy", "b2g_policy_set_layer", "b2g_policy_set_obs_norm", "b2g_policy_forward", "b2g_policy_launch_count",
 ]
 

@@ -176,9 +176,12 @@ class RolloutKernels:
         lib.b2g_rollout_counter_advance.argtypes = [vp, vp]
         lib.b2g_rollout_post.argtypes = [C.POINTER(RolloutPostArgs), vp]
         lib.b2g_gae_finish.argtypes = [C.POINTER(GaeArgs), vp]
+        lib.b2g_random_permutation.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp]
         for f in (lib.b2g_running_stat_update, lib.b2g_stat_workspace_doubles, lib.b2g_normalize_store, lib.b2g_rollout_sample,
-                  lib.b2g_rollout_counter_advance, lib.b2g_rollout_post, lib.b2g_gae_finish):
+                  lib.b2g_rollout_counter_advance, lib.b2g_rollout_post, lib.b2g_gae_finish, lib.b2g_random_permutation):
             f.restype = C.c_int
+        self.perm = None
+        self.perm_counter = 0
         self.p = ppo
         env, cfg = ppo.env, ppo.cfg
         dev = self.device = torch.device(ppo.device)
@@ -200,6 +203,15 @@ class RolloutKernels:
 
     def _s(self):
         return _stream(self.device)
+
+    def permutation(self, n):
+        """A fresh pseudo-random permutation of 0..n-1 (int64, device): the mini-epoch shuffle, one launch instead of torch.randperm's sort."""
+        if self.perm is None or self.perm.numel() != n:
+            self.perm = torch.empty(n, dtype=torch.int64, device=self.device)
+        self.perm_counter += 1
+        _lib.check(self.lib.b2g_random_permutation(C.c_void_p(self.perm.data_ptr()), int(n), C.c_uint64(self.seed ^ 0x5DEECE66D), C.c_uint64(self.perm_counter), self._s()),
+                   "b2g_random_permutation")
+        return self.perm
 
     def obs_stats(self, obs):
         """obs_rms.update(obs) + float32 mean / inverse std for the normalisation of this step."""

@@ -539,7 +539,7 @@ class PPO:
                 self._sync_normalisers()
             steps += T * N
             for _ in range(cfg.mini_epochs):
-                perm = torch.randperm(T * N, device=self.device)
+                perm = self.rk.permutation(T * N) if self.fused_update else torch.randperm(T * N, device=self.device)
                 self.kl_acc.zero_()
                 for k in range(n_mb):
                     self.idx.copy_(perm[k * self.mb:(k + 1) * self.mb])

@@ -391,3 +391,32 @@ def test_gather_rows_kernel(rows, cols, n):
     only16 = torch.zeros_like(out16)
     gather_rows(src, idx, None, only16)
     assert torch.equal(only16, out16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 4097, 196608])
+def test_random_permutation_kernel_is_a_bijection_and_moves_with_the_counter(n):
+    """b2g_random_permutation (the mini-epoch shuffle of the update): every index exactly once, a different order per (seed, counter), and no
+    visible structure -- the first half of the output draws about half of its entries from each half of the range."""
+    import ctypes as C
+
+    from isaacgymenv_b200 import _lib
+
+    lib = _lib.load()
+    lib.b2g_random_permutation.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.b2g_random_permutation.restype = C.c_int
+    dev = "cuda:0"
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    outs = []
+    for seed, ctr in ((7, 1), (7, 2), (8, 1)):
+        out = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        _lib.check(lib.b2g_random_permutation(C.c_void_p(out.data_ptr()), n, seed, ctr, st), "perm")
+        torch.cuda.synchronize()
+        assert torch.equal(torch.sort(out).values, torch.arange(n, device=dev))
+        outs.append(out)
+    if n >= 1000:
+        assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+        for o in outs:
+            low = float((o[: n // 2] < n // 2).float().mean())
+            assert 0.45 < low < 0.55, low
+            assert float((o == torch.arange(n, device=dev)).float().mean()) < 0.01      # fixed points: ~1 expected
