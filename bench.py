@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import statistics
@@ -59,7 +60,7 @@ def measured_peak():
 
 class ClockSampler:
     """SM clock / throttle-reason samples during the timed region: NVML in a thread of this process (one light query per GPU every
-    10 ms -- a per-rank `nvidia-smi -lms` subprocess takes driver locks the ranks' launches then wait on), nvidia-smi as the
+    20 ms -- a per-rank `nvidia-smi -lms` subprocess takes driver locks the ranks' launches then wait on), nvidia-smi as the
     fallback.  Rank 0 samples every GPU of the job."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -83,7 +84,7 @@ class ClockSampler:
                             self.reasons.add(name)
                 except Exception:
                     pass
-            time.sleep(0.01)
+            time.sleep(0.02)
 
     def start(self):
         try:
@@ -234,6 +235,8 @@ def measure_task(task, num_envs, steps, warmup, preroll, dev, rank, world, dist,
         step_dev(i)
     barrier()
     # ---- device-resident timing: per-step CUDA events, L2 flushed (untimed) between timed steps ----
+    gc.collect()
+    gc.disable()      # a collector pause between an event record and the launch behind it would be timed (re-enabled after the e2e loop)
     launches0 = lib.b2g_sim_launch_count(env.sim.handle)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -273,6 +276,9 @@ def measure_task(task, num_envs, steps, warmup, preroll, dev, rank, world, dist,
 
     for i in range(3):
         step_host(i)
+    # the interpreter's cycle collector can stop this thread for milliseconds (torch's module graph is large); a 20-step region is 1.3 ms
+    gc.collect()
+    gc.disable()
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
@@ -282,6 +288,7 @@ def measure_task(task, num_envs, steps, warmup, preroll, dev, rank, world, dist,
     # barrier stays outside the interval (an NCCL barrier costs a noticeable share of a 20-step, 1.2 ms region); max over ranks below
     wall_ms = (time.perf_counter() - t0) * 1e3
     e1.record(stream)
+    gc.enable()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), wall_ms)
     clocks = sampler.stop() if sampler else None
@@ -293,11 +300,15 @@ def measure_task(task, num_envs, steps, warmup, preroll, dev, rank, world, dist,
             stats = {"active_contacts": int(st[0]), "dropped_candidates": int(st[1]), "env_substeps_with_drop": int(st[2]), "env_substeps": int(st[3])}
 
     times = torch.tensor([cold_ms, warm_ms, e2e_ms], dtype=torch.float64, device=dev)
+    e2e_ranks = [e2e_ms]
     if world > 1:
+        allr = [torch.zeros_like(times) for _ in range(world)]
+        dist.all_gather(allr, times)
+        e2e_ranks = [float(t[2]) for t in allr]
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     cold_ms, warm_ms, e2e_ms = times.tolist()
     res = dict(task=task, n=n, na=na, num_obs=env.num_obs, algo_bytes=algo_bytes, kernel=kernel_name, workload=workload, cold_ms=cold_ms, warm_ms=warm_ms,
-               e2e_ms=e2e_ms, launches=int(launches), clocks=clocks, contact_stats=stats)
+               e2e_ms=e2e_ms, e2e_ranks_ms=e2e_ranks, launches=int(launches), clocks=clocks, contact_stats=stats)
     del env, flush, pool, h_arena
     torch.cuda.empty_cache()
     return res
@@ -440,6 +451,7 @@ def run_ours(args):
                 "value_warm_l2": total / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / args.steps,
                 "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * na * 4,
                         "d2h_bytes_per_step": n * res["num_obs"] * 4 + n * 4 + n * 8 + n * 8, "ms_per_step": e2e_ms / args.steps,
+                        "ms_per_step_by_rank": [round(t / args.steps, 5) for t in res.get("e2e_ranks_ms", [e2e_ms])],
                         "path": "b2g_task_step_host (C ABI), one blocking call per step: pinned host actions (read in place by the kernel over PCIe) -> "
                                 "obs/rew/reset/time_outs stored by the SMs into the caller's pinned buffer (b2g_task_host_layout; tail of the fused "
                                 "step kernel for the flat tasks / of k_terrain_post for the rough-terrain tasks, k_mirror_host otherwise), completion by a published sequence word the host polls"
