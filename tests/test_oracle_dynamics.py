@@ -1,5 +1,6 @@
 """The dynamics oracle validates itself by invariants (the reference offers no golden vector at this boundary --
-Isaac Gym/PhysX is a closed, absent binary: PARITY UNPINNED):
+Isaac Gym/PhysX is a closed, absent binary: PARITY UNPINNED against PhysX; the contact-free dynamics are pinned against an
+independent Euler-Lagrange derivation in tests/test_oracle_lagrange.py):
   * ABA forward dynamics == solve(CRBA mass matrix, tau - RNEA bias)          (two independent code paths)
   * kinetic energy from the spatial inertias == finite-difference FK energy   (independent numpy kinematics)
   * free flight: linear momentum (x, y), angular momentum (z) and energy conservation
