@@ -191,3 +191,23 @@ def test_kernel_code_equals_euler_lagrange(robot):
             ang = np.abs(xdd[3:6] - a0[e][:3]).max() / max(1.0, np.abs(xdd[3:6]).max())
             lin = np.abs(xdd[:3] - np.cross(r[10:13], r[7:10]) - a0[e][3:]).max() / max(1.0, np.abs(xdd[:3]).max())
             assert ang < 2e-4 and lin < 2e-4, (robot, e, ang, lin)
+
+
+@pytest.mark.parametrize("robot", ["houndarm", "manipulator"])
+def test_mass_matrix_equals_the_lagrangian_hessian(robot):
+    """The joint-space mass matrix the arm tasks' operational-space law inverts (acquire_mass_matrix_tensor; oracle: CRBA) is the Hessian of
+    the kinetic energy in the joint velocities, and the bias the RNEA returns is the rest of the Euler-Lagrange equation."""
+    art = load_robot(robot)
+    m = _abi.pack_model(art)
+    sp = flat_params(ground=False)
+    rng = np.random.default_rng(3)
+    root, dof = random_flying_state(art, 2, rng)
+    root, dof = root.astype(np.float64), dof.astype(np.float64)
+    root[:, 3:7] /= np.linalg.norm(root[:, 3:7], axis=1, keepdims=True)
+    L = Lagrange(art, m, [sp.gravity[0], sp.gravity[1], sp.gravity[2]])
+    tol = 1e-9 if robot in EXACT_FRAMES else 2e-6
+    for e in range(2):
+        H, Cb = O.crba_rnea(m, sp, root[e], dof[e])
+        xdd, _, M = L.accelerations(root[e], dof[e], np.zeros(art.num_dofs))
+        assert np.abs(H - M).max() < tol * np.abs(M).max()
+        np.testing.assert_allclose(-M @ xdd, Cb, rtol=0, atol=tol * max(1.0, np.abs(Cb).max()))      # tau = 0: M qdd = -bias
