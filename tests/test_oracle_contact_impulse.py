@@ -122,3 +122,37 @@ def test_sticking_contact_equals_the_operational_space_solution(robot):
     _, contact, info = O.simulate_ref(c["m"], sp, props, r, d, np.zeros((1, c["nd"])), c["tau"][None], friction=np.ones(1, np.float32), tol=1e-13)
     assert info[0][0] == 1 and info[0][3] == 0                                   # one contact, converged
     _compare(c, r, d, contact, v_pos, v_fin, lam_v, h, 5e-7 if robot in EXACT_FRAMES else 5e-6)
+
+
+@pytest.mark.parametrize("robot", ["hound", "anymal", "useful_hound"])
+@pytest.mark.parametrize("gap0,vz", [(-0.003, -0.5), (0.004, -1.5)])
+def test_kernel_code_frictionless_contact_equals_the_operational_space_solution(robot, gap0, vz):
+    """The step kernels' own contact code (float32, host lane emulator: contact candidates, per-slot Delassus terms, lane-Jacobi sweeps with
+    the root sum across chains, impulse propagation) on the same one-foot cases, straight against the operational-space solution."""
+    from tests.backends import EmuBackend
+
+    h = 0.005
+    c = _one_foot_case(robot, gap0, [0.3, -0.2, vz], seed=1, h=h)
+    sp, J, Minv, v_free, tgt = c["sp"], c["J"], c["Minv"], c["v_free"], c["tgt"]
+    sp.plane_dynamic_friction = sp.plane_static_friction = 0.0
+    Jn = J[2]
+    Wn = Jn @ Minv @ Jn
+    lam_p = max(0.0, (tgt - Jn @ v_free) / Wn)
+    v_pos = v_free + Minv @ Jn * lam_p
+    lam_v = max(0.0, lam_p - (Jn @ v_pos - min(tgt, 0.0)) / Wn)
+    v_fin = v_pos + Minv @ Jn * (lam_v - lam_p)
+    assert lam_p > 0
+    props = _abi.default_dof_props(c["art"], _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    be = EmuBackend(c["art"], sp, props, 1)
+    try:
+        be.set_state(c["root"][None].astype(np.float32), c["dof"][None].astype(np.float32))
+        be.set_friction(np.zeros(1, np.float32))
+        _, contact = be.simulate(np.zeros((1, c["nd"]), np.float32), c["tau"][None].astype(np.float32))
+        r, d = be.get_state()
+    finally:
+        be.close()
+    got_v = np.concatenate([r[0][7:10], r[0][10:13], d[0][:, 1]]).astype(np.float64)
+    scale = max(1.0, np.abs(v_fin).max())
+    assert np.abs(got_v - v_fin).max() < 2e-4 * scale, np.abs(got_v - v_fin).max()
+    fz = float(contact[0][c["body"]][2])
+    assert abs(fz - lam_v / h) < 1e-3 * max(1.0, lam_v / h), (fz, lam_v / h)
