@@ -291,3 +291,62 @@ def test_simulate_is_a_first_order_integrator_of_the_verified_equations(robot, m
     for a, b in ((q0, q1), (q1, q2), (p0, p1), (p1, p2), (w0, w1), (w1, w2)):
         assert 1.5 < a / b < 2.5, errs                            # first order
     assert q2 < 1e-2 and p2 < 3e-3, errs
+
+
+def _implicit_pd_case(robot, h=0.01, kp=85.0, kd=2.0):
+    from tests.kernel_checks import default_pose
+
+    art = load_robot(robot)
+    m = _abi.pack_model(art)
+    sp = flat_params(dt=h, substeps=1, ground=False)
+    rng = np.random.default_rng(7)
+    nd = art.num_dofs
+    root, dof = random_flying_state(art, 1, rng, scale_qd=0.5)
+    root, dof = root[0].astype(np.float64), dof[0].astype(np.float64)
+    root[3:7] /= np.linalg.norm(root[3:7])
+    root[7:13] *= 0.5
+    target = default_pose(art) + rng.uniform(-0.2, 0.2, nd)
+    L = Lagrange(art, m, [sp.gravity[0], sp.gravity[1], sp.gravity[2]])
+    nb = 0 if art.fixed_base else 6
+    q, qd = dof[:, 0], dof[:, 1]
+    # the drive law linearised about the end-of-step state: tau(q+, v+) = kp (target - q - h v+) - kd v+
+    #   => (M + h kd + h^2 kp) (v+ - v) = h [ kp (target - q - h v) - kd v - bias(q, v) ]
+    xdd, _, M = L.accelerations(root, dof, kp * (target - q - h * qd) - kd * qd)
+    D = np.zeros(nb + nd)
+    D[nb:] = h * kd + h * h * kp
+    xd = np.concatenate([root[7:10], root[10:13], qd]) if nb else qd.copy()
+    v_new = xd + np.linalg.solve(M + np.diag(D), h * (M @ xdd))
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_POS, kp, kd)
+    return art, m, sp, props, root, dof, target, v_new, nb
+
+
+@pytest.mark.parametrize("robot", ["hound", "anymal", "houndarm"])
+def test_implicit_pd_drive_is_the_linearly_implicit_euler_step(robot):
+    """Position drives (the flat tasks, cfg/task/Anymal.yaml:55-56) are integrated implicitly: one sub-step of the oracle equals the linearly
+    implicit Euler step of the Euler-Lagrange model with the drive's (diagonal) stiffness and damping on the left-hand side -- to rounding,
+    not to O(h)."""
+    art, m, sp, props, root, dof, target, v_new, nb = _implicit_pd_case(robot)
+    h = sp.dt
+    r, d = root[None].copy(), dof[None].copy()
+    O.simulate(m, sp, props, r, d, target[None], np.zeros((1, art.num_dofs)))
+    got = np.concatenate([r[0][7:10], r[0][10:13], d[0][:, 1]]) if nb else d[0][:, 1]
+    tol = 2e-7 if robot in EXACT_FRAMES else 2e-6
+    assert np.abs(got - v_new).max() < tol * max(1.0, np.abs(v_new).max())
+    assert np.abs(d[0][:, 0] - (dof[:, 0] + h * v_new[nb:])).max() < tol
+
+
+@pytest.mark.parametrize("robot", ["hound", "anymal", "houndarm"])
+def test_kernel_code_implicit_pd_step(robot):
+    """The same step through the step kernels' code (float32, host lane emulator)."""
+    from tests.backends import EmuBackend
+
+    art, m, sp, props, root, dof, target, v_new, nb = _implicit_pd_case(robot)
+    be = EmuBackend(art, sp, props, 1)
+    try:
+        be.set_state(root[None].astype(np.float32), dof[None].astype(np.float32))
+        be.simulate(target[None].astype(np.float32), np.zeros((1, art.num_dofs), np.float32))
+        r, d = be.get_state()
+    finally:
+        be.close()
+    got = (np.concatenate([r[0][7:10], r[0][10:13], d[0][:, 1]]) if nb else d[0][:, 1]).astype(np.float64)
+    assert np.abs(got - v_new).max() < 1e-4 * max(1.0, np.abs(v_new).max()), np.abs(got - v_new).max()
