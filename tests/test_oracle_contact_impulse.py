@@ -20,7 +20,7 @@ from tests.kernel_checks import default_pose, flat_params, load_robot
 from tests.test_oracle_lagrange import EXACT_FRAMES, Lagrange, _quat_to_mat
 
 
-def _one_foot_case(robot, gap0, vel, seed, h, spin=0.3):
+def _one_foot_case(robot, gap0, vel, seed, h, spin=0.3, slope=0.0, origin_x=0.0):
     """State with exactly one contact candidate (the lowest contact sphere at gap `gap0`, the next one far outside the contact offset),
     the Euler-Lagrange model, and the operational-space quantities of that contact."""
     art = load_robot(robot)
@@ -49,14 +49,16 @@ def _one_foot_case(robot, gap0, vel, seed, h, spin=0.3):
         com, rot = L.fk(x, rp, rr)
         return com - torch.einsum("lij,lj->li", rot, L.com), rot
 
+    # ground: z = slope * (x - origin_x) (slope 0: the plane); gap of a sphere as the simulator defines it, (z - ground(x, y)) n_z - radius
+    n = np.array([-slope, 0.0, 1.0]) / np.sqrt(1.0 + slope * slope)
     org, rot = frames(x0, torch.tensor(root[:3]))
-    gaps = np.array([float((org[cp_link[i]] + rot[cp_link[i]] @ cp_pos[i])[2]) for i in range(ncp)]) - cp_rad
+    ctr = np.array([(org[cp_link[i]] + rot[cp_link[i]] @ cp_pos[i]).numpy() for i in range(ncp)])
+    gaps = (ctr[:, 2] - slope * (ctr[:, 0] - origin_x)) * n[2] - cp_rad
     order = np.argsort(gaps)
-    root[2] += gap0 - gaps[order[0]]
+    root[2] += (gap0 - gaps[order[0]]) / n[2]
     assert gaps[order[1]] - gaps[order[0]] + gap0 > sp.contact_offset + 0.01      # the second-lowest sphere is out of range
     ic = int(order[0])
     rp = torch.tensor(root[:3])
-    n = np.array([0.0, 0.0, 1.0])
     off = -cp_rad[ic] * n                                  # contact point on the sphere's surface, as a point FIXED on the link
     Jc = torch.func.jacfwd(lambda x: (lambda o, r: o[cp_link[ic]] + r[cp_link[ic]] @ cp_pos[ic])(*frames(x, rp)))(x0).numpy()
     dR = torch.func.jacfwd(lambda x: frames(x, rp)[1][cp_link[ic]])(x0).numpy()
@@ -67,7 +69,7 @@ def _one_foot_case(robot, gap0, vel, seed, h, spin=0.3):
         J[:, k] = Jc[:, k] + np.cross([Wk[2, 1], Wk[0, 2], Wk[1, 0]], off)
     xd = np.concatenate([root[7:10], root[10:13], dof[:, 1]])
     xdd, _, M = L.accelerations(root, dof, tau)
-    return dict(art=art, m=m, sp=sp, root=root, dof=dof, tau=tau, J=J, Minv=np.linalg.inv(M), v_free=xd + h * xdd, body=int(m.cp_body[ic]), nd=nd,
+    return dict(art=art, m=m, sp=sp, root=root, dof=dof, tau=tau, n=n, J=J, Minv=np.linalg.inv(M), v_free=xd + h * xdd, body=int(m.cp_body[ic]), nd=nd,
                 tgt=min(-gap0 / h, float(sp.max_depenetration_velocity)))
 
 
@@ -156,3 +158,26 @@ def test_kernel_code_frictionless_contact_equals_the_operational_space_solution(
     assert np.abs(got_v - v_fin).max() < 2e-4 * scale, np.abs(got_v - v_fin).max()
     fz = float(contact[0][c["body"]][2])
     assert abs(fz - lam_v / h) < 1e-3 * max(1.0, lam_v / h), (fz, lam_v / h)
+
+
+@pytest.mark.parametrize("robot", ["hound", "anymal"])
+def test_frictionless_contact_on_a_sloped_heightfield(robot):
+    """The rough-terrain path (int16 height samples, triangle normal, gap along the vertical scaled by n_z): a field of constant slope 0.25,
+    one foot penetrating it -- the impulse acts along the field's normal (-0.25, 0, 1) / |.|, through the same operational-space solution."""
+    h, slope, ox = 0.005, 0.25, -5.0
+    c = _one_foot_case(robot, -0.003, [0.3, -0.2, -0.5], seed=1, h=h, slope=slope, origin_x=ox)
+    sp, J, Minv, v_free, tgt, n = c["sp"], c["J"], c["Minv"], c["v_free"], c["tgt"], c["n"]
+    hs, vs, rows, cols = 0.1, 0.005, 101, 101
+    samples = np.repeat((np.arange(rows) * round(slope * hs / vs)).astype(np.int16)[:, None], cols, axis=1)      # rows run along x
+    hf = _abi.Heightfield(rows=rows, cols=cols, horizontal_scale=hs, vertical_scale=vs, origin_x=ox, origin_y=-5.0, friction=0.0, restitution=0.0)
+    Jn = n @ J
+    Wn = Jn @ Minv @ Jn
+    lam_p = max(0.0, (tgt - Jn @ v_free) / Wn)
+    v_pos = v_free + Minv @ Jn * lam_p
+    lam_v = max(0.0, lam_p - (Jn @ v_pos - min(tgt, 0.0)) / Wn)
+    v_fin = v_pos + Minv @ Jn * (lam_v - lam_p)
+    assert lam_p > 0 and lam_v > 0
+    props = _abi.default_dof_props(c["art"], _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    r, d = c["root"][None].copy(), c["dof"][None].copy()
+    _, contact = O.simulate(c["m"], sp, props, r, d, np.zeros((1, c["nd"])), c["tau"][None], heightfield=hf, hf_samples=samples, friction=np.zeros(1, np.float32))
+    _compare(c, r, d, contact, v_pos, v_fin, n * lam_v, h, 5e-7 if robot in EXACT_FRAMES else 2e-6)
