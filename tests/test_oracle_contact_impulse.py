@@ -181,3 +181,88 @@ def test_frictionless_contact_on_a_sloped_heightfield(robot):
     r, d = c["root"][None].copy(), c["dof"][None].copy()
     _, contact = O.simulate(c["m"], sp, props, r, d, np.zeros((1, c["nd"])), c["tau"][None], heightfield=hf, hf_samples=samples, friction=np.zeros(1, np.float32))
     _compare(c, r, d, contact, v_pos, v_fin, n * lam_v, h, 5e-7 if robot in EXACT_FRAMES else 2e-6)
+
+
+@pytest.mark.parametrize("robot", ["hound", "anymal"])
+def test_two_frictionless_contacts_couple_through_the_base(robot):
+    """Two feet of different legs touch at once: their normal rows couple through the floating base (W is a full 2 x 2 matrix), and the
+    converged solver must land on the solution of the two-row complementarity problem.  The production scheme updates the two chains from the
+    same velocities (Jacobi across chains); the coupling is weak -- W_01 / W_00 ~ 5e-5: the base is heavy, the legs are light, which is what
+    makes the lane-Jacobi split cheap -- so 4 + 1 sweeps already sit within 5e-5 of the exact solution (measured and asserted < 1e-3)."""
+    h = 0.005
+    art = load_robot(robot)
+    m = _abi.pack_model(art)
+    sp = flat_params(dt=h, substeps=1, ground=True)
+    sp.plane_dynamic_friction = sp.plane_static_friction = 0.0
+    rng = np.random.default_rng(9)
+    nd = art.num_dofs
+    roll = 0.2
+    root = np.zeros(13)
+    root[3:7] = [np.sin(roll / 2), 0.0, 0.0, np.cos(roll / 2)]
+    root[7:10] = [0.1, 0.0, -0.6]
+    root[10:13] = rng.normal(size=3) * 0.1
+    dof = np.zeros((nd, 2))
+    dof[:, 0] = default_pose(art)
+    dof[:, 1] = rng.normal(size=nd) * 0.1
+    tau = rng.normal(size=nd) * 1.0
+    L = Lagrange(art, m, [sp.gravity[0], sp.gravity[1], sp.gravity[2]])
+    ncp = m.n_cpts
+    cp_link = [int(m.cp_link[i]) for i in range(ncp)]
+    cp_pos = torch.tensor([list(m.cp_pos[i]) for i in range(ncp)], dtype=torch.float64)
+    cp_rad = np.array([m.cp_radius[i] for i in range(ncp)], dtype=np.float64)
+    rr = _quat_to_mat(torch.tensor(root[3:7]))
+    x0 = torch.cat([torch.zeros(6, dtype=torch.float64), torch.tensor(dof[:, 0])])
+
+    def frames(x, rp):
+        com, rot = L.fk(x, rp, rr)
+        return com - torch.einsum("lij,lj->li", rot, L.com), rot
+
+    org, rot = frames(x0, torch.tensor(root[:3]))
+    gaps = np.array([float((org[cp_link[i]] + rot[cp_link[i]] @ cp_pos[i])[2]) for i in range(ncp)]) - cp_rad
+    order = np.argsort(gaps)
+    root[2] += -0.002 - gaps[order[0]]
+    gaps += -0.002 - gaps[order[0]]
+    ics = [int(i) for i in order[:2]]
+    assert gaps[ics[1]] < 0.002 and gaps[order[2]] > sp.contact_offset + 0.01 and int(m.cp_chain[ics[0]]) != int(m.cp_chain[ics[1]])
+    rp = torch.tensor(root[:3])
+    n = np.array([0.0, 0.0, 1.0])
+    rows = []
+    for ic in ics:
+        Jc = torch.func.jacfwd(lambda x, ic=ic: (lambda o, r: o[cp_link[ic]] + r[cp_link[ic]] @ cp_pos[ic])(*frames(x, rp)))(x0).numpy()
+        dR = torch.func.jacfwd(lambda x, ic=ic: frames(x, rp)[1][cp_link[ic]])(x0).numpy()
+        Rl = frames(x0, rp)[1][cp_link[ic]].numpy()
+        row = np.zeros(6 + nd)
+        for k in range(6 + nd):
+            Wk = dR[:, :, k] @ Rl.T
+            row[k] = (Jc[:, k] + np.cross([Wk[2, 1], Wk[0, 2], Wk[1, 0]], -cp_rad[ic] * n))[2]
+        rows.append(row)
+    Jn = np.array(rows)
+    xd = np.concatenate([root[7:10], root[10:13], dof[:, 1]])
+    xdd, _, M = L.accelerations(root, dof, tau)
+    Minv = np.linalg.inv(M)
+    v_free = xd + h * xdd
+    W = Jn @ Minv @ Jn.T
+    assert W[0, 1] != 0.0                                                         # the rows couple, weakly: the base is heavy, the legs are light
+    tgt = np.minimum(-gaps[ics] / h, float(sp.max_depenetration_velocity))
+    lam_p = np.linalg.solve(W, tgt - Jn @ v_free)
+    v_pos = v_free + Minv @ Jn.T @ lam_p
+    lam_v = lam_p + np.linalg.solve(W, np.minimum(tgt, 0.0) - Jn @ v_pos)
+    v_fin = v_pos + Minv @ Jn.T @ (lam_v - lam_p)
+    assert (lam_p > 0).all() and (lam_v > 0).all()                                # both contacts active in both stages: the LCP is this linear solve
+    props = _abi.default_dof_props(art, _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    r, d = root[None].copy(), dof[None].copy()
+    _, contact, info = O.simulate_ref(m, sp, props, r, d, np.zeros((1, nd)), tau[None], friction=np.zeros(1, np.float32), tol=1e-13)
+    assert info[0][0] == 2 and info[0][3] == 0
+    got = np.concatenate([r[0][7:10], r[0][10:13], d[0][:, 1]])
+    tol = 5e-7 if robot in EXACT_FRAMES else 5e-6
+    assert np.abs(got - v_fin).max() < tol * max(1.0, np.abs(v_fin).max()), np.abs(got - v_fin).max()
+    for k, ic in enumerate(ics):
+        assert abs(contact[0][int(m.cp_body[ic])][2] - lam_v[k] / h) < tol * max(1.0, lam_v[k] / h)
+    # production scheme, 4 + 1 sweeps
+    r2, d2 = root[None].copy(), dof[None].copy()
+    _, contact2 = O.simulate(m, sp, props, r2, d2, np.zeros((1, nd)), tau[None], friction=np.zeros(1, np.float32))
+    got2 = np.concatenate([r2[0][7:10], r2[0][10:13], d2[0][:, 1]])
+    dev = np.abs(got2 - v_fin).max() / max(1.0, np.abs(v_fin).max())
+    fdev = max(abs(contact2[0][int(m.cp_body[ic])][2] - lam_v[k] / h) / (lam_v[k] / h) for k, ic in enumerate(ics))
+    print(f"{robot}: production 4+1 sweeps vs the two-contact solution: velocity {dev:.2e}, force {fdev:.2e}")
+    assert dev < 1e-3 and fdev < 1e-3
