@@ -23,7 +23,12 @@
  *     split named by `num_position_iterations` / `num_velocity_iterations`);
  *   - semi-implicit Euler integration per sub-step.
  * It is self-validated by invariants in tests/ (ABA == CRBA/RNEA solve, kinetic energy against an
- * independent finite-difference FK, momentum and energy conservation), not by PhysX output.
+ * independent finite-difference FK, momentum and energy conservation), not by PhysX output, and pinned
+ * against rigid-body mechanics derived independently of this file: the Euler-Lagrange equations of the
+ * same robots by automatic differentiation of a kinematics-only Lagrangian (accelerations, mass matrix,
+ * implicit-drive step, RK4 horizon: tests/test_oracle_lagrange.py) and the operational-space solution
+ * W = J M^-1 J^T of one- and two-contact cases on the plane and on a sloped heightfield
+ * (tests/test_oracle_contact_impulse.py).  What PhysX adds to mechanics stays unpinned.
  *
  * This header is a template: include it with ORC_REAL and ORC_SUF defined.
  */
