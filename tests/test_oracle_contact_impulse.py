@@ -266,3 +266,46 @@ def test_two_frictionless_contacts_couple_through_the_base(robot):
     fdev = max(abs(contact2[0][int(m.cp_body[ic])][2] - lam_v[k] / h) / (lam_v[k] / h) for k, ic in enumerate(ics))
     print(f"{robot}: production 4+1 sweeps vs the two-contact solution: velocity {dev:.2e}, force {fdev:.2e}")
     assert dev < 1e-3 and fdev < 1e-3
+
+
+def _coulomb_sliding(W, vc, tgt_n, mu):
+    """Impulse lam = (t1, t2, n) with  v+ = vc + W lam,  v+_n = tgt_n,  lam_t = -mu lam_n v+_t / |v+_t|  (maximum dissipation), by Newton
+    iteration on the three equations (scipy)."""
+    from scipy.optimize import fsolve
+
+    def res(lam):
+        v = vc + W @ lam
+        vt = v[:2]
+        s = np.linalg.norm(vt)
+        return np.array([lam[0] + mu * lam[2] * vt[0] / s, lam[1] + mu * lam[2] * vt[1] / s, v[2] - tgt_n])
+
+    ln0 = (tgt_n - vc[2]) / W[2, 2]
+    lam0 = np.array([-mu * ln0 * vc[0] / np.linalg.norm(vc[:2]), -mu * ln0 * vc[1] / np.linalg.norm(vc[:2]), ln0])
+    lam, _, ok, msg = fsolve(res, lam0, xtol=1e-14, full_output=True)
+    assert ok == 1, msg
+    return lam
+
+
+@pytest.mark.parametrize("robot", ["hound", "anymal"])
+def test_sliding_contact_obeys_coulomb_with_maximum_dissipation(robot):
+    """Friction 0.3, a fast sideways drift: the contact slides, and the converged solver's impulse must be the root of Coulomb's law in
+    operational space -- normal velocity on target, friction of magnitude mu lambda_n opposite to the POST-impulse tangential velocity -- in
+    both stages."""
+    h, mu = 0.005, 0.3
+    c = _one_foot_case(robot, -0.002, [0.9, -0.6, -0.8], seed=6, h=h, spin=0.03)
+    sp, J, Minv, v_free, tgt = c["sp"], c["J"], c["Minv"], c["v_free"], c["tgt"]
+    sp.plane_dynamic_friction = sp.plane_static_friction = mu
+    W = J @ Minv @ J.T
+    lam_p = _coulomb_sliding(W, J @ v_free, tgt, mu)
+    v_pos = v_free + Minv @ J.T @ lam_p
+    lam_v = _coulomb_sliding(W, J @ v_pos - W @ lam_p, min(tgt, 0.0), mu)      # total impulse of the velocity stage, started from lam_p
+    v_fin = v_pos + Minv @ J.T @ (lam_v - lam_p)
+    for lam, v in ((lam_p, v_pos), (lam_v, v_fin)):
+        vt = (J @ v)[:2]
+        assert lam[2] > 0 and np.linalg.norm(vt) > 0.2                            # sliding, in contact
+        assert abs(np.hypot(lam[0], lam[1]) - mu * lam[2]) < 1e-10 and lam[:2] @ vt < 0
+    props = _abi.default_dof_props(c["art"], _abi.DOF_MODE_EFFORT, 0.0, 0.0)
+    r, d = c["root"][None].copy(), c["dof"][None].copy()
+    _, contact, info = O.simulate_ref(c["m"], sp, props, r, d, np.zeros((1, c["nd"])), c["tau"][None], friction=np.full(1, mu, np.float32), tol=1e-13)
+    assert info[0][0] == 1 and info[0][3] == 0
+    _compare(c, r, d, contact, v_pos, v_fin, lam_v, h, 2e-6 if robot in EXACT_FRAMES else 1e-5)
